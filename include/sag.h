@@ -1,0 +1,158 @@
+/*
+ * sag.h -- C ABI of libsag.so: the B200-native (sm_100a) inference hot path of spatialaudiogen.
+ *
+ * The reference (pedro-morgado/spatialaudiogen) is pure Python + TensorFlow 1.4 and has no FFI of its
+ * own; the boundary it exposes for this path is `sess.run(ambi_pred_t, feed_dict)` (deploy.py:141,
+ * eval.py:145) over the graph built by model.py:SptAudioGen.inference_ops (model.py:356-434) with
+ * variables restored by name (deploy.py:79-87).  Each entry point below cites the reference interface it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative SAG_E* code; sag_last_error() (thread local)
+ *    holds the message.  No aborts, no exit().
+ *  - all tensor pointers are DEVICE pointers to fp32 unless a parameter is called `host_*`;
+ *    layouts are the reference's (NHWC activations, HWIO conv weights, [kh,kw,Cout,Cin] transposed-conv
+ *    weights, [in,out] FC weights; complex64 as interleaved float pairs).
+ *  - the caller owns inputs, outputs and the workspace; the handle owns packed weights and descriptors.
+ *    No allocation happens inside sag_forward.
+ *  - `stream` is a cudaStream_t passed as void*; all launches go to it, nothing synchronises.
+ *  - a handle is not thread safe: one handle per (device, stream).
+ */
+#ifndef SAG_H_
+#define SAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAG_OK 0
+#define SAG_EINVAL (-1)   /* bad argument / shape */
+#define SAG_ECUDA (-2)    /* CUDA runtime or driver error */
+#define SAG_ENOMEM (-3)   /* workspace too small */
+#define SAG_ESTATE (-4)   /* missing weight / wrong call order */
+#define SAG_EUNSUPPORTED (-5)
+
+/* arithmetic type of the dense contractions (convs / transposed convs / FCs) */
+#define SAG_PREC_FP32 0   /* FFMA, fp32 in / fp32 accumulate (parity path) */
+#define SAG_PREC_TF32 1   /* tcgen05 kind::tf32, fp32 storage, fp32 accumulate in TMEM */
+#define SAG_PREC_BF16 2   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+#define SAG_PREC_BF16X3 3 /* tcgen05 kind::f16, operands split hi+lo (3 MMAs per K step): fp32-grade result */
+
+#define SAG_SEP_NONE 0      /* definitions.py NO_SEPARATION */
+#define SAG_SEP_UNET_MASK 1 /* definitions.py FREQ_MASK */
+
+typedef struct sag_handle sag_handle;
+
+/* Mirrors the constructor arguments of model.py:SptAudioGen.__init__ (model.py:24-32) and
+ * SptAudioGenParams (model.py:10-21). */
+typedef struct sag_config {
+  int32_t ambi_order;       /* 1 */
+  int32_t audio_rate;       /* 48000 */
+  int32_t video_rate;       /* 10 */
+  double context;           /* 1.0 s  (python floats are doubles: the integer crops of model.py:166-172 depend on it) */
+  double sample_duration;   /* 0.1 s */
+  int32_t enc_audio;        /* encoders list membership (definitions.py:1-4) */
+  int32_t enc_video;
+  int32_t enc_flow;
+  int32_t separation;       /* SAG_SEP_* */
+  int32_t sep_num_tracks;   /* 32 */
+  int32_t n_loc_fc;         /* len(loc_fc_units), <= 4 */
+  int32_t loc_fc_units[4];  /* [512,512] */
+  double sep_fft_window;    /* 0.025 s -> wind_size 1024 (model.py:59-60) */
+  int32_t precision;        /* SAG_PREC_* */
+  int32_t frame_h, frame_w; /* 224, 448 */
+} sag_config;
+
+/* Derived constants of model.py:36-60 (snd_contx, snd_dur, snd_size, wind_size, num_ambi_channels) and the
+ * integer crops of model.py:166-172, 313-323, 344-347 -- the "bit-exact frame indexing" contract. */
+typedef struct sag_dims {
+  int32_t snd_contx, snd_dur, snd_size, wind_size, num_ambi_channels;
+  int32_t n_stft_frames;            /* 200 */
+  int32_t enc_ss, enc_tt;           /* 46, 173 */
+  int32_t mask_ss, mask_tt, mask_skip; /* 89, 117, 46 */
+  int32_t final_crop;               /* 448 */
+  int32_t feat_dim;                 /* 1024 | 1536 | 2048 */
+} sag_dims;
+
+const char* sag_last_error(void);
+const char* sag_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int sag_config_default(sag_config* cfg);
+int sag_create(sag_handle** out, const sag_config* cfg);         /* model.py:24-60 + deploy.py:42-77 */
+int sag_destroy(sag_handle* h);
+int sag_get_dims(const sag_handle* h, sag_dims* out);
+
+/* ---- weights: tf.train.Saver().restore by variable name (deploy.py:79-87, eval.py:98-118) -------- */
+/* `host_data` is fp32 in the TF layout of the variable `tf_name`. */
+int sag_load_weight(sag_handle* h, const char* tf_name, const float* host_data, const int64_t* shape, int rank);
+int sag_num_weights_expected(const sag_handle* h);
+int sag_weight_name(const sag_handle* h, int i, char* buf, int buflen, int64_t* shape4, int* rank);
+int sag_finalize_weights(sag_handle* h, void* stream);   /* repack into kernel layouts; idempotent */
+
+/* ---- the forward: sess.run(ambi_pred_t, feed_dict) (deploy.py:141, eval.py:145) ------------------ */
+size_t sag_workspace_bytes(const sag_handle* h, int batch);
+/* audio (B,snd_size,1); video / flow (B,1,H,W,3) or NULL when the encoder is absent;
+ * ambix_out (B,snd_dur,3) = channels (Y,Z,X) (model.py:424-432). */
+int sag_forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* ambix_out,
+                void* workspace, size_t workspace_bytes, int batch, void* stream);
+/* Intermediate tensors of the last sag_forward (model.py `self.ends`, `sep_channels`, `loc_channels`).
+ * The pointer aliases the workspace and is valid until the next forward.  shape has up to 5 entries. */
+int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr, int64_t* shape5, int* rank,
+                   int64_t* row_stride /* elements between consecutive indices of the second-to-last axis */);
+int sag_num_tensors(const sag_handle* h);
+int sag_tensor_name(const sag_handle* h, int i, char* buf, int buflen);
+/* options: "skip_unused" (default 1: STFT frames / mask rows that cannot reach the cropped output are not
+ * computed; the result is bit-identical), "precision" (SAG_PREC_*). */
+int sag_set_option(sag_handle* h, const char* key, int value);
+/* how many kernels the last sag_forward launched (bench.py gpu_launches) */
+int sag_last_launch_count(const sag_handle* h);
+
+/* ---- stage entry points (tests / ncu); each replaces the named reference op -------------------- */
+/* myutils.stft (myutils.py:119-147): x (rows,n_samples) -> out complex (rows, n_frames_out, wind) for frames
+ * [frame0, frame0+n_frames_out) of the n_overlap*n_winds total; mag_out (optional) gets |.| for frames
+ * [mag0, mag0+n_mag).  wind must be a product of 2,3,4,5 radices and <= 4800. */
+int sag_stft(const float* x, int rows, int n_samples, int wind, int n_overlap, int frame0, int n_frames_out,
+             float* cplx_out, int mag0, int n_mag, float* mag_out, void* stream);
+/* myutils.istft (myutils.py:181-211): in complex (rows,n_frames,wind) -> out (rows, (n_frames/n_overlap)*wind - (n_overlap-1)*wind/n_overlap) */
+int sag_istft(const float* cplx_in, int rows, int n_frames, int wind, int n_overlap, float* out, void* stream);
+/* tfw.conv_2d (core.py:156-220): x NHWC, w HWIO, padding 0=VALID 1=SAME(TF asymmetric), optional bias, relu */
+int sag_conv2d(const float* x, int n, int h, int w, int cin, const float* w_hwio, int kh, int kw, int cout,
+               int sh, int sw, int same_pad, const float* bias, int relu, float* y, int precision, void* stream);
+/* tfw.deconv_2d VALID (core.py:96-153): w [kh,kw,Cout,Cin]; y (n,(h-1)*sh+kh,(w-1)*sw+kw,cout) */
+int sag_deconv2d(const float* x, int n, int h, int w, int cin, const float* w_hwoi, int kh, int kw, int cout,
+                 int sh, int sw, const float* bias, int relu, float* y, int precision, void* stream);
+/* tfw.fully_connected (core.py:43-93): x (rows,in) @ w[in,out] + b, optional relu */
+int sag_fc(const float* x, int rows, int in, const float* w, int out, const float* bias, int relu, float* y,
+           int precision, void* stream);
+/* contrib batch_norm(is_training=True) forward (core.py:209-210) + optional residual add + optional relu:
+ * y = act(gamma*(x-mu_B)/sqrt(var_B+1e-3)+beta [+ residual]), statistics over (n,h,w). scratch >= 4*c doubles. */
+int sag_batchnorm_train(const float* x, int64_t rows, int c, const float* gamma, const float* beta,
+                        const float* residual, int relu, float* y, void* scratch, void* stream);
+/* tf.nn.max_pool 3x3/2 SAME (resnet.py:135) */
+int sag_maxpool_3x3s2_same(const float* x, int n, int h, int w, int c, float* y, void* stream);
+/* ResNet18.inference_ops(truncate_at='conv5_2') with batch-statistics BN (resnet.py:123-190; model.py:189-201).
+ * scope is 'video_encoder' or 'flow_encoder'; x (B,H,W,3) -> y (B,H/32,W/32,512). Uses the handle's weights. */
+int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, float* y, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* decode step of inference_ops (model.py:424-432): x_sep (B,K,T), loc (B,S,3*(K+1)) -> out (B,T,3) */
+int sag_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out, void* stream);
+
+/* ---- evaluation metrics (model.py:110-154, myutils.py:109-116, eval.py:147-198) ----------------- */
+/* pred, gt (B,T,3).  Outputs (B,3) each: stft_ps, lsd_ps, mse_ps, snr_ps, env_ps; amp (B,2) = max|pred|, max|gt|.
+ * scratch: sag_metrics_scratch_bytes(B,T). */
+size_t sag_metrics_scratch_bytes(int batch, int t);
+int sag_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
+                float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, void* stream);
+/* AmbiDecoder.decode + RMS map (decoder.py:24-28, distance.py:41-52): ambi (B,T,4) [W,Y,Z,X] (already masked),
+ * mesh of `ang_res` degrees -> rms (B, n_nu, n_phi), rows flipped like np.flipud. */
+int sag_sh_rms_dims(float ang_res, int* n_nu, int* n_phi);
+int sag_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAG_H_ */

@@ -1,0 +1,131 @@
+// Shared host/device helpers for libsag.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/sag.h"
+
+namespace sag {
+
+void set_error(const char* fmt, ...);
+extern thread_local int g_launch_count;   // kernels launched by this thread since last reset
+
+#define SAG_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      sag::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e),    \
+                     cudaGetErrorString(_e));                                                  \
+      return SAG_ECUDA;                                                                        \
+    }                                                                                          \
+  } while (0)
+
+#define SAG_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      sag::set_error(__VA_ARGS__);    \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define SAG_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != SAG_OK) return _r; \
+  } while (0)
+
+#define SAG_LAUNCH_CHECK()                       \
+  do {                                           \
+    sag::g_launch_count++;                       \
+    SAG_CHECK_CUDA(cudaGetLastError());          \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// Gather-GEMM geometry shared by conv / transposed-conv phases / FC.
+//   rows   m = ((n*PH + i)*PW + j)                        output positions of this launch
+//   out pixel (oy0 + i*osy, ox0 + j*osx); address y + n*y_sn + oy*y_sh + ox*y_sw + co*y_sc
+//   tap t reads input pixel (i*isy + dy[t], j*isx + dx[t]) (zero outside [0,H)x[0,W)), channels ci,
+//   weight slab w + widx[t]*Cin*Cout laid out [Cin][Cout]
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 112;
+
+struct GatherGeom {
+  int N, H, W, Cin;       // input tensor
+  int64_t x_ld;           // input pixel stride (elements); input channel offset folded into pointer
+  int PH, PW;             // iteration grid
+  int isy, isx;           // input step per grid step
+  int oy0, ox0, osy, osx; // output placement
+  int64_t y_sn, y_sh, y_sw, y_sc;  // output strides (elements)
+  int Cout;
+  int T;                  // taps
+  short dy[kMaxTaps], dx[kMaxTaps], widx[kMaxTaps];
+};
+
+struct Epilogue {
+  const float* bias;      // [Cout] or null
+  int relu;
+  double* stat_sum;       // [Cout] accumulators for batch-norm statistics or null
+  double* stat_sqs;
+};
+
+// TF 'SAME' padding (asymmetric): returns pad_before; out = ceil(in/s)
+static inline int same_pad_before(int in, int k, int s, int* out) {
+  int o = (in + s - 1) / s;
+  int total = (o - 1) * s + k - in;
+  if (total < 0) total = 0;
+  *out = o;
+  return total / 2;
+}
+
+// FFMA gather-GEMM (conv_ffma.cu)
+int launch_gather_gemm_ffma(const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
+                            cudaStream_t st);
+
+// helpers building geometries (geom.cu)
+int make_conv_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh, int sw,
+                   int same_pad, int64_t y_ld, int* oh, int* ow);
+// transposed conv (VALID) phase (py,px) restricted to output rows [row0,row1) ; output strides for a tensor whose
+// row 0 is full-output row `row0`.  Returns 1 if the phase is empty.
+int make_deconv_phase_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh,
+                           int sw, int py, int px, int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw,
+                           int64_t y_sc);
+
+// pointwise.cu
+int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
+                       int c, float eps, float* scale, float* shift, cudaStream_t st);
+int launch_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, int relu,
+                    float* y, int64_t rows, int c, cudaStream_t st);
+int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
+                           float* y, cudaStream_t st);   // 3x3/2 SAME; scale==null -> plain max-pool
+int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st);
+int launch_tile_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int groups, int reps, int c,
+                     cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
+int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
+               cudaStream_t st);
+int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st);
+int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st);
+
+// fft.cu
+int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int n_frames_total, int frame0,
+                int n_frames_out, float* cplx_out, int mag0, int n_mag, float* mag_out, cudaStream_t st);
+// masked inverse STFT with overlap-add: S (rows_s, n_frames, wind) complex; mask (rows_s*tracks, n_frames, wind) real
+// logits (sigmoid applied inside when apply_sigmoid) or null (mask == 1, tracks == 1);
+// out[(row*tracks+k), j] for j in [crop0, crop0+n_out) of the reference istft output.
+int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_s, int tracks, int n_frames, int wind,
+                 int n_overlap, int crop0, int n_out, float* out, cudaStream_t st);
+
+// metrics.cu
+int launch_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
+                   float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, cudaStream_t st);
+int launch_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, cudaStream_t st);
+
+}  // namespace sag

@@ -1,0 +1,185 @@
+// Framed STFT / masked inverse STFT with overlap-add, as fused shared-memory Stockham FFT kernels.
+//
+//   launch_stft : myutils.stft (reference myutils.py:119-147)  frame t = samples [hop*t, hop*t+wind) x periodic Hann,
+//                 unnormalised two-sided forward FFT (tf.fft), plus tf.abs (model.py:178) for the encoder frames.
+//   launch_istft: sigmoid mask x STFT (model.py:334-337) -> real(tf.ifft) -> de-interleave/trim/sum/n_overlap
+//                 (myutils.py:181-211) -> crop (model.py:344-347), one CTA per (window, track).
+//
+// Both are HBM-bound: the whole transform lives in shared memory, the audio stream / mask is read once with
+// coalesced accesses, results are written once.  Twiddles and the Hann window are fp32 tables rounded from
+// float64 exactly as the reference builds them (np.cos in float64 -> tf.constant(float32)).
+#include "common.cuh"
+#include "fft_device.cuh"
+#include <mutex>
+#include <cmath>
+
+namespace sag {
+
+static std::mutex g_plan_mu;
+static std::map<std::pair<int, int>, FftPlan> g_plans;   // (device, n) -> plan
+
+int get_plan(int n, FftPlan* out) {
+  int dev = 0;
+  SAG_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto it = g_plans.find({dev, n});
+  if (it != g_plans.end()) { *out = it->second; return SAG_OK; }
+  FftPlan p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  int m = n;
+  while (m % 4 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 4; m /= 4; }
+  while (m % 2 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 2; m /= 2; }
+  while (m % 3 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 3; m /= 3; }
+  while (m % 5 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 5; m /= 5; }
+  SAG_REQUIRE(m == 1, SAG_EUNSUPPORTED, "fft: length %d is not a product of 2,3,5 (or too many passes)", n);
+  SAG_REQUIRE(n <= 8192, SAG_EUNSUPPORTED, "fft: length %d too large for the shared-memory transform", n);
+  std::vector<float2> tw(n);
+  std::vector<float> hw(n);
+  for (int i = 0; i < n; ++i) {
+    double a = -2.0 * M_PI * (double)i / (double)n;
+    tw[i] = make_float2((float)cos(a), (float)sin(a));
+    hw[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI / (double)n * (double)i));   // myutils.py:134
+  }
+  float2* dtw = nullptr;
+  float* dh = nullptr;
+  SAG_CHECK_CUDA(cudaMalloc(&dtw, sizeof(float2) * n));
+  SAG_CHECK_CUDA(cudaMalloc(&dh, sizeof(float) * n));
+  SAG_CHECK_CUDA(cudaMemcpy(dtw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+  SAG_CHECK_CUDA(cudaMemcpy(dh, hw.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  p.tw = dtw;
+  p.hann = dh;
+  g_plans[{dev, n}] = p;
+  *out = p;
+  return SAG_OK;
+}
+
+int fft_prepare(int n) {   // create tables ahead of time (outside stream capture)
+  FftPlan p;
+  return get_plan(n, &p);
+}
+
+// ---- K1: frame + window + FFT (+ magnitude) --------------------------------------------------------------------
+// grid (n_frames_launch, rows); frame index = fbase + blockIdx.x.
+__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, int n_samples, int hop, const FftPlan p,
+                                                   int fbase, int frame0, int n_frames_out, float2* __restrict__ cplx_out,
+                                                   int mag0, int n_mag, float* __restrict__ mag_out) {
+  extern __shared__ __align__(16) float2 smem[];
+  float2* buf0 = smem;
+  float2* buf1 = smem + p.n;
+  const int f = fbase + blockIdx.x;
+  const int row = blockIdx.y;
+  const float* xr = x + (int64_t)row * n_samples + (int64_t)f * hop;
+  for (int i = threadIdx.x; i < p.n; i += blockDim.x) buf0[i] = make_float2(__ldg(xr + i) * __ldg(p.hann + i), 0.f);
+  float2* res = block_fft(buf0, buf1, p);
+  if (cplx_out != nullptr && f >= frame0 && f < frame0 + n_frames_out) {
+    float2* o = cplx_out + ((int64_t)row * n_frames_out + (f - frame0)) * p.n;
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) o[i] = res[i];
+  }
+  if (mag_out != nullptr && f >= mag0 && f < mag0 + n_mag) {
+    float* o = mag_out + ((int64_t)row * n_mag + (f - mag0)) * p.n;
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+      float2 v = res[i];
+      o[i] = hypotf(v.x, v.y);       // tf.abs(complex64)
+    }
+  }
+}
+
+int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int n_frames_total, int frame0,
+                int n_frames_out, float* cplx_out, int mag0, int n_mag, float* mag_out, cudaStream_t st) {
+  SAG_REQUIRE(rows > 0 && wind > 0 && hop > 0, SAG_EINVAL, "stft: bad arguments");
+  SAG_REQUIRE((int64_t)(n_frames_total - 1) * hop + wind <= n_samples, SAG_EINVAL,
+              "stft: %d frames of %d (hop %d) exceed %d samples", n_frames_total, wind, hop, n_samples);
+  int lo = n_frames_total, hi = 0;
+  if (cplx_out != nullptr && n_frames_out > 0) { lo = std::min(lo, frame0); hi = std::max(hi, frame0 + n_frames_out); }
+  if (mag_out != nullptr && n_mag > 0) { lo = std::min(lo, mag0); hi = std::max(hi, mag0 + n_mag); }
+  if (hi <= lo) return SAG_OK;
+  SAG_REQUIRE(lo >= 0 && hi <= n_frames_total, SAG_EINVAL, "stft: frame range [%d,%d) outside [0,%d)", lo, hi, n_frames_total);
+  FftPlan p;
+  SAG_TRY(get_plan(wind, &p));
+  size_t smem = 2 * sizeof(float2) * wind;
+  if (smem > 48 * 1024) SAG_CHECK_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(hi - lo, rows);
+  stft_kernel<<<grid, 256, smem, st>>>(x, n_samples, hop, p, lo, frame0, n_frames_out, reinterpret_cast<float2*>(cplx_out),
+                                      mag0, n_mag, mag_out);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- K6a: (sigmoid mask x STFT) -> real inverse FFT -> overlap-add / n_overlap -> crop ----------------------------
+// grid (rows_s*tracks). Frame-space position of output sample j is j + (n_overlap-1)*hop (myutils.py:198-205).
+__global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ S, const float* __restrict__ mask,
+                                                    int apply_sigmoid, int tracks, int n_frames, const FftPlan p,
+                                                    int hop, int f_lo, int f_hi, int p0, int n_out, float inv_scale,
+                                                    float* __restrict__ out) {
+  extern __shared__ __align__(16) float2 smem[];
+  float2* buf0 = smem;
+  float2* buf1 = smem + p.n;
+  float* ola = reinterpret_cast<float*>(smem + 2 * p.n);
+  const int64_t rk = blockIdx.x;
+  const int64_t row = rk / tracks;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) ola[i] = 0.f;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const float2* s = S + (row * n_frames + f) * p.n;
+    const float* m = mask != nullptr ? mask + (rk * n_frames + f) * p.n : nullptr;
+    __syncthreads();     // previous frame's result fully consumed before buf0 is overwritten
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+      float2 v = __ldg(s + i);
+      if (m != nullptr) {
+        float g = __ldg(m + i);
+        if (apply_sigmoid) g = 1.f / (1.f + expf(-g));
+        v.x *= g; v.y *= g;
+      }
+      buf0[i] = make_float2(v.x, -v.y);     // conj: ifft(z) = conj(fft(conj z))/n ; only the real part is kept
+    }
+    float2* res = block_fft(buf0, buf1, p);
+    const int base = f * hop - p0;           // output index of sample 0 of this frame
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+      int j = base + i;
+      if (j >= 0 && j < n_out) ola[j] += res[i].x;    // frames are processed sequentially: no race
+    }
+  }
+  __syncthreads();
+  float* o = out + rk * n_out;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) o[i] = ola[i] * inv_scale;
+}
+
+int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_s, int tracks, int n_frames, int wind,
+                 int n_overlap, int crop0, int n_out, float* out, cudaStream_t st) {
+  SAG_REQUIRE(rows_s > 0 && tracks > 0 && n_overlap > 0 && wind % n_overlap == 0, SAG_EINVAL, "istft: bad arguments");
+  const int hop = wind / n_overlap;
+  const int nf = (n_frames / n_overlap) * n_overlap;      // myutils.py:187-188
+  const int full = (nf / n_overlap) * wind - (n_overlap - 1) * hop;
+  SAG_REQUIRE(nf > 0 && crop0 >= 0 && n_out > 0 && crop0 + n_out <= full, SAG_EINVAL,
+              "istft: crop [%d,%d) outside the %d output samples", crop0, crop0 + n_out, full);
+  FftPlan p;
+  SAG_TRY(get_plan(wind, &p));
+  const int p0 = crop0 + (n_overlap - 1) * hop, p1 = p0 + n_out;
+  int f_lo = (p0 - wind + 1 + hop - 1) / hop;
+  if (p0 - wind + 1 <= 0) f_lo = 0;
+  int f_hi = (p1 - 1) / hop;
+  if (f_hi > nf - 1) f_hi = nf - 1;
+  size_t smem = 2 * sizeof(float2) * wind + sizeof(float) * n_out;
+  SAG_REQUIRE(smem <= 200 * 1024, SAG_EUNSUPPORTED, "istft: %zu bytes of shared memory needed", smem);
+  if (smem > 48 * 1024) SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const float inv_scale = 1.0f / ((float)wind * (float)n_overlap);
+  istft_kernel<<<rows_s * tracks, 256, smem, st>>>(reinterpret_cast<const float2*>(S), mask, apply_sigmoid, tracks,
+                                                  n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, out);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// frames [f_lo, f_hi] of the inverse STFT that reach output samples [crop0, crop0+n_out)
+void istft_needed_frames(int n_frames, int wind, int n_overlap, int crop0, int n_out, int* f_lo, int* f_hi) {
+  const int hop = wind / n_overlap;
+  const int nf = (n_frames / n_overlap) * n_overlap;
+  const int p0 = crop0 + (n_overlap - 1) * hop, p1 = p0 + n_out;
+  int lo = (p0 - wind + 1 + hop - 1) / hop;
+  if (p0 - wind + 1 <= 0) lo = 0;
+  int hi = (p1 - 1) / hop;
+  if (hi > nf - 1) hi = nf - 1;
+  *f_lo = lo;
+  *f_hi = hi;
+}
+
+}  // namespace sag

@@ -1,0 +1,301 @@
+// Evaluation metrics of the reference as GPU kernels.
+//   metrics_kernel : evaluation_ops per-sample outputs (reference model.py:110-154): STFT distance
+//                    (_stft_mse_ops :62-76 + myutils.stft_for_loss myutils.py:151-178), LSD (_lsd_ops :78-94 +
+//                    myutils.stft with window 1200, overlap 2), temporal MSE (:96-99), SNR (:101-108); the Hilbert
+//                    envelope distance of myutils.compute_envelope_dist (myutils.py:109-116) and the amplitudes of
+//                    eval.py:197-198.  One CTA per (window, channel); all FFTs run in shared memory.
+//   sh_rms_kernel  : AmbiDecoder.decode 'projection' (decoder.py:24-26) on the spherical mesh of distance.py:9-13
+//                    followed by the RMS map of distance.py:48-51, as a warp-shuffle reduction over time.
+// HBM-bound (each input sample is read once); algorithmic bytes = 2*T*3*4 per window for the metrics,
+// T*4*4 per window for the RMS map.
+#include "common.cuh"
+#include "fft_device.cuh"
+#include <mutex>
+#include <cmath>
+
+namespace sag {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// sum over the block; result valid in every thread. red: >= 32 floats of shared memory.
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+  if (wid == 0) {
+    t = warp_max(t);
+    if (lane == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+struct MetricPlans {
+  FftPlan stft;   // 2048 (ceil-pow2 of int(0.025*rate), myutils.py:155)
+  FftPlan lsd;    // 1200 (int(0.025*rate), model.py:123)
+  FftPlan env;    // T (scipy.signal.hilbert over the whole 0.1 s window)
+};
+
+// windowed FFT of sig[off, off+n) into a result buffer; returns pointer to result
+__device__ float2* windowed_fft(const float* sig, int off, const FftPlan& p, float2* b0, float2* b1) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.n; i += blockDim.x) b0[i] = make_float2(sig[off + i] * __ldg(p.hann + i), 0.f);
+  return block_fft(b0, b1, p);
+}
+
+__global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int t,
+                                                      const MetricPlans P, float* __restrict__ stft_ps,
+                                                      float* __restrict__ lsd_ps, float* __restrict__ mse_ps,
+                                                      float* __restrict__ snr_ps, float* __restrict__ env_ps,
+                                                      float* __restrict__ amp) {
+  extern __shared__ __align__(16) float2 smem[];
+  const int nmax = max(max(P.stft.n, P.lsd.n), P.env.n);
+  float2* b0 = smem;
+  float2* b1 = smem + nmax;
+  float2* keep = smem + 2 * nmax;                       // spectrum / envelope of gt kept while pred is transformed
+  float* sg = reinterpret_cast<float*>(smem + 3 * nmax);  // gt signal [t]
+  float* sp = sg + t;                                   // pred signal [t]
+  __shared__ float red[32];
+
+  const int b = blockIdx.x / 3, ch = blockIdx.x % 3;
+  const float* pg = gt + (int64_t)b * t * 3 + ch;
+  const float* pp = pred + (int64_t)b * t * 3 + ch;
+  float se = 0.f, sgg = 0.f, mp = 0.f, mg = 0.f;
+  for (int i = threadIdx.x; i < t; i += blockDim.x) {
+    float g = __ldg(pg + (int64_t)i * 3), p = __ldg(pp + (int64_t)i * 3);
+    sg[i] = g;
+    sp[i] = p;
+    float d = g - p;
+    se = fmaf(d, d, se);
+    sgg = fmaf(g, g, sgg);
+    mp = fmaxf(mp, fabsf(p));
+    mg = fmaxf(mg, fabsf(g));
+  }
+  se = block_sum(se, red);
+  sgg = block_sum(sgg, red);
+  mp = block_max(mp, red);
+  mg = block_max(mg, red);
+  if (threadIdx.x == 0) {
+    mse_ps[blockIdx.x] = se / (float)t;                                         // model.py:99
+    snr_ps[blockIdx.x] = 10.f * logf((sgg + 0.1f) / (se + 0.1f)) / logf(10.f);  // model.py:105-107
+    atomicMax(reinterpret_cast<int*>(amp + b * 2 + 0), __float_as_int(mp));      // eval.py:197-198 (values >= 0)
+    atomicMax(reinterpret_cast<int*>(amp + b * 2 + 1), __float_as_int(mg));
+  }
+
+  // ---- STFT distance: windows of n=2048 at stride n/2 grouped as myutils.py:167-173 builds them ----
+  {
+    const int n = P.stft.n, stride = n / 2;
+    float acc_total = 0.f;
+    int nwin_total = 0;
+    for (int i = 0; i < 2; ++i) {
+      int nW = (t - i * stride - 1) / n;
+      for (int wdx = 0; wdx < nW; ++wdx) {
+        int off = i * stride + wdx * n;
+        float2* r = windowed_fft(sg, off, P.stft, b0, b1);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) keep[k] = r[k];
+        r = windowed_fft(sp, off, P.stft, b0, b1);
+        float a = 0.f;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+          float dx = keep[k].x - r[k].x, dy = keep[k].y - r[k].y;
+          a += dx * dx + dy * dy;                                                // |stft_gt - stft_pred|^2
+        }
+        acc_total += block_sum(a, red) / (float)n;                               // mean over freq
+        ++nwin_total;
+      }
+    }
+    if (threadIdx.x == 0) stft_ps[blockIdx.x] = nwin_total > 0 ? acc_total / (float)nwin_total : 0.f;
+  }
+
+  // ---- LSD: myutils.stft(x, 1200, 2): n_winds = t/1200 - 1, frames at hop 600 ----
+  {
+    const int n = P.lsd.n, hop = n / 2;
+    const int nframes = 2 * (t / n - 1);
+    float acc_total = 0.f;
+    const float k10 = 10.f / logf(10.f);
+    for (int f = 0; f < nframes; ++f) {
+      float2* r = windowed_fft(sg, f * hop, P.lsd, b0, b1);
+      for (int k = threadIdx.x; k < n; k += blockDim.x) keep[k].x = k10 * logf(hypotf(r[k].x, r[k].y) + 1e-2f);
+      r = windowed_fft(sp, f * hop, P.lsd, b0, b1);
+      float a = 0.f;
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        float d = keep[k].x - k10 * logf(hypotf(r[k].x, r[k].y) + 1e-2f);
+        a = fmaf(d, d, a);
+      }
+      acc_total += sqrtf(block_sum(a, red) / (float)n);
+    }
+    if (threadIdx.x == 0) lsd_ps[blockIdx.x] = nframes > 0 ? acc_total / (float)nframes : 0.f;
+  }
+
+  // ---- Hilbert envelope distance: analytic signal via FFT (scipy.signal.hilbert), N = t ----
+  if (env_ps != nullptr) {
+    const int n = P.env.n;
+    const float inv_n = 1.f / (float)n;
+    for (int pass = 0; pass < 2; ++pass) {
+      const float* sig = pass == 0 ? sg : sp;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) b0[i] = make_float2(sig[i], 0.f);
+      float2* r = block_fft(b0, b1, P.env);
+      float2* o = (r == b0) ? b1 : b0;
+      // h[0]=1, h[1..n/2-1]=2, h[n/2]=1 (n even), rest 0 ; then inverse FFT via conj trick
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        float h;
+        if ((n & 1) == 0) h = (k == 0 || k == n / 2) ? 1.f : (k < n / 2 ? 2.f : 0.f);
+        else h = (k == 0) ? 1.f : (k < (n + 1) / 2 ? 2.f : 0.f);
+        o[k] = make_float2(r[k].x * h, -r[k].y * h);
+      }
+      float2* other = (o == b0) ? b1 : b0;
+      float2* z = block_fft(o, other, P.env);           // conj(analytic)*n
+      if (pass == 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i].x = hypotf(z[i].x, z[i].y) * inv_n;
+      } else {
+        float a = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          float d = keep[i].x - hypotf(z[i].x, z[i].y) * inv_n;
+          a = fmaf(d, d, a);
+        }
+        a = block_sum(a, red);
+        if (threadIdx.x == 0) env_ps[blockIdx.x] = sqrtf(a * inv_n);
+      }
+    }
+  }
+}
+
+static size_t metrics_smem_bytes(int t, int n_stft, int n_lsd) {
+  int nmax = std::max(std::max(n_stft, n_lsd), t);
+  return (size_t)3 * nmax * sizeof(float2) + (size_t)2 * t * sizeof(float);
+}
+
+int launch_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
+                   float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, cudaStream_t st) {
+  (void)scratch;
+  SAG_REQUIRE(batch > 0 && t > 0, SAG_EINVAL, "metrics: bad arguments");
+  const int window = (int)(0.025 * (double)audio_rate);                      // definitions.py:10, model.py:123
+  int n_stft = 1;
+  while (n_stft < window) n_stft <<= 1;                                       // myutils.py:155
+  SAG_REQUIRE(t >= 2 * window && t > n_stft, SAG_EINVAL, "metrics: %d samples too short for window %d", t, window);
+  MetricPlans P;
+  SAG_TRY(get_plan(n_stft, &P.stft));
+  SAG_TRY(get_plan(window, &P.lsd));
+  SAG_TRY(get_plan(t, &P.env));
+  size_t smem = metrics_smem_bytes(t, n_stft, window);
+  SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "metrics: %zu bytes of shared memory needed", smem);
+  SAG_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SAG_CHECK_CUDA(cudaMemsetAsync(amp, 0, sizeof(float) * 2 * batch, st));
+  metrics_kernel<<<batch * 3, 256, smem, st>>>(pred, gt, t, P, stft_ps, lsd_ps, mse_ps, snr_ps, env_ps, amp);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- spherical-harmonic projection + RMS map -------------------------------------------------------------------
+struct ShMesh {
+  int n_nu, n_phi;
+  const float4* Y;    // [n_nu*n_phi] (W,Y,Z,X) coefficients, ACN/SN3D order 1
+};
+static std::mutex g_mesh_mu;
+static std::map<std::pair<int, int>, ShMesh> g_meshes;   // (device, ang_res*1000)
+
+static void mesh_dims(double ang_res, int* n_nu, int* n_phi) {
+  // np.arange(start, stop, step) has ceil((stop-start)/step) elements (distance.py:10-11)
+  *n_phi = (int)ceil((180.0 - (-180.0)) / ang_res);
+  *n_nu = (int)ceil((90.1 - (-90.0)) / ang_res);
+}
+
+static int get_mesh(float ang_res_f, ShMesh* out) {
+  int dev = 0;
+  SAG_CHECK_CUDA(cudaGetDevice(&dev));
+  SAG_REQUIRE(ang_res_f > 0.f, SAG_EINVAL, "sh_rms: angular resolution must be positive");
+  std::lock_guard<std::mutex> lk(g_mesh_mu);
+  auto key = std::make_pair(dev, (int)lround((double)ang_res_f * 1000.0));
+  auto it = g_meshes.find(key);
+  if (it != g_meshes.end()) { *out = it->second; return SAG_OK; }
+  const double res = (double)ang_res_f;
+  ShMesh m;
+  mesh_dims(res, &m.n_nu, &m.n_phi);
+  std::vector<float4> Y((size_t)m.n_nu * m.n_phi);
+  for (int iv = 0; iv < m.n_nu; ++iv)
+    for (int ip = 0; ip < m.n_phi; ++ip) {
+      // distance.py:10-11: phi = flip(arange(-180,180,res))/180*pi ; nu = arange(-90,90.1,res)/180*pi
+      double phi = (-180.0 + res * (double)(m.n_phi - 1 - ip)) / 180.0 * M_PI;
+      double nu = (-90.0 + res * (double)iv) / 180.0 * M_PI;
+      // position.py:23-37: polar -> cartesian -> polar round trip
+      double x = cos(phi) * cos(nu), y = sin(phi) * cos(nu), z = sin(nu);
+      double phi2 = atan2(y, x), nu2 = atan2(z, sqrt(x * x + y * y));
+      // common.py:151-157 at order 1, ACN/SN3D: [1, sin(phi)cos(nu), sin(nu), cos(phi)cos(nu)]
+      double cn = sqrt(fmax(0.0, 1.0 - sin(nu2) * sin(nu2)));     // -lpmv(1,1,sin nu) = sqrt(1-sin^2 nu)
+      Y[(size_t)iv * m.n_phi + ip] = make_float4(1.f, (float)(sin(phi2) * cn), (float)sin(nu2), (float)(cos(phi2) * cn));
+    }
+  float4* d = nullptr;
+  SAG_CHECK_CUDA(cudaMalloc(&d, sizeof(float4) * Y.size()));
+  SAG_CHECK_CUDA(cudaMemcpy(d, Y.data(), sizeof(float4) * Y.size(), cudaMemcpyHostToDevice));
+  m.Y = d;
+  g_meshes[key] = m;
+  *out = m;
+  return SAG_OK;
+}
+
+int sh_mesh_dims(float ang_res, int* n_nu, int* n_phi) {
+  if (!(ang_res > 0.f)) { set_error("sh_rms: angular resolution must be positive"); return SAG_EINVAL; }
+  mesh_dims((double)ang_res, n_nu, n_phi);
+  return SAG_OK;
+}
+
+// grid (ceil(D/dirs_per_block), batch); each warp owns one direction at a time and strides over time.
+__global__ void __launch_bounds__(256) sh_rms_kernel(const float4* __restrict__ ambi, int t, const ShMesh mesh,
+                                                     float* __restrict__ rms) {
+  const int b = blockIdx.y;
+  const int D = mesh.n_nu * mesh.n_phi;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float4* a = ambi + (int64_t)b * t;
+  for (int d = blockIdx.x * nw + wid; d < D; d += gridDim.x * nw) {
+    const float4 y = __ldg(mesh.Y + d);
+    float acc = 0.f;
+    for (int i = lane; i < t; i += 32) {
+      float4 v = __ldg(a + i);
+      float s = v.x * y.x + v.y * y.y + v.z * y.z + v.w * y.w;     // decoder.py:26
+      acc = fmaf(s, s, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      int iv = d / mesh.n_phi, ip = d % mesh.n_phi;
+      rms[((int64_t)b * mesh.n_nu + (mesh.n_nu - 1 - iv)) * mesh.n_phi + ip] = sqrtf(acc / (float)t);   // flipud
+    }
+  }
+}
+
+int launch_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, cudaStream_t st) {
+  SAG_REQUIRE(batch > 0 && t > 0, SAG_EINVAL, "sh_rms: bad arguments");
+  ShMesh m;
+  SAG_TRY(get_mesh(ang_res, &m));
+  const int D = m.n_nu * m.n_phi;
+  dim3 grid(std::min(cdiv(D, 8), 64), batch);
+  sh_rms_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(ambi), t, m, rms);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+}  // namespace sag

@@ -1,0 +1,472 @@
+// Handle lifetime, checkpoint-layout weight store and the forward orchestration of
+// SptAudioGen.inference_ops (reference model.py:356-434) for libsag.so.
+//
+// Data layout in HBM (all fp32, NHWC like the reference graph):
+//   mag   (B,127,1024)            |STFT| of frames 46..172       (audio_encoder input, model.py:173-178)
+//   S     (B,28,1024) complex     STFT frames 89..116             (model.py:318)
+//   catL  skip-concat buffers: the encoder writes enc_L straight into the upper channel half of the tensor the
+//         decoder's deconv_{L+1} fills the lower half of (model.py:310 concat order [relu(x), skip]); no copy.
+//   mask  (B,32,28,1024)          deconv1 rows 43..70, already transposed to (track, frame, freq) (model.py:326-330)
+//   x_sep (B,32,4800), loc (B,3,99), out (B,4800,3)
+#include "model.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace sag {
+
+static const int kAudioFilters[5] = {32, 64, 128, 256, 512};                       // model.py:162 / :283
+static const int kAudioKernel[5][2] = {{7, 16}, {3, 7}, {3, 5}, {3, 5}, {3, 5}};    // model.py:163 / :284
+static const int kAudioStride[5][2] = {{4, 8}, {2, 4}, {2, 2}, {1, 1}, {1, 1}};     // model.py:164 / :285
+
+struct BlockDef { const char* name; int cin, cout; bool first; };
+static const BlockDef kBlocks[8] = {{"conv2_1", 64, 64, false},  {"conv2_2", 64, 64, false},
+                                    {"conv3_1", 64, 128, true},  {"conv3_2", 128, 128, false},
+                                    {"conv4_1", 128, 256, true}, {"conv4_2", 256, 256, false},
+                                    {"conv5_1", 256, 512, true}, {"conv5_2", 512, 512, false}};   // resnet.py:137-186
+
+// ---- model.py:36-60 and the integer crops of :166-172, :313-317, :344-346, evaluated in double like python ----
+int derive_dims(const sag_config& c, sag_dims* d) {
+  SAG_REQUIRE(c.ambi_order >= 1 && c.audio_rate > 0 && c.video_rate > 0, SAG_EINVAL, "config: bad rates/order");
+  SAG_REQUIRE(c.audio_rate % c.video_rate == 0, SAG_EINVAL, "config: audio_rate %% video_rate != 0 (model.py:33,41)");
+  memset(d, 0, sizeof(*d));
+  int nch = 0;
+  for (int i = 0; i <= c.ambi_order; ++i) nch += 2 * i + 1;
+  d->num_ambi_channels = nch;
+  d->snd_contx = (int)(c.context * (double)c.audio_rate);
+  d->snd_dur = (int)(c.sample_duration * (double)c.audio_rate);
+  d->snd_size = d->snd_contx + d->snd_dur - 1;
+  int w0 = (int)(c.sep_fft_window * (double)c.audio_rate);
+  SAG_REQUIRE(w0 > 0, SAG_EINVAL, "config: fft window too small");
+  d->wind_size = (int)std::pow(2.0, std::nearbyint(std::log2((double)w0)));   // np.round = half-to-even
+  const double W = (double)d->wind_size, half = d->snd_contx / 2.0, inp_dim = 95.0;
+  int n_winds = d->snd_size / d->wind_size - 1;                                // myutils.py:126
+  d->n_stft_frames = 4 * n_winds;
+  double ss = half * (4.0 / W);
+  int iss = (int)(ss - (inp_dim - 1) / 2.0);
+  double tt = (half + d->snd_dur) * (4.0 / W);
+  int itt = (int)(tt + (inp_dim - 1) / 2.0);
+  itt = (int)(std::ceil((itt - iss - inp_dim) / 16.0) * 16 + inp_dim + iss);
+  d->enc_ss = iss;
+  d->enc_tt = itt;
+  d->mask_ss = (int)std::floor((half - W) * (4.0 / W));
+  d->mask_tt = (int)std::ceil((half + d->snd_dur + W) * (4.0 / W));
+  d->mask_skip = iss;
+  double skip = std::floor((half - W) * (4.0 / W)) * (W / 4.0) + 3.0 * W / 4.0;
+  d->final_crop = (int)(half - skip);
+  d->feat_dim = (c.enc_audio ? 1024 : 0) + (c.enc_video ? 512 : 0) + (c.enc_flow ? 512 : 0);
+  return SAG_OK;
+}
+
+static void add_expected(sag_handle* h, const std::string& n, std::vector<int64_t> s) { h->expected.push_back({n, s}); }
+
+// checkpoint layout (core.py:21,69,127,191,210)
+int build_expected(sag_handle* h) {
+  const sag_config& c = h->cfg;
+  h->expected.clear();
+  if (c.enc_audio) {
+    int cin = 1;
+    for (int l = 0; l < 5; ++l) {
+      std::string p = "audio_encoder/conv" + std::to_string(l + 1);
+      add_expected(h, p + "/weights", {kAudioKernel[l][0], kAudioKernel[l][1], cin, kAudioFilters[l]});
+      add_expected(h, p + "/biases", {kAudioFilters[l]});
+      cin = kAudioFilters[l];
+    }
+  }
+  for (int v = 0; v < 2; ++v) {
+    if (!(v == 0 ? c.enc_video : c.enc_flow)) continue;
+    std::string p = v == 0 ? "video_encoder/" : "flow_encoder/";
+    auto bn = [&](const std::string& q, int ch) {
+      for (const char* k : {"beta", "gamma", "moving_mean", "moving_variance"}) add_expected(h, q + "/bn/" + k, {ch});
+    };
+    add_expected(h, p + "conv1/conv/weights", {7, 7, 3, 64});
+    bn(p + "conv1/conv", 64);
+    for (const BlockDef& b : kBlocks) {
+      std::string q = p + b.name;
+      if (b.first) add_expected(h, q + "/shortcut/weights", {1, 1, b.cin, b.cout});
+      add_expected(h, q + "/conv_1/weights", {3, 3, b.cin, b.cout});
+      bn(q + "/conv_1", b.cout);
+      add_expected(h, q + "/conv_2/weights", {3, 3, b.cout, b.cout});
+      bn(q + "/conv_2", b.cout);
+    }
+  }
+  const int D = h->dims.feat_dim;
+  if (c.enc_audio) {
+    add_expected(h, "bottleneck/audio-fc/weights", {3 * 2 * 512, 1024});
+    add_expected(h, "bottleneck/audio-fc/biases", {1024});
+  }
+  for (int v = 0; v < 2; ++v) {
+    if (!(v == 0 ? c.enc_video : c.enc_flow)) continue;
+    std::string k = v == 0 ? "video" : "flow";
+    const int fh = (c.frame_h + 31) / 32, fw = (c.frame_w + 31) / 32;
+    add_expected(h, "bottleneck/" + k + "-fc-red/weights", {512, 128});
+    add_expected(h, "bottleneck/" + k + "-fc-red/biases", {128});
+    add_expected(h, "bottleneck/" + k + "-fc/weights", {(int64_t)fh * fw * 128, 512});
+    add_expected(h, "bottleneck/" + k + "-fc/biases", {512});
+  }
+  const int num_out = (c.ambi_order + 1) * (c.ambi_order + 1) - c.ambi_order * c.ambi_order;
+  const int num_in = c.ambi_order * c.ambi_order;
+  int prev = D;
+  for (int i = 0; i < c.n_loc_fc; ++i) {
+    std::string p = "localization/fc" + std::to_string(i + 1);
+    add_expected(h, p + "/weights", {prev, c.loc_fc_units[i]});
+    add_expected(h, p + "/biases", {c.loc_fc_units[i]});
+    prev = c.loc_fc_units[i];
+  }
+  {
+    std::string p = "localization/fc" + std::to_string(c.n_loc_fc + 1);
+    const int n3 = num_out * num_in * (c.sep_num_tracks + 1);
+    add_expected(h, p + "/weights", {prev, n3});
+    add_expected(h, p + "/biases", {n3});
+  }
+  if (c.separation == SAG_SEP_UNET_MASK) {
+    add_expected(h, "separation/fc-feats/weights", {D, 512});
+    add_expected(h, "separation/fc-feats/biases", {512});
+    for (int l = 4; l >= 0; --l) {
+      int cin = l == 4 ? 1024 : 2 * kAudioFilters[l];
+      int cout = l == 0 ? c.sep_num_tracks : kAudioFilters[l - 1];
+      std::string p = "separation/deconv" + std::to_string(l + 1);
+      add_expected(h, p + "/weights", {kAudioKernel[l][0], kAudioKernel[l][1], cout, cin});
+      add_expected(h, p + "/biases", {cout});
+    }
+  }
+  return SAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// layer helpers
+// ------------------------------------------------------------------------------------------------------------------
+int launch_gather_gemm(int precision, const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
+                       cudaStream_t st) {
+  switch (precision) {
+    case SAG_PREC_FP32: return launch_gather_gemm_ffma(x, w, y, g, ep, st);
+    case SAG_PREC_TF32:
+    case SAG_PREC_BF16:
+    case SAG_PREC_BF16X3: return launch_gather_gemm_umma(precision, x, w, y, g, ep, st);
+    default: set_error("unknown precision %d", precision); return SAG_EINVAL;
+  }
+}
+
+struct Fwd {
+  sag_handle* h;
+  Arena& ar;
+  cudaStream_t st;
+  int prec;
+  bool dry() const { return ar.dry; }
+
+  const float* W(const std::string& name, int* err) {
+    auto it = h->weights.find(name);
+    if (it == h->weights.end()) {
+      if (!dry()) { set_error("weight '%s' has not been loaded", name.c_str()); *err = SAG_ESTATE; }
+      return nullptr;
+    }
+    return it->second.p;
+  }
+  const float* Wp(const std::string& name, int* err) {     // packed variant (deconv: [tap][Cin][Cout])
+    auto it = h->packed.find(name);
+    if (it == h->packed.end()) {
+      if (!dry()) { set_error("weight '%s' has not been loaded/packed", name.c_str()); *err = SAG_ESTATE; }
+      return nullptr;
+    }
+    return it->second.p;
+  }
+  void tap(const std::string& name, const float* p, std::vector<int64_t> shape, int64_t ld = 0) {
+    if (dry()) return;
+    DevTensor t;
+    t.p = const_cast<float*>(p);
+    t.shape = shape;
+    t.ld = ld ? ld : shape.back();
+    h->ends[name] = t;
+    h->end_order.push_back(name);
+  }
+
+  // tfw.conv_2d (core.py:156-220) on an NHWC view: x has pixel stride x_ld, y has pixel stride y_ld.
+  int conv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
+           int cout, int sh, int sw, int same, bool bias, int relu, float* y, int64_t y_ld, double* ssum, double* ssqs,
+           int* oh, int* ow) {
+    GatherGeom g;
+    SAG_TRY(make_conv_geom(&g, n, hh, ww, cin, x_ld, kh, kw, cout, sh, sw, same, y_ld, oh, ow));
+    if (dry()) return SAG_OK;
+    int err = SAG_OK;
+    const float* w = W(scope + "/weights", &err);
+    const float* b = bias ? W(scope + "/biases", &err) : nullptr;
+    SAG_TRY(err);
+    Epilogue ep{b, relu, ssum, ssqs};
+    return launch_gather_gemm(prec, x, w, y, g, ep, st);
+  }
+
+  // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
+  int deconv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
+             int cout, int sh, int sw, int relu, float* y, int row0, int row1, int64_t y_sn, int64_t y_sh,
+             int64_t y_sw, int64_t y_sc) {
+    if (dry()) return SAG_OK;
+    int err = SAG_OK;
+    const float* w = Wp(scope + "/weights", &err);
+    const float* b = W(scope + "/biases", &err);
+    SAG_TRY(err);
+    Epilogue ep{b, relu, nullptr, nullptr};
+    for (int py = 0; py < sh; ++py)
+      for (int px = 0; px < sw; ++px) {
+        GatherGeom g;
+        int r = make_deconv_phase_geom(&g, n, hh, ww, cin, x_ld, kh, kw, cout, sh, sw, py, px, row0, row1, y_sn, y_sh,
+                                       y_sw, y_sc);
+        if (r == 1) continue;
+        SAG_TRY(r);
+        SAG_TRY(launch_gather_gemm(prec, x, w, y, g, ep, st));
+      }
+    return SAG_OK;
+  }
+
+  // tfw.fully_connected (core.py:43-93) on rows with stride x_ld / y_ld
+  int fc(const float* x, int rows, int in, int64_t x_ld, const std::string& scope, int out, int relu, float* y,
+         int64_t y_ld) {
+    int oh, ow;
+    return conv(x, 1, 1, rows, in, x_ld, scope, 1, 1, out, 1, 1, 0, true, relu, y, y_ld, nullptr, nullptr, &oh, &ow);
+  }
+};
+
+// contrib batch_norm(is_training=True) statistics -> per-channel scale/shift (core.py:209-210)
+struct BnBuf { double* sum; double* sqs; float* scale; float* shift; };
+static BnBuf alloc_bn(Arena& ar, int c) {
+  BnBuf b;
+  b.sum = ar.alloc<double>(2 * c);
+  b.sqs = b.sum + c;
+  b.scale = ar.alloc<float>(2 * c);
+  b.shift = b.scale + c;
+  return b;
+}
+
+// ResNet18.inference_ops(truncate_at='conv5_2') with batch statistics (resnet.py:123-190; model.py:189-201)
+int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int Wd, float* y, Arena& ar,
+                   cudaStream_t st) {
+  Fwd f{h, ar, st, h->cfg.precision};
+  const std::string p = scope + "/";
+  const float eps = 1e-3f;
+  int err = SAG_OK;
+  auto bn_finalize = [&](const std::string& q, const BnBuf& b, int c, int64_t count) -> int {
+    if (ar.dry) return SAG_OK;
+    const float* gamma = f.W(q + "/bn/gamma", &err);
+    const float* beta = f.W(q + "/bn/beta", &err);
+    SAG_TRY(err);
+    return launch_bn_finalize(b.sum, b.sqs, gamma, beta, (double)count, c, eps, b.scale, b.shift, st);
+  };
+  auto zero_bn = [&](const BnBuf& b, int c) -> int {
+    if (ar.dry) return SAG_OK;
+    SAG_CHECK_CUDA(cudaMemsetAsync(b.sum, 0, sizeof(double) * 2 * c, st));
+    return SAG_OK;
+  };
+
+  // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
+  int oh, ow;
+  int OH1 = (H + 1) / 2, OW1 = (Wd + 1) / 2;
+  float* c1 = ar.alloc<float>((int64_t)B * OH1 * OW1 * 64);
+  BnBuf b1 = alloc_bn(ar, 64);
+  SAG_TRY(zero_bn(b1, 64));
+  SAG_TRY(f.conv(x, B, H, Wd, 3, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, 64, b1.sum, b1.sqs, &oh, &ow));
+  SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
+  int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
+  float* cur = ar.alloc<float>((int64_t)B * ph * pw * 64);
+  if (!ar.dry) SAG_TRY(launch_bn_relu_maxpool(c1, b1.scale, b1.shift, B, oh, ow, 64, cur, st));
+  int ch = ph, cw = pw, cc = 64;
+
+  for (const BlockDef& b : kBlocks) {
+    const std::string q = p + b.name;
+    const int s = b.first ? 2 : 1;
+    const int nh = (ch + s - 1) / s, nw = (cw + s - 1) / s;
+    const int64_t npix = (int64_t)B * nh * nw;
+    const float* shortcut = cur;
+    if (b.first) {                                      // resnet.py:211-212: 1x1/s conv, no BN, no bias
+      float* sc = ar.alloc<float>(npix * b.cout);
+      SAG_TRY(f.conv(cur, B, ch, cw, cc, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, b.cout, nullptr,
+                     nullptr, &oh, &ow));
+      shortcut = sc;
+    }
+    float* r1 = ar.alloc<float>(npix * b.cout);
+    float* a1 = ar.alloc<float>(npix * b.cout);
+    float* r2 = ar.alloc<float>(npix * b.cout);
+    float* out = (std::string(b.name) == "conv5_2" && y != nullptr) ? y : ar.alloc<float>(npix * b.cout);
+    BnBuf s1 = alloc_bn(ar, b.cout), s2 = alloc_bn(ar, b.cout);
+    SAG_TRY(zero_bn(s1, b.cout));
+    SAG_TRY(zero_bn(s2, b.cout));
+    SAG_TRY(f.conv(cur, B, ch, cw, cc, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, b.cout, s1.sum, s1.sqs,
+                   &oh, &ow));
+    SAG_TRY(bn_finalize(q + "/conv_1", s1, b.cout, npix));
+    if (!ar.dry) SAG_TRY(launch_bn_apply(r1, s1.scale, s1.shift, nullptr, 1, a1, npix, b.cout, st));
+    SAG_TRY(f.conv(a1, B, nh, nw, b.cout, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, b.cout, s2.sum,
+                   s2.sqs, &oh, &ow));
+    SAG_TRY(bn_finalize(q + "/conv_2", s2, b.cout, npix));
+    if (!ar.dry) SAG_TRY(launch_bn_apply(r2, s2.scale, s2.shift, shortcut, 1, out, npix, b.cout, st));
+    f.tap(scope + "/" + b.name, out, {B, nh, nw, b.cout});
+    cur = out; ch = nh; cw = nw; cc = b.cout;
+  }
+  return SAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SptAudioGen.inference_ops (model.py:356-434)
+// ------------------------------------------------------------------------------------------------------------------
+int forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* out, Arena& ar, int B,
+            cudaStream_t st) {
+  const sag_config& c = h->cfg;
+  const sag_dims& d = h->dims;
+  Fwd f{h, ar, st, c.precision};
+  SAG_REQUIRE(B > 0, SAG_EINVAL, "forward: batch must be positive");
+  SAG_REQUIRE(c.enc_audio, SAG_EUNSUPPORTED, "the audio encoder is required (model.py:207 reads x_enc[AUDIO] unconditionally)");
+  SAG_REQUIRE(c.ambi_order == 1, SAG_EUNSUPPORTED, "only first-order ambisonics is supported");
+  if (!ar.dry) { h->ends.clear(); h->end_order.clear(); g_launch_count = 0; }
+  const bool unet = c.separation == SAG_SEP_UNET_MASK;
+  const int K = unet ? c.sep_num_tracks : 1;
+  const int wind = d.wind_size, hop = wind / 4;
+  const int T = d.snd_dur;
+
+  // ---- STFT (model.py:369; myutils.py:119-147) ----------------------------------------------------------------
+  const int n_enc = d.enc_tt - d.enc_ss;                  // 127
+  const int n_msk = d.mask_tt - d.mask_ss;                // 28
+  const bool full = !h->skip_unused;
+  float* S_all = nullptr;
+  float* S = nullptr;
+  if (full) {
+    S_all = ar.alloc<float>((int64_t)B * d.n_stft_frames * wind * 2);
+  } else if (unet) {
+    S = ar.alloc<float>((int64_t)B * n_msk * wind * 2);
+  }
+  float* mag = ar.alloc<float>((int64_t)B * n_enc * wind);
+  if (!ar.dry) {
+    if (full)
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag, st));
+    else
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, d.mask_ss, unet ? n_msk : 0, S, d.enc_ss, n_enc, mag, st));
+  }
+  if (full) f.tap("stft", S_all, {B, 1, d.n_stft_frames, wind, 2});
+  f.tap("audio_encoder/0", mag, {B, n_enc, wind, 1});
+
+  // ---- audio encoder (model.py:161-187): enc_l written into the skip halves of the decoder's concat buffers ----
+  int eh[6], ew[6], ecn[6];
+  eh[0] = n_enc; ew[0] = wind; ecn[0] = 1;
+  for (int l = 0; l < 5; ++l) {
+    SAG_REQUIRE(eh[l] >= kAudioKernel[l][0] && ew[l] >= kAudioKernel[l][1], SAG_EUNSUPPORTED, "audio window too short for the encoder");
+    eh[l + 1] = (eh[l] - kAudioKernel[l][0]) / kAudioStride[l][0] + 1;
+    ew[l + 1] = (ew[l] - kAudioKernel[l][1]) / kAudioStride[l][1] + 1;
+    ecn[l + 1] = kAudioFilters[l];
+  }
+  // cat[l] (l=1..5): pixel stride 2*C_l ; channels [0,C_l) decoder half, [C_l,2C_l) encoder skip -- except cat[5]
+  // which is [enc5, fc-feats] (model.py:296).
+  float* cat[6] = {nullptr};
+  int64_t cat_ld[6] = {0};
+  float* enc_ptr[6];
+  enc_ptr[0] = mag;
+  for (int l = 1; l <= 5; ++l) {
+    cat_ld[l] = unet ? 2 * ecn[l] : ecn[l];
+    cat[l] = ar.alloc<float>((int64_t)B * eh[l] * ew[l] * cat_ld[l]);
+    enc_ptr[l] = cat[l] + ((unet && l < 5) ? ecn[l] : 0);
+  }
+  for (int l = 0; l < 5; ++l) {
+    int oh, ow;
+    SAG_TRY(f.conv(enc_ptr[l], B, eh[l], ew[l], ecn[l], l == 0 ? 1 : cat_ld[l], "audio_encoder/conv" + std::to_string(l + 1),
+                   kAudioKernel[l][0], kAudioKernel[l][1], ecn[l + 1], kAudioStride[l][0], kAudioStride[l][1], 0, true, 1,
+                   enc_ptr[l + 1], cat_ld[l + 1], nullptr, nullptr, &oh, &ow));
+    f.tap("audio_encoder/" + std::to_string(l + 1), enc_ptr[l + 1], {B, eh[l + 1], ew[l + 1], ecn[l + 1]}, cat_ld[l + 1]);
+  }
+  const int nt = eh[5];                                    // 3 time steps of the bottleneck
+  SAG_REQUIRE(T % nt == 0, SAG_EUNSUPPORTED, "snd_dur %d not divisible by %d localization steps", T, nt);
+
+  // ---- visual towers (model.py:189-201) ---------------------------------------------------------------------
+  const int D = d.feat_dim;
+  float* feats = ar.alloc<float>((int64_t)B * nt * D);
+  int foff = 0;
+  // bottleneck audio (model.py:207-230): (B,3,6*512) -> fc 1024, as a (1 x ew5) VALID conv over the strided enc5
+  {
+    int oh, ow;
+    SAG_TRY(f.conv(enc_ptr[5], B * nt, 1, ew[5], ecn[5], cat_ld[5], "bottleneck/audio-fc", 1, ew[5], 1024, 1, 1, 0, true, 1,
+                   feats + foff, D, nullptr, nullptr, &oh, &ow));
+    foff += 1024;
+  }
+  for (int v = 0; v < 2; ++v) {
+    if (!(v == 0 ? c.enc_video : c.enc_flow)) continue;
+    const float* inp = v == 0 ? video : flow;
+    const std::string k = v == 0 ? "video" : "flow";
+    if (!ar.dry) SAG_REQUIRE(inp != nullptr, SAG_EINVAL, "forward: %s input is NULL but the encoder is enabled", k.c_str());
+    const int fh = (c.frame_h + 31) / 32, fw = (c.frame_w + 31) / 32;
+    float* vf = ar.alloc<float>((int64_t)B * fh * fw * 512);
+    SAG_TRY(resnet18_tower(h, k + "_encoder", inp, B, c.frame_h, c.frame_w, vf, ar, st));
+    float* red = ar.alloc<float>((int64_t)B * fh * fw * 128);
+    SAG_TRY(f.fc(vf, B * fh * fw, 512, 512, "bottleneck/" + k + "-fc-red", 128, 1, red, 128));
+    float* vfc = ar.alloc<float>((int64_t)B * 512);
+    SAG_TRY(f.fc(red, B, fh * fw * 128, (int64_t)fh * fw * 128, "bottleneck/" + k + "-fc", 512, 1, vfc, 512));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(vfc, 512, feats + foff, D, B, nt, 512, st));     // tf.tile (model.py:232)
+    foff += 512;
+  }
+  f.tap("bottleneck", feats, {B, nt, D});
+
+  // ---- localization (model.py:241-271) -----------------------------------------------------------------------
+  const int n3 = 3 * (K + 1);
+  float* loc = ar.alloc<float>((int64_t)B * nt * n3);
+  {
+    const float* x = feats;
+    int in = D;
+    for (int i = 0; i < c.n_loc_fc; ++i) {
+      float* y = ar.alloc<float>((int64_t)B * nt * c.loc_fc_units[i]);
+      SAG_TRY(f.fc(x, B * nt, in, in, "localization/fc" + std::to_string(i + 1), c.loc_fc_units[i], 1, y, c.loc_fc_units[i]));
+      x = y;
+      in = c.loc_fc_units[i];
+    }
+    SAG_TRY(f.fc(x, B * nt, in, in, "localization/fc" + std::to_string(c.n_loc_fc + 1), n3, 0, loc, n3));
+  }
+  f.tap("localization", loc, {B, nt, 3, 1, K + 1});
+
+  // ---- separation (model.py:273-354) --------------------------------------------------------------------------
+  float* x_sep = ar.alloc<float>((int64_t)B * K * T);
+  if (!unet) {
+    // NO_SEPARATION: x_sep = mono[snd_contx/2 : +snd_dur] (model.py:274-280); audio is (B,snd_size,1)
+    if (!ar.dry) SAG_TRY(launch_tile_rows(audio + d.snd_contx / 2, d.snd_size, x_sep, T, B, 1, T, st));
+  } else {
+    float* sf = ar.alloc<float>((int64_t)B * nt * 512);
+    SAG_TRY(f.fc(feats, B * nt, D, D, "separation/fc-feats", 512, 1, sf, 512));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(sf, 512, cat[5] + 512, cat_ld[5], B * nt, ew[5], 512, st));   // model.py:295-296
+    // deconv5..2 with ReLU into the lower halves of cat4..1 (model.py:299-310)
+    for (int l = 4; l >= 1; --l) {
+      const int cout = ecn[l];
+      const int OH = (eh[l + 1] - 1) * kAudioStride[l][0] + kAudioKernel[l][0];
+      const int OW = (ew[l + 1] - 1) * kAudioStride[l][1] + kAudioKernel[l][1];
+      SAG_REQUIRE(OH == eh[l] && OW == ew[l], SAG_EUNSUPPORTED, "decoder/encoder shape mismatch at level %d", l);
+      SAG_TRY(f.deconv(cat[l + 1], B, eh[l + 1], ew[l + 1], (int)cat_ld[l + 1], cat_ld[l + 1],
+                       "separation/deconv" + std::to_string(l + 1), kAudioKernel[l][0], kAudioKernel[l][1], cout,
+                       kAudioStride[l][0], kAudioStride[l][1], 1, cat[l], 0, OH, (int64_t)OH * OW * cat_ld[l],
+                       (int64_t)OW * cat_ld[l], cat_ld[l], 1));
+    }
+    // deconv1 (no ReLU): rows [r0,r1) only, written as (B, track, frame, freq) (model.py:319-330)
+    const int OH = (eh[1] - 1) * kAudioStride[0][0] + kAudioKernel[0][0];
+    const int OW = (ew[1] - 1) * kAudioStride[0][1] + kAudioKernel[0][1];
+    SAG_REQUIRE(OW == wind && OH == n_enc, SAG_EUNSUPPORTED, "deconv1 output %dx%d does not match the STFT crop %dx%d", OH, OW, n_enc, wind);
+    const int r0 = full ? 0 : d.mask_ss - d.mask_skip, r1 = full ? OH : d.mask_tt - d.mask_skip;
+    const int nr = r1 - r0;
+    float* mask = ar.alloc<float>((int64_t)B * K * nr * OW);
+    SAG_TRY(f.deconv(cat[1], B, eh[1], ew[1], (int)cat_ld[1], cat_ld[1], "separation/deconv1", kAudioKernel[0][0],
+                     kAudioKernel[0][1], K, kAudioStride[0][0], kAudioStride[0][1], 0, mask, r0, r1, (int64_t)K * nr * OW,
+                     OW, 1, (int64_t)nr * OW));
+    f.tap("separation/mask_logits", mask, {B, K, nr, OW});
+    // sigmoid mask x STFT -> istft -> crop (model.py:334-347; myutils.py:181-211)
+    // frames [mask_ss, mask_tt) of the full STFT / rows [mask_ss-skip, ..) of the full mask are strided views the
+    // kernel does not take: compact them first (test-only path, skip_unused == 0).
+    float* S2 = full ? ar.alloc<float>((int64_t)B * n_msk * wind * 2) : S;
+    float* m2 = full ? ar.alloc<float>((int64_t)B * K * n_msk * OW) : mask;
+    if (!ar.dry) {
+      if (full) {
+        SAG_CHECK_CUDA(cudaMemcpy2DAsync(S2, sizeof(float) * n_msk * wind * 2, S_all + (int64_t)d.mask_ss * wind * 2,
+                                         sizeof(float) * d.n_stft_frames * wind * 2, sizeof(float) * n_msk * wind * 2, B,
+                                         cudaMemcpyDeviceToDevice, st));
+        SAG_CHECK_CUDA(cudaMemcpy2DAsync(m2, sizeof(float) * n_msk * OW, mask + (int64_t)(d.mask_ss - d.mask_skip) * OW,
+                                         sizeof(float) * nr * OW, sizeof(float) * n_msk * OW, (size_t)B * K,
+                                         cudaMemcpyDeviceToDevice, st));
+      }
+      SAG_TRY(launch_istft(S2, m2, 1, B, K, n_msk, wind, 4, d.final_crop, T, x_sep, st));
+    }
+  }
+  f.tap("separation/all_channels", x_sep, {B, 1, K, T});
+
+  // ---- decode (model.py:424-432) -------------------------------------------------------------------------------
+  if (!ar.dry) SAG_TRY(launch_mix(x_sep, loc, B, K, T, nt, out, st));
+  if (!ar.dry) h->last_launches = g_launch_count;
+  return SAG_OK;
+}
+
+}  // namespace sag

@@ -1,0 +1,73 @@
+// Handle, weight store, workspace arena and the forward orchestration of SptAudioGen.inference_ops
+// (reference model.py:356-434) for libsag.so.
+#pragma once
+#include "common.cuh"
+
+namespace sag {
+
+struct DevTensor {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  int64_t ld = 0;      // stride of the second-to-last dimension (== shape.back() when contiguous)
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// Bump allocator over the caller's workspace.  In dry mode nothing is touched and only the peak is recorded
+// (that is how sag_workspace_bytes is computed: by running the same planner).
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  bool failed = false;
+  template <class T>
+  T* alloc(int64_t n) {
+    off = (off + 255) & ~(size_t)255;
+    size_t bytes = (size_t)n * sizeof(T);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    if (off > peak) peak = off;
+    if (!dry && off > cap) failed = true;
+    return p;
+  }
+};
+
+}  // namespace sag
+
+struct sag_handle {
+  sag_config cfg;
+  sag_dims dims;
+  int device = 0;
+  std::vector<std::pair<std::string, std::vector<int64_t>>> expected;   // checkpoint layout
+  std::map<std::string, sag::DevTensor> weights;                        // TF layout on device
+  std::map<std::string, sag::DevTensor> packed;                         // kernel layouts derived at load time
+  std::map<std::string, sag::DevTensor> ends;                           // taps of the last forward
+  std::vector<std::string> end_order;
+  int last_launches = 0;
+  int finalized = 0;
+  int skip_unused = 1;   // skip mask rows / frames that cannot reach the cropped output (bit-identical result)
+};
+
+namespace sag {
+
+int build_expected(sag_handle* h);
+int derive_dims(const sag_config& c, sag_dims* d);
+int forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* out, Arena& ar, int B,
+            cudaStream_t st);
+int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int W, float* y, Arena& ar,
+                   cudaStream_t st);
+const char* last_error_cstr();
+int fft_prepare(int n);
+void istft_needed_frames(int n_frames, int wind, int n_overlap, int crop0, int n_out, int* f_lo, int* f_hi);
+int sh_mesh_dims(float ang_res, int* n_nu, int* n_phi);
+
+// precision dispatch for the dense contractions
+int launch_gather_gemm_umma(int precision, const float* x, const float* w, float* y, const GatherGeom& g,
+                            const Epilogue& ep, cudaStream_t st);
+int launch_gather_gemm(int precision, const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
+                       cudaStream_t st);
+
+}  // namespace sag

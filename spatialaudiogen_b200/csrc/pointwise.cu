@@ -1,0 +1,275 @@
+// HBM-bound pointwise / reduction kernels: batch-statistics BN (reference core.py:209-210),
+// 3x3/2 SAME max-pool (resnet.py:135), tf.tile replacements (model.py:232,262,295) and the time-varying
+// 32->3 mixing of model.py:424-432.  All are streaming kernels: float4 accesses, grid sized in multiples
+// of the SM count, one pass over the data.
+#include "common.cuh"
+
+namespace sag {
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// ---- BN finalize: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale (biased variance) ----
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqs,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, double inv_count,
+                                   int c, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double mean = sum[i] * inv_count;
+  double var = sqs[i] * inv_count - mean * mean;
+  if (var < 0) var = 0;
+  double sc = (double)gamma[i] / sqrt(var + (double)eps);
+  scale[i] = (float)sc;
+  shift[i] = (float)((double)beta[i] - mean * sc);
+}
+
+int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
+                       int c, float eps, float* scale, float* shift, cudaStream_t st) {
+  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, st>>>(sum, sqs, gamma, beta, 1.0 / count, c, eps, scale, shift);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- BN apply (+residual)(+relu): y = act(x*scale[c] + shift[c] + res) ; c % 4 == 0 ----
+__global__ void bn_apply_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const float4* __restrict__ res, int relu,
+                                float4* __restrict__ y, int64_t n4, int c4) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int cc = (int)(i % c4) * 4;
+    float4 v = __ldg(x + i);
+    float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc));
+    float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc));
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (res != nullptr) {
+      float4 r = __ldg(res + i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    y[i] = v;
+  }
+}
+
+int launch_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, int relu,
+                    float* y, int64_t rows, int c, cudaStream_t st) {
+  SAG_REQUIRE(c % 4 == 0, SAG_EINVAL, "bn_apply: channels %d not a multiple of 4", c);
+  int64_t n4 = rows * c / 4;
+  if (n4 == 0) return SAG_OK;
+  int64_t blocks = cdiv64(n4, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale, shift,
+                                                    reinterpret_cast<const float4*>(residual), relu,
+                                                    reinterpret_cast<float4*>(y), n4, c / 4);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- fused BN + ReLU + max-pool 3x3/2 SAME (pad before 0: TF puts the odd pad cell after) ----
+__global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, int n, int h, int w, int c, int oh, int ow,
+                                       int pt, int pl, float* __restrict__ y) {
+  int c4 = c / 4;
+  int64_t total = (int64_t)n * oh * ow * c4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4) * 4;
+    int64_t r = i / c4;
+    int ox = (int)(r % ow); r /= ow;
+    int oy = (int)(r % oh);
+    int b = (int)(r / oh);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale != nullptr) {
+      sc = __ldg(reinterpret_cast<const float4*>(scale + cc));
+      sh = __ldg(reinterpret_cast<const float4*>(shift + cc));
+    }
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      int iy = oy * 2 + dy - pt;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int ix = ox * 2 + dx - pl;
+        if (ix < 0 || ix >= w) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * h + iy) * w + ix) * c + cc));
+        if (scale != nullptr) {
+          v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+          v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+        }
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = m;
+  }
+}
+
+int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
+                           float* y, cudaStream_t st) {
+  SAG_REQUIRE(c % 4 == 0, SAG_EINVAL, "maxpool: channels %d not a multiple of 4", c);
+  int oh, ow;
+  int pt = same_pad_before(h, 3, 2, &oh), pl = same_pad_before(w, 3, 2, &ow);
+  int64_t total = (int64_t)n * oh * ow * (c / 4);
+  int64_t blocks = cdiv64(total, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  bn_relu_maxpool_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, scale, shift, n, h, w, c, oh, ow, pt, pl, y);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- per-channel sum / sum of squares over rows (stand-alone BN statistics) ----
+// block = 256 threads = 8 row lanes x 32 channel lanes(x4 via float4 when possible): generic scalar version
+__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t rows, int c, double* __restrict__ sum,
+                                     double* __restrict__ sqs) {
+  // each block handles a contiguous slab of rows; thread t covers channels t, t+blockDim, ...
+  int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float v = __ldg(x + r * c + ch);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    if (r1 > r0) {
+      atomicAdd(sum + ch, (double)s);
+      atomicAdd(sqs + ch, (double)q);
+    }
+  }
+}
+
+int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st) {
+  int threads = c >= 256 ? 256 : (c >= 128 ? 128 : (c >= 64 ? 64 : 32));
+  int64_t blocks = cdiv64(rows, 64);
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  channel_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(x, rows, c, sum, sqs);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- tf.tile replacement: dst[(g*reps + r)*dst_ld + 0..c) = src[g*src_ld + 0..c) ----
+__global__ void tile_rows_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
+                                 int64_t dst_ld, int groups, int reps, int c) {
+  int64_t total = (int64_t)groups * reps * c;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int ch = (int)(i % c);
+    int64_t row = i / c;
+    int64_t gidx = row / reps;
+    dst[row * dst_ld + ch] = __ldg(src + gidx * src_ld + ch);
+  }
+}
+
+int launch_tile_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int groups, int reps, int c,
+                     cudaStream_t st) {
+  int64_t total = (int64_t)groups * reps * c;
+  if (total == 0) return SAG_OK;
+  int64_t blocks = cdiv64(total, 256);
+  int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  tile_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, src_ld, dst, dst_ld, groups, reps, c);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- decode (model.py:424-432): out[b,n,o] = sum_k loc[b,seg(n),o*(K+1)+k]*x_sep[b,k,n] + loc[b,seg(n),o*(K+1)+K]
+// loc weights are piecewise constant over t/segments samples (model.py:262-263 tiles them); they stay in smem.
+// One block per (b, chunk of 256 samples); coalesced reads along n for every track.
+__global__ void mix_kernel(const float* __restrict__ x_sep, const float* __restrict__ loc, int tracks, int t,
+                           int segments, float* __restrict__ out) {
+  extern __shared__ float s_loc[];   // [3*(tracks+1)]
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * blockDim.x;
+  const int seg_len = t / segments;
+  const int K1 = tracks + 1;
+  const int n = n0 + threadIdx.x;
+  // a block never straddles a segment boundary when seg_len % blockDim.x == 0; otherwise reload per thread
+  const bool uniform = (seg_len % blockDim.x) == 0;
+  int seg = min(n0 / seg_len, segments - 1);
+  if (uniform) {
+    for (int i = threadIdx.x; i < 3 * K1; i += blockDim.x) s_loc[i] = __ldg(loc + ((int64_t)b * segments + seg) * 3 * K1 + i);
+    __syncthreads();
+  }
+  if (n >= t) return;
+  const float* lw = s_loc;
+  if (!uniform) {
+    seg = min(n / seg_len, segments - 1);
+    lw = loc + ((int64_t)b * segments + seg) * 3 * K1;
+  }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const float* xs = x_sep + (int64_t)b * tracks * t + n;
+  for (int k = 0; k < tracks; ++k) {
+    float v = __ldg(xs + (int64_t)k * t);
+    a0 = fmaf(lw[k], v, a0);
+    a1 = fmaf(lw[K1 + k], v, a1);
+    a2 = fmaf(lw[2 * K1 + k], v, a2);
+  }
+  float* o = out + ((int64_t)b * t + n) * 3;
+  o[0] = a0 + lw[tracks];
+  o[1] = a1 + lw[K1 + tracks];
+  o[2] = a2 + lw[2 * K1 + tracks];
+}
+
+int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
+               cudaStream_t st) {
+  SAG_REQUIRE(segments > 0 && t % segments == 0, SAG_EINVAL, "mix: %d samples not divisible into %d segments", t, segments);
+  int threads = 64;
+  dim3 grid(cdiv(t, threads), batch);
+  mix_kernel<<<grid, threads, 3 * (tracks + 1) * sizeof(float), st>>>(x_sep, loc, tracks, t, segments, out);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+__global__ void sigmoid_kernel(float* x, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = 1.f / (1.f + expf(-x[i]));
+}
+
+int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st) {
+  int64_t blocks = cdiv64(n, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return SAG_OK;
+  sigmoid_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin] (core.py:118) -> per-tap [Cin][Cout] slabs ----
+__global__ void pack_deconv_w_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cout, int cin) {
+  int64_t total = (int64_t)taps * cout * cin;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int co = (int)(i % cout);
+    int64_t r = i / cout;
+    int ci = (int)(r % cin);
+    int t = (int)(r / cin);
+    out[i] = __ldg(w + ((int64_t)t * cout + co) * cin + ci);
+  }
+}
+
+int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st) {
+  int64_t total = (int64_t)taps * cout * cin;
+  if (total == 0) return SAG_OK;
+  int64_t blocks = cdiv64(total, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  pack_deconv_w_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwoi, out, taps, cout, cin);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+}  // namespace sag

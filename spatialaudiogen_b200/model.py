@@ -1,0 +1,285 @@
+"""SptAudioGen: the reference's model.py operator API (reference model.py:10-434) backed by libsag.so.
+
+Same constructor arguments, attribute names (snd_contx, snd_dur, snd_size, wind_size, num_ambi_channels, encoders,
+separation, ends, loc_channels, sep_channels, init_ops) and method names as the reference; the TF graph +
+`sess.run` is replaced by eager calls on `torch.cuda` tensors that go straight to hand-written sm_100a kernels
+through the C ABI (include/sag.h).  Weights enter by TF variable name like `Saver.restore`.
+PyTorch only owns the buffers; there is no CPU / PyTorch compute fallback.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .definitions import *          # noqa: F401,F403  (AUDIO, VIDEO, FLOW, ENCODERS, NO_SEPARATION, FREQ_MASK, ...)
+from .definitions import (AUDIO, VIDEO, FLOW, ENCODERS, NO_SEPARATION, FREQ_MASK, FFT_WINDOW, FFT_OVERLAP_R,
+                          NUM_SEP_TRACKS_DEF, CTX_FEATS_FCUNITS_DEF, LOC_FCUNITS_DEF, SEP_FREQ_MASK_FCUNITS_DEF,
+                          SEP_FFT_WINDOW_DEF)
+
+
+class SptAudioGenParams:
+    """reference model.py:10-21 (ctx_feats_fc_units / sep_freq_mask_fc_units are stored but unused there too)."""
+
+    def __init__(self,
+                 sep_num_tracks=NUM_SEP_TRACKS_DEF,
+                 ctx_feats_fc_units=CTX_FEATS_FCUNITS_DEF,
+                 loc_fc_units=LOC_FCUNITS_DEF,
+                 sep_freq_mask_fc_units=SEP_FREQ_MASK_FCUNITS_DEF,
+                 sep_fft_window=SEP_FFT_WINDOW_DEF):
+        self.sep_num_tracks = sep_num_tracks
+        self.ctx_feats_fc_units = ctx_feats_fc_units
+        self.loc_fc_units = loc_fc_units
+        self.sep_freq_mask_fc_units = sep_freq_mask_fc_units
+        self.sep_fft_window = sep_fft_window
+
+
+class SptAudioGen(object):
+    """reference model.py:24-434.  Extra keyword arguments (not in the reference): `precision`
+    ('fp32' | 'tf32' | 'bf16' | 'bf16x3': arithmetic of the dense contractions), `device`, `frame_size`."""
+
+    def __init__(self, ambi_order,
+                 audio_rate=48000,
+                 video_rate=10,
+                 context=1.,
+                 sample_duration=0.1,
+                 encoders=None,
+                 separation='none',
+                 params=None,
+                 precision='fp32',
+                 device=None,
+                 frame_size=(224, 448)):
+        assert float(audio_rate) / video_rate == int(audio_rate) // int(video_rate)          # model.py:33
+        if params is None:
+            params = SptAudioGenParams()
+        self.ambi_order = ambi_order
+        self.num_ambi_channels = sum([2 * i + 1 for i in range(ambi_order + 1)])
+        self.snd_rate, self.vid_rate = audio_rate, video_rate
+        self.context, self.duration = context, sample_duration
+        self.snd_contx = int(context * audio_rate)
+        self.snd_dur = int(sample_duration * audio_rate)
+        self.snd_size = self.snd_contx + self.snd_dur - 1
+        assert self.snd_rate % self.vid_rate == 0
+
+        if encoders is None:
+            encoders = [AUDIO, VIDEO, FLOW]
+        assert isinstance(encoders, list)
+        assert all([e in ENCODERS for e in encoders])
+        self.encoders = encoders
+        if separation not in (NO_SEPARATION, FREQ_MASK):
+            raise ValueError('Unknown separation mode.')                                      # model.py:351
+        self.separation = separation
+        self.params = params
+
+        self.model = None
+        self.deploy = None
+        self.solver = None
+        self.ends = OrderedDict()
+        self.init_ops = []
+        self.loc_channels = None
+        self.sep_channels = None
+        self.wind_size = int(self.params.sep_fft_window * self.snd_rate)
+        self.wind_size = int(2 ** np.round(np.log2(self.wind_size)))
+
+        # ---- native handle ----
+        if not torch.cuda.is_available():
+            raise RuntimeError('spatialaudiogen_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.precision = precision
+        lib = L.lib()
+        cfg = L.sag_config()
+        L.check(lib.sag_config_default(C.byref(cfg)))
+        cfg.ambi_order, cfg.audio_rate, cfg.video_rate = int(ambi_order), int(audio_rate), int(video_rate)
+        cfg.context, cfg.sample_duration = float(context), float(sample_duration)
+        cfg.enc_audio, cfg.enc_video, cfg.enc_flow = int(AUDIO in encoders), int(VIDEO in encoders), int(FLOW in encoders)
+        cfg.separation = L.SAG_SEP_UNET_MASK if separation == FREQ_MASK else L.SAG_SEP_NONE
+        cfg.sep_num_tracks = int(params.sep_num_tracks)
+        units = list(params.loc_fc_units)
+        if len(units) > 4:
+            raise ValueError('at most 4 localization FC layers are supported')
+        cfg.n_loc_fc = len(units)
+        for i, u in enumerate(units):
+            cfg.loc_fc_units[i] = int(u)
+        cfg.sep_fft_window = float(params.sep_fft_window)
+        cfg.precision = L.PRECISIONS[precision]
+        cfg.frame_h, cfg.frame_w = int(frame_size[0]), int(frame_size[1])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(lib.sag_create(C.byref(self._h), C.byref(cfg)))
+        d = L.sag_dims()
+        L.check(lib.sag_get_dims(self._h, C.byref(d)))
+        self.dims = d
+        assert (d.snd_contx, d.snd_dur, d.snd_size, d.wind_size) == (self.snd_contx, self.snd_dur, self.snd_size, self.wind_size)
+        self._frame = (int(frame_size[0]), int(frame_size[1]))
+        self._ws = None
+        self._ws_batch = 0
+        self._weights_ready = False
+        self._w = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None) is not None and self._h.value:
+                L.lib().sag_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- checkpoint layout ------------------------------------------------------------------------------------
+    def variable_shapes(self):
+        """OrderedDict TF variable name -> shape the handle expects."""
+        lib = L.lib()
+        out = OrderedDict()
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int64 * 4)()
+        rank = C.c_int()
+        for i in range(lib.sag_num_weights_expected(self._h)):
+            L.check(lib.sag_weight_name(self._h, i, buf, 256, shape, C.byref(rank)))
+            out[buf.value.decode()] = tuple(int(shape[k]) for k in range(rank.value))
+        return out
+
+    def load_weights(self, arrays, strict=True):
+        """tf.train.Saver().restore replacement (deploy.py:79-87, eval.py:98-118): `arrays` maps TF variable
+        names to ndarrays in TF layouts.  Unknown names (optimizer slots, 'metrics/...', 'step') are ignored."""
+        lib = L.lib()
+        expected = self.variable_shapes()
+        with torch.cuda.device(self.device):
+            for name, shape in expected.items():
+                if name not in arrays:
+                    if strict and '/bn/moving_' not in name:
+                        raise KeyError('checkpoint is missing variable %s' % name)
+                    continue
+                a = np.ascontiguousarray(np.asarray(arrays[name], dtype=np.float32))
+                if tuple(a.shape) != tuple(shape):
+                    raise ValueError('variable %s has shape %s, expected %s' % (name, a.shape, shape))
+                sh = (C.c_int64 * len(shape))(*shape)
+                L.check(lib.sag_load_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), sh, len(shape)))
+                self._w[name] = a
+            L.check(lib.sag_finalize_weights(self._h, L.stream()))
+        self._weights_ready = True
+        return self
+
+    def set_option(self, key, value):
+        if key == 'precision' and isinstance(value, str):
+            self.precision = value
+            value = L.PRECISIONS[value]
+        L.check(L.lib().sag_set_option(self._h, key.encode(), int(value)))
+        self._ws_batch = 0
+
+    # ---- forward ---------------------------------------------------------------------------------------------
+    def _workspace(self, B):
+        if self._ws is None or self._ws_batch != B:
+            need = L.lib().sag_workspace_bytes(self._h, B)
+            if need == 0:
+                raise L.SagError(L.SAG_EUNSUPPORTED, L.lib().sag_last_error().decode('utf-8', 'replace'))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_batch = B
+        return self._ws
+
+    def forward_into(self, audio, video, flow, out):
+        """sag_forward on pre-staged contiguous float32 CUDA tensors (no allocation, no copies, no sync)."""
+        B = audio.shape[0]
+        ws = self._workspace(B)
+        L.check(L.lib().sag_forward(self._h, L.ptr(audio), L.ptr(video), L.ptr(flow), L.ptr(out), C.c_void_p(ws.data_ptr()),
+                                    ws.numel(), B, L.stream()))
+        return out
+
+    def inference_ops(self, audio, video=None, flow=None, is_training=True):
+        """reference model.py:356-434.  audio (B, snd_size, 1); video / flow (B, 1, H, W, 3); returns the
+        (B, snd_dur, 3) first-order channels (Y, Z, X) as a CUDA tensor.  `is_training` is accepted for API
+        compatibility: the reference never forwards it to the visual towers (they always use batch statistics,
+        model.py:197) and no other layer depends on it."""
+        if not self._weights_ready:
+            raise RuntimeError('load_weights() must be called before inference_ops()')
+        with torch.cuda.device(self.device):
+            audio = L.f32(audio, self.device)
+            if audio.dim() != 3 or audio.shape[1] != self.snd_size or audio.shape[2] != 1:
+                raise ValueError('audio must be (B, %d, 1), got %s' % (self.snd_size, tuple(audio.shape)))
+            B = audio.shape[0]
+            ins = {}
+            for key, t in ((VIDEO, video), (FLOW, flow)):
+                if key in self.encoders:
+                    if t is None:
+                        raise ValueError('%s input required by encoders=%s' % (key, self.encoders))
+                    t = L.f32(t, self.device)
+                    want = (B, 1, self.dims_frame()[0], self.dims_frame()[1], 3)
+                    if tuple(t.shape) != want:
+                        raise ValueError('%s must be %s, got %s' % (key, want, tuple(t.shape)))
+                    ins[key] = t
+            out = torch.empty((B, self.snd_dur, self.num_ambi_channels - self.ambi_order ** 2), dtype=torch.float32,
+                              device=self.device)
+            self.forward_into(audio, ins.get(VIDEO), ins.get(FLOW), out)
+            self._collect_ends()
+        return out
+
+    def dims_frame(self):
+        return self._frame
+
+    def _view(self, name):
+        lib = L.lib()
+        p = C.c_void_p()
+        shape = (C.c_int64 * 5)()
+        rank = C.c_int()
+        ld = C.c_int64()
+        L.check(lib.sag_get_tensor(self._h, name.encode(), C.byref(p), shape, C.byref(rank), C.byref(ld)))
+        shp = [int(shape[k]) for k in range(rank.value)]
+        off = p.value - self._ws.data_ptr()
+        assert off >= 0 and off % 4 == 0
+        flat = self._ws[off:].view(torch.float32)
+        strides = [1] * len(shp)
+        if len(shp) >= 2:
+            strides[-2] = int(ld.value)
+            for k in range(len(shp) - 3, -1, -1):
+                strides[k] = strides[k + 1] * shp[k + 1]
+        return flat.as_strided(shp, strides)
+
+    def _collect_ends(self):
+        """Views (aliasing the workspace, valid until the next forward) of the taps the reference keeps in
+        `self.ends`, `self.sep_channels`, `self.loc_channels` (model.py:371-432)."""
+        lib = L.lib()
+        buf = C.create_string_buffer(256)
+        self.ends = OrderedDict()
+        for i in range(lib.sag_num_tensors(self._h)):
+            L.check(lib.sag_tensor_name(self._h, i, buf, 256))
+            name = buf.value.decode()
+            self.ends[name] = self._view(name)
+        if 'stft' in self.ends:
+            self.ends['stft'] = torch.view_as_complex(self.ends['stft'])
+        self.sep_channels = self.ends.get('separation/all_channels')
+        loc = self.ends.get('localization')
+        if loc is not None:
+            self.loc_channels = [loc[..., :-1], loc[..., -1]]       # per segment; the reference tiles x1600 (model.py:262)
+
+    # ---- evaluation (model.py:110-154) ----------------------------------------------------------------------------
+    def evaluation_ops(self, preds_t, targets_t, w_t, mask_channels=None):
+        """reference model.py:110-154 -> (metrics, stft_dist_ps, lsd_ps, mse_ps, snr_ps); tensors (B,3), channel
+        order (Y,Z,X).  Like the reference, the channel mask is mandatory (model.py:114 dereferences it first)."""
+        if mask_channels is None:
+            raise ValueError('mask_channels is required (reference model.py:114-118)')
+        from . import metrics as M
+        preds = L.f32(preds_t, self.device)
+        targets = L.f32(targets_t, self.device)
+        mask = L.f32(mask_channels, self.device)
+        if mask.dim() == 1:
+            mask = mask[None].expand(preds.shape[0], -1)
+        if mask.shape[1] == self.num_ambi_channels:
+            mask = mask[:, self.ambi_order ** 2:]
+        res = M.window_metrics(preds, targets, self.snd_rate)
+        stft_ps, lsd_ps, mse_ps, snr_ps = res['stft'], res['lsd'], res['mse'], res['snr']
+        self.last_eval = res
+        num_masked = mask.sum(0).clamp(min=1)                                              # model.py:115-116
+        metrics = OrderedDict()
+        for key, ps, scale in (('stft', stft_ps, 100.), ('lsd', lsd_ps, 1.), ('mse', mse_ps, 5e3), ('snr', snr_ps, 1.)):
+            v = (ps * mask).sum(0) / num_masked * scale
+            metrics[key + '/avg'] = v.mean()
+            for i, ch in zip(range(3), 'YZX'):
+                metrics[key + '/' + ch] = v[i]
+        metrics['pow/pred'] = (preds ** 2).mean(2).mean(0).sum()
+        metrics['pow/gt'] = (targets ** 2).mean(2).mean(0).sum()
+        return metrics, stft_ps, lsd_ps, mse_ps, snr_ps
+
+    def loss_ops(self, metrics_t, step_t=None):
+        """reference model.py:156-159: the training loss is the STFT distance (training itself is out of scope)."""
+        return metrics_t['stft/avg']

@@ -1,0 +1,336 @@
+"""GPU parity tests: every CUDA stage and the whole forward, called through the C ABI (libsag.so), against the CPU
+oracle on the same seeded inputs.  Tolerances are stated per test; indices are bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sag_oracle as O
+from spatialaudiogen_b200 import weights as Wt
+
+pytestmark = pytest.mark.gpu
+
+RESNET_NPY = '/root/reference/pyutils/tflib/models/image/resnet18.npy'
+
+
+def _L():
+    from spatialaudiogen_b200 import _lib as L
+    return L
+
+
+def _audio(B, seed=0, n=52799):
+    rng = np.random.RandomState(seed)
+    t = np.arange(n)
+    ph = rng.uniform(0, 2 * np.pi, size=(B, 1))
+    x = 0.1 * rng.randn(B, n) + 0.3 * np.sin(2 * np.pi * 440 * t / 48000. + ph)
+    return np.clip(x, -1, 1).astype(np.float32)[:, :, None]
+
+
+def _video(B, seed=1, h=224, w=448):
+    rng = np.random.RandomState(seed)
+    return (rng.randint(0, 256, size=(B, 1, h, w, 3)) / 255. - 0.5).astype(np.float32)
+
+
+def _flow(B, seed=2, h=224, w=448):
+    rng = np.random.RandomState(seed)
+    mag = rng.uniform(0, 20, size=(B, 1, h, w))
+    th = rng.uniform(0, 2 * np.pi, size=(B, 1, h, w))
+    return np.stack([mag * np.cos(th), mag * np.sin(th), mag], -1).astype(np.float32)
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def cu(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ STFT / iSTFT
+def test_stft_matches_oracle_and_frame_indexing_bit_exact():
+    from spatialaudiogen_b200 import myutils
+    a = _audio(3, 4)[:, :, 0]
+    s = myutils.stft(cu(a)[:, None, :], 1024, 4)
+    ref = O.stft(torch.as_tensor(a)[:, None, :].double(), 1024, 4)
+    assert tuple(s.shape) == (3, 1, 200, 1024)
+    assert _rel(torch.view_as_real(s), torch.view_as_real(ref)) < 2e-6
+    # bit-exact frame indexing: an impulse at sample n lights exactly the frames with 256t <= n < 256t+1024
+    w = O.hann(1024, torch.float32)
+    for n in [0, 255, 256, 1023, 1024, 30000, 51967, 51968, 52798]:
+        x = torch.zeros(1, 52799)
+        x[0, n] = 1.0
+        e = myutils.stft(x.cuda(), 1024, 4).abs().sum(-1)[0].cpu()
+        hit = set(torch.nonzero(e > 0).flatten().tolist())
+        exp = {t for t in range(200) if 256 * t <= n < 256 * t + 1024 and w[n - 256 * t] > 0}
+        assert hit == exp, (n, hit, exp)
+
+
+@pytest.mark.parametrize('wind,ov,n', [(1200, 2, 4800), (2048, 2, 8192), (64, 4, 1000), (1024, 4, 2048)])
+def test_stft_other_windows(wind, ov, n):
+    from spatialaudiogen_b200 import myutils
+    x = np.random.RandomState(0).randn(2, 3, n).astype(np.float32)
+    s = myutils.stft(cu(x), wind, ov)
+    ref = O.stft(torch.as_tensor(x).double(), wind, ov)
+    assert tuple(s.shape) == tuple(ref.shape)
+    assert _rel(torch.view_as_real(s), torch.view_as_real(ref)) < 3e-6
+
+
+def test_istft_matches_oracle_and_gain_half():
+    from spatialaudiogen_b200 import myutils
+    a = _audio(2, 6)[:, :, 0]
+    s = myutils.stft(cu(a), 1024, 4)[:, 89:117]
+    y = myutils.istft(s.contiguous(), 4)
+    assert tuple(y.shape) == (2, 6400)
+    assert _rel(y, 0.5 * torch.as_tensor(a[:, 23552:29952])) < 2e-6
+    g = torch.Generator().manual_seed(0)
+    z = torch.complex(torch.randn(3, 2, 30, 1024, generator=g), torch.randn(3, 2, 30, 1024, generator=g))
+    y = myutils.istft(z.cuda(), 4)
+    ref = O.istft(z.to(torch.complex128), 4)
+    assert tuple(y.shape) == tuple(ref.shape) == (3, 2, 6400)     # 30 frames -> 28 used (myutils.py:187-188)
+    assert _rel(y, ref) < 3e-6
+
+
+def test_stft_rejects_short_input():
+    from spatialaudiogen_b200 import myutils
+    with pytest.raises(ValueError):
+        myutils.stft(torch.zeros(1, 1500).cuda(), 1024, 4)
+
+
+# ------------------------------------------------------------------------------------------------ dense stages
+def _conv_case(L, n, h, w, cin, kh, kw, cout, sh, sw, same, bias, relu, prec, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = torch.randn(kh, kw, cin, cout, generator=g) / np.sqrt(kh * kw * cin)
+    b = torch.randn(cout, generator=g) if bias else None
+    ref = O.tf_conv2d(x.double(), wt.double(), (sh, sw), 'SAME' if same else 'VALID')
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    y = torch.empty(tuple(ref.shape), dtype=torch.float32, device='cuda')
+    xc, wc, bc = x.cuda(), wt.cuda(), (b.cuda() if bias else None)
+    L.check(L.lib().sag_conv2d(L.ptr(xc), n, h, w, cin, L.ptr(wc), kh, kw, cout, sh, sw, int(same), L.ptr(bc), int(relu),
+                               L.ptr(y), prec, L.stream()))
+    torch.cuda.synchronize()
+    return _rel(y, ref)
+
+
+CONV_CASES = [
+    (2, 127, 1024, 1, 7, 16, 32, 4, 8, 0, 1, 1),      # audio conv1
+    (2, 31, 127, 32, 3, 7, 64, 2, 4, 0, 1, 1),        # audio conv2
+    (2, 7, 14, 128, 3, 5, 256, 1, 1, 0, 1, 1),        # audio conv4
+    (1, 64, 96, 3, 7, 7, 64, 2, 2, 1, 0, 0),          # resnet conv1 (SAME 2,3)
+    (2, 14, 28, 64, 3, 3, 128, 2, 2, 1, 0, 0),        # 3x3/2 SAME (0,1)
+    (2, 14, 28, 64, 3, 3, 64, 1, 1, 1, 0, 0),         # 3x3/1 SAME
+    (2, 14, 28, 64, 1, 1, 128, 2, 2, 1, 0, 0),        # shortcut 1x1/2
+    (1, 5, 7, 5, 3, 3, 7, 1, 2, 1, 1, 0),             # ragged channels
+    (1, 9, 9, 16, 2, 4, 40, 1, 1, 0, 1, 1),           # even kernel, Cout not multiple of 32
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv2d_fp32(case):
+    assert _conv_case(_L(), *case, prec=0) < 2e-5
+
+
+def _deconv_case(L, n, h, w, cin, kh, kw, cout, sh, sw, relu, prec, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = torch.randn(kh, kw, cout, cin, generator=g) / np.sqrt(kh * kw * cin / (sh * sw))
+    b = torch.randn(cout, generator=g)
+    ref = O.tf_conv2d_transpose_valid(x.double(), wt.double(), (sh, sw)) + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    y = torch.full(tuple(ref.shape), float('nan'), dtype=torch.float32, device='cuda')
+    xc, wc, bc = x.cuda(), wt.cuda(), b.cuda()
+    L.check(L.lib().sag_deconv2d(L.ptr(xc), n, h, w, cin, L.ptr(wc), kh, kw, cout, sh, sw, L.ptr(bc), int(relu), L.ptr(y),
+                                 prec, L.stream()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any()
+    return _rel(y, ref)
+
+
+DECONV_CASES = [
+    (2, 3, 6, 1024, 3, 5, 256, 1, 1, 1),      # deconv5
+    (2, 7, 14, 256, 3, 5, 64, 2, 2, 1),       # deconv3
+    (1, 15, 31, 128, 3, 7, 32, 2, 4, 1),      # deconv2
+    (1, 8, 20, 64, 7, 16, 32, 4, 8, 0),       # deconv1 geometry (small)
+    (1, 4, 5, 3, 2, 2, 5, 3, 3, 0),           # stride > kernel (holes get only the bias)
+]
+
+
+@pytest.mark.parametrize('case', DECONV_CASES)
+def test_deconv2d_fp32(case):
+    assert _deconv_case(_L(), *case, prec=0) < 2e-5
+
+
+def test_fc_fp32():
+    L = _L()
+    g = torch.Generator().manual_seed(0)
+    for rows, cin, cout, relu in [(6, 3072, 1024, 1), (2, 12544, 512, 1), (6, 512, 99, 0), (1, 7, 3, 0)]:
+        x = torch.randn(rows, cin, generator=g)
+        w = torch.randn(cin, cout, generator=g) / np.sqrt(cin)
+        b = torch.randn(cout, generator=g)
+        ref = x.double() @ w.double() + b.double()
+        if relu:
+            ref = torch.relu(ref)
+        y = torch.empty(rows, cout, device='cuda')
+        xc, wc, bc = x.cuda(), w.cuda(), b.cuda()
+        L.check(L.lib().sag_fc(L.ptr(xc), rows, cin, L.ptr(wc), cout, L.ptr(bc), relu, L.ptr(y), 0, L.stream()))
+        assert _rel(y, ref) < 2e-5
+
+
+def test_batchnorm_train_and_maxpool():
+    L = _L()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 10, 12, 64, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+    res = torch.randn(3, 10, 12, 64, generator=g)
+    ref = torch.relu(O.tf_batch_norm_train(x.double(), gamma.double(), beta.double()) + res.double())
+    y = torch.empty_like(x, device='cuda')
+    scratch = torch.empty(4 * 64, dtype=torch.float64, device='cuda')
+    xc, gc, bc, rc = x.cuda(), gamma.cuda(), beta.cuda(), res.cuda()
+    L.check(L.lib().sag_batchnorm_train(L.ptr(xc), 3 * 10 * 12, 64, L.ptr(gc), L.ptr(bc), L.ptr(rc), 1, L.ptr(y),
+                                        C.c_void_p(scratch.data_ptr()), L.stream()))
+    assert _rel(y, ref) < 1e-5
+    for (h, w) in [(112, 224), (7, 9), (8, 8)]:
+        x = torch.randn(2, h, w, 64, generator=g)
+        ref = O.tf_max_pool_same_3x3s2(x)
+        y = torch.empty(tuple(ref.shape), device='cuda')
+        xc = x.cuda()
+        L.check(L.lib().sag_maxpool_3x3s2_same(L.ptr(xc), 2, h, w, 64, L.ptr(y), L.stream()))
+        assert torch.equal(y.cpu(), ref)
+
+
+def test_mix_matches_reference_decode():
+    L = _L()
+    g = torch.Generator().manual_seed(0)
+    B, K, T = 2, 32, 4800
+    xs = torch.randn(B, K, T, generator=g)
+    loc = torch.randn(B, 3, 3 * (K + 1), generator=g)
+    w = loc.reshape(B, 3, 3, 1, K + 1).unsqueeze(2).repeat(1, 1, T // 3, 1, 1, 1).reshape(B, T, 3, 1, K + 1)
+    ref = (w[..., :-1].double() * xs.double().permute(0, 2, 1)[:, :, None, None, :]).sum(4).sum(3) + w[..., -1].double()[:, :, :, 0]
+    y = torch.empty(B, T, 3, device='cuda')
+    xc, lc = xs.cuda(), loc.cuda()
+    L.check(L.lib().sag_mix(L.ptr(xc), L.ptr(lc), B, K, T, 3, L.ptr(y), L.stream()))
+    assert _rel(y, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ whole forward
+def _models(encoders, separation, seed, B, precision='fp32', resnet=None, stress=True):
+    from spatialaudiogen_b200 import SptAudioGen
+    W = Wt.init_weights(encoders, separation=separation, seed=seed, stress=stress, resnet_npy=resnet)
+    ref = O.SptAudioGen(W, encoders=encoders, separation=separation, dtype=torch.float64)
+    m = SptAudioGen(1, encoders=encoders, separation=separation, precision=precision).load_weights(W)
+    return ref, m
+
+
+def test_forward_audio_only_fp32_parity():
+    """BASELINE config 1 shape (audio-only encoder, random weights) at B=1 and B=3; <= 1e-3 rel required,
+    the fp32 path lands around 1e-5."""
+    ref, m = _models(['audio'], 'unet_mask', 3, 1)
+    for B in (1, 3):
+        a = _audio(B, 10 + B)
+        y = m.inference_ops(cu(a))
+        yr = ref.inference_ops(a)
+        assert tuple(y.shape) == (B, 4800, 3)
+        assert _rel(y, yr) < 1e-4
+        assert _rel(m.sep_channels, ref.sep_channels) < 1e-4
+        assert _rel(m.ends['separation/mask_logits'], ref.ends['separation/mask_logits'][:, 0]) < 1e-4
+        for l in range(6):
+            assert _rel(m.ends['audio_encoder/%d' % l], ref.ends['audio_encoder'][l]) < 1e-4, l
+        assert _rel(m.ends['bottleneck'], ref.ends['bottleneck']) < 1e-4
+
+
+def test_forward_skip_unused_is_bit_identical_to_full():
+    ref, m = _models(['audio'], 'unet_mask', 5, 2)
+    a = cu(_audio(2, 21))
+    y0 = m.inference_ops(a).clone()
+    m.set_option('skip_unused', 0)
+    y1 = m.inference_ops(a).clone()
+    assert torch.equal(y0, y1)
+    s = m.ends['stft']
+    assert tuple(s.shape) == (2, 1, 200, 1024)
+    assert _rel(torch.view_as_real(s), torch.view_as_real(O.stft(torch.as_tensor(_audio(2, 21)).double().permute(0, 2, 1), 1024, 4))) < 2e-6
+
+
+def test_forward_no_separation():
+    ref, m = _models(['audio'], 'none', 7, 2)
+    a = _audio(2, 22)
+    assert _rel(m.inference_ops(cu(a)), ref.inference_ops(a)) < 1e-4
+
+
+def test_forward_audio_video_fp32_parity():
+    """BASELINE config 2 shape (audio+video, batch-statistics BN) at a small batch."""
+    ref, m = _models(['audio', 'video'], 'unet_mask', 9, 2)
+    a, v = _audio(2, 23), _video(2, 24)
+    y = m.inference_ops(cu(a), video=cu(v))
+    yr = ref.inference_ops(a, video=v)
+    assert _rel(m.ends['video_encoder/conv2_1'], ref.ends['video_encoder/conv2_1']) < 1e-4
+    assert _rel(m.ends['video_encoder/conv5_2'], ref.ends['video_encoder/conv5_2']) < 1e-3
+    assert _rel(m.ends['bottleneck'], ref.ends['bottleneck']) < 1e-3
+    assert _rel(y, yr) < 1e-3
+
+
+def test_forward_audio_video_flow_fp32_parity():
+    ref, m = _models(['audio', 'video', 'flow'], 'unet_mask', 11, 2)
+    a, v, fl = _audio(2, 25), _video(2, 26), _flow(2, 27)
+    y = m.inference_ops(cu(a), video=cu(v), flow=cu(fl))
+    yr = ref.inference_ops(a, video=v, flow=fl)
+    assert _rel(y, yr) < 1e-3
+
+
+def test_forward_errors():
+    from spatialaudiogen_b200 import SptAudioGen
+    with pytest.raises(ValueError):
+        SptAudioGen(1, encoders=['audio'], separation='bogus')
+    m = SptAudioGen(1, encoders=['audio'], separation='unet_mask')
+    with pytest.raises(RuntimeError):
+        m.inference_ops(torch.zeros(1, 52799, 1).cuda())           # weights not loaded
+    W = Wt.init_weights(['audio'])
+    bad = dict(W)
+    bad['audio_encoder/conv1/weights'] = np.zeros((7, 16, 2, 32), np.float32)
+    with pytest.raises(ValueError):
+        m.load_weights(bad)
+    m.load_weights(W)
+    with pytest.raises(ValueError):
+        m.inference_ops(torch.zeros(1, 1000, 1).cuda())
+    with pytest.raises(TypeError):
+        m.forward_into(torch.zeros(1, 52799, 1), None, None, torch.zeros(1, 4800, 3).cuda())   # CPU tensor: no CPU path
+
+
+# ------------------------------------------------------------------------------------------------ metrics
+def test_metrics_match_oracle():
+    from spatialaudiogen_b200 import SptAudioGen
+    from spatialaudiogen_b200 import metrics as M
+    rng = np.random.RandomState(0)
+    B = 5
+    gt = (rng.randn(B, 4800, 3) * 0.1).astype(np.float32)
+    pred = (gt + rng.randn(B, 4800, 3) * 0.03).astype(np.float32)
+    mask = np.ones((B, 3), np.float32)
+    mask[1, 1] = 0
+    ref = O.SptAudioGen({}, encoders=['audio'], separation='unet_mask', dtype=torch.float64)
+    mr, stft_r, lsd_r, mse_r, snr_r = ref.evaluation_ops(pred, gt, None, mask)
+    m = SptAudioGen(1, encoders=['audio'], separation='unet_mask')
+    mm, stft_g, lsd_g, mse_g, snr_g = m.evaluation_ops(cu(pred), cu(gt), None, cu(mask))
+    assert _rel(stft_g, stft_r) < 1e-4
+    assert _rel(lsd_g, lsd_r) < 1e-4
+    assert _rel(mse_g, mse_r) < 1e-5
+    assert _rel(snr_g, snr_r) < 1e-5
+    for k in mr:
+        assert abs(float(mm[k]) - float(mr[k])) <= 1e-4 * max(1.0, abs(float(mr[k]))), k
+    env_r = np.stack([O.compute_envelope_dist(pred[b], gt[b]) for b in range(B)])
+    assert _rel(m.last_eval['env'], env_r) < 1e-4
+    amp = m.last_eval['amp'].cpu().numpy()
+    assert np.array_equal(amp[:, 0], np.abs(pred).reshape(B, -1).max(1)) and np.array_equal(amp[:, 1], np.abs(gt).reshape(B, -1).max(1))
+    # spherical-harmonic RMS maps (84 directions at 30 degrees; 37x72 at 5 degrees)
+    ambi = (rng.randn(B, 4800, 4) * 0.1).astype(np.float32)
+    for res, shape in ((30., (7, 12)), (5., (37, 72))):
+        g = M.ambix_rms_map(cu(ambi), res)
+        assert tuple(g.shape) == (B,) + shape
+        r = np.stack([O.ambix_rms_map(ambi[b], res) for b in range(B)])
+        assert _rel(g, r) < 1e-5
