@@ -106,10 +106,23 @@ int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr,
 int sag_num_tensors(const sag_handle* h);
 int sag_tensor_name(const sag_handle* h, int i, char* buf, int buflen);
 /* options: "skip_unused" (default 1: STFT frames / mask rows that cannot reach the cropped output are not
- * computed; the result is bit-identical), "precision" (SAG_PREC_*). */
+ * computed; the result is bit-identical), "precision" (SAG_PREC_*), "profile" (0/1, see sag_get_profile). */
 int sag_set_option(sag_handle* h, const char* key, int value);
 /* how many kernels the last sag_forward launched (bench.py gpu_launches) */
 int sag_last_launch_count(const sag_handle* h);
+/* With option "profile" = 1 every launch group of sag_forward is bracketed by CUDA events on the caller's stream.
+ * Sums over the last forward for one category: 0 conv, 1 transposed conv, 2 fully connected (the three share the
+ * contraction kernel), 3 STFT, 4 inverse STFT, 5 BN / pooling passes, 6 mixing.  flops / bytes are the algorithmic
+ * figures of DESIGN.md (executed work only).  Synchronises on the recorded events. */
+#define SAG_PROF_CONV 0
+#define SAG_PROF_DECONV 1
+#define SAG_PROF_FC 2
+#define SAG_PROF_STFT 3
+#define SAG_PROF_ISTFT 4
+#define SAG_PROF_POINTWISE 5
+#define SAG_PROF_MIX 6
+#define SAG_PROF_NCAT 7
+int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, double* bytes, int* launches);
 
 /* ---- stage entry points (tests / ncu); each replaces the named reference op -------------------- */
 /* myutils.stft (myutils.py:119-147): x (rows,n_samples) -> out complex (rows, n_frames_out, wind) for frames

@@ -82,6 +82,7 @@ int sag_destroy(sag_handle* h) {
   if (h == nullptr) return SAG_OK;
   for (auto& kv : h->weights) free_tensor(kv.second);
   for (auto& kv : h->packed) free_tensor(kv.second);
+  h->prof.clear();
   delete h;
   return SAG_OK;
 }
@@ -96,6 +97,7 @@ int sag_set_option(sag_handle* h, const char* key, int value) {
   SAG_REQUIRE(h != nullptr && key != nullptr, SAG_EINVAL, "sag_set_option: NULL argument");
   std::string k(key);
   if (k == "skip_unused") { h->skip_unused = value ? 1 : 0; return SAG_OK; }
+  if (k == "profile") { h->prof.on = value != 0; if (!value) h->prof.clear(); return SAG_OK; }
   if (k == "precision") {
     SAG_REQUIRE(value >= SAG_PREC_FP32 && value <= SAG_PREC_BF16X3, SAG_EINVAL, "unknown precision %d", value);
     h->cfg.precision = value;
@@ -218,6 +220,25 @@ int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr,
 }
 
 int sag_last_launch_count(const sag_handle* h) { return h ? h->last_launches : SAG_EINVAL; }
+
+int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, double* bytes, int* launches) {
+  SAG_REQUIRE(h != nullptr, SAG_EINVAL, "sag_get_profile: NULL handle");
+  SAG_REQUIRE(category >= 0 && category < PROF_NCAT, SAG_EINVAL, "sag_get_profile: category %d outside [0,%d)", category, (int)PROF_NCAT);
+  double t = 0, f = 0, b = 0;
+  int n = 0;
+  for (auto& r : h->prof.recs) {
+    if (r.cat != category) continue;
+    SAG_CHECK_CUDA(cudaEventSynchronize(r.e1));
+    float dt = 0.f;
+    SAG_CHECK_CUDA(cudaEventElapsedTime(&dt, r.e0, r.e1));
+    t += dt; f += r.flops; b += r.bytes; ++n;
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (bytes) *bytes = b;
+  if (launches) *launches = n;
+  return SAG_OK;
+}
 
 // ---- stage entry points --------------------------------------------------------------------------------------
 int sag_stft(const float* x, int rows, int n_samples, int wind, int n_overlap, int frame0, int n_frames_out,

@@ -46,6 +46,22 @@ extern thread_local int g_launch_count;   // kernels launched by this thread sin
     SAG_CHECK_CUDA(cudaGetLastError());          \
   } while (0)
 
+// ---- optional per-launch CUDA-event profiling (sag_set_option "profile"): bench.py's roofline numbers ----
+enum ProfCat { PROF_CONV = 0, PROF_DECONV, PROF_FC, PROF_STFT, PROF_ISTFT, PROF_POINTWISE, PROF_MIX, PROF_NCAT };
+struct ProfRec { int cat; double flops; double bytes; cudaEvent_t e0, e1; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  void clear();
+};
+extern thread_local Profiler* g_prof;   // set by forward() while profiling is enabled
+struct ProfScope {                      // records an event pair around the launches issued in its lifetime
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(int cat, double flops, double bytes, cudaStream_t s);
+  ~ProfScope();
+};
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS) gather_gemm_ffma_kernel(const float*
 
 int launch_gather_gemm_ffma(const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
                             cudaStream_t st) {
-  SAG_REQUIRE(g.T >= 1 && g.T <= kMaxTaps, SAG_EINVAL, "gather_gemm: %d taps unsupported (max %d)", g.T, kMaxTaps);
+  SAG_REQUIRE(g.T >= 0 && g.T <= kMaxTaps, SAG_EINVAL, "gather_gemm: %d taps unsupported (max %d)", g.T, kMaxTaps);
   int64_t M = (int64_t)g.N * g.PH * g.PW;
   if (M == 0) return SAG_OK;
   bool veca = (g.Cin % 8 == 0) && (g.x_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);

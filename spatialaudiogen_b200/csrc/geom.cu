@@ -18,6 +18,28 @@ void set_error(const char* fmt, ...) {
 
 const char* last_error_cstr() { return g_err.c_str(); }
 
+thread_local Profiler* g_prof = nullptr;
+
+void Profiler::clear() {
+  for (auto& r : recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  recs.clear();
+}
+
+ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t s) : st(s) {
+  if (g_prof == nullptr || !g_prof->on) return;
+  ProfRec r;
+  r.cat = cat; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess) return;
+  if (cudaEventCreate(&r.e1) != cudaSuccess) { cudaEventDestroy(r.e0); return; }
+  cudaEventRecord(r.e0, st);
+  g_prof->recs.push_back(r);
+  idx = (int)g_prof->recs.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (idx >= 0 && g_prof != nullptr) cudaEventRecord(g_prof->recs[idx].e1, st);
+}
+
 // tf.nn.convolution (core.py:206): cross-correlation, VALID or TF-SAME (pad_before = total/2).
 int make_conv_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh, int sw,
                    int same_pad, int64_t y_ld, int* oh, int* ow) {
@@ -58,7 +80,8 @@ int make_deconv_phase_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t 
   const int OHf = (h - 1) * sh + kh, OWf = (w - 1) * sw + kw;
   if (row1 > OHf) row1 = OHf;
   int ty = (kh - py + sh - 1) / sh, tx = (kw - px + sw - 1) / sw;      // taps of this phase
-  if (ty <= 0 || tx <= 0) return 1;
+  // stride > kernel: phases no tap reaches still exist in the output and receive the bias only (T == 0)
+  if (ty <= 0 || tx <= 0) { ty = 0; tx = 0; }
   SAG_REQUIRE(ty * tx <= kMaxTaps, SAG_EINVAL, "deconv phase has too many taps");
   // rows o = py + sh*u in [row0,row1)
   int u0 = (row0 - py + sh - 1) / sh;

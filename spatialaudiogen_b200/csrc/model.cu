@@ -151,6 +151,7 @@ struct Fwd {
   Arena& ar;
   cudaStream_t st;
   int prec;
+  int cat = PROF_CONV;
   bool dry() const { return ar.dry; }
 
   const float* W(const std::string& name, int* err) {
@@ -191,6 +192,8 @@ struct Fwd {
     const float* b = bias ? W(scope + "/biases", &err) : nullptr;
     SAG_TRY(err);
     Epilogue ep{b, relu, ssum, ssqs};
+    const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
+    ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
     return launch_gather_gemm(prec, x, w, y, g, ep, st);
   }
 
@@ -211,6 +214,8 @@ struct Fwd {
                                        y_sw, y_sc);
         if (r == 1) continue;
         SAG_TRY(r);
+        const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
+        ProfScope ps(PROF_DECONV, 2.0 * M * K * cout, 4.0 * (M * cin / (sh * sw) + K * cout + M * cout), st);
         SAG_TRY(launch_gather_gemm(prec, x, w, y, g, ep, st));
       }
     return SAG_OK;
@@ -220,7 +225,11 @@ struct Fwd {
   int fc(const float* x, int rows, int in, int64_t x_ld, const std::string& scope, int out, int relu, float* y,
          int64_t y_ld) {
     int oh, ow;
-    return conv(x, 1, 1, rows, in, x_ld, scope, 1, 1, out, 1, 1, 0, true, relu, y, y_ld, nullptr, nullptr, &oh, &ow);
+    const int saved = cat;
+    cat = PROF_FC;
+    int r = conv(x, 1, 1, rows, in, x_ld, scope, 1, 1, out, 1, 1, 0, true, relu, y, y_ld, nullptr, nullptr, &oh, &ow);
+    cat = saved;
+    return r;
   }
 };
 
@@ -265,7 +274,10 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
   float* cur = ar.alloc<float>((int64_t)B * ph * pw * 64);
-  if (!ar.dry) SAG_TRY(launch_bn_relu_maxpool(c1, b1.scale, b1.shift, B, oh, ow, 64, cur, st));
+  if (!ar.dry) {
+    ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * 64 * ((double)oh * ow + (double)ph * pw), st);
+    SAG_TRY(launch_bn_relu_maxpool(c1, b1.scale, b1.shift, B, oh, ow, 64, cur, st));
+  }
   int ch = ph, cw = pw, cc = 64;
 
   for (const BlockDef& b : kBlocks) {
@@ -290,11 +302,17 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     SAG_TRY(f.conv(cur, B, ch, cw, cc, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, b.cout, s1.sum, s1.sqs,
                    &oh, &ow));
     SAG_TRY(bn_finalize(q + "/conv_1", s1, b.cout, npix));
-    if (!ar.dry) SAG_TRY(launch_bn_apply(r1, s1.scale, s1.shift, nullptr, 1, a1, npix, b.cout, st));
+    if (!ar.dry) {
+      ProfScope ps(PROF_POINTWISE, 0, 8.0 * npix * b.cout, st);
+      SAG_TRY(launch_bn_apply(r1, s1.scale, s1.shift, nullptr, 1, a1, npix, b.cout, st));
+    }
     SAG_TRY(f.conv(a1, B, nh, nw, b.cout, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, b.cout, s2.sum,
                    s2.sqs, &oh, &ow));
     SAG_TRY(bn_finalize(q + "/conv_2", s2, b.cout, npix));
-    if (!ar.dry) SAG_TRY(launch_bn_apply(r2, s2.scale, s2.shift, shortcut, 1, out, npix, b.cout, st));
+    if (!ar.dry) {
+      ProfScope ps(PROF_POINTWISE, 0, 12.0 * npix * b.cout, st);
+      SAG_TRY(launch_bn_apply(r2, s2.scale, s2.shift, shortcut, 1, out, npix, b.cout, st));
+    }
     f.tap(scope + "/" + b.name, out, {B, nh, nw, b.cout});
     cur = out; ch = nh; cw = nw; cc = b.cout;
   }
@@ -312,7 +330,12 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   SAG_REQUIRE(B > 0, SAG_EINVAL, "forward: batch must be positive");
   SAG_REQUIRE(c.enc_audio, SAG_EUNSUPPORTED, "the audio encoder is required (model.py:207 reads x_enc[AUDIO] unconditionally)");
   SAG_REQUIRE(c.ambi_order == 1, SAG_EUNSUPPORTED, "only first-order ambisonics is supported");
-  if (!ar.dry) { h->ends.clear(); h->end_order.clear(); g_launch_count = 0; }
+  if (!ar.dry) {
+    h->ends.clear(); h->end_order.clear(); g_launch_count = 0;
+    h->prof.clear();
+    g_prof = &h->prof;
+  }
+  struct ProfGuard { ~ProfGuard() { g_prof = nullptr; } } prof_guard;   // stage entry points never see a stale profiler
   const bool unet = c.separation == SAG_SEP_UNET_MASK;
   const int K = unet ? c.sep_num_tracks : 1;
   const int wind = d.wind_size, hop = wind / 4;
@@ -331,6 +354,8 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   }
   float* mag = ar.alloc<float>((int64_t)B * n_enc * wind);
   if (!ar.dry) {
+    ProfScope ps(PROF_STFT, 5.0 * wind * std::log2((double)wind) * B * (full ? d.n_stft_frames : n_enc),
+                 4.0 * B * ((double)d.snd_size + (double)n_enc * wind + (unet ? 2.0 * n_msk * wind : 0.0)), st);
     if (full)
       SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag, st));
     else
@@ -458,13 +483,18 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
                                          sizeof(float) * nr * OW, sizeof(float) * n_msk * OW, (size_t)B * K,
                                          cudaMemcpyDeviceToDevice, st));
       }
+      ProfScope ps(PROF_ISTFT, 5.0 * wind * std::log2((double)wind) * B * K * n_msk,
+                   4.0 * B * ((double)K * n_msk * wind + 2.0 * n_msk * wind + (double)K * T), st);
       SAG_TRY(launch_istft(S2, m2, 1, B, K, n_msk, wind, 4, d.final_crop, T, x_sep, st));
     }
   }
   f.tap("separation/all_channels", x_sep, {B, 1, K, T});
 
   // ---- decode (model.py:424-432) -------------------------------------------------------------------------------
-  if (!ar.dry) SAG_TRY(launch_mix(x_sep, loc, B, K, T, nt, out, st));
+  if (!ar.dry) {
+    ProfScope ps(PROF_MIX, 6.0 * B * K * T, 4.0 * B * ((double)K * T + 3.0 * T), st);
+    SAG_TRY(launch_mix(x_sep, loc, B, K, T, nt, out, st));
+  }
   if (!ar.dry) h->last_launches = g_launch_count;
   return SAG_OK;
 }

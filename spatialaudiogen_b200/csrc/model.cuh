@@ -48,6 +48,7 @@ struct sag_handle {
   std::vector<std::string> end_order;
   int last_launches = 0;
   int finalized = 0;
+  sag::Profiler prof;    // per-launch event timing of the last forward (option "profile")
   int skip_unused = 1;   // skip mask rows / frames that cannot reach the cropped output (bit-identical result)
 };
 
