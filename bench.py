@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- ambisonic audio seconds per second of the spatialaudiogen inference hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision P] [--encoders a,v[,f]]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (sag_forward: STFT -> audio/video towers -> U-Net decoder -> masked iSTFT ->
+32->3 mixing, reference model.py:356-434 behind deploy.py:141 / eval.py:145) over one batch of B=32 synthetic
+0.1 s windows (52 799 mono samples @48 kHz + one 224x448x3 RGB frame each), followed by the per-window evaluation
+metrics (reference model.py:110-154, eval.py:145 fetches both).  At N>1 every rank processes its own batches (whole
+batches shard, weights replicate: SURVEY.md 8e) and ONE all-gather of the per-window metric rows closes the timed
+region.  value = 0.1 s x windows processed by all ranks / max-over-ranks device time.
+
+Lines printed (rank 0 only, one JSON object each run):
+  default arm      : value (inputs resident in HBM), e2e (host pinned buffers -> H2D -> forward -> D2H of the waveform,
+                     through SptAudioGen.inference_ops, the call a user makes), roofline of the dominant kernel family
+                     (dense contractions), cpu_baseline (the CPU oracle on this box's host cores, N=1 only).
+  --impl reference : the reference's CPU path.  TensorFlow 1.4 / python2 cannot be installed, so the
+                     stand-in is oracle/sag_oracle.py (PyTorch-CPU restatement of the TF graph) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = 'ambisonic_audio_seconds_per_second'
+UNIT = 'audio_s/s'
+SND_SIZE, SND_DUR, RATE = 52799, 4800, 48000
+FRAME = (224, 448)
+WINDOW_S = 0.1
+# executed / reference conv-stack FLOPs per window: A = 2.386, each ResNet tower 7.254 GFLOP
+CONV_GFLOP_REF = {'audio': 2.386365440, 'tower': 7.254245376}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--encoders', default='audio,video')
+    ap.add_argument('--precision', default=os.environ.get('SAG_BENCH_PRECISION', 'auto'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
+    ap.add_argument('--rotate', type=int, default=4, help='distinct input batches cycled through (L2 hygiene)')
+    return ap.parse_args()
+
+
+# ---- synthetic inputs (SURVEY.md 8d "Synthetic value distributions") ----------------------------------------------
+def synth_batch(B, encoders, seed):
+    rng = np.random.RandomState(seed)
+    t = np.arange(SND_SIZE)
+    phase = rng.uniform(0, 2 * np.pi, size=(B, 1))
+
+    def wave():
+        return np.clip(0.1 * rng.randn(B, SND_SIZE) + 0.3 * np.sin(2 * np.pi * 440. * t / RATE + phase), -1, 1).astype(np.float32)
+
+    out = {'audio': wave()[:, :, None]}
+    # targets: independently generated Y,Z,X for the centre 0.1 s (eval.py:70)
+    out['target'] = np.stack([wave()[:, RATE // 2:RATE // 2 + SND_DUR] for _ in range(3)], axis=2)
+    if 'video' in encoders:
+        out['video'] = (rng.randint(0, 256, size=(B, 1) + FRAME + (3,)).astype(np.float32) / 255. - 0.5).astype(np.float32)
+    if 'flow' in encoders:
+        mag = rng.uniform(0, 20, size=(B, 1) + FRAME).astype(np.float32)
+        th = rng.uniform(0, 2 * np.pi, size=(B, 1) + FRAME).astype(np.float32)
+        out['flow'] = np.stack([mag * np.cos(th), mag * np.sin(th), mag], axis=-1).astype(np.float32)
+    return out
+
+
+def conv_gflop_per_window(encoders):
+    return CONV_GFLOP_REF['audio'] + CONV_GFLOP_REF['tower'] * (('video' in encoders) + ('flow' in encoders))
+
+
+# ---- clocks sampler (B200_PROFILING.md "clocks DURING the timed region") ------------------------------------------
+class ClockSampler(object):
+    Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix='sag_clocks_', suffix='.csv')
+        self.proc = None
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self, t0, t1):
+        """Median SM clock / reasons over wall interval [t0, t1] (falls back to all samples if none land inside)."""
+        res = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return res
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        rows = []
+        try:
+            import datetime
+            for line in open(self.path):
+                p = [s.strip() for s in line.split(',')]
+                if len(p) < 10:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(p[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                    rows.append((ts, float(p[2]), float(p[3]), p[6], p[7], p[8], p[9]))
+                except Exception:
+                    continue
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        inside = [r for r in rows if t0 <= r[0] <= t1 + 0.1]
+        use = inside if inside else rows
+        if not use:
+            return res
+        res['samples'] = len(inside)
+        res['sm_mhz'] = float(np.median([r[1] for r in use]))
+        res['sm_max_mhz'] = float(max(r[2] for r in use))
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for k, n in enumerate(names):
+            if any(r[3 + k].lower().startswith('active') for r in use):
+                res['reasons'].append(n)
+        return res
+
+
+# ---- the CPU arm: oracle port of the reference's TF1 CPU deploy path ----------------------------------------------
+def oracle_model(encoders, seed=1234):
+    from oracle import sag_oracle as O                    # bench.py's cpu legs are allowed to execute the oracle
+    from spatialaudiogen_b200 import weights as Wt
+    W = Wt.init_weights(encoders, separation='unet_mask', seed=seed)
+    return O.SptAudioGen(W, encoders=encoders, separation='unet_mask')
+
+
+def cpu_time_forward(model, batch, encoders, b):
+    kw = {k: batch[k][:b] for k in ('video', 'flow') if k in encoders}
+    t = time.perf_counter()
+    model.inference_ops(batch['audio'][:b], **kw)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(encoders, B, budget_s):
+    """Oracle forward at the bench batch size on all host threads; median of the timed forwards."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = oracle_model(encoders)
+    batch = synth_batch(B, encoders, 99)
+    cpu_time_forward(m, batch, encoders, B)                # warm-up (oneDNN primitive caches)
+    ts = []
+    t_start = time.perf_counter()
+    while len(ts) < 3 or (time.perf_counter() - t_start < budget_s and len(ts) < 50):
+        ts.append(cpu_time_forward(m, batch, encoders, B))
+    med = float(np.median(ts))
+    return {'value': WINDOW_S * B / med, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d forwards of one batch of %d windows (%s), median %.3f s each; oracle/sag_oracle.py '
+                      '(PyTorch-CPU fp32 restatement; TF 1.4 is not installable)' % (len(ts), B, '+'.join(encoders), med)}
+
+
+def run_reference(args, encoders):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    torch.set_num_threads(os.cpu_count() or 1)
+    B = args.batch
+    m = oracle_model(encoders)
+    batch = synth_batch(B, encoders, 1234)
+    t32 = cpu_time_forward(m, batch, encoders, B)          # untimed probe (also warms caches)
+    t32 = min(t32, cpu_time_forward(m, batch, encoders, B))
+    total = args.steps + args.warmup
+    b = B
+    if total * t32 > 150.0:                                # bound the whole run to a few minutes
+        b = max(1, int(B * 150.0 / (total * t32)))
+    for _ in range(args.warmup):
+        cpu_time_forward(m, batch, encoders, b)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_time_forward(m, batch, encoders, b)
+    el = time.perf_counter() - t
+    val = WINDOW_S * b * args.steps / el
+    sample = 'each step = oracle forward of %d of the %d windows of a batch (%s) on %d host threads' % (
+        b, B, '+'.join(encoders), torch.get_num_threads())
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(encoders, B, 'fp32', args, 1),
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+            'note': 'reference = TF1.4 CPU graph; not installable here, so the PyTorch-CPU oracle port stands in'}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(encoders, B, precision, args, world):
+    return {'workload': 'configs[1]: %s encoders, unet_mask separation, batch %d, 0.1 s @48 kHz mono + 224x448 RGB per window'
+                        % ('+'.join(encoders), B),
+            'batch_per_gpu': B, 'global_batch': B * world, 'encoders': encoders, 'precision': precision,
+            'weights': 'xavier random init (seed 1234), resnet towers random (no checkpoint offline)',
+            'step': 'sag_forward + sag_metrics over one batch',
+            'l2': 'inputs rotate over %d distinct batches and each step streams >1 GB of activations through the '
+                  'workspace (> 126 MB L2)' % args.rotate,
+            'parallelism': 'clip-sharded dp%d, one all-gather of metric rows' % world}
+
+
+# ---- our arm -------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    encoders = [e.strip() for e in args.encoders.split(',') if e.strip()]
+    if args.impl == 'reference':
+        return run_reference(args, encoders)
+
+    import torch.distributed as dist
+    from spatialaudiogen_b200 import SptAudioGen, weights as Wt, metrics as M, _lib as L
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: libsag.so has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch
+    precision = args.precision
+    if precision == 'auto':
+        precision = L.default_precision() if hasattr(L, 'default_precision') else 'fp32'
+    model = SptAudioGen(1, encoders=encoders, separation='unet_mask', precision=precision, device=dev)
+    model.load_weights(Wt.init_weights(encoders, separation='unet_mask', seed=1234))
+
+    # R distinct synthetic batches, resident in HBM (value) and in pinned host memory (e2e)
+    R = max(1, args.rotate)
+    host, devb = [], []
+    for r in range(R):
+        b = synth_batch(B, encoders, 1234 + 1000 * rank + r)
+        hb = {k: torch.from_numpy(v).pin_memory() for k, v in b.items()}
+        host.append(hb)
+        devb.append({k: v.to(dev) for k, v in hb.items()})
+    out = torch.empty((B, SND_DUR, 3), dtype=torch.float32, device=dev)
+    out_host = torch.empty((B, SND_DUR, 3), dtype=torch.float32).pin_memory()
+    rows = torch.zeros((args.steps, B, 17), dtype=torch.float32, device=dev)    # 5x3 metrics + 2 amplitudes per window
+
+    def step(i, store=None):
+        d = devb[i % R]
+        model.forward_into(d['audio'], d.get('video'), d.get('flow'), out)
+        res = M.window_metrics(out, d['target'], RATE)
+        if store is not None:
+            store[:, 0:3], store[:, 3:6], store[:, 6:9] = res['stft'], res['lsd'], res['mse']
+            store[:, 9:12], store[:, 12:15], store[:, 15:17] = res['snr'], res['env'], res['amp']
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    if world > 1:                                        # warm the collective too
+        g = [torch.empty_like(rows) for _ in range(world)]
+        dist.all_gather(g, rows)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    time.sleep(0.3 if sampler else 0.0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i, rows[i])
+    if world > 1:
+        dist.all_gather(g, rows)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop(w0, w1) if sampler else None
+    launches_fwd = int(L.lib().sag_last_launch_count(model._h))
+    launches = args.steps * (launches_fwd + 1)           # + metrics_kernel
+    value = WINDOW_S * B * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in, host waveform out, through the public operator API ----
+    def e2e_step(i):
+        h = host[i % R]
+        y = model.inference_ops(h['audio'], video=h.get('video'), flow=h.get('flow'))
+        out_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()         # the caller consumes the waveform every step (deploy.py:143)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    h2d = sum(int(v.numel() * 4) for k, v in host[0].items() if k in ('audio', 'video', 'flow'))
+    e2e = {'value': WINDOW_S * B * world * args.steps / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+           'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms2 / args.steps,
+           'api': 'SptAudioGen.inference_ops(pinned host tensors) + D2H of the (B,4800,3) waveform'}
+
+    # ---- roofline of the dominant kernel family, timed live with CUDA events on the launching stream ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    model.set_option('profile', 1)
+    cats = ['conv', 'deconv', 'fc', 'stft', 'istft', 'pointwise', 'mix']
+    agg = {c: [0.0, 0.0, 0.0, 0] for c in cats}
+    P = 3
+    import ctypes as C
+    for i in range(P):
+        d = devb[i % R]
+        model.forward_into(d['audio'], d.get('video'), d.get('flow'), out)
+        torch.cuda.synchronize()
+        for ci, c in enumerate(cats):
+            msv, fl, by, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+            L.check(L.lib().sag_get_profile(model._h, ci, C.byref(msv), C.byref(fl), C.byref(by), C.byref(n)))
+            agg[c][0] += msv.value / P
+            agg[c][1] += fl.value / P
+            agg[c][2] += by.value / P
+            agg[c][3] = n.value
+    model.set_option('profile', 0)
+    dense_ms = agg['conv'][0] + agg['deconv'][0] + agg['fc'][0]
+    dense_fl = agg['conv'][1] + agg['deconv'][1] + agg['fc'][1]
+    dense_n = agg['conv'][3] + agg['deconv'][3] + agg['fc'][3]
+    peak_tf = peaks.get('bf16_tflops_sustained')
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (measured)'
+    if peak_tf is None:
+        peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained)'
+    ach = dense_fl / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
+                'traffic': None, 'kernel': 'gather_gemm (conv / transposed-conv phases / FC contractions)',
+                'launches_per_step': dense_n, 'ms_per_step': dense_ms, 'executed_gflop_per_step': dense_fl / 1e9,
+                'reference_graph_gflop_per_step': conv_gflop_per_window(encoders) * B, 'peak_source': peak_src,
+                'breakdown_ms_per_step': {c: round(agg[c][0], 4) for c in cats},
+                'hbm_kernels_gbs': {c: (agg[c][2] / (agg[c][0] * 1e-3) / 1e9 if agg[c][0] > 0 else 0.0)
+                                    for c in ('stft', 'istft', 'pointwise', 'mix')},
+                'hbm_peak_gbs': peaks.get('hbm_gbs')}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'fp32': 'f32', 'tf32': 'tf32', 'bf16': 'bf16', 'bf16x3': 'bf16x3(f32-grade)'}.get(precision, precision),
+            'data': 'synthetic', 'config': workload_config(encoders, B, precision, args, world),
+            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(encoders, B, args.cpu_baseline_seconds)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -68,7 +68,6 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
   sag_handle* h = new (std::nothrow) sag_handle();
   SAG_REQUIRE(h != nullptr, SAG_ENOMEM, "sag_create: out of host memory");
   h->cfg = *cfg;
-  if (h->cfg.separation == SAG_SEP_NONE) h->cfg.sep_num_tracks = 1;                   // deploy.py:56
   int r = derive_dims(h->cfg, &h->dims);
   if (r == SAG_OK) r = build_expected(h);
   if (r == SAG_OK && cudaGetDevice(&h->device) != cudaSuccess) { set_error("cudaGetDevice failed"); r = SAG_ECUDA; }

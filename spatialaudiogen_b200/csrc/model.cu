@@ -337,7 +337,9 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   }
   struct ProfGuard { ~ProfGuard() { g_prof = nullptr; } } prof_guard;   // stage entry points never see a stale profiler
   const bool unet = c.separation == SAG_SEP_UNET_MASK;
-  const int K = unet ? c.sep_num_tracks : 1;
+  // NO_SEPARATION keeps params.sep_num_tracks localization weights per output channel; the single mono track
+  // broadcasts against them (model.py:430), i.e. the mono crop is replicated K times before the mixing.
+  const int K = c.sep_num_tracks;
   const int wind = d.wind_size, hop = wind / 4;
   const int T = d.snd_dur;
 
@@ -442,7 +444,7 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   float* x_sep = ar.alloc<float>((int64_t)B * K * T);
   if (!unet) {
     // NO_SEPARATION: x_sep = mono[snd_contx/2 : +snd_dur] (model.py:274-280); audio is (B,snd_size,1)
-    if (!ar.dry) SAG_TRY(launch_tile_rows(audio + d.snd_contx / 2, d.snd_size, x_sep, T, B, 1, T, st));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(audio + d.snd_contx / 2, d.snd_size, x_sep, T, B, K, T, st));
   } else {
     float* sf = ar.alloc<float>((int64_t)B * nt * 512);
     SAG_TRY(f.fc(feats, B * nt, D, D, "separation/fc-feats", 512, 1, sf, 512));
@@ -488,7 +490,8 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
       SAG_TRY(launch_istft(S2, m2, 1, B, K, n_msk, wind, 4, d.final_crop, T, x_sep, st));
     }
   }
-  f.tap("separation/all_channels", x_sep, {B, 1, K, T});
+  if (unet) f.tap("separation/all_channels", x_sep, {B, 1, K, T});
+  else f.tap("separation/all_channels", x_sep, {B, 1, 1, T}, (int64_t)K * T);
 
   // ---- decode (model.py:424-432) -------------------------------------------------------------------------------
   if (!ar.dry) {
