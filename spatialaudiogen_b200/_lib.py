@@ -12,6 +12,13 @@ LIB_PATH = os.path.join(HERE, 'libsag.so')
 SAG_PREC_FP32, SAG_PREC_TF32, SAG_PREC_BF16, SAG_PREC_BF16X3 = 0, 1, 2, 3
 PRECISIONS = {'fp32': SAG_PREC_FP32, 'tf32': SAG_PREC_TF32, 'bf16': SAG_PREC_BF16, 'bf16x3': SAG_PREC_BF16X3}
 SAG_SEP_NONE, SAG_SEP_UNET_MASK = 0, 1
+
+
+def default_precision():
+    """Arithmetic of the dense contractions when the caller does not choose: 'bf16x3' = tcgen05 tensor cores with
+    every fp32 operand split into bf16 hi+lo (3 MMAs per K step, fp32 accumulate in TMEM) -- meets the <= 1e-3 waveform
+    parity of the fp32 reference; 'fp32' is the exact FFMA path, 'bf16' the single-MMA fast mode."""
+    return os.environ.get('SAG_PRECISION', 'bf16x3')
 SAG_EINVAL, SAG_ECUDA, SAG_ENOMEM, SAG_ESTATE, SAG_EUNSUPPORTED = -1, -2, -3, -4, -5
 
 

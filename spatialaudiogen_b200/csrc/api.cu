@@ -81,6 +81,7 @@ int sag_destroy(sag_handle* h) {
   if (h == nullptr) return SAG_OK;
   for (auto& kv : h->weights) free_tensor(kv.second);
   for (auto& kv : h->packed) free_tensor(kv.second);
+  for (auto& kv : h->umma) umma_free(&kv.second);
   h->prof.clear();
   delete h;
   return SAG_OK;
@@ -141,6 +142,11 @@ int sag_load_weight(sag_handle* h, const char* tf_name, const float* host_data, 
   auto it = h->weights.find(name);
   if (it != h->weights.end()) free_tensor(it->second);
   h->weights[name] = t;
+  for (auto it = h->umma.begin(); it != h->umma.end();) {     // stale tensor-core images of this layer
+    const std::string scope = name.substr(0, name.rfind('/'));
+    if (it->first.compare(0, scope.size() + 1, scope + "#") == 0) { umma_free(&it->second); it = h->umma.erase(it); }
+    else ++it;
+  }
   if (is_deconv_weight(name)) {
     DevTensor p;
     p.shape = {(*exp)[0] * (*exp)[1], (*exp)[3], (*exp)[2]};
@@ -274,6 +280,21 @@ int sag_deconv2d(const float* x, int n, int h, int w, int cin, const float* w_hw
   SAG_REQUIRE(x != nullptr && w_hwoi != nullptr && y != nullptr, SAG_EINVAL, "sag_deconv2d: NULL argument");
   SAG_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && sh > 0 && sw > 0 && kh > 0 && kw > 0, SAG_EINVAL, "sag_deconv2d: bad dims");
   cudaStream_t st = as_stream(stream);
+  if (precision != SAG_PREC_FP32) {               // tcgen05: one sub-pixel GEMM
+    const int OH = (h - 1) * sh + kh, OW = (w - 1) * sw + kw;
+    UmmaWeights uw;
+    SAG_TRY(umma_pack_deconv(w_hwoi, bias, kh, kw, cout, cin, sh, sw, 0, (int64_t)OW * cout, cout, 1, precision, &uw, st));
+    GatherGeom g;
+    int oh_lim, ow_lim;
+    int r = make_deconv_subpixel_geom(&g, n, h, w, cin, cin, kh, kw, sh, sw, 0, OH, (int64_t)OH * OW * cout, (int64_t)OW * cout,
+                                      cout, 1, &oh_lim, &ow_lim);
+    g.Cout = uw.N;
+    Epilogue ep{bias, relu, nullptr, nullptr};
+    if (r == SAG_OK) r = launch_gather_gemm_umma(x, uw, y, g, ep, oh_lim, ow_lim, st);
+    cudaStreamSynchronize(st);
+    umma_free(&uw);
+    return r;
+  }
   float* wp = nullptr;
   SAG_CHECK_CUDA(cudaMallocAsync(&wp, sizeof(float) * (size_t)kh * kw * cin * cout, st));
   int r = launch_pack_deconv_weights(w_hwoi, wp, kh * kw, cout, cin, st);

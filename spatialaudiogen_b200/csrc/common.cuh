@@ -106,6 +106,29 @@ static inline int same_pad_before(int in, int k, int s, int* out) {
 int launch_gather_gemm_ffma(const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
                             cudaStream_t st);
 
+// ---- tcgen05 path (conv_umma.cu): SAG_PREC_BF16 / SAG_PREC_BF16X3 -----------------------------------------------
+// B operand of one layer, packed once: per (N tile, K chunk) a bf16 hi plane (+ lo plane for BF16X3) already in the
+// swizzled K-major shared-memory layout of tcgen05.mma, so each pipeline stage fetches it with one bulk-async copy.
+struct UmmaWeights {
+  void* packed = nullptr;
+  int K = 0, KC = 0, N = 0, BN = 0, NT = 0, planes = 0;
+  // output column map of the sub-pixel transposed conv (null for conv / FC): element offset, row / column displacement
+  // and bias per GEMM column
+  int* col_off = nullptr;
+  short* col_dy = nullptr;
+  short* col_dx = nullptr;
+  float* col_bias = nullptr;
+  int vec4 = 0;
+};
+void umma_free(UmmaWeights* w);
+// wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form)
+int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, UmmaWeights* out, cudaStream_t st);
+// w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
+int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
+                     int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, UmmaWeights* out, cudaStream_t st);
+int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, const GatherGeom& g, const Epilogue& ep,
+                            int oh_lim, int ow_lim, cudaStream_t st);
+
 // helpers building geometries (geom.cu)
 int make_conv_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh, int sw,
                    int same_pad, int64_t y_ld, int* oh, int* ow);
@@ -114,6 +137,11 @@ int make_conv_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, in
 int make_deconv_phase_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh,
                            int sw, int py, int px, int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw,
                            int64_t y_sc);
+
+// sub-pixel GEMM geometry of a whole transposed conv restricted to output rows [row0,row1) (conv_umma.cu)
+int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int sh, int sw,
+                              int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw, int64_t y_sc, int* oh_lim,
+                              int* ow_lim);
 
 // pointwise.cu
 int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,

@@ -137,13 +137,16 @@ int build_expected(sag_handle* h) {
 // ------------------------------------------------------------------------------------------------------------------
 int launch_gather_gemm(int precision, const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
                        cudaStream_t st) {
-  switch (precision) {
-    case SAG_PREC_FP32: return launch_gather_gemm_ffma(x, w, y, g, ep, st);
-    case SAG_PREC_TF32:
-    case SAG_PREC_BF16:
-    case SAG_PREC_BF16X3: return launch_gather_gemm_umma(precision, x, w, y, g, ep, st);
-    default: set_error("unknown precision %d", precision); return SAG_EINVAL;
-  }
+  if (precision == SAG_PREC_FP32) return launch_gather_gemm_ffma(x, w, y, g, ep, st);
+  // one-shot tcgen05 contraction (stage entry points): pack, run, release
+  for (int t = 0; t < g.T; ++t)
+    SAG_REQUIRE(g.widx[t] == t, SAG_EUNSUPPORTED, "tcgen05 path needs weights in tap order");
+  UmmaWeights uw;
+  SAG_TRY(umma_pack_weights(w, g.T * g.Cin, g.Cout, g.Cout, precision, &uw, st));
+  int r = launch_gather_gemm_umma(x, uw, y, g, ep, 0, 0, st);
+  cudaStreamSynchronize(st);
+  umma_free(&uw);
+  return r;
 }
 
 struct Fwd {
@@ -193,8 +196,19 @@ struct Fwd {
     SAG_TRY(err);
     Epilogue ep{b, relu, ssum, ssqs};
     const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
+    if (prec == SAG_PREC_FP32) {
+      ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
+      return launch_gather_gemm_ffma(x, w, y, g, ep, st);
+    }
+    const std::string key = scope + "#" + std::to_string(prec);
+    auto it = h->umma.find(key);
+    if (it == h->umma.end()) {                    // first use: build the tensor-core operand image of this layer
+      UmmaWeights uw;
+      SAG_TRY(umma_pack_weights(w, g.T * g.Cin, cout, cout, prec, &uw, st));
+      it = h->umma.emplace(key, uw).first;
+    }
     ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
-    return launch_gather_gemm(prec, x, w, y, g, ep, st);
+    return launch_gather_gemm_umma(x, it->second, y, g, ep, 0, 0, st);
   }
 
   // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
@@ -207,6 +221,27 @@ struct Fwd {
     const float* b = W(scope + "/biases", &err);
     SAG_TRY(err);
     Epilogue ep{b, relu, nullptr, nullptr};
+    if (prec != SAG_PREC_FP32) {
+      // one sub-pixel GEMM for the whole layer: N = sh*sw*cout columns, (kh/sh)*(kw/sw) taps
+      const int order = y_sc == 1 ? 0 : 1;
+      const std::string key = scope + "#" + std::to_string(prec);
+      auto it = h->umma.find(key);
+      if (it == h->umma.end()) {
+        const float* w_tf = W(scope + "/weights", &err);
+        SAG_TRY(err);
+        UmmaWeights uw;
+        SAG_TRY(umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, &uw, st));
+        it = h->umma.emplace(key, uw).first;
+      }
+      GatherGeom g;
+      int oh_lim, ow_lim;
+      SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x_ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
+                                        &oh_lim, &ow_lim));
+      g.Cout = it->second.N;
+      const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
+      ProfScope ps(PROF_DECONV, 2.0 * M * K * g.Cout, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st);
+      return launch_gather_gemm_umma(x, it->second, y, g, ep, oh_lim, ow_lim, st);
+    }
     for (int py = 0; py < sh; ++py)
       for (int px = 0; px < sw; ++px) {
         GatherGeom g;

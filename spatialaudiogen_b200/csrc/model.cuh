@@ -44,6 +44,7 @@ struct sag_handle {
   std::vector<std::pair<std::string, std::vector<int64_t>>> expected;   // checkpoint layout
   std::map<std::string, sag::DevTensor> weights;                        // TF layout on device
   std::map<std::string, sag::DevTensor> packed;                         // kernel layouts derived at load time
+  std::map<std::string, sag::UmmaWeights> umma;                         // tcgen05 operand images, key "<scope>#<precision>"
   std::map<std::string, sag::DevTensor> ends;                           // taps of the last forward
   std::vector<std::string> end_order;
   int last_launches = 0;
@@ -65,9 +66,7 @@ int fft_prepare(int n);
 void istft_needed_frames(int n_frames, int wind, int n_overlap, int crop0, int n_out, int* f_lo, int* f_hi);
 int sh_mesh_dims(float ang_res, int* n_nu, int* n_phi);
 
-// precision dispatch for the dense contractions
-int launch_gather_gemm_umma(int precision, const float* x, const float* w, float* y, const GatherGeom& g,
-                            const Epilogue& ep, cudaStream_t st);
+// one-shot contraction with unpacked weights (stage entry points): FFMA for SAG_PREC_FP32, else packs and runs tcgen05
 int launch_gather_gemm(int precision, const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
                        cudaStream_t st);
 

@@ -47,7 +47,7 @@ class SptAudioGen(object):
                  encoders=None,
                  separation='none',
                  params=None,
-                 precision='fp32',
+                 precision=None,
                  device=None,
                  frame_size=(224, 448)):
         assert float(audio_rate) / video_rate == int(audio_rate) // int(video_rate)          # model.py:33
@@ -86,6 +86,8 @@ class SptAudioGen(object):
         if not torch.cuda.is_available():
             raise RuntimeError('spatialaudiogen_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if precision is None:
+            precision = L.default_precision()
         self.precision = precision
         lib = L.lib()
         cfg = L.sag_config()

@@ -168,6 +168,26 @@ def test_deconv2d_fp32(case):
     assert _deconv_case(_L(), *case, prec=0) < 2e-5
 
 
+# tcgen05 path: bf16x3 (operands split hi+lo, 3 MMAs per K step) must be fp32-grade; plain bf16 is the fast mode
+UMMA_TOL = {3: 5e-5, 2: 2e-2}
+
+
+@pytest.mark.parametrize('prec', [3, 2])
+@pytest.mark.parametrize('case', CONV_CASES + [
+    (2, 56, 112, 64, 3, 3, 64, 1, 1, 1, 0, 0),        # resnet conv2_x (many M tiles, BN=64)
+    (3, 14, 28, 256, 3, 3, 256, 1, 1, 1, 0, 0),       # resnet conv4_x (two N tiles of 128, 36 K chunks)
+    (1, 6, 6, 64, 1, 1, 99, 1, 1, 0, 1, 0),           # N = 99 (localization/fc3 width)
+])
+def test_conv2d_tcgen05(case, prec):
+    assert _conv_case(_L(), *case, prec=prec) < UMMA_TOL[prec]
+
+
+@pytest.mark.parametrize('prec', [3, 2])
+@pytest.mark.parametrize('case', DECONV_CASES)
+def test_deconv2d_tcgen05(case, prec):
+    assert _deconv_case(_L(), *case, prec=prec) < UMMA_TOL[prec]
+
+
 def test_fc_fp32():
     L = _L()
     g = torch.Generator().manual_seed(0)
@@ -282,6 +302,32 @@ def test_forward_audio_video_flow_fp32_parity():
     y = m.inference_ops(cu(a), video=cu(v), flow=cu(fl))
     yr = ref.inference_ops(a, video=v, flow=fl)
     assert _rel(y, yr) < 1e-3
+
+
+def test_forward_tcgen05_bf16x3_parity_and_bf16_error():
+    """The tensor-core path: bf16x3 must meet the same <= 1e-3 waveform tolerance as the fp32 path (north_star);
+    plain bf16 is reported against a looser bound (BASELINE config 3)."""
+    ref, m = _models(['audio', 'video'], 'unet_mask', 9, 2, precision='bf16x3')
+    a, v = _audio(2, 23), _video(2, 24)
+    y = m.inference_ops(cu(a), video=cu(v))
+    yr = ref.inference_ops(a, video=v)
+    assert _rel(m.ends['audio_encoder/5'], ref.ends['audio_encoder'][5]) < 1e-4
+    assert _rel(m.ends['video_encoder/conv2_1'], ref.ends['video_encoder/conv2_1']) < 1e-4
+    assert _rel(m.ends['video_encoder/conv5_2'], ref.ends['video_encoder/conv5_2']) < 1e-3
+    assert _rel(m.ends['separation/mask_logits'], ref.ends['separation/mask_logits'][:, 0]) < 1e-3
+    assert _rel(y, yr) < 1e-3
+    m.set_option('precision', 'bf16')
+    y16 = m.inference_ops(cu(a), video=cu(v))
+    assert _rel(y16, yr) < 1e-1
+
+
+def test_forward_tcgen05_audio_only_and_flow():
+    ref, m = _models(['audio'], 'unet_mask', 3, 3, precision='bf16x3')
+    a = _audio(3, 13)
+    assert _rel(m.inference_ops(cu(a)), ref.inference_ops(a)) < 1e-3
+    ref, m = _models(['audio', 'video', 'flow'], 'unet_mask', 11, 2, precision='bf16x3')
+    a, v, fl = _audio(2, 25), _video(2, 26), _flow(2, 27)
+    assert _rel(m.inference_ops(cu(a), video=cu(v), flow=cu(fl)), ref.inference_ops(a, video=v, flow=fl)) < 1e-3
 
 
 def test_forward_errors():
