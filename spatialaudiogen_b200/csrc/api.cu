@@ -184,7 +184,7 @@ size_t sag_workspace_bytes(const sag_handle* h, int batch) {
   ar.dry = true;
   int r = forward(const_cast<sag_handle*>(h), nullptr, nullptr, nullptr, nullptr, ar, batch, 0);
   if (r != SAG_OK) return 0;
-  return ar.peak + 256;
+  return ar.peak + ar.scratch_need + 768;
 }
 
 int sag_forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* ambix_out,
@@ -195,9 +195,13 @@ int sag_forward(sag_handle* h, const float* audio, const float* video, const flo
   Arena dry;
   dry.dry = true;
   SAG_TRY(forward(h, nullptr, nullptr, nullptr, nullptr, dry, batch, 0));
-  SAG_REQUIRE(dry.peak + 256 <= workspace_bytes, SAG_ENOMEM, "sag_forward: workspace of %zu bytes is too small, need %zu", workspace_bytes, dry.peak + 256);
+  const size_t need = dry.peak + dry.scratch_need + 768;
+  SAG_REQUIRE(need <= workspace_bytes, SAG_ENOMEM, "sag_forward: workspace of %zu bytes is too small, need %zu", workspace_bytes, need);
   Arena ar;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  ar.scratch = reinterpret_cast<float*>(base);                       // split-K region first, then the bump arena
+  ar.scratch_cap = dry.scratch_need;
+  base = (base + dry.scratch_need + 255) & ~(uintptr_t)255;
   ar.base = reinterpret_cast<char*>(base);
   ar.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   return forward(h, audio, video, flow, ambix_out, ar, batch, as_stream(stream));
@@ -290,7 +294,7 @@ int sag_deconv2d(const float* x, int n, int h, int w, int cin, const float* w_hw
                                       cout, 1, &oh_lim, &ow_lim);
     g.Cout = uw.N;
     Epilogue ep{bias, relu, nullptr, nullptr};
-    if (r == SAG_OK) r = launch_gather_gemm_umma(x, uw, y, g, ep, oh_lim, ow_lim, st);
+    if (r == SAG_OK) r = launch_gather_gemm_umma(x, uw, y, g, ep, oh_lim, ow_lim, nullptr, st);
     cudaStreamSynchronize(st);
     umma_free(&uw);
     return r;
@@ -350,9 +354,13 @@ int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, fl
   Arena dry;
   dry.dry = true;
   SAG_TRY(resnet18_tower(h, scope, nullptr, batch, h->cfg.frame_h, h->cfg.frame_w, y, dry, 0));
-  SAG_REQUIRE(dry.peak + 256 <= workspace_bytes, SAG_ENOMEM, "sag_resnet18: workspace of %zu bytes is too small, need %zu", workspace_bytes, dry.peak + 256);
+  const size_t need = dry.peak + dry.scratch_need + 768;
+  SAG_REQUIRE(need <= workspace_bytes, SAG_ENOMEM, "sag_resnet18: workspace of %zu bytes is too small, need %zu", workspace_bytes, need);
   Arena ar;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  ar.scratch = reinterpret_cast<float*>(base);
+  ar.scratch_cap = dry.scratch_need;
+  base = (base + dry.scratch_need + 255) & ~(uintptr_t)255;
   ar.base = reinterpret_cast<char*>(base);
   ar.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   h->ends.clear();

@@ -123,11 +123,16 @@ struct UmmaWeights {
 void umma_free(UmmaWeights* w);
 // wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form)
 int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, UmmaWeights* out, cudaStream_t st);
+// conv weights HWIO zero-extended to kw2 taps per row and cin2 channels (convolution over a zero-padded NHWC4 image)
+int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
+                            UmmaWeights* out, cudaStream_t st);
 // w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
                      int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, UmmaWeights* out, cudaStream_t st);
+// scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
+int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
 int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, const GatherGeom& g, const Epilogue& ep,
-                            int oh_lim, int ow_lim, cudaStream_t st);
+                            int oh_lim, int ow_lim, float* scratch, cudaStream_t st);
 
 // helpers building geometries (geom.cu)
 int make_conv_geom(GatherGeom* g, int n, int h, int w, int cin, int64_t x_ld, int kh, int kw, int cout, int sh, int sw,
@@ -156,6 +161,8 @@ int launch_tile_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_l
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
                cudaStream_t st);
 int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st);
+// (n,h,w,3) -> (n,hp,wp,4): image at offset (pt,pl), zeros elsewhere (explicit TF-SAME border + 4th channel)
+int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, float* out, cudaStream_t st);
 int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st);
 
 // fft.cu

@@ -48,6 +48,8 @@ struct UmmaArgs {
   int KC;                 // K chunks of 64
   int stages;
   int vec_store;          // groups of 4 columns are contiguous and 16-byte aligned in the output
+  float* partial;         // split-K: raw accumulators [split][M][n_pad] (bias / activation / statistics run in the reduce)
+  int n_pad;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -183,8 +185,10 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-template <int BN, int NSPLIT, bool VEC>
-__global__ void __launch_bounds__(UM_THREADS, (BN <= 64 ? 2 : 1))
+// VEC: every 8-element K group lies inside one tap and is contiguous + 16-byte aligned in memory (Cin % 8 == 0).
+// PF: K chunks whose global loads are in flight per producer thread (register prefetch distance).
+template <int BN, int NSPLIT, bool VEC, int PF>
+__global__ void __launch_bounds__(UM_THREADS, (BN <= 64 && PF <= 2 ? 2 : 1))
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) {
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int B_PLANE = BN * 128;
@@ -202,7 +206,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES, bar_acc = bars + 16 * UM_MAX_STAGES;
   const uint32_t tmem_slot = bar_acc + 8;
   const int S = a.stages;
-  const int KC = a.KC;
+  // split-K: this CTA owns K chunks [kc_begin, kc_end)
+  const int kc_begin = (int)((int64_t)blockIdx.z * a.KC / gridDim.z);
+  const int kc_end = (int)((int64_t)(blockIdx.z + 1) * a.KC / gridDim.z);
+  const int KC = kc_end - kc_begin;
 
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   const int64_t m0 = (int64_t)blockIdx.x * UM_BM;
@@ -272,21 +279,20 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         img[it] = a.x + (int64_t)n * g.H * g.W * g.x_ld;
       }
     }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kc = 0; kc < KC; ++kc) {
-      float f[4][8];
-      const int k0 = kc * UM_BK;
+    // loads of one K chunk into registers (zero outside the image / beyond K)
+    auto load_chunk = [&](int kc, float (&f)[4][8]) {
+      if (kc >= kc_end) return;
+      const int kk = kc * UM_BK + jchunk * 8;
       if (VEC) {
-        // Cin % 64 == 0: the whole chunk lies inside one tap; 8 consecutive threads read one row's 256 contiguous bytes
-        const int t = k0 / g.Cin;
-        const int ci = k0 - t * g.Cin + jchunk * 8;
-        const int dy = g.dy[t], dx = g.dx[t];
+        const int t = kk / g.Cin;
+        const int ci = kk - t * g.Cin;
+        const bool kok = kk < a.K;
+        const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int iy = iy0[it] + dy, ix = ix0[it] + dx;
           float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
+          if (kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
             const float4* p = reinterpret_cast<const float4*>(img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci);
             v0 = __ldg(p);
             v1 = __ldg(p + 1);
@@ -295,9 +301,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
           f[it][4] = v1.x; f[it][5] = v1.y; f[it][6] = v1.z; f[it][7] = v1.w;
         }
       } else {
-        const int kk = k0 + jchunk * 8;
-        int t = kk / g.Cin;
-        int ci0 = kk - t * g.Cin;
+        const int t = kk / g.Cin;
+        const int ci0 = kk - t * g.Cin;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           int tt = t, ci = ci0;
@@ -314,12 +319,16 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
           }
         }
       }
-      // wait until the MMAs that read this stage the previous time round have completed
-      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    // split hi/lo, store into the swizzled stage, publish it
+    auto store_chunk = [&](int kc, float (&f)[4][8]) {
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);     // the MMAs that read this stage last time round have completed
       const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
       if (tid == 0) {
         mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
-        bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * KC + kc) * (size_t)(PLANES * B_PLANE),
+        bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
                  PLANES * B_PLANE, bar_full + 8 * stage);
       }
 #pragma unroll
@@ -335,6 +344,19 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * stage);
       if (++stage == S) { stage = 0; phase ^= 1; }
+    };
+    float f[PF][4][8];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) load_chunk(kc_begin + p, f[p]);
+#pragma unroll 1
+    for (int kc = kc_begin; kc < kc_end; kc += PF) {
+#pragma unroll
+      for (int p = 0; p < PF; ++p) {
+        if (kc + p < kc_end) {
+          store_chunk(kc + p, f[p]);
+          load_chunk(kc + p + PF, f[p]);
+        }
+      }
     }
 
     // ================================ epilogue ================================
@@ -357,7 +379,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       ox = g.ox0 + j * g.osx;
       yrow = a.y + (int64_t)n * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
     }
-    const bool do_stats = a.stat_sum != nullptr;
+    const bool do_stats = a.stat_sum != nullptr && a.partial == nullptr;
     constexpr int HALF = BN / 2;
 #pragma unroll 1
     for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 16) {
@@ -369,6 +391,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         for (int e = 0; e < 16; ++e) v[e] = 0.f;
       }
       const int n0 = n_base + c0;
+      if (a.partial != nullptr) {     // split-K: raw accumulators, finished by splitk_reduce_kernel
+        if (row_ok) {
+          float4* pp = reinterpret_cast<float4*>(a.partial + ((int64_t)blockIdx.z * M + m) * a.n_pad + n0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pp[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+        continue;
+      }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int n = n0 + e;
@@ -430,7 +460,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < KC; ++kc) {
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
@@ -439,7 +469,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
 #pragma unroll
         for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
           const uint64_t da_hi = make_sw128_desc(a_hi + k4 * 32), db_hi = make_sw128_desc(b_hi + k4 * 32);
-          umma_bf16(tmem_acc, da_hi, db_hi, IDESC, (kc > 0 || k4 > 0) ? 1u : 0u);
+          umma_bf16(tmem_acc, da_hi, db_hi, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
           if (NSPLIT == 3) {
             const uint64_t da_lo = make_sw128_desc(a_lo + k4 * 32), db_lo = make_sw128_desc(b_lo + k4 * 32);
             umma_bf16(tmem_acc, da_lo, db_hi, IDESC, 1u);
@@ -459,7 +489,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     tc_fence_after();
     tmem_dealloc(tmem_acc, TMEM_COLS);
   }
-  if (a.stat_sum != nullptr && tid < BN && n_base + tid < a.Ntot) {
+  if (a.stat_sum != nullptr && a.partial == nullptr && tid < BN && n_base + tid < a.Ntot) {
     atomicAdd(a.stat_sum + n_base + tid, (double)s_sum[tid]);
     atomicAdd(a.stat_sqs + n_base + tid, (double)s_sqs[tid]);
   }
@@ -523,6 +553,21 @@ __global__ void subpixel_weights_kernel(const float* __restrict__ w, int kh, int
   }
 }
 
+// HWIO conv weights [kh][kw][cin][cout] -> [kh][kw2][cin2][cout] with zeros in the added taps / channels
+__global__ void expand_hwio_kernel(const float* __restrict__ w, int kh, int kw, int cin, int cout, int kw2, int cin2,
+                                   float* __restrict__ out) {
+  const int64_t total = (int64_t)kh * kw2 * cin2 * cout;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int co = (int)(idx % cout);
+    int64_t r = idx / cout;
+    const int c = (int)(r % cin2); r /= cin2;
+    const int sx = (int)(r % kw2);
+    const int ry = (int)(r / kw2);
+    out[idx] = (c < cin && sx < kw) ? __ldg(w + (((int64_t)ry * kw + sx) * cin + c) * cout + co) : 0.f;
+  }
+}
+
 __global__ void expand_bias_kernel(const float* __restrict__ bias, int cout, int sw, int N, int order, float* __restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -530,36 +575,115 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias, int cout, int
   out[n] = __ldg(bias + co);
 }
 
-template <int BN, int NSPLIT, bool VEC>
-int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, cudaStream_t st) {
+// ---- split-K finish: sum the partial accumulators, then the same bias / activation / statistics / store as the
+//      fused epilogue.  One thread per (row, 4-column group); a block owns `rows_per_block` consecutive rows. ----
+__global__ void __launch_bounds__(128) splitk_reduce_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, int Z,
+                                                            int rows_per_block) {
+  const int64_t M = (int64_t)g.N * g.PH * g.PW;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  const int ncg = (a.Ntot + 3) / 4;
+  for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
+    const int n = cg * 4;
+    float bs[4], ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssqs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bs[e] = (a.bias != nullptr && n + e < a.Ntot) ? __ldg(a.bias + n + e) : 0.f;
+    for (int64_t m = r0; m < r1; ++m) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int z = 0; z < Z; ++z) {
+        const float4 p = __ldcs(reinterpret_cast<const float4*>(a.partial + ((int64_t)z * M + m) * a.n_pad + n));
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      float v[4] = {acc.x + bs[0], acc.y + bs[1], acc.z + bs[2], acc.w + bs[3]};
+      if (a.relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      const int j = (int)(m % g.PW);
+      const int64_t q = m / g.PW;
+      const int i = (int)(q % g.PH);
+      const int b = (int)(q / g.PH);
+      const int oy = g.oy0 + i * g.osy, ox = g.ox0 + j * g.osx;
+      float* yrow = a.y + (int64_t)b * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
+      if (a.col_off == nullptr) {
+        if (a.vec_store) {
+          *reinterpret_cast<float4*>(yrow + n) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < a.Ntot) yrow[(int64_t)(n + e) * g.y_sc] = v[e];
+        }
+      } else {
+        if (a.vec_store) {
+          if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)
+            *reinterpret_cast<float4*>(yrow + a.col_off[n]) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (n + e < a.Ntot && (unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim &&
+                (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)
+              yrow[a.col_off[n + e]] = v[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ssum[e] += v[e]; ssqs[e] = fmaf(v[e], v[e], ssqs[e]); }
+    }
+    if (a.stat_sum != nullptr && r1 > r0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < a.Ntot) {
+          atomicAdd(a.stat_sum + n + e, (double)ssum[e]);
+          atomicAdd(a.stat_sqs + n + e, (double)ssqs[e]);
+        }
+    }
+  }
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int BN, int NSPLIT, bool VEC, int PF>
+int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStream_t st) {
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
+  constexpr bool TWO_PER_SM = BN <= 64 && PF <= 2;
   UmmaArgs a = a_in;
-  // shared memory budget: two CTAs per SM for the narrow tiles, one for BN >= 128
-  const int budget = (BN <= 64 ? 110 : 220) * 1024 - UM_BAR_BYTES - 1024;
+  const int budget = (TWO_PER_SM ? 110 : 220) * 1024 - UM_BAR_BYTES - 1024;
   int S = budget / STAGE_BYTES;
-  if (S > UM_MAX_STAGES) S = UM_MAX_STAGES;
   if (S > 4) S = 4;
   if (S < 2) S = 2;
   a.stages = S;
   const size_t smem = (size_t)UM_BAR_BYTES + 1024 + (size_t)S * STAGE_BYTES;
-  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, VEC>;
+  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, VEC, PF>;
   static bool attr_set = false;
   if (!attr_set) {
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_set = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  dim3 grid((unsigned)cdiv64(M, UM_BM), (unsigned)nt);
+  dim3 grid((unsigned)cdiv64(M, UM_BM), (unsigned)nt, (unsigned)Z);
   kern<<<grid, UM_THREADS, smem, st>>>(g, a);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
 
+template <int BN, int NSPLIT>
+int launch_ns(const GatherGeom& g, const UmmaArgs& a, int nt, bool vec, int Z, cudaStream_t st) {
+  if (!vec) return launch_cfg<BN, NSPLIT, false, 1>(g, a, nt, Z, st);
+  static const int pf = env_int("SAG_UMMA_PF", 1);
+  switch (pf) {
+    case 1: return launch_cfg<BN, NSPLIT, true, 1>(g, a, nt, Z, st);
+    case 2: return launch_cfg<BN, NSPLIT, true, 2>(g, a, nt, Z, st);
+    default: return launch_cfg<BN, NSPLIT, true, 3>(g, a, nt, Z, st);
+  }
+}
+
 template <int BN>
-int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, bool vec, cudaStream_t st) {
-  if (planes == 2) return vec ? launch_cfg<BN, 3, true>(g, a, nt, st) : launch_cfg<BN, 3, false>(g, a, nt, st);
-  return vec ? launch_cfg<BN, 1, true>(g, a, nt, st) : launch_cfg<BN, 1, false>(g, a, nt, st);
+int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, bool vec, int Z, cudaStream_t st) {
+  if (planes == 2) return launch_ns<BN, 3>(g, a, nt, vec, Z, st);
+  return launch_ns<BN, 1>(g, a, nt, vec, Z, st);
 }
 
 }  // namespace
@@ -581,7 +705,7 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   UmmaWeights w;
   w.K = K; w.N = N;
   w.KC = cdiv(K, UM_BK);
-  w.BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  w.BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);   // == tile_width(N)
   w.NT = cdiv(N, w.BN);
   w.planes = precision == SAG_PREC_BF16X3 ? 2 : 1;
   const size_t bytes = (size_t)w.NT * w.KC * w.planes * w.BN * 128;
@@ -597,6 +721,20 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   }
   *out = w;
   return SAG_OK;
+}
+
+int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
+                            UmmaWeights* out, cudaStream_t st) {
+  float* wk = nullptr;
+  const int64_t total = (int64_t)kh * kw2 * cin2 * cout;
+  SAG_CHECK_CUDA(cudaMalloc(&wk, sizeof(float) * (size_t)total));
+  int64_t blocks = cdiv64(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  expand_hwio_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, kw2, cin2, wk);
+  int r = umma_pack_weights(wk, kh * kw2 * cin2, cout, cout, precision, out, st);
+  cudaStreamSynchronize(st);
+  cudaFree(wk);
+  return r;
 }
 
 // Sub-pixel formulation of tf.nn.conv2d_transpose VALID (core.py:139-140): every cell (u, v) of the
@@ -688,8 +826,28 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
   return SAG_OK;
 }
 
+// Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the
+// partial accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them
+// (deterministic: fixed summation order).
+static int tile_width(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+
+int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
+  static const int enabled = env_int("SAG_UMMA_SPLITK", 1);
+  const int BN = tile_width(N), NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
+  const int64_t tiles = cdiv64(M, UM_BM) * NT;
+  int Z = 1;
+  if (enabled && tiles > 0 && tiles < 120 && KC >= 8) {
+    Z = (int)(296 / tiles);                 // aim at ~2 CTAs worth of work per SM
+    if (Z > KC / 4) Z = KC / 4;             // at least 4 chunks per split
+    if (Z > 32) Z = 32;
+    if (Z < 1) Z = 1;
+  }
+  if (scratch_bytes) *scratch_bytes = Z > 1 ? sizeof(float) * (size_t)Z * (size_t)M * (size_t)(NT * BN) : 0;
+  return Z;
+}
+
 int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, const GatherGeom& g, const Epilogue& ep,
-                            int oh_lim, int ow_lim, cudaStream_t st) {
+                            int oh_lim, int ow_lim, float* scratch, cudaStream_t st) {
   SAG_REQUIRE(w.packed != nullptr || w.KC == 0, SAG_ESTATE, "tcgen05 path: weights are not packed");
   SAG_REQUIRE(g.T * g.Cin == w.K, SAG_EINVAL, "tcgen05 path: geometry K %d does not match packed K %d", g.T * g.Cin, w.K);
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
@@ -703,21 +861,34 @@ int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, cons
   a.bias = w.col_off != nullptr ? w.col_bias : ep.bias;
   a.oh_lim = oh_lim; a.ow_lim = ow_lim;
   a.Ntot = w.N; a.K = w.K; a.KC = w.KC;
+  a.n_pad = w.NT * w.BN;
   const bool aligned_y = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
   if (w.col_off != nullptr) {
     SAG_REQUIRE(ep.stat_sum == nullptr, SAG_EUNSUPPORTED, "tcgen05 path: statistics with mapped outputs");
-    a.vec_store = (w.vec4 && aligned_y && g.y_sn % 4 == 0 && g.y_sh % 4 == 0 && (g.y_sw * g.osx) % 4 == 0 &&
-                   ((int64_t)g.oy0 * g.y_sh) % 4 == 0 && ow_lim % 4 == 0) ? 1 : 0;
+    a.vec_store = (w.vec4 && aligned_y && g.y_sn % 4 == 0 && g.y_sh % 4 == 0 && (g.y_sw * g.osx) % 4 == 0 && ow_lim % 4 == 0) ? 1 : 0;
   } else {
     a.vec_store = (g.y_sc == 1 && aligned_y && w.N % 4 == 0 && g.y_sn % 4 == 0 && g.y_sh % 4 == 0 && g.y_sw % 4 == 0) ? 1 : 0;
   }
-  const bool vec = (g.Cin % UM_BK == 0) && (g.x_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  // vector gather: every 8-element K group is one tap's 8 contiguous, 16-byte aligned floats
+  bool vec = (g.Cin % 8 == 0) && ((g.x_ld * g.isx) % 4 == 0) && ((g.x_ld * g.W) % 4 == 0) &&
+             ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int t = 0; t < g.T && vec; ++t) vec = (g.dx[t] * g.x_ld) % 4 == 0;
+  int Z = scratch != nullptr ? umma_split_k(w.K, w.N, M, nullptr) : 1;
+  if (Z > 1) a.partial = scratch;
+  int r;
   switch (w.BN) {
-    case 32: return launch_bn<32>(g, a, w.NT, w.planes, vec, st);
-    case 64: return launch_bn<64>(g, a, w.NT, w.planes, vec, st);
-    case 128: return launch_bn<128>(g, a, w.NT, w.planes, vec, st);
+    case 32: r = launch_bn<32>(g, a, w.NT, w.planes, vec, Z, st); break;
+    case 64: r = launch_bn<64>(g, a, w.NT, w.planes, vec, Z, st); break;
+    case 128: r = launch_bn<128>(g, a, w.NT, w.planes, vec, Z, st); break;
     default: set_error("tcgen05 path: unsupported tile width %d", w.BN); return SAG_EINVAL;
   }
+  SAG_TRY(r);
+  if (Z > 1) {
+    const int rows_per_block = 8;
+    splitk_reduce_kernel<<<(unsigned)cdiv64(M, rows_per_block), 128, 0, st>>>(g, a, Z, rows_per_block);
+    SAG_LAUNCH_CHECK();
+  }
+  return SAG_OK;
 }
 
 }  // namespace sag

@@ -143,8 +143,12 @@ int launch_gather_gemm(int precision, const float* x, const float* w, float* y, 
     SAG_REQUIRE(g.widx[t] == t, SAG_EUNSUPPORTED, "tcgen05 path needs weights in tap order");
   UmmaWeights uw;
   SAG_TRY(umma_pack_weights(w, g.T * g.Cin, g.Cout, g.Cout, precision, &uw, st));
-  int r = launch_gather_gemm_umma(x, uw, y, g, ep, 0, 0, st);
+  size_t sbytes = 0;
+  float* scratch = nullptr;
+  if (umma_split_k(uw.K, uw.N, (int64_t)g.N * g.PH * g.PW, &sbytes) > 1 && cudaMalloc(&scratch, sbytes) != cudaSuccess) scratch = nullptr;
+  int r = launch_gather_gemm_umma(x, uw, y, g, ep, 0, 0, scratch, st);
   cudaStreamSynchronize(st);
+  if (scratch) cudaFree(scratch);
   umma_free(&uw);
   return r;
 }
@@ -183,12 +187,27 @@ struct Fwd {
     h->end_order.push_back(name);
   }
 
+  // split-K scratch of a tcgen05 contraction (recorded in the dry pass, served from the shared region otherwise)
+  float* splitk(int K, int N, int64_t M) {
+    size_t bytes = 0;
+    umma_split_k(K, N, M, &bytes);
+    if (bytes > ar.scratch_need) ar.scratch_need = bytes;
+    return (!dry() && bytes > 0 && bytes <= ar.scratch_cap) ? ar.scratch : nullptr;
+  }
+
   // tfw.conv_2d (core.py:156-220) on an NHWC view: x has pixel stride x_ld, y has pixel stride y_ld.
   int conv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
            int cout, int sh, int sw, int same, bool bias, int relu, float* y, int64_t y_ld, double* ssum, double* ssqs,
            int* oh, int* ow) {
     GatherGeom g;
     SAG_TRY(make_conv_geom(&g, n, hh, ww, cin, x_ld, kh, kw, cout, sh, sw, same, y_ld, oh, ow));
+    if (prec != SAG_PREC_FP32 && !same && x_ld == cin && cin < 8 && (kw * cin) % 8 == 0) {
+      // VALID conv over a dense image with few channels: a kernel row's kw*cin inputs are contiguous in memory, so
+      // it becomes one tap of kw*cin "channels" (HWIO weights already have that K order) -> vector gather
+      g.T = kh; g.Cin = kw * cin;
+      for (int r = 0; r < kh; ++r) { g.dy[r] = (short)r; g.dx[r] = 0; g.widx[r] = (short)r; }
+    }
+    float* scratch = prec != SAG_PREC_FP32 ? splitk(g.T * g.Cin, cout, (int64_t)g.N * g.PH * g.PW) : nullptr;
     if (dry()) return SAG_OK;
     int err = SAG_OK;
     const float* w = W(scope + "/weights", &err);
@@ -208,13 +227,20 @@ struct Fwd {
       it = h->umma.emplace(key, uw).first;
     }
     ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
-    return launch_gather_gemm_umma(x, it->second, y, g, ep, 0, 0, st);
+    return launch_gather_gemm_umma(x, it->second, y, g, ep, 0, 0, scratch, st);
   }
 
   // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
   int deconv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
              int cout, int sh, int sw, int relu, float* y, int row0, int row1, int64_t y_sn, int64_t y_sh,
              int64_t y_sw, int64_t y_sc) {
+    float* scratch = nullptr;
+    if (prec != SAG_PREC_FP32) {
+      GatherGeom g0;
+      int a0, b0;
+      SAG_TRY(make_deconv_subpixel_geom(&g0, n, hh, ww, cin, x_ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc, &a0, &b0));
+      scratch = splitk(g0.T * cin, sh * sw * cout, (int64_t)g0.N * g0.PH * g0.PW);
+    }
     if (dry()) return SAG_OK;
     int err = SAG_OK;
     const float* w = Wp(scope + "/weights", &err);
@@ -240,7 +266,7 @@ struct Fwd {
       g.Cout = it->second.N;
       const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
       ProfScope ps(PROF_DECONV, 2.0 * M * K * g.Cout, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st);
-      return launch_gather_gemm_umma(x, it->second, y, g, ep, oh_lim, ow_lim, st);
+      return launch_gather_gemm_umma(x, it->second, y, g, ep, oh_lim, ow_lim, scratch, st);
     }
     for (int py = 0; py < sh; ++py)
       for (int px = 0; px < sw; ++px) {
@@ -305,7 +331,41 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   float* c1 = ar.alloc<float>((int64_t)B * OH1 * OW1 * 64);
   BnBuf b1 = alloc_bn(ar, 64);
   SAG_TRY(zero_bn(b1, 64));
-  SAG_TRY(f.conv(x, B, H, Wd, 3, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, 64, b1.sum, b1.sqs, &oh, &ow));
+  if (f.prec == SAG_PREC_FP32) {
+    SAG_TRY(f.conv(x, B, H, Wd, 3, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, 64, b1.sum, b1.sqs, &oh, &ow));
+  } else {
+    // tensor-core route: explicit TF-SAME border + a zero 4th channel (NHWC4), kernel rows widened to 8 taps so that
+    // one row = 8 pixels x 4 channels = 32 contiguous, 16-byte aligned floats -> 7 taps of 32 "channels" (K = 224)
+    int pt = same_pad_before(H, 7, 2, &oh), pl = same_pad_before(Wd, 7, 2, &ow);
+    const int Hp = (oh - 1) * 2 + 7, Wp = (((ow - 1) * 2 + 8) + 3) / 4 * 4;
+    float* xp = ar.alloc<float>((int64_t)B * Hp * Wp * 4);
+    GatherGeom g;
+    memset(&g, 0, sizeof(g));
+    g.N = B; g.H = Hp; g.W = Wp; g.Cin = 32; g.x_ld = 4;
+    g.PH = oh; g.PW = ow; g.isy = 2; g.isx = 2;
+    g.osy = 1; g.osx = 1; g.y_sc = 1; g.y_sw = 64; g.y_sh = (int64_t)ow * 64; g.y_sn = (int64_t)oh * ow * 64;
+    g.Cout = 64; g.T = 7;
+    for (int r = 0; r < 7; ++r) { g.dy[r] = (short)r; g.dx[r] = 0; g.widx[r] = (short)r; }
+    float* scratch = f.splitk(g.T * g.Cin, 64, (int64_t)B * oh * ow);
+    if (!ar.dry) {
+      const float* w = f.W(p + "conv1/conv/weights", &err);
+      SAG_TRY(err);
+      const std::string key = p + "conv1/conv#" + std::to_string(f.prec);
+      auto it = h->umma.find(key);
+      if (it == h->umma.end()) {
+        UmmaWeights uw;
+        SAG_TRY(umma_pack_conv_expanded(w, 7, 7, 3, 64, 8, 4, f.prec, &uw, st));
+        it = h->umma.emplace(key, uw).first;
+      }
+      {
+        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * ((double)H * Wd * 3 + (double)Hp * Wp * 4), st);
+        SAG_TRY(launch_pad_nhwc3_to_nhwc4(x, B, H, Wd, pt, pl, Hp, Wp, xp, st));
+      }
+      Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
+      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, 4.0 * B * ((double)Hp * Wp * 4 + (double)oh * ow * 64), st);
+      SAG_TRY(launch_gather_gemm_umma(xp, it->second, c1, g, ep, 0, 0, scratch, st));
+    }
+  }
   SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
   float* cur = ar.alloc<float>((int64_t)B * ph * pw * 64);

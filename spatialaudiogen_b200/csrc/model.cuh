@@ -23,6 +23,10 @@ struct Arena {
   size_t cap = 0, off = 0, peak = 0;
   bool dry = false;
   bool failed = false;
+  // split-K scratch shared by all layers of a pass (they run back to back on one stream): the dry pass records the
+  // largest request in scratch_need, the real pass gets that many bytes at `scratch`
+  size_t scratch_need = 0, scratch_cap = 0;
+  float* scratch = nullptr;
   template <class T>
   T* alloc(int64_t n) {
     off = (off + 255) & ~(size_t)255;

@@ -248,6 +248,36 @@ int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st) {
   return SAG_OK;
 }
 
+// ---- (n,h,w,3) -> zero-bordered (n,hp,wp,4): one float4 store per output pixel ----
+__global__ void pad_nhwc3_to_nhwc4_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int hp, int wp,
+                                          float4* __restrict__ out) {
+  const int64_t total = (int64_t)n * hp * wp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int px = (int)(i % wp);
+    const int64_t r = i / wp;
+    const int py = (int)(r % hp);
+    const int b = (int)(r / hp);
+    const int iy = py - pt, ix = px - pl;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w) {
+      const float* p = x + (((int64_t)b * h + iy) * w + ix) * 3;
+      v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    out[i] = v;
+  }
+}
+
+int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, float* out, cudaStream_t st) {
+  const int64_t total = (int64_t)n * hp * wp;
+  int64_t blocks = cdiv64(total, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  pad_nhwc3_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, h, w, pt, pl, hp, wp, reinterpret_cast<float4*>(out));
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
 // ---- tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin] (core.py:118) -> per-tap [Cin][Cout] slabs ----
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cout, int cin) {
   int64_t total = (int64_t)taps * cout * cin;
