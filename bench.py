@@ -201,7 +201,7 @@ def run_reference(args, encoders):
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(encoders, B, 'fp32', args, 1),
+            'config': workload_config(encoders, B, default_precision_name(args), args, 1),
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0,
@@ -210,15 +210,21 @@ def run_reference(args, encoders):
     return 0
 
 
+def default_precision_name(args):
+    if args.precision != 'auto':
+        return args.precision
+    return os.environ.get('SAG_PRECISION', 'bf16x3')     # == spatialaudiogen_b200._lib.default_precision()
+
+
 def workload_config(encoders, B, precision, args, world):
     return {'workload': 'configs[1]: %s encoders, unet_mask separation, batch %d, 0.1 s @48 kHz mono + 224x448 RGB per window'
                         % ('+'.join(encoders), B),
-            'batch_per_gpu': B, 'global_batch': B * world, 'encoders': encoders, 'precision': precision,
+            'batch_per_gpu': B, 'encoders': encoders, 'precision': precision,
             'weights': 'xavier random init (seed 1234), resnet towers random (no checkpoint offline)',
             'step': 'sag_forward + sag_metrics over one batch',
             'l2': 'inputs rotate over %d distinct batches and each step streams >1 GB of activations through the '
                   'workspace (> 126 MB L2)' % args.rotate,
-            'parallelism': 'clip-sharded dp%d, one all-gather of metric rows' % world}
+            'parallelism': 'clip-sharded, weights replicated, one all-gather of metric rows at the end of the pass'}
 
 
 # ---- our arm -------------------------------------------------------------------------------------------------------
@@ -229,7 +235,7 @@ def main():
         return run_reference(args, encoders)
 
     import torch.distributed as dist
-    from spatialaudiogen_b200 import SptAudioGen, weights as Wt, metrics as M, _lib as L
+    from spatialaudiogen_b200 import SptAudioGen, weights as Wt, _lib as L, evaluate as E, dist as D
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -259,15 +265,16 @@ def main():
         devb.append({k: v.to(dev) for k, v in hb.items()})
     out = torch.empty((B, SND_DUR, 3), dtype=torch.float32, device=dev)
     out_host = torch.empty((B, SND_DUR, 3), dtype=torch.float32).pin_memory()
-    rows = torch.zeros((args.steps, B, 17), dtype=torch.float32, device=dev)    # 5x3 metrics + 2 amplitudes per window
+    rows = torch.zeros((args.steps, B, E.N_COLS), dtype=torch.float32, device=dev)   # eval-detailed.txt columns per window
+    ids = torch.stack([torch.full((args.steps * B,), rank, dtype=torch.int64),
+                       torch.arange(args.steps * B, dtype=torch.int64)], 1).to(dev)       # (clip = rank, window)
 
     def step(i, store=None):
         d = devb[i % R]
         model.forward_into(d['audio'], d.get('video'), d.get('flow'), out)
-        res = M.window_metrics(out, d['target'], RATE)
+        r, _ = E.metric_rows(out, d['target'], audio_rate=RATE)
         if store is not None:
-            store[:, 0:3], store[:, 3:6], store[:, 6:9] = res['stft'], res['lsd'], res['mse']
-            store[:, 9:12], store[:, 12:15], store[:, 15:17] = res['snr'], res['env'], res['amp']
+            store.copy_(r)
 
     def barrier():
         if world > 1:
@@ -277,8 +284,7 @@ def main():
     for i in range(max(3, args.warmup)):
         step(i)
     if world > 1:                                        # warm the collective too
-        g = [torch.empty_like(rows) for _ in range(world)]
-        dist.all_gather(g, rows)
+        D.gather_rows(rows.reshape(-1, E.N_COLS), ids, max_rows=args.steps * B)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     time.sleep(0.3 if sampler else 0.0)
@@ -288,8 +294,8 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i, rows[i])
-    if world > 1:
-        dist.all_gather(g, rows)
+    if world > 1:                                        # the pass's single collective: all ranks' metric rows
+        all_rows, all_ids = D.gather_rows(rows.reshape(-1, E.N_COLS), ids, max_rows=args.steps * B)
     e1.record()
     barrier()
     w1 = time.time()
@@ -299,7 +305,9 @@ def main():
     ms = float(ms.item())
     clocks = sampler.stop(w0, w1) if sampler else None
     launches_fwd = int(L.lib().sag_last_launch_count(model._h))
-    launches = args.steps * (launches_fwd + 1)           # + metrics_kernel
+    launches = args.steps * (launches_fwd + 1)           # + metrics_kernel (torch's own fill/copy kernels not counted)
+    if world > 1 and rank == 0:
+        assert all_rows.shape == (world * args.steps * B, E.N_COLS) and int(all_ids[:, 0].max()) == world - 1
     value = WINDOW_S * B * world * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers in, host waveform out, through the public operator API ----

@@ -103,6 +103,12 @@ int sag_forward(sag_handle* h, const float* audio, const float* video, const flo
  * The pointer aliases the workspace and is valid until the next forward.  shape has up to 5 entries. */
 int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr, int64_t* shape5, int* rank,
                    int64_t* row_stride /* elements between consecutive indices of the second-to-last axis */);
+/* Storage format of an intermediate tensor: SAG_FMT_F32, or SAG_FMT_BF16_SPLIT on the tensor-core path, where a
+ * value x is kept as two bf16 planes hi = bf16(x) at dev_ptr and lo = bf16(x - hi) `plane_bytes` further
+ * (plane_bytes == 0: hi only); shape and row_stride are in elements either way. */
+#define SAG_FMT_F32 0
+#define SAG_FMT_BF16_SPLIT 1
+int sag_get_tensor_format(const sag_handle* h, const char* name, int* format, int64_t* plane_bytes);
 int sag_num_tensors(const sag_handle* h);
 int sag_tensor_name(const sag_handle* h, int i, char* buf, int buflen);
 /* options: "skip_unused" (default 1: STFT frames / mask rows that cannot reach the cropped output are not

@@ -55,6 +55,7 @@ PROTOTYPES = {
     'sag_workspace_bytes': (_S, [_P, _I]),
     'sag_forward': (_I, [_P, _P, _P, _P, _P, _P, _S, _I, _P]),
     'sag_get_tensor': (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I), C.POINTER(_L)]),
+    'sag_get_tensor_format': (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_L)]),
     'sag_num_tensors': (_I, [_P]),
     'sag_tensor_name': (_I, [_P, _I, C.c_char_p, _I]),
     'sag_last_launch_count': (_I, [_P]),

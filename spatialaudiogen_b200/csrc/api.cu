@@ -228,6 +228,15 @@ int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr,
   return SAG_OK;
 }
 
+int sag_get_tensor_format(const sag_handle* h, const char* name, int* format, int64_t* plane_bytes) {
+  SAG_REQUIRE(h != nullptr && name != nullptr, SAG_EINVAL, "sag_get_tensor_format: NULL argument");
+  auto it = h->ends.find(name);
+  SAG_REQUIRE(it != h->ends.end(), SAG_EINVAL, "sag_get_tensor_format: no tensor named '%s' in the last forward", name);
+  if (format) *format = it->second.fmt;
+  if (plane_bytes) *plane_bytes = it->second.plane;
+  return SAG_OK;
+}
+
 int sag_last_launch_count(const sag_handle* h) { return h ? h->last_launches : SAG_EINVAL; }
 
 int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, double* bytes, int* launches) {
@@ -353,7 +362,8 @@ int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, fl
   SAG_REQUIRE(batch > 0, SAG_EINVAL, "sag_resnet18: batch must be positive");
   Arena dry;
   dry.dry = true;
-  SAG_TRY(resnet18_tower(h, scope, nullptr, batch, h->cfg.frame_h, h->cfg.frame_w, y, dry, 0));
+  Act yact;
+  SAG_TRY(resnet18_tower(h, scope, nullptr, batch, h->cfg.frame_h, h->cfg.frame_w, &yact, dry, 0));
   const size_t need = dry.peak + dry.scratch_need + 768;
   SAG_REQUIRE(need <= workspace_bytes, SAG_ENOMEM, "sag_resnet18: workspace of %zu bytes is too small, need %zu", workspace_bytes, need);
   Arena ar;
@@ -365,7 +375,9 @@ int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, fl
   ar.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   h->ends.clear();
   h->end_order.clear();
-  return resnet18_tower(h, scope, x, batch, h->cfg.frame_h, h->cfg.frame_w, y, ar, as_stream(stream));
+  SAG_TRY(resnet18_tower(h, scope, x, batch, h->cfg.frame_h, h->cfg.frame_w, &yact, ar, as_stream(stream)));
+  const int fh = (h->cfg.frame_h + 31) / 32, fw = (h->cfg.frame_w + 31) / 32;
+  return launch_act_to_f32(yact.v, y, (int64_t)batch * fh * fw * 512, as_stream(stream));
 }
 
 int sag_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out, void* stream) {

@@ -129,9 +129,21 @@ int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int co
 // w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
                      int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, UmmaWeights* out, cudaStream_t st);
+// Activation view handed to the tensor-core kernels.  ACT_F32: p = float*.  ACT_BF2: the value x is stored as two bf16
+// planes, hi = bf16(x) at p and lo = bf16(x - hi) at p + plane bytes (plane == 0: hi only, SAG_PREC_BF16); strides of
+// the geometry are in elements either way.
+enum { ACT_F32 = 0, ACT_BF2 = 1 };
+struct ActView {
+  void* p = nullptr;
+  int fmt = ACT_F32;
+  int64_t plane = 0;
+  ActView() {}
+  ActView(const float* f) : p(const_cast<float*>(f)) {}
+  ActView(void* q, int f, int64_t pl) : p(q), fmt(f), plane(pl) {}
+};
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
-int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, const GatherGeom& g, const Epilogue& ep,
+int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st);
 
 // helpers building geometries (geom.cu)
@@ -151,23 +163,24 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
 // pointwise.cu
 int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
                        int c, float eps, float* scale, float* shift, cudaStream_t st);
-int launch_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, int relu,
-                    float* y, int64_t rows, int c, cudaStream_t st);
+int launch_bn_apply(const float* x, const float* scale, const float* shift, const ActView& residual, int relu,
+                    const ActView& y, int64_t rows, int c, cudaStream_t st);
 int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
-                           float* y, cudaStream_t st);   // 3x3/2 SAME; scale==null -> plain max-pool
+                           const ActView& y, cudaStream_t st);   // 3x3/2 SAME; scale==null -> plain max-pool
 int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st);
-int launch_tile_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int groups, int reps, int c,
+int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int64_t dst_ld, int groups, int reps, int c,
                      cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
                cudaStream_t st);
 int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st);
 // (n,h,w,3) -> (n,hp,wp,4): image at offset (pt,pl), zeros elsewhere (explicit TF-SAME border + 4th channel)
-int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, float* out, cudaStream_t st);
+int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, const ActView& out,
+                              cudaStream_t st);
 int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st);
 
 // fft.cu
 int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int n_frames_total, int frame0,
-                int n_frames_out, float* cplx_out, int mag0, int n_mag, float* mag_out, cudaStream_t st);
+                int n_frames_out, float* cplx_out, int mag0, int n_mag, const ActView& mag_out, cudaStream_t st);
 // masked inverse STFT with overlap-add: S (rows_s, n_frames, wind) complex; mask (rows_s*tracks, n_frames, wind) real
 // logits (sigmoid applied inside when apply_sigmoid) or null (mask == 1, tracks == 1);
 // out[(row*tracks+k), j] for j in [crop0, crop0+n_out) of the reference istft output.

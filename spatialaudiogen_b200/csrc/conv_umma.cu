@@ -4,11 +4,17 @@
 //
 //   C[m, n] = sum_{t, ci} X[pixel(m) + tap t, ci] * Wk[t*Cin + ci, n]          (zero outside the image)
 //
+// Activations travel between layers as two bf16 planes (hi = bf16(x), lo = bf16(x - hi); same bytes as fp32), written
+// once by whichever kernel produces them, so the gather is a pure copy: each producer thread issues 16-byte cp.async
+// (LDGSTS, zero-filled outside the image) straight into the swizzled operand tile -- no registers, no conversion, the
+// loads of several K chunks in flight.  fp32 sources (stage entry points, first use of user inputs) take the register
+// path that splits on the fly.
+//
 // CTA = one 128 x BN output tile, 9 warps:
-//   warps 0-7  producers: gather fp32 activations (coalesced 32 B per thread), split each value into bf16 hi + bf16 lo,
-//              store both planes into shared memory in the UMMA K-major SWIZZLE_128B canonical layout; warp 0 lane 0 also
-//              issues the bulk-async (TMA, cp.async.bulk) copy of the pre-packed weight tile; afterwards the same warps run
-//              the epilogue: tcgen05.ld of the accumulator, bias / ReLU, batch-norm statistics, strided or mapped store.
+//   warps 0-7  producers: gather the A operand into shared memory in the UMMA K-major SWIZZLE_128B canonical layout;
+//              thread 0 also issues the bulk-async (TMA, cp.async.bulk) copy of the pre-packed weight tile; afterwards
+//              the same warps run the epilogue: tcgen05.ld of the accumulator, bias / ReLU, batch-norm statistics,
+//              strided or mapped store as fp32 or as split bf16 planes.
 //   warp 8     allocates TMEM and (one elected lane) issues tcgen05.mma kind::f16 with the accumulator in TMEM:
 //              SAG_PREC_BF16   : 1 MMA per K step  (A_hi x B_hi)
 //              SAG_PREC_BF16X3 : 3 MMAs per K step (A_hi x B_hi + A_lo x B_hi + A_hi x B_lo) -> fp32-grade products
@@ -32,9 +38,12 @@ constexpr int UM_MAX_STAGES = 8;
 constexpr int UM_BAR_BYTES = 256;
 
 struct UmmaArgs {
-  const float* x;
+  const void* x;          // fp32 activation, or the hi plane of a split-bf16 activation (src_bf2)
+  int64_t x_plane;        // bytes from the hi plane to the lo plane
   const uint8_t* wpacked;
-  float* y;
+  void* y;                // fp32 output, or the hi plane of a split-bf16 output (out_bf2: 1 = hi only, 2 = hi + lo)
+  int64_t y_plane;
+  int out_bf2;
   const float* bias;      // indexed by GEMM column (already expanded for mapped outputs) or null
   int relu;
   double* stat_sum;
@@ -50,7 +59,13 @@ struct UmmaArgs {
   int vec_store;          // groups of 4 columns are contiguous and 16-byte aligned in the output
   float* partial;         // split-K: raw accumulators [split][M][n_pad] (bias / activation / statistics run in the reduce)
   int n_pad;
+  int staged;             // dense rows (output pixel m at element m*y_sw): epilogue goes through a shared-memory tile
+  long long* trace;       // SAG_UMMA_TRACE: 8 clock stamps per CTA (debug)
 };
+#define UM_STAMP(slot)                                                                                          \
+  do {                                                                                                          \
+    if (a.trace != nullptr) a.trace[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64();  \
+  } while (0)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,6 +165,35 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 4 fp32 -> 4 bf16 hi (8 bytes) and 4 bf16 lo
+__device__ __forceinline__ void split4(const float* f, uint2& hi, uint2& lo) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 l0 = __floats2bfloat162_rn(f[0] - __low2float(h0), f[1] - __high2float(h0));
+  __nv_bfloat162 l1 = __floats2bfloat162_rn(f[2] - __low2float(h1), f[3] - __high2float(h1));
+  hi = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+}
+// store one value of a split-bf16 tensor (element index e from the hi plane base)
+__device__ __forceinline__ void store_bf2_1(void* yhi, int64_t plane, int64_t e, float v, int planes) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  reinterpret_cast<__nv_bfloat16*>(yhi)[e] = h;
+  if (planes == 2)
+    reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(yhi) + plane)[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void store_bf2_4(void* yhi, int64_t plane, int64_t e, const float* v, int planes) {
+  uint2 hi, lo;
+  split4(v, hi, lo);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yhi) + e) = hi;
+  if (planes == 2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(yhi) + plane) + e) = lo;
+}
+
 // sum of v[c] over the 32 lanes for 16 columns at once (transposing butterfly, 16 shuffles): afterwards the lanes
 // with an even index hold the total of column ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
 __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
@@ -185,11 +229,14 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-// VEC: every 8-element K group lies inside one tap and is contiguous + 16-byte aligned in memory (Cin % 8 == 0).
-// PF: K chunks whose global loads are in flight per producer thread (register prefetch distance).
-template <int BN, int NSPLIT, bool VEC, int PF>
-__global__ void __launch_bounds__(UM_THREADS, (BN <= 64 && PF <= 2 ? 2 : 1))
+// SRC: 0 = fp32 activations, element-wise gather; 1 = fp32, every 8-element K group lies inside one tap and is
+// contiguous + 16-byte aligned (Cin % 8 == 0): vector gather; 2 = split-bf16 planes, same alignment rule: cp.async gather.
+constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2;
+template <int BN, int NSPLIT, int SRC>
+__global__ void __launch_bounds__(UM_THREADS, (BN <= 64 ? 2 : 1))
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) {
+  constexpr bool VEC = SRC == SRC_F32_VEC;
+  constexpr int PF = 1;
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
@@ -221,9 +268,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     if (tid == 0) s_any_valid = 0;
     __syncthreads();
     if (tid < UM_BM && m0 + tid < M) {
-      int64_t m = m0 + tid;
-      int j = (int)(m % g.PW);
-      int i = (int)((m / g.PW) % g.PH);
+      const uint32_t mu = (uint32_t)(m0 + tid);
+      const uint32_t qd = mu / (uint32_t)g.PW;
+      const int j = (int)(mu - qd * (uint32_t)g.PW);
+      const int i = (int)(qd % (uint32_t)g.PH);
       const int oy = g.oy0 + i * g.osy, ox = g.ox0 + j * g.osx;
       bool any = false;
       for (int c = 0; c < BN && !any; ++c) {
@@ -238,6 +286,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   }
 
   // ---- one-time setup ----
+  if (tid == 0) UM_STAMP(0);
   if (tid < BN) { s_sum[tid] = 0.f; s_sqs[tid] = 0.f; }
   if (warp == UM_PRODUCER_WARPS) {
     if (lane == 0) {
@@ -256,129 +305,251 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  if (tid == 0) UM_STAMP(1);
 
   if (warp < UM_PRODUCER_WARPS) {
     // ================================ producers ================================
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
     int iy0[4], ix0[4];
-    const float* img[4];
+    int64_t img[4];                             // element offset of the row's image
     bool rok[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int r = it * 32 + (tid >> 3);
       const int64_t m = m0 + r;
       rok[it] = m < M;
-      iy0[it] = 0; ix0[it] = 0; img[it] = a.x;
-      if (rok[it]) {
-        int j = (int)(m % g.PW);
-        int64_t q = m / g.PW;
-        int i = (int)(q % g.PH);
-        int n = (int)(q / g.PH);
-        iy0[it] = i * g.isy;
-        ix0[it] = j * g.isx;
-        img[it] = a.x + (int64_t)n * g.H * g.W * g.x_ld;
+      iy0[it] = 0; ix0[it] = 0; img[it] = 0;
+      if (rok[it]) {                              // M < 2^31 (checked on the host): 32-bit decode
+        const uint32_t mu = (uint32_t)m;
+        const uint32_t q = mu / (uint32_t)g.PW, j = mu - q * (uint32_t)g.PW;
+        const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
+        iy0[it] = (int)i * g.isy;
+        ix0[it] = (int)j * g.isx;
+        img[it] = (int64_t)n * g.H * g.W * g.x_ld;
       }
     }
-    // loads of one K chunk into registers (zero outside the image / beyond K)
-    auto load_chunk = [&](int kc, float (&f)[4][8]) {
-      if (kc >= kc_end) return;
-      const int kk = kc * UM_BK + jchunk * 8;
-      if (VEC) {
-        const int t = kk / g.Cin;
-        const int ci = kk - t * g.Cin;
-        const bool kok = kk < a.K;
-        const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int iy = iy0[it] + dy, ix = ix0[it] + dx;
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
-            const float4* p = reinterpret_cast<const float4*>(img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci);
-            v0 = __ldg(p);
-            v1 = __ldg(p + 1);
-          }
-          f[it][0] = v0.x; f[it][1] = v0.y; f[it][2] = v0.z; f[it][3] = v0.w;
-          f[it][4] = v1.x; f[it][5] = v1.y; f[it][6] = v1.z; f[it][7] = v1.w;
-        }
-      } else {
-        const int t = kk / g.Cin;
-        const int ci0 = kk - t * g.Cin;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          int tt = t, ci = ci0;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = 0.f;
-            if (rok[it] && kk + e < a.K) {
-              const int iy = iy0[it] + g.dy[tt], ix = ix0[it] + g.dx[tt];
-              if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
-                v = __ldg(img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci);
-            }
-            f[it][e] = v;
-            if (++ci == g.Cin) { ci = 0; ++tt; }
-          }
-        }
-      }
-    };
     int stage = 0;
     uint32_t phase = 0;
-    // split hi/lo, store into the swizzled stage, publish it
-    auto store_chunk = [&](int kc, float (&f)[4][8]) {
-      mbar_wait(bar_empty + 8 * stage, phase ^ 1);     // the MMAs that read this stage last time round have completed
+    // claim the next stage: wait until the MMAs that read it last time round have completed, start the weight copy
+    auto claim_stage = [&](int kc) -> uint32_t {
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
       const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
       if (tid == 0) {
         mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
         bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
                  PLANES * B_PLANE, bar_full + 8 * stage);
       }
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = it * 32 + (tid >> 3);
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
-        uint4 hi, lo;
-        split8(f[it], hi, lo);
-        st_shared_v4(st_base + off, hi);
-        if (PLANES == 2) st_shared_v4(st_base + UM_A_PLANE + off, lo);
-      }
-      fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * stage);
-      if (++stage == S) { stage = 0; phase ^= 1; }
+      return st_base;
     };
-    float f[PF][4][8];
-#pragma unroll
-    for (int p = 0; p < PF; ++p) load_chunk(kc_begin + p, f[p]);
+
+    if (SRC == SRC_BF2) {
+      // ---- split-bf16 source: 16-byte cp.async per (row, K group) and plane, up to DEPTH chunks in flight ----
+      const char* xhi = reinterpret_cast<const char*>(a.x);
+      // Up to S-1 chunks are in flight (issued, not yet published).  The oldest one is published BEFORE the next
+      // stage is claimed: claiming waits for the MMAs of chunk kc-S, and the tensor pipe must already hold chunk
+      // kc-S+1 by then or it would idle for a whole producer round trip between consecutive chunks.
+      int pending = 0, pub_stage = 0;
+      auto publish = [&]() {                        // the oldest outstanding chunk has landed
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * pub_stage);
+        if (++pub_stage == S) pub_stage = 0;
+        --pending;
+      };
 #pragma unroll 1
-    for (int kc = kc_begin; kc < kc_end; kc += PF) {
-#pragma unroll
-      for (int p = 0; p < PF; ++p) {
-        if (kc + p < kc_end) {
-          store_chunk(kc + p, f[p]);
-          load_chunk(kc + p + PF, f[p]);
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        if (pending == S - 1) {                     // wait for the oldest group only: S-2 newer ones stay in flight
+          switch (S) {
+            case 2: cp_async_wait<0>(); break;
+            case 3: cp_async_wait<1>(); break;
+            case 4: cp_async_wait<2>(); break;
+            case 5: cp_async_wait<3>(); break;
+            default: cp_async_wait<4>(); break;
+          }
+          publish();
+          if (tid == 0 && kc == kc_begin + S - 1) UM_STAMP(2);
         }
+        const int kk = kc * UM_BK + jchunk * 8;
+        const int t = kk / g.Cin;
+        const int ci = kk - t * g.Cin;
+        const bool kok = kk < a.K;
+        const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
+        const uint32_t st_base = claim_stage(kc);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 32 + (tid >> 3);
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
+          const int iy = iy0[it] + dy, ix = ix0[it] + dx;
+          const bool ok = kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+          const char* src = ok ? xhi + 2 * (img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci) : xhi;
+          cp_async16(st_base + off, src, ok ? 16u : 0u);
+          if (PLANES == 2) cp_async16(st_base + UM_A_PLANE + off, src + (ok ? a.x_plane : 0), ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        ++pending;
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      // drain in order: each remaining group is published as soon as it (and everything older) has landed
+      while (pending > 0) {
+        switch (pending) {
+          case 1: cp_async_wait<0>(); break;
+          case 2: cp_async_wait<1>(); break;
+          case 3: cp_async_wait<2>(); break;
+          case 4: cp_async_wait<3>(); break;
+          default: cp_async_wait<4>(); break;
+        }
+        publish();
+      }
+    } else {
+      // ---- fp32 source: gather into registers, split hi/lo, store into the swizzled stage ----
+      const float* xf = reinterpret_cast<const float*>(a.x);
+#pragma unroll 1
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        float f[4][8];
+        const int kk = kc * UM_BK + jchunk * 8;
+        const int t = kk / g.Cin;
+        const int ci0 = kk - t * g.Cin;
+        if (VEC) {
+          const bool kok = kk < a.K;
+          const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int iy = iy0[it] + dy, ix = ix0[it] + dx;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
+              const float4* p = reinterpret_cast<const float4*>(xf + img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci0);
+              v0 = __ldg(p);
+              v1 = __ldg(p + 1);
+            }
+            f[it][0] = v0.x; f[it][1] = v0.y; f[it][2] = v0.z; f[it][3] = v0.w;
+            f[it][4] = v1.x; f[it][5] = v1.y; f[it][6] = v1.z; f[it][7] = v1.w;
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            int tt = t, ci = ci0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = 0.f;
+              if (rok[it] && kk + e < a.K) {
+                const int iy = iy0[it] + g.dy[tt], ix = ix0[it] + g.dx[tt];
+                if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
+                  v = __ldg(xf + img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci);
+              }
+              f[it][e] = v;
+              if (++ci == g.Cin) { ci = 0; ++tt; }
+            }
+          }
+        }
+        const uint32_t st_base = claim_stage(kc);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 32 + (tid >> 3);
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
+          uint4 hi, lo;
+          split8(f[it], hi, lo);
+          st_shared_v4(st_base + off, hi);
+          if (PLANES == 2) st_shared_v4(st_base + UM_A_PLANE + off, lo);
+        }
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
 
     // ================================ epilogue ================================
+    if (tid == 0) UM_STAMP(3);
     if (KC > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
     }
+    if (tid == 0) UM_STAMP(4);
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
     const int64_t m = m0 + r;
     const bool row_ok = m < M;
-    float* yrow = a.y;
+    if (a.staged) {
+      // ---- staged epilogue: accumulator -> (bias, activation) -> padded fp32 tile in the (now idle) stage ring ->
+      //      coalesced whole-row writes; batch-norm statistics are column sums of the same tile ----
+      constexpr uint32_t PITCH = BN * 4 + 16;           // +16 B: the 16-byte row stores of a quarter warp hit 32 banks
+      const uint32_t stile = tiles;
+      constexpr int HALF = BN / 2;
+      const bool raw = a.partial != nullptr;
+#pragma unroll 1
+      for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 16) {
+        float v[16];
+        if (KC > 0) {
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        }
+        if (!raw) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n_base + c0 + e;
+            float b = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
+            float w = v[e] + b;
+            if (a.relu) w = fmaxf(w, 0.f);
+            v[e] = w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          st_shared_v4(stile + (uint32_t)r * PITCH + (uint32_t)(c0 + e) * 4u,
+                       make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");      // the 8 epilogue warps only
+      constexpr int F4_PER_ROW = BN / 4;
+      constexpr int ROWS_PER_ITER = 32 / F4_PER_ROW;      // BN=128: 1 row per warp instruction, 64: 2, 32: 4
+      const int lr = lane / F4_PER_ROW, lc = (lane % F4_PER_ROW) * 4;
+      const int ncols = raw ? a.n_pad : a.Ntot;
+      if (n_base + lc < ncols) {
+#pragma unroll 2
+        for (int rb = warp * ROWS_PER_ITER; rb < UM_BM; rb += UM_PRODUCER_WARPS * ROWS_PER_ITER) {
+          const int rr = rb + lr;
+          const int64_t mm = m0 + rr;
+          if (mm >= M) continue;
+          float4 w4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                       : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
+          if (raw) {
+            *reinterpret_cast<float4*>(a.partial + ((int64_t)blockIdx.z * M + mm) * a.n_pad + n_base + lc) = w4;
+          } else {
+            const int64_t eoff = mm * g.y_sw + n_base + lc;
+            if (a.out_bf2) { const float t4[4] = {w4.x, w4.y, w4.z, w4.w}; store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2); }
+            else *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + eoff) = w4;
+          }
+        }
+      }
+      if (a.stat_sum != nullptr && !raw) {
+        constexpr int PARTS = UM_PRODUCERS / BN;          // threads per column
+        const int c = tid % BN, part = tid / BN;
+        const int rows_valid = (int)((M - m0) < UM_BM ? (M - m0) : UM_BM);
+        float cs = 0.f, cq = 0.f;
+        for (int rr = part; rr < rows_valid; rr += PARTS) {
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)c * 4u));
+          cs += x;
+          cq = fmaf(x, x, cq);
+        }
+        if (n_base + c < a.Ntot) { atomicAdd(&s_sum[c], cs); atomicAdd(&s_sqs[c], cq); }
+      }
+      if (tid == 0) UM_STAMP(5);
+    } else {
+    int64_t yoff = 0;                     // element offset of this row's output pixel
     int oy = 0, ox = 0;
     if (row_ok) {
-      int j = (int)(m % g.PW);
-      int64_t qq = m / g.PW;
-      int i = (int)(qq % g.PH);
-      int n = (int)(qq / g.PH);
-      oy = g.oy0 + i * g.osy;
-      ox = g.ox0 + j * g.osx;
-      yrow = a.y + (int64_t)n * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
+      const uint32_t mu = (uint32_t)m;
+      const uint32_t qq = mu / (uint32_t)g.PW, j = mu - qq * (uint32_t)g.PW;
+      const uint32_t n = qq / (uint32_t)g.PH, i = qq - n * (uint32_t)g.PH;
+      oy = g.oy0 + (int)i * g.osy;
+      ox = g.ox0 + (int)j * g.osx;
+      yoff = (int64_t)n * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
     }
+    float* yf = reinterpret_cast<float*>(a.y);
     const bool do_stats = a.stat_sum != nullptr && a.partial == nullptr;
     constexpr int HALF = BN / 2;
 #pragma unroll 1
@@ -408,33 +579,35 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         v[e] = w;
       }
       if (row_ok) {
-        if (a.col_off == nullptr) {
-          if (a.vec_store) {
+        if (a.vec_store) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              if (n0 + e < a.Ntot) *reinterpret_cast<float4*>(yrow + (n0 + e)) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n0 + e < a.Ntot) yrow[(int64_t)(n0 + e) * g.y_sc] = v[e];
+          for (int e = 0; e < 16; e += 4) {
+            const int n = n0 + e;
+            if (n >= a.Ntot) continue;
+            int64_t eoff;
+            if (a.col_off == nullptr) {
+              eoff = yoff + n;
+            } else {
+              if (!((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)) continue;
+              eoff = yoff + a.col_off[n];
+            }
+            if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, v + e, a.out_bf2);
+            else *reinterpret_cast<float4*>(yf + eoff) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
           }
         } else {
-          if (a.vec_store) {
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const int n = n0 + e;
-              if (n < a.Ntot && (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim &&
-                  (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)
-                *reinterpret_cast<float4*>(yrow + a.col_off[n]) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            if (n >= a.Ntot) continue;
+            int64_t eoff;
+            if (a.col_off == nullptr) {
+              eoff = yoff + (int64_t)n * g.y_sc;
+            } else {
+              if (!((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)) continue;
+              eoff = yoff + a.col_off[n];
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int n = n0 + e;
-              if (n < a.Ntot && (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim &&
-                  (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)
-                yrow[a.col_off[n]] = v[e];
-            }
+            if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, v[e], a.out_bf2);
+            else yf[eoff] = v[e];
           }
         }
       }
@@ -455,6 +628,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       }
     }
     tc_fence_before();
+    if (tid == 0) UM_STAMP(5);
+    }
   } else {
     // ================================ MMA issuer ================================
     if (lane == 0) {
@@ -462,6 +637,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       uint32_t phase = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         mbar_wait(bar_full + 8 * stage, phase);
+        if (kc == kc_begin) UM_STAMP(6);
         tc_fence_after();
         const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
         const uint32_t a_hi = st_base, a_lo = st_base + UM_A_PLANE;
@@ -480,6 +656,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
       if (KC > 0) umma_commit(bar_acc);          // accumulator complete
+      UM_STAMP(7);
     }
     __syncwarp();
   }
@@ -604,25 +781,30 @@ __global__ void __launch_bounds__(128) splitk_reduce_kernel(const __grid_constan
       const int i = (int)(q % g.PH);
       const int b = (int)(q / g.PH);
       const int oy = g.oy0 + i * g.osy, ox = g.ox0 + j * g.osx;
-      float* yrow = a.y + (int64_t)b * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
-      if (a.col_off == nullptr) {
-        if (a.vec_store) {
-          *reinterpret_cast<float4*>(yrow + n) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < a.Ntot) yrow[(int64_t)(n + e) * g.y_sc] = v[e];
+      const int64_t yoff = (int64_t)b * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
+      float* yf = reinterpret_cast<float*>(a.y);
+      if (a.vec_store) {
+        bool ok = true;
+        int64_t eoff = yoff + n;
+        if (a.col_off != nullptr) {
+          ok = (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim;
+          eoff = yoff + a.col_off[n];
+        }
+        if (ok) {
+          if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, v, a.out_bf2);
+          else *reinterpret_cast<float4*>(yf + eoff) = make_float4(v[0], v[1], v[2], v[3]);
         }
       } else {
-        if (a.vec_store) {
-          if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)
-            *reinterpret_cast<float4*>(yrow + a.col_off[n]) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < a.Ntot && (unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim &&
-                (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)
-              yrow[a.col_off[n + e]] = v[e];
+        for (int e = 0; e < 4; ++e) {
+          if (n + e >= a.Ntot) continue;
+          int64_t eoff = yoff + (int64_t)(n + e) * g.y_sc;
+          if (a.col_off != nullptr) {
+            if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
+            eoff = yoff + a.col_off[n + e];
+          }
+          if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, v[e], a.out_bf2);
+          else yf[eoff] = v[e];
         }
       }
 #pragma unroll
@@ -644,19 +826,19 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, int NSPLIT, bool VEC, int PF>
+template <int BN, int NSPLIT, int SRC>
 int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStream_t st) {
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
-  constexpr bool TWO_PER_SM = BN <= 64 && PF <= 2;
+  constexpr bool TWO_PER_SM = BN <= 64;
   UmmaArgs a = a_in;
   const int budget = (TWO_PER_SM ? 110 : 220) * 1024 - UM_BAR_BYTES - 1024;
   int S = budget / STAGE_BYTES;
-  if (S > 4) S = 4;
+  if (S > 6) S = 6;    // the cp.async drain handles at most 5 groups in flight
   if (S < 2) S = 2;
   a.stages = S;
   const size_t smem = (size_t)UM_BAR_BYTES + 1024 + (size_t)S * STAGE_BYTES;
-  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, VEC, PF>;
+  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC>;
   static bool attr_set = false;
   if (!attr_set) {
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
@@ -664,26 +846,55 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   dim3 grid((unsigned)cdiv64(M, UM_BM), (unsigned)nt, (unsigned)Z);
+  // debug: SAG_UMMA_TRACE=<grid.x> prints the average phase durations (clocks) of the first launch with that grid.x
+  static const int trace_grid = env_int("SAG_UMMA_TRACE", 0);
+  static int traced = 0;
+  if (trace_grid > 0 && (int)grid.x == trace_grid && Z == 1 && traced < env_int("SAG_UMMA_TRACE_N", 1)) {
+    ++traced;
+    const size_t n = (size_t)grid.x * grid.y * 8;
+    long long* dtr = nullptr;
+    cudaMalloc(&dtr, n * sizeof(long long));
+    cudaMemset(dtr, 0, n * sizeof(long long));
+    a.trace = dtr;
+    cudaStreamSynchronize(st);
+    kern<<<grid, UM_THREADS, smem, st>>>(g, a);
+    cudaStreamSynchronize(st);
+    std::vector<long long> tr(n);
+    cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dtr);
+    double d[8] = {0};
+    const char* names[8] = {"setup (alloc+barriers)", "start -> first chunk published", "start -> producer loop done",
+                            "start -> accumulator ready", "epilogue (acc ready -> done)", "start -> MMA saw first chunk",
+                            "start -> all MMAs issued", "total (entry -> epilogue done)"};
+    const size_t ctas = n / 8;
+    for (size_t c = 0; c < ctas; ++c) {
+      const long long* t = &tr[c * 8];
+      d[0] += t[1] - t[0]; d[1] += t[2] ? t[2] - t[0] : 0; d[2] += t[3] - t[0]; d[3] += t[4] - t[0];
+      d[4] += t[5] - t[4]; d[5] += t[6] - t[0]; d[6] += t[7] - t[0]; d[7] += t[5] - t[0];
+    }
+    fprintf(stderr, "[umma trace] BN=%d NSPLIT=%d SRC=%d grid=(%u,%u) KC=%d stages=%d\n", BN, NSPLIT, SRC, grid.x, grid.y, a.KC, S);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, "[umma trace]   %-34s %10.0f clk\n", names[i], d[i] / ctas);
+    SAG_LAUNCH_CHECK();
+    return SAG_OK;
+  }
   kern<<<grid, UM_THREADS, smem, st>>>(g, a);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
 
 template <int BN, int NSPLIT>
-int launch_ns(const GatherGeom& g, const UmmaArgs& a, int nt, bool vec, int Z, cudaStream_t st) {
-  if (!vec) return launch_cfg<BN, NSPLIT, false, 1>(g, a, nt, Z, st);
-  static const int pf = env_int("SAG_UMMA_PF", 1);
-  switch (pf) {
-    case 1: return launch_cfg<BN, NSPLIT, true, 1>(g, a, nt, Z, st);
-    case 2: return launch_cfg<BN, NSPLIT, true, 2>(g, a, nt, Z, st);
-    default: return launch_cfg<BN, NSPLIT, true, 3>(g, a, nt, Z, st);
+int launch_ns(const GatherGeom& g, const UmmaArgs& a, int nt, int src, int Z, cudaStream_t st) {
+  switch (src) {
+    case SRC_BF2: return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, nt, Z, st);
+    case SRC_F32_VEC: return launch_cfg<BN, NSPLIT, SRC_F32_VEC>(g, a, nt, Z, st);
+    default: return launch_cfg<BN, NSPLIT, SRC_F32>(g, a, nt, Z, st);
   }
 }
 
 template <int BN>
-int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, bool vec, int Z, cudaStream_t st) {
-  if (planes == 2) return launch_ns<BN, 3>(g, a, nt, vec, Z, st);
-  return launch_ns<BN, 1>(g, a, nt, vec, Z, st);
+int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, int src, int Z, cudaStream_t st) {
+  if (planes == 2) return launch_ns<BN, 3>(g, a, nt, src, Z, st);
+  return launch_ns<BN, 1>(g, a, nt, src, Z, st);
 }
 
 }  // namespace
@@ -836,50 +1047,73 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   const int BN = tile_width(N), NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
   const int64_t tiles = cdiv64(M, UM_BM) * NT;
   int Z = 1;
-  if (enabled && tiles > 0 && tiles < 120 && KC >= 8) {
-    Z = (int)(296 / tiles);                 // aim at ~2 CTAs worth of work per SM
-    if (Z > KC / 4) Z = KC / 4;             // at least 4 chunks per split
-    if (Z > 32) Z = 32;
-    if (Z < 1) Z = 1;
+  if (enabled && tiles > 0 && KC >= 8) {
+    // Cost model in units of one K chunk: a CTA costs its chunks plus ~6 chunks of fixed work (pipeline fill, epilogue);
+    // CTAs run in waves of `slots`; splitting adds the partial round trip (~5 % + the reduce launch).  Pick the split
+    // that minimises the wave-quantised time -- it both fills the SMs of small layers and trims ragged last waves.
+    const int64_t slots = 148 * (BN <= 64 ? 2 : 1);
+    double best = 0.0;
+    for (int z = 1; z <= 32 && z <= KC / 4; ++z) {
+      const int64_t waves = cdiv64(tiles * z, slots);
+      double t = (double)waves * ((double)cdiv(KC, z) + 6.0);
+      if (z > 1) t = t * 1.05 + 4.0;
+      if (z == 1 || t < best * 0.97) { best = t; Z = z; }   // split only for a clear (>3 %) win
+    }
   }
   if (scratch_bytes) *scratch_bytes = Z > 1 ? sizeof(float) * (size_t)Z * (size_t)M * (size_t)(NT * BN) : 0;
   return Z;
 }
 
-int launch_gather_gemm_umma(const float* x, const UmmaWeights& w, float* y, const GatherGeom& g, const Epilogue& ep,
+int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st) {
   SAG_REQUIRE(w.packed != nullptr || w.KC == 0, SAG_ESTATE, "tcgen05 path: weights are not packed");
   SAG_REQUIRE(g.T * g.Cin == w.K, SAG_EINVAL, "tcgen05 path: geometry K %d does not match packed K %d", g.T * g.Cin, w.K);
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   if (M == 0) return SAG_OK;
-  SAG_REQUIRE(cdiv64(M, UM_BM) < (1ll << 31), SAG_EINVAL, "tcgen05 path: too many rows");
+  SAG_REQUIRE(M < (1ll << 31), SAG_EINVAL, "tcgen05 path: too many rows");
   UmmaArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.wpacked = reinterpret_cast<const uint8_t*>(w.packed); a.y = y;
+  a.x = x.p; a.x_plane = x.plane;
+  a.wpacked = reinterpret_cast<const uint8_t*>(w.packed);
+  a.y = y.p; a.y_plane = y.plane;
+  a.out_bf2 = y.fmt == ACT_BF2 ? (y.plane != 0 ? 2 : 1) : 0;
   a.relu = ep.relu; a.stat_sum = ep.stat_sum; a.stat_sqs = ep.stat_sqs;
   a.col_off = w.col_off; a.col_dy = w.col_dy; a.col_dx = w.col_dx;
   a.bias = w.col_off != nullptr ? w.col_bias : ep.bias;
   a.oh_lim = oh_lim; a.ow_lim = ow_lim;
   a.Ntot = w.N; a.K = w.K; a.KC = w.KC;
   a.n_pad = w.NT * w.BN;
-  const bool aligned_y = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+  const bool aligned_y = (reinterpret_cast<uintptr_t>(y.p) & 15) == 0 && (y.plane & 15) == 0;
   if (w.col_off != nullptr) {
     SAG_REQUIRE(ep.stat_sum == nullptr, SAG_EUNSUPPORTED, "tcgen05 path: statistics with mapped outputs");
     a.vec_store = (w.vec4 && aligned_y && g.y_sn % 4 == 0 && g.y_sh % 4 == 0 && (g.y_sw * g.osx) % 4 == 0 && ow_lim % 4 == 0) ? 1 : 0;
   } else {
     a.vec_store = (g.y_sc == 1 && aligned_y && w.N % 4 == 0 && g.y_sn % 4 == 0 && g.y_sh % 4 == 0 && g.y_sw % 4 == 0) ? 1 : 0;
   }
-  // vector gather: every 8-element K group is one tap's 8 contiguous, 16-byte aligned floats
-  bool vec = (g.Cin % 8 == 0) && ((g.x_ld * g.isx) % 4 == 0) && ((g.x_ld * g.W) % 4 == 0) &&
-             ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (int t = 0; t < g.T && vec; ++t) vec = (g.dx[t] * g.x_ld) % 4 == 0;
+  // vector gather: every 8-element K group is one tap's 8 contiguous, 16-byte aligned elements
+  const int elt = x.fmt == ACT_BF2 ? 8 : 4;     // elements per 16 bytes
+  bool vec = (g.Cin % 8 == 0) && ((g.x_ld * g.isx) % elt == 0) && ((g.x_ld * g.W) % elt == 0) &&
+             ((reinterpret_cast<uintptr_t>(x.p) & 15) == 0) && (x.plane & 15) == 0;
+  for (int t = 0; t < g.T && vec; ++t) vec = (g.dx[t] * g.x_ld) % elt == 0;
+  int src = vec ? SRC_F32_VEC : SRC_F32;
+  if (x.fmt == ACT_BF2) {
+    SAG_REQUIRE(vec, SAG_EUNSUPPORTED, "tcgen05 path: split-bf16 activations need 16-byte aligned 8-channel groups (Cin %d, ld %lld)",
+                g.Cin, (long long)g.x_ld);
+    SAG_REQUIRE(w.planes == 1 || x.plane != 0, SAG_EINVAL, "tcgen05 path: bf16x3 needs the lo plane of the activation");
+    src = SRC_BF2;
+  }
   int Z = scratch != nullptr ? umma_split_k(w.K, w.N, M, nullptr) : 1;
   if (Z > 1) a.partial = scratch;
+  // staged epilogue: split-K partials always; direct outputs when pixel m sits at element m*y_sw and rows vectorise
+  const bool dense_rows = w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
+                          g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh;
+  static const int staged_on = env_int("SAG_UMMA_STAGED", 1);
+  a.staged = (staged_on && (Z > 1 || (dense_rows && a.vec_store))) ? 1 : 0;
   int r;
   switch (w.BN) {
-    case 32: r = launch_bn<32>(g, a, w.NT, w.planes, vec, Z, st); break;
-    case 64: r = launch_bn<64>(g, a, w.NT, w.planes, vec, Z, st); break;
-    case 128: r = launch_bn<128>(g, a, w.NT, w.planes, vec, Z, st); break;
+    case 32: r = launch_bn<32>(g, a, w.NT, w.planes, src, Z, st); break;
+    case 64: r = launch_bn<64>(g, a, w.NT, w.planes, src, Z, st); break;
+    case 128: r = launch_bn<128>(g, a, w.NT, w.planes, src, Z, st); break;
     default: set_error("tcgen05 path: unsupported tile width %d", w.BN); return SAG_EINVAL;
   }
   SAG_TRY(r);

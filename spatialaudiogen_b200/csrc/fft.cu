@@ -10,6 +10,7 @@
 // float64 exactly as the reference builds them (np.cos in float64 -> tf.constant(float32)).
 #include "common.cuh"
 #include "fft_device.cuh"
+#include <cuda_bf16.h>
 #include <mutex>
 #include <cmath>
 
@@ -63,7 +64,7 @@ int fft_prepare(int n) {   // create tables ahead of time (outside stream captur
 // grid (n_frames_launch, rows); frame index = fbase + blockIdx.x.
 __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, int n_samples, int hop, const FftPlan p,
                                                    int fbase, int frame0, int n_frames_out, float2* __restrict__ cplx_out,
-                                                   int mag0, int n_mag, float* __restrict__ mag_out) {
+                                                   int mag0, int n_mag, const ActView mag_out) {
   extern __shared__ __align__(16) float2 smem[];
   float2* buf0 = smem;
   float2* buf1 = smem + p.n;
@@ -76,23 +77,32 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, 
     float2* o = cplx_out + ((int64_t)row * n_frames_out + (f - frame0)) * p.n;
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) o[i] = res[i];
   }
-  if (mag_out != nullptr && f >= mag0 && f < mag0 + n_mag) {
-    float* o = mag_out + ((int64_t)row * n_mag + (f - mag0)) * p.n;
+  if (mag_out.p != nullptr && f >= mag0 && f < mag0 + n_mag) {
+    const int64_t e0 = ((int64_t)row * n_mag + (f - mag0)) * p.n;
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
       float2 v = res[i];
-      o[i] = hypotf(v.x, v.y);       // tf.abs(complex64)
+      const float a = hypotf(v.x, v.y);       // tf.abs(complex64)
+      if (mag_out.fmt == ACT_F32) {
+        reinterpret_cast<float*>(mag_out.p)[e0 + i] = a;
+      } else {                                // split-bf16 planes for the tensor-core encoder
+        const __nv_bfloat16 h = __float2bfloat16_rn(a);
+        reinterpret_cast<__nv_bfloat16*>(mag_out.p)[e0 + i] = h;
+        if (mag_out.plane != 0)
+          reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(mag_out.p) + mag_out.plane)[e0 + i] =
+              __float2bfloat16_rn(a - __bfloat162float(h));
+      }
     }
   }
 }
 
 int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int n_frames_total, int frame0,
-                int n_frames_out, float* cplx_out, int mag0, int n_mag, float* mag_out, cudaStream_t st) {
+                int n_frames_out, float* cplx_out, int mag0, int n_mag, const ActView& mag_out, cudaStream_t st) {
   SAG_REQUIRE(rows > 0 && wind > 0 && hop > 0, SAG_EINVAL, "stft: bad arguments");
   SAG_REQUIRE((int64_t)(n_frames_total - 1) * hop + wind <= n_samples, SAG_EINVAL,
               "stft: %d frames of %d (hop %d) exceed %d samples", n_frames_total, wind, hop, n_samples);
   int lo = n_frames_total, hi = 0;
   if (cplx_out != nullptr && n_frames_out > 0) { lo = std::min(lo, frame0); hi = std::max(hi, frame0 + n_frames_out); }
-  if (mag_out != nullptr && n_mag > 0) { lo = std::min(lo, mag0); hi = std::max(hi, mag0 + n_mag); }
+  if (mag_out.p != nullptr && n_mag > 0) { lo = std::min(lo, mag0); hi = std::max(hi, mag0 + n_mag); }
   if (hi <= lo) return SAG_OK;
   SAG_REQUIRE(lo >= 0 && hi <= n_frames_total, SAG_EINVAL, "stft: frame range [%d,%d) outside [0,%d)", lo, hi, n_frames_total);
   FftPlan p;

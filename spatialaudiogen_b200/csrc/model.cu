@@ -160,6 +160,23 @@ struct Fwd {
   int prec;
   int cat = PROF_CONV;
   bool dry() const { return ar.dry; }
+  bool tc() const { return prec != SAG_PREC_FP32; }
+
+  // activation buffer in the format the contractions of this precision read
+  Act alloc_act(int64_t pixels, int64_t ld) {
+    Act a;
+    a.ld = ld;
+    if (!tc()) {
+      a.v = ActView(ar.alloc<float>(pixels * ld));
+    } else {
+      const int planes = prec == SAG_PREC_BF16X3 ? 2 : 1;
+      const int64_t plane_bytes = ((pixels * ld * 2 + 255) / 256) * 256;
+      char* p = ar.alloc<char>(plane_bytes * planes);
+      a.v = ActView(p, ACT_BF2, planes == 2 ? plane_bytes : 0);
+    }
+    return a;
+  }
+  Act alloc_f32(int64_t pixels, int64_t ld) { return Act(ar.alloc<float>(pixels * ld), ld); }
 
   const float* W(const std::string& name, int* err) {
     auto it = h->weights.find(name);
@@ -177,12 +194,14 @@ struct Fwd {
     }
     return it->second.p;
   }
-  void tap(const std::string& name, const float* p, std::vector<int64_t> shape, int64_t ld = 0) {
+  void tap(const std::string& name, const Act& a, std::vector<int64_t> shape, int64_t ld = 0) {
     if (dry()) return;
     DevTensor t;
-    t.p = const_cast<float*>(p);
+    t.p = reinterpret_cast<float*>(a.v.p);
     t.shape = shape;
-    t.ld = ld ? ld : shape.back();
+    t.ld = ld ? ld : (a.ld ? a.ld : shape.back());
+    t.fmt = a.v.fmt;
+    t.plane = a.v.plane;
     h->ends[name] = t;
     h->end_order.push_back(name);
   }
@@ -195,19 +214,18 @@ struct Fwd {
     return (!dry() && bytes > 0 && bytes <= ar.scratch_cap) ? ar.scratch : nullptr;
   }
 
-  // tfw.conv_2d (core.py:156-220) on an NHWC view: x has pixel stride x_ld, y has pixel stride y_ld.
-  int conv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
-           int cout, int sh, int sw, int same, bool bias, int relu, float* y, int64_t y_ld, double* ssum, double* ssqs,
-           int* oh, int* ow) {
+  // tfw.conv_2d (core.py:156-220) on an NHWC view: x has pixel stride x.ld, y has pixel stride y.ld.
+  int conv(const Act& x, int n, int hh, int ww, int cin, const std::string& scope, int kh, int kw, int cout, int sh,
+           int sw, int same, bool bias, int relu, const Act& y, double* ssum, double* ssqs, int* oh, int* ow) {
     GatherGeom g;
-    SAG_TRY(make_conv_geom(&g, n, hh, ww, cin, x_ld, kh, kw, cout, sh, sw, same, y_ld, oh, ow));
-    if (prec != SAG_PREC_FP32 && !same && x_ld == cin && cin < 8 && (kw * cin) % 8 == 0) {
+    SAG_TRY(make_conv_geom(&g, n, hh, ww, cin, x.ld, kh, kw, cout, sh, sw, same, y.ld, oh, ow));
+    if (tc() && !same && x.ld == cin && cin < 8 && (kw * cin) % 8 == 0) {
       // VALID conv over a dense image with few channels: a kernel row's kw*cin inputs are contiguous in memory, so
       // it becomes one tap of kw*cin "channels" (HWIO weights already have that K order) -> vector gather
       g.T = kh; g.Cin = kw * cin;
       for (int r = 0; r < kh; ++r) { g.dy[r] = (short)r; g.dx[r] = 0; g.widx[r] = (short)r; }
     }
-    float* scratch = prec != SAG_PREC_FP32 ? splitk(g.T * g.Cin, cout, (int64_t)g.N * g.PH * g.PW) : nullptr;
+    float* scratch = tc() ? splitk(g.T * g.Cin, cout, (int64_t)g.N * g.PH * g.PW) : nullptr;
     if (dry()) return SAG_OK;
     int err = SAG_OK;
     const float* w = W(scope + "/weights", &err);
@@ -215,9 +233,11 @@ struct Fwd {
     SAG_TRY(err);
     Epilogue ep{b, relu, ssum, ssqs};
     const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
-    if (prec == SAG_PREC_FP32) {
-      ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
-      return launch_gather_gemm_ffma(x, w, y, g, ep, st);
+    const double esz_in = x.v.fmt == ACT_BF2 ? (x.v.plane ? 4.0 : 2.0) : 4.0, esz_out = y.v.fmt == ACT_BF2 ? (y.v.plane ? 4.0 : 2.0) : 4.0;
+    ProfScope ps(cat, 2.0 * M * K * cout, esz_in * (double)n * hh * ww * cin + 4.0 * K * cout + esz_out * M * cout, st);
+    if (!tc()) {
+      SAG_REQUIRE(x.v.fmt == ACT_F32 && y.v.fmt == ACT_F32, SAG_EINVAL, "fp32 contraction on a split-bf16 tensor");
+      return launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st);
     }
     const std::string key = scope + "#" + std::to_string(prec);
     auto it = h->umma.find(key);
@@ -226,29 +246,26 @@ struct Fwd {
       SAG_TRY(umma_pack_weights(w, g.T * g.Cin, cout, cout, prec, &uw, st));
       it = h->umma.emplace(key, uw).first;
     }
-    ProfScope ps(cat, 2.0 * M * K * cout, 4.0 * ((double)n * hh * ww * cin + K * cout + M * cout), st);
-    return launch_gather_gemm_umma(x, it->second, y, g, ep, 0, 0, scratch, st);
+    return launch_gather_gemm_umma(x.v, it->second, y.v, g, ep, 0, 0, scratch, st);
   }
 
   // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
-  int deconv(const float* x, int n, int hh, int ww, int cin, int64_t x_ld, const std::string& scope, int kh, int kw,
-             int cout, int sh, int sw, int relu, float* y, int row0, int row1, int64_t y_sn, int64_t y_sh,
-             int64_t y_sw, int64_t y_sc) {
+  int deconv(const Act& x, int n, int hh, int ww, int cin, const std::string& scope, int kh, int kw, int cout, int sh,
+             int sw, int relu, const Act& y, int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw, int64_t y_sc) {
     float* scratch = nullptr;
-    if (prec != SAG_PREC_FP32) {
+    if (tc()) {
       GatherGeom g0;
       int a0, b0;
-      SAG_TRY(make_deconv_subpixel_geom(&g0, n, hh, ww, cin, x_ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc, &a0, &b0));
+      SAG_TRY(make_deconv_subpixel_geom(&g0, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc, &a0, &b0));
       scratch = splitk(g0.T * cin, sh * sw * cout, (int64_t)g0.N * g0.PH * g0.PW);
     }
     if (dry()) return SAG_OK;
     int err = SAG_OK;
-    const float* w = Wp(scope + "/weights", &err);
     const float* b = W(scope + "/biases", &err);
     SAG_TRY(err);
     Epilogue ep{b, relu, nullptr, nullptr};
-    if (prec != SAG_PREC_FP32) {
-      // one sub-pixel GEMM for the whole layer: N = sh*sw*cout columns, (kh/sh)*(kw/sw) taps
+    if (tc()) {
+      // one sub-pixel GEMM for the whole layer: N = sh*sw*cout columns, ceil(kh/sh)*ceil(kw/sw) taps
       const int order = y_sc == 1 ? 0 : 1;
       const std::string key = scope + "#" + std::to_string(prec);
       auto it = h->umma.find(key);
@@ -261,34 +278,35 @@ struct Fwd {
       }
       GatherGeom g;
       int oh_lim, ow_lim;
-      SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x_ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
+      SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
                                         &oh_lim, &ow_lim));
       g.Cout = it->second.N;
       const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
       ProfScope ps(PROF_DECONV, 2.0 * M * K * g.Cout, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st);
-      return launch_gather_gemm_umma(x, it->second, y, g, ep, oh_lim, ow_lim, scratch, st);
+      return launch_gather_gemm_umma(x.v, it->second, y.v, g, ep, oh_lim, ow_lim, scratch, st);
     }
+    const float* w = Wp(scope + "/weights", &err);
+    SAG_TRY(err);
     for (int py = 0; py < sh; ++py)
       for (int px = 0; px < sw; ++px) {
         GatherGeom g;
-        int r = make_deconv_phase_geom(&g, n, hh, ww, cin, x_ld, kh, kw, cout, sh, sw, py, px, row0, row1, y_sn, y_sh,
+        int r = make_deconv_phase_geom(&g, n, hh, ww, cin, x.ld, kh, kw, cout, sh, sw, py, px, row0, row1, y_sn, y_sh,
                                        y_sw, y_sc);
         if (r == 1) continue;
         SAG_TRY(r);
         const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
         ProfScope ps(PROF_DECONV, 2.0 * M * K * cout, 4.0 * (M * cin / (sh * sw) + K * cout + M * cout), st);
-        SAG_TRY(launch_gather_gemm(prec, x, w, y, g, ep, st));
+        SAG_TRY(launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st));
       }
     return SAG_OK;
   }
 
-  // tfw.fully_connected (core.py:43-93) on rows with stride x_ld / y_ld
-  int fc(const float* x, int rows, int in, int64_t x_ld, const std::string& scope, int out, int relu, float* y,
-         int64_t y_ld) {
+  // tfw.fully_connected (core.py:43-93) on rows with stride x.ld / y.ld
+  int fc(const Act& x, int rows, int in, const std::string& scope, int out, int relu, const Act& y) {
     int oh, ow;
     const int saved = cat;
     cat = PROF_FC;
-    int r = conv(x, 1, 1, rows, in, x_ld, scope, 1, 1, out, 1, 1, 0, true, relu, y, y_ld, nullptr, nullptr, &oh, &ow);
+    int r = conv(x, 1, 1, rows, in, scope, 1, 1, out, 1, 1, 0, true, relu, y, nullptr, nullptr, &oh, &ow);
     cat = saved;
     return r;
   }
@@ -305,8 +323,10 @@ static BnBuf alloc_bn(Arena& ar, int c) {
   return b;
 }
 
-// ResNet18.inference_ops(truncate_at='conv5_2') with batch statistics (resnet.py:123-190; model.py:189-201)
-int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int Wd, float* y, Arena& ar,
+// ResNet18.inference_ops(truncate_at='conv5_2') with batch statistics (resnet.py:123-190; model.py:189-201).
+// x: fp32 (B,H,W,3).  The result lands in `y_out` when given (must be in the precision's activation format), else in a
+// fresh arena tensor; *y_act receives it.
+int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int Wd, Act* y_act, Arena& ar,
                    cudaStream_t st) {
   Fwd f{h, ar, st, h->cfg.precision};
   const std::string p = scope + "/";
@@ -324,21 +344,22 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     SAG_CHECK_CUDA(cudaMemsetAsync(b.sum, 0, sizeof(double) * 2 * c, st));
     return SAG_OK;
   };
+  const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;   // bytes per activation element
 
   // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
   int oh, ow;
   int OH1 = (H + 1) / 2, OW1 = (Wd + 1) / 2;
-  float* c1 = ar.alloc<float>((int64_t)B * OH1 * OW1 * 64);
+  Act c1 = f.alloc_f32((int64_t)B * OH1 * OW1, 64);
   BnBuf b1 = alloc_bn(ar, 64);
   SAG_TRY(zero_bn(b1, 64));
-  if (f.prec == SAG_PREC_FP32) {
-    SAG_TRY(f.conv(x, B, H, Wd, 3, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, 64, b1.sum, b1.sqs, &oh, &ow));
+  if (!f.tc()) {
+    SAG_TRY(f.conv(Act(x, 3), B, H, Wd, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, b1.sum, b1.sqs, &oh, &ow));
   } else {
     // tensor-core route: explicit TF-SAME border + a zero 4th channel (NHWC4), kernel rows widened to 8 taps so that
-    // one row = 8 pixels x 4 channels = 32 contiguous, 16-byte aligned floats -> 7 taps of 32 "channels" (K = 224)
+    // one row = 8 pixels x 4 channels = 32 contiguous, 16-byte aligned elements -> 7 taps of 32 "channels" (K = 224)
     int pt = same_pad_before(H, 7, 2, &oh), pl = same_pad_before(Wd, 7, 2, &ow);
     const int Hp = (oh - 1) * 2 + 7, Wp = (((ow - 1) * 2 + 8) + 3) / 4 * 4;
-    float* xp = ar.alloc<float>((int64_t)B * Hp * Wp * 4);
+    Act xp = f.alloc_act((int64_t)B * Hp * Wp, 4);
     GatherGeom g;
     memset(&g, 0, sizeof(g));
     g.N = B; g.H = Hp; g.W = Wp; g.Cin = 32; g.x_ld = 4;
@@ -358,20 +379,20 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
         it = h->umma.emplace(key, uw).first;
       }
       {
-        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * ((double)H * Wd * 3 + (double)Hp * Wp * 4), st);
-        SAG_TRY(launch_pad_nhwc3_to_nhwc4(x, B, H, Wd, pt, pl, Hp, Wp, xp, st));
+        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * (double)H * Wd * 3 + act_b * B * (double)Hp * Wp * 4, st);
+        SAG_TRY(launch_pad_nhwc3_to_nhwc4(x, B, H, Wd, pt, pl, Hp, Wp, xp.v, st));
       }
       Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
-      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, 4.0 * B * ((double)Hp * Wp * 4 + (double)oh * ow * 64), st);
-      SAG_TRY(launch_gather_gemm_umma(xp, it->second, c1, g, ep, 0, 0, scratch, st));
+      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)Hp * Wp * 4 + 4.0 * B * (double)oh * ow * 64, st);
+      SAG_TRY(launch_gather_gemm_umma(xp.v, it->second, c1.v, g, ep, 0, 0, scratch, st));
     }
   }
   SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
-  float* cur = ar.alloc<float>((int64_t)B * ph * pw * 64);
+  Act cur = f.alloc_act((int64_t)B * ph * pw, 64);
   if (!ar.dry) {
-    ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * 64 * ((double)oh * ow + (double)ph * pw), st);
-    SAG_TRY(launch_bn_relu_maxpool(c1, b1.scale, b1.shift, B, oh, ow, 64, cur, st));
+    ProfScope ps(PROF_POINTWISE, 0, B * 64.0 * (4.0 * oh * ow + act_b * ph * pw), st);
+    SAG_TRY(launch_bn_relu_maxpool(c1.f32(), b1.scale, b1.shift, B, oh, ow, 64, cur.v, st));
   }
   int ch = ph, cw = pw, cc = 64;
 
@@ -380,37 +401,35 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     const int s = b.first ? 2 : 1;
     const int nh = (ch + s - 1) / s, nw = (cw + s - 1) / s;
     const int64_t npix = (int64_t)B * nh * nw;
-    const float* shortcut = cur;
+    ActView shortcut = cur.v;
     if (b.first) {                                      // resnet.py:211-212: 1x1/s conv, no BN, no bias
-      float* sc = ar.alloc<float>(npix * b.cout);
-      SAG_TRY(f.conv(cur, B, ch, cw, cc, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, b.cout, nullptr,
-                     nullptr, &oh, &ow));
-      shortcut = sc;
+      Act sc = f.alloc_f32(npix, b.cout);
+      SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, nullptr, nullptr, &oh, &ow));
+      shortcut = sc.v;
     }
-    float* r1 = ar.alloc<float>(npix * b.cout);
-    float* a1 = ar.alloc<float>(npix * b.cout);
-    float* r2 = ar.alloc<float>(npix * b.cout);
-    float* out = (std::string(b.name) == "conv5_2" && y != nullptr) ? y : ar.alloc<float>(npix * b.cout);
+    Act r1 = f.alloc_f32(npix, b.cout);
+    Act a1 = f.alloc_act(npix, b.cout);
+    Act r2 = f.alloc_f32(npix, b.cout);
+    Act out = f.alloc_act(npix, b.cout);
     BnBuf s1 = alloc_bn(ar, b.cout), s2 = alloc_bn(ar, b.cout);
     SAG_TRY(zero_bn(s1, b.cout));
     SAG_TRY(zero_bn(s2, b.cout));
-    SAG_TRY(f.conv(cur, B, ch, cw, cc, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, b.cout, s1.sum, s1.sqs,
-                   &oh, &ow));
+    SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, s1.sum, s1.sqs, &oh, &ow));
     SAG_TRY(bn_finalize(q + "/conv_1", s1, b.cout, npix));
     if (!ar.dry) {
-      ProfScope ps(PROF_POINTWISE, 0, 8.0 * npix * b.cout, st);
-      SAG_TRY(launch_bn_apply(r1, s1.scale, s1.shift, nullptr, 1, a1, npix, b.cout, st));
+      ProfScope ps(PROF_POINTWISE, 0, (4.0 + act_b) * npix * b.cout, st);
+      SAG_TRY(launch_bn_apply(r1.f32(), s1.scale, s1.shift, ActView(), 1, a1.v, npix, b.cout, st));
     }
-    SAG_TRY(f.conv(a1, B, nh, nw, b.cout, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, b.cout, s2.sum,
-                   s2.sqs, &oh, &ow));
+    SAG_TRY(f.conv(a1, B, nh, nw, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, s2.sum, s2.sqs, &oh, &ow));
     SAG_TRY(bn_finalize(q + "/conv_2", s2, b.cout, npix));
     if (!ar.dry) {
-      ProfScope ps(PROF_POINTWISE, 0, 12.0 * npix * b.cout, st);
-      SAG_TRY(launch_bn_apply(r2, s2.scale, s2.shift, shortcut, 1, out, npix, b.cout, st));
+      ProfScope ps(PROF_POINTWISE, 0, (4.0 + 2.0 * act_b) * npix * b.cout, st);
+      SAG_TRY(launch_bn_apply(r2.f32(), s2.scale, s2.shift, shortcut, 1, out.v, npix, b.cout, st));
     }
     f.tap(scope + "/" + b.name, out, {B, nh, nw, b.cout});
     cur = out; ch = nh; cw = nw; cc = b.cout;
   }
+  *y_act = cur;
   return SAG_OK;
 }
 
@@ -437,6 +456,7 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   const int K = c.sep_num_tracks;
   const int wind = d.wind_size, hop = wind / 4;
   const int T = d.snd_dur;
+  const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;
 
   // ---- STFT (model.py:369; myutils.py:119-147) ----------------------------------------------------------------
   const int n_enc = d.enc_tt - d.enc_ss;                  // 127
@@ -449,16 +469,16 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   } else if (unet) {
     S = ar.alloc<float>((int64_t)B * n_msk * wind * 2);
   }
-  float* mag = ar.alloc<float>((int64_t)B * n_enc * wind);
+  Act mag = f.alloc_act((int64_t)B * n_enc * wind, 1);
   if (!ar.dry) {
     ProfScope ps(PROF_STFT, 5.0 * wind * std::log2((double)wind) * B * (full ? d.n_stft_frames : n_enc),
-                 4.0 * B * ((double)d.snd_size + (double)n_enc * wind + (unet ? 2.0 * n_msk * wind : 0.0)), st);
+                 4.0 * B * (double)d.snd_size + act_b * B * (double)n_enc * wind + (unet ? 8.0 * B * n_msk * wind : 0.0), st);
     if (full)
-      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag, st));
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag.v, st));
     else
-      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, d.mask_ss, unet ? n_msk : 0, S, d.enc_ss, n_enc, mag, st));
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, d.mask_ss, unet ? n_msk : 0, S, d.enc_ss, n_enc, mag.v, st));
   }
-  if (full) f.tap("stft", S_all, {B, 1, d.n_stft_frames, wind, 2});
+  if (full) f.tap("stft", Act(S_all, 2), {B, 1, d.n_stft_frames, wind, 2});
   f.tap("audio_encoder/0", mag, {B, n_enc, wind, 1});
 
   // ---- audio encoder (model.py:161-187): enc_l written into the skip halves of the decoder's concat buffers ----
@@ -472,34 +492,32 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   }
   // cat[l] (l=1..5): pixel stride 2*C_l ; channels [0,C_l) decoder half, [C_l,2C_l) encoder skip -- except cat[5]
   // which is [enc5, fc-feats] (model.py:296).
-  float* cat[6] = {nullptr};
-  int64_t cat_ld[6] = {0};
-  float* enc_ptr[6];
-  enc_ptr[0] = mag;
+  Act cat[6], enc[6];
+  enc[0] = mag;
   for (int l = 1; l <= 5; ++l) {
-    cat_ld[l] = unet ? 2 * ecn[l] : ecn[l];
-    cat[l] = ar.alloc<float>((int64_t)B * eh[l] * ew[l] * cat_ld[l]);
-    enc_ptr[l] = cat[l] + ((unet && l < 5) ? ecn[l] : 0);
+    const int64_t ld = unet ? 2 * ecn[l] : ecn[l];
+    cat[l] = f.alloc_act((int64_t)B * eh[l] * ew[l], ld);
+    enc[l] = cat[l].channels((unet && l < 5) ? ecn[l] : 0);
   }
   for (int l = 0; l < 5; ++l) {
     int oh, ow;
-    SAG_TRY(f.conv(enc_ptr[l], B, eh[l], ew[l], ecn[l], l == 0 ? 1 : cat_ld[l], "audio_encoder/conv" + std::to_string(l + 1),
-                   kAudioKernel[l][0], kAudioKernel[l][1], ecn[l + 1], kAudioStride[l][0], kAudioStride[l][1], 0, true, 1,
-                   enc_ptr[l + 1], cat_ld[l + 1], nullptr, nullptr, &oh, &ow));
-    f.tap("audio_encoder/" + std::to_string(l + 1), enc_ptr[l + 1], {B, eh[l + 1], ew[l + 1], ecn[l + 1]}, cat_ld[l + 1]);
+    SAG_TRY(f.conv(enc[l], B, eh[l], ew[l], ecn[l], "audio_encoder/conv" + std::to_string(l + 1), kAudioKernel[l][0],
+                   kAudioKernel[l][1], ecn[l + 1], kAudioStride[l][0], kAudioStride[l][1], 0, true, 1, enc[l + 1], nullptr,
+                   nullptr, &oh, &ow));
+    f.tap("audio_encoder/" + std::to_string(l + 1), enc[l + 1], {B, eh[l + 1], ew[l + 1], ecn[l + 1]});
   }
   const int nt = eh[5];                                    // 3 time steps of the bottleneck
   SAG_REQUIRE(T % nt == 0, SAG_EUNSUPPORTED, "snd_dur %d not divisible by %d localization steps", T, nt);
 
-  // ---- visual towers (model.py:189-201) ---------------------------------------------------------------------
+  // ---- visual towers + bottleneck (model.py:189-239) ------------------------------------------------------------
   const int D = d.feat_dim;
-  float* feats = ar.alloc<float>((int64_t)B * nt * D);
+  Act feats = f.alloc_act((int64_t)B * nt, D);
   int foff = 0;
   // bottleneck audio (model.py:207-230): (B,3,6*512) -> fc 1024, as a (1 x ew5) VALID conv over the strided enc5
   {
     int oh, ow;
-    SAG_TRY(f.conv(enc_ptr[5], B * nt, 1, ew[5], ecn[5], cat_ld[5], "bottleneck/audio-fc", 1, ew[5], 1024, 1, 1, 0, true, 1,
-                   feats + foff, D, nullptr, nullptr, &oh, &ow));
+    SAG_TRY(f.conv(enc[5], B * nt, 1, ew[5], ecn[5], "bottleneck/audio-fc", 1, ew[5], 1024, 1, 1, 0, true, 1,
+                   feats.channels(foff), nullptr, nullptr, &oh, &ow));
     foff += 1024;
   }
   for (int v = 0; v < 2; ++v) {
@@ -508,13 +526,15 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
     const std::string k = v == 0 ? "video" : "flow";
     if (!ar.dry) SAG_REQUIRE(inp != nullptr, SAG_EINVAL, "forward: %s input is NULL but the encoder is enabled", k.c_str());
     const int fh = (c.frame_h + 31) / 32, fw = (c.frame_w + 31) / 32;
-    float* vf = ar.alloc<float>((int64_t)B * fh * fw * 512);
-    SAG_TRY(resnet18_tower(h, k + "_encoder", inp, B, c.frame_h, c.frame_w, vf, ar, st));
-    float* red = ar.alloc<float>((int64_t)B * fh * fw * 128);
-    SAG_TRY(f.fc(vf, B * fh * fw, 512, 512, "bottleneck/" + k + "-fc-red", 128, 1, red, 128));
-    float* vfc = ar.alloc<float>((int64_t)B * 512);
-    SAG_TRY(f.fc(red, B, fh * fw * 128, (int64_t)fh * fw * 128, "bottleneck/" + k + "-fc", 512, 1, vfc, 512));
-    if (!ar.dry) SAG_TRY(launch_tile_rows(vfc, 512, feats + foff, D, B, nt, 512, st));     // tf.tile (model.py:232)
+    Act vf;
+    SAG_TRY(resnet18_tower(h, k + "_encoder", inp, B, c.frame_h, c.frame_w, &vf, ar, st));
+    Act red = f.alloc_act((int64_t)B * fh * fw, 128);
+    SAG_TRY(f.fc(vf, B * fh * fw, 512, "bottleneck/" + k + "-fc-red", 128, 1, red));
+    Act vfc = f.alloc_act(B, 512);
+    Act red_rows = red;
+    red_rows.ld = (int64_t)fh * fw * 128;                   // NHWC flatten (model.py:224-226): one row per window
+    SAG_TRY(f.fc(red_rows, B, fh * fw * 128, "bottleneck/" + k + "-fc", 512, 1, vfc));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(vfc.v, 512, feats.channels(foff).v, D, B, nt, 512, st));     // tf.tile (model.py:232)
     foff += 512;
   }
   f.tap("bottleneck", feats, {B, nt, D});
@@ -523,37 +543,36 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   const int n3 = 3 * (K + 1);
   float* loc = ar.alloc<float>((int64_t)B * nt * n3);
   {
-    const float* x = feats;
+    Act x = feats;
     int in = D;
     for (int i = 0; i < c.n_loc_fc; ++i) {
-      float* y = ar.alloc<float>((int64_t)B * nt * c.loc_fc_units[i]);
-      SAG_TRY(f.fc(x, B * nt, in, in, "localization/fc" + std::to_string(i + 1), c.loc_fc_units[i], 1, y, c.loc_fc_units[i]));
+      Act y = f.alloc_act((int64_t)B * nt, c.loc_fc_units[i]);
+      SAG_TRY(f.fc(x, B * nt, in, "localization/fc" + std::to_string(i + 1), c.loc_fc_units[i], 1, y));
       x = y;
       in = c.loc_fc_units[i];
     }
-    SAG_TRY(f.fc(x, B * nt, in, in, "localization/fc" + std::to_string(c.n_loc_fc + 1), n3, 0, loc, n3));
+    SAG_TRY(f.fc(x, B * nt, in, "localization/fc" + std::to_string(c.n_loc_fc + 1), n3, 0, Act(loc, n3)));
   }
-  f.tap("localization", loc, {B, nt, 3, 1, K + 1});
+  f.tap("localization", Act(loc, K + 1), {B, nt, 3, 1, K + 1});
 
   // ---- separation (model.py:273-354) --------------------------------------------------------------------------
   float* x_sep = ar.alloc<float>((int64_t)B * K * T);
   if (!unet) {
     // NO_SEPARATION: x_sep = mono[snd_contx/2 : +snd_dur] (model.py:274-280); audio is (B,snd_size,1)
-    if (!ar.dry) SAG_TRY(launch_tile_rows(audio + d.snd_contx / 2, d.snd_size, x_sep, T, B, K, T, st));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(ActView(audio + d.snd_contx / 2), d.snd_size, ActView(x_sep), T, B, K, T, st));
   } else {
-    float* sf = ar.alloc<float>((int64_t)B * nt * 512);
-    SAG_TRY(f.fc(feats, B * nt, D, D, "separation/fc-feats", 512, 1, sf, 512));
-    if (!ar.dry) SAG_TRY(launch_tile_rows(sf, 512, cat[5] + 512, cat_ld[5], B * nt, ew[5], 512, st));   // model.py:295-296
+    Act sf = f.alloc_act((int64_t)B * nt, 512);
+    SAG_TRY(f.fc(feats, B * nt, D, "separation/fc-feats", 512, 1, sf));
+    if (!ar.dry) SAG_TRY(launch_tile_rows(sf.v, 512, cat[5].channels(512).v, cat[5].ld, B * nt, ew[5], 512, st));   // model.py:295-296
     // deconv5..2 with ReLU into the lower halves of cat4..1 (model.py:299-310)
     for (int l = 4; l >= 1; --l) {
       const int cout = ecn[l];
       const int OH = (eh[l + 1] - 1) * kAudioStride[l][0] + kAudioKernel[l][0];
       const int OW = (ew[l + 1] - 1) * kAudioStride[l][1] + kAudioKernel[l][1];
       SAG_REQUIRE(OH == eh[l] && OW == ew[l], SAG_EUNSUPPORTED, "decoder/encoder shape mismatch at level %d", l);
-      SAG_TRY(f.deconv(cat[l + 1], B, eh[l + 1], ew[l + 1], (int)cat_ld[l + 1], cat_ld[l + 1],
-                       "separation/deconv" + std::to_string(l + 1), kAudioKernel[l][0], kAudioKernel[l][1], cout,
-                       kAudioStride[l][0], kAudioStride[l][1], 1, cat[l], 0, OH, (int64_t)OH * OW * cat_ld[l],
-                       (int64_t)OW * cat_ld[l], cat_ld[l], 1));
+      SAG_TRY(f.deconv(cat[l + 1], B, eh[l + 1], ew[l + 1], (int)cat[l + 1].ld, "separation/deconv" + std::to_string(l + 1),
+                       kAudioKernel[l][0], kAudioKernel[l][1], cout, kAudioStride[l][0], kAudioStride[l][1], 1, cat[l], 0, OH,
+                       (int64_t)OH * OW * cat[l].ld, (int64_t)OW * cat[l].ld, cat[l].ld, 1));
     }
     // deconv1 (no ReLU): rows [r0,r1) only, written as (B, track, frame, freq) (model.py:319-330)
     const int OH = (eh[1] - 1) * kAudioStride[0][0] + kAudioKernel[0][0];
@@ -562,10 +581,10 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
     const int r0 = full ? 0 : d.mask_ss - d.mask_skip, r1 = full ? OH : d.mask_tt - d.mask_skip;
     const int nr = r1 - r0;
     float* mask = ar.alloc<float>((int64_t)B * K * nr * OW);
-    SAG_TRY(f.deconv(cat[1], B, eh[1], ew[1], (int)cat_ld[1], cat_ld[1], "separation/deconv1", kAudioKernel[0][0],
-                     kAudioKernel[0][1], K, kAudioStride[0][0], kAudioStride[0][1], 0, mask, r0, r1, (int64_t)K * nr * OW,
-                     OW, 1, (int64_t)nr * OW));
-    f.tap("separation/mask_logits", mask, {B, K, nr, OW});
+    SAG_TRY(f.deconv(cat[1], B, eh[1], ew[1], (int)cat[1].ld, "separation/deconv1", kAudioKernel[0][0], kAudioKernel[0][1], K,
+                     kAudioStride[0][0], kAudioStride[0][1], 0, Act(mask, 1), r0, r1, (int64_t)K * nr * OW, OW, 1,
+                     (int64_t)nr * OW));
+    f.tap("separation/mask_logits", Act(mask, OW), {B, K, nr, OW});
     // sigmoid mask x STFT -> istft -> crop (model.py:334-347; myutils.py:181-211)
     // frames [mask_ss, mask_tt) of the full STFT / rows [mask_ss-skip, ..) of the full mask are strided views the
     // kernel does not take: compact them first (test-only path, skip_unused == 0).
@@ -585,8 +604,8 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
       SAG_TRY(launch_istft(S2, m2, 1, B, K, n_msk, wind, 4, d.final_crop, T, x_sep, st));
     }
   }
-  if (unet) f.tap("separation/all_channels", x_sep, {B, 1, K, T});
-  else f.tap("separation/all_channels", x_sep, {B, 1, 1, T}, (int64_t)K * T);
+  if (unet) f.tap("separation/all_channels", Act(x_sep, T), {B, 1, K, T});
+  else f.tap("separation/all_channels", Act(x_sep, T), {B, 1, 1, T}, (int64_t)K * T);
 
   // ---- decode (model.py:424-432) -------------------------------------------------------------------------------
   if (!ar.dry) {

@@ -9,6 +9,8 @@ struct DevTensor {
   float* p = nullptr;
   std::vector<int64_t> shape;
   int64_t ld = 0;      // stride of the second-to-last dimension (== shape.back() when contiguous)
+  int fmt = 0;         // ACT_F32, or ACT_BF2 (split bf16 planes: p = hi plane, lo plane `plane` bytes further)
+  int64_t plane = 0;
   int64_t numel() const {
     int64_t n = 1;
     for (auto s : shape) n *= s;
@@ -39,6 +41,22 @@ struct Arena {
   }
 };
 
+// A tensor of the forward: NHWC pixels with `ld` elements between consecutive pixels, stored as fp32 (FFMA path,
+// raw conv outputs awaiting batch-norm, final outputs) or as split-bf16 planes (everything the tensor cores read).
+struct Act {
+  ActView v;
+  int64_t ld = 0;
+  Act() {}
+  Act(const float* p, int64_t ld_) : v(p), ld(ld_) {}
+  float* f32() const { return reinterpret_cast<float*>(v.p); }
+  // same tensor, channel range starting at `c`
+  Act channels(int64_t c) const {
+    Act a = *this;
+    a.v.p = reinterpret_cast<char*>(v.p) + c * (v.fmt == ACT_BF2 ? 2 : 4);
+    return a;
+  }
+};
+
 }  // namespace sag
 
 struct sag_handle {
@@ -63,8 +81,9 @@ int build_expected(sag_handle* h);
 int derive_dims(const sag_config& c, sag_dims* d);
 int forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* out, Arena& ar, int B,
             cudaStream_t st);
-int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int W, float* y, Arena& ar,
+int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int W, Act* y, Arena& ar,
                    cudaStream_t st);
+int launch_act_to_f32(const ActView& src, float* dst, int64_t n, cudaStream_t st);   // pointwise.cu
 const char* last_error_cstr();
 int fft_prepare(int n);
 void istft_needed_frames(int n_frames, int wind, int n_overlap, int crop0, int n_out, int* f_lo, int* f_hi);

@@ -3,8 +3,39 @@
 // 32->3 mixing of model.py:424-432.  All are streaming kernels: float4 accesses, grid sized in multiples
 // of the SM count, one pass over the data.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace sag {
+
+// ---- split-bf16 activation stores / loads (ACT_BF2: hi = bf16(x), lo = bf16(x - hi)) ----
+__device__ __forceinline__ void store_act4(void* p, int fmt, int64_t plane, int64_t e, const float4& v) {
+  if (fmt == ACT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + e) = v;
+    return;
+  }
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + e) =
+      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  if (plane != 0) {
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+    __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(p) + plane) + e) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+  }
+}
+__device__ __forceinline__ float4 load_act4(const void* p, int fmt, int64_t plane, int64_t e) {
+  if (fmt == ACT_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + e));
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + e));
+  float4 v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                         __uint_as_float(h.y & 0xffff0000u));
+  if (plane != 0) {
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(
+        reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(p) + plane) + e));
+    v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xffff0000u);
+    v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xffff0000u);
+  }
+  return v;
+}
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -40,8 +71,8 @@ int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma,
 
 // ---- BN apply (+residual)(+relu): y = act(x*scale[c] + shift[c] + res) ; c % 4 == 0 ----
 __global__ void bn_apply_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const float4* __restrict__ res, int relu,
-                                float4* __restrict__ y, int64_t n4, int c4) {
+                                const float* __restrict__ shift, const ActView res, int relu, const ActView y, int64_t n4,
+                                int c4) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int cc = (int)(i % c4) * 4;
@@ -49,26 +80,25 @@ __global__ void bn_apply_kernel(const float4* __restrict__ x, const float* __res
     float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc));
     float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc));
     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (res != nullptr) {
-      float4 r = __ldg(res + i);
+    if (res.p != nullptr) {
+      float4 r = load_act4(res.p, res.fmt, res.plane, i * 4);
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    y[i] = v;
+    store_act4(y.p, y.fmt, y.plane, i * 4, v);
   }
 }
 
-int launch_bn_apply(const float* x, const float* scale, const float* shift, const float* residual, int relu,
-                    float* y, int64_t rows, int c, cudaStream_t st) {
+int launch_bn_apply(const float* x, const float* scale, const float* shift, const ActView& residual, int relu,
+                    const ActView& y, int64_t rows, int c, cudaStream_t st) {
   SAG_REQUIRE(c % 4 == 0, SAG_EINVAL, "bn_apply: channels %d not a multiple of 4", c);
   int64_t n4 = rows * c / 4;
   if (n4 == 0) return SAG_OK;
   int64_t blocks = cdiv64(n4, 256);
   int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale, shift,
-                                                    reinterpret_cast<const float4*>(residual), relu,
-                                                    reinterpret_cast<float4*>(y), n4, c / 4);
+  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale, shift, residual, relu, y, n4,
+                                                    c / 4);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -76,7 +106,7 @@ int launch_bn_apply(const float* x, const float* scale, const float* shift, cons
 // ---- fused BN + ReLU + max-pool 3x3/2 SAME (pad before 0: TF puts the odd pad cell after) ----
 __global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                        const float* __restrict__ shift, int n, int h, int w, int c, int oh, int ow,
-                                       int pt, int pl, float* __restrict__ y) {
+                                       int pt, int pl, const ActView y) {
   int c4 = c / 4;
   int64_t total = (int64_t)n * oh * ow * c4;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -108,12 +138,12 @@ __global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float*
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
     }
-    *reinterpret_cast<float4*>(y + i * 4) = m;
+    store_act4(y.p, y.fmt, y.plane, i * 4, m);
   }
 }
 
 int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
-                           float* y, cudaStream_t st) {
+                           const ActView& y, cudaStream_t st) {
   SAG_REQUIRE(c % 4 == 0, SAG_EINVAL, "maxpool: channels %d not a multiple of 4", c);
   int oh, ow;
   int pt = same_pad_before(h, 3, 2, &oh), pl = same_pad_before(w, 3, 2, &ow);
@@ -160,28 +190,58 @@ int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, doubl
   return SAG_OK;
 }
 
+// ---- split-bf16 (or fp32) activation -> dense fp32 (stage entry points / taps); n % 4 == 0 ----
+__global__ void act_to_f32_kernel(const ActView src, float4* __restrict__ dst, int64_t n4) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    dst[i] = load_act4(src.p, src.fmt, src.plane, i * 4);
+}
+
+int launch_act_to_f32(const ActView& src, float* dst, int64_t n, cudaStream_t st) {
+  SAG_REQUIRE(n % 4 == 0, SAG_EINVAL, "act_to_f32: %lld elements not a multiple of 4", (long long)n);
+  int64_t blocks = cdiv64(n / 4, 256);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return SAG_OK;
+  act_to_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), n / 4);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
 // ---- tf.tile replacement: dst[(g*reps + r)*dst_ld + 0..c) = src[g*src_ld + 0..c) ----
-__global__ void tile_rows_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
-                                 int64_t dst_ld, int groups, int reps, int c) {
+template <class T>
+__global__ void tile_rows_kernel(const T* __restrict__ src, int64_t src_ld, T* __restrict__ dst, int64_t dst_ld, int groups,
+                                 int reps, int c) {
   int64_t total = (int64_t)groups * reps * c;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int ch = (int)(i % c);
     int64_t row = i / c;
     int64_t gidx = row / reps;
-    dst[row * dst_ld + ch] = __ldg(src + gidx * src_ld + ch);
+    dst[row * dst_ld + ch] = src[gidx * src_ld + ch];
   }
 }
 
-int launch_tile_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int groups, int reps, int c,
+int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int64_t dst_ld, int groups, int reps, int c,
                      cudaStream_t st) {
   int64_t total = (int64_t)groups * reps * c;
   if (total == 0) return SAG_OK;
+  SAG_REQUIRE(src.fmt == dst.fmt && (src.plane != 0) == (dst.plane != 0), SAG_EINVAL, "tile_rows: format mismatch");
   int64_t blocks = cdiv64(total, 256);
   int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  tile_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, src_ld, dst, dst_ld, groups, reps, c);
-  SAG_LAUNCH_CHECK();
+  if (src.fmt == ACT_F32) {
+    tile_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src.p), src_ld,
+                                                             reinterpret_cast<float*>(dst.p), dst_ld, groups, reps, c);
+    SAG_LAUNCH_CHECK();
+  } else {
+    for (int pl = 0; pl < (src.plane != 0 ? 2 : 1); ++pl) {
+      tile_rows_kernel<unsigned short><<<(unsigned)blocks, 256, 0, st>>>(
+          reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(src.p) + pl * src.plane), src_ld,
+          reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(dst.p) + pl * dst.plane), dst_ld, groups, reps, c);
+      SAG_LAUNCH_CHECK();
+    }
+  }
   return SAG_OK;
 }
 
@@ -250,7 +310,7 @@ int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st) {
 
 // ---- (n,h,w,3) -> zero-bordered (n,hp,wp,4): one float4 store per output pixel ----
 __global__ void pad_nhwc3_to_nhwc4_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int hp, int wp,
-                                          float4* __restrict__ out) {
+                                          const ActView out) {
   const int64_t total = (int64_t)n * hp * wp;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -264,16 +324,17 @@ __global__ void pad_nhwc3_to_nhwc4_kernel(const float* __restrict__ x, int n, in
       const float* p = x + (((int64_t)b * h + iy) * w + ix) * 3;
       v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
     }
-    out[i] = v;
+    store_act4(out.p, out.fmt, out.plane, i * 4, v);
   }
 }
 
-int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, float* out, cudaStream_t st) {
+int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, const ActView& out,
+                              cudaStream_t st) {
   const int64_t total = (int64_t)n * hp * wp;
   int64_t blocks = cdiv64(total, 256);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  pad_nhwc3_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, h, w, pt, pl, hp, wp, reinterpret_cast<float4*>(out));
+  pad_nhwc3_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, h, w, pt, pl, hp, wp, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }

@@ -1,0 +1,92 @@
+"""W2XYZ: the reference's deploy driver (reference deploy.py:41-152) on top of libsag.so.
+
+Same construction (model_dir with train-params.txt + weights) and the same hot loop: consecutive 0.1 s windows in
+batches of 10, the last batch zero-padded (deploy.py:124-139 -- it matters: the visual towers use batch statistics),
+W taken from the input crop, rows [W, Y, Z, X] appended window after window (deploy.py:143-151).  The reference reads
+windows from disk through feeder.SampleReader; here the windows are handed in as arrays (`deploy_windows`), the
+on-disk reader is a "next" row.  `sess.run` becomes one sag_forward per batch on the caller's stream,
+with the host<->device copies on pinned buffers.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import myutils
+from .definitions import AUDIO, VIDEO, FLOW, NO_SEPARATION
+from .model import SptAudioGen, SptAudioGenParams
+
+
+def load_weights_file(path):
+    """name -> ndarray dict from an .npz written with np.savez (TF variable names, TF layouts: SURVEY.md App. B)."""
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+class W2XYZ(object):
+    def __init__(self, model_dir=None, params=None, weights=None, precision=None, device=None):
+        """model_dir: directory holding train-params.txt (reference myutils.load_params) and weights.npz; or pass
+        `params` (object with the fields load_params returns) and `weights` (dict) directly."""
+        if params is None:
+            params = myutils.load_params(model_dir)
+        self.params = params
+        self.duration = 0.1                                                        # deploy.py:49
+        self.batch_size = 10                                                       # deploy.py:50
+        num_sep = params.num_sep_tracks if params.separation != NO_SEPARATION else 1          # deploy.py:54
+        net_params = SptAudioGenParams(sep_num_tracks=num_sep, ctx_feats_fc_units=params.context_units,
+                                       loc_fc_units=params.loc_units, sep_freq_mask_fc_units=params.freq_mask_units,
+                                       sep_fft_window=params.fft_window)
+        self.model = SptAudioGen(ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
+                                 context=params.context, sample_duration=self.duration, encoders=list(params.encoders),
+                                 separation=params.separation, params=net_params, precision=precision, device=device)
+        self.audio_size = self.model.snd_dur + self.model.snd_contx - 1
+        self.video_size = int(self.duration * params.video_rate)
+        if weights is None:
+            weights = load_weights_file(os.path.join(model_dir, 'weights.npz'))
+        self.model.load_weights(weights)
+        B, dev = self.batch_size, self.model.device
+        H, W = self.model.dims_frame()
+        # pinned staging + device buffers, allocated once (the reference's placeholders, deploy.py:69-76)
+        self._h = {AUDIO: torch.zeros((B, self.audio_size, 1), dtype=torch.float32).pin_memory()}
+        for k in (VIDEO, FLOW):
+            if k in params.encoders:
+                self._h[k] = torch.zeros((B, self.video_size, H, W, 3), dtype=torch.float32).pin_memory()
+        self._d = {k: torch.empty_like(v, device=dev) for k, v in self._h.items()}
+        self._out = torch.empty((B, self.model.snd_dur, 3), dtype=torch.float32, device=dev)
+        self._out_h = torch.empty((B, self.model.snd_dur, 3), dtype=torch.float32).pin_memory()
+
+    def run_batch(self, audio, video=None, flow=None):
+        """One `sess.run(ambi_pred_t, feed_dict)` (deploy.py:141): host arrays of n <= batch_size windows in, host
+        (n, snd_dur, 3) predictions out.  The batch is zero-padded to batch_size like the reference."""
+        n = audio.shape[0]
+        srcs = {AUDIO: audio, VIDEO: video, FLOW: flow}
+        with torch.cuda.device(self.model.device):
+            for k, h in self._h.items():
+                if srcs[k] is None:
+                    raise ValueError('%s windows required by encoders=%s' % (k, self.params.encoders))
+                h[:n].copy_(torch.as_tensor(np.asarray(srcs[k], dtype=np.float32)))
+                if n != self.batch_size:
+                    h[n:].zero_()
+                self._d[k].copy_(h, non_blocking=True)
+            self.model.forward_into(self._d[AUDIO], self._d.get(VIDEO), self._d.get(FLOW), self._out)
+            self._out_h.copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self._out_h[:n].numpy().copy()
+
+    def deploy_windows(self, ambix_windows, video_windows=None, flow_windows=None):
+        """The loop of deploy.py:112-151.  ambix_windows (N, audio_size, C>=1) with W in channel 0; video / flow
+        (N, video_size, H, W, 3).  Returns (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
+        ambix_windows = np.asarray(ambix_windows)
+        N = ambix_windows.shape[0]
+        ss = self.model.snd_contx // 2
+        mono, pred = [], []
+        for b0 in range(0, N, self.batch_size):
+            a = np.asarray(ambix_windows[b0:b0 + self.batch_size], np.float64)
+            n = a.shape[0]
+            v = None if video_windows is None else video_windows[b0:b0 + n]
+            f = None if flow_windows is None else flow_windows[b0:b0 + n]
+            out = self.run_batch(a[:, :, :1], v, f)
+            pred.append(out.reshape(n * out.shape[1], out.shape[2]))
+            mono.append(np.copy(a[:, ss:ss + self.model.snd_dur, :1]).reshape(-1, 1))
+        mono = np.concatenate(mono, 0)
+        return np.concatenate((mono, np.concatenate(pred, 0)), 1)          # float64, like numpy promotes in deploy.py:151

@@ -1,0 +1,81 @@
+"""Evaluation pass of the reference's eval.py (reference eval.py:29-232) on top of libsag.so.
+
+Per batch of windows: forward (eval.py:90), the in-graph per-sample metrics (model.evaluation_ops, model.py:110-154),
+the Hilbert-envelope distance (myutils.py:109-116), amplitudes (eval.py:197-198) and the 84-direction RMS energy maps
+that feed the EMD (distance.py:41-52, ang_res=30) -- all as GPU kernels.  Rows come out in the reference's
+`eval-detailed.txt` format (`SampleID | <28 metric names>`, eval.py:125-133, 212-215); the two columns that need
+absent third-party solvers (mel_lsd: librosa, emd: pyemd -- SURVEY.md 8f) are written as nan.  With several ranks
+(one process per GPU) whole batches are sharded and the rows meet in one all-gather (dist.gather_rows).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import metrics as M
+
+ALL_METRICS = ['amplitude/predicted', 'amplitude/gt',
+               'mse/avg', 'mse/X', 'mse/Y', 'mse/Z',
+               'stft/avg', 'stft/X', 'stft/Y', 'stft/Z',
+               'lsd/avg', 'lsd/X', 'lsd/Y', 'lsd/Z',
+               'mel_lsd/avg', 'mel_lsd/X', 'mel_lsd/Y', 'mel_lsd/Z',
+               'snr/avg', 'snr/X', 'snr/Y', 'snr/Z',
+               'env_mse/avg', 'env_mse/X', 'env_mse/Y', 'env_mse/Z',
+               'emd/dir', 'emd/dir2']                                      # eval.py:125-132
+_COL = {k: i for i, k in enumerate(ALL_METRICS)}
+N_COLS = len(ALL_METRICS)
+
+
+def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False):
+    """pred, target (B, T, 3) CUDA, channels (Y, Z, X).  Returns (rows (B, 28) CUDA float32 in ALL_METRICS order,
+    maps or None).  maps = (rms_pred, rms_gt), each (B, 7, 12): energy maps of [W | pred or gt] * layout
+    (eval.py:147-148, 190), needs `mono` (B, T, 1)."""
+    res = M.window_metrics(pred, target, audio_rate)
+    B = pred.shape[0]
+    rows = torch.full((B, N_COLS), float('nan'), dtype=torch.float32, device=pred.device)
+    rows[:, _COL['amplitude/predicted']] = res['amp'][:, 0]
+    rows[:, _COL['amplitude/gt']] = res['amp'][:, 1]
+    for key, name in (('mse', 'mse'), ('stft', 'stft'), ('lsd', 'lsd'), ('snr', 'snr'), ('env', 'env_mse')):
+        v = res[key]
+        rows[:, _COL[name + '/avg']] = v.mean(1)                           # np.mean / np.nanmean over the 3 channels
+        for i, ch in enumerate('YZX'):                                     # filled by key, not by position (eval.py:159-171)
+            rows[:, _COL[name + '/' + ch]] = v[:, i]
+    maps = None
+    if rms_maps:
+        if mono is None:
+            raise ValueError('rms_maps needs the W channel (mono)')
+        lay = torch.ones((B, 1, 4), device=pred.device) if layout is None else torch.as_tensor(layout, device=pred.device).float()[:, None, :]
+        maps = (M.ambix_rms_map(torch.cat((mono, pred), 2) * lay, 30.), M.ambix_rms_map(torch.cat((mono, target), 2) * lay, 30.))
+    return rows, maps
+
+
+def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
+    """eval.py:140-201 for an iterable of dicts {'id': list, 'ambix': (B, snd_size, 4), 'video'/'flow': ..., 'mask': (B,4)}
+    (CUDA float32 tensors).  Returns (ids, rows (N, 28) CUDA)."""
+    ids, out = [], []
+    ss, t = model.snd_contx // 2, model.snd_dur                            # eval.py:67-68
+    for b in batches:
+        ambix = b['ambix']
+        audio_input = ambix[:, :, :1].contiguous()                          # eval.py:69
+        target = ambix[:, ss:ss + t, 1:].contiguous()                       # eval.py:70
+        pred = model.inference_ops(audio_input, video=b.get('video'), flow=b.get('flow'), is_training=False)
+        rows, _ = metric_rows(pred, target, mono=audio_input[:, ss:ss + t], layout=b.get('mask'), audio_rate=audio_rate,
+                              rms_maps=rms_maps)
+        ids.extend(b['id'])
+        out.append(rows)
+    return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
+
+
+def write_eval_detailed(path, sample_ids, rows):
+    """eval.py:212-215: header `SampleID | names`, then `<id> | v1 ... v28` (space-pipe-space separator)."""
+    rows = np.asarray(rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows)
+    with open(path, 'w') as f:
+        f.write('SampleID | {}\n'.format(' '.join(ALL_METRICS)))
+        for sid, r in zip(sample_ids, rows):
+            f.write('{} | {}\n'.format(sid, ' '.join([str(float(v)) for v in r])))
+
+
+def summarize(rows):
+    rows = np.asarray(rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows)
+    return OrderedDict((k, float(np.nanmean(rows[:, i])) if np.isfinite(rows[:, i]).any() else float('nan'))
+                       for k, i in _COL.items())

@@ -227,15 +227,25 @@ class SptAudioGen(object):
         ld = C.c_int64()
         L.check(lib.sag_get_tensor(self._h, name.encode(), C.byref(p), shape, C.byref(rank), C.byref(ld)))
         shp = [int(shape[k]) for k in range(rank.value)]
+        fmt, plane = C.c_int(), C.c_int64()
+        L.check(lib.sag_get_tensor_format(self._h, name.encode(), C.byref(fmt), C.byref(plane)))
         off = p.value - self._ws.data_ptr()
-        assert off >= 0 and off % 4 == 0
-        flat = self._ws[off:].view(torch.float32)
         strides = [1] * len(shp)
         if len(shp) >= 2:
             strides[-2] = int(ld.value)
             for k in range(len(shp) - 3, -1, -1):
                 strides[k] = strides[k + 1] * shp[k + 1]
-        return flat.as_strided(shp, strides)
+        if fmt.value == 0:
+            assert off >= 0 and off % 4 == 0
+            return self._ws[off:].view(torch.float32).as_strided(shp, strides)
+        # tensor-core path: the value is hi + lo of two bf16 planes (a copy, not a view)
+        assert off >= 0 and off % 2 == 0
+        span = sum((n - 1) * s for n, s in zip(shp, strides)) + 1
+        out = self._ws[off:off + 2 * span].view(torch.bfloat16).as_strided(shp, strides).float()
+        if plane.value:
+            o2 = off + plane.value
+            out = out + self._ws[o2:o2 + 2 * span].view(torch.bfloat16).as_strided(shp, strides).float()
+        return out
 
     def _collect_ends(self):
         """Views (aliasing the workspace, valid until the next forward) of the taps the reference keeps in

@@ -380,3 +380,63 @@ def test_metrics_match_oracle():
         assert tuple(g.shape) == (B,) + shape
         r = np.stack([O.ambix_rms_map(ambi[b], res) for b in range(B)])
         assert _rel(g, r) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+class _P(object):
+    """What myutils.load_params returns for a model_dir (reference myutils.py:40-85)."""
+    def __init__(self, encoders, separation='unet_mask'):
+        self.encoders, self.separation = encoders, separation
+        self.ambi_order, self.audio_rate, self.video_rate, self.context = 1, 48000, 10, 1.0
+        self.num_sep_tracks, self.fft_window = 32, 0.025
+        self.context_units, self.freq_mask_units, self.loc_units = [64, 128, 128], [256], [512, 512]
+
+
+def test_w2xyz_deploy_matches_reference_loop_with_zero_padded_tail():
+    """deploy.py:112-151: 13 windows -> one full batch of 10 and a zero-padded batch of 3 (batch statistics make the
+    padding visible in the video tower); rows [W, Y, Z, X], float64."""
+    from spatialaudiogen_b200.deploy import W2XYZ
+    enc = ['audio', 'video']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=21, stress=True)
+    N = 13
+    amb = np.concatenate([_audio(N, 31), _audio(N, 32), _audio(N, 33), _audio(N, 34)], axis=2)     # (N, 52799, 4)
+    vid = _video(N, 35)
+    ref = O.deploy_assemble(O.SptAudioGen(W, encoders=enc, separation='unet_mask'), amb, video_windows=vid)
+    w = W2XYZ(params=_P(enc), weights=W)
+    out = w.deploy_windows(amb, video_windows=vid)
+    assert out.dtype == np.float64 and out.shape == (N * 4800, 4) == ref.shape
+    assert np.array_equal(out[:, 0], amb[:, 24000:28800, 0].reshape(-1).astype(np.float64))   # W: bit-exact crop
+    assert _rel(out[:, 1:], ref[:, 1:]) < 1e-3
+
+
+def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
+    from spatialaudiogen_b200 import evaluate as E
+    rng = np.random.RandomState(3)
+    B = 4
+    gt = (rng.randn(B, 4800, 3) * 0.1).astype(np.float32)
+    pred = (gt + rng.randn(B, 4800, 3) * 0.02).astype(np.float32)
+    mono = (rng.randn(B, 4800, 1) * 0.1).astype(np.float32)
+    layout = np.ones((B, 4), np.float32)
+    layout[2, 2] = 0                                     # a WXY clip: no Z (feeder.py:312-314)
+    rows, maps = E.metric_rows(cu(pred), cu(gt), mono=cu(mono), layout=cu(layout), rms_maps=True)
+    rows = rows.cpu().numpy()
+    assert rows.shape == (B, 28) and E.ALL_METRICS[0] == 'amplitude/predicted' and E.ALL_METRICS[-1] == 'emd/dir2'
+    ref = O.SptAudioGen({}, encoders=['audio'], separation='unet_mask', dtype=torch.float64)
+    _, stft_r, lsd_r, mse_r, snr_r = ref.evaluation_ops(pred, gt, None, np.ones((B, 3), np.float32))
+    col = {k: i for i, k in enumerate(E.ALL_METRICS)}
+    for name, r in (('stft', stft_r), ('lsd', lsd_r), ('mse', mse_r), ('snr', snr_r)):
+        r = r.numpy()
+        assert np.allclose(rows[:, col[name + '/avg']], r.mean(1), rtol=2e-4, atol=1e-7)
+        for i, ch in enumerate('YZX'):                   # keyed by channel name, channel order of the model is Y,Z,X
+            assert np.allclose(rows[:, col[name + '/' + ch]], r[:, i], rtol=2e-4, atol=1e-7)
+    env_r = np.stack([O.compute_envelope_dist(pred[b], gt[b]) for b in range(B)])
+    assert np.allclose(rows[:, col['env_mse/X']], env_r[:, 2], rtol=2e-4)
+    assert np.isnan(rows[:, col['mel_lsd/avg']]).all() and np.isnan(rows[:, col['emd/dir']]).all()
+    for b in range(B):
+        rp = O.ambix_rms_map(np.concatenate((mono[b], pred[b]), 1) * layout[b], 30.)
+        assert _rel(maps[0][b], np.ascontiguousarray(rp)) < 1e-5
+    fn = str(tmp_path / 'eval-detailed.txt')
+    E.write_eval_detailed(fn, ['vid%d 0.5' % b for b in range(B)], rows)
+    lines = open(fn).read().splitlines()
+    assert lines[0] == 'SampleID | ' + ' '.join(E.ALL_METRICS) and len(lines) == B + 1
+    assert lines[1].startswith('vid0 0.5 | ') and len(lines[1].split(' | ')[1].split(' ')) == 28
