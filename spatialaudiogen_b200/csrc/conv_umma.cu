@@ -30,12 +30,17 @@ namespace {
 
 constexpr int UM_BM = 128;                  // rows per tile (UMMA M, one TMEM lane per row)
 constexpr int UM_BK = 64;                   // K elements per stage = one 128-byte swizzle atom of bf16
-constexpr int UM_PRODUCER_WARPS = 8;
-constexpr int UM_PRODUCERS = UM_PRODUCER_WARPS * 32;
-constexpr int UM_THREADS = UM_PRODUCERS + 32;
+constexpr int UM_PRODUCER_WARPS = 8;         // warps 0-7
+constexpr int UM_EPI_WARP0 = 8;              // warps 8-11: epilogue (warp % 4 == TMEM lane quadrant)
+constexpr int UM_EPI_WARPS = 4;
+constexpr int UM_MMA_WARP = 12;              // warp 12: TMEM allocation + MMA issue
+constexpr int UM_THREADS = 13 * 32;
+constexpr int UM_MAX_N = 1024;               // widest GEMM with batch-norm statistics / per-CTA column sums
+constexpr int UM_STAGING_BYTES = UM_BM * (32 * 4 + 16);
+constexpr long long UM_ROW_INVALID = (long long)0x8000000000000000ull;   // row beyond M (mapped outputs may have negative bases)
 constexpr int UM_A_PLANE = UM_BM * 128;     // bytes of one A plane per stage
 constexpr int UM_MAX_STAGES = 8;
-constexpr int UM_BAR_BYTES = 256;
+constexpr int UM_BAR_BYTES = 256;            // full[8] empty[8] tmem_full[2] tmem_empty[2] tmem slot
 
 struct UmmaArgs {
   const void* x;          // fp32 activation, or the hi plane of a split-bf16 activation (src_bf2)
@@ -59,14 +64,9 @@ struct UmmaArgs {
   int vec_store;          // groups of 4 columns are contiguous and 16-byte aligned in the output
   float* partial;         // split-K: raw accumulators [split][M][n_pad] (bias / activation / statistics run in the reduce)
   int n_pad;
-  int staged;             // dense rows (output pixel m at element m*y_sw): epilogue goes through a shared-memory tile
-  long long* trace;       // SAG_UMMA_TRACE: 8 clock stamps per CTA (debug)
+  int dense;              // output pixel m sits at element m*y_sw (no row decode)
+  int NT, Z;              // N tiles, K splits
 };
-#define UM_STAMP(slot)                                                                                          \
-  do {                                                                                                          \
-    if (a.trace != nullptr) a.trace[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64();  \
-  } while (0)
-
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -232,69 +232,52 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
 // SRC: 0 = fp32 activations, element-wise gather; 1 = fp32, every 8-element K group lies inside one tap and is
 // contiguous + 16-byte aligned (Cin % 8 == 0): vector gather; 2 = split-bf16 planes, same alignment rule: cp.async gather.
 constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2;
+
+// Persistent: one CTA per SM walks the work list (m tile, n tile, K split) with a static stride; the three roles run
+// decoupled through mbarriers, so the operand ring never drains between tiles and the epilogue of tile i overlaps the
+// MMAs of tile i+1 (two TMEM accumulators).
 template <int BN, int NSPLIT, int SRC>
-__global__ void __launch_bounds__(UM_THREADS, (BN <= 64 ? 2 : 1))
+__global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
-  constexpr int PF = 1;
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulators
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
 
   extern __shared__ __align__(16) uint8_t um_smem[];
-  __shared__ float s_sum[BN], s_sqs[BN];
-  __shared__ int s_any_valid;
+  __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
+  __shared__ long long s_yoff[UM_BM];                    // per-row output element offset of the tile in the epilogue
+  __shared__ int s_oy[UM_BM], s_ox[UM_BM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = smem_u32(um_smem);
-  const uint32_t tiles = (bars + UM_BAR_BYTES + 1023u) & ~1023u;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES, bar_acc = bars + 16 * UM_MAX_STAGES;
-  const uint32_t tmem_slot = bar_acc + 8;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES;
+  const uint32_t bar_tfull = bars + 16 * UM_MAX_STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t stile = (bars + UM_BAR_BYTES + 15u) & ~15u;                 // epilogue staging tile (128 x 144 B)
+  const uint32_t tiles = (stile + UM_STAGING_BYTES + 1023u) & ~1023u;        // operand stage ring
   const int S = a.stages;
-  // split-K: this CTA owns K chunks [kc_begin, kc_end)
-  const int kc_begin = (int)((int64_t)blockIdx.z * a.KC / gridDim.z);
-  const int kc_end = (int)((int64_t)(blockIdx.z + 1) * a.KC / gridDim.z);
-  const int KC = kc_end - kc_begin;
 
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  const int64_t m0 = (int64_t)blockIdx.x * UM_BM;
-  const int nt = blockIdx.y;
-  const int n_base = nt * BN;
-
-  // ---- mapped outputs: skip tiles none of whose (row, column) pairs land inside the output window ----
-  if (a.col_off != nullptr) {
-    if (tid == 0) s_any_valid = 0;
-    __syncthreads();
-    if (tid < UM_BM && m0 + tid < M) {
-      const uint32_t mu = (uint32_t)(m0 + tid);
-      const uint32_t qd = mu / (uint32_t)g.PW;
-      const int j = (int)(mu - qd * (uint32_t)g.PW);
-      const int i = (int)(qd % (uint32_t)g.PH);
-      const int oy = g.oy0 + i * g.osy, ox = g.ox0 + j * g.osx;
-      bool any = false;
-      for (int c = 0; c < BN && !any; ++c) {
-        int n = n_base + c;
-        if (n >= a.Ntot) break;
-        any = (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim;
-      }
-      if (any) s_any_valid = 1;
-    }
-    __syncthreads();
-    if (!s_any_valid) return;
-  }
+  const int MT = (int)((M + UM_BM - 1) / UM_BM);
+  const int NT = a.NT, Z = a.Z;
+  const int64_t n_work = (int64_t)MT * NT * Z;
+  const bool stats = a.stat_sum != nullptr && a.partial == nullptr;
 
   // ---- one-time setup ----
-  if (tid == 0) UM_STAMP(0);
-  if (tid < BN) { s_sum[tid] = 0.f; s_sqs[tid] = 0.f; }
-  if (warp == UM_PRODUCER_WARPS) {
+  if (stats) for (int i = tid; i < UM_MAX_N; i += UM_THREADS) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
+  if (warp == UM_MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(bar_full + 8 * s, UM_PRODUCER_WARPS + 1);   // 8 producer warps + the expect_tx arrival of the B copy
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
-      mbar_init(bar_acc, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_tfull + 8 * b, 1);                       // one tcgen05.commit per tile
+        mbar_init(bar_tempty + 8 * b, UM_EPI_WARPS);           // the epilogue warps have drained the accumulator
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -303,115 +286,76 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  uint32_t tmem_acc;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
-  if (tid == 0) UM_STAMP(1);
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // work item -> (m tile, n tile, split): m fastest, so neighbouring CTAs share the weight tile in L2
+  auto decode_work = [&](int64_t wk, int& mt, int& nt, int& z) {
+    mt = (int)(wk % MT);
+    const int64_t r = wk / MT;
+    nt = (int)(r % NT);
+    z = (int)(r / NT);
+  };
 
   if (warp < UM_PRODUCER_WARPS) {
     // ================================ producers ================================
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
-    int iy0[4], ix0[4];
-    int64_t img[4];                             // element offset of the row's image
-    bool rok[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = it * 32 + (tid >> 3);
-      const int64_t m = m0 + r;
-      rok[it] = m < M;
-      iy0[it] = 0; ix0[it] = 0; img[it] = 0;
-      if (rok[it]) {                              // M < 2^31 (checked on the host): 32-bit decode
-        const uint32_t mu = (uint32_t)m;
-        const uint32_t q = mu / (uint32_t)g.PW, j = mu - q * (uint32_t)g.PW;
-        const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
-        iy0[it] = (int)i * g.isy;
-        ix0[it] = (int)j * g.isx;
-        img[it] = (int64_t)n * g.H * g.W * g.x_ld;
-      }
-    }
     int stage = 0;
     uint32_t phase = 0;
-    // claim the next stage: wait until the MMAs that read it last time round have completed, start the weight copy
-    auto claim_stage = [&](int kc) -> uint32_t {
-      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-      const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
-      if (tid == 0) {
-        mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
-        bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
-                 PLANES * B_PLANE, bar_full + 8 * stage);
-      }
-      return st_base;
+    int pending = 0, pub_stage = 0;             // cp.async path: chunks issued but not yet published
+    auto publish = [&]() {
+      fence_proxy_async();                      // writes of this thread -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * pub_stage);
+      if (++pub_stage == S) pub_stage = 0;
+      --pending;
     };
-
-    if (SRC == SRC_BF2) {
-      // ---- split-bf16 source: 16-byte cp.async per (row, K group) and plane, up to DEPTH chunks in flight ----
-      const char* xhi = reinterpret_cast<const char*>(a.x);
-      // Up to S-1 chunks are in flight (issued, not yet published).  The oldest one is published BEFORE the next
-      // stage is claimed: claiming waits for the MMAs of chunk kc-S, and the tensor pipe must already hold chunk
-      // kc-S+1 by then or it would idle for a whole producer round trip between consecutive chunks.
-      int pending = 0, pub_stage = 0;
-      auto publish = [&]() {                        // the oldest outstanding chunk has landed
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * pub_stage);
-        if (++pub_stage == S) pub_stage = 0;
-        --pending;
-      };
-#pragma unroll 1
-      for (int kc = kc_begin; kc < kc_end; ++kc) {
-        if (pending == S - 1) {                     // wait for the oldest group only: S-2 newer ones stay in flight
-          switch (S) {
-            case 2: cp_async_wait<0>(); break;
-            case 3: cp_async_wait<1>(); break;
-            case 4: cp_async_wait<2>(); break;
-            case 5: cp_async_wait<3>(); break;
-            default: cp_async_wait<4>(); break;
-          }
-          publish();
-          if (tid == 0 && kc == kc_begin + S - 1) UM_STAMP(2);
-        }
-        const int kk = kc * UM_BK + jchunk * 8;
-        const int t = kk / g.Cin;
-        const int ci = kk - t * g.Cin;
-        const bool kok = kk < a.K;
-        const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
-        const uint32_t st_base = claim_stage(kc);
+    auto wait_oldest = [&]() {                  // the oldest of `pending` cp.async groups has landed
+      switch (pending) {
+        case 1: cp_async_wait<0>(); break;
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        case 4: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+      }
+    };
+    for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      int mt, nt, z;
+      decode_work(wk, mt, nt, z);
+      const int64_t m0 = (int64_t)mt * UM_BM;
+      const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+      int iy0[4], ix0[4];
+      int64_t img[4];                           // element offset of the row's image
+      bool rok[4];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 32 + (tid >> 3);
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
-          const int iy = iy0[it] + dy, ix = ix0[it] + dx;
-          const bool ok = kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
-          const char* src = ok ? xhi + 2 * (img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci) : xhi;
-          cp_async16(st_base + off, src, ok ? 16u : 0u);
-          if (PLANES == 2) cp_async16(st_base + UM_A_PLANE + off, src + (ok ? a.x_plane : 0), ok ? 16u : 0u);
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 32 + (tid >> 3);
+        const int64_t m = m0 + r;
+        rok[it] = m < M;
+        iy0[it] = 0; ix0[it] = 0; img[it] = 0;
+        if (rok[it]) {                          // M < 2^31 (checked on the host): 32-bit decode
+          const uint32_t mu = (uint32_t)m;
+          const uint32_t q = mu / (uint32_t)g.PW, j = mu - q * (uint32_t)g.PW;
+          const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
+          iy0[it] = (int)i * g.isy;
+          ix0[it] = (int)j * g.isx;
+          img[it] = (int64_t)n * g.H * g.W * g.x_ld;
         }
-        cp_async_commit();
-        ++pending;
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      // drain in order: each remaining group is published as soon as it (and everything older) has landed
-      while (pending > 0) {
-        switch (pending) {
-          case 1: cp_async_wait<0>(); break;
-          case 2: cp_async_wait<1>(); break;
-          case 3: cp_async_wait<2>(); break;
-          case 4: cp_async_wait<3>(); break;
-          default: cp_async_wait<4>(); break;
-        }
-        publish();
-      }
-    } else {
-      // ---- fp32 source: gather into registers, split hi/lo, store into the swizzled stage ----
-      const float* xf = reinterpret_cast<const float*>(a.x);
 #pragma unroll 1
       for (int kc = kc_begin; kc < kc_end; ++kc) {
-        float f[4][8];
         const int kk = kc * UM_BK + jchunk * 8;
         const int t = kk / g.Cin;
         const int ci0 = kk - t * g.Cin;
-        if (VEC) {
+        float f[4][8];
+        if (SRC == SRC_BF2) {
+          // publish the oldest outstanding chunk BEFORE claiming the next stage: claiming waits for the MMAs of chunk
+          // kc-S, and the tensor pipe must already hold the following chunk by then
+          if (pending == S - 1) { wait_oldest(); publish(); }
+        } else if (VEC) {
           const bool kok = kk < a.K;
           const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
+          const float* xf = reinterpret_cast<const float*>(a.x);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int iy = iy0[it] + dy, ix = ix0[it] + dx;
@@ -425,6 +369,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             f[it][4] = v1.x; f[it][5] = v1.y; f[it][6] = v1.z; f[it][7] = v1.w;
           }
         } else {
+          const float* xf = reinterpret_cast<const float*>(a.x);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             int tt = t, ci = ci0;
@@ -441,234 +386,225 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             }
           }
         }
-        const uint32_t st_base = claim_stage(kc);
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 32 + (tid >> 3);
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
-          uint4 hi, lo;
-          split8(f[it], hi, lo);
-          st_shared_v4(st_base + off, hi);
-          if (PLANES == 2) st_shared_v4(st_base + UM_A_PLANE + off, lo);
+        // claim the stage: the MMAs that read it last time round have completed; start the weight copy
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
+          bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
+                   PLANES * B_PLANE, bar_full + 8 * stage);
         }
-        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        if (SRC == SRC_BF2) {
+          const char* xhi = reinterpret_cast<const char*>(a.x);
+          const bool kok = kk < a.K;
+          const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 32 + (tid >> 3);
+            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
+            const int iy = iy0[it] + dy, ix = ix0[it] + dx;
+            const bool ok = kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
+            const char* src = ok ? xhi + 2 * (img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci0) : xhi;
+            cp_async16(st_base + off, src, ok ? 16u : 0u);
+            if (PLANES == 2) cp_async16(st_base + UM_A_PLANE + off, src + (ok ? a.x_plane : 0), ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          ++pending;
+        } else {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 32 + (tid >> 3);
+            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
+            uint4 hi, lo;
+            split8(f[it], hi, lo);
+            st_shared_v4(st_base + off, hi);
+            if (PLANES == 2) st_shared_v4(st_base + UM_A_PLANE + off, lo);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-
-    // ================================ epilogue ================================
-    if (tid == 0) UM_STAMP(3);
-    if (KC > 0) {
-      mbar_wait(bar_acc, 0);
-      tc_fence_after();
-    }
-    if (tid == 0) UM_STAMP(4);
-    const int q = warp & 3, half = warp >> 2;
-    const int r = q * 32 + lane;
-    const int64_t m = m0 + r;
-    const bool row_ok = m < M;
-    if (a.staged) {
-      // ---- staged epilogue: accumulator -> (bias, activation) -> padded fp32 tile in the (now idle) stage ring ->
-      //      coalesced whole-row writes; batch-norm statistics are column sums of the same tile ----
-      constexpr uint32_t PITCH = BN * 4 + 16;           // +16 B: the 16-byte row stores of a quarter warp hit 32 banks
-      const uint32_t stile = tiles;
-      constexpr int HALF = BN / 2;
-      const bool raw = a.partial != nullptr;
-#pragma unroll 1
-      for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 16) {
-        float v[16];
-        if (KC > 0) {
-          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        } else {
+    while (pending > 0) { wait_oldest(); publish(); }      // drain in order
+  } else if (warp == UM_MMA_WARP) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it_local = 0;
+      for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+        int mt, nt, z;
+        decode_work(wk, mt, nt, z);
+        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+        const int b = (int)(it_local & 1);
+        const uint32_t use = (uint32_t)(it_local >> 1);
+        mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
+          const uint32_t a_hi = st_base, a_lo = st_base + UM_A_PLANE;
+          const uint32_t b_hi = st_base + PLANES * UM_A_PLANE, b_lo = b_hi + B_PLANE;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
+            const uint64_t da_hi = make_sw128_desc(a_hi + k4 * 32), db_hi = make_sw128_desc(b_hi + k4 * 32);
+            umma_bf16(tmem_acc, da_hi, db_hi, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = make_sw128_desc(a_lo + k4 * 32), db_lo = make_sw128_desc(b_lo + k4 * 32);
+              umma_bf16(tmem_acc, da_lo, db_hi, IDESC, 1u);
+              umma_bf16(tmem_acc, da_hi, db_lo, IDESC, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * b);            // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (4 warps = the 4 TMEM lane quadrants) ================================
+    const int q = warp & 3;                        // warps 8..11 -> quadrants 0..3
+    const int et = tid - UM_EPI_WARP0 * 32;        // 0..127 = row of the tile this thread owns in TMEM
+    constexpr uint32_t PITCH = 32 * 4 + 16;        // 32 fp32 columns per pass; +16 B keeps 16-byte row stores conflict-free
+    const bool raw = a.partial != nullptr;
+    float* yf = reinterpret_cast<float*>(a.y);
+    int64_t it_local = 0;
+    for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+      int mt, nt, z;
+      decode_work(wk, mt, nt, z);
+      const int64_t m0 = (int64_t)mt * UM_BM;
+      const int n_base = nt * BN;
+      const int b = (int)(it_local & 1);
+      const uint32_t use = (uint32_t)(it_local >> 1);
+      {                                            // where this thread's row goes
+        const int64_t m = m0 + et;
+        long long yo = UM_ROW_INVALID;
+        int oy = 0, ox = 0;
+        if (m < M) {
+          if (raw) {
+            yo = ((int64_t)z * M + m) * a.n_pad;
+          } else if (a.dense) {
+            yo = m * g.y_sw;
+          } else {
+            const uint32_t mu = (uint32_t)m;
+            const uint32_t qq = mu / (uint32_t)g.PW, j = mu - qq * (uint32_t)g.PW;
+            const uint32_t n = qq / (uint32_t)g.PH, i = qq - n * (uint32_t)g.PH;
+            oy = g.oy0 + (int)i * g.osy;
+            ox = g.ox0 + (int)j * g.osx;
+            yo = (int64_t)n * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
+          }
+        }
+        s_yoff[et] = yo; s_oy[et] = oy; s_ox[et] = ox;
+      }
+      mbar_wait(bar_tfull + 8 * b, use & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + (uint32_t)(b * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld16(tmem_row + (uint32_t)c0, v);
+        tmem_ld16(tmem_row + (uint32_t)c0 + 16u, v + 16);
+        if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
         }
         if (!raw) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < 32; ++e) {
             const int n = n_base + c0 + e;
-            float b = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
-            float w = v[e] + b;
+            const float bb = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
+            float w = v[e] + bb;
             if (a.relu) w = fmaxf(w, 0.f);
             v[e] = w;
           }
         }
 #pragma unroll
-        for (int e = 0; e < 16; e += 4)
-          st_shared_v4(stile + (uint32_t)r * PITCH + (uint32_t)(c0 + e) * 4u,
+        for (int e = 0; e < 32; e += 4)
+          st_shared_v4(stile + (uint32_t)et * PITCH + (uint32_t)e * 4u,
                        make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
-      }
-      tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");      // the 8 epilogue warps only
-      constexpr int F4_PER_ROW = BN / 4;
-      constexpr int ROWS_PER_ITER = 32 / F4_PER_ROW;      // BN=128: 1 row per warp instruction, 64: 2, 32: 4
-      const int lr = lane / F4_PER_ROW, lc = (lane % F4_PER_ROW) * 4;
-      const int ncols = raw ? a.n_pad : a.Ntot;
-      if (n_base + lc < ncols) {
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+        // copy-out: a warp instruction covers 4 rows x 128 contiguous bytes; 4 warps x 8 rounds = 128 rows
+        const int lr = lane >> 3, lc = (lane & 7) * 4;
+        const int n = n_base + c0 + lc;
+        const int ncols = raw ? a.n_pad : a.Ntot;
 #pragma unroll 2
-        for (int rb = warp * ROWS_PER_ITER; rb < UM_BM; rb += UM_PRODUCER_WARPS * ROWS_PER_ITER) {
-          const int rr = rb + lr;
-          const int64_t mm = m0 + rr;
-          if (mm >= M) continue;
+        for (int rd = 0; rd < 8; ++rd) {
+          const int rr = rd * 16 + q * 4 + lr;
+          const long long yo = s_yoff[rr];
+          if (yo == UM_ROW_INVALID || n >= ncols) continue;
           float4 w4;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
                        : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
+          const float t4[4] = {w4.x, w4.y, w4.z, w4.w};
           if (raw) {
-            *reinterpret_cast<float4*>(a.partial + ((int64_t)blockIdx.z * M + mm) * a.n_pad + n_base + lc) = w4;
+            *reinterpret_cast<float4*>(a.partial + yo + n) = w4;
+          } else if (a.col_off == nullptr) {
+            if (a.vec_store) {
+              if (a.out_bf2) store_bf2_4(a.y, a.y_plane, yo + n, t4, a.out_bf2);
+              else *reinterpret_cast<float4*>(yf + yo + n) = w4;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e >= a.Ntot) continue;
+                const int64_t eoff = yo + (int64_t)(n + e) * g.y_sc;
+                if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
+                else yf[eoff] = t4[e];
+              }
+            }
           } else {
-            const int64_t eoff = mm * g.y_sw + n_base + lc;
-            if (a.out_bf2) { const float t4[4] = {w4.x, w4.y, w4.z, w4.w}; store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2); }
-            else *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.y) + eoff) = w4;
-          }
-        }
-      }
-      if (a.stat_sum != nullptr && !raw) {
-        constexpr int PARTS = UM_PRODUCERS / BN;          // threads per column
-        const int c = tid % BN, part = tid / BN;
-        const int rows_valid = (int)((M - m0) < UM_BM ? (M - m0) : UM_BM);
-        float cs = 0.f, cq = 0.f;
-        for (int rr = part; rr < rows_valid; rr += PARTS) {
-          float x;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)c * 4u));
-          cs += x;
-          cq = fmaf(x, x, cq);
-        }
-        if (n_base + c < a.Ntot) { atomicAdd(&s_sum[c], cs); atomicAdd(&s_sqs[c], cq); }
-      }
-      if (tid == 0) UM_STAMP(5);
-    } else {
-    int64_t yoff = 0;                     // element offset of this row's output pixel
-    int oy = 0, ox = 0;
-    if (row_ok) {
-      const uint32_t mu = (uint32_t)m;
-      const uint32_t qq = mu / (uint32_t)g.PW, j = mu - qq * (uint32_t)g.PW;
-      const uint32_t n = qq / (uint32_t)g.PH, i = qq - n * (uint32_t)g.PH;
-      oy = g.oy0 + (int)i * g.osy;
-      ox = g.ox0 + (int)j * g.osx;
-      yoff = (int64_t)n * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
-    }
-    float* yf = reinterpret_cast<float*>(a.y);
-    const bool do_stats = a.stat_sum != nullptr && a.partial == nullptr;
-    constexpr int HALF = BN / 2;
-#pragma unroll 1
-    for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 16) {
-      float v[16];
-      if (KC > 0) {
-        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-      }
-      const int n0 = n_base + c0;
-      if (a.partial != nullptr) {     // split-K: raw accumulators, finished by splitk_reduce_kernel
-        if (row_ok) {
-          float4* pp = reinterpret_cast<float4*>(a.partial + ((int64_t)blockIdx.z * M + m) * a.n_pad + n0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) pp[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        }
-        continue;
-      }
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int n = n0 + e;
-        float b = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
-        float w = v[e] + b;
-        if (a.relu) w = fmaxf(w, 0.f);
-        v[e] = w;
-      }
-      if (row_ok) {
-        if (a.vec_store) {
-#pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const int n = n0 + e;
-            if (n >= a.Ntot) continue;
-            int64_t eoff;
-            if (a.col_off == nullptr) {
-              eoff = yoff + n;
+            const int oy = s_oy[rr], ox = s_ox[rr];
+            if (a.vec_store) {
+              if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim) {
+                const int64_t eoff = yo + a.col_off[n];
+                if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
+                else *reinterpret_cast<float4*>(yf + eoff) = w4;
+              }
             } else {
-              if (!((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)) continue;
-              eoff = yoff + a.col_off[n];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e >= a.Ntot) continue;
+                if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
+                const int64_t eoff = yo + a.col_off[n + e];
+                if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
+                else yf[eoff] = t4[e];
+              }
             }
-            if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, v + e, a.out_bf2);
-            else *reinterpret_cast<float4*>(yf + eoff) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int n = n0 + e;
-            if (n >= a.Ntot) continue;
-            int64_t eoff;
-            if (a.col_off == nullptr) {
-              eoff = yoff + (int64_t)n * g.y_sc;
-            } else {
-              if (!((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim)) continue;
-              eoff = yoff + a.col_off[n];
-            }
-            if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, v[e], a.out_bf2);
-            else yf[eoff] = v[e];
           }
         }
-      }
-      if (do_stats) {   // batch-norm statistics of the stored values (padded rows / columns contribute zeros)
-        float sq[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if (!row_ok || n0 + e >= a.Ntot) v[e] = 0.f;
-          sq[e] = v[e] * v[e];
-        }
-        const float cs = warp_colsum16(v, lane);
-        const float cq = warp_colsum16(sq, lane);
-        if ((lane & 1) == 0) {
-          const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          atomicAdd(&s_sum[c0 + col], cs);
-          atomicAdd(&s_sqs[c0 + col], cq);
-        }
-      }
-    }
-    tc_fence_before();
-    if (tid == 0) UM_STAMP(5);
-    }
-  } else {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kc = kc_begin; kc < kc_end; ++kc) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        if (kc == kc_begin) UM_STAMP(6);
-        tc_fence_after();
-        const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t a_hi = st_base, a_lo = st_base + UM_A_PLANE;
-        const uint32_t b_hi = st_base + PLANES * UM_A_PLANE, b_lo = b_hi + B_PLANE;
-#pragma unroll
-        for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
-          const uint64_t da_hi = make_sw128_desc(a_hi + k4 * 32), db_hi = make_sw128_desc(b_hi + k4 * 32);
-          umma_bf16(tmem_acc, da_hi, db_hi, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
-          if (NSPLIT == 3) {
-            const uint64_t da_lo = make_sw128_desc(a_lo + k4 * 32), db_lo = make_sw128_desc(b_lo + k4 * 32);
-            umma_bf16(tmem_acc, da_lo, db_hi, IDESC, 1u);
-            umma_bf16(tmem_acc, da_hi, db_lo, IDESC, 1u);
+        if (stats) {                               // column sums of the staged pass: 4 threads per column
+          const int c = et & 31, part = et >> 5;
+          float cs = 0.f, cq = 0.f;
+          for (int rr = part; rr < UM_BM; rr += 4) {
+            if (s_yoff[rr] == UM_ROW_INVALID) continue;
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)c * 4u));
+            cs += x;
+            cq = fmaf(x, x, cq);
           }
+          if (n_base + c0 + c < a.Ntot) { atomicAdd(&s_sum[n_base + c0 + c], cs); atomicAdd(&s_sqs[n_base + c0 + c], cq); }
         }
-        umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");   // staging tile and row table reusable
       }
-      if (KC > 0) umma_commit(bar_acc);          // accumulator complete
-      UM_STAMP(7);
     }
-    __syncwarp();
   }
 
+  tc_fence_before();
   __syncthreads();
-  if (warp == UM_PRODUCER_WARPS) {
+  if (warp == UM_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (a.stat_sum != nullptr && a.partial == nullptr && tid < BN && n_base + tid < a.Ntot) {
-    atomicAdd(a.stat_sum + n_base + tid, (double)s_sum[tid]);
-    atomicAdd(a.stat_sqs + n_base + tid, (double)s_sqs[tid]);
+  if (stats) {
+    for (int i = tid; i < a.Ntot; i += UM_THREADS) {
+      atomicAdd(a.stat_sum + i, (double)s_sum[i]);
+      atomicAdd(a.stat_sqs + i, (double)s_sqs[i]);
+    }
   }
 }
 
@@ -826,57 +762,42 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int NSPLIT, int SRC>
 int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStream_t st) {
   constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
-  constexpr bool TWO_PER_SM = BN <= 64;
   UmmaArgs a = a_in;
-  const int budget = (TWO_PER_SM ? 110 : 220) * 1024 - UM_BAR_BYTES - 1024;
-  int S = budget / STAGE_BYTES;
+  a.NT = nt;
+  a.Z = Z;
+  // one persistent CTA per SM: barriers + staging tile + alignment slack + as many operand stages as fit (<= 6)
+  const int fixed = UM_BAR_BYTES + 16 + UM_STAGING_BYTES + 1024;
+  int S = (215 * 1024 - fixed) / STAGE_BYTES;    // + ~10 KB of static shared memory stays under the 227 KB limit
   if (S > 6) S = 6;    // the cp.async drain handles at most 5 groups in flight
   if (S < 2) S = 2;
   a.stages = S;
-  const size_t smem = (size_t)UM_BAR_BYTES + 1024 + (size_t)S * STAGE_BYTES;
+  const size_t smem = (size_t)fixed + (size_t)S * STAGE_BYTES;
   auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC>;
   static bool attr_set = false;
   if (!attr_set) {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr_set = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  dim3 grid((unsigned)cdiv64(M, UM_BM), (unsigned)nt, (unsigned)Z);
-  // debug: SAG_UMMA_TRACE=<grid.x> prints the average phase durations (clocks) of the first launch with that grid.x
-  static const int trace_grid = env_int("SAG_UMMA_TRACE", 0);
-  static int traced = 0;
-  if (trace_grid > 0 && (int)grid.x == trace_grid && Z == 1 && traced < env_int("SAG_UMMA_TRACE_N", 1)) {
-    ++traced;
-    const size_t n = (size_t)grid.x * grid.y * 8;
-    long long* dtr = nullptr;
-    cudaMalloc(&dtr, n * sizeof(long long));
-    cudaMemset(dtr, 0, n * sizeof(long long));
-    a.trace = dtr;
-    cudaStreamSynchronize(st);
-    kern<<<grid, UM_THREADS, smem, st>>>(g, a);
-    cudaStreamSynchronize(st);
-    std::vector<long long> tr(n);
-    cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
-    cudaFree(dtr);
-    double d[8] = {0};
-    const char* names[8] = {"setup (alloc+barriers)", "start -> first chunk published", "start -> producer loop done",
-                            "start -> accumulator ready", "epilogue (acc ready -> done)", "start -> MMA saw first chunk",
-                            "start -> all MMAs issued", "total (entry -> epilogue done)"};
-    const size_t ctas = n / 8;
-    for (size_t c = 0; c < ctas; ++c) {
-      const long long* t = &tr[c * 8];
-      d[0] += t[1] - t[0]; d[1] += t[2] ? t[2] - t[0] : 0; d[2] += t[3] - t[0]; d[3] += t[4] - t[0];
-      d[4] += t[5] - t[4]; d[5] += t[6] - t[0]; d[6] += t[7] - t[0]; d[7] += t[5] - t[0];
-    }
-    fprintf(stderr, "[umma trace] BN=%d NSPLIT=%d SRC=%d grid=(%u,%u) KC=%d stages=%d\n", BN, NSPLIT, SRC, grid.x, grid.y, a.KC, S);
-    for (int i = 0; i < 8; ++i) fprintf(stderr, "[umma trace]   %-34s %10.0f clk\n", names[i], d[i] / ctas);
-    SAG_LAUNCH_CHECK();
-    return SAG_OK;
-  }
+  const int64_t n_work = cdiv64(M, UM_BM) * nt * Z;
+  static const int max_ctas = env_int("SAG_UMMA_MAX_CTAS", 0);      // test knob: force many work items per CTA
+  const int64_t ctas = max_ctas > 0 ? max_ctas : num_sms();
+  const unsigned grid = (unsigned)(n_work < ctas ? n_work : ctas);
   kern<<<grid, UM_THREADS, smem, st>>>(g, a);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
@@ -1048,14 +969,15 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   const int64_t tiles = cdiv64(M, UM_BM) * NT;
   int Z = 1;
   if (enabled && tiles > 0 && KC >= 8) {
-    // Cost model in units of one K chunk: a CTA costs its chunks plus ~6 chunks of fixed work (pipeline fill, epilogue);
-    // CTAs run in waves of `slots`; splitting adds the partial round trip (~5 % + the reduce launch).  Pick the split
-    // that minimises the wave-quantised time -- it both fills the SMs of small layers and trims ragged last waves.
-    const int64_t slots = 148 * (BN <= 64 ? 2 : 1);
+    // Cost model in units of one K chunk: a work item costs its chunks plus ~2 chunks of per-tile work, a launch ~4
+    // chunks of pipeline fill; items run in waves of `slots`; splitting adds the partial round trip (~5 % + the
+    // reduce launch).  Pick the split that minimises the wave-quantised time -- it both fills the SMs of small layers
+    // and trims ragged last waves.
+    const int64_t slots = 148;                // one persistent CTA per SM
     double best = 0.0;
     for (int z = 1; z <= 32 && z <= KC / 4; ++z) {
       const int64_t waves = cdiv64(tiles * z, slots);
-      double t = (double)waves * ((double)cdiv(KC, z) + 6.0);
+      double t = (double)waves * ((double)cdiv(KC, z) + 2.0) + 4.0;
       if (z > 1) t = t * 1.05 + 4.0;
       if (z == 1 || t < best * 0.97) { best = t; Z = z; }   // split only for a clear (>3 %) win
     }
@@ -1104,11 +1026,11 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   int Z = scratch != nullptr ? umma_split_k(w.K, w.N, M, nullptr) : 1;
   if (Z > 1) a.partial = scratch;
-  // staged epilogue: split-K partials always; direct outputs when pixel m sits at element m*y_sw and rows vectorise
-  const bool dense_rows = w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
-                          g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh;
-  static const int staged_on = env_int("SAG_UMMA_STAGED", 1);
-  a.staged = (staged_on && (Z > 1 || (dense_rows && a.vec_store))) ? 1 : 0;
+  // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
+  a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
+             g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;
+  SAG_REQUIRE(w.KC >= 1, SAG_EINVAL, "tcgen05 path: empty contraction");
+  SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);
   int r;
   switch (w.BN) {
     case 32: r = launch_bn<32>(g, a, w.NT, w.planes, src, Z, st); break;

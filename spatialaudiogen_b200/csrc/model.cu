@@ -387,6 +387,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
       SAG_TRY(launch_gather_gemm_umma(xp.v, it->second, c1.v, g, ep, 0, 0, scratch, st));
     }
   }
+  f.tap(scope + "/conv1_raw", c1, {B, oh, ow, 64});
   SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
   Act cur = f.alloc_act((int64_t)B * ph * pw, 64);
@@ -394,6 +395,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     ProfScope ps(PROF_POINTWISE, 0, B * 64.0 * (4.0 * oh * ow + act_b * ph * pw), st);
     SAG_TRY(launch_bn_relu_maxpool(c1.f32(), b1.scale, b1.shift, B, oh, ow, 64, cur.v, st));
   }
+  f.tap(scope + "/pool1", cur, {B, ph, pw, 64});
   int ch = ph, cw = pw, cc = 64;
 
   for (const BlockDef& b : kBlocks) {
