@@ -689,70 +689,102 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias, int cout, int
 }
 
 // ---- split-K finish: sum the partial accumulators, then the same bias / activation / statistics / store as the
-//      fused epilogue.  One thread per (row, 4-column group); a block owns `rows_per_block` consecutive rows. ----
-__global__ void __launch_bounds__(128) splitk_reduce_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, int Z,
-                                                            int rows_per_block) {
+//      fused epilogue.  A block owns SK_ROWS (1..16) consecutive rows; its 256 threads sweep (row, 4-column group) pairs with the
+//      column group fastest, so partial reads and output writes are whole contiguous rows; when 256 % groups == 0 a
+//      thread keeps one column group and carries that group's batch-norm sums in registers. ----
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, int Z,
+                                                            int SK_ROWS) {
+  __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  const int64_t r0 = (int64_t)blockIdx.x * SK_ROWS;
+  const int rows = (int)((M - r0) < SK_ROWS ? (M - r0) : SK_ROWS);
   const int ncg = (a.Ntot + 3) / 4;
-  for (int cg = threadIdx.x; cg < ncg; cg += blockDim.x) {
+  const bool stats = a.stat_sum != nullptr;
+  if (stats) {
+    for (int i = threadIdx.x; i < a.Ntot; i += blockDim.x) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
+    __syncthreads();
+  }
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssqs[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool fixed_cg = (blockDim.x % ncg) == 0;
+  int last_n = -1;
+  float* yf = reinterpret_cast<float*>(a.y);
+  for (int idx = threadIdx.x; idx < rows * ncg; idx += blockDim.x) {
+    const int rr = idx / ncg, cg = idx - rr * ncg;
     const int n = cg * 4;
-    float bs[4], ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssqs[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t m = r0 + rr;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* pp = a.partial + m * a.n_pad + n;
+    const int64_t zs = M * a.n_pad;
+#pragma unroll 4
+    for (int z = 0; z < Z; ++z) {
+      const float4 p = __ldcs(reinterpret_cast<const float4*>(pp + (int64_t)z * zs));
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) bs[e] = (a.bias != nullptr && n + e < a.Ntot) ? __ldg(a.bias + n + e) : 0.f;
-    for (int64_t m = r0; m < r1; ++m) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int z = 0; z < Z; ++z) {
-        const float4 p = __ldcs(reinterpret_cast<const float4*>(a.partial + ((int64_t)z * M + m) * a.n_pad + n));
-        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    for (int e = 0; e < 4; ++e) {
+      if (a.bias != nullptr && n + e < a.Ntot) v[e] += __ldg(a.bias + n + e);
+      if (a.relu) v[e] = fmaxf(v[e], 0.f);
+      if (n + e >= a.Ntot) v[e] = 0.f;
+    }
+    int64_t yoff;
+    int oy = 0, ox = 0;
+    if (a.dense) {
+      yoff = m * g.y_sw;
+    } else {
+      const uint32_t mu = (uint32_t)m;
+      const uint32_t qq = mu / (uint32_t)g.PW, j = mu - qq * (uint32_t)g.PW;
+      const uint32_t b = qq / (uint32_t)g.PH, i = qq - b * (uint32_t)g.PH;
+      oy = g.oy0 + (int)i * g.osy;
+      ox = g.ox0 + (int)j * g.osx;
+      yoff = (int64_t)b * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
+    }
+    if (a.vec_store) {
+      bool ok = true;
+      int64_t eoff = yoff + n;
+      if (a.col_off != nullptr) {
+        ok = (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim;
+        eoff = yoff + a.col_off[n];
       }
-      float v[4] = {acc.x + bs[0], acc.y + bs[1], acc.z + bs[2], acc.w + bs[3]};
-      if (a.relu) {
+      if (ok) {
+        if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, v, a.out_bf2);
+        else *reinterpret_cast<float4*>(yf + eoff) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-      }
-      const int j = (int)(m % g.PW);
-      const int64_t q = m / g.PW;
-      const int i = (int)(q % g.PH);
-      const int b = (int)(q / g.PH);
-      const int oy = g.oy0 + i * g.osy, ox = g.ox0 + j * g.osx;
-      const int64_t yoff = (int64_t)b * g.y_sn + (int64_t)oy * g.y_sh + (int64_t)ox * g.y_sw;
-      float* yf = reinterpret_cast<float*>(a.y);
-      if (a.vec_store) {
-        bool ok = true;
-        int64_t eoff = yoff + n;
+      for (int e = 0; e < 4; ++e) {
+        if (n + e >= a.Ntot) continue;
+        int64_t eoff = yoff + (int64_t)(n + e) * g.y_sc;
         if (a.col_off != nullptr) {
-          ok = (unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim;
-          eoff = yoff + a.col_off[n];
+          if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
+          eoff = yoff + a.col_off[n + e];
         }
-        if (ok) {
-          if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, v, a.out_bf2);
-          else *reinterpret_cast<float4*>(yf + eoff) = make_float4(v[0], v[1], v[2], v[3]);
-        }
+        if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, v[e], a.out_bf2);
+        else yf[eoff] = v[e];
+      }
+    }
+    if (stats) {
+      if (fixed_cg) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ssum[e] += v[e]; ssqs[e] = fmaf(v[e], v[e], ssqs[e]); }
+        last_n = n;
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (n + e >= a.Ntot) continue;
-          int64_t eoff = yoff + (int64_t)(n + e) * g.y_sc;
-          if (a.col_off != nullptr) {
-            if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
-            eoff = yoff + a.col_off[n + e];
-          }
-          if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, v[e], a.out_bf2);
-          else yf[eoff] = v[e];
-        }
+        for (int e = 0; e < 4; ++e)
+          if (n + e < a.Ntot) { atomicAdd(&s_sum[n + e], v[e]); atomicAdd(&s_sqs[n + e], v[e] * v[e]); }
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { ssum[e] += v[e]; ssqs[e] = fmaf(v[e], v[e], ssqs[e]); }
     }
-    if (a.stat_sum != nullptr && r1 > r0) {
+  }
+  if (stats) {
+    if (fixed_cg && last_n >= 0) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (n + e < a.Ntot) {
-          atomicAdd(a.stat_sum + n + e, (double)ssum[e]);
-          atomicAdd(a.stat_sqs + n + e, (double)ssqs[e]);
-        }
+        if (last_n + e < a.Ntot) { atomicAdd(&s_sum[last_n + e], ssum[e]); atomicAdd(&s_sqs[last_n + e], ssqs[e]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.Ntot; i += blockDim.x) {
+      atomicAdd(a.stat_sum + i, (double)s_sum[i]);
+      atomicAdd(a.stat_sqs + i, (double)s_sqs[i]);
     }
   }
 }
@@ -1040,8 +1072,10 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   SAG_TRY(r);
   if (Z > 1) {
-    const int rows_per_block = 8;
-    splitk_reduce_kernel<<<(unsigned)cdiv64(M, rows_per_block), 128, 0, st>>>(g, a, Z, rows_per_block);
+    int rpb = (int)(M / (2 * num_sms()));           // rows per block: keep >= 2 blocks per SM, at most 16 rows
+    if (rpb > 16) rpb = 16;
+    if (rpb < 1) rpb = 1;
+    splitk_reduce_kernel<<<(unsigned)cdiv64(M, rpb), 256, 0, st>>>(g, a, Z, rpb);
     SAG_LAUNCH_CHECK();
   }
   return SAG_OK;
