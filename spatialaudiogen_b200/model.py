@@ -219,6 +219,66 @@ class SptAudioGen(object):
     def dims_frame(self):
         return self._frame
 
+    def inference_stream(self, batches, depth=2):
+        """The driver loop around `sess.run` (reference deploy.py:112-148, eval.py:140-201) as a generator: `batches`
+        yields dicts of HOST tensors {'audio': (B, snd_size, 1)[, 'video', 'flow': (B, 1, H, W, 3)]} (pinned memory
+        makes the copies asynchronous); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
+        `depth` steps) is yielded in order.  Host->device copies of step i+1 and the device->host copy of step i-1 run
+        on their own streams while step i computes, so the PCIe transfers hide behind the forward."""
+        if not self._weights_ready:
+            raise RuntimeError('load_weights() must be called before inference_stream()')
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=dev)           # host -> device copies
+            back = torch.cuda.Stream(device=dev)           # device -> host copies (own stream: a D2H waiting for its
+                                                           # forward must not block the next step's H2D behind it)
+            slots = []
+            pending = []                                   # (slot index) in flight, oldest first
+
+            def make_slot(b):
+                sl = {'in': {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in b.items()
+                             if k in (AUDIO, VIDEO, FLOW)},
+                      'out': torch.empty((b[AUDIO].shape[0], self.snd_dur, 3), dtype=torch.float32, device=dev),
+                      'host': torch.empty((b[AUDIO].shape[0], self.snd_dur, 3), dtype=torch.float32).pin_memory(),
+                      'in_ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'out_ready': torch.cuda.Event(),
+                      'free': torch.cuda.Event()}
+                sl['free'].record(main)
+                return sl
+
+            def finish(idx):
+                sl = slots[idx]
+                sl['out_ready'].synchronize()
+                return sl['host']
+
+            i = 0
+            for b in batches:
+                if len(slots) < depth:
+                    slots.append(make_slot(b))
+                idx = i % depth
+                if len(pending) == depth:                  # the slot we are about to reuse must have been consumed
+                    yield finish(pending.pop(0))
+                sl = slots[idx]
+                if sl['in'][AUDIO].shape != b[AUDIO].shape:
+                    raise ValueError('all batches of a stream must have the same shape')
+                with torch.cuda.stream(side):
+                    side.wait_event(sl['free'])            # previous forward that read these inputs has finished
+                    for k, t in sl['in'].items():
+                        t.copy_(torch.as_tensor(b[k]), non_blocking=True)
+                    sl['in_ready'].record(side)
+                main.wait_event(sl['in_ready'])
+                self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'])
+                sl['done'].record(main)
+                sl['free'].record(main)
+                with torch.cuda.stream(back):
+                    back.wait_event(sl['done'])
+                    sl['host'].copy_(sl['out'], non_blocking=True)
+                    sl['out_ready'].record(back)
+                pending.append(idx)
+                i += 1
+            while pending:
+                yield finish(pending.pop(0))
+
     def _view(self, name):
         lib = L.lib()
         p = C.c_void_p()

@@ -440,3 +440,18 @@ def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
     lines = open(fn).read().splitlines()
     assert lines[0] == 'SampleID | ' + ' '.join(E.ALL_METRICS) and len(lines) == B + 1
     assert lines[1].startswith('vid0 0.5 | ') and len(lines[1].split(' | ')[1].split(' ')) == 28
+
+
+def test_inference_stream_matches_per_batch_calls():
+    """The pipelined driver loop returns, in order, exactly what one inference_ops call per batch returns."""
+    from spatialaudiogen_b200 import SptAudioGen
+    enc = ['audio', 'video']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=5, stress=True)
+    m = SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(W)
+    batches = [{'audio': torch.as_tensor(_audio(2, 40 + i)).pin_memory(), 'video': torch.as_tensor(_video(2, 50 + i)).pin_memory()}
+               for i in range(5)]
+    outs = [y.clone() for y in m.inference_stream(iter(batches))]
+    assert len(outs) == 5
+    for b, y in zip(batches, outs):
+        ref = m.inference_ops(b['audio'], video=b['video']).cpu()
+        assert _rel(y, ref) < 2e-4      # not bit-equal: batch-norm sums are accumulated with atomics (order varies, ~2e-5)
