@@ -116,42 +116,76 @@ int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int 
   return SAG_OK;
 }
 
-// ---- K6a: (sigmoid mask x STFT) -> real inverse FFT -> overlap-add / n_overlap -> crop ----------------------------
-// grid (rows_s*tracks). Frame-space position of output sample j is j + (n_overlap-1)*hop (myutils.py:198-205).
-__global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ S, const float* __restrict__ mask,
-                                                    int apply_sigmoid, int tracks, int n_frames, const FftPlan p,
-                                                    int hop, int f_lo, int f_hi, int p0, int n_out, float inv_scale,
-                                                    float* __restrict__ out) {
+// ---- K6: (sigmoid mask x STFT) -> real inverse FFT -> overlap-add / n_overlap -> crop ------------------------------
+// One CTA per (window, PAIR of tracks).  Only the real part of ifft(m.S) is kept (myutils.py:191-192), and
+//   real(ifft(Y)) = ifft(Yh),  Yh[k] = (Y[k] + conj(Y[N-k])) / 2   (Hermitian part),
+// so two tracks ride one complex transform: Z = Yh_a + i Yh_b  ->  ifft(Z) = y_a + i y_b.  NFR frames are transformed
+// together (one set of block-wide syncs and twiddle fetches for all of them); every mask element is read, and its
+// sigmoid evaluated, exactly once.  Frame-space position of output sample j is j + (n_overlap-1)*hop
+// (myutils.py:198-205); each thread owns output positions, so the overlap-add needs no atomics.
+constexpr int ISTFT_NFR = 4;
+__global__ void __launch_bounds__(256) istft_pair_kernel(const float2* __restrict__ S, const float* __restrict__ mask,
+                                                         int apply_sigmoid, int tracks, int n_frames, const FftPlan p,
+                                                         int hop, int f_lo, int f_hi, int p0, int n_out, float inv_scale,
+                                                         int nfr, float* __restrict__ out) {
   extern __shared__ __align__(16) float2 smem[];
+  const int n = p.n;
   float2* buf0 = smem;
-  float2* buf1 = smem + p.n;
-  float* ola = reinterpret_cast<float*>(smem + 2 * p.n);
-  const int64_t rk = blockIdx.x;
-  const int64_t row = rk / tracks;
-  for (int i = threadIdx.x; i < n_out; i += blockDim.x) ola[i] = 0.f;
-  for (int f = f_lo; f <= f_hi; ++f) {
-    const float2* s = S + (row * n_frames + f) * p.n;
-    const float* m = mask != nullptr ? mask + (rk * n_frames + f) * p.n : nullptr;
-    __syncthreads();     // previous frame's result fully consumed before buf0 is overwritten
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-      float2 v = __ldg(s + i);
-      if (m != nullptr) {
-        float g = __ldg(m + i);
-        if (apply_sigmoid) g = 1.f / (1.f + expf(-g));
-        v.x *= g; v.y *= g;
+  float2* buf1 = smem + nfr * n;
+  float* ola_a = reinterpret_cast<float*>(smem + 2 * nfr * n);
+  float* ola_b = ola_a + n_out;
+  const int pairs = (tracks + 1) / 2;
+  const int64_t row = blockIdx.x / pairs;
+  const int ka = (int)(blockIdx.x % pairs) * 2, kb = ka + 1;
+  const bool has_b = kb < tracks;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) { ola_a[i] = 0.f; ola_b[i] = 0.f; }
+  const float* ma = mask != nullptr ? mask + (row * tracks + ka) * (int64_t)n_frames * n : nullptr;
+  const float* mb = (mask != nullptr && has_b) ? mask + (row * tracks + kb) * (int64_t)n_frames * n : nullptr;
+  for (int f0 = f_lo; f0 <= f_hi; f0 += nfr) {
+    const int nf = min(nfr, f_hi - f0 + 1);
+    __syncthreads();                                   // previous group's transforms fully consumed
+    for (int g = 0; g < nf; ++g) {
+      const float2* s = S + (row * n_frames + (f0 + g)) * (int64_t)n;
+      const int64_t mo = (int64_t)(f0 + g) * n;
+      for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
+        const int kn = k == 0 ? 0 : n - k;
+        const float2 xk = __ldg(s + k), xn = __ldg(s + kn);
+        float gak = 1.f, gan = 1.f, gbk = has_b ? 1.f : 0.f, gbn = gbk;
+        if (ma != nullptr) {
+          gak = __ldg(ma + mo + k); gan = __ldg(ma + mo + kn);
+          if (apply_sigmoid) { gak = 1.f / (1.f + expf(-gak)); gan = 1.f / (1.f + expf(-gan)); }
+        }
+        if (mb != nullptr) {
+          gbk = __ldg(mb + mo + k); gbn = __ldg(mb + mo + kn);
+          if (apply_sigmoid) { gbk = 1.f / (1.f + expf(-gbk)); gbn = 1.f / (1.f + expf(-gbn)); }
+        }
+        // Hermitian parts of the two masked spectra at bin k
+        const float2 ya = make_float2(0.5f * (gak * xk.x + gan * xn.x), 0.5f * (gak * xk.y - gan * xn.y));
+        const float2 yb = make_float2(0.5f * (gbk * xk.x + gbn * xn.x), 0.5f * (gbk * xk.y - gbn * xn.y));
+        // Z[k] = ya + i yb ; Z[N-k] = conj(ya) + i conj(yb); stored conjugated: ifft(Z) = conj(fft(conj Z)) / N
+        buf0[g * n + k] = make_float2(ya.x - yb.y, -(ya.y + yb.x));
+        buf0[g * n + kn] = make_float2(ya.x + yb.y, -(yb.x - ya.y));
       }
-      buf0[i] = make_float2(v.x, -v.y);     // conj: ifft(z) = conj(fft(conj z))/n ; only the real part is kept
     }
-    float2* res = block_fft(buf0, buf1, p);
-    const int base = f * hop - p0;           // output index of sample 0 of this frame
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-      int j = base + i;
-      if (j >= 0 && j < n_out) ola[j] += res[i].x;    // frames are processed sequentially: no race
+    const float2* res = block_fft_nf(buf0, buf1, p, nf);     // res = N * (y_a - i y_b)
+    const int lo = max(f0 * hop - p0, 0), hi = min((f0 + nf - 1) * hop - p0 + n, n_out);
+    for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+      float aa = 0.f, ab = 0.f;
+      for (int g = 0; g < nf; ++g) {
+        const int i = j - ((f0 + g) * hop - p0);
+        if (i >= 0 && i < n) { const float2 r = res[g * n + i]; aa += r.x; ab -= r.y; }
+      }
+      ola_a[j] += aa;
+      ola_b[j] += ab;
     }
   }
   __syncthreads();
-  float* o = out + rk * n_out;
-  for (int i = threadIdx.x; i < n_out; i += blockDim.x) o[i] = ola[i] * inv_scale;
+  float* oa = out + (row * tracks + ka) * (int64_t)n_out;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) oa[i] = ola_a[i] * inv_scale;
+  if (has_b) {
+    float* ob = out + (row * tracks + kb) * (int64_t)n_out;
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) ob[i] = ola_b[i] * inv_scale;
+  }
 }
 
 int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_s, int tracks, int n_frames, int wind,
@@ -169,12 +203,18 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
   if (p0 - wind + 1 <= 0) f_lo = 0;
   int f_hi = (p1 - 1) / hop;
   if (f_hi > nf - 1) f_hi = nf - 1;
-  size_t smem = 2 * sizeof(float2) * wind + sizeof(float) * n_out;
-  SAG_REQUIRE(smem <= 200 * 1024, SAG_EUNSUPPORTED, "istft: %zu bytes of shared memory needed", smem);
-  if (smem > 48 * 1024) SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int nfr = ISTFT_NFR;
+  size_t smem = 0;
+  for (; nfr >= 1; nfr >>= 1) {
+    smem = 2 * sizeof(float2) * (size_t)wind * nfr + 2 * sizeof(float) * (size_t)n_out;
+    if (smem <= 110 * 1024 || nfr == 1) break;             // two CTAs per SM when possible
+  }
+  SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft: %zu bytes of shared memory needed", smem);
+  SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const float inv_scale = 1.0f / ((float)wind * (float)n_overlap);
-  istft_kernel<<<rows_s * tracks, 256, smem, st>>>(reinterpret_cast<const float2*>(S), mask, apply_sigmoid, tracks,
-                                                  n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, out);
+  const int pairs = (tracks + 1) / 2;
+  istft_pair_kernel<<<rows_s * pairs, 256, smem, st>>>(reinterpret_cast<const float2*>(S), mask, apply_sigmoid, tracks,
+                                                     n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
