@@ -40,7 +40,7 @@ constexpr int UM_STAGING_BYTES = UM_BM * (32 * 4 + 16);
 constexpr long long UM_ROW_INVALID = (long long)0x8000000000000000ull;   // row beyond M (mapped outputs may have negative bases)
 constexpr int UM_A_PLANE = UM_BM * 128;     // bytes of one A plane per stage
 constexpr int UM_MAX_STAGES = 8;
-constexpr int UM_BAR_BYTES = 256;            // full[8] empty[8] tmem_full[2] tmem_empty[2] tmem slot
+constexpr int UM_BAR_BYTES = 256;            // full[8] empty[8] tmem_full[2] tmem_empty[2] tmem slot peer[8]
 
 struct UmmaArgs {
   const void* x;          // fp32 activation, or the hi plane of a split-bf16 activation (src_bf2)
@@ -66,6 +66,7 @@ struct UmmaArgs {
   int n_pad;
   int dense;              // output pixel m sits at element m*y_sw (no row decode)
   int NT, Z;              // N tiles, K splits
+  int cluster;            // CTAs per cluster (1 or 2): the CTAs of a cluster take adjacent M tiles and share the weight copy
 };
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +108,41 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// same copy, delivered to the same CTA-relative offsets (data and mbarrier) of every CTA in `cta_mask` of the cluster
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {      // acquire at cluster scope
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
@@ -256,14 +292,19 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES;
   const uint32_t bar_tfull = bars + 16 * UM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t bar_peer = bars + 16 * UM_MAX_STAGES + 48;   // leader only: the other CTAs of the cluster freed stage s
   const uint32_t stile = (bars + UM_BAR_BYTES + 15u) & ~15u;                 // epilogue staging tile (128 x 144 B)
   const uint32_t tiles = (stile + UM_STAGING_BYTES + 1023u) & ~1023u;        // operand stage ring
   const int S = a.stages;
 
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
+  const int CL = a.cluster;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   const int MT = (int)((M + UM_BM - 1) / UM_BM);
+  const int MG = (MT + CL - 1) / CL;             // groups of CL adjacent M tiles: one per CTA of a cluster
   const int NT = a.NT, Z = a.Z;
-  const int64_t n_work = (int64_t)MT * NT * Z;
+  const int64_t n_work = (int64_t)MG * NT * Z;   // work items per cluster
+  const int64_t wk0 = blockIdx.x / CL, wk_step = gridDim.x / CL;
   const bool stats = a.stat_sum != nullptr && a.partial == nullptr;
 
   // ---- one-time setup ----
@@ -278,21 +319,25 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         mbar_init(bar_tfull + 8 * b, 1);                       // one tcgen05.commit per tile
         mbar_init(bar_tempty + 8 * b, UM_EPI_WARPS);           // the epilogue warps have drained the accumulator
       }
+      for (int s = 0; s < S; ++s) mbar_init(bar_peer + 8 * s, CL > 1 ? CL - 1 : 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();                              // peers' barriers exist before anyone arrives remotely
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item -> (m tile, n tile, split): m fastest, so neighbouring CTAs share the weight tile in L2
+  // work item -> (m tile, n tile, split): m fastest, so neighbouring CTAs share the weight tile in L2; the CTAs of a
+  // cluster take adjacent m tiles of the same (n tile, split) and walk their K chunks in lockstep (mt may be >= MT
+  // for the last group: that CTA then runs an all-padding tile to keep the lockstep)
   auto decode_work = [&](int64_t wk, int& mt, int& nt, int& z) {
-    mt = (int)(wk % MT);
-    const int64_t r = wk / MT;
+    mt = (int)(wk % MG) * CL + (int)crank;
+    const int64_t r = wk / MG;
     nt = (int)(r % NT);
     z = (int)(r / NT);
   };
@@ -319,7 +364,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         default: cp_async_wait<4>(); break;
       }
     };
-    for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
       int mt, nt, z;
       decode_work(wk, mt, nt, z);
       const int64_t m0 = (int64_t)mt * UM_BM;
@@ -391,8 +436,17 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
-          bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
-                   PLANES * B_PLANE, bar_full + 8 * stage);
+          const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
+          if (CL == 1) {
+            bulk_g2s(st_base + PLANES * UM_A_PLANE, wsrc, PLANES * B_PLANE, bar_full + 8 * stage);
+          } else if (crank == 0) {
+            // leader: once every CTA of the cluster has freed (and armed) this stage, one multicast copy feeds them all
+            mbar_wait_cluster(bar_peer + 8 * stage, phase);
+            bulk_g2s_multicast(st_base + PLANES * UM_A_PLANE, wsrc, PLANES * B_PLANE, bar_full + 8 * stage,
+                               (uint16_t)((1u << CL) - 1u));
+          } else {
+            mbar_arrive_remote(bar_peer + 8 * stage, 0);       // my stage is free and its barrier expects the bytes
+          }
         }
         if (SRC == SRC_BF2) {
           const char* xhi = reinterpret_cast<const char*>(a.x);
@@ -434,7 +488,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       int stage = 0;
       uint32_t phase = 0;
       int64_t it_local = 0;
-      for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+      for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
         int mt, nt, z;
         decode_work(wk, mt, nt, z);
         const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
@@ -474,7 +528,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     const bool raw = a.partial != nullptr;
     float* yf = reinterpret_cast<float*>(a.y);
     int64_t it_local = 0;
-    for (int64_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+    for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int mt, nt, z;
       decode_work(wk, mt, nt, z);
       const int64_t m0 = (int64_t)mt * UM_BM;
@@ -595,7 +649,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == UM_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -826,11 +881,32 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
     attr_set = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  const int64_t n_work = cdiv64(M, UM_BM) * nt * Z;
+  const int64_t MT = cdiv64(M, UM_BM);
+  // SAG_UMMA_CLUSTER=2: clusters of 2 CTAs share each weight tile through one multicast copy.  It halves the weight
+  // reads at the L2 slices but not the bytes entering each SM, and the lockstep adds a cross-SM round trip to every
+  // stage recycle: measured 15 % slower on B200 (conv 2.03 ms vs 1.74 ms per step), so it is off by default.
+  static const int cluster_on = env_int("SAG_UMMA_CLUSTER", 1);
+  const int CL = (cluster_on >= 2 && MT >= 2) ? 2 : 1;
+  a.cluster = CL;
+  const int64_t n_work = cdiv64(MT, CL) * nt * Z;                   // per cluster
   static const int max_ctas = env_int("SAG_UMMA_MAX_CTAS", 0);      // test knob: force many work items per CTA
-  const int64_t ctas = max_ctas > 0 ? max_ctas : num_sms();
-  const unsigned grid = (unsigned)(n_work < ctas ? n_work : ctas);
-  kern<<<grid, UM_THREADS, smem, st>>>(g, a);
+  int64_t clusters = (max_ctas > 0 ? max_ctas : num_sms()) / CL;
+  if (clusters < 1) clusters = 1;
+  if (n_work < clusters) clusters = n_work;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(UM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = CL;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -853,6 +929,12 @@ int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, int sr
 }  // namespace
 
 // ---- host API -----------------------------------------------------------------------------------------------------
+// 256-wide tiles halve the A re-reads of wide layers (the gather is L2-bandwidth bound); they use all 512 TMEM columns
+static int tile_width(int N) {
+  static const int wide = env_int("SAG_UMMA_BN256", 1);
+  return N <= 32 ? 32 : (N <= 64 ? 64 : ((N >= 256 && wide) ? 256 : 128));
+}
+
 void umma_free(UmmaWeights* w) {
   if (w->packed) cudaFree(w->packed);
   if (w->col_off) cudaFree(w->col_off);
@@ -869,7 +951,7 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   UmmaWeights w;
   w.K = K; w.N = N;
   w.KC = cdiv(K, UM_BK);
-  w.BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);   // == tile_width(N)
+  w.BN = tile_width(N);
   w.NT = cdiv(N, w.BN);
   w.planes = precision == SAG_PREC_BF16X3 ? 2 : 1;
   const size_t bytes = (size_t)w.NT * w.KC * w.planes * w.BN * 128;
@@ -993,8 +1075,6 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
 // Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the
 // partial accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them
 // (deterministic: fixed summation order).
-static int tile_width(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
-
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   static const int enabled = env_int("SAG_UMMA_SPLITK", 1);
   const int BN = tile_width(N), NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
@@ -1068,6 +1148,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     case 32: r = launch_bn<32>(g, a, w.NT, w.planes, src, Z, st); break;
     case 64: r = launch_bn<64>(g, a, w.NT, w.planes, src, Z, st); break;
     case 128: r = launch_bn<128>(g, a, w.NT, w.planes, src, Z, st); break;
+    case 256: r = launch_bn<256>(g, a, w.NT, w.planes, src, Z, st); break;
     default: set_error("tcgen05 path: unsupported tile width %d", w.BN); return SAG_EINVAL;
   }
   SAG_TRY(r);
