@@ -66,6 +66,7 @@ struct UmmaArgs {
   int n_pad;
   int dense;              // output pixel m sits at element m*y_sw (no row decode)
   int NT, Z;              // N tiles, K splits
+  long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
   int cluster;            // CTAs per cluster (1 or 2): the CTAs of a cluster take adjacent M tiles and share the weight copy
 };
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -144,6 +145,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -203,6 +214,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed (count pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -312,7 +327,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   if (warp == UM_MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, UM_PRODUCER_WARPS + 1);   // 8 producer warps + the expect_tx arrival of the B copy
+        mbar_init(bar_full + 8 * s, UM_PRODUCER_WARPS * 32 + 1);   // every producer thread + the expect_tx arrival of the B copy
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -347,23 +362,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
     int stage = 0;
     uint32_t phase = 0;
-    int pending = 0, pub_stage = 0;             // cp.async path: chunks issued but not yet published
-    auto publish = [&]() {
-      fence_proxy_async();                      // writes of this thread -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * pub_stage);
-      if (++pub_stage == S) pub_stage = 0;
-      --pending;
-    };
-    auto wait_oldest = [&]() {                  // the oldest of `pending` cp.async groups has landed
-      switch (pending) {
-        case 1: cp_async_wait<0>(); break;
-        case 2: cp_async_wait<1>(); break;
-        case 3: cp_async_wait<2>(); break;
-        case 4: cp_async_wait<3>(); break;
-        default: cp_async_wait<4>(); break;
-      }
-    };
+    long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
     for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
       int mt, nt, z;
       decode_work(wk, mt, nt, z);
@@ -394,9 +393,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         const int ci0 = kk - t * g.Cin;
         float f[4][8];
         if (SRC == SRC_BF2) {
-          // publish the oldest outstanding chunk BEFORE claiming the next stage: claiming waits for the MMAs of chunk
-          // kc-S, and the tensor pipe must already hold the following chunk by then
-          if (pending == S - 1) { wait_oldest(); publish(); }
+          // nothing to stage in registers: the copies go straight to shared memory below
         } else if (VEC) {
           const bool kok = kk < a.K;
           const int dy = kok ? g.dy[t] : 0, dx = kok ? g.dx[t] : 0;
@@ -432,7 +429,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
           }
         }
         // claim the stage: the MMAs that read it last time round have completed; start the weight copy
+        const long long tr_w0 = a.trace ? clock64() : 0;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (a.trace) { tr_wait += clock64() - tr_w0; ++tr_chunks; }
         const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
@@ -462,8 +461,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             cp_async16(st_base + off, src, ok ? 16u : 0u);
             if (PLANES == 2) cp_async16(st_base + UM_A_PLANE + off, src + (ok ? a.x_plane : 0), ok ? 16u : 0u);
           }
-          cp_async_commit();
-          ++pending;
+          // asynchronous publication: the full barrier gets this thread's arrival when its copies have landed -- no
+          // wait and no fence here (a MEMBAR in the producer would wait for every copy in flight and serialise the
+          // ring); the MMA thread orders the generic-proxy writes against the tensor core after its barrier wait
+          cp_async_arrive_noinc(bar_full + 8 * stage);
         } else {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -474,52 +475,72 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             st_shared_v4(st_base + off, hi);
             if (PLANES == 2) st_shared_v4(st_base + UM_A_PLANE + off, lo);
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+          fence_proxy_async();                     // st.shared of this thread -> visible to the tensor core
+          mbar_arrive(bar_full + 8 * stage);
         }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-    while (pending > 0) { wait_oldest(); publish(); }      // drain in order
+    if (a.trace && tid == 0) {
+      a.trace[blockIdx.x * 8 + 2] = tr_wait;
+      a.trace[blockIdx.x * 8 + 3] = clock64() - tr_t0;
+      a.trace[blockIdx.x * 8 + 6] = tr_chunks;
+    }
   } else if (warp == UM_MMA_WARP) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow keeps the shared-memory descriptors in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
       int64_t it_local = 0;
+      long long tr_wait = 0, tr_wacc = 0, tr_t0 = clock64();
+      constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);   // LBO, SBO, version, SW128
       for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
         int mt, nt, z;
         decode_work(wk, mt, nt, z);
         const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
         const int b = (int)(it_local & 1);
         const uint32_t use = (uint32_t)(it_local >> 1);
+        const long long tr_a0 = a.trace ? clock64() : 0;
         mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);      // the epilogue has drained this accumulator
+        if (a.trace) tr_wacc += clock64() - tr_a0;
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
         for (int kc = kc_begin; kc < kc_end; ++kc) {
+          const long long tr_w0 = a.trace ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
+          if (a.trace) tr_wait += clock64() - tr_w0;
+          if (SRC == SRC_BF2) fence_proxy_async();   // cp.async (generic proxy) writes observed through the barrier
           tc_fence_after();
           const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
-          const uint32_t a_hi = st_base, a_lo = st_base + UM_A_PLANE;
-          const uint32_t b_hi = st_base + PLANES * UM_A_PLANE, b_lo = b_hi + B_PLANE;
+          // descriptor low words (address >> 4) of the four operand planes; +2 per 32-byte K step inside the atom
+          const uint64_t da_hi = DESC_HI | (uint64_t)((st_base & 0x3FFFFu) >> 4);
+          const uint64_t da_lo = DESC_HI | (uint64_t)(((st_base + UM_A_PLANE) & 0x3FFFFu) >> 4);
+          const uint64_t db_hi = DESC_HI | (uint64_t)(((st_base + PLANES * UM_A_PLANE) & 0x3FFFFu) >> 4);
+          const uint64_t db_lo = DESC_HI | (uint64_t)(((st_base + PLANES * UM_A_PLANE + B_PLANE) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
-            const uint64_t da_hi = make_sw128_desc(a_hi + k4 * 32), db_hi = make_sw128_desc(b_hi + k4 * 32);
-            umma_bf16(tmem_acc, da_hi, db_hi, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
-            if (NSPLIT == 3) {
-              const uint64_t da_lo = make_sw128_desc(a_lo + k4 * 32), db_lo = make_sw128_desc(b_lo + k4 * 32);
-              umma_bf16(tmem_acc, da_lo, db_hi, IDESC, 1u);
-              umma_bf16(tmem_acc, da_hi, db_lo, IDESC, 1u);
+            for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
+              umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+              if (NSPLIT == 3) {
+                umma_bf16(tmem_acc, da_lo + 2 * k4, db_hi + 2 * k4, IDESC, 1u);
+                umma_bf16(tmem_acc, da_hi + 2 * k4, db_lo + 2 * k4, IDESC, 1u);
+              }
             }
+            umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
+            if (kc + 1 == kc_end) umma_commit(bar_tfull + 8 * b);   // accumulator complete
           }
-          umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * b);            // accumulator complete
+      }
+      if (a.trace && lane == 0) {
+        a.trace[blockIdx.x * 8 + 0] = tr_wait;
+        a.trace[blockIdx.x * 8 + 1] = clock64() - tr_t0;
+        a.trace[blockIdx.x * 8 + 7] = tr_wacc;
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue (4 warps = the 4 TMEM lane quadrants) ================================
     const int q = warp & 3;                        // warps 8..11 -> quadrants 0..3
@@ -528,6 +549,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     const bool raw = a.partial != nullptr;
     float* yf = reinterpret_cast<float*>(a.y);
     int64_t it_local = 0;
+    long long tr_wait = 0, tr_t0 = clock64();
     for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int mt, nt, z;
       decode_work(wk, mt, nt, z);
@@ -555,7 +577,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         }
         s_yoff[et] = yo; s_oy[et] = oy; s_ox[et] = ox;
       }
+      const long long tr_w0 = a.trace ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * b, use & 1);
+      if (a.trace) tr_wait += clock64() - tr_w0;
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -568,7 +592,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
         }
-        if (!raw) {
+        if (!raw && (a.bias != nullptr || a.relu)) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int n = n_base + c0 + e;
@@ -587,64 +611,96 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         const int lr = lane >> 3, lc = (lane & 7) * 4;
         const int n = n_base + c0 + lc;
         const int ncols = raw ? a.n_pad : a.Ntot;
-#pragma unroll 2
-        for (int rd = 0; rd < 8; ++rd) {
-          const int rr = rd * 16 + q * 4 + lr;
-          const long long yo = s_yoff[rr];
-          if (yo == UM_ROW_INVALID || n >= ncols) continue;
-          float4 w4;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
-                       : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
-          const float t4[4] = {w4.x, w4.y, w4.z, w4.w};
-          if (raw) {
-            *reinterpret_cast<float4*>(a.partial + yo + n) = w4;
-          } else if (a.col_off == nullptr) {
-            if (a.vec_store) {
-              if (a.out_bf2) store_bf2_4(a.y, a.y_plane, yo + n, t4, a.out_bf2);
-              else *reinterpret_cast<float4*>(yf + yo + n) = w4;
-            } else {
+        const int rows_valid = (int)((M - m0) < UM_BM ? ((M - m0) > 0 ? (M - m0) : 0) : UM_BM);   // valid rows come first
+        if (n < ncols) {
+          if (raw || (a.dense && a.vec_store)) {
+            // fast path: row rr of the tile lands at a fixed stride; all loads first, then all stores
+            float4 w4[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e >= a.Ntot) continue;
-                const int64_t eoff = yo + (int64_t)(n + e) * g.y_sc;
-                if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
-                else yf[eoff] = t4[e];
+            for (int rd = 0; rd < 8; ++rd) {
+              const int rr = rd * 16 + q * 4 + lr;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4[rd].x), "=f"(w4[rd].y), "=f"(w4[rd].z), "=f"(w4[rd].w)
+                           : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
+            }
+            const int64_t rstride = raw ? (int64_t)a.n_pad : g.y_sw;
+            const int64_t base = (raw ? ((int64_t)z * M + m0) * a.n_pad : m0 * g.y_sw) + n;
+#pragma unroll
+            for (int rd = 0; rd < 8; ++rd) {
+              const int rr = rd * 16 + q * 4 + lr;
+              if (rr >= rows_valid) continue;
+              const int64_t eoff = base + (int64_t)rr * rstride;
+              if (raw) {
+                *reinterpret_cast<float4*>(a.partial + eoff) = w4[rd];
+              } else if (a.out_bf2) {
+                const float t4[4] = {w4[rd].x, w4[rd].y, w4[rd].z, w4[rd].w};
+                store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
+              } else {
+                *reinterpret_cast<float4*>(yf + eoff) = w4[rd];
               }
             }
           } else {
-            const int oy = s_oy[rr], ox = s_ox[rr];
-            if (a.vec_store) {
-              if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim) {
-                const int64_t eoff = yo + a.col_off[n];
-                if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
-                else *reinterpret_cast<float4*>(yf + eoff) = w4;
-              }
-            } else {
+#pragma unroll 2
+            for (int rd = 0; rd < 8; ++rd) {
+              const int rr = rd * 16 + q * 4 + lr;
+              const long long yo = s_yoff[rr];
+              if (yo == UM_ROW_INVALID) continue;
+              float4 w4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                           : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
+              const float t4[4] = {w4.x, w4.y, w4.z, w4.w};
+              if (a.col_off == nullptr) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e >= a.Ntot) continue;
-                if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
-                const int64_t eoff = yo + a.col_off[n + e];
-                if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
-                else yf[eoff] = t4[e];
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e >= a.Ntot) continue;
+                  const int64_t eoff = yo + (int64_t)(n + e) * g.y_sc;
+                  if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
+                  else yf[eoff] = t4[e];
+                }
+              } else {
+                const int oy = s_oy[rr], ox = s_ox[rr];
+                if (a.vec_store) {
+                  if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim) {
+                    const int64_t eoff = yo + a.col_off[n];
+                    if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
+                    else *reinterpret_cast<float4*>(yf + eoff) = w4;
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    if (n + e >= a.Ntot) continue;
+                    if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
+                    const int64_t eoff = yo + a.col_off[n + e];
+                    if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
+                    else yf[eoff] = t4[e];
+                  }
+                }
               }
             }
           }
         }
-        if (stats) {                               // column sums of the staged pass: 4 threads per column
+        if (stats) {                               // column sums of the staged pass: 4 threads per column, 32 rows each
           const int c = et & 31, part = et >> 5;
-          float cs = 0.f, cq = 0.f;
-          for (int rr = part; rr < UM_BM; rr += 4) {
-            if (s_yoff[rr] == UM_ROW_INVALID) continue;
+          float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int rr = part + 4 * i;
             float x;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)c * 4u));
-            cs += x;
-            cq = fmaf(x, x, cq);
+            if (rr >= rows_valid) x = 0.f;
+            cs[i & 3] += x;
+            cq[i & 3] = fmaf(x, x, cq[i & 3]);
           }
-          if (n_base + c0 + c < a.Ntot) { atomicAdd(&s_sum[n_base + c0 + c], cs); atomicAdd(&s_sqs[n_base + c0 + c], cq); }
+          if (n_base + c0 + c < a.Ntot) {
+            atomicAdd(&s_sum[n_base + c0 + c], (cs[0] + cs[1]) + (cs[2] + cs[3]));
+            atomicAdd(&s_sqs[n_base + c0 + c], (cq[0] + cq[1]) + (cq[2] + cq[3]));
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");   // staging tile and row table reusable
       }
+    }
+    if (a.trace && et == 0) {
+      a.trace[blockIdx.x * 8 + 4] = tr_wait;
+      a.trace[blockIdx.x * 8 + 5] = clock64() - tr_t0;
     }
   }
 
@@ -906,6 +962,33 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
+  // debug: SAG_UMMA_TRACE=<M tiles> prints where the three roles of the first launch with that many M tiles wait
+  static const int trace_mt = env_int("SAG_UMMA_TRACE", 0);
+  static int traced = 0;
+  if (trace_mt > 0 && MT == trace_mt && traced < env_int("SAG_UMMA_TRACE_N", 1)) {
+    ++traced;
+    const size_t n = (size_t)cfg.gridDim.x * 8;
+    long long* dtr = nullptr;
+    cudaMalloc(&dtr, n * sizeof(long long));
+    cudaMemset(dtr, 0, n * sizeof(long long));
+    a.trace = dtr;
+    cudaStreamSynchronize(st);
+    cudaLaunchKernelEx(&cfg, kern, g, a);
+    cudaStreamSynchronize(st);
+    std::vector<long long> tr(n);
+    cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dtr);
+    double d[8] = {0};
+    for (size_t c = 0; c < n / 8; ++c)
+      for (int i = 0; i < 8; ++i) d[i] += (double)tr[c * 8 + i] / (double)(n / 8);
+    fprintf(stderr, "[umma trace] BN=%d NSPLIT=%d SRC=%d ctas=%u MT=%lld NT=%d Z=%d KC=%d stages=%d chunks/cta=%.1f\n", BN, NSPLIT, SRC,
+            cfg.gridDim.x, (long long)MT, nt, Z, a.KC, S, d[6]);
+    fprintf(stderr, "[umma trace]   MMA thread   : total %9.0f clk, waiting for operands %9.0f, for a free accumulator %9.0f\n", d[1], d[0], d[7]);
+    fprintf(stderr, "[umma trace]   producer t0  : total %9.0f clk, waiting for a free stage %9.0f\n", d[3], d[2]);
+    fprintf(stderr, "[umma trace]   epilogue t0  : total %9.0f clk, waiting for an accumulator %9.0f\n", d[5], d[4]);
+    SAG_LAUNCH_CHECK();
+    return SAG_OK;
+  }
   SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
   SAG_LAUNCH_CHECK();
   return SAG_OK;
