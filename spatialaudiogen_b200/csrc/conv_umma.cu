@@ -301,6 +301,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
   __shared__ long long s_yoff[UM_BM];                    // per-row output element offset of the tile in the epilogue
   __shared__ int s_oy[UM_BM], s_ox[UM_BM];
+  __shared__ float s_part[UM_EPI_WARPS][64];             // per-epilogue-warp column sums / sums of squares of a pass
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = smem_u32(um_smem);
@@ -482,9 +483,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       }
     }
     if (a.trace && tid == 0) {
-      a.trace[blockIdx.x * 8 + 2] = tr_wait;
-      a.trace[blockIdx.x * 8 + 3] = clock64() - tr_t0;
-      a.trace[blockIdx.x * 8 + 6] = tr_chunks;
+      a.trace[blockIdx.x * 16 + 2] = tr_wait;
+      a.trace[blockIdx.x * 16 + 3] = clock64() - tr_t0;
+      a.trace[blockIdx.x * 16 + 6] = tr_chunks;
     }
   } else if (warp == UM_MMA_WARP) {
     // ================================ MMA issuer ================================
@@ -536,9 +537,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         }
       }
       if (a.trace && lane == 0) {
-        a.trace[blockIdx.x * 8 + 0] = tr_wait;
-        a.trace[blockIdx.x * 8 + 1] = clock64() - tr_t0;
-        a.trace[blockIdx.x * 8 + 7] = tr_wacc;
+        a.trace[blockIdx.x * 16 + 0] = tr_wait;
+        a.trace[blockIdx.x * 16 + 1] = clock64() - tr_t0;
+        a.trace[blockIdx.x * 16 + 7] = tr_wacc;
       }
     }
   } else {
@@ -550,6 +551,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     float* yf = reinterpret_cast<float*>(a.y);
     int64_t it_local = 0;
     long long tr_wait = 0, tr_t0 = clock64();
+    long long tr_p[5] = {0, 0, 0, 0, 0};
     for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int mt, nt, z;
       decode_work(wk, mt, nt, z);
@@ -585,6 +587,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
+        long long tp0 = a.trace ? clock64() : 0;
         tmem_ld16(tmem_row + (uint32_t)c0, v);
         tmem_ld16(tmem_row + (uint32_t)c0 + 16u, v + 16);
         if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
@@ -606,7 +609,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         for (int e = 0; e < 32; e += 4)
           st_shared_v4(stile + (uint32_t)et * PITCH + (uint32_t)e * 4u,
                        make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+        long long tp1 = a.trace ? clock64() : 0;
         asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+        long long tp2 = a.trace ? clock64() : 0;
         // copy-out: a warp instruction covers 4 rows x 128 contiguous bytes; 4 warps x 8 rounds = 128 rows
         const int lr = lane >> 3, lc = (lane & 7) * 4;
         const int n = n_base + c0 + lc;
@@ -639,7 +644,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
               }
             }
           } else {
-#pragma unroll 2
+            // column map of this thread's 4 columns (fixed for the whole pass)
+            int c_off[4] = {0, 0, 0, 0}, c_dy[4] = {0, 0, 0, 0}, c_dx[4] = {0, 0, 0, 0};
+            if (a.col_off != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < a.Ntot) { c_off[e] = __ldg(a.col_off + n + e); c_dy[e] = __ldg(a.col_dy + n + e); c_dx[e] = __ldg(a.col_dx + n + e); }
+            }
+#pragma unroll 4
             for (int rd = 0; rd < 8; ++rd) {
               const int rr = rd * 16 + q * 4 + lr;
               const long long yo = s_yoff[rr];
@@ -659,8 +671,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
               } else {
                 const int oy = s_oy[rr], ox = s_ox[rr];
                 if (a.vec_store) {
-                  if ((unsigned)(oy + a.col_dy[n]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n]) < (unsigned)a.ow_lim) {
-                    const int64_t eoff = yo + a.col_off[n];
+                  if ((unsigned)(oy + c_dy[0]) < (unsigned)a.oh_lim && (unsigned)(ox + c_dx[0]) < (unsigned)a.ow_lim) {
+                    const int64_t eoff = yo + c_off[0];
                     if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
                     else *reinterpret_cast<float4*>(yf + eoff) = w4;
                   }
@@ -668,8 +680,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     if (n + e >= a.Ntot) continue;
-                    if (!((unsigned)(oy + a.col_dy[n + e]) < (unsigned)a.oh_lim && (unsigned)(ox + a.col_dx[n + e]) < (unsigned)a.ow_lim)) continue;
-                    const int64_t eoff = yo + a.col_off[n + e];
+                    if (!((unsigned)(oy + c_dy[e]) < (unsigned)a.oh_lim && (unsigned)(ox + c_dx[e]) < (unsigned)a.ow_lim)) continue;
+                    const int64_t eoff = yo + c_off[e];
                     if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
                     else yf[eoff] = t4[e];
                   }
@@ -678,6 +690,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             }
           }
         }
+        long long tp3 = a.trace ? clock64() : 0;
         if (stats) {                               // column sums of the staged pass: 4 threads per column, 32 rows each
           const int c = et & 31, part = et >> 5;
           float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -690,17 +703,28 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
             cs[i & 3] += x;
             cq[i & 3] = fmaf(x, x, cq[i & 3]);
           }
-          if (n_base + c0 + c < a.Ntot) {
-            atomicAdd(&s_sum[n_base + c0 + c], (cs[0] + cs[1]) + (cs[2] + cs[3]));
-            atomicAdd(&s_sqs[n_base + c0 + c], (cq[0] + cq[1]) + (cq[2] + cq[3]));
-          }
+          // per-warp partials; epilogue warp 0 folds them into the CTA sums after the barrier below, in a fixed order
+          // (no atomics: the per-CTA statistics are run-to-run reproducible)
+          s_part[part][c] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
+          s_part[part][32 + c] = (cq[0] + cq[1]) + (cq[2] + cq[3]);
         }
+        long long tp4 = a.trace ? clock64() : 0;
         asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");   // staging tile and row table reusable
+        if (stats && et < 32 && n_base + c0 + et < a.Ntot) {
+          // (the next pass rewrites s_part only after its own first barrier, which this warp has not reached yet)
+          s_sum[n_base + c0 + et] += (s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et]);
+          s_sqs[n_base + c0 + et] += (s_part[0][32 + et] + s_part[1][32 + et]) + (s_part[2][32 + et] + s_part[3][32 + et]);
+        }
+        if (a.trace) {
+          const long long tp5 = clock64();
+          tr_p[0] += tp1 - tp0; tr_p[1] += tp3 - tp2; tr_p[2] += tp4 - tp3; tr_p[3] += (tp2 - tp1) + (tp5 - tp4); tr_p[4] += 1;
+        }
       }
     }
     if (a.trace && et == 0) {
-      a.trace[blockIdx.x * 8 + 4] = tr_wait;
-      a.trace[blockIdx.x * 8 + 5] = clock64() - tr_t0;
+      for (int i = 0; i < 5; ++i) a.trace[blockIdx.x * 16 + 8 + i] = tr_p[i];
+      a.trace[blockIdx.x * 16 + 4] = tr_wait;
+      a.trace[blockIdx.x * 16 + 5] = clock64() - tr_t0;
     }
   }
 
@@ -967,7 +991,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
   static int traced = 0;
   if (trace_mt > 0 && MT == trace_mt && traced < env_int("SAG_UMMA_TRACE_N", 1)) {
     ++traced;
-    const size_t n = (size_t)cfg.gridDim.x * 8;
+    const size_t n = (size_t)cfg.gridDim.x * 16;
     long long* dtr = nullptr;
     cudaMalloc(&dtr, n * sizeof(long long));
     cudaMemset(dtr, 0, n * sizeof(long long));
@@ -978,14 +1002,16 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
     std::vector<long long> tr(n);
     cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dtr);
-    double d[8] = {0};
-    for (size_t c = 0; c < n / 8; ++c)
-      for (int i = 0; i < 8; ++i) d[i] += (double)tr[c * 8 + i] / (double)(n / 8);
+    double d[16] = {0};
+    for (size_t c = 0; c < n / 16; ++c)
+      for (int i = 0; i < 16; ++i) d[i] += (double)tr[c * 16 + i] / (double)(n / 16);
     fprintf(stderr, "[umma trace] BN=%d NSPLIT=%d SRC=%d ctas=%u MT=%lld NT=%d Z=%d KC=%d stages=%d chunks/cta=%.1f\n", BN, NSPLIT, SRC,
             cfg.gridDim.x, (long long)MT, nt, Z, a.KC, S, d[6]);
     fprintf(stderr, "[umma trace]   MMA thread   : total %9.0f clk, waiting for operands %9.0f, for a free accumulator %9.0f\n", d[1], d[0], d[7]);
     fprintf(stderr, "[umma trace]   producer t0  : total %9.0f clk, waiting for a free stage %9.0f\n", d[3], d[2]);
     fprintf(stderr, "[umma trace]   epilogue t0  : total %9.0f clk, waiting for an accumulator %9.0f\n", d[5], d[4]);
+    fprintf(stderr, "[umma trace]   epilogue t0  : tmem->smem %9.0f, copy-out %9.0f, statistics %9.0f, barriers %9.0f (sum over %0.f passes)\n",
+            d[8], d[9], d[10], d[11], d[12]);
     SAG_LAUNCH_CHECK();
     return SAG_OK;
   }
