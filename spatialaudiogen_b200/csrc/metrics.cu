@@ -61,28 +61,38 @@ struct MetricPlans {
   FftPlan env;    // T (scipy.signal.hilbert over the whole 0.1 s window)
 };
 
-// windowed FFT of sig[off, off+n) into a result buffer; returns pointer to result
-__device__ float2* windowed_fft(const float* sig, int off, const FftPlan& p, float2* b0, float2* b1) {
+// Hann-windowed frames of gt and pred at sample offset `off`, transformed together (one set of block-wide passes):
+// result[0..n) = FFT(gt frame), result[n..2n) = FFT(pred frame)
+__device__ const float2* windowed_fft_pair(const float* sg, const float* sp, int off, const FftPlan& p, float2* b0, float2* b1) {
   __syncthreads();
-  for (int i = threadIdx.x; i < p.n; i += blockDim.x) b0[i] = make_float2(sig[off + i] * __ldg(p.hann + i), 0.f);
-  return block_fft(b0, b1, p);
+  for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+    const float w = __ldg(p.hann + i);
+    b0[i] = make_float2(sg[off + i] * w, 0.f);
+    b0[p.n + i] = make_float2(sp[off + i] * w, 0.f);
+  }
+  return block_fft_nf(b0, b1, p, 2);
 }
 
-__global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int t,
-                                                      const MetricPlans P, float* __restrict__ stft_ps,
+// One CTA per (task, window, channel); tasks: 0 = Hilbert envelope distance (the longest, scheduled first),
+// 1 = STFT distance + temporal MSE / SNR / amplitudes, 2 = LSD.  gt and pred ride every transform together.
+__global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int batch,
+                                                      int t, const MetricPlans P, int has_env, float* __restrict__ stft_ps,
                                                       float* __restrict__ lsd_ps, float* __restrict__ mse_ps,
                                                       float* __restrict__ snr_ps, float* __restrict__ env_ps,
                                                       float* __restrict__ amp) {
   extern __shared__ __align__(16) float2 smem[];
-  const int nmax = max(max(P.stft.n, P.lsd.n), P.env.n);
-  float2* b0 = smem;
-  float2* b1 = smem + nmax;
-  float2* keep = smem + 2 * nmax;                       // spectrum / envelope of gt kept while pred is transformed
-  float* sg = reinterpret_cast<float*>(smem + 3 * nmax);  // gt signal [t]
-  float* sp = sg + t;                                   // pred signal [t]
   __shared__ float red[32];
+  const int nwc = batch * 3;
+  int task = blockIdx.x / nwc;
+  const int wc = blockIdx.x % nwc;                     // window * 3 + channel
+  if (!has_env) task += 1;                             // grid holds only tasks 1 and 2
+  const int b = wc / 3, ch = wc % 3;
+  const int nmax = task == 0 ? P.env.n : (task == 1 ? P.stft.n : P.lsd.n);
+  float2* b0 = smem;
+  float2* b1 = smem + 2 * nmax;
+  float* sg = reinterpret_cast<float*>(smem + 4 * nmax);   // gt signal [t]
+  float* sp = sg + t;                                      // pred signal [t]
 
-  const int b = blockIdx.x / 3, ch = blockIdx.x % 3;
   const float* pg = gt + (int64_t)b * t * 3 + ch;
   const float* pp = pred + (int64_t)b * t * 3 + ch;
   float se = 0.f, sgg = 0.f, mp = 0.f, mg = 0.f;
@@ -96,99 +106,83 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
     mp = fmaxf(mp, fabsf(p));
     mg = fmaxf(mg, fabsf(g));
   }
-  se = block_sum(se, red);
-  sgg = block_sum(sgg, red);
-  mp = block_max(mp, red);
-  mg = block_max(mg, red);
-  if (threadIdx.x == 0) {
-    mse_ps[blockIdx.x] = se / (float)t;                                         // model.py:99
-    snr_ps[blockIdx.x] = 10.f * logf((sgg + 0.1f) / (se + 0.1f)) / logf(10.f);  // model.py:105-107
-    atomicMax(reinterpret_cast<int*>(amp + b * 2 + 0), __float_as_int(mp));      // eval.py:197-198 (values >= 0)
-    atomicMax(reinterpret_cast<int*>(amp + b * 2 + 1), __float_as_int(mg));
-  }
 
-  // ---- STFT distance: windows of n=2048 at stride n/2 grouped as myutils.py:167-173 builds them ----
-  {
+  if (task == 1) {
+    se = block_sum(se, red);
+    sgg = block_sum(sgg, red);
+    mp = block_max(mp, red);
+    mg = block_max(mg, red);
+    if (threadIdx.x == 0) {
+      mse_ps[wc] = se / (float)t;                                         // model.py:99
+      snr_ps[wc] = 10.f * logf((sgg + 0.1f) / (se + 0.1f)) / logf(10.f);  // model.py:105-107
+      atomicMax(reinterpret_cast<int*>(amp + b * 2 + 0), __float_as_int(mp));      // eval.py:197-198 (values >= 0)
+      atomicMax(reinterpret_cast<int*>(amp + b * 2 + 1), __float_as_int(mg));
+    }
+    // ---- STFT distance: windows of n=2048 at stride n/2 grouped as myutils.py:167-173 builds them ----
     const int n = P.stft.n, stride = n / 2;
     float acc_total = 0.f;
     int nwin_total = 0;
     for (int i = 0; i < 2; ++i) {
       int nW = (t - i * stride - 1) / n;
       for (int wdx = 0; wdx < nW; ++wdx) {
-        int off = i * stride + wdx * n;
-        float2* r = windowed_fft(sg, off, P.stft, b0, b1);
-        for (int k = threadIdx.x; k < n; k += blockDim.x) keep[k] = r[k];
-        r = windowed_fft(sp, off, P.stft, b0, b1);
+        const float2* r = windowed_fft_pair(sg, sp, i * stride + wdx * n, P.stft, b0, b1);
         float a = 0.f;
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
-          float dx = keep[k].x - r[k].x, dy = keep[k].y - r[k].y;
-          a += dx * dx + dy * dy;                                                // |stft_gt - stft_pred|^2
+          float dx = r[k].x - r[n + k].x, dy = r[k].y - r[n + k].y;
+          a += dx * dx + dy * dy;                                          // |stft_gt - stft_pred|^2
         }
-        acc_total += block_sum(a, red) / (float)n;                               // mean over freq
+        acc_total += block_sum(a, red) / (float)n;                         // mean over freq
         ++nwin_total;
       }
     }
-    if (threadIdx.x == 0) stft_ps[blockIdx.x] = nwin_total > 0 ? acc_total / (float)nwin_total : 0.f;
-  }
-
-  // ---- LSD: myutils.stft(x, 1200, 2): n_winds = t/1200 - 1, frames at hop 600 ----
-  {
+    if (threadIdx.x == 0) stft_ps[wc] = nwin_total > 0 ? acc_total / (float)nwin_total : 0.f;
+  } else if (task == 2) {
+    // ---- LSD: myutils.stft(x, 1200, 2): n_winds = t/1200 - 1, frames at hop 600 ----
     const int n = P.lsd.n, hop = n / 2;
     const int nframes = 2 * (t / n - 1);
     float acc_total = 0.f;
     const float k10 = 10.f / logf(10.f);
     for (int f = 0; f < nframes; ++f) {
-      float2* r = windowed_fft(sg, f * hop, P.lsd, b0, b1);
-      for (int k = threadIdx.x; k < n; k += blockDim.x) keep[k].x = k10 * logf(hypotf(r[k].x, r[k].y) + 1e-2f);
-      r = windowed_fft(sp, f * hop, P.lsd, b0, b1);
+      const float2* r = windowed_fft_pair(sg, sp, f * hop, P.lsd, b0, b1);
       float a = 0.f;
       for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        float d = keep[k].x - k10 * logf(hypotf(r[k].x, r[k].y) + 1e-2f);
+        float d = k10 * (logf(hypotf(r[k].x, r[k].y) + 1e-2f) - logf(hypotf(r[n + k].x, r[n + k].y) + 1e-2f));
         a = fmaf(d, d, a);
       }
       acc_total += sqrtf(block_sum(a, red) / (float)n);
     }
-    if (threadIdx.x == 0) lsd_ps[blockIdx.x] = nframes > 0 ? acc_total / (float)nframes : 0.f;
-  }
-
-  // ---- Hilbert envelope distance: analytic signal via FFT (scipy.signal.hilbert), N = t ----
-  if (env_ps != nullptr) {
+    if (threadIdx.x == 0) lsd_ps[wc] = nframes > 0 ? acc_total / (float)nframes : 0.f;
+  } else {
+    // ---- Hilbert envelope distance: analytic signals via FFT (scipy.signal.hilbert), N = t, gt and pred together ----
     const int n = P.env.n;
     const float inv_n = 1.f / (float)n;
-    for (int pass = 0; pass < 2; ++pass) {
-      const float* sig = pass == 0 ? sg : sp;
-      __syncthreads();
-      for (int i = threadIdx.x; i < n; i += blockDim.x) b0[i] = make_float2(sig[i], 0.f);
-      float2* r = block_fft(b0, b1, P.env);
-      float2* o = (r == b0) ? b1 : b0;
-      // h[0]=1, h[1..n/2-1]=2, h[n/2]=1 (n even), rest 0 ; then inverse FFT via conj trick
-      for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        float h;
-        if ((n & 1) == 0) h = (k == 0 || k == n / 2) ? 1.f : (k < n / 2 ? 2.f : 0.f);
-        else h = (k == 0) ? 1.f : (k < (n + 1) / 2 ? 2.f : 0.f);
-        o[k] = make_float2(r[k].x * h, -r[k].y * h);
-      }
-      float2* other = (o == b0) ? b1 : b0;
-      float2* z = block_fft(o, other, P.env);           // conj(analytic)*n
-      if (pass == 0) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i].x = hypotf(z[i].x, z[i].y) * inv_n;
-      } else {
-        float a = 0.f;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-          float d = keep[i].x - hypotf(z[i].x, z[i].y) * inv_n;
-          a = fmaf(d, d, a);
-        }
-        a = block_sum(a, red);
-        if (threadIdx.x == 0) env_ps[blockIdx.x] = sqrtf(a * inv_n);
-      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      b0[i] = make_float2(sg[i], 0.f);
+      b0[n + i] = make_float2(sp[i], 0.f);
     }
+    float2* r = block_fft_nf(b0, b1, P.env, 2);
+    float2* o = (r == b0) ? b1 : b0;
+    // h[0]=1, h[1..n/2-1]=2, h[n/2]=1 (n even), rest 0 ; then inverse FFT via conj trick
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      float h;
+      if ((n & 1) == 0) h = (k == 0 || k == n / 2) ? 1.f : (k < n / 2 ? 2.f : 0.f);
+      else h = (k == 0) ? 1.f : (k < (n + 1) / 2 ? 2.f : 0.f);
+      o[k] = make_float2(r[k].x * h, -r[k].y * h);
+      o[n + k] = make_float2(r[n + k].x * h, -r[n + k].y * h);
+    }
+    const float2* z = block_fft_nf(o, r, P.env, 2);     // conj(analytic)*n for gt and pred
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float d = (hypotf(z[i].x, z[i].y) - hypotf(z[n + i].x, z[n + i].y)) * inv_n;
+      a = fmaf(d, d, a);
+    }
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) env_ps[wc] = sqrtf(a * inv_n);
   }
 }
 
-static size_t metrics_smem_bytes(int t, int n_stft, int n_lsd) {
-  int nmax = std::max(std::max(n_stft, n_lsd), t);
-  return (size_t)3 * nmax * sizeof(float2) + (size_t)2 * t * sizeof(float);
-}
+static size_t metrics_smem_bytes(int t, int nmax) { return (size_t)4 * nmax * sizeof(float2) + (size_t)2 * t * sizeof(float); }
 
 int launch_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
                    float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, cudaStream_t st) {
@@ -202,11 +196,14 @@ int launch_metrics(const float* pred, const float* gt, int batch, int t, int aud
   SAG_TRY(get_plan(n_stft, &P.stft));
   SAG_TRY(get_plan(window, &P.lsd));
   SAG_TRY(get_plan(t, &P.env));
-  size_t smem = metrics_smem_bytes(t, n_stft, window);
+  const int has_env = env_ps != nullptr ? 1 : 0;
+  const int nmax = std::max(std::max(n_stft, window), has_env ? t : 0);
+  size_t smem = metrics_smem_bytes(t, nmax);
   SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "metrics: %zu bytes of shared memory needed", smem);
   SAG_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SAG_CHECK_CUDA(cudaMemsetAsync(amp, 0, sizeof(float) * 2 * batch, st));
-  metrics_kernel<<<batch * 3, 256, smem, st>>>(pred, gt, t, P, stft_ps, lsd_ps, mse_ps, snr_ps, env_ps, amp);
+  metrics_kernel<<<batch * 3 * (has_env ? 3 : 2), 256, smem, st>>>(pred, gt, batch, t, P, has_env, stft_ps, lsd_ps, mse_ps,
+                                                                  snr_ps, env_ps, amp);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
