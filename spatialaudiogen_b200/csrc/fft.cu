@@ -29,10 +29,11 @@ int get_plan(int n, FftPlan* out) {
   memset(&p, 0, sizeof(p));
   p.n = n;
   int m = n;
-  while (m % 4 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 4; m /= 4; }
-  while (m % 2 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 2; m /= 2; }
-  while (m % 3 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 3; m /= 3; }
-  while (m % 5 == 0 && p.npass < kMaxPasses) { p.radix[p.npass++] = 5; m /= 5; }
+  auto add_pass = [&](unsigned r) { p.radix_code |= r << (4 * p.npass); ++p.npass; };
+  while (m % 4 == 0 && p.npass < kMaxPasses) { add_pass(4); m /= 4; }
+  while (m % 2 == 0 && p.npass < kMaxPasses) { add_pass(2); m /= 2; }
+  while (m % 3 == 0 && p.npass < kMaxPasses) { add_pass(3); m /= 3; }
+  while (m % 5 == 0 && p.npass < kMaxPasses) { add_pass(5); m /= 5; }
   SAG_REQUIRE(m == 1, SAG_EUNSUPPORTED, "fft: length %d is not a product of 2,3,5 (or too many passes)", n);
   SAG_REQUIRE(n <= 8192, SAG_EUNSUPPORTED, "fft: length %d too large for the shared-memory transform", n);
   std::vector<float2> tw(n);
@@ -157,24 +158,43 @@ __global__ void __launch_bounds__(256, REG_OLA ? 3 : 1) istft_pair_kernel(const 
     for (int g = 0; g < nf; ++g) {
       const float2* s = S + (row * n_frames + (f0 + g)) * (int64_t)n;
       const int64_t mo = (int64_t)(f0 + g) * n;
-      for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
-        const int kn = k == 0 ? 0 : n - k;
-        const float2 xk = __ldg(s + k), xn = __ldg(s + kn);
-        float gak = 1.f, gan = 1.f, gbk = has_b ? 1.f : 0.f, gbn = gbk;
-        if (ma != nullptr) {
-          gak = __ldg(ma + mo + k); gan = __ldg(ma + mo + kn);
-          if (apply_sigmoid) { gak = 1.f / (1.f + expf(-gak)); gan = 1.f / (1.f + expf(-gan)); }
+      constexpr int U = 3;                               // bins per thread per batch: all loads first, then the math
+      for (int kb0 = 0; kb0 <= n / 2; kb0 += U * 256) {
+        float2 xk[U], xn[U];
+        float mak[U], man[U], mbk[U], mbn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = kb0 + threadIdx.x + 256 * u;
+          xk[u] = xn[u] = make_float2(0.f, 0.f);
+          mak[u] = man[u] = mbk[u] = mbn[u] = 0.f;
+          if (k <= n / 2) {
+            const int kn = k == 0 ? 0 : n - k;
+            xk[u] = __ldg(s + k); xn[u] = __ldg(s + kn);
+            if (ma != nullptr) { mak[u] = __ldg(ma + mo + k); man[u] = __ldg(ma + mo + kn); }
+            if (mb != nullptr) { mbk[u] = __ldg(mb + mo + k); mbn[u] = __ldg(mb + mo + kn); }
+          }
         }
-        if (mb != nullptr) {
-          gbk = __ldg(mb + mo + k); gbn = __ldg(mb + mo + kn);
-          if (apply_sigmoid) { gbk = 1.f / (1.f + expf(-gbk)); gbn = 1.f / (1.f + expf(-gbn)); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = kb0 + threadIdx.x + 256 * u;
+          if (k > n / 2) continue;
+          const int kn = k == 0 ? 0 : n - k;
+          float gak = 1.f, gan = 1.f, gbk = has_b ? 1.f : 0.f, gbn = gbk;
+          if (ma != nullptr) {
+            gak = mak[u]; gan = man[u];
+            if (apply_sigmoid) { gak = 1.f / (1.f + expf(-gak)); gan = 1.f / (1.f + expf(-gan)); }
+          }
+          if (mb != nullptr) {
+            gbk = mbk[u]; gbn = mbn[u];
+            if (apply_sigmoid) { gbk = 1.f / (1.f + expf(-gbk)); gbn = 1.f / (1.f + expf(-gbn)); }
+          }
+          // Hermitian parts of the two masked spectra at bin k
+          const float2 ya = make_float2(0.5f * (gak * xk[u].x + gan * xn[u].x), 0.5f * (gak * xk[u].y - gan * xn[u].y));
+          const float2 yb = make_float2(0.5f * (gbk * xk[u].x + gbn * xn[u].x), 0.5f * (gbk * xk[u].y - gbn * xn[u].y));
+          // Z[k] = ya + i yb ; Z[N-k] = conj(ya) + i conj(yb); stored conjugated: ifft(Z) = conj(fft(conj Z)) / N
+          buf0[g * n + k] = make_float2(ya.x - yb.y, -(ya.y + yb.x));
+          buf0[g * n + kn] = make_float2(ya.x + yb.y, -(yb.x - ya.y));
         }
-        // Hermitian parts of the two masked spectra at bin k
-        const float2 ya = make_float2(0.5f * (gak * xk.x + gan * xn.x), 0.5f * (gak * xk.y - gan * xn.y));
-        const float2 yb = make_float2(0.5f * (gbk * xk.x + gbn * xn.x), 0.5f * (gbk * xk.y - gbn * xn.y));
-        // Z[k] = ya + i yb ; Z[N-k] = conj(ya) + i conj(yb); stored conjugated: ifft(Z) = conj(fft(conj Z)) / N
-        buf0[g * n + k] = make_float2(ya.x - yb.y, -(ya.y + yb.x));
-        buf0[g * n + kn] = make_float2(ya.x + yb.y, -(yb.x - ya.y));
       }
     }
     const float2* res = block_fft_nf(buf0, buf1, p, nf);     // res = N * (y_a - i y_b)

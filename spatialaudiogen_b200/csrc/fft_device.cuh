@@ -8,7 +8,8 @@ constexpr int kMaxPasses = 8;
 struct FftPlan {
   int n;
   int npass;
-  int radix[kMaxPasses];
+  unsigned radix_code;  // radix of pass s in bits [4s, 4s+4): register/constant-bank friendly (an indexed array would be
+                        // copied to local memory inside the kernels)
   const float2* tw;     // exp(-2*pi*i*m/n), m in [0,n)
   const float* hann;    // periodic Hann of length n
 };
@@ -151,7 +152,7 @@ __device__ __forceinline__ float2* block_fft_nf(float2* buf0, float2* buf1, cons
   float2* out = buf1;
   for (int s = 0; s < p.npass; ++s) {
     __syncthreads();
-    const int R = p.radix[s];
+    const int R = (int)((p.radix_code >> (4 * s)) & 15u);
     if (R == 4) stockham_pass_nf<4>(in, out, p.n, ns, p.tw, nf);
     else if (R == 2) stockham_pass_nf<2>(in, out, p.n, ns, p.tw, nf);
     else if (R == 3) stockham_pass_nf<3>(in, out, p.n, ns, p.tw, nf);
@@ -170,7 +171,7 @@ __device__ __forceinline__ float2* block_fft(float2* buf0, float2* buf1, const F
   float2* out = buf1;
   for (int s = 0; s < p.npass; ++s) {
     __syncthreads();
-    const int R = p.radix[s];
+    const int R = (int)((p.radix_code >> (4 * s)) & 15u);
     if (R == 4) stockham_pass<4>(in, out, p.n, ns, p.tw);
     else if (R == 2) stockham_pass<2>(in, out, p.n, ns, p.tw);
     else if (R == 3) stockham_pass<3>(in, out, p.n, ns, p.tw);
