@@ -370,8 +370,17 @@ def main():
     if peak_tf is None:
         peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md sustained)'
     ach = dense_fl / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:                                                  # DRAM bytes per launch of the same kernel family, from ncu
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel_traffic.json')))
+        if encoders == ['audio', 'video'] and B == 32 and precision == 'bf16x3':
+            traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/r1_dominant_kernel_traffic.json (%s)' % tj.get('source', 'ncu')
+    except Exception:
+        pass
     roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
-                'traffic': None, 'kernel': 'gather_gemm (conv / transposed-conv phases / FC contractions)',
+                'traffic': traffic, 'traffic_source': traffic_src,
+                'algorithmic_bytes_per_launch': (agg['conv'][2] + agg['deconv'][2] + agg['fc'][2]) / max(dense_n, 1),
+                'kernel': 'gather_gemm_umma_kernel (tcgen05 conv / sub-pixel transposed conv / FC contractions; splitk_reduce included in the time)',
                 'launches_per_step': dense_n, 'ms_per_step': dense_ms, 'executed_gflop_per_step': dense_fl / 1e9,
                 'reference_graph_gflop_per_step': conv_gflop_per_window(encoders) * B, 'peak_source': peak_src,
                 'breakdown_ms_per_step': {c: round(agg[c][0], 4) for c in cats},

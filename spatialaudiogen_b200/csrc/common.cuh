@@ -161,6 +161,20 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
                               int* ow_lim);
 
 // pointwise.cu
+// Batch statistics of one BN layer as the conv epilogues leave them: the consumer kernels turn them into per-channel
+// scale / shift in their prologue (no separate finalize launch).  scale = gamma*rsqrt(var+eps), shift = beta - mean*scale,
+// biased variance (contrib batch_norm, core.py:209-210).
+struct BnStats {
+  const double* sum = nullptr;
+  const double* sqs = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  double inv_count = 0.0;
+  float eps = 1e-3f;
+};
+int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& residual, int relu, const ActView& y, int64_t rows,
+                          int c, cudaStream_t st);
+int launch_bn_relu_maxpool_stats(const float* x, const BnStats& bn, int n, int h, int w, int c, const ActView& y, cudaStream_t st);
 int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
                        int c, float eps, float* scale, float* shift, cudaStream_t st);
 int launch_bn_apply(const float* x, const float* scale, const float* shift, const ActView& residual, int relu,

@@ -843,18 +843,33 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   const bool fixed_cg = (blockDim.x % ncg) == 0;
   int last_n = -1;
   float* yf = reinterpret_cast<float*>(a.y);
-  for (int idx = threadIdx.x; idx < rows * ncg; idx += blockDim.x) {
+  const int total = rows * ncg;
+  const int64_t zs = M * a.n_pad;
+  for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+   // four (row, column group) items per thread per round: all partial loads are issued before any is consumed
+   float4 accs[4];
+#pragma unroll
+   for (int u = 0; u < 4; ++u) {
+     accs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+     const int idx = base + u * blockDim.x;
+     if (idx < total) {
+       const int rr = idx / ncg, cg = idx - rr * ncg;
+       const float* pp = a.partial + (r0 + rr) * a.n_pad + cg * 4;
+#pragma unroll 4
+       for (int z = 0; z < Z; ++z) {
+         const float4 p = __ldcs(reinterpret_cast<const float4*>(pp + (int64_t)z * zs));
+         accs[u].x += p.x; accs[u].y += p.y; accs[u].z += p.z; accs[u].w += p.w;
+       }
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < 4; ++u) {
+    const int idx = base + u * blockDim.x;
+    if (idx >= total) continue;
     const int rr = idx / ncg, cg = idx - rr * ncg;
     const int n = cg * 4;
     const int64_t m = r0 + rr;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* pp = a.partial + m * a.n_pad + n;
-    const int64_t zs = M * a.n_pad;
-#pragma unroll 4
-    for (int z = 0; z < Z; ++z) {
-      const float4 p = __ldcs(reinterpret_cast<const float4*>(pp + (int64_t)z * zs));
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
+    const float4 acc = accs[u];
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -909,6 +924,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
           if (n + e < a.Ntot) { atomicAdd(&s_sum[n + e], v[e]); atomicAdd(&s_sqs[n + e], v[e] * v[e]); }
       }
     }
+   }
   }
   if (stats) {
     if (fixed_cg && last_n >= 0) {

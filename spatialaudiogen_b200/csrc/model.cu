@@ -313,13 +313,13 @@ struct Fwd {
 };
 
 // contrib batch_norm(is_training=True) statistics -> per-channel scale/shift (core.py:209-210)
-struct BnBuf { double* sum; double* sqs; float* scale; float* shift; };
-static BnBuf alloc_bn(Arena& ar, int c) {
+struct BnBuf { double* sum; double* sqs; };
+// all statistics accumulators of a tower live in one block that is cleared with a single memset
+static BnBuf take_bn(double*& pool, int c) {
   BnBuf b;
-  b.sum = ar.alloc<double>(2 * c);
-  b.sqs = b.sum + c;
-  b.scale = ar.alloc<float>(2 * c);
-  b.shift = b.scale + c;
+  b.sum = pool;
+  b.sqs = pool + c;
+  pool += 2 * c;
   return b;
 }
 
@@ -332,26 +332,27 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   const std::string p = scope + "/";
   const float eps = 1e-3f;
   int err = SAG_OK;
-  auto bn_finalize = [&](const std::string& q, const BnBuf& b, int c, int64_t count) -> int {
+  auto bn_stats = [&](const std::string& q, const BnBuf& b, int64_t count, BnStats* out) -> int {
     if (ar.dry) return SAG_OK;
-    const float* gamma = f.W(q + "/bn/gamma", &err);
-    const float* beta = f.W(q + "/bn/beta", &err);
-    SAG_TRY(err);
-    return launch_bn_finalize(b.sum, b.sqs, gamma, beta, (double)count, c, eps, b.scale, b.shift, st);
+    out->sum = b.sum; out->sqs = b.sqs;
+    out->gamma = f.W(q + "/bn/gamma", &err);
+    out->beta = f.W(q + "/bn/beta", &err);
+    out->inv_count = 1.0 / (double)count;
+    out->eps = eps;
+    return err;
   };
-  auto zero_bn = [&](const BnBuf& b, int c) -> int {
-    if (ar.dry) return SAG_OK;
-    SAG_CHECK_CUDA(cudaMemsetAsync(b.sum, 0, sizeof(double) * 2 * c, st));
-    return SAG_OK;
-  };
+  // statistics accumulators: conv1 (64) + two per block
+  int64_t n_stat = 2 * 64;
+  for (const BlockDef& b : kBlocks) n_stat += 4 * b.cout;
+  double* stat_pool = ar.alloc<double>(n_stat);
+  if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(double) * n_stat, st));
   const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;   // bytes per activation element
 
   // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
   int oh, ow;
   int OH1 = (H + 1) / 2, OW1 = (Wd + 1) / 2;
   Act c1 = f.alloc_f32((int64_t)B * OH1 * OW1, 64);
-  BnBuf b1 = alloc_bn(ar, 64);
-  SAG_TRY(zero_bn(b1, 64));
+  BnBuf b1 = take_bn(stat_pool, 64);
   if (!f.tc()) {
     SAG_TRY(f.conv(Act(x, 3), B, H, Wd, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, b1.sum, b1.sqs, &oh, &ow));
   } else {
@@ -388,12 +389,13 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     }
   }
   f.tap(scope + "/conv1_raw", c1, {B, oh, ow, 64});
-  SAG_TRY(bn_finalize(p + "conv1/conv", b1, 64, (int64_t)B * oh * ow));
+  BnStats st1;
+  SAG_TRY(bn_stats(p + "conv1/conv", b1, (int64_t)B * oh * ow, &st1));
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
   Act cur = f.alloc_act((int64_t)B * ph * pw, 64);
   if (!ar.dry) {
     ProfScope ps(PROF_POINTWISE, 0, B * 64.0 * (4.0 * oh * ow + act_b * ph * pw), st);
-    SAG_TRY(launch_bn_relu_maxpool(c1.f32(), b1.scale, b1.shift, B, oh, ow, 64, cur.v, st));
+    SAG_TRY(launch_bn_relu_maxpool_stats(c1.f32(), st1, B, oh, ow, 64, cur.v, st));
   }
   f.tap(scope + "/pool1", cur, {B, ph, pw, 64});
   int ch = ph, cw = pw, cc = 64;
@@ -413,20 +415,19 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     Act a1 = f.alloc_act(npix, b.cout);
     Act r2 = f.alloc_f32(npix, b.cout);
     Act out = f.alloc_act(npix, b.cout);
-    BnBuf s1 = alloc_bn(ar, b.cout), s2 = alloc_bn(ar, b.cout);
-    SAG_TRY(zero_bn(s1, b.cout));
-    SAG_TRY(zero_bn(s2, b.cout));
+    BnBuf s1 = take_bn(stat_pool, b.cout), s2 = take_bn(stat_pool, b.cout);
+    BnStats t1, t2;
     SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, s1.sum, s1.sqs, &oh, &ow));
-    SAG_TRY(bn_finalize(q + "/conv_1", s1, b.cout, npix));
+    SAG_TRY(bn_stats(q + "/conv_1", s1, npix, &t1));
     if (!ar.dry) {
       ProfScope ps(PROF_POINTWISE, 0, (4.0 + act_b) * npix * b.cout, st);
-      SAG_TRY(launch_bn_apply(r1.f32(), s1.scale, s1.shift, ActView(), 1, a1.v, npix, b.cout, st));
+      SAG_TRY(launch_bn_apply_stats(r1.f32(), t1, ActView(), 1, a1.v, npix, b.cout, st));
     }
     SAG_TRY(f.conv(a1, B, nh, nw, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, s2.sum, s2.sqs, &oh, &ow));
-    SAG_TRY(bn_finalize(q + "/conv_2", s2, b.cout, npix));
+    SAG_TRY(bn_stats(q + "/conv_2", s2, npix, &t2));
     if (!ar.dry) {
       ProfScope ps(PROF_POINTWISE, 0, (4.0 + 2.0 * act_b) * npix * b.cout, st);
-      SAG_TRY(launch_bn_apply(r2.f32(), s2.scale, s2.shift, shortcut, 1, out.v, npix, b.cout, st));
+      SAG_TRY(launch_bn_apply_stats(r2.f32(), t2, shortcut, 1, out.v, npix, b.cout, st));
     }
     f.tap(scope + "/" + b.name, out, {B, nh, nw, b.cout});
     cur = out; ch = nh; cw = nw; cc = b.cout;

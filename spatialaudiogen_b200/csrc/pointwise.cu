@@ -103,6 +103,57 @@ int launch_bn_apply(const float* x, const float* scale, const float* shift, cons
   return SAG_OK;
 }
 
+// ---- variants that derive scale / shift from the raw batch statistics in the block prologue (c <= 1024) ----
+__device__ __forceinline__ void bn_scale_shift_to_smem(const BnStats& bn, int c, float* s_scale, float* s_shift) {
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const double mean = bn.sum[i] * bn.inv_count;
+    double var = bn.sqs[i] * bn.inv_count - mean * mean;
+    if (var < 0) var = 0;
+    const double sc = (double)__ldg(bn.gamma + i) / sqrt(var + (double)bn.eps);
+    s_scale[i] = (float)sc;
+    s_shift[i] = (float)((double)__ldg(bn.beta + i) - mean * sc);
+  }
+  __syncthreads();
+}
+
+__global__ void bn_apply_stats_kernel(const float4* __restrict__ x, const BnStats bn, const ActView res, int relu, const ActView y,
+                                      int64_t n4, int c) {
+  extern __shared__ float s_ss[];
+  float* s_scale = s_ss;
+  float* s_shift = s_ss + c;
+  bn_scale_shift_to_smem(bn, c, s_scale, s_shift);
+  const int c4 = c / 4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int cc = (int)(i % c4) * 4;
+    float4 v = __ldg(x + i);
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (res.p != nullptr) {
+      float4 r = load_act4(res.p, res.fmt, res.plane, i * 4);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    store_act4(y.p, y.fmt, y.plane, i * 4, v);
+  }
+}
+
+int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& residual, int relu, const ActView& y, int64_t rows,
+                          int c, cudaStream_t st) {
+  SAG_REQUIRE(c % 4 == 0 && c <= 4096, SAG_EINVAL, "bn_apply: channels %d not a multiple of 4 (or too many)", c);
+  int64_t n4 = rows * c / 4;
+  if (n4 == 0) return SAG_OK;
+  int64_t blocks = cdiv64(n4, 256 * 2);                 // >= 2 vectors per thread amortise the prologue
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 2 * c * sizeof(float), st>>>(reinterpret_cast<const float4*>(x), bn, residual, relu,
+                                                                             y, n4, c);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
 // ---- fused BN + ReLU + max-pool 3x3/2 SAME (pad before 0: TF puts the odd pad cell after) ----
 __global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                        const float* __restrict__ shift, int n, int h, int w, int c, int oh, int ow,
@@ -140,6 +191,56 @@ __global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float*
     }
     store_act4(y.p, y.fmt, y.plane, i * 4, m);
   }
+}
+
+__global__ void bn_relu_maxpool_stats_kernel(const float* __restrict__ x, const BnStats bn, int n, int h, int w, int c, int oh,
+                                             int ow, int pt, int pl, const ActView y) {
+  extern __shared__ float s_ss[];
+  float* s_scale = s_ss;
+  float* s_shift = s_ss + c;
+  bn_scale_shift_to_smem(bn, c, s_scale, s_shift);
+  int c4 = c / 4;
+  int64_t total = (int64_t)n * oh * ow * c4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int cc = (int)(i % c4) * 4;
+    int64_t r = i / c4;
+    int ox = (int)(r % ow); r /= ow;
+    int oy = (int)(r % oh);
+    int b = (int)(r / oh);
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc);
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      int iy = oy * 2 + dy - pt;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int ix = ox * 2 + dx - pl;
+        if (ix < 0 || ix >= w) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * h + iy) * w + ix) * c + cc));
+        v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+        v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    store_act4(y.p, y.fmt, y.plane, i * 4, m);
+  }
+}
+
+int launch_bn_relu_maxpool_stats(const float* x, const BnStats& bn, int n, int h, int w, int c, const ActView& y, cudaStream_t st) {
+  SAG_REQUIRE(c % 4 == 0 && c <= 4096, SAG_EINVAL, "maxpool: channels %d not a multiple of 4 (or too many)", c);
+  int oh, ow;
+  int pt = same_pad_before(h, 3, 2, &oh), pl = same_pad_before(w, 3, 2, &ow);
+  int64_t total = (int64_t)n * oh * ow * (c / 4);
+  int64_t blocks = cdiv64(total, 256 * 2);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  bn_relu_maxpool_stats_kernel<<<(unsigned)blocks, 256, 2 * c * sizeof(float), st>>>(x, bn, n, h, w, c, oh, ow, pt, pl, y);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
 }
 
 int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
