@@ -343,12 +343,13 @@ int sag_batchnorm_train(const float* x, int64_t rows, int c, const float* gamma,
   cudaStream_t st = as_stream(stream);
   double* sum = reinterpret_cast<double*>(scratch);
   double* sqs = sum + c;
-  float* scale = reinterpret_cast<float*>(sqs + c);
-  float* shift = scale + c;
   SAG_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * c, st));
   SAG_TRY(launch_channel_stats(x, rows, c, sum, sqs, st));
-  SAG_TRY(launch_bn_finalize(sum, sqs, gamma, beta, (double)rows, c, 1e-3f, scale, shift, st));
-  return launch_bn_apply(x, scale, shift, residual, relu, y, rows, c, st);
+  BnStats bn;
+  bn.sum = sum; bn.sqs = sqs; bn.gamma = gamma; bn.beta = beta;
+  bn.inv_count = 1.0 / (double)rows;
+  bn.eps = 1e-3f;
+  return launch_bn_apply_stats(x, bn, ActView(residual), relu, ActView(y), rows, c, st);
 }
 
 int sag_maxpool_3x3s2_same(const float* x, int n, int h, int w, int c, float* y, void* stream) {

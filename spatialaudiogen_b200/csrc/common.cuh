@@ -175,10 +175,6 @@ struct BnStats {
 int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& residual, int relu, const ActView& y, int64_t rows,
                           int c, cudaStream_t st);
 int launch_bn_relu_maxpool_stats(const float* x, const BnStats& bn, int n, int h, int w, int c, const ActView& y, cudaStream_t st);
-int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
-                       int c, float eps, float* scale, float* shift, cudaStream_t st);
-int launch_bn_apply(const float* x, const float* scale, const float* shift, const ActView& residual, int relu,
-                    const ActView& y, int64_t rows, int c, cudaStream_t st);
 int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
                            const ActView& y, cudaStream_t st);   // 3x3/2 SAME; scale==null -> plain max-pool
 int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st);
@@ -186,7 +182,6 @@ int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int
                      cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
                cudaStream_t st);
-int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st);
 // (n,h,w,3) -> (n,hp,wp,4): image at offset (pt,pl), zeros elsewhere (explicit TF-SAME border + 4th channel)
 int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, const ActView& out,
                               cudaStream_t st);

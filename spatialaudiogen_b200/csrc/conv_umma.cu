@@ -10,17 +10,20 @@
 // loads of several K chunks in flight.  fp32 sources (stage entry points, first use of user inputs) take the register
 // path that splits on the fly.
 //
-// CTA = one 128 x BN output tile, 9 warps:
-//   warps 0-7  producers: gather the A operand into shared memory in the UMMA K-major SWIZZLE_128B canonical layout;
-//              thread 0 also issues the bulk-async (TMA, cp.async.bulk) copy of the pre-packed weight tile; afterwards
-//              the same warps run the epilogue: tcgen05.ld of the accumulator, bias / ReLU, batch-norm statistics,
-//              strided or mapped store as fp32 or as split bf16 planes.
-//   warp 8     allocates TMEM and (one elected lane) issues tcgen05.mma kind::f16 with the accumulator in TMEM:
-//              SAG_PREC_BF16   : 1 MMA per K step  (A_hi x B_hi)
-//              SAG_PREC_BF16X3 : 3 MMAs per K step (A_hi x B_hi + A_lo x B_hi + A_hi x B_lo) -> fp32-grade products
+// Persistent, warp-specialised: one CTA per SM walks the list of (M tile, N tile, K split) work items; tile = 128 x BN.
+//   warps 0-7   producers: gather the A operand into shared memory in the UMMA K-major SWIZZLE_128B canonical layout
+//               (cp.async with asynchronous mbarrier arrival); thread 0 also issues the bulk-async (TMA, cp.async.bulk)
+//               copy of the pre-packed weight tile.
+//   warps 8-11  epilogue (one per TMEM lane quadrant): tcgen05.ld of the accumulator, bias / ReLU, staging tile,
+//               coalesced row writes as fp32 / split bf16 / split-K partials, batch-norm column sums.
+//   warp 12     allocates TMEM (two accumulators) and issues tcgen05.mma kind::f16 through one elected lane:
+//               SAG_PREC_BF16   : 1 MMA per K step  (A_hi x B_hi)
+//               SAG_PREC_BF16X3 : 3 MMAs per K step (A_hi x B_hi + A_lo x B_hi + A_hi x B_lo) -> fp32-grade products
 // full/empty mbarrier ring between producers and the MMA issuer, tcgen05.commit releases stages and publishes the
-// accumulator.  Roofline: tensor pipe (BN=128, x3: 768 clk of MMA per 64-wide K chunk against ~650 clk to gather the
-// 32 KB A chunk from L2); the A gather re-reads each activation once per tap from L2, never from HBM.
+// accumulator; tmem_full/tmem_empty barriers between the MMA issuer and the epilogue, so the epilogue of tile i overlaps
+// the MMAs of tile i+1.  Roofline: tensor pipe; measured limits today are the shared-memory operand reads of the
+// three-MMA scheme on narrow tiles and the L2->SM gather (each activation is re-read once per tap from L2, never
+// from HBM) -- see DESIGN.md section 3.
 #include "model.cuh"
 #include <cuda_bf16.h>
 
@@ -219,9 +222,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 4 fp32 -> 4 bf16 hi (8 bytes) and 4 bf16 lo
 __device__ __forceinline__ void split4(const float* f, uint2& hi, uint2& lo) {
@@ -971,10 +971,12 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
   a.stages = S;
   const size_t smem = (size_t)fixed + (size_t)S * STAGE_BYTES;
   auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};               // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   const int64_t MT = cdiv64(M, UM_BM);

@@ -48,62 +48,8 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// ---- BN finalize: scale = gamma*rsqrt(var+eps), shift = beta - mean*scale (biased variance) ----
-__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqs,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, double inv_count,
-                                   int c, float eps, float* __restrict__ scale, float* __restrict__ shift) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  double mean = sum[i] * inv_count;
-  double var = sqs[i] * inv_count - mean * mean;
-  if (var < 0) var = 0;
-  double sc = (double)gamma[i] / sqrt(var + (double)eps);
-  scale[i] = (float)sc;
-  shift[i] = (float)((double)beta[i] - mean * sc);
-}
-
-int launch_bn_finalize(const double* sum, const double* sqs, const float* gamma, const float* beta, double count,
-                       int c, float eps, float* scale, float* shift, cudaStream_t st) {
-  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, st>>>(sum, sqs, gamma, beta, 1.0 / count, c, eps, scale, shift);
-  SAG_LAUNCH_CHECK();
-  return SAG_OK;
-}
-
-// ---- BN apply (+residual)(+relu): y = act(x*scale[c] + shift[c] + res) ; c % 4 == 0 ----
-__global__ void bn_apply_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const ActView res, int relu, const ActView y, int64_t n4,
-                                int c4) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    int cc = (int)(i % c4) * 4;
-    float4 v = __ldg(x + i);
-    float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc));
-    float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc));
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (res.p != nullptr) {
-      float4 r = load_act4(res.p, res.fmt, res.plane, i * 4);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-    }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    store_act4(y.p, y.fmt, y.plane, i * 4, v);
-  }
-}
-
-int launch_bn_apply(const float* x, const float* scale, const float* shift, const ActView& residual, int relu,
-                    const ActView& y, int64_t rows, int c, cudaStream_t st) {
-  SAG_REQUIRE(c % 4 == 0, SAG_EINVAL, "bn_apply: channels %d not a multiple of 4", c);
-  int64_t n4 = rows * c / 4;
-  if (n4 == 0) return SAG_OK;
-  int64_t blocks = cdiv64(n4, 256);
-  int64_t cap = (int64_t)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), scale, shift, residual, relu, y, n4,
-                                                    c / 4);
-  SAG_LAUNCH_CHECK();
-  return SAG_OK;
-}
-
-// ---- variants that derive scale / shift from the raw batch statistics in the block prologue (c <= 1024) ----
+// ---- batch-norm consumers: scale / shift are derived from the raw batch statistics in the block prologue ----
+//      scale = gamma*rsqrt(var+eps), shift = beta - mean*scale (biased variance); y = act(x*scale + shift [+ res])
 __device__ __forceinline__ void bn_scale_shift_to_smem(const BnStats& bn, int c, float* s_scale, float* s_shift) {
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
     const double mean = bn.sum[i] * bn.inv_count;
@@ -390,21 +336,6 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
   int threads = 64;
   dim3 grid(cdiv(t, threads), batch);
   mix_kernel<<<grid, threads, 3 * (tracks + 1) * sizeof(float), st>>>(x_sep, loc, tracks, t, segments, out);
-  SAG_LAUNCH_CHECK();
-  return SAG_OK;
-}
-
-__global__ void sigmoid_kernel(float* x, int64_t n) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = 1.f / (1.f + expf(-x[i]));
-}
-
-int launch_sigmoid_inplace(float* x, int64_t n, cudaStream_t st) {
-  int64_t blocks = cdiv64(n, 256);
-  int64_t cap = (int64_t)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) return SAG_OK;
-  sigmoid_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
