@@ -244,6 +244,16 @@ int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, doub
   SAG_REQUIRE(category >= 0 && category < PROF_NCAT, SAG_EINVAL, "sag_get_profile: category %d outside [0,%d)", category, (int)PROF_NCAT);
   double t = 0, f = 0, b = 0;
   int n = 0;
+  static const bool dump = getenv("SAG_PROF_DUMP") != nullptr;   // debug: one line per launch scope of the last forward
+  if (dump && category == 0) {
+    int i = 0;
+    for (auto& r : h->prof.recs) {
+      float dt = 0.f;
+      cudaEventSynchronize(r.e1);
+      cudaEventElapsedTime(&dt, r.e0, r.e1);
+      fprintf(stderr, "[prof] %3d cat %d %8.2f us %8.3f GFLOP %8.2f MB\n", i++, r.cat, dt * 1e3, r.flops * 1e-9, r.bytes * 1e-6);
+    }
+  }
   for (auto& r : h->prof.recs) {
     if (r.cat != category) continue;
     SAG_CHECK_CUDA(cudaEventSynchronize(r.e1));
@@ -295,12 +305,14 @@ int sag_deconv2d(const float* x, int n, int h, int w, int cin, const float* w_hw
   cudaStream_t st = as_stream(stream);
   if (precision != SAG_PREC_FP32) {               // tcgen05: one sub-pixel GEMM
     const int OH = (h - 1) * sh + kh, OW = (w - 1) * sw + kw;
-    UmmaWeights uw;
-    SAG_TRY(umma_pack_deconv(w_hwoi, bias, kh, kw, cout, cin, sh, sw, 0, (int64_t)OW * cout, cout, 1, precision, &uw, st));
     GatherGeom g;
     int oh_lim, ow_lim;
-    int r = make_deconv_subpixel_geom(&g, n, h, w, cin, cin, kh, kw, sh, sw, 0, OH, (int64_t)OH * OW * cout, (int64_t)OW * cout,
-                                      cout, 1, &oh_lim, &ow_lim);
+    SAG_TRY(make_deconv_subpixel_geom(&g, n, h, w, cin, cin, kh, kw, sh, sw, 0, OH, (int64_t)OH * OW * cout, (int64_t)OW * cout,
+                                      cout, 1, &oh_lim, &ow_lim));
+    UmmaWeights uw;
+    SAG_TRY(umma_pack_deconv(w_hwoi, bias, kh, kw, cout, cin, sh, sw, 0, (int64_t)OW * cout, cout, 1, precision,
+                             (int64_t)g.N * g.PH * g.PW, &uw, st));
+    int r = SAG_OK;
     g.Cout = uw.N;
     Epilogue ep{bias, relu, nullptr, nullptr};
     if (r == SAG_OK) r = launch_gather_gemm_umma(x, uw, y, g, ep, oh_lim, ow_lim, nullptr, st);

@@ -119,16 +119,20 @@ struct UmmaWeights {
   short* col_dx = nullptr;
   float* col_bias = nullptr;
   int vec4 = 0;
+  int64_t M_hint = 0;   // row count the tile width was chosen for
 };
 void umma_free(UmmaWeights* w);
-// wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form)
-int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, UmmaWeights* out, cudaStream_t st);
+// tile width of a contraction with N columns over M rows (a single M tile takes narrow tiles: see conv_umma.cu)
+int umma_tile_width(int N, int64_t M);
+// wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form); M: rows of the GEMM
+// the image will be used for (selects the tile width)
+int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
 // conv weights HWIO zero-extended to kw2 taps per row and cin2 channels (convolution over a zero-padded NHWC4 image)
 int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
-                            UmmaWeights* out, cudaStream_t st);
+                            int64_t M, UmmaWeights* out, cudaStream_t st);
 // w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
-                     int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, UmmaWeights* out, cudaStream_t st);
+                     int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
 // Activation view handed to the tensor-core kernels.  ACT_F32: p = float*.  ACT_BF2: the value x is stored as two bf16
 // planes, hi = bf16(x) at p and lo = bf16(x - hi) at p + plane bytes (plane == 0: hi only, SAG_PREC_BF16); strides of
 // the geometry are in elements either way.

@@ -291,11 +291,15 @@ template <int BN, int NSPLIT, int SRC>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
-  constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
+  constexpr bool CONCAT = NSPLIT == 2;        // A_hi x [B_hi | B_lo] as one MMA of width 2*BN, then A_lo x B_hi
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulators
+  constexpr int ACC_COLS = CONCAT ? 2 * BN : BN;                 // TMEM columns of one accumulator
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;      // two accumulators
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
 
   extern __shared__ __align__(16) uint8_t um_smem[];
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
@@ -507,7 +511,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);      // the epilogue has drained this accumulator
         if (a.trace) tr_wacc += clock64() - tr_a0;
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(b * ACC_COLS);
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           const long long tr_w0 = a.trace ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
@@ -523,10 +527,17 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
           if (elect_one()) {
 #pragma unroll
             for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
-              umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
-              if (NSPLIT == 3) {
+              if (CONCAT) {
+                // the lo plane of B follows its hi plane in the stage: one 2*BN-wide MMA yields [A_hi.B_hi | A_hi.B_lo]
+                // in adjacent accumulator blocks (summed by the epilogue); A_lo.B_hi lands on the first block
+                umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC2, (kc > kc_begin || k4 > 0) ? 1u : 0u);
                 umma_bf16(tmem_acc, da_lo + 2 * k4, db_hi + 2 * k4, IDESC, 1u);
-                umma_bf16(tmem_acc, da_hi + 2 * k4, db_lo + 2 * k4, IDESC, 1u);
+              } else {
+                umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+                if (NSPLIT == 3) {
+                  umma_bf16(tmem_acc, da_lo + 2 * k4, db_hi + 2 * k4, IDESC, 1u);
+                  umma_bf16(tmem_acc, da_hi + 2 * k4, db_lo + 2 * k4, IDESC, 1u);
+                }
               }
             }
             umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
@@ -547,8 +558,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     const int q = warp & 3;                        // warps 8..11 -> quadrants 0..3
     const int et = tid - UM_EPI_WARP0 * 32;        // 0..127 = row of the tile this thread owns in TMEM
     constexpr uint32_t PITCH = 32 * 4 + 16;        // 32 fp32 columns per pass; +16 B keeps 16-byte row stores conflict-free
-    const bool raw = a.partial != nullptr;
+    const bool split = a.partial != nullptr;       // K split: raw accumulators go to the partial region first
     float* yf = reinterpret_cast<float*>(a.y);
+    const int lr = lane >> 3, lc = (lane & 7) * 4; // copy-out role: a warp instruction covers 4 rows x 128 contiguous bytes
     int64_t it_local = 0;
     long long tr_wait = 0, tr_t0 = clock64();
     long long tr_p[5] = {0, 0, 0, 0, 0};
@@ -559,14 +571,13 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
       const int n_base = nt * BN;
       const int b = (int)(it_local & 1);
       const uint32_t use = (uint32_t)(it_local >> 1);
-      {                                            // where this thread's row goes
+      const int rows_valid = (int)((M - m0) < UM_BM ? ((M - m0) > 0 ? (M - m0) : 0) : UM_BM);   // valid rows come first
+      {                                            // where this thread's row goes in the output tensor
         const int64_t m = m0 + et;
         long long yo = UM_ROW_INVALID;
         int oy = 0, ox = 0;
         if (m < M) {
-          if (raw) {
-            yo = ((int64_t)z * M + m) * a.n_pad;
-          } else if (a.dense) {
+          if (a.dense) {
             yo = m * g.y_sw;
           } else {
             const uint32_t mu = (uint32_t)m;
@@ -579,44 +590,13 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         }
         s_yoff[et] = yo; s_oy[et] = oy; s_ox[et] = ox;
       }
-      const long long tr_w0 = a.trace ? clock64() : 0;
-      mbar_wait(bar_tfull + 8 * b, use & 1);
-      if (a.trace) tr_wait += clock64() - tr_w0;
-      tc_fence_after();
-      const uint32_t tmem_row = tmem_base + (uint32_t)(b * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        long long tp0 = a.trace ? clock64() : 0;
-        tmem_ld16(tmem_row + (uint32_t)c0, v);
-        tmem_ld16(tmem_row + (uint32_t)c0 + 16u, v + 16);
-        if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-        }
-        if (!raw && (a.bias != nullptr || a.relu)) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = n_base + c0 + e;
-            const float bb = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
-            float w = v[e] + bb;
-            if (a.relu) w = fmaxf(w, 0.f);
-            v[e] = w;
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          st_shared_v4(stile + (uint32_t)et * PITCH + (uint32_t)e * 4u,
-                       make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
-        long long tp1 = a.trace ? clock64() : 0;
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+
+      // copy-out of the staged 128 x 32 pass (+ batch-norm column sums): raw -> this split's partial accumulators,
+      // else the layer output in its final format.  Ends with a barrier: staging tile and row table are reusable.
+      auto emit_pass = [&](const int c0, const bool raw) {
         long long tp2 = a.trace ? clock64() : 0;
-        // copy-out: a warp instruction covers 4 rows x 128 contiguous bytes; 4 warps x 8 rounds = 128 rows
-        const int lr = lane >> 3, lc = (lane & 7) * 4;
         const int n = n_base + c0 + lc;
         const int ncols = raw ? a.n_pad : a.Ntot;
-        const int rows_valid = (int)((M - m0) < UM_BM ? ((M - m0) > 0 ? (M - m0) : 0) : UM_BM);   // valid rows come first
         if (n < ncols) {
           if (raw || (a.dense && a.vec_store)) {
             // fast path: row rr of the tile lands at a fixed stride; all loads first, then all stores
@@ -635,8 +615,35 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
               if (rr >= rows_valid) continue;
               const int64_t eoff = base + (int64_t)rr * rstride;
               if (raw) {
-                *reinterpret_cast<float4*>(a.partial + eoff) = w4[rd];
+                __stcg(reinterpret_cast<float4*>(a.partial + eoff), w4[rd]);
               } else if (a.out_bf2) {
+                const float t4[4] = {w4[rd].x, w4[rd].y, w4[rd].z, w4[rd].w};
+                store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
+              } else {
+                *reinterpret_cast<float4*>(yf + eoff) = w4[rd];
+              }
+            }
+          } else if (a.col_off != nullptr && a.vec_store) {
+            // mapped output (sub-pixel transposed conv), groups of 4 columns contiguous: row table and values of all
+            // 8 rows are loaded before the first store
+            const int c_off = __ldg(a.col_off + n), c_dy = __ldg(a.col_dy + n), c_dx = __ldg(a.col_dx + n);
+            float4 w4[8];
+            long long yo[8];
+            bool ok[8];
+#pragma unroll
+            for (int rd = 0; rd < 8; ++rd) {
+              const int rr = rd * 16 + q * 4 + lr;
+              yo[rd] = s_yoff[rr];
+              ok[rd] = yo[rd] != UM_ROW_INVALID && (unsigned)(s_oy[rr] + c_dy) < (unsigned)a.oh_lim &&
+                       (unsigned)(s_ox[rr] + c_dx) < (unsigned)a.ow_lim;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4[rd].x), "=f"(w4[rd].y), "=f"(w4[rd].z), "=f"(w4[rd].w)
+                           : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
+            }
+#pragma unroll
+            for (int rd = 0; rd < 8; ++rd) {
+              if (!ok[rd]) continue;
+              const int64_t eoff = yo[rd] + c_off;
+              if (a.out_bf2) {
                 const float t4[4] = {w4[rd].x, w4[rd].y, w4[rd].z, w4[rd].w};
                 store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
               } else {
@@ -670,28 +677,21 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
                 }
               } else {
                 const int oy = s_oy[rr], ox = s_ox[rr];
-                if (a.vec_store) {
-                  if ((unsigned)(oy + c_dy[0]) < (unsigned)a.oh_lim && (unsigned)(ox + c_dx[0]) < (unsigned)a.ow_lim) {
-                    const int64_t eoff = yo + c_off[0];
-                    if (a.out_bf2) store_bf2_4(a.y, a.y_plane, eoff, t4, a.out_bf2);
-                    else *reinterpret_cast<float4*>(yf + eoff) = w4;
-                  }
-                } else {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (n + e >= a.Ntot) continue;
-                    if (!((unsigned)(oy + c_dy[e]) < (unsigned)a.oh_lim && (unsigned)(ox + c_dx[e]) < (unsigned)a.ow_lim)) continue;
-                    const int64_t eoff = yo + c_off[e];
-                    if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
-                    else yf[eoff] = t4[e];
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e >= a.Ntot) continue;
+                  if (!((unsigned)(oy + c_dy[e]) < (unsigned)a.oh_lim && (unsigned)(ox + c_dx[e]) < (unsigned)a.ow_lim)) continue;
+                  const int64_t eoff = yo + c_off[e];
+                  if (a.out_bf2) store_bf2_1(a.y, a.y_plane, eoff, t4[e], a.out_bf2);
+                  else yf[eoff] = t4[e];
                 }
               }
             }
           }
         }
         long long tp3 = a.trace ? clock64() : 0;
-        if (stats) {                               // column sums of the staged pass: 4 threads per column, 32 rows each
+        const bool st_pass = stats && !raw;
+        if (st_pass) {                             // column sums of the staged pass: 4 threads per column, 32 rows each
           const int c = et & 31, part = et >> 5;
           float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -710,16 +710,60 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
         }
         long long tp4 = a.trace ? clock64() : 0;
         asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");   // staging tile and row table reusable
-        if (stats && et < 32 && n_base + c0 + et < a.Ntot) {
+        if (st_pass && et < 32 && n_base + c0 + et < a.Ntot) {
           // (the next pass rewrites s_part only after its own first barrier, which this warp has not reached yet)
           s_sum[n_base + c0 + et] += (s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et]);
           s_sqs[n_base + c0 + et] += (s_part[0][32 + et] + s_part[1][32 + et]) + (s_part[2][32 + et] + s_part[3][32 + et]);
         }
         if (a.trace) {
           const long long tp5 = clock64();
-          tr_p[0] += tp1 - tp0; tr_p[1] += tp3 - tp2; tr_p[2] += tp4 - tp3; tr_p[3] += (tp2 - tp1) + (tp5 - tp4); tr_p[4] += 1;
+          tr_p[1] += tp3 - tp2; tr_p[2] += tp4 - tp3; tr_p[3] += tp5 - tp4; tr_p[4] += 1;
         }
+      };
+
+      const long long tr_w0 = a.trace ? clock64() : 0;
+      mbar_wait(bar_tfull + 8 * b, use & 1);
+      if (a.trace) tr_wait += clock64() - tr_w0;
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + (uint32_t)(b * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        long long tp0 = a.trace ? clock64() : 0;
+        tmem_ld16(tmem_row + (uint32_t)c0, v);
+        tmem_ld16(tmem_row + (uint32_t)c0 + 16u, v + 16);
+        if (CONCAT) {                              // second accumulator block: A_hi x B_lo
+          float u[32];
+          tmem_ld16(tmem_row + (uint32_t)(BN + c0), u);
+          tmem_ld16(tmem_row + (uint32_t)(BN + c0) + 16u, u + 16);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] += u[e];
+        }
+        if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        if (!split && (a.bias != nullptr || a.relu)) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int n = n_base + c0 + e;
+            const float bb = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
+            float w = v[e] + bb;
+            if (a.relu) w = fmaxf(w, 0.f);
+            v[e] = w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          st_shared_v4(stile + (uint32_t)et * PITCH + (uint32_t)e * 4u,
+                       make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+        long long tp1 = a.trace ? clock64() : 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+        if (a.trace) tr_p[0] += tp1 - tp0;
+        emit_pass(c0, split);
       }
+
     }
     if (a.trace && et == 0) {
       for (int i = 0; i < 5; ++i) a.trace[blockIdx.x * 16 + 8 + i] = tr_p[i];
@@ -958,14 +1002,14 @@ int num_sms() {
 
 template <int BN, int NSPLIT, int SRC>
 int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStream_t st) {
-  constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
   UmmaArgs a = a_in;
   a.NT = nt;
   a.Z = Z;
   // one persistent CTA per SM: barriers + staging tile + alignment slack + as many operand stages as fit (<= 6)
   const int fixed = UM_BAR_BYTES + 16 + UM_STAGING_BYTES + 1024;
-  int S = (215 * 1024 - fixed) / STAGE_BYTES;    // + ~10 KB of static shared memory stays under the 227 KB limit
+  int S = (215 * 1024 - fixed) / STAGE_BYTES;    // + ~11 KB of static shared memory: 215 KB dynamic stays under the 227 KB limit
   if (S > 6) S = 6;    // the cp.async drain handles at most 5 groups in flight
   if (S < 2) S = 2;
   a.stages = S;
@@ -975,7 +1019,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024));
     attr_set[dev & 63] = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
@@ -1049,7 +1093,15 @@ int launch_ns(const GatherGeom& g, const UmmaArgs& a, int nt, int src, int Z, cu
 
 template <int BN>
 int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, int src, int Z, cudaStream_t st) {
-  if (planes == 2) return launch_ns<BN, 3>(g, a, nt, src, Z, st);
+  // bf16x3 on tiles up to 128 wide: two MMAs per K step (A_hi x [B_hi | B_lo], A_lo x B_hi) instead of three -- 22 % / 17 %
+  // fewer shared-memory operand bytes on 64- / 128-wide tiles; 256-wide tiles have no TMEM for a second accumulator block
+  static const int concat = env_int("SAG_UMMA_CONCAT", 1);
+  if (planes == 2) {
+    if constexpr (BN <= 128) {
+      if (concat) return launch_ns<BN, 2>(g, a, nt, src, Z, st);
+    }
+    return launch_ns<BN, 3>(g, a, nt, src, Z, st);
+  }
   return launch_ns<BN, 1>(g, a, nt, src, Z, st);
 }
 
@@ -1057,8 +1109,40 @@ int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, int sr
 
 // ---- host API -----------------------------------------------------------------------------------------------------
 // 256-wide tiles halve the A re-reads of wide layers (the gather is L2-bandwidth bound); they use all 512 TMEM columns
-static int tile_width(int N) {
+// A single M tile (fully connected layers on a batch of windows) is weight-streaming bound: narrow tiles spread the
+// weight matrix over many CTAs (together with a deep K split) instead of feeding it through a handful of SMs.
+// Tuning knob (development): SAG_UMMA_FORCE="MT:N:BN:Z,..." pins tile width / K split of the layers with MT m tiles
+// and N columns (BN or Z = 0 keeps the planner's choice).
+struct ForcedCfg { int64_t mt; int n, bn, z; };
+static const std::vector<ForcedCfg>& forced_cfgs() {
+  static std::vector<ForcedCfg> v;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("SAG_UMMA_FORCE");
+    while (e != nullptr && *e) {
+      long long mt = 0;
+      int n = 0, bn = 0, z = 0;
+      if (sscanf(e, "%lld:%d:%d:%d", &mt, &n, &bn, &z) == 4) v.push_back({(int64_t)mt, n, bn, z});
+      e = strchr(e, ',');
+      if (e) ++e;
+    }
+  }
+  return v;
+}
+static const ForcedCfg* forced_for(int N, int64_t M) {
+  for (const ForcedCfg& f : forced_cfgs())
+    if (f.n == N && f.mt == cdiv64(M, UM_BM)) return &f;
+  return nullptr;
+}
+
+static int tile_width(int N, int64_t M) {
+  if (const ForcedCfg* f = forced_for(N, M)) {
+    if (f->bn == 32 || f->bn == 64 || f->bn == 128 || f->bn == 256) return f->bn;
+  }
   static const int wide = env_int("SAG_UMMA_BN256", 1);
+  static const int narrow_fc = env_int("SAG_UMMA_NARROW_FC", 1);
+  if (narrow_fc && M <= UM_BM) return N <= 32 ? 32 : 64;
   return N <= 32 ? 32 : (N <= 64 ? 64 : ((N >= 256 && wide) ? 256 : 128));
 }
 
@@ -1071,14 +1155,15 @@ void umma_free(UmmaWeights* w) {
   *w = UmmaWeights();
 }
 
-int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, UmmaWeights* out, cudaStream_t st) {
+int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, int64_t M, UmmaWeights* out, cudaStream_t st) {
   SAG_REQUIRE(precision == SAG_PREC_BF16 || precision == SAG_PREC_BF16X3, SAG_EUNSUPPORTED,
               "tcgen05 path: precision %d is not built (use bf16 or bf16x3)", precision);
   SAG_REQUIRE(K >= 0 && N > 0, SAG_EINVAL, "umma_pack_weights: bad shape %dx%d", K, N);
   UmmaWeights w;
   w.K = K; w.N = N;
   w.KC = cdiv(K, UM_BK);
-  w.BN = tile_width(N);
+  w.BN = tile_width(N, M);
+  w.M_hint = M;
   w.NT = cdiv(N, w.BN);
   w.planes = precision == SAG_PREC_BF16X3 ? 2 : 1;
   const size_t bytes = (size_t)w.NT * w.KC * w.planes * w.BN * 128;
@@ -1097,14 +1182,14 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
 }
 
 int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
-                            UmmaWeights* out, cudaStream_t st) {
+                            int64_t M, UmmaWeights* out, cudaStream_t st) {
   float* wk = nullptr;
   const int64_t total = (int64_t)kh * kw2 * cin2 * cout;
   SAG_CHECK_CUDA(cudaMalloc(&wk, sizeof(float) * (size_t)total));
   int64_t blocks = cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   expand_hwio_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, kw2, cin2, wk);
-  int r = umma_pack_weights(wk, kh * kw2 * cin2, cout, cout, precision, out, st);
+  int r = umma_pack_weights(wk, kh * kw2 * cin2, cout, cout, precision, M, out, st);
   cudaStreamSynchronize(st);
   cudaFree(wk);
   return r;
@@ -1113,7 +1198,7 @@ int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int co
 // Sub-pixel formulation of tf.nn.conv2d_transpose VALID (core.py:139-140): every cell (u, v) of the
 // (H+ty-1) x (W+tx-1) grid produces its sh x sw x Cout outputs from ty x tx taps of the input.
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
-                     int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, UmmaWeights* out, cudaStream_t st) {
+                     int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, int64_t M, UmmaWeights* out, cudaStream_t st) {
   const int ty = cdiv(kh, sh), tx = cdiv(kw, sw);
   const int K = ty * tx * cin, N = sh * sw * cout;
   SAG_REQUIRE(ty * tx <= kMaxTaps, SAG_EINVAL, "deconv: too many taps");
@@ -1126,7 +1211,7 @@ int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int
     subpixel_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwoi, kh, kw, cout, cin, sh, sw, ty, tx, order, wk);
   }
   UmmaWeights w;
-  int r = umma_pack_weights(wk, K, N, N, precision, &w, st);
+  int r = umma_pack_weights(wk, K, N, N, precision, M, &w, st);
   cudaStreamSynchronize(st);
   cudaFree(wk);
   SAG_TRY(r);
@@ -1202,19 +1287,29 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
 // Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the
 // partial accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them
 // (deterministic: fixed summation order).
-int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
+int umma_tile_width(int N, int64_t M) { return tile_width(N, M); }
+
+static int plan_split_k(int K, int N, int64_t M, int BN, size_t* scratch_bytes) {
   static const int enabled = env_int("SAG_UMMA_SPLITK", 1);
-  const int BN = tile_width(N), NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
+  const int NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
   const int64_t tiles = cdiv64(M, UM_BM) * NT;
   int Z = 1;
-  if (enabled && tiles > 0 && KC >= 8) {
+  if (const ForcedCfg* f = forced_for(N, M)) {
+    if (f->z >= 1 && f->z <= KC) {
+      if (scratch_bytes) *scratch_bytes = f->z > 1 ? sizeof(float) * (size_t)f->z * (size_t)M * (size_t)(NT * BN) : 0;
+      return f->z;
+    }
+  }
+  // a single M tile streams its weights once: splits down to 2 chunks keep every SM pulling its share
+  const int min_chunks = M <= UM_BM ? 2 : 4;
+  if (enabled && tiles > 0 && KC >= 2 * min_chunks) {
     // Cost model in units of one K chunk: a work item costs its chunks plus ~2 chunks of per-tile work, a launch ~4
     // chunks of pipeline fill; items run in waves of `slots`; splitting adds the partial round trip (~5 % + the
-    // reduce launch).  Pick the split that minimises the wave-quantised time -- it both fills the SMs of small layers
-    // and trims ragged last waves.
+    // reduce launch).  Pick the split that minimises the wave-quantised time -- it both fills
+    // the SMs of small layers and trims ragged last waves.
     const int64_t slots = 148;                // one persistent CTA per SM
     double best = 0.0;
-    for (int z = 1; z <= 32 && z <= KC / 4; ++z) {
+    for (int z = 1; z <= 32 && z <= KC / min_chunks; ++z) {
       const int64_t waves = cdiv64(tiles * z, slots);
       double t = (double)waves * ((double)cdiv(KC, z) + 2.0) + 4.0;
       if (z > 1) t = t * 1.05 + 4.0;
@@ -1224,6 +1319,12 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   if (scratch_bytes) *scratch_bytes = Z > 1 ? sizeof(float) * (size_t)Z * (size_t)M * (size_t)(NT * BN) : 0;
   return Z;
 }
+
+// Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the partial
+// accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them (deterministic: fixed
+// summation order).  (A fix-up by the last CTA to arrive at a tile was measured 25 % slower end to end: 128 threads
+// pulling Z partial tiles through L2 latency cannot compete with a reduce spread over the whole GPU.)
+int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) { return plan_split_k(K, N, M, tile_width(N, M), scratch_bytes); }
 
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st) {
@@ -1263,8 +1364,11 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     SAG_REQUIRE(w.planes == 1 || x.plane != 0, SAG_EINVAL, "tcgen05 path: bf16x3 needs the lo plane of the activation");
     src = SRC_BF2;
   }
-  int Z = scratch != nullptr ? umma_split_k(w.K, w.N, M, nullptr) : 1;
-  if (Z > 1) a.partial = scratch;
+  int Z = scratch != nullptr ? plan_split_k(w.K, w.N, M, w.BN, nullptr) : 1;
+  if (Z > 1) {
+    SAG_REQUIRE(w.BN == tile_width(w.N, M), SAG_ESTATE, "tcgen05 path: weights were packed for a different row count (tile %d)", w.BN);
+    a.partial = scratch;
+  }
   // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
   a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;

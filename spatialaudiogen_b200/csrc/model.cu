@@ -142,7 +142,7 @@ int launch_gather_gemm(int precision, const float* x, const float* w, float* y, 
   for (int t = 0; t < g.T; ++t)
     SAG_REQUIRE(g.widx[t] == t, SAG_EUNSUPPORTED, "tcgen05 path needs weights in tap order");
   UmmaWeights uw;
-  SAG_TRY(umma_pack_weights(w, g.T * g.Cin, g.Cout, g.Cout, precision, &uw, st));
+  SAG_TRY(umma_pack_weights(w, g.T * g.Cin, g.Cout, g.Cout, precision, (int64_t)g.N * g.PH * g.PW, &uw, st));
   size_t sbytes = 0;
   float* scratch = nullptr;
   if (umma_split_k(uw.K, uw.N, (int64_t)g.N * g.PH * g.PW, &sbytes) > 1 && cudaMalloc(&scratch, sbytes) != cudaSuccess) scratch = nullptr;
@@ -239,11 +239,12 @@ struct Fwd {
       SAG_REQUIRE(x.v.fmt == ACT_F32 && y.v.fmt == ACT_F32, SAG_EINVAL, "fp32 contraction on a split-bf16 tensor");
       return launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st);
     }
-    const std::string key = scope + "#" + std::to_string(prec);
+    const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
+    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(cout, Mrows));
     auto it = h->umma.find(key);
     if (it == h->umma.end()) {                    // first use: build the tensor-core operand image of this layer
       UmmaWeights uw;
-      SAG_TRY(umma_pack_weights(w, g.T * g.Cin, cout, cout, prec, &uw, st));
+      SAG_TRY(umma_pack_weights(w, g.T * g.Cin, cout, cout, prec, Mrows, &uw, st));
       it = h->umma.emplace(key, uw).first;
     }
     return launch_gather_gemm_umma(x.v, it->second, y.v, g, ep, 0, 0, scratch, st);
@@ -267,19 +268,20 @@ struct Fwd {
     if (tc()) {
       // one sub-pixel GEMM for the whole layer: N = sh*sw*cout columns, ceil(kh/sh)*ceil(kw/sw) taps
       const int order = y_sc == 1 ? 0 : 1;
-      const std::string key = scope + "#" + std::to_string(prec);
+      GatherGeom g;
+      int oh_lim, ow_lim;
+      SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
+                                        &oh_lim, &ow_lim));
+      const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
+      const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(sh * sw * cout, Mrows));
       auto it = h->umma.find(key);
       if (it == h->umma.end()) {
         const float* w_tf = W(scope + "/weights", &err);
         SAG_TRY(err);
         UmmaWeights uw;
-        SAG_TRY(umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, &uw, st));
+        SAG_TRY(umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, &uw, st));
         it = h->umma.emplace(key, uw).first;
       }
-      GatherGeom g;
-      int oh_lim, ow_lim;
-      SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
-                                        &oh_lim, &ow_lim));
       g.Cout = it->second.N;
       const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
       ProfScope ps(PROF_DECONV, 2.0 * M * K * g.Cout, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st);
@@ -372,11 +374,12 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     if (!ar.dry) {
       const float* w = f.W(p + "conv1/conv/weights", &err);
       SAG_TRY(err);
-      const std::string key = p + "conv1/conv#" + std::to_string(f.prec);
+      const int64_t Mrows = (int64_t)B * oh * ow;
+      const std::string key = p + "conv1/conv#" + std::to_string(f.prec) + "#" + std::to_string(umma_tile_width(64, Mrows));
       auto it = h->umma.find(key);
       if (it == h->umma.end()) {
         UmmaWeights uw;
-        SAG_TRY(umma_pack_conv_expanded(w, 7, 7, 3, 64, 8, 4, f.prec, &uw, st));
+        SAG_TRY(umma_pack_conv_expanded(w, 7, 7, 3, 64, 8, 4, f.prec, Mrows, &uw, st));
         it = h->umma.emplace(key, uw).first;
       }
       {
