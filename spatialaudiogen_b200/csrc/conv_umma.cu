@@ -25,6 +25,7 @@
 // three-MMA scheme on narrow tiles and the L2->SM gather (each activation is re-read once per tap from L2, never
 // from HBM) -- see DESIGN.md section 3.
 #include "model.cuh"
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 namespace sag {
@@ -69,9 +70,12 @@ struct UmmaArgs {
   int n_pad;
   int dense;              // output pixel m sits at element m*y_sw (no row decode)
   int NT, Z;              // N tiles, K splits
+  int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
   int cluster;            // CTAs per cluster (1 or 2): the CTAs of a cluster take adjacent M tiles and share the weight copy
 };
+// im2col tensor maps of the two activation planes (SRC_TMA); kernel parameter, read by the TMA unit
+struct alignas(64) TmaPair { CUtensorMap hi, lo; };
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -112,6 +116,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// im2col tensor copy (NHWC activation, rank 4): 128 output pixels starting at base pixel (w, h, n) -- the hardware walks
+// the bounding box of the tensor map with the convolution stride, wrapping rows and images -- x 64 channels from c, at
+// filter offset (off_w, off_h); lands as 128 rows of 128 bytes in the SWIZZLE_128B pattern; out-of-image pixels read 0.
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst_smem, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                              uint32_t bar, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
 }
 // same copy, delivered to the same CTA-relative offsets (data and mbarrier) of every CTA in `cta_mask` of the cluster
 __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
@@ -282,14 +296,15 @@ __device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // SRC: 0 = fp32 activations, element-wise gather; 1 = fp32, every 8-element K group lies inside one tap and is
 // contiguous + 16-byte aligned (Cin % 8 == 0): vector gather; 2 = split-bf16 planes, same alignment rule: cp.async gather.
-constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2;
+// 3 = split-bf16 planes through the TMA unit in im2col mode (Cin % 64 == 0): one thread per CTA feeds the operand ring.
+constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2, SRC_TMA = 3;
 
 // Persistent: one CTA per SM walks the work list (m tile, n tile, K split) with a static stride; the three roles run
 // decoupled through mbarriers, so the operand ring never drains between tiles and the epilogue of tile i overlaps the
 // MMAs of tile i+1 (two TMEM accumulators).
 template <int BN, int NSPLIT, int SRC>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) {
+gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
   constexpr bool CONCAT = NSPLIT == 2;        // A_hi x [B_hi | B_lo] as one MMA of width 2*BN, then A_lo x B_hi
@@ -332,7 +347,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
   if (warp == UM_MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, UM_PRODUCER_WARPS * 32 + 1);   // every producer thread + the expect_tx arrival of the B copy
+        // every producer thread + the expect_tx arrival of the B copy; TMA gather: the expect_tx arrival alone
+        mbar_init(bar_full + 8 * s, SRC == SRC_TMA ? 1 : UM_PRODUCER_WARPS * 32 + 1);
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -362,7 +378,50 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a) 
     z = (int)(r / NT);
   };
 
-  if (warp < UM_PRODUCER_WARPS) {
+  if (SRC == SRC_TMA && warp < UM_PRODUCER_WARPS) {
+    // ================================ producer (TMA im2col): warp 0, one elected lane ================================
+    if (warp == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
+      for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
+        int mt, nt, z;
+        decode_work(wk, mt, nt, z);
+        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+        // base input pixel of the tile's first row (tiles never start beyond M with one CTA per cluster)
+        const uint32_t mu = (uint32_t)((int64_t)mt * UM_BM);
+        const uint32_t q = mu / (uint32_t)g.PW, j = mu - q * (uint32_t)g.PW;
+        const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
+        const int cw = (int)j * g.isx + a.tma_w0, ch = (int)i * g.isy + a.tma_h0;
+#pragma unroll 1
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          const long long tr_w0 = a.trace ? clock64() : 0;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (a.trace) { tr_wait += clock64() - tr_w0; ++tr_chunks; }
+          if (elect_one()) {
+            const int kk = kc * UM_BK;
+            const int t = kk / g.Cin;
+            const int ci0 = kk - t * g.Cin;
+            const uint16_t ow = (uint16_t)(g.dx[t] - a.tma_w0), oh = (uint16_t)(g.dy[t] - a.tma_h0);
+            const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
+            const uint32_t bar = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(bar, PLANES * (UM_A_PLANE + B_PLANE));
+            tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
+            if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
+            bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
+                     PLANES * B_PLANE, bar);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (a.trace && lane == 0) {
+        a.trace[blockIdx.x * 16 + 2] = tr_wait;
+        a.trace[blockIdx.x * 16 + 3] = clock64() - tr_t0;
+        a.trace[blockIdx.x * 16 + 6] = tr_chunks;
+      }
+    }
+  } else if (warp < UM_PRODUCER_WARPS) {
     // ================================ producers ================================
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
     int stage = 0;
@@ -1001,7 +1060,7 @@ int num_sms() {
 }
 
 template <int BN, int NSPLIT, int SRC>
-int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStream_t st) {
+int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int nt, int Z, cudaStream_t st) {
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
   UmmaArgs a = a_in;
@@ -1059,7 +1118,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
     cudaMemset(dtr, 0, n * sizeof(long long));
     a.trace = dtr;
     cudaStreamSynchronize(st);
-    cudaLaunchKernelEx(&cfg, kern, g, a);
+    cudaLaunchKernelEx(&cfg, kern, g, a, tm);
     cudaStreamSynchronize(st);
     std::vector<long long> tr(n);
     cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1077,32 +1136,35 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, int nt, int Z, cudaStr
     SAG_LAUNCH_CHECK();
     return SAG_OK;
   }
-  SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a));
+  SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, g, a, tm));
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
 
 template <int BN, int NSPLIT>
-int launch_ns(const GatherGeom& g, const UmmaArgs& a, int nt, int src, int Z, cudaStream_t st) {
+int launch_ns(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt, int src, int Z, cudaStream_t st) {
   switch (src) {
-    case SRC_BF2: return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, nt, Z, st);
-    case SRC_F32_VEC: return launch_cfg<BN, NSPLIT, SRC_F32_VEC>(g, a, nt, Z, st);
-    default: return launch_cfg<BN, NSPLIT, SRC_F32>(g, a, nt, Z, st);
+    case SRC_TMA:
+      if constexpr (BN >= 64) return launch_cfg<BN, NSPLIT, SRC_TMA>(g, a, tm, nt, Z, st);
+      else return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, tm, nt, Z, st);      // (the host never picks TMA for 32-wide tiles)
+    case SRC_BF2: return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, tm, nt, Z, st);
+    case SRC_F32_VEC: return launch_cfg<BN, NSPLIT, SRC_F32_VEC>(g, a, tm, nt, Z, st);
+    default: return launch_cfg<BN, NSPLIT, SRC_F32>(g, a, tm, nt, Z, st);
   }
 }
 
 template <int BN>
-int launch_bn(const GatherGeom& g, const UmmaArgs& a, int nt, int planes, int src, int Z, cudaStream_t st) {
+int launch_bn(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt, int planes, int src, int Z, cudaStream_t st) {
   // bf16x3 on tiles up to 128 wide: two MMAs per K step (A_hi x [B_hi | B_lo], A_lo x B_hi) instead of three -- 22 % / 17 %
   // fewer shared-memory operand bytes on 64- / 128-wide tiles; 256-wide tiles have no TMEM for a second accumulator block
   static const int concat = env_int("SAG_UMMA_CONCAT", 1);
   if (planes == 2) {
     if constexpr (BN <= 128) {
-      if (concat) return launch_ns<BN, 2>(g, a, nt, src, Z, st);
+      if (concat) return launch_ns<BN, 2>(g, a, tm, nt, src, Z, st);
     }
-    return launch_ns<BN, 3>(g, a, nt, src, Z, st);
+    return launch_ns<BN, 3>(g, a, tm, nt, src, Z, st);
   }
-  return launch_ns<BN, 1>(g, a, nt, src, Z, st);
+  return launch_ns<BN, 1>(g, a, tm, nt, src, Z, st);
 }
 
 }  // namespace
@@ -1326,6 +1388,45 @@ static int plan_split_k(int K, int N, int64_t M, int BN, size_t* scratch_bytes) 
 // pulling Z partial tiles through L2 latency cannot compete with a reduce spread over the whole GPU.)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) { return plan_split_k(K, N, M, tile_width(N, M), scratch_bytes); }
 
+thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
+
+// im2col tensor maps over the two bf16 planes of an NHWC activation for the geometry's taps (reference for the
+// corner arithmetic: base pixel of output (i, j) = (i*isy + min dy, j*isx + min dx); the box's upper corner is chosen so
+// that exactly PW x PH base pixels fit).  Returns false when the layer does not fit the TMA unit's limits.
+static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm, int* w0, int* h0) {
+  if (x.fmt != ACT_BF2 || g.Cin % UM_BK != 0 || g.x_ld % 8 != 0 || g.T < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return false;
+  int mindx = g.dx[0], mindy = g.dy[0], maxdx = g.dx[0], maxdy = g.dy[0];
+  for (int t = 1; t < g.T; ++t) {
+    mindx = std::min(mindx, (int)g.dx[t]); maxdx = std::max(maxdx, (int)g.dx[t]);
+    mindy = std::min(mindy, (int)g.dy[t]); maxdy = std::max(maxdy, (int)g.dy[t]);
+  }
+  const int up_w = (g.PW - 1) * g.isx + 1 + mindx - g.W, up_h = (g.PH - 1) * g.isy + 1 + mindy - g.H;
+  if (mindx < -128 || mindx > 127 || mindy < -128 || mindy > 127 || up_w < -128 || up_w > 127 || up_h < -128 || up_h > 127) return false;
+  if (maxdx - mindx > 255 || maxdy - mindy > 255 || g.isx < 1 || g.isx > 8 || g.isy < 1 || g.isy > 8) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, (cuuint64_t)g.W * g.x_ld * 2, (cuuint64_t)g.H * g.W * g.x_ld * 2};
+  const int lower[2] = {mindx, mindy}, upper[2] = {up_w, up_h};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)g.isx, (cuuint32_t)g.isy, 1};
+  static int driver = -1;
+  if (driver < 0) cudaDriverGetVersion(&driver);
+  for (int pl = 0; pl < (x.plane != 0 ? 2 : 1); ++pl) {
+    CUtensorMap* m = pl == 0 ? &tm->hi : &tm->lo;
+    void* base = reinterpret_cast<char*>(x.p) + (pl == 0 ? 0 : x.plane);
+    CUresult r = cuTensorMapEncodeIm2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper,
+                                         (cuuint32_t)UM_BK, (cuuint32_t)UM_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    // same adjustment CUTLASS applies to im2col maps of tensors under 128 KB on drivers up to 13.1
+    // (cute/atom/copy_traits_sm90_im2col.hpp, make_im2col_tma_copy_desc)
+    if (driver <= 13010 && (cuuint64_t)g.N * strides[2] < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  }
+  *w0 = mindx;
+  *h0 = mindy;
+  return true;
+}
+
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st) {
   SAG_REQUIRE(w.packed != nullptr || w.KC == 0, SAG_ESTATE, "tcgen05 path: weights are not packed");
@@ -1364,6 +1465,11 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     SAG_REQUIRE(w.planes == 1 || x.plane != 0, SAG_EINVAL, "tcgen05 path: bf16x3 needs the lo plane of the activation");
     src = SRC_BF2;
   }
+  TmaPair tm;
+  memset(&tm, 0, sizeof(tm));
+  static const int tma_env = env_int("SAG_UMMA_TMA", 1);
+  if (src == SRC_BF2 && w.BN >= 64 && (g_umma_tma < 0 ? tma_env : g_umma_tma) && make_im2col_maps(x, g, &tm, &a.tma_w0, &a.tma_h0))
+    src = SRC_TMA;
   int Z = scratch != nullptr ? plan_split_k(w.K, w.N, M, w.BN, nullptr) : 1;
   if (Z > 1) {
     SAG_REQUIRE(w.BN == tile_width(w.N, M), SAG_ESTATE, "tcgen05 path: weights were packed for a different row count (tile %d)", w.BN);
@@ -1376,10 +1482,10 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);
   int r;
   switch (w.BN) {
-    case 32: r = launch_bn<32>(g, a, w.NT, w.planes, src, Z, st); break;
-    case 64: r = launch_bn<64>(g, a, w.NT, w.planes, src, Z, st); break;
-    case 128: r = launch_bn<128>(g, a, w.NT, w.planes, src, Z, st); break;
-    case 256: r = launch_bn<256>(g, a, w.NT, w.planes, src, Z, st); break;
+    case 32: r = launch_bn<32>(g, a, tm, w.NT, w.planes, src, Z, st); break;
+    case 64: r = launch_bn<64>(g, a, tm, w.NT, w.planes, src, Z, st); break;
+    case 128: r = launch_bn<128>(g, a, tm, w.NT, w.planes, src, Z, st); break;
+    case 256: r = launch_bn<256>(g, a, tm, w.NT, w.planes, src, Z, st); break;
     default: set_error("tcgen05 path: unsupported tile width %d", w.BN); return SAG_EINVAL;
   }
   SAG_TRY(r);

@@ -330,6 +330,25 @@ def test_forward_tcgen05_audio_only_and_flow():
     assert _rel(m.inference_ops(cu(a), video=cu(v), flow=cu(fl)), ref.inference_ops(a, video=v, flow=fl)) < 1e-3
 
 
+def test_forward_tma_gather_matches_cp_async_gather():
+    """The TMA im2col producer and the cp.async producer put the same bytes into the operand ring: the audio-only
+    forward (no batch-norm atomics) is bit-identical, the audio+video forward agrees to the atomics' rounding."""
+    _, m = _models(['audio'], 'unet_mask', 5, 3, precision='bf16x3')
+    a = cu(_audio(3, 31))
+    m.set_option('tma_gather', 1)
+    y1 = m.inference_ops(a).clone()
+    m.set_option('tma_gather', 0)
+    y0 = m.inference_ops(a).clone()
+    assert torch.equal(y0, y1)
+    _, m = _models(['audio', 'video'], 'unet_mask', 7, 2, precision='bf16x3')
+    a, v = cu(_audio(2, 32)), cu(_video(2, 33))
+    m.set_option('tma_gather', 1)
+    y1 = m.inference_ops(a, video=v).clone()
+    m.set_option('tma_gather', 0)
+    y0 = m.inference_ops(a, video=v).clone()
+    assert _rel(y1, y0) < 1e-4
+
+
 def test_forward_errors():
     from spatialaudiogen_b200 import SptAudioGen
     with pytest.raises(ValueError):
