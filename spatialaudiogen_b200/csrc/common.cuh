@@ -123,7 +123,7 @@ struct UmmaWeights {
 };
 void umma_free(UmmaWeights* w);
 // tile width of a contraction with N columns over M rows (a single M tile takes narrow tiles: see conv_umma.cu)
-int umma_tile_width(int N, int64_t M);
+int umma_tile_width(int K, int N, int64_t M);
 // wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form); M: rows of the GEMM
 // the image will be used for (selects the tile width)
 int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);

@@ -35,8 +35,7 @@ namespace {
 constexpr int UM_BM = 128;                  // rows per tile (UMMA M, one TMEM lane per row)
 constexpr int UM_BK = 64;                   // K elements per stage = one 128-byte swizzle atom of bf16
 constexpr int UM_PRODUCER_WARPS = 8;         // warps 0-7
-constexpr int UM_EPI_WARP0 = 8;              // warps 8-11: epilogue (warp % 4 == TMEM lane quadrant)
-constexpr int UM_EPI_WARPS = 4;
+constexpr int UM_EPI_WARP0 = 8;              // warps 8-11: epilogue (warp % 4 == TMEM lane quadrant); + warps 4-7 with the TMA producer
 constexpr int UM_MMA_WARP = 12;              // warp 12: TMEM allocation + MMA issue
 constexpr int UM_THREADS = 13 * 32;
 constexpr int UM_MAX_N = 1024;               // widest GEMM with batch-norm statistics / per-CTA column sums
@@ -307,6 +306,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
+  constexpr int EW = SRC == SRC_TMA ? 8 : 4;   // epilogue warps (see the epilogue role)
   constexpr bool CONCAT = NSPLIT == 2;        // A_hi x [B_hi | B_lo] as one MMA of width 2*BN, then A_lo x B_hi
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
@@ -320,7 +320,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
   __shared__ long long s_yoff[UM_BM];                    // per-row output element offset of the tile in the epilogue
   __shared__ int s_oy[UM_BM], s_ox[UM_BM];
-  __shared__ float s_part[UM_EPI_WARPS][64];             // per-epilogue-warp column sums / sums of squares of a pass
+  __shared__ float s_part[8][64];             // per-epilogue-warp column sums / sums of squares of a pass
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = smem_u32(um_smem);
@@ -353,7 +353,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull + 8 * b, 1);                       // one tcgen05.commit per tile
-        mbar_init(bar_tempty + 8 * b, UM_EPI_WARPS);           // the epilogue warps have drained the accumulator
+        mbar_init(bar_tempty + 8 * b, EW);                     // the epilogue warps have drained the accumulator
       }
       for (int s = 0; s < S; ++s) mbar_init(bar_peer + 8 * s, CL > 1 ? CL - 1 : 1);
       fence_barrier_init();
@@ -378,8 +378,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     z = (int)(r / NT);
   };
 
-  if (SRC == SRC_TMA && warp < UM_PRODUCER_WARPS) {
-    // ================================ producer (TMA im2col): warp 0, one elected lane ================================
+  if (SRC == SRC_TMA && warp < 4) {
+    // ================================ producer (TMA im2col): warp 0, one elected lane (warps 1-3 idle) ================================
     if (warp == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -421,7 +421,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 6] = tr_chunks;
       }
     }
-  } else if (warp < UM_PRODUCER_WARPS) {
+  } else if (SRC != SRC_TMA && warp < UM_PRODUCER_WARPS) {
     // ================================ producers ================================
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
     int stage = 0;
@@ -612,10 +612,19 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 7] = tr_wacc;
       }
     }
-  } else {
-    // ================================ epilogue (4 warps = the 4 TMEM lane quadrants) ================================
-    const int q = warp & 3;                        // warps 8..11 -> quadrants 0..3
-    const int et = tid - UM_EPI_WARP0 * 32;        // 0..127 = row of the tile this thread owns in TMEM
+  } else if (warp >= UM_EPI_WARP0 || (SRC == SRC_TMA && warp >= 4)) {
+    // ================================ epilogue ================================
+    // EW warps: 4 (one per TMEM lane quadrant) next to the cp.async producers; 8 when the TMA unit gathers and warps 4-7
+    // are free: two warps per quadrant, each draining half of the columns of a pass.  The pass is latency bound
+    // (~600 dependent instructions per warp), so the second warp per scheduler nearly halves it.
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp (hardware rule: warp % 4)
+    const int half = (EW == 8 && warp < UM_EPI_WARP0) ? 1 : 0;      // which CPT-column half of a pass this warp drains
+    const int ew = half * 4 + q;                   // epilogue warp index 0..EW-1
+    const int et = ew * 32 + lane;                 // epilogue thread index 0..EW*32-1
+    const int row = q * 32 + lane;                 // tile row (= TMEM lane) this thread drains
+    constexpr int CPT = 128 / EW;                  // columns per thread per pass: 32 or 16
+    constexpr int RD = 32 / EW;                    // copy-out rows per thread per pass: 8 or 4
+    constexpr int RPP = 128 / EW;                  // statistics: rows per partial sum
     constexpr uint32_t PITCH = 32 * 4 + 16;        // 32 fp32 columns per pass; +16 B keeps 16-byte row stores conflict-free
     const bool split = a.partial != nullptr;       // K split: raw accumulators go to the partial region first
     float* yf = reinterpret_cast<float*>(a.y);
@@ -631,7 +640,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       const int b = (int)(it_local & 1);
       const uint32_t use = (uint32_t)(it_local >> 1);
       const int rows_valid = (int)((M - m0) < UM_BM ? ((M - m0) > 0 ? (M - m0) : 0) : UM_BM);   // valid rows come first
-      {                                            // where this thread's row goes in the output tensor
+      if (et < UM_BM) {                            // where row `et` of the tile goes in the output tensor
         const int64_t m = m0 + et;
         long long yo = UM_ROW_INVALID;
         int oy = 0, ox = 0;
@@ -659,18 +668,18 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         if (n < ncols) {
           if (raw || (a.dense && a.vec_store)) {
             // fast path: row rr of the tile lands at a fixed stride; all loads first, then all stores
-            float4 w4[8];
+            float4 w4[RD];
 #pragma unroll
-            for (int rd = 0; rd < 8; ++rd) {
-              const int rr = rd * 16 + q * 4 + lr;
+            for (int rd = 0; rd < RD; ++rd) {
+              const int rr = rd * (EW * 4) + ew * 4 + lr;
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w4[rd].x), "=f"(w4[rd].y), "=f"(w4[rd].z), "=f"(w4[rd].w)
                            : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
             }
             const int64_t rstride = raw ? (int64_t)a.n_pad : g.y_sw;
             const int64_t base = (raw ? ((int64_t)z * M + m0) * a.n_pad : m0 * g.y_sw) + n;
 #pragma unroll
-            for (int rd = 0; rd < 8; ++rd) {
-              const int rr = rd * 16 + q * 4 + lr;
+            for (int rd = 0; rd < RD; ++rd) {
+              const int rr = rd * (EW * 4) + ew * 4 + lr;
               if (rr >= rows_valid) continue;
               const int64_t eoff = base + (int64_t)rr * rstride;
               if (raw) {
@@ -684,14 +693,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
             }
           } else if (a.col_off != nullptr && a.vec_store) {
             // mapped output (sub-pixel transposed conv), groups of 4 columns contiguous: row table and values of all
-            // 8 rows are loaded before the first store
+            // rows are loaded before the first store
             const int c_off = __ldg(a.col_off + n), c_dy = __ldg(a.col_dy + n), c_dx = __ldg(a.col_dx + n);
-            float4 w4[8];
-            long long yo[8];
-            bool ok[8];
+            float4 w4[RD];
+            long long yo[RD];
+            bool ok[RD];
 #pragma unroll
-            for (int rd = 0; rd < 8; ++rd) {
-              const int rr = rd * 16 + q * 4 + lr;
+            for (int rd = 0; rd < RD; ++rd) {
+              const int rr = rd * (EW * 4) + ew * 4 + lr;
               yo[rd] = s_yoff[rr];
               ok[rd] = yo[rd] != UM_ROW_INVALID && (unsigned)(s_oy[rr] + c_dy) < (unsigned)a.oh_lim &&
                        (unsigned)(s_ox[rr] + c_dx) < (unsigned)a.ow_lim;
@@ -699,7 +708,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
                            : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
             }
 #pragma unroll
-            for (int rd = 0; rd < 8; ++rd) {
+            for (int rd = 0; rd < RD; ++rd) {
               if (!ok[rd]) continue;
               const int64_t eoff = yo[rd] + c_off;
               if (a.out_bf2) {
@@ -718,8 +727,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
                 if (n + e < a.Ntot) { c_off[e] = __ldg(a.col_off + n + e); c_dy[e] = __ldg(a.col_dy + n + e); c_dx[e] = __ldg(a.col_dx + n + e); }
             }
 #pragma unroll 4
-            for (int rd = 0; rd < 8; ++rd) {
-              const int rr = rd * 16 + q * 4 + lr;
+            for (int rd = 0; rd < RD; ++rd) {
+              const int rr = rd * (EW * 4) + ew * 4 + lr;
               const long long yo = s_yoff[rr];
               if (yo == UM_ROW_INVALID) continue;
               float4 w4;
@@ -750,29 +759,32 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         }
         long long tp3 = a.trace ? clock64() : 0;
         const bool st_pass = stats && !raw;
-        if (st_pass) {                             // column sums of the staged pass: 4 threads per column, 32 rows each
+        if (st_pass) {                             // column sums of the staged pass: EW threads per column, RPP rows each
           const int c = et & 31, part = et >> 5;
           float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int rr = part + 4 * i;
+          for (int i = 0; i < RPP; ++i) {
+            const int rr = part + EW * i;
             float x;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)c * 4u));
             if (rr >= rows_valid) x = 0.f;
             cs[i & 3] += x;
             cq[i & 3] = fmaf(x, x, cq[i & 3]);
           }
-          // per-warp partials; epilogue warp 0 folds them into the CTA sums after the barrier below, in a fixed order
-          // (no atomics: the per-CTA statistics are run-to-run reproducible)
+          // per-warp partials; the first epilogue warp folds them into the CTA sums after the barrier below, in a fixed
+          // order (no atomics: the per-CTA statistics are run-to-run reproducible)
           s_part[part][c] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
           s_part[part][32 + c] = (cq[0] + cq[1]) + (cq[2] + cq[3]);
         }
         long long tp4 = a.trace ? clock64() : 0;
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");   // staging tile and row table reusable
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // staging tile and row table reusable
         if (st_pass && et < 32 && n_base + c0 + et < a.Ntot) {
           // (the next pass rewrites s_part only after its own first barrier, which this warp has not reached yet)
-          s_sum[n_base + c0 + et] += (s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et]);
-          s_sqs[n_base + c0 + et] += (s_part[0][32 + et] + s_part[1][32 + et]) + (s_part[2][32 + et] + s_part[3][32 + et]);
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int p = 0; p < EW; ++p) { ts += s_part[p][et]; tq += s_part[p][32 + et]; }
+          s_sum[n_base + c0 + et] += ts;
+          s_sqs[n_base + c0 + et] += tq;
         }
         if (a.trace) {
           const long long tp5 = clock64();
@@ -787,16 +799,17 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
+        float v[CPT];
         long long tp0 = a.trace ? clock64() : 0;
-        tmem_ld16(tmem_row + (uint32_t)c0, v);
-        tmem_ld16(tmem_row + (uint32_t)c0 + 16u, v + 16);
-        if (CONCAT) {                              // second accumulator block: A_hi x B_lo
-          float u[32];
-          tmem_ld16(tmem_row + (uint32_t)(BN + c0), u);
-          tmem_ld16(tmem_row + (uint32_t)(BN + c0) + 16u, u + 16);
+        const int cc = c0 + half * CPT;            // first column of this thread's share of the pass
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += u[e];
+        for (int e = 0; e < CPT; e += 16) tmem_ld16(tmem_row + (uint32_t)(cc + e), v + e);
+        if (CONCAT) {                              // second accumulator block: A_hi x B_lo
+          float u[CPT];
+#pragma unroll
+          for (int e = 0; e < CPT; e += 16) tmem_ld16(tmem_row + (uint32_t)(BN + cc + e), u + e);
+#pragma unroll
+          for (int e = 0; e < CPT; ++e) v[e] += u[e];
         }
         if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
@@ -804,25 +817,34 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
         }
         if (!split && (a.bias != nullptr || a.relu)) {
+          const int n0 = n_base + cc;
+          if (a.bias != nullptr) {
+            if (n0 + CPT <= a.Ntot && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int n = n_base + c0 + e;
-            const float bb = (a.bias != nullptr && n < a.Ntot) ? __ldg(a.bias + n) : 0.f;
-            float w = v[e] + bb;
-            if (a.relu) w = fmaxf(w, 0.f);
-            v[e] = w;
+              for (int e = 0; e < CPT; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + e));
+                v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < CPT; ++e)
+                if (n0 + e < a.Ntot) v[e] += __ldg(a.bias + n0 + e);
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) v[e] = fmaxf(v[e], 0.f);
           }
         }
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          st_shared_v4(stile + (uint32_t)et * PITCH + (uint32_t)e * 4u,
+        for (int e = 0; e < CPT; e += 4)
+          st_shared_v4(stile + (uint32_t)row * PITCH + (uint32_t)(half * CPT + e) * 4u,
                        make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
         long long tp1 = a.trace ? clock64() : 0;
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_WARPS * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         if (a.trace) tr_p[0] += tp1 - tp0;
         emit_pass(c0, split);
       }
-
     }
     if (a.trace && et == 0) {
       for (int i = 0; i < 5; ++i) a.trace[blockIdx.x * 16 + 8 + i] = tr_p[i];
@@ -1068,7 +1090,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   a.Z = Z;
   // one persistent CTA per SM: barriers + staging tile + alignment slack + as many operand stages as fit (<= 6)
   const int fixed = UM_BAR_BYTES + 16 + UM_STAGING_BYTES + 1024;
-  int S = (215 * 1024 - fixed) / STAGE_BYTES;    // + ~11 KB of static shared memory: 215 KB dynamic stays under the 227 KB limit
+  int S = (214 * 1024 - fixed) / STAGE_BYTES;    // + ~12 KB of static shared memory: 214 KB dynamic stays under the 227 KB limit
   if (S > 6) S = 6;    // the cp.async drain handles at most 5 groups in flight
   if (S < 2) S = 2;
   a.stages = S;
@@ -1078,7 +1100,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024));
+    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024));
     attr_set[dev & 63] = true;
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
@@ -1171,8 +1193,6 @@ int launch_bn(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt,
 
 // ---- host API -----------------------------------------------------------------------------------------------------
 // 256-wide tiles halve the A re-reads of wide layers (the gather is L2-bandwidth bound); they use all 512 TMEM columns
-// A single M tile (fully connected layers on a batch of windows) is weight-streaming bound: narrow tiles spread the
-// weight matrix over many CTAs (together with a deep K split) instead of feeding it through a handful of SMs.
 // Tuning knob (development): SAG_UMMA_FORCE="MT:N:BN:Z,..." pins tile width / K split of the layers with MT m tiles
 // and N columns (BN or Z = 0 keeps the planner's choice).
 struct ForcedCfg { int64_t mt; int n, bn, z; };
@@ -1198,14 +1218,45 @@ static const ForcedCfg* forced_for(int N, int64_t M) {
   return nullptr;
 }
 
-static int tile_width(int N, int64_t M) {
-  if (const ForcedCfg* f = forced_for(N, M)) {
-    if (f->bn == 32 || f->bn == 64 || f->bn == 128 || f->bn == 256) return f->bn;
-  }
+// Tile width and K split of a contraction with K x N weights over M rows, from a cost model in microseconds fitted to
+// per-layer CUDA-event timings on B200 (profiles/README.md, "planner"): a work item = its K chunks (shared-memory
+// operand traffic grows with the tile width) + its epilogue passes; items run in waves over the 148 persistent CTAs;
+// a K split adds the partial round trip through L2 and the reduce launch.  A single M tile (fully connected layers
+// on a batch of windows) is weight-streaming bound: narrow tiles + a deep split spread the weights over all SMs.
+struct TilePlan { int BN, Z; };
+static TilePlan plan_tile(int K, int N, int64_t M) {
   static const int wide = env_int("SAG_UMMA_BN256", 1);
   static const int narrow_fc = env_int("SAG_UMMA_NARROW_FC", 1);
-  if (narrow_fc && M <= UM_BM) return N <= 32 ? 32 : 64;
-  return N <= 32 ? 32 : (N <= 64 ? 64 : ((N >= 256 && wide) ? 256 : 128));
+  static const int splitk = env_int("SAG_UMMA_SPLITK", 1);
+  const int KC = cdiv(K, UM_BK);
+  int cand[2], nc = 0;
+  if (N <= 32) cand[nc++] = 32;
+  else if (N <= 64 || (narrow_fc && M <= UM_BM)) cand[nc++] = 64;
+  else { if (N >= 256 && wide) cand[nc++] = 256; cand[nc++] = 128; }      // the wide tile is the incumbent
+  const ForcedCfg* f = forced_for(N, M);
+  if (f && (f->bn == 32 || f->bn == 64 || f->bn == 128 || f->bn == 256)) { cand[0] = f->bn; nc = 1; }
+  const int min_chunks = M <= UM_BM ? 2 : 4;      // a single M tile may split down to 2 chunks per item
+  TilePlan best{cand[0], 1};
+  double best_t = 0.0;
+  for (int ci = 0; ci < nc; ++ci) {
+    const int BN = cand[ci], NT = cdiv(N, BN);
+    const int64_t tiles = cdiv64(M, UM_BM) * NT;
+    const double chunk_us = BN == 256 ? 0.95 : (BN == 128 ? 0.59 : (BN == 64 ? 0.43 : 0.36));
+    const double epi_us = 0.6 * (BN / 32);
+    int z_lo = 1, z_hi = splitk ? std::min(32, KC / min_chunks) : 1;
+    if (z_hi < 1) z_hi = 1;
+    if (f && f->z >= 1 && f->z <= KC) z_lo = z_hi = f->z;
+    int bz = z_lo;
+    double bt = 0.0;
+    for (int z = z_lo; z <= z_hi; ++z) {
+      const int64_t waves = cdiv64(tiles * z, 148);
+      double t = (double)waves * ((double)cdiv(KC, z) * chunk_us + epi_us) + 5.0;
+      if (z > 1) t += 8.0 + (2.0 * z + 1.0) * (double)M * (double)(NT * BN) * 4.0 / 4.0e6;
+      if (z == z_lo || t < bt * 0.97) { bt = t; bz = z; }     // split further only for a clear (>3 %) win
+    }
+    if (ci == 0 || bt < best_t * 0.95) { best_t = bt; best = TilePlan{BN, bz}; }
+  }
+  return best;
 }
 
 void umma_free(UmmaWeights* w) {
@@ -1224,7 +1275,7 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   UmmaWeights w;
   w.K = K; w.N = N;
   w.KC = cdiv(K, UM_BK);
-  w.BN = tile_width(N, M);
+  w.BN = plan_tile(K, N, M).BN;
   w.M_hint = M;
   w.NT = cdiv(N, w.BN);
   w.planes = precision == SAG_PREC_BF16X3 ? 2 : 1;
@@ -1349,44 +1400,17 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
 // Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the
 // partial accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them
 // (deterministic: fixed summation order).
-int umma_tile_width(int N, int64_t M) { return tile_width(N, M); }
-
-static int plan_split_k(int K, int N, int64_t M, int BN, size_t* scratch_bytes) {
-  static const int enabled = env_int("SAG_UMMA_SPLITK", 1);
-  const int NT = cdiv(N, BN), KC = cdiv(K, UM_BK);
-  const int64_t tiles = cdiv64(M, UM_BM) * NT;
-  int Z = 1;
-  if (const ForcedCfg* f = forced_for(N, M)) {
-    if (f->z >= 1 && f->z <= KC) {
-      if (scratch_bytes) *scratch_bytes = f->z > 1 ? sizeof(float) * (size_t)f->z * (size_t)M * (size_t)(NT * BN) : 0;
-      return f->z;
-    }
-  }
-  // a single M tile streams its weights once: splits down to 2 chunks keep every SM pulling its share
-  const int min_chunks = M <= UM_BM ? 2 : 4;
-  if (enabled && tiles > 0 && KC >= 2 * min_chunks) {
-    // Cost model in units of one K chunk: a work item costs its chunks plus ~2 chunks of per-tile work, a launch ~4
-    // chunks of pipeline fill; items run in waves of `slots`; splitting adds the partial round trip (~5 % + the
-    // reduce launch).  Pick the split that minimises the wave-quantised time -- it both fills
-    // the SMs of small layers and trims ragged last waves.
-    const int64_t slots = 148;                // one persistent CTA per SM
-    double best = 0.0;
-    for (int z = 1; z <= 32 && z <= KC / min_chunks; ++z) {
-      const int64_t waves = cdiv64(tiles * z, slots);
-      double t = (double)waves * ((double)cdiv(KC, z) + 2.0) + 4.0;
-      if (z > 1) t = t * 1.05 + 4.0;
-      if (z == 1 || t < best * 0.97) { best = t; Z = z; }   // split only for a clear (>3 %) win
-    }
-  }
-  if (scratch_bytes) *scratch_bytes = Z > 1 ? sizeof(float) * (size_t)Z * (size_t)M * (size_t)(NT * BN) : 0;
-  return Z;
-}
+int umma_tile_width(int K, int N, int64_t M) { return plan_tile(K, N, M).BN; }
 
 // Split-K plan: layers whose tile count cannot fill the 148 SMs but whose K loop is long are cut along K; the partial
 // accumulators go through `scratch` ([Z][M][n_pad] fp32) and splitk_reduce_kernel finishes them (deterministic: fixed
 // summation order).  (A fix-up by the last CTA to arrive at a tile was measured 25 % slower end to end: 128 threads
 // pulling Z partial tiles through L2 latency cannot compete with a reduce spread over the whole GPU.)
-int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) { return plan_split_k(K, N, M, tile_width(N, M), scratch_bytes); }
+int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
+  const TilePlan p = plan_tile(K, N, M);
+  if (scratch_bytes) *scratch_bytes = p.Z > 1 ? sizeof(float) * (size_t)p.Z * (size_t)M * (size_t)(cdiv(N, p.BN) * p.BN) : 0;
+  return p.Z;
+}
 
 thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
 
@@ -1470,11 +1494,10 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   static const int tma_env = env_int("SAG_UMMA_TMA", 1);
   if (src == SRC_BF2 && w.BN >= 64 && (g_umma_tma < 0 ? tma_env : g_umma_tma) && make_im2col_maps(x, g, &tm, &a.tma_w0, &a.tma_h0))
     src = SRC_TMA;
-  int Z = scratch != nullptr ? plan_split_k(w.K, w.N, M, w.BN, nullptr) : 1;
-  if (Z > 1) {
-    SAG_REQUIRE(w.BN == tile_width(w.N, M), SAG_ESTATE, "tcgen05 path: weights were packed for a different row count (tile %d)", w.BN);
-    a.partial = scratch;
-  }
+  const TilePlan plan = plan_tile(w.K, w.N, M);
+  SAG_REQUIRE(w.BN == plan.BN, SAG_ESTATE, "tcgen05 path: weights were packed for a different row count (tile %d, planned %d)", w.BN, plan.BN);
+  const int Z = scratch != nullptr ? plan.Z : 1;
+  if (Z > 1) a.partial = scratch;
   // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
   a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;

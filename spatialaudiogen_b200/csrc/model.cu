@@ -240,7 +240,7 @@ struct Fwd {
       return launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st);
     }
     const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
-    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(cout, Mrows));
+    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, cout, Mrows));
     auto it = h->umma.find(key);
     if (it == h->umma.end()) {                    // first use: build the tensor-core operand image of this layer
       UmmaWeights uw;
@@ -273,7 +273,7 @@ struct Fwd {
       SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
                                         &oh_lim, &ow_lim));
       const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
-      const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(sh * sw * cout, Mrows));
+      const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, sh * sw * cout, Mrows));
       auto it = h->umma.find(key);
       if (it == h->umma.end()) {
         const float* w_tf = W(scope + "/weights", &err);
@@ -375,7 +375,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
       const float* w = f.W(p + "conv1/conv/weights", &err);
       SAG_TRY(err);
       const int64_t Mrows = (int64_t)B * oh * ow;
-      const std::string key = p + "conv1/conv#" + std::to_string(f.prec) + "#" + std::to_string(umma_tile_width(64, Mrows));
+      const std::string key = p + "conv1/conv#" + std::to_string(f.prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, 64, Mrows));
       auto it = h->umma.find(key);
       if (it == h->umma.end()) {
         UmmaWeights uw;
