@@ -62,6 +62,33 @@ struct ProfScope {                      // records an event pair around the laun
   ~ProfScope();
 };
 
+// ---- programmatic dependent launch: the kernels of the forward are launched with programmatic stream serialisation,
+// so the next kernel's launch and prologue overlap the tail of the current one.  Every such kernel calls
+// pdl_prologue() first: it lets its own dependent start launching and then waits until the kernel before it in the
+// stream has completed and flushed its writes (transitively: everything earlier in the stream).  SAG_PDL=0 disables it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) { cfg.attrs = &at; cfg.numAttrs = 1; }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

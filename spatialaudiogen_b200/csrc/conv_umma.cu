@@ -365,6 +365,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   if (CL > 1) cluster_sync_all();                              // peers' barriers exist before anyone arrives remotely
   else __syncthreads();
   tc_fence_after();
+  // everything above (barriers, TMEM, zeroed statistics) is independent of earlier kernels: with programmatic dependent
+  // launch it overlaps the tail of the previous kernel; from here on this kernel reads / overwrites global tensors
+  pdl_prologue();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -955,6 +958,7 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias, int cout, int
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, int Z,
                                                             int SK_ROWS) {
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];
+  pdl_prologue();
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   const int64_t r0 = (int64_t)blockIdx.x * SK_ROWS;
   const int rows = (int)((M - r0) < SK_ROWS ? (M - r0) : SK_ROWS);
@@ -1127,8 +1131,13 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   attr.val.clusterDim.x = CL;
   attr.val.clusterDim.y = 1;
   attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attrs[2];
+  attrs[0] = attr;
+  memset(&attrs[1], 0, sizeof(attrs[1]));
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // debug: SAG_UMMA_TRACE=<M tiles> prints where the three roles of the first launch with that many M tiles wait
   static const int trace_mt = env_int("SAG_UMMA_TRACE", 0);
   static int traced = 0;
@@ -1516,7 +1525,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     int rpb = (int)(M / (2 * num_sms()));           // rows per block: keep >= 2 blocks per SM, at most 16 rows
     if (rpb > 16) rpb = 16;
     if (rpb < 1) rpb = 1;
-    splitk_reduce_kernel<<<(unsigned)cdiv64(M, rpb), 256, 0, st>>>(g, a, Z, rpb);
+    launch_pdl(splitk_reduce_kernel, dim3((unsigned)cdiv64(M, rpb)), dim3(256), 0, st, g, a, Z, rpb);
     SAG_LAUNCH_CHECK();
   }
   return SAG_OK;

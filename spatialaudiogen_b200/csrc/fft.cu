@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, 
   extern __shared__ __align__(16) float2 smem[];
   float2* buf0 = smem;
   float2* buf1 = smem + p.n;
+  pdl_prologue();
   const int f = fbase + blockIdx.x;
   const int row = blockIdx.y;
   const float* xr = x + (int64_t)row * n_samples + (int64_t)f * hop;
@@ -111,8 +112,8 @@ int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int 
   size_t smem = 2 * sizeof(float2) * wind;
   if (smem > 48 * 1024) SAG_CHECK_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(hi - lo, rows);
-  stft_kernel<<<grid, 256, smem, st>>>(x, n_samples, hop, p, lo, frame0, n_frames_out, reinterpret_cast<float2*>(cplx_out),
-                                      mag0, n_mag, mag_out);
+  launch_pdl(stft_kernel, grid, dim3(256), smem, st, x, n_samples, hop, p, lo, frame0, n_frames_out, reinterpret_cast<float2*>(cplx_out),
+             mag0, n_mag, mag_out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256, REG_OLA ? 3 : 1) istft_pair_kernel(const 
   float* ola_a = reinterpret_cast<float*>(smem + 2 * nfr * n);
   float* ola_b = ola_a + n_out;
   float ra[ISTFT_SLOTS], rb[ISTFT_SLOTS];
+  pdl_prologue();
   const int pairs = (tracks + 1) / 2;
   const int64_t row = blockIdx.x / pairs;
   const int ka = (int)(blockIdx.x % pairs) * 2, kb = ka + 1;
@@ -271,12 +273,12 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
   const int pairs = (tracks + 1) / 2;
   if (reg_ola) {
     SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    istft_pair_kernel<true><<<rows_s * pairs, 256, smem, st>>>(reinterpret_cast<const float2*>(S), mask, apply_sigmoid, tracks,
-                                                             n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
+    launch_pdl(istft_pair_kernel<true>, dim3(rows_s * pairs), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
+               tracks, n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
   } else {
     SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    istft_pair_kernel<false><<<rows_s * pairs, 256, smem, st>>>(reinterpret_cast<const float2*>(S), mask, apply_sigmoid, tracks,
-                                                              n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
+    launch_pdl(istft_pair_kernel<false>, dim3(rows_s * pairs), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
+               tracks, n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
   }
   SAG_LAUNCH_CHECK();
   return SAG_OK;

@@ -20,6 +20,11 @@ const char* last_error_cstr() { return g_err.c_str(); }
 
 thread_local Profiler* g_prof = nullptr;
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("SAG_PDL"); return v == nullptr || atoi(v) != 0; }();
+  return on;
+}
+
 void Profiler::clear() {
   for (auto& r : recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   recs.clear();

@@ -67,6 +67,7 @@ __global__ void bn_apply_stats_kernel(const float4* __restrict__ x, const BnStat
   extern __shared__ float s_ss[];
   float* s_scale = s_ss;
   float* s_shift = s_ss + c;
+  pdl_prologue();
   bn_scale_shift_to_smem(bn, c, s_scale, s_shift);
   const int c4 = c / 4;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -94,8 +95,8 @@ int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& resi
   int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  bn_apply_stats_kernel<<<(unsigned)blocks, 256, 2 * c * sizeof(float), st>>>(reinterpret_cast<const float4*>(x), bn, residual, relu,
-                                                                             y, n4, c);
+  launch_pdl(bn_apply_stats_kernel, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, reinterpret_cast<const float4*>(x), bn,
+             residual, relu, y, n4, c);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -144,6 +145,7 @@ __global__ void bn_relu_maxpool_stats_kernel(const float* __restrict__ x, const 
   extern __shared__ float s_ss[];
   float* s_scale = s_ss;
   float* s_shift = s_ss + c;
+  pdl_prologue();
   bn_scale_shift_to_smem(bn, c, s_scale, s_shift);
   int c4 = c / 4;
   int64_t total = (int64_t)n * oh * ow * c4;
@@ -184,7 +186,7 @@ int launch_bn_relu_maxpool_stats(const float* x, const BnStats& bn, int n, int h
   int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  bn_relu_maxpool_stats_kernel<<<(unsigned)blocks, 256, 2 * c * sizeof(float), st>>>(x, bn, n, h, w, c, oh, ow, pt, pl, y);
+  launch_pdl(bn_relu_maxpool_stats_kernel, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, x, bn, n, h, w, c, oh, ow, pt, pl, y);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -259,6 +261,7 @@ int launch_act_to_f32(const ActView& src, float* dst, int64_t n, cudaStream_t st
 template <class T>
 __global__ void tile_rows_kernel(const T* __restrict__ src, int64_t src_ld, T* __restrict__ dst, int64_t dst_ld, int groups,
                                  int reps, int c) {
+  pdl_prologue();
   int64_t total = (int64_t)groups * reps * c;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -278,14 +281,14 @@ int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int
   int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (src.fmt == ACT_F32) {
-    tile_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src.p), src_ld,
-                                                             reinterpret_cast<float*>(dst.p), dst_ld, groups, reps, c);
+    launch_pdl(tile_rows_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const float*>(src.p), src_ld,
+               reinterpret_cast<float*>(dst.p), dst_ld, groups, reps, c);
     SAG_LAUNCH_CHECK();
   } else {
     for (int pl = 0; pl < (src.plane != 0 ? 2 : 1); ++pl) {
-      tile_rows_kernel<unsigned short><<<(unsigned)blocks, 256, 0, st>>>(
-          reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(src.p) + pl * src.plane), src_ld,
-          reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(dst.p) + pl * dst.plane), dst_ld, groups, reps, c);
+      launch_pdl(tile_rows_kernel<unsigned short>, dim3((unsigned)blocks), dim3(256), 0, st,
+                 reinterpret_cast<const unsigned short*>(reinterpret_cast<const char*>(src.p) + pl * src.plane), src_ld,
+                 reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(dst.p) + pl * dst.plane), dst_ld, groups, reps, c);
       SAG_LAUNCH_CHECK();
     }
   }
@@ -298,6 +301,7 @@ int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int
 __global__ void mix_kernel(const float* __restrict__ x_sep, const float* __restrict__ loc, int tracks, int t,
                            int segments, float* __restrict__ out) {
   extern __shared__ float s_loc[];   // [3*(tracks+1)]
+  pdl_prologue();
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * blockDim.x;
   const int seg_len = t / segments;
@@ -335,7 +339,7 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
   SAG_REQUIRE(segments > 0 && t % segments == 0, SAG_EINVAL, "mix: %d samples not divisible into %d segments", t, segments);
   int threads = 64;
   dim3 grid(cdiv(t, threads), batch);
-  mix_kernel<<<grid, threads, 3 * (tracks + 1) * sizeof(float), st>>>(x_sep, loc, tracks, t, segments, out);
+  launch_pdl(mix_kernel, grid, dim3(threads), 3 * (tracks + 1) * sizeof(float), st, x_sep, loc, tracks, t, segments, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -343,6 +347,7 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
 // ---- (n,h,w,3) -> zero-bordered (n,hp,wp,4): one float4 store per output pixel ----
 __global__ void pad_nhwc3_to_nhwc4_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int hp, int wp,
                                           const ActView out) {
+  pdl_prologue();
   const int64_t total = (int64_t)n * hp * wp;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -366,7 +371,7 @@ int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int p
   int64_t blocks = cdiv64(total, 256);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  pad_nhwc3_to_nhwc4_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, h, w, pt, pl, hp, wp, out);
+  launch_pdl(pad_nhwc3_to_nhwc4_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, hp, wp, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
