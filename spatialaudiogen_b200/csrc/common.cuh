@@ -104,6 +104,7 @@ constexpr int kMaxTaps = 112;
 struct GatherGeom {
   int N, H, W, Cin;       // input tensor
   int64_t x_ld;           // input pixel stride (elements); input channel offset folded into pointer
+  int64_t x_row;          // elements between image rows (0: W * x_ld); tcgen05 path only -- lets pixels overlap (x_ld < Cin)
   int PH, PW;             // iteration grid
   int isy, isx;           // input step per grid step
   int oy0, ox0, osy, osx; // output placement
@@ -154,9 +155,9 @@ int umma_tile_width(int K, int N, int64_t M);
 // wk: device fp32 [K][N] with row stride ldw (conv HWIO / FC [in,out] are already in this form); M: rows of the GEMM
 // the image will be used for (selects the tile width)
 int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
-// conv weights HWIO zero-extended to kw2 taps per row and cin2 channels (convolution over a zero-padded NHWC4 image)
-int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
-                            int64_t M, UmmaWeights* out, cudaStream_t st);
+// stride-2 conv weights HWIO re-expressed for the 2x2 space-to-depth image with 16-channel pixels (K = ceil(kh/2)*ceil(kw/2)*16)
+int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, UmmaWeights* out,
+                       cudaStream_t st);
 // w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
                      int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
@@ -214,9 +215,10 @@ int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int
                      cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
                cudaStream_t st);
-// (n,h,w,3) -> (n,hp,wp,4): image at offset (pt,pl), zeros elsewhere (explicit TF-SAME border + 4th channel)
-int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, const ActView& out,
-                              cudaStream_t st);
+// (n,h,w,c<=4) fp32 -> 2x2 space-to-depth of the image placed at (pt,pl) inside a zero canvas: (n,h2,w2,16) with channel
+// (py*2+px)*c + ch = canvas[2*y2+py][2*x2+px][ch], zero beyond 4*c
+int launch_space_to_depth16(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
+                            cudaStream_t st);
 int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st);
 
 // fft.cu

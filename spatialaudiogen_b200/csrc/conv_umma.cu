@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
-  constexpr int EW = SRC == SRC_TMA ? 8 : 4;   // epilogue warps (see the epilogue role)
+  constexpr bool TMA_ANY = SRC == SRC_TMA;
+  constexpr int EW = TMA_ANY ? 8 : 4;         // epilogue warps (see the epilogue role)
   constexpr bool CONCAT = NSPLIT == 2;        // A_hi x [B_hi | B_lo] as one MMA of width 2*BN, then A_lo x B_hi
   constexpr int B_PLANE = BN * 128;
   constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
@@ -348,7 +349,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         // every producer thread + the expect_tx arrival of the B copy; TMA gather: the expect_tx arrival alone
-        mbar_init(bar_full + 8 * s, SRC == SRC_TMA ? 1 : UM_PRODUCER_WARPS * 32 + 1);
+        mbar_init(bar_full + 8 * s, TMA_ANY ? 1 : UM_PRODUCER_WARPS * 32 + 1);
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -381,7 +382,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     z = (int)(r / NT);
   };
 
-  if (SRC == SRC_TMA && warp < 4) {
+  if (TMA_ANY && warp < 4) {
     // ================================ producer (TMA im2col): warp 0, one elected lane (warps 1-3 idle) ================================
     if (warp == 0) {
       int stage = 0;
@@ -403,14 +404,16 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           if (a.trace) { tr_wait += clock64() - tr_w0; ++tr_chunks; }
           if (elect_one()) {
             const int kk = kc * UM_BK;
-            const int t = kk / g.Cin;
-            const int ci0 = kk - t * g.Cin;
-            const uint16_t ow = (uint16_t)(g.dx[t] - a.tma_w0), oh = (uint16_t)(g.dy[t] - a.tma_h0);
             const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
             const uint32_t bar = bar_full + 8 * stage;
             mbar_arrive_expect_tx(bar, PLANES * (UM_A_PLANE + B_PLANE));
-            tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
-            if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
+            {
+              const int t = kk / g.Cin;
+              const int ci0 = kk - t * g.Cin;
+              const uint16_t ow = (uint16_t)(g.dx[t] - a.tma_w0), oh = (uint16_t)(g.dy[t] - a.tma_h0);
+              tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
+              if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
+            }
             bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
                      PLANES * B_PLANE, bar);
           }
@@ -424,9 +427,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 6] = tr_chunks;
       }
     }
-  } else if (SRC != SRC_TMA && warp < UM_PRODUCER_WARPS) {
+  } else if (!TMA_ANY && warp < UM_PRODUCER_WARPS) {
     // ================================ producers ================================
     const int jchunk = tid & 7;                 // which 8-element (16-byte bf16) group of the 64-wide K chunk
+    const int64_t x_row = g.x_row != 0 ? g.x_row : (int64_t)g.W * g.x_ld;      // elements between image rows
     int stage = 0;
     uint32_t phase = 0;
     long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
@@ -450,7 +454,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
           iy0[it] = (int)i * g.isy;
           ix0[it] = (int)j * g.isx;
-          img[it] = (int64_t)n * g.H * g.W * g.x_ld;
+          img[it] = (int64_t)n * g.H * x_row;
         }
       }
 #pragma unroll 1
@@ -470,7 +474,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
             const int iy = iy0[it] + dy, ix = ix0[it] + dx;
             float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
             if (kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) {
-              const float4* p = reinterpret_cast<const float4*>(xf + img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci0);
+              const float4* p = reinterpret_cast<const float4*>(xf + img[it] + ((int64_t)iy * x_row + (int64_t)ix * g.x_ld) + ci0);
               v0 = __ldg(p);
               v1 = __ldg(p + 1);
             }
@@ -488,7 +492,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
               if (rok[it] && kk + e < a.K) {
                 const int iy = iy0[it] + g.dy[tt], ix = ix0[it] + g.dx[tt];
                 if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W)
-                  v = __ldg(xf + img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci);
+                  v = __ldg(xf + img[it] + ((int64_t)iy * x_row + (int64_t)ix * g.x_ld) + ci);
               }
               f[it][e] = v;
               if (++ci == g.Cin) { ci = 0; ++tt; }
@@ -524,7 +528,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
             const uint32_t off = (uint32_t)r * 128u + (uint32_t)((jchunk ^ (r & 7)) << 4);
             const int iy = iy0[it] + dy, ix = ix0[it] + dx;
             const bool ok = kok && rok[it] && (unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W;
-            const char* src = ok ? xhi + 2 * (img[it] + ((int64_t)iy * g.W + ix) * g.x_ld + ci0) : xhi;
+            const char* src = ok ? xhi + 2 * (img[it] + ((int64_t)iy * x_row + (int64_t)ix * g.x_ld) + ci0) : xhi;
             cp_async16(st_base + off, src, ok ? 16u : 0u);
             if (PLANES == 2) cp_async16(st_base + UM_A_PLANE + off, src + (ok ? a.x_plane : 0), ok ? 16u : 0u);
           }
@@ -589,16 +593,17 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           if (elect_one()) {
 #pragma unroll
             for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
+              const uint64_t xa_hi = da_hi + 2 * k4, xa_lo = da_lo + 2 * k4;   // 32 bytes further inside the swizzle atom
               if (CONCAT) {
                 // the lo plane of B follows its hi plane in the stage: one 2*BN-wide MMA yields [A_hi.B_hi | A_hi.B_lo]
                 // in adjacent accumulator blocks (summed by the epilogue); A_lo.B_hi lands on the first block
-                umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC2, (kc > kc_begin || k4 > 0) ? 1u : 0u);
-                umma_bf16(tmem_acc, da_lo + 2 * k4, db_hi + 2 * k4, IDESC, 1u);
+                umma_bf16(tmem_acc, xa_hi, db_hi + 2 * k4, IDESC2, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+                umma_bf16(tmem_acc, xa_lo, db_hi + 2 * k4, IDESC, 1u);
               } else {
-                umma_bf16(tmem_acc, da_hi + 2 * k4, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+                umma_bf16(tmem_acc, xa_hi, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
                 if (NSPLIT == 3) {
-                  umma_bf16(tmem_acc, da_lo + 2 * k4, db_hi + 2 * k4, IDESC, 1u);
-                  umma_bf16(tmem_acc, da_hi + 2 * k4, db_lo + 2 * k4, IDESC, 1u);
+                  umma_bf16(tmem_acc, xa_lo, db_hi + 2 * k4, IDESC, 1u);
+                  umma_bf16(tmem_acc, xa_hi, db_lo + 2 * k4, IDESC, 1u);
                 }
               }
             }
@@ -615,7 +620,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 7] = tr_wacc;
       }
     }
-  } else if (warp >= UM_EPI_WARP0 || (SRC == SRC_TMA && warp >= 4)) {
+  } else if (warp >= UM_EPI_WARP0 || (TMA_ANY && warp >= 4)) {
     // ================================ epilogue ================================
     // EW warps: 4 (one per TMEM lane quadrant) next to the cp.async producers; 8 when the TMA unit gathers and warps 4-7
     // are free: two warps per quadrant, each draining half of the columns of a pass.  The pass is latency bound
@@ -929,18 +934,26 @@ __global__ void subpixel_weights_kernel(const float* __restrict__ w, int kh, int
   }
 }
 
-// HWIO conv weights [kh][kw][cin][cout] -> [kh][kw2][cin2][cout] with zeros in the added taps / channels
-__global__ void expand_hwio_kernel(const float* __restrict__ w, int kh, int kw, int cin, int cout, int kw2, int cin2,
+// HWIO weights of a stride-2 convolution over C channels -> weights of the equivalent stride-1 convolution over the 2x2
+// space-to-depth image with 16 channels per pixel (channel (py*2+px)*C + c, zero beyond 4*C):
+//   out[(a*tw + b)*16 + ch][co] = w[2a+py][2b+px][c][co]   (zero when the kernel index falls outside kh x kw)
+__global__ void s2d_weights_kernel(const float* __restrict__ w, int kh, int kw, int cin, int cout, int th, int tw,
                                    float* __restrict__ out) {
-  const int64_t total = (int64_t)kh * kw2 * cin2 * cout;
+  const int64_t total = (int64_t)th * tw * 16 * cout;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
     const int co = (int)(idx % cout);
     int64_t r = idx / cout;
-    const int c = (int)(r % cin2); r /= cin2;
-    const int sx = (int)(r % kw2);
-    const int ry = (int)(r / kw2);
-    out[idx] = (c < cin && sx < kw) ? __ldg(w + (((int64_t)ry * kw + sx) * cin + c) * cout + co) : 0.f;
+    const int ch = (int)(r % 16); r /= 16;
+    const int b = (int)(r % tw);
+    const int a = (int)(r / tw);
+    float v = 0.f;
+    if (ch < 4 * cin) {
+      const int sub = ch / cin, c = ch - sub * cin;
+      const int ky = 2 * a + (sub >> 1), kx = 2 * b + (sub & 1);
+      if (ky < kh && kx < kw) v = __ldg(w + (((int64_t)ky * kw + kx) * cin + c) * cout + co);
+    }
+    out[idx] = v;
   }
 }
 
@@ -1303,15 +1316,17 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   return SAG_OK;
 }
 
-int umma_pack_conv_expanded(const float* w_hwio, int kh, int kw, int cin, int cout, int kw2, int cin2, int precision,
-                            int64_t M, UmmaWeights* out, cudaStream_t st) {
+int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, UmmaWeights* out,
+                       cudaStream_t st) {
+  SAG_REQUIRE(4 * cin <= 16, SAG_EUNSUPPORTED, "space-to-depth route: %d input channels do not fit 16-channel pixels", cin);
+  const int th = (kh + 1) / 2, tw = (kw + 1) / 2;
   float* wk = nullptr;
-  const int64_t total = (int64_t)kh * kw2 * cin2 * cout;
+  const int64_t total = (int64_t)th * tw * 16 * cout;
   SAG_CHECK_CUDA(cudaMalloc(&wk, sizeof(float) * (size_t)total));
   int64_t blocks = cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  expand_hwio_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, kw2, cin2, wk);
-  int r = umma_pack_weights(wk, kh * kw2 * cin2, cout, cout, precision, M, out, st);
+  s2d_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, th, tw, wk);
+  int r = umma_pack_weights(wk, th * tw * 16, cout, cout, precision, M, out, st);
   cudaStreamSynchronize(st);
   cudaFree(wk);
   return r;
@@ -1438,7 +1453,8 @@ static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm,
   if (mindx < -128 || mindx > 127 || mindy < -128 || mindy > 127 || up_w < -128 || up_w > 127 || up_h < -128 || up_h > 127) return false;
   if (maxdx - mindx > 255 || maxdy - mindy > 255 || g.isx < 1 || g.isx > 8 || g.isy < 1 || g.isy > 8) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-  const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, (cuuint64_t)g.W * g.x_ld * 2, (cuuint64_t)g.H * g.W * g.x_ld * 2};
+  const cuuint64_t x_row = g.x_row != 0 ? (cuuint64_t)g.x_row : (cuuint64_t)g.W * g.x_ld;
+  const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, x_row * 2, (cuuint64_t)g.H * x_row * 2};
   const int lower[2] = {mindx, mindy}, upper[2] = {up_w, up_h};
   const cuuint32_t estr[4] = {1, (cuuint32_t)g.isx, (cuuint32_t)g.isy, 1};
   static int driver = -1;
@@ -1488,7 +1504,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   // vector gather: every 8-element K group is one tap's 8 contiguous, 16-byte aligned elements
   const int elt = x.fmt == ACT_BF2 ? 8 : 4;     // elements per 16 bytes
-  bool vec = (g.Cin % 8 == 0) && ((g.x_ld * g.isx) % elt == 0) && ((g.x_ld * g.W) % elt == 0) &&
+  bool vec = (g.Cin % 8 == 0) && ((g.x_ld * g.isx) % elt == 0) && ((g.x_row != 0 ? g.x_row : g.x_ld * g.W) % elt == 0) &&
              ((reinterpret_cast<uintptr_t>(x.p) & 15) == 0) && (x.plane & 15) == 0;
   for (int t = 0; t < g.T && vec; ++t) vec = (g.dx[t] * g.x_ld) % elt == 0;
   int src = vec ? SRC_F32_VEC : SRC_F32;

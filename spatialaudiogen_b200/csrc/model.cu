@@ -358,18 +358,20 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   if (!f.tc()) {
     SAG_TRY(f.conv(Act(x, 3), B, H, Wd, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, b1.sum, b1.sqs, &oh, &ow));
   } else {
-    // tensor-core route: explicit TF-SAME border + a zero 4th channel (NHWC4), kernel rows widened to 8 taps so that
-    // one row = 8 pixels x 4 channels = 32 contiguous, 16-byte aligned elements -> 7 taps of 32 "channels" (K = 224)
+    // tensor-core route: the stride-2 7x7 convolution over 3 channels becomes a stride-1 4x4 convolution over the 2x2
+    // space-to-depth image of the explicitly TF-SAME padded frame, 12 (+4 zero) channels per pixel = 32 bytes.  The four
+    // taps of a kernel row are four neighbouring pixels = 128 contiguous bytes, so the gather sees 64-channel pixels
+    // that overlap (pixel stride 16 channels): 4 taps (kernel rows) x 64 channels, K = 256, one 64-wide chunk per row
     int pt = same_pad_before(H, 7, 2, &oh), pl = same_pad_before(Wd, 7, 2, &ow);
-    const int Hp = (oh - 1) * 2 + 7, Wp = (((ow - 1) * 2 + 8) + 3) / 4 * 4;
-    Act xp = f.alloc_act((int64_t)B * Hp * Wp, 4);
+    const int H2 = oh + 3, W2 = ow + 3;                     // rows / columns of the space-to-depth image a 4x4 window needs
+    Act xp = f.alloc_act((int64_t)B * H2 * W2, 16);
     GatherGeom g;
     memset(&g, 0, sizeof(g));
-    g.N = B; g.H = Hp; g.W = Wp; g.Cin = 32; g.x_ld = 4;
-    g.PH = oh; g.PW = ow; g.isy = 2; g.isx = 2;
+    g.N = B; g.H = H2; g.W = ow; g.Cin = 64; g.x_ld = 16; g.x_row = (int64_t)W2 * 16;
+    g.PH = oh; g.PW = ow; g.isy = 1; g.isx = 1;
     g.osy = 1; g.osx = 1; g.y_sc = 1; g.y_sw = 64; g.y_sh = (int64_t)ow * 64; g.y_sn = (int64_t)oh * ow * 64;
-    g.Cout = 64; g.T = 7;
-    for (int r = 0; r < 7; ++r) { g.dy[r] = (short)r; g.dx[r] = 0; g.widx[r] = (short)r; }
+    g.Cout = 64; g.T = 4;
+    for (int t = 0; t < 4; ++t) { g.dy[t] = (short)t; g.dx[t] = 0; g.widx[t] = (short)t; }
     float* scratch = f.splitk(g.T * g.Cin, 64, (int64_t)B * oh * ow);
     if (!ar.dry) {
       const float* w = f.W(p + "conv1/conv/weights", &err);
@@ -379,15 +381,15 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
       auto it = h->umma.find(key);
       if (it == h->umma.end()) {
         UmmaWeights uw;
-        SAG_TRY(umma_pack_conv_expanded(w, 7, 7, 3, 64, 8, 4, f.prec, Mrows, &uw, st));
+        SAG_TRY(umma_pack_conv_s2d(w, 7, 7, 3, 64, f.prec, Mrows, &uw, st));
         it = h->umma.emplace(key, uw).first;
       }
       {
-        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * (double)H * Wd * 3 + act_b * B * (double)Hp * Wp * 4, st);
-        SAG_TRY(launch_pad_nhwc3_to_nhwc4(x, B, H, Wd, pt, pl, Hp, Wp, xp.v, st));
+        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * (double)H * Wd * 3 + act_b * B * (double)H2 * W2 * 16, st);
+        SAG_TRY(launch_space_to_depth16(x, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
       }
       Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
-      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)Hp * Wp * 4 + 4.0 * B * (double)oh * ow * 64, st);
+      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)H2 * W2 * 16 + 4.0 * B * (double)oh * ow * 64, st);
       SAG_TRY(launch_gather_gemm_umma(xp.v, it->second, c1.v, g, ep, 0, 0, scratch, st));
     }
   }

@@ -344,37 +344,52 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
   return SAG_OK;
 }
 
-// ---- (n,h,w,3) -> zero-bordered (n,hp,wp,4): one float4 store per output pixel ----
-__global__ void pad_nhwc3_to_nhwc4_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int hp, int wp,
-                                          const ActView out) {
+// ---- (n,h,w,c) -> 2x2 space-to-depth of the zero-bordered image, 16 channels per pixel ----
+template <int C>
+__global__ void space_to_depth16_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int h2, int w2,
+                                        const ActView out) {
   pdl_prologue();
-  const int64_t total = (int64_t)n * hp * wp;
+  const int64_t total = (int64_t)n * h2 * w2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int px = (int)(i % wp);
-    const int64_t r = i / wp;
-    const int py = (int)(r % hp);
-    const int b = (int)(r / hp);
-    const int iy = py - pt, ix = px - pl;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w) {
-      const float* p = x + (((int64_t)b * h + iy) * w + ix) * 3;
-      v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    const int x2 = (int)(i % w2);
+    const int64_t r = i / w2;
+    const int y2 = (int)(r % h2);
+    const int b = (int)(r / h2);
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int iy = 2 * y2 + (sub >> 1) - pt, ix = 2 * x2 + (sub & 1) - pl;
+      if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w) {
+        const float* p = x + (((int64_t)b * h + iy) * w + ix) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) v[sub * C + ch] = __ldg(p + ch);
+      }
     }
-    store_act4(out.p, out.fmt, out.plane, i * 4, v);
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) store_act4(out.p, out.fmt, out.plane, i * 16 + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
   }
 }
 
-int launch_pad_nhwc3_to_nhwc4(const float* x, int n, int h, int w, int pt, int pl, int hp, int wp, const ActView& out,
-                              cudaStream_t st) {
-  const int64_t total = (int64_t)n * hp * wp;
+int launch_space_to_depth16(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
+                            cudaStream_t st) {
+  SAG_REQUIRE(c >= 1 && 4 * c <= 16, SAG_EINVAL, "space_to_depth16: %d channels", c);
+  const int64_t total = (int64_t)n * h2 * w2;
   int64_t blocks = cdiv64(total, 256);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  launch_pdl(pad_nhwc3_to_nhwc4_kernel, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, hp, wp, out);
+  switch (c) {
+    case 1: launch_pdl(space_to_depth16_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
+    case 2: launch_pdl(space_to_depth16_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
+    case 3: launch_pdl(space_to_depth16_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
+    default: launch_pdl(space_to_depth16_kernel<4>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
+  }
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
+
 
 // ---- tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin] (core.py:118) -> per-tap [Cin][Cout] slabs ----
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, float* __restrict__ out, int taps, int cout, int cin) {
