@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed building libsag.so')
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ARCH + ['-lcuda']
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ARCH
     subprocess.check_call(cmd)
     return LIB
 

@@ -1441,6 +1441,22 @@ thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: for
 // im2col tensor maps over the two bf16 planes of an NHWC activation for the geometry's taps (reference for the
 // corner arithmetic: base pixel of output (i, j) = (i*isy + min dy, j*isx + min dx); the box's upper corner is chosen so
 // that exactly PW x PH base pixels fit).  Returns false when the layer does not fit the TMA unit's limits.
+// cuTensorMapEncodeIm2col through the runtime's driver entry point lookup: libsag.so carries no link-time dependency
+// on libcuda.so (it must load -- and report "no device" -- on machines without a driver)
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeIm2colFn>(p);
+  }();
+  return fn;
+}
+
 static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm, int* w0, int* h0) {
   if (x.fmt != ACT_BF2 || g.Cin % UM_BK != 0 || g.x_ld % 8 != 0 || g.T < 1) return false;
   if ((reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return false;
@@ -1459,10 +1475,12 @@ static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm,
   const cuuint32_t estr[4] = {1, (cuuint32_t)g.isx, (cuuint32_t)g.isy, 1};
   static int driver = -1;
   if (driver < 0) cudaDriverGetVersion(&driver);
+  const EncodeIm2colFn encode = encode_im2col_fn();
+  if (encode == nullptr) return false;
   for (int pl = 0; pl < (x.plane != 0 ? 2 : 1); ++pl) {
     CUtensorMap* m = pl == 0 ? &tm->hi : &tm->lo;
     void* base = reinterpret_cast<char*>(x.p) + (pl == 0 ? 0 : x.plane);
-    CUresult r = cuTensorMapEncodeIm2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper,
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, lower, upper,
                                          (cuuint32_t)UM_BK, (cuuint32_t)UM_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
