@@ -126,32 +126,34 @@ int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int 
 // sigmoid evaluated, exactly once.  Frame-space position of output sample j is j + (n_overlap-1)*hop
 // (myutils.py:198-205); each thread owns output positions, so the overlap-add needs no atomics.
 constexpr int ISTFT_NFR = 4;
-constexpr int ISTFT_SLOTS = 19;            // register overlap-add: output positions tid + 256*s, s < 19 (n_out <= 4864)
-// REG_OLA: the overlap-add accumulators live in registers (each thread owns positions tid + 256*s), which frees
-// 2*n_out*4 bytes of shared memory per CTA -> three CTAs per SM instead of two hide the mask-load latency better.
-template <bool REG_OLA>
-__global__ void __launch_bounds__(256, REG_OLA ? 3 : 1) istft_pair_kernel(const float2* __restrict__ S, const float* __restrict__ mask,
+constexpr int ISTFT_SLOTS = 10;            // register overlap-add: output positions tid + 256*s, s < 10 -> segments of 2560 samples
+constexpr int ISTFT_SEG = 256 * ISTFT_SLOTS;
+// The output range is cut into segments of ISTFT_SEG samples (blockIdx.y), each with its own frame range: twice the
+// CTAs of half the length fill the SMs' CTA slots evenly (512 long CTAs over 444 slots left the second wave 15 % full),
+// and the shorter accumulator arrays free registers for a fourth CTA per SM.
+// The overlap-add accumulators live in registers (each thread owns positions tid + 256*s of its segment).
+__global__ void __launch_bounds__(256, 4) istft_pair_kernel(const float2* __restrict__ S, const float* __restrict__ mask,
                                                          int apply_sigmoid, int tracks, int n_frames, const FftPlan p,
-                                                         int hop, int f_lo, int f_hi, int p0, int n_out, float inv_scale,
+                                                         int hop, int nf_total, int p0_all, int n_out_all, float inv_scale,
                                                          int nfr, float* __restrict__ out) {
   extern __shared__ __align__(16) float2 smem[];
   const int n = p.n;
   float2* buf0 = smem;
   float2* buf1 = smem + nfr * n;
-  float* ola_a = reinterpret_cast<float*>(smem + 2 * nfr * n);
-  float* ola_b = ola_a + n_out;
   float ra[ISTFT_SLOTS], rb[ISTFT_SLOTS];
   pdl_prologue();
+  // this CTA's segment of the output and the frames that reach it
+  const int seg0 = (int)blockIdx.y * ISTFT_SEG;
+  const int n_out = min(ISTFT_SEG, n_out_all - seg0);
+  const int p0 = p0_all + seg0;
+  int f_lo = p0 - n + 1 <= 0 ? 0 : (p0 - n + 1 + hop - 1) / hop;
+  int f_hi = min((p0 + n_out - 1) / hop, nf_total - 1);
   const int pairs = (tracks + 1) / 2;
   const int64_t row = blockIdx.x / pairs;
   const int ka = (int)(blockIdx.x % pairs) * 2, kb = ka + 1;
   const bool has_b = kb < tracks;
-  if (REG_OLA) {
 #pragma unroll
-    for (int sl = 0; sl < ISTFT_SLOTS; ++sl) { ra[sl] = 0.f; rb[sl] = 0.f; }
-  } else {
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x) { ola_a[i] = 0.f; ola_b[i] = 0.f; }
-  }
+  for (int sl = 0; sl < ISTFT_SLOTS; ++sl) { ra[sl] = 0.f; rb[sl] = 0.f; }
   const float* ma = mask != nullptr ? mask + (row * tracks + ka) * (int64_t)n_frames * n : nullptr;
   const float* mb = (mask != nullptr && has_b) ? mask + (row * tracks + kb) * (int64_t)n_frames * n : nullptr;
   for (int f0 = f_lo; f0 <= f_hi; f0 += nfr) {
@@ -201,48 +203,29 @@ __global__ void __launch_bounds__(256, REG_OLA ? 3 : 1) istft_pair_kernel(const 
     }
     const float2* res = block_fft_nf(buf0, buf1, p, nf);     // res = N * (y_a - i y_b)
     const int lo = max(f0 * hop - p0, 0), hi = min((f0 + nf - 1) * hop - p0 + n, n_out);
-    if (REG_OLA) {
 #pragma unroll
-      for (int sl = 0; sl < ISTFT_SLOTS; ++sl) {
-        const int j = threadIdx.x + 256 * sl;
-        if (j >= lo && j < hi) {
-          float aa = 0.f, ab = 0.f;
-          for (int g = 0; g < nf; ++g) {
-            const int i = j - ((f0 + g) * hop - p0);
-            if (i >= 0 && i < n) { const float2 r = res[g * n + i]; aa += r.x; ab -= r.y; }
-          }
-          ra[sl] += aa;
-          rb[sl] += ab;
-        }
-      }
-    } else {
-      for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    for (int sl = 0; sl < ISTFT_SLOTS; ++sl) {
+      const int j = threadIdx.x + 256 * sl;
+      if (j >= lo && j < hi) {
         float aa = 0.f, ab = 0.f;
         for (int g = 0; g < nf; ++g) {
           const int i = j - ((f0 + g) * hop - p0);
           if (i >= 0 && i < n) { const float2 r = res[g * n + i]; aa += r.x; ab -= r.y; }
         }
-        ola_a[j] += aa;
-        ola_b[j] += ab;
+        ra[sl] += aa;
+        rb[sl] += ab;
       }
     }
   }
-  float* oa = out + (row * tracks + ka) * (int64_t)n_out;
-  float* ob = out + (row * tracks + kb) * (int64_t)n_out;
-  if (REG_OLA) {
+  float* oa = out + (row * tracks + ka) * (int64_t)n_out_all + seg0;
+  float* ob = out + (row * tracks + kb) * (int64_t)n_out_all + seg0;
 #pragma unroll
-    for (int sl = 0; sl < ISTFT_SLOTS; ++sl) {
-      const int j = threadIdx.x + 256 * sl;
-      if (j < n_out) {
-        oa[j] = ra[sl] * inv_scale;
-        if (has_b) ob[j] = rb[sl] * inv_scale;
-      }
+  for (int sl = 0; sl < ISTFT_SLOTS; ++sl) {
+    const int j = threadIdx.x + 256 * sl;
+    if (j < n_out) {
+      oa[j] = ra[sl] * inv_scale;
+      if (has_b) ob[j] = rb[sl] * inv_scale;
     }
-  } else {
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x) oa[i] = ola_a[i] * inv_scale;
-    if (has_b)
-      for (int i = threadIdx.x; i < n_out; i += blockDim.x) ob[i] = ola_b[i] * inv_scale;
   }
 }
 
@@ -256,30 +239,20 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
               "istft: crop [%d,%d) outside the %d output samples", crop0, crop0 + n_out, full);
   FftPlan p;
   SAG_TRY(get_plan(wind, &p));
-  const int p0 = crop0 + (n_overlap - 1) * hop, p1 = p0 + n_out;
-  int f_lo = (p0 - wind + 1 + hop - 1) / hop;
-  if (p0 - wind + 1 <= 0) f_lo = 0;
-  int f_hi = (p1 - 1) / hop;
-  if (f_hi > nf - 1) f_hi = nf - 1;
-  const bool reg_ola = n_out <= 256 * ISTFT_SLOTS;
+  const int p0 = crop0 + (n_overlap - 1) * hop;
+  const int n_seg = cdiv(n_out, ISTFT_SEG);
   int nfr = ISTFT_NFR;
   size_t smem = 0;
   for (; nfr >= 1; nfr >>= 1) {
-    smem = 2 * sizeof(float2) * (size_t)wind * nfr + (reg_ola ? 0 : 2 * sizeof(float) * (size_t)n_out);
-    if (smem <= 110 * 1024 || nfr == 1) break;             // at least two CTAs per SM when possible
+    smem = 2 * sizeof(float2) * (size_t)wind * nfr;
+    if (smem <= 56 * 1024 || nfr == 1) break;              // four CTAs per SM when possible
   }
   SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft: %zu bytes of shared memory needed", smem);
   const float inv_scale = 1.0f / ((float)wind * (float)n_overlap);
   const int pairs = (tracks + 1) / 2;
-  if (reg_ola) {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(istft_pair_kernel<true>, dim3(rows_s * pairs), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
-               tracks, n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
-  } else {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(istft_pair_kernel<false>, dim3(rows_s * pairs), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
-               tracks, n_frames, p, hop, f_lo, f_hi, p0, n_out, inv_scale, nfr, out);
-  }
+  SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  launch_pdl(istft_pair_kernel, dim3(rows_s * pairs, n_seg), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
+             tracks, n_frames, p, hop, nf, p0, n_out, inv_scale, nfr, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }

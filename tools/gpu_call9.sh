@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/c9_pytest.log 2>&1
+echo "pytest exit $?"; tail -15 gpurun_out/c9_pytest.log | cut -c1-300
+SAG_PROF_DUMP=1 timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/c9_bench.json 2> gpurun_out/c9_bench.err
+python -c "import json,sys; d=json.load(open('gpurun_out/c9_bench.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['breakdown_ms_per_step'])"
