@@ -24,6 +24,25 @@ ALL_METRICS = ['amplitude/predicted', 'amplitude/gt',
                'emd/dir', 'emd/dir2']                                      # eval.py:125-132
 _COL = {k: i for i, k in enumerate(ALL_METRICS)}
 N_COLS = len(ALL_METRICS)
+# metric_rows gathers its columns from [amp_pred, amp_gt | mse, stft, lsd, snr, env x (Y,Z,X) | the 5 channel means | nan]
+_KEYS = ('mse', 'stft', 'lsd', 'snr', 'env')
+_NAMES = ('mse', 'stft', 'lsd', 'snr', 'env_mse')
+_PERM_CACHE = {}
+
+
+def _perm(device):
+    """Column gather of metric_rows: ALL_METRICS position -> position in the concatenated metric buffer (filled by key,
+    not by position, like eval.py:159-171; mel_lsd / emd columns point at the nan column)."""
+    key = str(device)
+    if key not in _PERM_CACHE:
+        src = {'amplitude/predicted': 0, 'amplitude/gt': 1}
+        for k, name in enumerate(_NAMES):
+            for i, ch in enumerate('YZX'):
+                src[name + '/' + ch] = 2 + 3 * k + i
+            src[name + '/avg'] = 2 + 3 * len(_NAMES) + k
+        nan_col = 2 + 4 * len(_NAMES)
+        _PERM_CACHE[key] = torch.tensor([src.get(m, nan_col) for m in ALL_METRICS], dtype=torch.int64, device=device)
+    return _PERM_CACHE[key]
 
 
 def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False):
@@ -32,14 +51,11 @@ def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps
     (eval.py:147-148, 190), needs `mono` (B, T, 1)."""
     res = M.window_metrics(pred, target, audio_rate)
     B = pred.shape[0]
-    rows = torch.full((B, N_COLS), float('nan'), dtype=torch.float32, device=pred.device)
-    rows[:, _COL['amplitude/predicted']] = res['amp'][:, 0]
-    rows[:, _COL['amplitude/gt']] = res['amp'][:, 1]
-    for key, name in (('mse', 'mse'), ('stft', 'stft'), ('lsd', 'lsd'), ('snr', 'snr'), ('env', 'env_mse')):
-        v = res[key]
-        rows[:, _COL[name + '/avg']] = v.mean(1)                           # np.mean / np.nanmean over the 3 channels
-        for i, ch in enumerate('YZX'):                                     # filled by key, not by position (eval.py:159-171)
-            rows[:, _COL[name + '/' + ch]] = v[:, i]
+    # four small launches instead of one per column: [amp | per-channel metrics] -> channel means -> one column gather
+    per_ch = torch.cat([res['amp']] + [res[k] for k in _KEYS], 1)          # (B, 2 + 5*3), channels in (Y, Z, X) order
+    avg = per_ch[:, 2:].reshape(B, len(_KEYS), 3).mean(2)                  # np.mean over the 3 channels (eval.py:159-171)
+    full = torch.cat((per_ch, avg, torch.full((B, 1), float('nan'), dtype=torch.float32, device=pred.device)), 1)
+    rows = full.index_select(1, _perm(pred.device))
     maps = None
     if rms_maps:
         if mono is None:
