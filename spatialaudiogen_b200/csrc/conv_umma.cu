@@ -5,25 +5,28 @@
 //   C[m, n] = sum_{t, ci} X[pixel(m) + tap t, ci] * Wk[t*Cin + ci, n]          (zero outside the image)
 //
 // Activations travel between layers as two bf16 planes (hi = bf16(x), lo = bf16(x - hi); same bytes as fp32), written
-// once by whichever kernel produces them, so the gather is a pure copy: each producer thread issues 16-byte cp.async
-// (LDGSTS, zero-filled outside the image) straight into the swizzled operand tile -- no registers, no conversion, the
-// loads of several K chunks in flight.  fp32 sources (stage entry points, first use of user inputs) take the register
+// once by whichever kernel produces them, so the gather is a pure copy.  Layers whose channel count is a multiple of 64
+// (all but the first two audio convolutions) are fed by the TMA unit in im2col mode: one thread issues, per 64-wide K
+// chunk, two cp.async.bulk.tensor.4d...im2col copies (hi / lo plane: 128 output pixels x 64 channels at the chunk's
+// filter offset, zero outside the image, landing in the swizzled operand layout) + one bulk copy of the packed weight
+// tile.  The others gather with 16-byte cp.async (LDGSTS, zero-fill); fp32 sources (stage entry points) take a register
 // path that splits on the fly.
 //
 // Persistent, warp-specialised: one CTA per SM walks the list of (M tile, N tile, K split) work items; tile = 128 x BN.
-//   warps 0-7   producers: gather the A operand into shared memory in the UMMA K-major SWIZZLE_128B canonical layout
-//               (cp.async with asynchronous mbarrier arrival); thread 0 also issues the bulk-async (TMA, cp.async.bulk)
-//               copy of the pre-packed weight tile.
-//   warps 8-11  epilogue (one per TMEM lane quadrant): tcgen05.ld of the accumulator, bias / ReLU, staging tile,
-//               coalesced row writes as fp32 / split bf16 / split-K partials, batch-norm column sums.
-//   warp 12     allocates TMEM (two accumulators) and issues tcgen05.mma kind::f16 through one elected lane:
+//   TMA gather      : warp 0 producer (one elected lane), warps 4-11 epilogue (two per TMEM lane quadrant)
+//   cp.async gather : warps 0-7 producers (asynchronous mbarrier arrival), warps 8-11 epilogue
+//   epilogue        : tcgen05.ld of the accumulator, bias / ReLU, staging tile, coalesced row writes as fp32 / split
+//                     bf16 / split-K partials, batch-norm column sums
+//   warp 12         : allocates TMEM (two accumulators) and issues tcgen05.mma kind::f16 through one elected lane:
 //               SAG_PREC_BF16   : 1 MMA per K step  (A_hi x B_hi)
-//               SAG_PREC_BF16X3 : 3 MMAs per K step (A_hi x B_hi + A_lo x B_hi + A_hi x B_lo) -> fp32-grade products
+//               SAG_PREC_BF16X3 : A_hi x B_hi + A_hi x B_lo + A_lo x B_hi -> fp32-grade products; tiles up to 128 wide
+//                                 do it with 2 MMAs (A_hi x [B_hi | B_lo] at width 2*BN, A_lo x B_hi), 256-wide with 3
 // full/empty mbarrier ring between producers and the MMA issuer, tcgen05.commit releases stages and publishes the
 // accumulator; tmem_full/tmem_empty barriers between the MMA issuer and the epilogue, so the epilogue of tile i overlaps
-// the MMAs of tile i+1.  Roofline: tensor pipe; measured limits today are the shared-memory operand reads of the
-// three-MMA scheme on narrow tiles and the L2->SM gather (each activation is re-read once per tap from L2, never
-// from HBM) -- see DESIGN.md section 3.
+// the MMAs of tile i+1.  Launched with programmatic stream serialisation: the prologue (barriers, TMEM) overlaps the
+// previous kernel's tail.  Roofline: tensor pipe; the measured limit today is the shared-memory port (operand reads of
+// the 2-3 MMAs per product + stage writes) on narrow tiles and the epilogue's global stores on small-K layers -- see
+// DESIGN.md section 3.
 #include "model.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
