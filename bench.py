@@ -31,6 +31,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the one JSON line only
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 import numpy as np
 import torch

@@ -173,6 +173,7 @@ struct ActView {
   ActView(const float* f) : p(const_cast<float*>(f)) {}
   ActView(void* q, int f, int64_t pl) : p(q), fmt(f), plane(pl) {}
 };
+extern thread_local int g_umma_pair;  // -1: SAG_UMMA_PAIR env (default off); 0/1: forced: CTA pairs (cta_group::2) on the TMA path
 extern thread_local int g_umma_tma;   // -1: SAG_UMMA_TMA env (default on); 0/1: forced for this thread's launches
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);

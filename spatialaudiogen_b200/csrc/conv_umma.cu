@@ -74,7 +74,6 @@ struct UmmaArgs {
   int NT, Z;              // N tiles, K splits
   int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
-  int cluster;            // CTAs per cluster (1 or 2): the CTAs of a cluster take adjacent M tiles and share the weight copy
 };
 // im2col tensor maps of the two activation planes (SRC_TMA); kernel parameter, read by the TMA unit
 struct alignas(64) TmaPair { CUtensorMap hi, lo; };
@@ -129,12 +128,6 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst_smem, const CUtensorM
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
-// same copy, delivered to the same CTA-relative offsets (data and mbarrier) of every CTA in `cta_mask` of the cluster
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-               : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -180,6 +173,28 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// CTA-pair variants (cta_group::2): the TMEM allocation covers both CTAs, one MMA spans M = 256 (each CTA's own 128-row
+// A tile) and reads half of the N rows of B from each CTA's shared memory, commits arrive on both CTAs' barriers
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {       // arrives on the barrier at this offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]; bf16 operands, fp32 accumulate
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -304,7 +319,7 @@ constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2, SRC_TMA = 3;
 // Persistent: one CTA per SM walks the work list (m tile, n tile, K split) with a static stride; the three roles run
 // decoupled through mbarriers, so the operand ring never drains between tiles and the epilogue of tile i overlaps the
 // MMAs of tile i+1 (two TMEM accumulators).
-template <int BN, int NSPLIT, int SRC>
+template <int BN, int NSPLIT, int SRC, bool PAIR>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
@@ -313,12 +328,21 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   constexpr int EW = TMA_ANY ? 8 : 4;         // epilogue warps (see the epilogue role)
   constexpr bool CONCAT = NSPLIT == 2;        // A_hi x [B_hi | B_lo] as one MMA of width 2*BN, then A_lo x B_hi
   constexpr int B_PLANE = BN * 128;
-  constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + B_PLANE);
+  // B rows per CTA and stage.  Alone: [B_hi | B_lo] (BN rows each).  CTA pair (each CTA feeds half of the N rows of an
+  // MMA, at the same shared-memory offset in both): block X = B_hi (rank 0) / B_lo (rank 1) for the 2*BN-wide MMA of
+  // the two-MMA scheme, block Y = this CTA's half of B_hi for the BN-wide one; three-MMA scheme: X / Y = this CTA's
+  // half of B_hi / B_lo.
+  constexpr int BX_ROWS = !PAIR ? BN : (NSPLIT == 2 ? BN : BN / 2);
+  constexpr int BY_ROWS = PLANES == 1 ? 0 : (!PAIR ? BN : BN / 2);
+  constexpr int B_BYTES = (BX_ROWS + BY_ROWS) * 128;
+  constexpr int STAGE_BYTES = PLANES * UM_A_PLANE + B_BYTES;
+  static_assert(!PAIR || SRC == SRC_TMA, "CTA pairs need the TMA producer");
   constexpr int ACC_COLS = CONCAT ? 2 * BN : BN;                 // TMEM columns of one accumulator
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;      // two accumulators
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+  constexpr uint32_t UM_M = PAIR ? 2 * UM_BM : UM_BM;            // rows of one MMA
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((UM_M >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((UM_M >> 4) << 24);
 
   extern __shared__ __align__(16) uint8_t um_smem[];
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
@@ -331,14 +355,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES;
   const uint32_t bar_tfull = bars + 16 * UM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t bar_peer = bars + 16 * UM_MAX_STAGES + 48;   // leader only: the other CTAs of the cluster freed stage s
+  const uint32_t bar_pfull = bars + 16 * UM_MAX_STAGES + 48;  // pair leader: the peer CTA's operands of stage s have landed
   const uint32_t stile = (bars + UM_BAR_BYTES + 15u) & ~15u;                 // epilogue staging tile (128 x 144 B)
   const uint32_t tiles = (stile + UM_STAGING_BYTES + 1023u) & ~1023u;        // operand stage ring
   const int S = a.stages;
 
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
-  const int CL = a.cluster;
-  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr int CL = PAIR ? 2 : 1;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const int MT = (int)((M + UM_BM - 1) / UM_BM);
   const int MG = (MT + CL - 1) / CL;             // groups of CL adjacent M tiles: one per CTA of a cluster
   const int NT = a.NT, Z = a.Z;
@@ -357,13 +381,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull + 8 * b, 1);                       // one tcgen05.commit per tile
-        mbar_init(bar_tempty + 8 * b, EW);                     // the epilogue warps have drained the accumulator
+        mbar_init(bar_tempty + 8 * b, PAIR ? 2 * EW : EW);     // the epilogue warps (of both CTAs) have drained the accumulator
       }
-      for (int s = 0; s < S; ++s) mbar_init(bar_peer + 8 * s, CL > 1 ? CL - 1 : 1);
+      for (int s = 0; s < S; ++s) mbar_init(bar_pfull + 8 * s, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all();                              // peers' barriers exist before anyone arrives remotely
@@ -395,8 +420,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         int mt, nt, z;
         decode_work(wk, mt, nt, z);
         const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
-        // base input pixel of the tile's first row (tiles never start beyond M with one CTA per cluster)
-        const uint32_t mu = (uint32_t)((int64_t)mt * UM_BM);
+        // base input pixel of the tile's first row (the padding tile of an odd pair reloads the last tile; its rows
+        // are never stored)
+        const uint32_t mu = (uint32_t)((int64_t)(mt < MT ? mt : MT - 1) * UM_BM);
         const uint32_t q = mu / (uint32_t)g.PW, j = mu - q * (uint32_t)g.PW;
         const uint32_t n = q / (uint32_t)g.PH, i = q - n * (uint32_t)g.PH;
         const int cw = (int)j * g.isx + a.tma_w0, ch = (int)i * g.isy + a.tma_h0;
@@ -409,7 +435,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
             const int kk = kc * UM_BK;
             const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
             const uint32_t bar = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(bar, PLANES * (UM_A_PLANE + B_PLANE));
+            mbar_arrive_expect_tx(bar, PLANES * UM_A_PLANE + B_BYTES);
             {
               const int t = kk / g.Cin;
               const int ci0 = kk - t * g.Cin;
@@ -417,8 +443,17 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
               tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
               if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
             }
-            bulk_g2s(st_base + PLANES * UM_A_PLANE, a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE),
-                     PLANES * B_PLANE, bar);
+            const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
+            const uint32_t bx = st_base + PLANES * UM_A_PLANE;
+            if (!PAIR) {
+              bulk_g2s(bx, wsrc, B_BYTES, bar);
+            } else if (NSPLIT == 2) {
+              bulk_g2s(bx, wsrc + crank * B_PLANE, BX_ROWS * 128, bar);                              // B_hi | B_lo
+              bulk_g2s(bx + BX_ROWS * 128, wsrc + crank * (BN / 2) * 128, BY_ROWS * 128, bar);        // my half of B_hi
+            } else {
+              bulk_g2s(bx, wsrc + crank * (BN / 2) * 128, BX_ROWS * 128, bar);                       // my half of B_hi
+              if (PLANES == 2) bulk_g2s(bx + BX_ROWS * 128, wsrc + B_PLANE + crank * (BN / 2) * 128, BY_ROWS * 128, bar);
+            }
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -428,6 +463,21 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 2] = tr_wait;
         a.trace[blockIdx.x * 16 + 3] = clock64() - tr_t0;
         a.trace[blockIdx.x * 16 + 6] = tr_chunks;
+      }
+    } else if (PAIR && warp == 1 && crank != 0) {
+      // relay (peer CTA of a pair): once this CTA's operands of a stage have landed, tell the leader's MMA warp
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
+        int mt, nt, z;
+        decode_work(wk, mt, nt, z);
+        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+        for (int kc = kc_begin; kc < kc_end; ++kc) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (lane == 0) mbar_arrive_remote(bar_pfull + 8 * stage, 0);
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (!TMA_ANY && warp < UM_PRODUCER_WARPS) {
@@ -510,16 +560,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, PLANES * B_PLANE);
           const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
-          if (CL == 1) {
-            bulk_g2s(st_base + PLANES * UM_A_PLANE, wsrc, PLANES * B_PLANE, bar_full + 8 * stage);
-          } else if (crank == 0) {
-            // leader: once every CTA of the cluster has freed (and armed) this stage, one multicast copy feeds them all
-            mbar_wait_cluster(bar_peer + 8 * stage, phase);
-            bulk_g2s_multicast(st_base + PLANES * UM_A_PLANE, wsrc, PLANES * B_PLANE, bar_full + 8 * stage,
-                               (uint16_t)((1u << CL) - 1u));
-          } else {
-            mbar_arrive_remote(bar_peer + 8 * stage, 0);       // my stage is free and its barrier expects the bytes
-          }
+          bulk_g2s(st_base + PLANES * UM_A_PLANE, wsrc, PLANES * B_PLANE, bar_full + 8 * stage);
         }
         if (SRC == SRC_BF2) {
           const char* xhi = reinterpret_cast<const char*>(a.x);
@@ -563,8 +604,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   } else if (warp == UM_MMA_WARP) {
     // ================================ MMA issuer ================================
     // The whole warp walks the loop (warp-uniform control flow keeps the shared-memory descriptors in uniform
-    // registers); one elected lane issues the tcgen05 instructions.
-    {
+    // registers); one elected lane issues the tcgen05 instructions.  In a CTA pair only the leader (rank 0) issues:
+    // its MMAs span both CTAs' A tiles and accumulators.
+    if (!PAIR || crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int64_t it_local = 0;
@@ -584,6 +626,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           const long long tr_w0 = a.trace ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
+          if (PAIR) mbar_wait_cluster(bar_pfull + 8 * stage, phase);      // the peer's half of the operands
           if (a.trace) tr_wait += clock64() - tr_w0;
           if (SRC == SRC_BF2) fence_proxy_async();   // cp.async (generic proxy) writes observed through the barrier
           tc_fence_after();
@@ -592,26 +635,38 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           const uint64_t da_hi = DESC_HI | (uint64_t)((st_base & 0x3FFFFu) >> 4);
           const uint64_t da_lo = DESC_HI | (uint64_t)(((st_base + UM_A_PLANE) & 0x3FFFFu) >> 4);
           const uint64_t db_hi = DESC_HI | (uint64_t)(((st_base + PLANES * UM_A_PLANE) & 0x3FFFFu) >> 4);
-          const uint64_t db_lo = DESC_HI | (uint64_t)(((st_base + PLANES * UM_A_PLANE + B_PLANE) & 0x3FFFFu) >> 4);
+          // second B block of the stage: B_lo (alone) / block Y (pair: see BX_ROWS)
+          const uint64_t db_lo = DESC_HI | (uint64_t)(((st_base + PLANES * UM_A_PLANE + BX_ROWS * 128) & 0x3FFFFu) >> 4);
           if (elect_one()) {
+            auto mma = [&](uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+              if (PAIR) umma_bf16_2(tmem_acc, da, db, idesc, acc);
+              else umma_bf16(tmem_acc, da, db, idesc, acc);
+            };
 #pragma unroll
             for (int k4 = 0; k4 < UM_BK / 16; ++k4) {
               const uint64_t xa_hi = da_hi + 2 * k4, xa_lo = da_lo + 2 * k4;   // 32 bytes further inside the swizzle atom
+              const uint32_t first = (kc > kc_begin || k4 > 0) ? 1u : 0u;
               if (CONCAT) {
-                // the lo plane of B follows its hi plane in the stage: one 2*BN-wide MMA yields [A_hi.B_hi | A_hi.B_lo]
-                // in adjacent accumulator blocks (summed by the epilogue); A_lo.B_hi lands on the first block
-                umma_bf16(tmem_acc, xa_hi, db_hi + 2 * k4, IDESC2, (kc > kc_begin || k4 > 0) ? 1u : 0u);
-                umma_bf16(tmem_acc, xa_lo, db_hi + 2 * k4, IDESC, 1u);
+                // one 2*BN-wide MMA yields [A_hi.B_hi | A_hi.B_lo] in adjacent accumulator blocks (summed by the
+                // epilogue): alone the lo plane of B follows its hi plane in the stage, in a pair rank 0 holds B_hi and
+                // rank 1 B_lo in block X; A_lo.B_hi lands on the first block (pair: the two halves of B_hi in block Y)
+                mma(xa_hi, db_hi + 2 * k4, IDESC2, first);
+                mma(xa_lo, (PAIR ? db_lo : db_hi) + 2 * k4, IDESC, 1u);
               } else {
-                umma_bf16(tmem_acc, xa_hi, db_hi + 2 * k4, IDESC, (kc > kc_begin || k4 > 0) ? 1u : 0u);
+                mma(xa_hi, db_hi + 2 * k4, IDESC, first);
                 if (NSPLIT == 3) {
-                  umma_bf16(tmem_acc, xa_lo, db_hi + 2 * k4, IDESC, 1u);
-                  umma_bf16(tmem_acc, xa_hi, db_lo + 2 * k4, IDESC, 1u);
+                  mma(xa_lo, db_hi + 2 * k4, IDESC, 1u);
+                  mma(xa_hi, db_lo + 2 * k4, IDESC, 1u);
                 }
               }
             }
-            umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
-            if (kc + 1 == kc_end) umma_commit(bar_tfull + 8 * b);   // accumulator complete
+            if (PAIR) {
+              umma_commit2(bar_empty + 8 * stage);     // frees the stage in both CTAs
+              if (kc + 1 == kc_end) umma_commit2(bar_tfull + 8 * b);
+            } else {
+              umma_commit(bar_empty + 8 * stage);      // frees the stage once these MMAs have read it
+              if (kc + 1 == kc_end) umma_commit(bar_tfull + 8 * b);   // accumulator complete
+            }
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -825,7 +880,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         if (c0 + 32 >= BN) {                       // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+          if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
         }
         if (!split && (a.bias != nullptr || a.relu)) {
           const int n0 = n_base + cc;
@@ -869,7 +924,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   else __syncthreads();
   if (warp == UM_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (stats) {
     for (int i = tid; i < a.Ntot; i += UM_THREADS) {
@@ -1101,10 +1157,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int NSPLIT, int SRC>
+template <int BN, int NSPLIT, int SRC, bool PAIR>
 int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int nt, int Z, cudaStream_t st) {
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
-  constexpr int STAGE_BYTES = PLANES * (UM_A_PLANE + BN * 128);
+  constexpr int BX_ROWS = !PAIR ? BN : (NSPLIT == 2 ? BN : BN / 2);          // (same as in the kernel)
+  constexpr int BY_ROWS = PLANES == 1 ? 0 : (!PAIR ? BN : BN / 2);
+  constexpr int STAGE_BYTES = PLANES * UM_A_PLANE + (BX_ROWS + BY_ROWS) * 128;
   UmmaArgs a = a_in;
   a.NT = nt;
   a.Z = Z;
@@ -1115,7 +1173,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   if (S < 2) S = 2;
   a.stages = S;
   const size_t smem = (size_t)fixed + (size_t)S * STAGE_BYTES;
-  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC>;
+  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC, PAIR>;
   static bool attr_set[64] = {false};               // per device: the attribute lives in the device's context
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1125,12 +1183,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   const int64_t MT = cdiv64(M, UM_BM);
-  // SAG_UMMA_CLUSTER=2: clusters of 2 CTAs share each weight tile through one multicast copy.  It halves the weight
-  // reads at the L2 slices but not the bytes entering each SM, and the lockstep adds a cross-SM round trip to every
-  // stage recycle: measured 15 % slower on B200 (conv 2.03 ms vs 1.74 ms per step), so it is off by default.
-  static const int cluster_on = env_int("SAG_UMMA_CLUSTER", 1);
-  const int CL = (cluster_on >= 2 && MT >= 2) ? 2 : 1;
-  a.cluster = CL;
+  constexpr int CL = PAIR ? 2 : 1;                                  // CTA pair: a cluster of two SMs of one TPC per work item
   const int64_t n_work = cdiv64(MT, CL) * nt * Z;                   // per cluster
   static const int max_ctas = env_int("SAG_UMMA_MAX_CTAS", 0);      // test knob: force many work items per CTA
   int64_t clusters = (max_ctas > 0 ? max_ctas : num_sms()) / CL;
@@ -1192,11 +1245,21 @@ template <int BN, int NSPLIT>
 int launch_ns(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt, int src, int Z, cudaStream_t st) {
   switch (src) {
     case SRC_TMA:
-      if constexpr (BN >= 64) return launch_cfg<BN, NSPLIT, SRC_TMA>(g, a, tm, nt, Z, st);
-      else return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, tm, nt, Z, st);      // (the host never picks TMA for 32-wide tiles)
-    case SRC_BF2: return launch_cfg<BN, NSPLIT, SRC_BF2>(g, a, tm, nt, Z, st);
-    case SRC_F32_VEC: return launch_cfg<BN, NSPLIT, SRC_F32_VEC>(g, a, tm, nt, Z, st);
-    default: return launch_cfg<BN, NSPLIT, SRC_F32>(g, a, tm, nt, Z, st);
+      if constexpr (BN >= 64) {
+        // CTA pairs (cta_group::2, M = 256): two adjacent M tiles per cluster, each CTA feeds half of every weight tile
+        // (15-33 % fewer shared-memory bytes per K chunk).  Parity-tested, off by default: with 4 stages of ~44 KB the
+        // ring cannot cover the longer loop (peer relay + multicast commit on top of the TMA latency) -- measured
+        // conv2_x 66 -> 90 us, conv1 130 -> 170 us on B200 (SAG_UMMA_PAIR=1 / sag_set_option "cta_pair").
+        static const int pair_env = env_int("SAG_UMMA_PAIR", 0);
+        const int64_t MT = cdiv64((int64_t)g.N * g.PH * g.PW, UM_BM);
+        if ((g_umma_pair < 0 ? pair_env : g_umma_pair) && MT >= 2) return launch_cfg<BN, NSPLIT, SRC_TMA, true>(g, a, tm, nt, Z, st);
+        return launch_cfg<BN, NSPLIT, SRC_TMA, false>(g, a, tm, nt, Z, st);
+      } else {
+        return launch_cfg<BN, NSPLIT, SRC_BF2, false>(g, a, tm, nt, Z, st);  // (the host never picks TMA for 32-wide tiles)
+      }
+    case SRC_BF2: return launch_cfg<BN, NSPLIT, SRC_BF2, false>(g, a, tm, nt, Z, st);
+    case SRC_F32_VEC: return launch_cfg<BN, NSPLIT, SRC_F32_VEC, false>(g, a, tm, nt, Z, st);
+    default: return launch_cfg<BN, NSPLIT, SRC_F32, false>(g, a, tm, nt, Z, st);
   }
 }
 
@@ -1440,6 +1503,7 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
 }
 
 thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
+thread_local int g_umma_pair = -1;  // -1: SAG_UMMA_PAIR (default off); 0 / 1: forced (sag_set_option "cta_pair")
 
 // im2col tensor maps over the two bf16 planes of an NHWC activation for the geometry's taps (reference for the
 // corner arithmetic: base pixel of output (i, j) = (i*isy + min dy, j*isx + min dx); the box's upper corner is chosen so

@@ -457,8 +457,9 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
     h->prof.clear();
     g_prof = &h->prof;
   }
-  struct ProfGuard { ~ProfGuard() { g_prof = nullptr; g_umma_tma = -1; } } prof_guard;   // stage entry points never see a stale profiler
+  struct ProfGuard { ~ProfGuard() { g_prof = nullptr; g_umma_tma = -1; g_umma_pair = -1; } } prof_guard;   // stage entry points never see a stale profiler
   g_umma_tma = h->tma_gather;
+  g_umma_pair = h->cta_pair;
   const bool unet = c.separation == SAG_SEP_UNET_MASK;
   // NO_SEPARATION keeps params.sep_num_tracks localization weights per output channel; the single mono track
   // broadcasts against them (model.py:430), i.e. the mono crop is replicated K times before the mixing.

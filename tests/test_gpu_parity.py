@@ -349,6 +349,25 @@ def test_forward_tma_gather_matches_cp_async_gather():
     assert _rel(y1, y0) < 1e-4
 
 
+def test_forward_cta_pair_matches_single_cta():
+    """cta_group::2 (two M tiles per cluster, each CTA feeding half of every weight tile) computes the same products in
+    the same order as the single-CTA kernel: bit-identical without batch-norm atomics, to rounding with them."""
+    _, m = _models(['audio'], 'unet_mask', 5, 3, precision='bf16x3')
+    a = cu(_audio(3, 41))
+    m.set_option('cta_pair', 1)
+    y1 = m.inference_ops(a).clone()
+    m.set_option('cta_pair', 0)
+    y0 = m.inference_ops(a).clone()
+    assert torch.equal(y0, y1)
+    _, m = _models(['audio', 'video'], 'unet_mask', 7, 3, precision='bf16x3')     # odd M tile counts: padding tiles
+    a, v = cu(_audio(3, 42)), cu(_video(3, 43))
+    m.set_option('cta_pair', 1)
+    y1 = m.inference_ops(a, video=v).clone()
+    m.set_option('cta_pair', 0)
+    y0 = m.inference_ops(a, video=v).clone()
+    assert _rel(y1, y0) < 1e-4
+
+
 def test_forward_errors():
     from spatialaudiogen_b200 import SptAudioGen
     with pytest.raises(ValueError):
