@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import myutils
+from . import myutils, tf_checkpoint
 from .definitions import AUDIO, VIDEO, FLOW, NO_SEPARATION
 from .model import SptAudioGen, SptAudioGenParams
 
@@ -25,8 +25,10 @@ def load_weights_file(path):
 
 class W2XYZ(object):
     def __init__(self, model_dir=None, params=None, weights=None, precision=None, device=None):
-        """model_dir: directory holding train-params.txt (reference myutils.load_params) and weights.npz; or pass
-        `params` (object with the fields load_params returns) and `weights` (dict) directly."""
+        """model_dir: directory holding train-params.txt (reference myutils.load_params) and the weights -- a TensorFlow
+        V2 checkpoint as the reference saves it (`checkpoint` + `model.ckpt-N.index/.data-*`, restored like
+        deploy.py:79-87 through tf_checkpoint.read_bundle) or weights.npz; or pass `params` (object with the fields
+        load_params returns) and `weights` (dict) directly."""
         if params is None:
             params = myutils.load_params(model_dir)
         self.params = params
@@ -42,7 +44,7 @@ class W2XYZ(object):
         self.audio_size = self.model.snd_dur + self.model.snd_contx - 1
         self.video_size = int(self.duration * params.video_rate)
         if weights is None:
-            weights = load_weights_file(os.path.join(model_dir, 'weights.npz'))
+            weights = tf_checkpoint.load_model_dir(model_dir, names=set(self.model.variable_shapes()))
         self.model.load_weights(weights)
         B, dev = self.batch_size, self.model.device
         H, W = self.model.dims_frame()

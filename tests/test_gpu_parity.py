@@ -447,6 +447,24 @@ def test_w2xyz_deploy_matches_reference_loop_with_zero_padded_tail():
     assert _rel(out[:, 1:], ref[:, 1:]) < 1e-3
 
 
+def test_w2xyz_restores_a_tf_checkpoint_bundle(tmp_path):
+    """deploy.py:79-87: the weights come from `checkpoint` + model.ckpt-N.index/.data (variables, Adam slots and
+    global_step side by side); restoring by name gives the same network as handing the arrays over directly."""
+    from spatialaudiogen_b200.deploy import W2XYZ
+    from spatialaudiogen_b200 import tf_checkpoint as T
+    enc = ['audio']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=5, stress=True)
+    bundle = dict(W)
+    for k, v in W.items():
+        bundle[k + '/Adam'] = np.zeros_like(v)
+    bundle['global_step'] = np.asarray(777, dtype=np.int64)
+    T.write_bundle(str(tmp_path / 'model.ckpt-777'), bundle)
+    amb = np.concatenate([_audio(4, 51)] * 4, axis=2)
+    a = W2XYZ(model_dir=str(tmp_path), params=_P(enc)).deploy_windows(amb)
+    b = W2XYZ(params=_P(enc), weights=W).deploy_windows(amb)
+    assert np.array_equal(a, b)
+
+
 def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
     from spatialaudiogen_b200 import evaluate as E
     rng = np.random.RandomState(3)
