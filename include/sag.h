@@ -171,6 +171,12 @@ int sag_metrics(const float* pred, const float* gt, int batch, int t, int audio_
 int sag_sh_rms_dims(float ang_res, int* n_nu, int* n_phi);
 int sag_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, void* stream);
 
+/* Earth mover's distance (EMD-hat, pyemd.emd semantics) of `count` pairs of n-bin histograms over one ground-distance
+ * matrix: the last two eval-detailed.txt columns (eval.py:190-193 -> distance.py:100-143 ambix_emd / emd).  Host code
+ * (the reference solves it on the host too); exact min-cost flow in doubles; extra_mass_penalty < 0 = max(dist). */
+int sag_emd_hat(const double* first, const double* second, int n, const double* dist, double extra_mass_penalty, int count,
+                double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -580,3 +580,35 @@ def ambix_rms_map(ambi, angular_res=30.):
     decoded = np.dot(np.asarray(ambi, np.float64), Y.T)
     rms = np.sqrt(np.mean(decoded ** 2, 0)).reshape(phi_mesh.shape)
     return np.flipud(rms)
+
+
+def emd_hat_lp(first, second, dist, extra_mass_penalty=-1.0):
+    """pyemd.emd(first, second, dist) restated as its defining linear program (Pele & Werman's EMD-hat; pyemd==0.5.1 is
+    absent): min sum f_ij d_ij + |sum P - sum Q| * penalty over flows f >= 0 with row sums <= P, column sums <= Q and
+    total flow min(sum P, sum Q); penalty = max(dist) for -1.  Solved with scipy's HiGHS -- independent of the
+    product's min-cost-flow solver."""
+    from scipy.optimize import linprog
+    p, q, D = np.asarray(first, np.float64), np.asarray(second, np.float64), np.asarray(dist, np.float64)
+    n = p.size
+    pen = D.max() if extra_mass_penalty < 0 else extra_mass_penalty
+    rows = np.zeros((2 * n, n * n))
+    for i in range(n):
+        rows[i, i * n:(i + 1) * n] = 1.0
+        rows[n + i, i::n] = 1.0
+    res = linprog(D.reshape(-1), A_ub=rows, b_ub=np.concatenate((p, q)), A_eq=np.ones((1, n * n)), b_eq=[min(p.sum(), q.sum())],
+                  bounds=(0, None), method='highs')
+    return float(res.fun + abs(p.sum() - q.sum()) * pen)
+
+
+def ambix_emd(ambi1, ambi2, ang_res=30.):
+    """distance.py:129-143 for one 0.1 s window (one visualizer frame): ambi (T, 4) -> (emd_dir, emd_dir2)."""
+    phi_mesh, nu_mesh = spherical_mesh(ang_res)
+    p_mesh = np.stack((np.cos(nu_mesh) * np.cos(phi_mesh), np.cos(nu_mesh) * np.sin(phi_mesh), np.sin(nu_mesh)), 0).reshape((3, -1))
+    ang_dist = np.dot(p_mesh.T, p_mesh)
+    ang_dist[ang_dist >= 1] = 1
+    ang_dist[ang_dist <= -1] = -1
+    ang_dist = np.arccos(ang_dist)                                        # distance.py:106-109
+    m1, m2 = ambix_rms_map(ambi1, ang_res).reshape(-1), ambix_rms_map(ambi2, ang_res).reshape(-1)
+    n_nodes = m1.size
+    return (emd_hat_lp(m1 / n_nodes, m2 / n_nodes, ang_dist),
+            emd_hat_lp(m1 / (m1.sum() + 0.01), m2 / (m2.sum() + 0.01), ang_dist))       # distance.py:124-125

@@ -3,8 +3,9 @@
 Per batch of windows: forward (eval.py:90), the in-graph per-sample metrics (model.evaluation_ops, model.py:110-154),
 the Hilbert-envelope distance (myutils.py:109-116), amplitudes (eval.py:197-198) and the 84-direction RMS energy maps
 that feed the EMD (distance.py:41-52, ang_res=30) -- all as GPU kernels.  Rows come out in the reference's
-`eval-detailed.txt` format (`SampleID | <28 metric names>`, eval.py:125-133, 212-215); the two columns that need
-absent third-party solvers (mel_lsd: librosa, emd: pyemd -- SURVEY.md 8f) are written as nan.  With several ranks
+`eval-detailed.txt` format (`SampleID | <28 metric names>`, eval.py:125-133, 212-215).  The EMD columns (pyemd in the
+reference) come from the exact host solver in libsag.so when the energy maps are requested; the mel_lsd columns
+(librosa) are written as nan.  With several ranks
 (one process per GPU) whole batches are sharded and the rows meet in one all-gather (dist.gather_rows).
 """
 from collections import OrderedDict
@@ -62,6 +63,9 @@ def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps
             raise ValueError('rms_maps needs the W channel (mono)')
         lay = torch.ones((B, 1, 4), device=pred.device) if layout is None else torch.as_tensor(layout, device=pred.device).float()[:, None, :]
         maps = (M.ambix_rms_map(torch.cat((mono, pred), 2) * lay, 30.), M.ambix_rms_map(torch.cat((mono, target), 2) * lay, 30.))
+        # emd/dir, emd/dir2 (eval.py:190-193): exact EMD of the two 84-node maps, solved on the host like the reference
+        d1, d2 = M.ambix_emd_from_maps(maps[0], maps[1], 30.)
+        rows[:, _COL['emd/dir']:_COL['emd/dir2'] + 1] = torch.as_tensor(np.stack((d1, d2), 1), dtype=torch.float32).to(rows.device)
     return rows, maps
 
 

@@ -4,6 +4,7 @@ spherical-harmonic RMS energy maps of pyutils/ambisonics (decoder.py:24-28, dist
 in libsag.so (metrics.cu); this module only allocates outputs."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -50,3 +51,45 @@ def ambix_rms_map(ambi, ang_res=30.):
         rms = torch.empty((B, n_nu.value, n_phi.value), dtype=torch.float32, device=ambi.device)
         L.check(L.lib().sag_sh_rms(L.ptr(ambi), B, T, float(ang_res), L.ptr(rms), L.stream()))
     return rms
+
+
+def spherical_mesh(ang_res):
+    """reference distance.py:9-13: (phi_mesh, nu_mesh), each (n_nu, n_phi), radians."""
+    phi_rg = np.flip(np.arange(-180., 180., ang_res) / 180. * np.pi, 0)
+    nu_rg = np.arange(-90., 90.1, ang_res) / 180. * np.pi
+    return np.meshgrid(phi_rg, nu_rg)
+
+
+def emd_hat(first, second, dist, extra_mass_penalty=-1.0):
+    """pyemd.emd semantics (EMD-hat, exact) for `count` pairs of histograms: first, second (count, n) or (n,), dist (n, n).
+    Host solver in libsag.so (csrc/emd.cu), float64.  Returns (count,) float64."""
+    first = np.ascontiguousarray(np.atleast_2d(np.asarray(first, np.float64)))
+    second = np.ascontiguousarray(np.atleast_2d(np.asarray(second, np.float64)))
+    dist = np.ascontiguousarray(np.asarray(dist, np.float64))
+    if first.shape != second.shape or dist.shape != (first.shape[1], first.shape[1]):
+        raise ValueError('emd_hat: histograms %s / %s do not match the %s distance matrix' % (first.shape, second.shape, dist.shape))
+    out = np.zeros(first.shape[0], np.float64)
+    L.check(L.lib().sag_emd_hat(first.ctypes.data_as(C.c_void_p), second.ctypes.data_as(C.c_void_p), first.shape[1],
+                                dist.ctypes.data_as(C.c_void_p), float(extra_mass_penalty), first.shape[0],
+                                out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def ambix_emd_from_maps(maps1, maps2, ang_res=30.):
+    """The two EMD columns of eval-detailed.txt from the RMS energy maps of one 0.1 s window each (reference
+    distance.py:100-143 `emd` inside `ambix_emd`, eval.py:190): ground distance = great-circle angle between mesh
+    directions; `dir` compares map / n_nodes, `dir2` compares map / (sum(map) + 0.01).  maps (B, n_nu, n_phi), CUDA or
+    host.  Returns (dir, dir2), each (B,) float64."""
+    m1 = np.asarray(maps1.detach().cpu() if isinstance(maps1, torch.Tensor) else maps1, np.float64)
+    m2 = np.asarray(maps2.detach().cpu() if isinstance(maps2, torch.Tensor) else maps2, np.float64)
+    B = m1.shape[0]
+    phi_mesh, nu_mesh = spherical_mesh(ang_res)
+    if m1.shape[1:] != phi_mesh.shape or m2.shape != m1.shape:
+        raise ValueError('maps %s / %s do not match the %s mesh' % (m1.shape, m2.shape, phi_mesh.shape))
+    p_mesh = np.stack((np.cos(nu_mesh) * np.cos(phi_mesh), np.cos(nu_mesh) * np.sin(phi_mesh), np.sin(nu_mesh)), 0).reshape((3, -1))
+    ang_dist = np.arccos(np.clip(np.dot(p_mesh.T, p_mesh), -1., 1.))       # distance.py:106-109
+    m1, m2 = m1.reshape(B, -1), m2.reshape(B, -1)
+    n_nodes = m1.shape[1]
+    d1 = emd_hat(m1 / n_nodes, m2 / n_nodes, ang_dist)                      # distance.py:124
+    d2 = emd_hat(m1 / (m1.sum(1, keepdims=True) + 0.01), m2 / (m2.sum(1, keepdims=True) + 0.01), ang_dist)   # :125
+    return d1, d2

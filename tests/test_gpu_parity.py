@@ -487,10 +487,16 @@ def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
             assert np.allclose(rows[:, col[name + '/' + ch]], r[:, i], rtol=2e-4, atol=1e-7)
     env_r = np.stack([O.compute_envelope_dist(pred[b], gt[b]) for b in range(B)])
     assert np.allclose(rows[:, col['env_mse/X']], env_r[:, 2], rtol=2e-4)
-    assert np.isnan(rows[:, col['mel_lsd/avg']]).all() and np.isnan(rows[:, col['emd/dir']]).all()
+    assert np.isnan(rows[:, col['mel_lsd/avg']]).all()
     for b in range(B):
         rp = O.ambix_rms_map(np.concatenate((mono[b], pred[b]), 1) * layout[b], 30.)
         assert _rel(maps[0][b], np.ascontiguousarray(rp)) < 1e-5
+        # emd/dir, emd/dir2 (eval.py:190): GPU maps + host min-cost flow against the oracle's maps + LP
+        e1, e2 = O.ambix_emd(np.concatenate((mono[b], pred[b]), 1) * layout[b], np.concatenate((mono[b], gt[b]), 1) * layout[b], 30.)
+        assert abs(rows[b, col['emd/dir']] - e1) < 1e-5 * max(1.0, abs(e1)) + 1e-6
+        assert abs(rows[b, col['emd/dir2']] - e2) < 1e-4 * max(1.0, abs(e2)) + 1e-5
+    rows_nomaps, _ = E.metric_rows(cu(pred), cu(gt))                     # without the maps the EMD columns stay nan
+    assert np.isnan(rows_nomaps.cpu().numpy()[:, col['emd/dir']]).all()
     fn = str(tmp_path / 'eval-detailed.txt')
     E.write_eval_detailed(fn, ['vid%d 0.5' % b for b in range(B)], rows)
     lines = open(fn).read().splitlines()

@@ -38,3 +38,29 @@ def test_definitions_and_checkpoint_layout():
     assert sh['bottleneck/video-fc/weights'] == (12544, 512) and sh['video_encoder/conv3_1/shortcut/weights'] == (1, 1, 64, 128)
     sh1 = Wt.variable_shapes(['audio'], separation='none', sep_num_tracks=1)
     assert sh1['localization/fc3/weights'] == (512, 6) and not any(k.startswith('separation/') for k in sh1)
+
+
+def test_emd_hat_host_solver_matches_the_defining_lp():
+    """sag_emd_hat (host code in libsag.so, no GPU involved) against the oracle's LP restatement of pyemd.emd."""
+    import numpy as np
+    from oracle import sag_oracle as O
+    from spatialaudiogen_b200 import metrics as M
+    rng = np.random.RandomState(1)
+    phi, nu = M.spherical_mesh(30.)
+    assert phi.shape == (7, 12)
+    p = np.stack((np.cos(nu) * np.cos(phi), np.cos(nu) * np.sin(phi), np.sin(nu)), 0).reshape(3, -1)
+    D = np.arccos(np.clip(p.T.dot(p), -1, 1))
+    first, second = rng.rand(5, 84), rng.rand(5, 84) * np.array([[0.5], [1.0], [2.0], [1.0], [1.3]])
+    second[1] *= first[1].sum() / second[1].sum()                       # one balanced pair
+    got = M.emd_hat(first, second, D)
+    for k in range(5):
+        assert abs(got[k] - O.emd_hat_lp(first[k], second[k], D)) < 1e-9
+    # identities: zero to itself; a unit of mass moved between two nodes costs their distance; excess mass costs max(D)
+    assert M.emd_hat(first[0], first[0], D)[0] < 1e-6                   # (arccos of a rounded dot product leaves ~1e-8 on the diagonal)
+    e3, e40 = np.eye(84)[3], np.eye(84)[40]
+    assert abs(M.emd_hat(e3, e40, D)[0] - D[3, 40]) < 1e-12
+    assert abs(M.emd_hat(2 * e3, e3, D)[0] - D.max()) < 1e-12
+    assert abs(M.emd_hat(2 * e3, e3, D, extra_mass_penalty=0.25)[0] - 0.25) < 1e-12
+    import pytest
+    with pytest.raises(ValueError):
+        M.emd_hat(-e3, e3, D)
