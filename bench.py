@@ -274,7 +274,7 @@ def main():
     def step(i, store=None):
         d = devb[i % R]
         model.forward_into(d['audio'], d.get('video'), d.get('flow'), out)
-        r, _ = E.metric_rows(out, d['target'], audio_rate=RATE)
+        r, _ = E.metric_rows(out, d['target'], audio_rate=RATE, mel_lsd=False)   # the metric set of SURVEY.md 8d config 5
         if store is not None:
             store.copy_(r)
 

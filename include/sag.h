@@ -171,6 +171,9 @@ int sag_metrics(const float* pred, const float* gt, int batch, int t, int audio_
 int sag_sh_rms_dims(float ang_res, int* n_nu, int* n_phi);
 int sag_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, void* stream);
 
+/* Mel log-spectral distance (myutils.compute_lsd_dist, myutils.py:96-106: librosa melspectrogram n_fft 2048, hop 512,
+ * 128 Slaney mels up to 12 kHz, power 2; 10*log10(|.| + 0.01); RMS over bands x frames): pred, gt (B,T,3) -> (B,3). */
+int sag_mel_lsd(const float* pred, const float* gt, int batch, int t, int audio_rate, float* mel_lsd_ps, void* stream);
 /* Earth mover's distance (EMD-hat, pyemd.emd semantics) of `count` pairs of n-bin histograms over one ground-distance
  * matrix: the last two eval-detailed.txt columns (eval.py:190-193 -> distance.py:100-143 ambix_emd / emd).  Host code
  * (the reference solves it on the host too); exact min-cost flow in doubles; extra_mass_penalty < 0 = max(dist). */

@@ -612,3 +612,54 @@ def ambix_emd(ambi1, ambi2, ang_res=30.):
     n_nodes = m1.size
     return (emd_hat_lp(m1 / n_nodes, m2 / n_nodes, ang_dist),
             emd_hat_lp(m1 / (m1.sum() + 0.01), m2 / (m2.sum() + 0.01), ang_dist))       # distance.py:124-125
+
+
+def _mel_filter_bank(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """librosa.filters.mel of librosa 0.6.0 (htk=False, norm=1): Slaney mel scale (linear below 1 kHz, log above),
+    triangles between consecutive mel points, area normalised.  librosa is absent: restated from its algorithm."""
+    fmax = float(sr) / 2 if fmax is None else fmax
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        f = np.asarray(f, np.float64)
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, f / f_sp)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, np.float64)
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mels + 2))
+    fftfreqs = np.linspace(0, float(sr) / 2, 1 + n_fft // 2)
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    weights = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+    return weights * enorm[:, None]
+
+
+def compute_lsd_dist(pred, gt, rate):
+    """myutils.py:96-106: librosa.feature.melspectrogram(y, sr=rate, n_mels=128, fmax=12000) (n_fft 2048, hop 512,
+    centred with reflect padding, periodic Hann, power 2) -> 10*log10(|S| + 0.01) -> RMS difference.  (T, 3) x 2 -> (3,)."""
+    n_fft, hop = 2048, 512
+    basis = _mel_filter_bank(rate, n_fft, 128, 0.0, 12000.0)
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
+
+    def melspec(y):
+        y = np.pad(np.asarray(y, np.float64), n_fft // 2, mode='reflect')
+        n_frames = 1 + (len(y) - n_fft) // hop
+        frames = np.stack([y[f * hop:f * hop + n_fft] * win for f in range(n_frames)], 1)
+        return basis.dot(np.abs(np.fft.rfft(frames, axis=0)) ** 2)
+
+    def power_spect(x):
+        return 10 * np.log(np.abs(x) + 1e-2) / np.log(10.)
+
+    pred, gt = np.asarray(pred), np.asarray(gt)
+    dist = np.zeros(gt.shape[1])
+    for i in range(gt.shape[1]):
+        dist[i] = np.sqrt(np.mean((power_spect(melspec(gt[:, i])) - power_spect(melspec(pred[:, i]))) ** 2))
+    return dist

@@ -73,6 +73,7 @@ PROTOTYPES = {
     'sag_metrics': (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'sag_sh_rms_dims': (_I, [_F, C.POINTER(_I), C.POINTER(_I)]),
     'sag_sh_rms': (_I, [_P, _I, _I, _F, _P, _P]),
+    'sag_mel_lsd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     'sag_emd_hat': (_I, [_P, _P, _I, _P, C.c_double, _I, _P]),
 }
 

@@ -410,6 +410,11 @@ int sag_metrics(const float* pred, const float* gt, int batch, int t, int audio_
   return launch_metrics(pred, gt, batch, t, audio_rate, stft_ps, lsd_ps, mse_ps, snr_ps, env_ps, amp, scratch, as_stream(stream));
 }
 
+int sag_mel_lsd(const float* pred, const float* gt, int batch, int t, int audio_rate, float* mel_lsd_ps, void* stream) {
+  SAG_REQUIRE(pred != nullptr && gt != nullptr && mel_lsd_ps != nullptr, SAG_EINVAL, "sag_mel_lsd: NULL argument");
+  return launch_mel_lsd(pred, gt, batch, t, audio_rate, mel_lsd_ps, as_stream(stream));
+}
+
 int sag_sh_rms_dims(float ang_res, int* n_nu, int* n_phi) {
   SAG_REQUIRE(n_nu != nullptr && n_phi != nullptr, SAG_EINVAL, "sag_sh_rms_dims: NULL argument");
   return sh_mesh_dims(ang_res, n_nu, n_phi);

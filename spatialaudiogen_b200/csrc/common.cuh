@@ -234,6 +234,8 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
 // metrics.cu
 int launch_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
                    float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, cudaStream_t st);
+// mel log-spectral distance of myutils.compute_lsd_dist (librosa melspectrogram restated): pred, gt (B,T,3) -> out (B,3)
+int launch_mel_lsd(const float* pred, const float* gt, int batch, int t, int audio_rate, float* out, cudaStream_t st);
 int launch_sh_rms(const float* ambi, int batch, int t, float ang_res, float* rms, cudaStream_t st);
 
 }  // namespace sag

@@ -208,6 +208,151 @@ int launch_metrics(const float* pred, const float* gt, int batch, int t, int aud
   return SAG_OK;
 }
 
+// ---- mel log-spectral distance (reference myutils.compute_lsd_dist, myutils.py:96-106) -----------------------------------
+// librosa.feature.melspectrogram(y, sr, n_mels=128, fmax=12000) of librosa 0.6.0 (absent third-party code, restated from
+// its published algorithm): centred STFT (reflect padding n_fft/2, periodic Hann, n_fft 2048, hop 512), power spectrum,
+// Slaney mel filter bank with area normalisation; then 10*log10(|mel| + 0.01) and the RMS difference over all
+// (band, frame) cells.  One CTA per (window, channel); gt and pred ride every transform together.
+struct MelBank {
+  int n_fft, hop, n_mels, nnz;
+  const int* start;      // [n_mels] first FFT bin with a non-zero weight
+  const int* len;        // [n_mels]
+  const int* off;        // [n_mels] offset into w
+  const float* w;        // packed triangle weights
+};
+static std::mutex g_mel_mu;
+static std::map<std::pair<int, int>, MelBank> g_mels;   // (device, rate) -> bank
+
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static int get_mel_bank(int rate, MelBank* out) {
+  int dev = 0;
+  SAG_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mel_mu);
+  auto it = g_mels.find({dev, rate});
+  if (it != g_mels.end()) { *out = it->second; return SAG_OK; }
+  MelBank m;
+  m.n_fft = 2048; m.hop = 512; m.n_mels = 128;
+  const double fmax = 12000.0, fmin = 0.0;
+  const int nb = 1 + m.n_fft / 2;
+  std::vector<double> mel_f(m.n_mels + 2);
+  const double m0 = hz_to_mel(fmin), m1 = hz_to_mel(fmax);
+  for (int i = 0; i < m.n_mels + 2; ++i) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * (double)i / (double)(m.n_mels + 1));
+  std::vector<int> start(m.n_mels), len(m.n_mels), off(m.n_mels);
+  std::vector<float> w;
+  for (int i = 0; i < m.n_mels; ++i) {
+    const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+    int first = -1, last = -1;
+    std::vector<float> row;
+    for (int k = 0; k < nb; ++k) {
+      const double f = (double)rate / 2.0 * (double)k / (double)(nb - 1);         // np.linspace(0, sr/2, 1 + n_fft//2)
+      const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]), upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+      const double v = std::max(0.0, std::min(lower, upper)) * enorm;
+      if (v > 0.0) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    start[i] = first < 0 ? 0 : first;
+    len[i] = first < 0 ? 0 : last - first + 1;
+    off[i] = (int)w.size();
+    for (int k = start[i]; k < start[i] + len[i]; ++k) {
+      const double f = (double)rate / 2.0 * (double)k / (double)(nb - 1);
+      const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]), upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+      w.push_back((float)(std::max(0.0, std::min(lower, upper)) * enorm));
+    }
+  }
+  m.nnz = (int)w.size();
+  int *ds = nullptr, *dl = nullptr, *dof = nullptr;
+  float* dw = nullptr;
+  SAG_CHECK_CUDA(cudaMalloc(&ds, sizeof(int) * m.n_mels));
+  SAG_CHECK_CUDA(cudaMalloc(&dl, sizeof(int) * m.n_mels));
+  SAG_CHECK_CUDA(cudaMalloc(&dof, sizeof(int) * m.n_mels));
+  SAG_CHECK_CUDA(cudaMalloc(&dw, sizeof(float) * std::max<size_t>(w.size(), 1)));
+  SAG_CHECK_CUDA(cudaMemcpy(ds, start.data(), sizeof(int) * m.n_mels, cudaMemcpyHostToDevice));
+  SAG_CHECK_CUDA(cudaMemcpy(dl, len.data(), sizeof(int) * m.n_mels, cudaMemcpyHostToDevice));
+  SAG_CHECK_CUDA(cudaMemcpy(dof, off.data(), sizeof(int) * m.n_mels, cudaMemcpyHostToDevice));
+  SAG_CHECK_CUDA(cudaMemcpy(dw, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  m.start = ds; m.len = dl; m.off = dof; m.w = dw;
+  g_mels[{dev, rate}] = m;
+  *out = m;
+  return SAG_OK;
+}
+
+__global__ void __launch_bounds__(256) mel_lsd_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int t,
+                                                      const FftPlan P, const MelBank mel, int n_frames,
+                                                      float* __restrict__ out) {
+  extern __shared__ __align__(16) float2 smem[];
+  __shared__ float red[32];
+  const int n = P.n, nb = n / 2 + 1;
+  float2* b0 = smem;
+  float2* b1 = smem + 2 * n;
+  float* sg = reinterpret_cast<float*>(smem + 4 * n);
+  float* sp = sg + t;
+  float* pw = sp + t;                                   // [2][nb] power spectra of the current frame
+  const int wc = blockIdx.x;                            // window * 3 + channel
+  const float* pg = gt + (int64_t)(wc / 3) * t * 3 + wc % 3;
+  const float* pp = pred + (int64_t)(wc / 3) * t * 3 + wc % 3;
+  for (int i = threadIdx.x; i < t; i += blockDim.x) { sg[i] = __ldg(pg + (int64_t)i * 3); sp[i] = __ldg(pp + (int64_t)i * 3); }
+  const float k10 = 10.f / logf(10.f);
+  float acc = 0.f;
+  for (int f = 0; f < n_frames; ++f) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int j = f * mel.hop + i - n / 2;                  // centred frame over the reflect-padded signal (np.pad mode='reflect')
+      if (j < 0) j = -j;
+      if (j >= t) j = 2 * (t - 1) - j;
+      const float w = __ldg(P.hann + i);
+      b0[i] = make_float2(sg[j] * w, 0.f);
+      b0[n + i] = make_float2(sp[j] * w, 0.f);
+    }
+    const float2* r = block_fft_nf(b0, b1, P, 2);
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      pw[k] = r[k].x * r[k].x + r[k].y * r[k].y;
+      pw[nb + k] = r[n + k].x * r[n + k].x + r[n + k].y * r[n + k].y;
+    }
+    __syncthreads();
+    if (threadIdx.x < mel.n_mels) {
+      const int s0 = __ldg(mel.start + threadIdx.x), ln = __ldg(mel.len + threadIdx.x);
+      const float* w = mel.w + __ldg(mel.off + threadIdx.x);
+      float mg = 0.f, mp = 0.f;
+      for (int k = 0; k < ln; ++k) {
+        const float wk = __ldg(w + k);
+        mg = fmaf(wk, pw[s0 + k], mg);
+        mp = fmaf(wk, pw[nb + s0 + k], mp);
+      }
+      const float d = k10 * (logf(fabsf(mg) + 1e-2f) - logf(fabsf(mp) + 1e-2f));      // myutils.py:98-100
+      acc = fmaf(d, d, acc);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[wc] = sqrtf(acc / (float)(mel.n_mels * n_frames));           // myutils.py:105
+}
+
+int launch_mel_lsd(const float* pred, const float* gt, int batch, int t, int audio_rate, float* out, cudaStream_t st) {
+  SAG_REQUIRE(batch > 0 && audio_rate > 0, SAG_EINVAL, "mel_lsd: bad arguments");
+  MelBank mel;
+  SAG_TRY(get_mel_bank(audio_rate, &mel));
+  SAG_REQUIRE(t > mel.n_fft / 2, SAG_EINVAL, "mel_lsd: %d samples are too few for reflect padding by %d", t, mel.n_fft / 2);
+  FftPlan P;
+  SAG_TRY(get_plan(mel.n_fft, &P));
+  const int n_frames = 1 + t / mel.hop;                 // librosa 0.6 stft with center=True
+  const size_t smem = (size_t)4 * mel.n_fft * sizeof(float2) + (size_t)2 * t * sizeof(float) + (size_t)2 * (mel.n_fft / 2 + 1) * sizeof(float);
+  SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "mel_lsd: %zu bytes of shared memory needed", smem);
+  SAG_CHECK_CUDA(cudaFuncSetAttribute(mel_lsd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mel_lsd_kernel<<<batch * 3, 256, smem, st>>>(pred, gt, t, P, mel, n_frames, out);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+
 // ---- spherical-harmonic projection + RMS map -------------------------------------------------------------------
 struct ShMesh {
   int n_nu, n_phi;

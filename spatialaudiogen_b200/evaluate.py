@@ -4,8 +4,8 @@ Per batch of windows: forward (eval.py:90), the in-graph per-sample metrics (mod
 the Hilbert-envelope distance (myutils.py:109-116), amplitudes (eval.py:197-198) and the 84-direction RMS energy maps
 that feed the EMD (distance.py:41-52, ang_res=30) -- all as GPU kernels.  Rows come out in the reference's
 `eval-detailed.txt` format (`SampleID | <28 metric names>`, eval.py:125-133, 212-215).  The EMD columns (pyemd in the
-reference) come from the exact host solver in libsag.so when the energy maps are requested; the mel_lsd columns
-(librosa) are written as nan.  With several ranks
+reference) come from the exact host solver in libsag.so when the energy maps are requested (nan otherwise); the mel_lsd
+columns (librosa in the reference) from the restated mel spectrogram kernel.  With several ranks
 (one process per GPU) whole batches are sharded and the rows meet in one all-gather (dist.gather_rows).
 """
 from collections import OrderedDict
@@ -25,15 +25,15 @@ ALL_METRICS = ['amplitude/predicted', 'amplitude/gt',
                'emd/dir', 'emd/dir2']                                      # eval.py:125-132
 _COL = {k: i for i, k in enumerate(ALL_METRICS)}
 N_COLS = len(ALL_METRICS)
-# metric_rows gathers its columns from [amp_pred, amp_gt | mse, stft, lsd, snr, env x (Y,Z,X) | the 5 channel means | nan]
-_KEYS = ('mse', 'stft', 'lsd', 'snr', 'env')
-_NAMES = ('mse', 'stft', 'lsd', 'snr', 'env_mse')
+# metric_rows gathers its columns from [amp_pred, amp_gt | mse, stft, lsd, mel_lsd, snr, env x (Y,Z,X) | the 6 channel means | nan]
+_KEYS = ('mse', 'stft', 'lsd', 'mel', 'snr', 'env')
+_NAMES = ('mse', 'stft', 'lsd', 'mel_lsd', 'snr', 'env_mse')
 _PERM_CACHE = {}
 
 
 def _perm(device):
     """Column gather of metric_rows: ALL_METRICS position -> position in the concatenated metric buffer (filled by key,
-    not by position, like eval.py:159-171; mel_lsd / emd columns point at the nan column)."""
+    not by position, like eval.py:159-171; the emd columns point at the nan column until metric_rows fills them)."""
     key = str(device)
     if key not in _PERM_CACHE:
         src = {'amplitude/predicted': 0, 'amplitude/gt': 1}
@@ -46,14 +46,16 @@ def _perm(device):
     return _PERM_CACHE[key]
 
 
-def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False):
+def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False, mel_lsd=True):
     """pred, target (B, T, 3) CUDA, channels (Y, Z, X).  Returns (rows (B, 28) CUDA float32 in ALL_METRICS order,
     maps or None).  maps = (rms_pred, rms_gt), each (B, 7, 12): energy maps of [W | pred or gt] * layout
     (eval.py:147-148, 190), needs `mono` (B, T, 1)."""
     res = M.window_metrics(pred, target, audio_rate)
+    # eval.py:173-178 (myutils.compute_lsd_dist); mel_lsd=False leaves those four columns nan
+    res['mel'] = M.mel_lsd(pred, target, audio_rate) if mel_lsd else torch.full_like(res['mse'], float('nan'))
     B = pred.shape[0]
     # four small launches instead of one per column: [amp | per-channel metrics] -> channel means -> one column gather
-    per_ch = torch.cat([res['amp']] + [res[k] for k in _KEYS], 1)          # (B, 2 + 5*3), channels in (Y, Z, X) order
+    per_ch = torch.cat([res['amp']] + [res[k] for k in _KEYS], 1)          # (B, 2 + 6*3), channels in (Y, Z, X) order
     avg = per_ch[:, 2:].reshape(B, len(_KEYS), 3).mean(2)                  # np.mean over the 3 channels (eval.py:159-171)
     full = torch.cat((per_ch, avg, torch.full((B, 1), float('nan'), dtype=torch.float32, device=pred.device)), 1)
     rows = full.index_select(1, _perm(pred.device))

@@ -30,6 +30,25 @@ def window_metrics(preds, targets, audio_rate=48000, envelope=True):
     return out
 
 
+def mel_lsd(preds, targets, audio_rate=48000):
+    """reference myutils.compute_lsd_dist (myutils.py:96-106) for a batch: preds, targets (B, T, 3) float32 CUDA ->
+    (B, 3) distances between the 128-band mel power spectrograms in dB (librosa melspectrogram restated in metrics.cu)."""
+    preds = L.f32(preds)
+    targets = L.f32(targets, preds.device)
+    if preds.shape != targets.shape or preds.dim() != 3 or preds.shape[2] != 3:
+        raise ValueError('preds/targets must both be (B, T, 3), got %s and %s' % (tuple(preds.shape), tuple(targets.shape)))
+    B, T, _ = preds.shape
+    with torch.cuda.device(preds.device):
+        out = torch.empty((B, 3), dtype=torch.float32, device=preds.device)
+        L.check(L.lib().sag_mel_lsd(L.ptr(preds), L.ptr(targets), B, T, int(audio_rate), L.ptr(out), L.stream()))
+    return out
+
+
+def compute_lsd_dist(pred, gt, rate):
+    """reference myutils.compute_lsd_dist for one window: pred, gt (T, 3) -> (3,)."""
+    return mel_lsd(L.f32(pred)[None], L.f32(gt)[None], rate)[0]
+
+
 def compute_envelope_dist(pred, gt):
     """reference myutils.py:109-116 for one window: pred, gt (T, 3) -> (3,)."""
     r = window_metrics(L.f32(pred)[None], L.f32(gt)[None])

@@ -487,7 +487,10 @@ def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
             assert np.allclose(rows[:, col[name + '/' + ch]], r[:, i], rtol=2e-4, atol=1e-7)
     env_r = np.stack([O.compute_envelope_dist(pred[b], gt[b]) for b in range(B)])
     assert np.allclose(rows[:, col['env_mse/X']], env_r[:, 2], rtol=2e-4)
-    assert np.isnan(rows[:, col['mel_lsd/avg']]).all()
+    mel_r = np.stack([O.compute_lsd_dist(pred[b], gt[b], 48000) for b in range(B)])      # myutils.py:96-106
+    assert np.allclose(rows[:, col['mel_lsd/avg']], mel_r.mean(1), rtol=1e-3)
+    for i, ch in enumerate('YZX'):
+        assert np.allclose(rows[:, col['mel_lsd/' + ch]], mel_r[:, i], rtol=1e-3)
     for b in range(B):
         rp = O.ambix_rms_map(np.concatenate((mono[b], pred[b]), 1) * layout[b], 30.)
         assert _rel(maps[0][b], np.ascontiguousarray(rp)) < 1e-5
