@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from . import myutils, tf_checkpoint
+from . import myutils, readers, tf_checkpoint
 from .definitions import AUDIO, VIDEO, FLOW, NO_SEPARATION
 from .model import SptAudioGen, SptAudioGenParams
 
@@ -92,3 +92,24 @@ class W2XYZ(object):
             mono.append(np.copy(a[:, ss:ss + self.model.snd_dur, :1]).reshape(-1, 1))
         mono = np.concatenate(mono, 0)
         return np.concatenate((mono, np.concatenate(pred, 0)), 1)          # float64, like numpy promotes in deploy.py:151
+
+    def deploy(self, input_folder, deploy_start, deploy_duration):
+        """deploy.py:90-152: read the windows of `input_folder` (the per-video folder layout of readers.SampleReader)
+        scheduled by its audio_pow.lst from `deploy_start` for `deploy_duration` seconds -- the schedule is shifted so
+        that the first window sits exactly at deploy_start (deploy.py:108-109) -- and generate their ambisonics.
+        Returns (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
+        p = self.params
+        reader = readers.SampleReader(input_folder, ambi_order=p.ambi_order, audio_rate=p.audio_rate, video_rate=p.video_rate,
+                                      context=p.context, duration=self.duration, return_video=VIDEO in p.encoders,
+                                      img_prep=myutils.img_prep_fcn(), return_flow=FLOW in p.encoders, start_time=deploy_start,
+                                      sample_duration=deploy_duration, skip_silence_thr=None, shuffle=False,
+                                      random_rotations=False, skip_rate=None)
+        if not reader.chunks_t:
+            raise ValueError('%s has no windows in [%s, %s)' % (input_folder, deploy_start, deploy_start + deploy_duration))
+        dt = reader.chunks_t[0] - deploy_start
+        reader.chunks_t = [t - dt for t in reader.chunks_t]
+        chunks = list(reader.loop_chunks())
+        ambix = np.stack([c['ambix'] for c in chunks], 0)
+        video = np.stack([c['video'] for c in chunks], 0).astype(np.float32) if VIDEO in p.encoders else None
+        flow = np.stack([c['flow'] for c in chunks], 0).astype(np.float32) if FLOW in p.encoders else None
+        return self.deploy_windows(ambix, video, flow)

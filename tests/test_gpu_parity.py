@@ -465,6 +465,26 @@ def test_w2xyz_restores_a_tf_checkpoint_bundle(tmp_path):
     assert np.array_equal(a, b)
 
 
+def test_w2xyz_deploy_reads_a_video_folder(tmp_path):
+    """deploy.py:90-152 end to end: wav / jpg files on disk -> readers.SampleReader -> batches -> [W, Y, Z, X] rows; equal to
+    handing the same windows to deploy_windows."""
+    from spatialaudiogen_b200.deploy import W2XYZ
+    from spatialaudiogen_b200 import readers as R
+    from test_host import _make_video_folder
+    folder, full = _make_video_folder(str(tmp_path), seconds=4)
+    enc = ['audio', 'video']
+    w = W2XYZ(params=_P(enc), weights=Wt.init_weights(enc, separation='unet_mask', seed=9, stress=True))
+    out = w.deploy(folder, 1.2, 2.0)                                     # windows at 1.2 and 2.2 s (schedule 1.5, 2.5 shifted by 0.3)
+    assert out.shape == (2 * 4800, 4) and out.dtype == np.float64
+    s0 = int(1.2 * 48000)                                                # W = the mono crop at the window centre (deploy.py:143-147)
+    assert np.array_equal(out[:4800, 0], full[s0:s0 + 4800, 0])
+    r = R.SampleReader(folder, shuffle=False, random_rotations=False, start_time=1.2, sample_duration=2.0, img_prep=lambda x: x / 255. - 0.5)
+    r.chunks_t = [t - 0.3 for t in r.chunks_t]
+    chunks = list(r.loop_chunks())
+    ref = w.deploy_windows(np.stack([c['ambix'] for c in chunks]), np.stack([c['video'] for c in chunks]).astype(np.float32))
+    assert np.array_equal(out, ref)
+
+
 def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
     from spatialaudiogen_b200 import evaluate as E
     rng = np.random.RandomState(3)

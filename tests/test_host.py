@@ -1,5 +1,7 @@
 """CPU tests of the host-side mirror of the reference interface that need no GPU: parameter parsing with the
 reference's fall-backs (myutils.py:40-85), constants (definitions.py), checkpoint layout helpers."""
+import os
+
 import numpy as np
 
 from spatialaudiogen_b200 import definitions as Df
@@ -64,3 +66,58 @@ def test_emd_hat_host_solver_matches_the_defining_lp():
     import pytest
     with pytest.raises(ValueError):
         M.emd_hat(-e3, e3, D)
+
+
+def _make_video_folder(root, seconds=4, flow=False, seed=0):
+    """A per-video folder in the layout scraping/preprocess.py writes (readers.py docstring); returns (folder, ambix)."""
+    import numpy as np
+    from PIL import Image
+    from spatialaudiogen_b200 import readers as R
+    folder = os.path.join(root, 'vidA')
+    for sub in ('ambix', 'video') + (('flow',) if flow else ()):
+        os.makedirs(os.path.join(folder, sub))
+    rng = np.random.RandomState(seed)
+    full = np.round(rng.uniform(-0.5, 0.5, size=(seconds * 48000, 4)) * 32768) / 32768      # exactly representable in PCM16
+    for i in range(seconds):
+        R.save_wav(os.path.join(folder, 'ambix', '%06d.wav' % i), full[i * 48000:(i + 1) * 48000], 48000)
+    for i in range(seconds * 10):
+        Image.fromarray(rng.randint(0, 256, size=(224, 448, 3)).astype(np.uint8)).save(os.path.join(folder, 'video', '%06d.jpg' % i), quality=95)
+        if flow:
+            Image.fromarray(rng.randint(0, 256, size=(224, 448, 3)).astype(np.uint8)).save(os.path.join(folder, 'flow', '%06d.jpg' % i), quality=95)
+    if flow:
+        np.save(os.path.join(folder, 'flow', 'flow_limits.npy'), np.stack([np.full(seconds * 10, 1.0), np.full(seconds * 10, 21.0)], 1))
+    with open(os.path.join(folder, 'audio_pow.lst'), 'w') as f:
+        for k in range(seconds):
+            f.write('%.1f %.3f\n' % (0.5 + k, 0.05 if k == 1 else 0.3))
+    return folder, full
+
+
+def test_sample_reader_follows_the_reference_schedule_and_padding(tmp_path):
+    """feeder.py:50-278 on a synthetic folder: chunk ids / times from audio_pow.lst, audio windows centred on the chunk
+    with zero padding at both clip edges, frame index int(t * 10), flow de-quantisation, silence / duration filters."""
+    import numpy as np
+    from PIL import Image
+    from spatialaudiogen_b200 import readers as R
+    folder, full = _make_video_folder(str(tmp_path), seconds=4, flow=True)
+    r = R.SampleReader(folder, shuffle=False, random_rotations=False, return_flow=True, img_prep=lambda x: x / 255. - 0.5)
+    assert r.chunks_t == [0.5, 1.5, 2.5, 3.5] and r.audio_size == 52799 and r.video_size == 1
+    c = r.get()
+    assert c['id'] == 'vidA 0.5' and c['ambix'].shape == (52799, 4) and c['video'].shape == (1, 224, 448, 3)
+    assert np.array_equal(c['ambix'], full[:52799])                      # window [t - 0.5, t + 0.6) s, bit-exact PCM16 decode
+    img = np.asarray(Image.open(os.path.join(folder, 'video', '000005.jpg')).convert('RGB'))
+    assert np.array_equal(c['video'][0], img / 255. - 0.5)               # frame int(0.5 * 10), myutils.img_prep_fcn
+    raw = np.asarray(Image.open(os.path.join(folder, 'flow', '000005.jpg')).convert('RGB')).astype(np.float32)
+    mag = raw[:, :, 2] * (21.0 - 1.0) / 255. + 1.0                       # feeder.py:153-160
+    ang = raw[:, :, 0] * (2 * np.pi) / 255.
+    assert np.allclose(c['flow'][0, :, :, 2], mag) and np.allclose(c['flow'][0, :, :, 0], mag * np.cos(ang), atol=1e-4)
+    assert np.allclose(c['flow'][0, :, :, 1], mag * np.sin(ang), atol=1e-4)
+    r.get(); r.get()
+    c = r.get()                                                          # t = 3.5: 1 s of audio left, 4799 zeros after it
+    assert np.array_equal(c['ambix'][:48000], full[3 * 48000:]) and not c['ambix'][48000:].any()
+    assert r.get() is None
+    a = R.AudioReader(os.path.join(folder, 'ambix'), 48000).get(-0.25, 52799)        # before the start: 12000 zeros first
+    assert not a[:12000].any() and np.array_equal(a[12000:], full[:52799 - 12000])
+    assert R.SampleReader(folder, shuffle=False, skip_silence_thr=0.2, return_video=False).chunks_t == [0.5, 2.5, 3.5]
+    assert R.SampleReader(folder, shuffle=False, start_time=1.0, sample_duration=2.0, return_video=False).chunks_t == [1.5, 2.5]
+    rot = R.AudioReader(os.path.join(folder, 'ambix'), 48000).get(0.0, 100, rotation=np.pi / 2)   # yaw by 90 deg: Y' = X, X' = -Y
+    assert np.allclose(rot[:, 1], full[:100, 3]) and np.allclose(rot[:, 3], -full[:100, 1]) and np.allclose(rot[:, [0, 2]], full[:100, [0, 2]])
