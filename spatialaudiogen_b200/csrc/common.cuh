@@ -231,6 +231,12 @@ int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int 
 int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_s, int tracks, int n_frames, int wind,
                  int n_overlap, int crop0, int n_out, float* out, cudaStream_t st);
 
+// fused masked inverse STFT + mixing (model.py:334-347 + 424-432 by linearity): out (rows, t_out, 3); see fft.cu
+int istft_mix_supported(int tracks, int t_out, int segments, int wind);
+size_t istft_mix_gain_floats(int rows, int n_frames, int wind, int segments);
+int launch_istft_mix(const float* S, const float* mask, const float* loc, float* gains, int rows, int tracks, int n_frames, int wind,
+                     int n_overlap, int crop0, int t_out, int segments, float* out, cudaStream_t st);
+
 // metrics.cu
 int launch_metrics(const float* pred, const float* gt, int batch, int t, int audio_rate, float* stft_ps, float* lsd_ps,
                    float* mse_ps, float* snr_ps, float* env_ps, float* amp, void* scratch, cudaStream_t st);

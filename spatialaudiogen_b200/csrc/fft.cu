@@ -243,9 +243,10 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
   const int n_seg = cdiv(n_out, ISTFT_SEG);
   int nfr = ISTFT_NFR;
   size_t smem = 0;
+  static const int smem_cap_kb = [] { const char* v = getenv("SAG_ISTFT_SMEM_KB"); return v ? atoi(v) : 56; }();   // tuning knob
   for (; nfr >= 1; nfr >>= 1) {
     smem = 2 * sizeof(float2) * (size_t)wind * nfr;
-    if (smem <= 56 * 1024 || nfr == 1) break;              // four CTAs per SM when possible
+    if (smem <= (size_t)smem_cap_kb * 1024 || nfr == 1) break;   // four CTAs per SM when possible
   }
   SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft: %zu bytes of shared memory needed", smem);
   const float inv_scale = 1.0f / ((float)wind * (float)n_overlap);
@@ -253,6 +254,172 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
   SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   launch_pdl(istft_pair_kernel, dim3(rows_s * pairs, n_seg), dim3(256), smem, st, reinterpret_cast<const float2*>(S), mask, apply_sigmoid,
              tracks, n_frames, p, hop, nf, p0, n_out, inv_scale, nfr, out);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// ---- K6+K9 fused: masked inverse STFT + time-varying mixing -----------------------------------------------------------
+// The decode of inference_ops (model.py:424-432) is linear in the separated tracks, and so are ifft / overlap-add:
+//   out[n, o] = sum_k W[o, k, seg(n)] * x_sep[k, n] + b[o, seg(n)]
+//             = OLA( real ifft( S[f] * G[o, seg][f] ) )[n] / (n_overlap * N) + b[o, seg],
+//   G[o, seg][f, bin] = sum_k W[o, k, seg] * sigmoid(m_k[f, bin])
+// for the samples n of one localization segment `seg` (the weights are piecewise constant: model.py:262-263).  So instead
+// of 32 inverse transforms per frame (16 with two tracks per complex FFT) the 3 output channels need 1.5.
+//   mask_gains_kernel : streams the 32 mask planes once (one thread per (window, frame, bin), 32 independent coalesced
+//                       loads in flight) and folds them into the 9 gains (3 segments x 3 channels) -- HBM/L2 bound.
+//   istft_mix_kernel  : one CTA per (window, segment): channels (Y, Z) ride one complex transform per frame, channel X of
+//                       two consecutive frames the third; register overlap-add; + bias; writes (B, T, 3).
+// x_sep is never formed: this is the production path (sag_forward); inference_ops, which exposes `sep_channels`, keeps
+// the two-kernel path (istft_pair_kernel + mix_kernel).
+constexpr int MIX_SLOTS = 8;              // output positions tid + 256*s of a segment (segments up to 2048 samples)
+constexpr int GAIN_MAX_TRACKS = 64;
+
+// gains (rows, segments*3, n_frames, n) <- mask (rows*tracks, n_frames, n) logits, loc (rows, segments, 3*(tracks+1))
+__global__ void __launch_bounds__(256) mask_gains_kernel(const float* __restrict__ mask, const float* __restrict__ loc, int tracks,
+                                                         int n_frames, int n, int segments, float* __restrict__ gains) {
+  extern __shared__ float s_w[];          // [segments*3][tracks]
+  pdl_prologue();
+  const int b = blockIdx.y, f = blockIdx.x / (n / 256), k = (blockIdx.x % (n / 256)) * 256 + threadIdx.x;
+  const int K1 = tracks + 1, ng = segments * 3;
+  for (int i = threadIdx.x; i < ng * tracks; i += blockDim.x) s_w[i] = __ldg(loc + ((int64_t)b * ng + i / tracks) * K1 + i % tracks);
+  __syncthreads();
+  const int64_t plane = (int64_t)n_frames * n;
+  const float* mp = mask + (int64_t)b * tracks * plane + (int64_t)f * n + k;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < tracks; k0 += 8) {
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = k0 + u < tracks ? __ldg(mp + (int64_t)(k0 + u) * plane) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (k0 + u >= tracks) break;
+      const float sg = 1.f / (1.f + expf(-m[u]));             // tf.sigmoid (model.py:334)
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        if (i < ng) acc[i] = fmaf(s_w[i * tracks + k0 + u], sg, acc[i]);
+    }
+  }
+  float* gp = gains + (int64_t)b * ng * plane + (int64_t)f * n + k;
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    if (i < ng) gp[(int64_t)i * plane] = acc[i];
+}
+
+__global__ void __launch_bounds__(256, 2) istft_mix_kernel(const float2* __restrict__ S, const float* __restrict__ gains,
+                                                           const float* __restrict__ loc, int tracks, int n_frames,
+                                                           const FftPlan p, int hop, int nf_total, int p0_all, int t_out,
+                                                           int segments, float inv_scale, float* __restrict__ out) {
+  extern __shared__ __align__(16) float2 smem[];
+  const int n = p.n;
+  float2* buf0 = smem;                    // [3][n]: frame f (Y, Z), frame f+1 (Y, Z), X of both frames
+  float2* buf1 = smem + 3 * n;
+  pdl_prologue();
+  const int b = blockIdx.x / segments, seg = blockIdx.x % segments;
+  const int seg_len = t_out / segments, K1 = tracks + 1;
+  const int p0 = p0_all + seg * seg_len;                     // frame-space position of the segment's first sample
+  const int f_lo = p0 - n + 1 <= 0 ? 0 : (p0 - n + 1 + hop - 1) / hop;
+  const int f_hi = min((p0 + seg_len - 1) / hop, nf_total - 1);
+  float acc[3][MIX_SLOTS];
+#pragma unroll
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int sl = 0; sl < MIX_SLOTS; ++sl) acc[o][sl] = 0.f;
+  const int64_t plane = (int64_t)n_frames * n;               // between gain planes
+  const float* gb = gains + ((int64_t)b * segments + seg) * 3 * plane;
+  for (int f0 = f_lo; f0 <= f_hi; f0 += 2) {
+    const int nf = min(2, f_hi - f0 + 1);
+    __syncthreads();                                         // previous pair fully consumed
+    if (nf == 1)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) buf0[n + i] = make_float2(0.f, 0.f);
+    for (int g = 0; g < nf; ++g) {
+      const float2* s = S + ((int64_t)b * n_frames + (f0 + g)) * (int64_t)n;
+      const float* gf = gb + (int64_t)(f0 + g) * n;
+      for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
+        const int kn = k == 0 ? 0 : n - k;
+        const float2 xk = __ldg(s + k), xn = __ldg(s + kn);
+        float gk[3], gn[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) { gk[o] = __ldg(gf + o * plane + k); gn[o] = __ldg(gf + o * plane + kn); }
+        // Hermitian parts of the three gain-weighted spectra at bin k (see istft_pair_kernel)
+        float2 y[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) y[o] = make_float2(0.5f * (gk[o] * xk.x + gn[o] * xn.x), 0.5f * (gk[o] * xk.y - gn[o] * xn.y));
+        // Z = y0 + i y1, stored conjugated: ifft(Z) = conj(fft(conj Z)) / N
+        buf0[g * n + k] = make_float2(y[0].x - y[1].y, -(y[0].y + y[1].x));
+        buf0[g * n + kn] = make_float2(y[0].x + y[1].y, -(y[1].x - y[0].y));
+        // third transform: X of frame f0 as the real carrier, X of frame f0+1 as the imaginary one (same thread owns the
+        // bin in both rounds)
+        if (g == 0) {
+          buf0[2 * n + k] = make_float2(y[2].x, -y[2].y);
+          buf0[2 * n + kn] = make_float2(y[2].x, y[2].y);
+        } else {
+          float2 u = buf0[2 * n + k];
+          buf0[2 * n + k] = make_float2(u.x - y[2].y, u.y - y[2].x);
+          if (kn != k) {
+            u = buf0[2 * n + kn];
+            buf0[2 * n + kn] = make_float2(u.x + y[2].y, u.y - y[2].x);
+          }
+        }
+      }
+    }
+    const float2* res = block_fft_nf(buf0, buf1, p, 3);       // res[0..1] = N (y_Y - i y_Z) of the two frames, res[2] = N (x_f - i x_f+1)
+#pragma unroll
+    for (int sl = 0; sl < MIX_SLOTS; ++sl) {
+      const int j = threadIdx.x + 256 * sl;
+      if (j < seg_len) {
+        const int i0 = p0 + j - f0 * hop, i1 = i0 - hop;       // offsets inside frame f0 / f0+1
+        if (i0 >= 0 && i0 < n) {
+          const float2 r = res[i0], x = res[2 * n + i0];
+          acc[0][sl] += r.x; acc[1][sl] -= r.y; acc[2][sl] += x.x;
+        }
+        if (nf == 2 && i1 >= 0 && i1 < n) {
+          const float2 r = res[n + i1], x = res[2 * n + i1];
+          acc[0][sl] += r.x; acc[1][sl] -= r.y; acc[2][sl] -= x.y;
+        }
+      }
+    }
+  }
+  const float* lb = loc + ((int64_t)b * segments + seg) * 3 * K1 + tracks;     // bias of channel o at lb[o * K1]
+  float* ob = out + ((int64_t)b * t_out + (int64_t)seg * seg_len) * 3;
+#pragma unroll
+  for (int sl = 0; sl < MIX_SLOTS; ++sl) {
+    const int j = threadIdx.x + 256 * sl;
+    if (j < seg_len) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) ob[(int64_t)j * 3 + o] = fmaf(acc[o][sl], inv_scale, __ldg(lb + o * K1));
+    }
+  }
+}
+
+int istft_mix_supported(int tracks, int t_out, int segments, int wind) {
+  return segments > 0 && segments <= 3 && t_out % segments == 0 && t_out / segments <= 256 * MIX_SLOTS && tracks >= 1 &&
+         tracks <= GAIN_MAX_TRACKS && wind % 256 == 0;
+}
+size_t istft_mix_gain_floats(int rows, int n_frames, int wind, int segments) { return (size_t)rows * segments * 3 * n_frames * wind; }
+
+// S (rows, n_frames, wind) complex, mask (rows*tracks, n_frames, wind) logits, loc (rows, segments, 3*(tracks+1));
+// gains: scratch of istft_mix_gain_floats() floats; out (rows, t_out, 3) = samples [crop0, crop0 + t_out) of the mixed
+// inverse STFT.
+int launch_istft_mix(const float* S, const float* mask, const float* loc, float* gains, int rows, int tracks, int n_frames, int wind,
+                     int n_overlap, int crop0, int t_out, int segments, float* out, cudaStream_t st) {
+  SAG_REQUIRE(rows > 0 && n_overlap > 0 && wind % n_overlap == 0 && mask != nullptr && loc != nullptr && gains != nullptr, SAG_EINVAL, "istft_mix: bad arguments");
+  SAG_REQUIRE(istft_mix_supported(tracks, t_out, segments, wind), SAG_EUNSUPPORTED, "istft_mix: %d samples / %d segments / %d tracks", t_out, segments, tracks);
+  const int hop = wind / n_overlap;
+  const int nf = (n_frames / n_overlap) * n_overlap;      // myutils.py:187-188
+  const int full = (nf / n_overlap) * wind - (n_overlap - 1) * hop;
+  SAG_REQUIRE(nf > 0 && crop0 >= 0 && crop0 + t_out <= full, SAG_EINVAL, "istft_mix: crop [%d,%d) outside the %d output samples", crop0, crop0 + t_out, full);
+  FftPlan p;
+  SAG_TRY(get_plan(wind, &p));
+  launch_pdl(mask_gains_kernel, dim3(n_frames * (wind / 256), rows), dim3(256), sizeof(float) * segments * 3 * tracks, st, mask, loc, tracks,
+             n_frames, wind, segments, gains);
+  SAG_LAUNCH_CHECK();
+  const size_t smem = 6 * sizeof(float2) * (size_t)wind;
+  SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft_mix: %zu bytes of shared memory needed", smem);
+  SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  launch_pdl(istft_mix_kernel, dim3(rows * segments), dim3(256), smem, st, reinterpret_cast<const float2*>(S), (const float*)gains, loc, tracks,
+             n_frames, p, hop, nf, crop0 + (n_overlap - 1) * hop, t_out, segments, 1.0f / ((float)wind * (float)n_overlap), out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }

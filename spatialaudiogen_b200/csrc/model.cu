@@ -600,6 +600,8 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
     // kernel does not take: compact them first (test-only path, skip_unused == 0).
     float* S2 = full ? ar.alloc<float>((int64_t)B * n_msk * wind * 2) : S;
     float* m2 = full ? ar.alloc<float>((int64_t)B * K * n_msk * OW) : mask;
+    const bool fuse_mix = istft_mix_supported(K, T, nt, wind) != 0;
+    float* gains = fuse_mix ? ar.alloc<float>((int64_t)istft_mix_gain_floats(B, n_msk, wind, nt)) : nullptr;
     if (!ar.dry) {
       if (full) {
         SAG_CHECK_CUDA(cudaMemcpy2DAsync(S2, sizeof(float) * n_msk * wind * 2, S_all + (int64_t)d.mask_ss * wind * 2,
@@ -608,6 +610,14 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
         SAG_CHECK_CUDA(cudaMemcpy2DAsync(m2, sizeof(float) * n_msk * OW, mask + (int64_t)(d.mask_ss - d.mask_skip) * OW,
                                          sizeof(float) * nr * OW, sizeof(float) * n_msk * OW, (size_t)B * K,
                                          cudaMemcpyDeviceToDevice, st));
+      }
+      if (!h->keep_sep_channels && fuse_mix) {
+        // production path: inverse STFT and mixing fused by linearity (x_sep is never formed)
+        ProfScope ps(PROF_ISTFT, 5.0 * wind * std::log2((double)wind) * B * 1.5 * n_msk + 18.0 * B * K * (double)n_msk * wind,
+                     4.0 * B * ((double)K * n_msk * wind + 2.0 * n_msk * wind + 3.0 * T), st);
+        SAG_TRY(launch_istft_mix(S2, m2, loc, gains, B, K, n_msk, wind, 4, d.final_crop, T, nt, out, st));
+        h->last_launches = g_launch_count;
+        return SAG_OK;
       }
       ProfScope ps(PROF_ISTFT, 5.0 * wind * std::log2((double)wind) * B * K * n_msk,
                    4.0 * B * ((double)K * n_msk * wind + 2.0 * n_msk * wind + (double)K * T), st);

@@ -166,7 +166,8 @@ class SptAudioGen(object):
             self.precision = value
             value = L.PRECISIONS[value]
         L.check(L.lib().sag_set_option(self._h, key.encode(), int(value)))
-        self._ws_batch = 0
+        if key not in ('keep_sep_channels', 'profile', 'tma_gather', 'cta_pair'):     # (these do not change the workspace plan)
+            self._ws_batch = 0
 
     # ---- forward ---------------------------------------------------------------------------------------------
     def _workspace(self, B):
@@ -212,7 +213,14 @@ class SptAudioGen(object):
                     ins[key] = t
             out = torch.empty((B, self.snd_dur, self.num_ambi_channels - self.ambi_order ** 2), dtype=torch.float32,
                               device=self.device)
-            self.forward_into(audio, ins.get(VIDEO), ins.get(FLOW), out)
+            # this call exposes the graph's intermediate tensors (`ends`, `sep_channels`) like the reference's
+            # inference_ops: the separated tracks must exist, so the inverse STFT and the mixing run as two kernels;
+            # forward_into / inference_stream / W2XYZ (the deploy and eval hot loops) use the fused kernel
+            self.set_option('keep_sep_channels', 1)
+            try:
+                self.forward_into(audio, ins.get(VIDEO), ins.get(FLOW), out)
+            finally:
+                self.set_option('keep_sep_channels', 0)
             self._collect_ends()
         return out
 

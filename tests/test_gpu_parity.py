@@ -349,6 +349,29 @@ def test_forward_tma_gather_matches_cp_async_gather():
     assert _rel(y1, y0) < 1e-4
 
 
+def test_fused_istft_mix_matches_the_two_kernel_path_and_the_oracle():
+    """forward_into (deploy / eval hot loop) folds the 32->3 mixing into the inverse STFT by linearity; inference_ops
+    keeps x_sep and mixes afterwards.  Same waveform to fp32 rounding, and within tolerance of the oracle."""
+    for enc, B in ((['audio'], 3), (['audio', 'video'], 2)):
+        ref, m = _models(enc, 'unet_mask', 13, B, precision='bf16x3')
+        a = _audio(B, 61)
+        v = _video(B, 62) if 'video' in enc else None
+        y_two = m.inference_ops(cu(a), video=None if v is None else cu(v)).clone()
+        assert m.sep_channels is not None
+        y_fused = torch.empty_like(y_two)
+        m.forward_into(cu(a), None if v is None else cu(v), None, y_fused)
+        torch.cuda.synchronize()
+        assert _rel(y_fused, y_two) < (2e-5 if v is None else 1e-4)
+        assert _rel(y_fused, ref.inference_ops(a, video=v)) < 1e-3
+    # exact-arithmetic check of the fusion itself on the fp32 path, B = 1 (one window: segments x channels)
+    ref, m = _models(['audio'], 'unet_mask', 14, 1, precision='fp32')
+    a = _audio(1, 63)
+    y = torch.empty((1, 4800, 3), device='cuda')
+    m.forward_into(cu(a), None, None, y)
+    torch.cuda.synchronize()
+    assert _rel(y, ref.inference_ops(a)) < 1e-4
+
+
 def test_forward_cta_pair_matches_single_cta():
     """cta_group::2 (two M tiles per cluster, each CTA feeding half of every weight tile) computes the same products in
     the same order as the single-CTA kernel: bit-identical without batch-norm atomics, to rounding with them."""
