@@ -274,51 +274,66 @@ int launch_istft(const float* S, const float* mask, int apply_sigmoid, int rows_
 constexpr int MIX_SLOTS = 8;              // output positions tid + 256*s of a segment (segments up to 2048 samples)
 constexpr int GAIN_MAX_TRACKS = 64;
 
-// gains (rows, segments*3, n_frames, n) <- mask (rows*tracks, n_frames, n) logits, loc (rows, segments, 3*(tracks+1))
+// gains (rows, segments*3, n_frames, n) <- mask (rows*tracks, n_frames, n) logits, loc (rows, segments, 3*(tracks+1)).
+// One thread per 4 consecutive bins: 16-byte loads, every weight fetched from shared memory serves 4 bins.
 __global__ void __launch_bounds__(256) mask_gains_kernel(const float* __restrict__ mask, const float* __restrict__ loc, int tracks,
                                                          int n_frames, int n, int segments, float* __restrict__ gains) {
-  extern __shared__ float s_w[];          // [segments*3][tracks]
+  extern __shared__ float s_w[];          // [tracks][12]: the (up to) 9 weights of a track side by side
   pdl_prologue();
-  const int b = blockIdx.y, f = blockIdx.x / (n / 256), k = (blockIdx.x % (n / 256)) * 256 + threadIdx.x;
+  const int per_frame = n / 1024;
+  const int b = blockIdx.y, f = blockIdx.x / per_frame, k = ((blockIdx.x % per_frame) * 256 + threadIdx.x) * 4;
   const int K1 = tracks + 1, ng = segments * 3;
-  for (int i = threadIdx.x; i < ng * tracks; i += blockDim.x) s_w[i] = __ldg(loc + ((int64_t)b * ng + i / tracks) * K1 + i % tracks);
+  for (int i = threadIdx.x; i < 12 * tracks; i += blockDim.x) {
+    const int kk = i / 12, gi = i % 12;
+    s_w[i] = gi < ng ? __ldg(loc + ((int64_t)b * ng + gi) * K1 + kk) : 0.f;
+  }
   __syncthreads();
   const int64_t plane = (int64_t)n_frames * n;
   const float* mp = mask + (int64_t)b * tracks * plane + (int64_t)f * n + k;
-  float acc[9];
+  float4 acc[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 9; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k0 = 0; k0 < tracks; k0 += 8) {
-    float m[8];
+    float4 m[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) m[u] = k0 + u < tracks ? __ldg(mp + (int64_t)(k0 + u) * plane) : 0.f;
+    for (int u = 0; u < 8; ++u)
+      m[u] = k0 + u < tracks ? __ldg(reinterpret_cast<const float4*>(mp + (int64_t)(k0 + u) * plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (k0 + u >= tracks) break;
-      const float sg = 1.f / (1.f + expf(-m[u]));             // tf.sigmoid (model.py:334)
+      float4 sg;                                             // tf.sigmoid (model.py:334)
+      sg.x = 1.f / (1.f + expf(-m[u].x)); sg.y = 1.f / (1.f + expf(-m[u].y));
+      sg.z = 1.f / (1.f + expf(-m[u].z)); sg.w = 1.f / (1.f + expf(-m[u].w));
+      const float4* w4 = reinterpret_cast<const float4*>(s_w + (k0 + u) * 12);
+      const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+      const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
 #pragma unroll
-      for (int i = 0; i < 9; ++i)
-        if (i < ng) acc[i] = fmaf(s_w[i * tracks + k0 + u], sg, acc[i]);
+      for (int i = 0; i < 9; ++i) {
+        acc[i].x = fmaf(w[i], sg.x, acc[i].x); acc[i].y = fmaf(w[i], sg.y, acc[i].y);
+        acc[i].z = fmaf(w[i], sg.z, acc[i].z); acc[i].w = fmaf(w[i], sg.w, acc[i].w);
+      }
     }
   }
   float* gp = gains + (int64_t)b * ng * plane + (int64_t)f * n + k;
 #pragma unroll
   for (int i = 0; i < 9; ++i)
-    if (i < ng) gp[(int64_t)i * plane] = acc[i];
+    if (i < ng) *reinterpret_cast<float4*>(gp + (int64_t)i * plane) = acc[i];
 }
 
 __global__ void __launch_bounds__(256, 2) istft_mix_kernel(const float2* __restrict__ S, const float* __restrict__ gains,
                                                            const float* __restrict__ loc, int tracks, int n_frames,
                                                            const FftPlan p, int hop, int nf_total, int p0_all, int t_out,
-                                                           int segments, float inv_scale, float* __restrict__ out) {
+                                                           int segments, int n_sub, float inv_scale, float* __restrict__ out) {
   extern __shared__ __align__(16) float2 smem[];
   const int n = p.n;
   float2* buf0 = smem;                    // [3][n]: frame f (Y, Z), frame f+1 (Y, Z), X of both frames
   float2* buf1 = smem + 3 * n;
   pdl_prologue();
-  const int b = blockIdx.x / segments, seg = blockIdx.x % segments;
-  const int seg_len = t_out / segments, K1 = tracks + 1;
-  const int p0 = p0_all + seg * seg_len;                     // frame-space position of the segment's first sample
+  // CTA -> (window, localization segment, part of the segment): parts shorten the frame loop and fill more SMs
+  const int sub = blockIdx.x % n_sub, seg = (blockIdx.x / n_sub) % segments, b = blockIdx.x / (n_sub * segments);
+  const int seg_len = t_out / segments / n_sub, K1 = tracks + 1;
+  const int out0 = seg * (t_out / segments) + sub * seg_len;  // first output sample of this CTA
+  const int p0 = p0_all + out0;                              // its frame-space position
   const int f_lo = p0 - n + 1 <= 0 ? 0 : (p0 - n + 1 + hop - 1) / hop;
   const int f_hi = min((p0 + seg_len - 1) / hop, nf_total - 1);
   float acc[3][MIX_SLOTS];
@@ -382,7 +397,7 @@ __global__ void __launch_bounds__(256, 2) istft_mix_kernel(const float2* __restr
     }
   }
   const float* lb = loc + ((int64_t)b * segments + seg) * 3 * K1 + tracks;     // bias of channel o at lb[o * K1]
-  float* ob = out + ((int64_t)b * t_out + (int64_t)seg * seg_len) * 3;
+  float* ob = out + ((int64_t)b * t_out + out0) * 3;
 #pragma unroll
   for (int sl = 0; sl < MIX_SLOTS; ++sl) {
     const int j = threadIdx.x + 256 * sl;
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(256, 2) istft_mix_kernel(const float2* __restr
 
 int istft_mix_supported(int tracks, int t_out, int segments, int wind) {
   return segments > 0 && segments <= 3 && t_out % segments == 0 && t_out / segments <= 256 * MIX_SLOTS && tracks >= 1 &&
-         tracks <= GAIN_MAX_TRACKS && wind % 256 == 0;
+         tracks <= GAIN_MAX_TRACKS && wind % 1024 == 0;
 }
 size_t istft_mix_gain_floats(int rows, int n_frames, int wind, int segments) { return (size_t)rows * segments * 3 * n_frames * wind; }
 
@@ -412,14 +427,17 @@ int launch_istft_mix(const float* S, const float* mask, const float* loc, float*
   SAG_REQUIRE(nf > 0 && crop0 >= 0 && crop0 + t_out <= full, SAG_EINVAL, "istft_mix: crop [%d,%d) outside the %d output samples", crop0, crop0 + t_out, full);
   FftPlan p;
   SAG_TRY(get_plan(wind, &p));
-  launch_pdl(mask_gains_kernel, dim3(n_frames * (wind / 256), rows), dim3(256), sizeof(float) * segments * 3 * tracks, st, mask, loc, tracks,
+  launch_pdl(mask_gains_kernel, dim3(n_frames * (wind / 1024), rows), dim3(256), sizeof(float) * 12 * tracks, st, mask, loc, tracks,
              n_frames, wind, segments, gains);
   SAG_LAUNCH_CHECK();
   const size_t smem = 6 * sizeof(float2) * (size_t)wind;
   SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft_mix: %zu bytes of shared memory needed", smem);
   SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  launch_pdl(istft_mix_kernel, dim3(rows * segments), dim3(256), smem, st, reinterpret_cast<const float2*>(S), (const float*)gains, loc, tracks,
-             n_frames, p, hop, nf, crop0 + (n_overlap - 1) * hop, t_out, segments, 1.0f / ((float)wind * (float)n_overlap), out);
+  static const int sub_env = [] { const char* v = getenv("SAG_ISTFT_MIX_SUB"); return v ? atoi(v) : 2; }();   // tuning knob
+  const int seg_len = t_out / segments;
+  const int n_sub = (sub_env >= 1 && seg_len % sub_env == 0) ? sub_env : 1;
+  launch_pdl(istft_mix_kernel, dim3(rows * segments * n_sub), dim3(256), smem, st, reinterpret_cast<const float2*>(S), (const float*)gains, loc,
+             tracks, n_frames, p, hop, nf, crop0 + (n_overlap - 1) * hop, t_out, segments, n_sub, 1.0f / ((float)wind * (float)n_overlap), out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
