@@ -62,38 +62,56 @@ int fft_prepare(int n) {   // create tables ahead of time (outside stream captur
 }
 
 // ---- K1: frame + window + FFT (+ magnitude) --------------------------------------------------------------------
-// grid (n_frames_launch, rows); frame index = fbase + blockIdx.x.
+// grid (ceil(n_frames_launch / 2), rows): two consecutive frames per CTA, transformed side by side (one set of block-wide
+// passes and twiddle fetches).  They are NOT packed into one complex transform: an all-zero frame must come out exactly
+// zero (frame indexing is checked bit-exactly), which the Hermitian split of a packed pair does not guarantee.
+__device__ __forceinline__ void stft_emit(const float2 v, int i, int64_t cplx_base, int64_t mag_base, float2* __restrict__ cplx_out,
+                                          const ActView& mag_out) {
+  if (cplx_base >= 0) cplx_out[cplx_base + i] = v;
+  if (mag_base >= 0) {
+    const float a = hypotf(v.x, v.y);         // tf.abs(complex64)
+    if (mag_out.fmt == ACT_F32) {
+      reinterpret_cast<float*>(mag_out.p)[mag_base + i] = a;
+    } else {                                  // split-bf16 planes for the tensor-core encoder
+      const __nv_bfloat16 h = __float2bfloat16_rn(a);
+      reinterpret_cast<__nv_bfloat16*>(mag_out.p)[mag_base + i] = h;
+      if (mag_out.plane != 0)
+        reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(mag_out.p) + mag_out.plane)[mag_base + i] =
+            __float2bfloat16_rn(a - __bfloat162float(h));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, int n_samples, int hop, const FftPlan p,
-                                                   int fbase, int frame0, int n_frames_out, float2* __restrict__ cplx_out,
+                                                   int fbase, int fend, int frame0, int n_frames_out, float2* __restrict__ cplx_out,
                                                    int mag0, int n_mag, const ActView mag_out) {
   extern __shared__ __align__(16) float2 smem[];
   float2* buf0 = smem;
-  float2* buf1 = smem + p.n;
+  float2* buf1 = smem + 2 * p.n;
   pdl_prologue();
-  const int f = fbase + blockIdx.x;
+  const int n = p.n;
+  const int fa = fbase + 2 * blockIdx.x, fb = fa + 1;
+  const bool has_b = fb < fend;
   const int row = blockIdx.y;
-  const float* xr = x + (int64_t)row * n_samples + (int64_t)f * hop;
-  for (int i = threadIdx.x; i < p.n; i += blockDim.x) buf0[i] = make_float2(__ldg(xr + i) * __ldg(p.hann + i), 0.f);
-  float2* res = block_fft(buf0, buf1, p);
-  if (cplx_out != nullptr && f >= frame0 && f < frame0 + n_frames_out) {
-    float2* o = cplx_out + ((int64_t)row * n_frames_out + (f - frame0)) * p.n;
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) o[i] = res[i];
+  const float* xa = x + (int64_t)row * n_samples + (int64_t)fa * hop;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float w = __ldg(p.hann + i);
+    buf0[i] = make_float2(__ldg(xa + i) * w, 0.f);
+    buf0[n + i] = make_float2(has_b ? __ldg(xa + hop + i) * w : 0.f, 0.f);
   }
-  if (mag_out.p != nullptr && f >= mag0 && f < mag0 + n_mag) {
-    const int64_t e0 = ((int64_t)row * n_mag + (f - mag0)) * p.n;
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-      float2 v = res[i];
-      const float a = hypotf(v.x, v.y);       // tf.abs(complex64)
-      if (mag_out.fmt == ACT_F32) {
-        reinterpret_cast<float*>(mag_out.p)[e0 + i] = a;
-      } else {                                // split-bf16 planes for the tensor-core encoder
-        const __nv_bfloat16 h = __float2bfloat16_rn(a);
-        reinterpret_cast<__nv_bfloat16*>(mag_out.p)[e0 + i] = h;
-        if (mag_out.plane != 0)
-          reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(mag_out.p) + mag_out.plane)[e0 + i] =
-              __float2bfloat16_rn(a - __bfloat162float(h));
-      }
-    }
+  const float2* z = block_fft_nf(buf0, buf1, p, 2);
+  // where the two frames go (-1: not wanted)
+  auto bases = [&](int f, int64_t& cb, int64_t& mb) {
+    cb = (cplx_out != nullptr && f >= frame0 && f < frame0 + n_frames_out) ? ((int64_t)row * n_frames_out + (f - frame0)) * n : -1;
+    mb = (mag_out.p != nullptr && f >= mag0 && f < mag0 + n_mag) ? ((int64_t)row * n_mag + (f - mag0)) * n : -1;
+  };
+  int64_t ca, ma, cb, mb;
+  bases(fa, ca, ma);
+  bases(fb, cb, mb);
+  if (!has_b) { cb = -1; mb = -1; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    stft_emit(z[i], i, ca, ma, cplx_out, mag_out);
+    if (has_b) stft_emit(z[n + i], i, cb, mb, cplx_out, mag_out);
   }
 }
 
@@ -109,10 +127,10 @@ int launch_stft(const float* x, int rows, int n_samples, int wind, int hop, int 
   SAG_REQUIRE(lo >= 0 && hi <= n_frames_total, SAG_EINVAL, "stft: frame range [%d,%d) outside [0,%d)", lo, hi, n_frames_total);
   FftPlan p;
   SAG_TRY(get_plan(wind, &p));
-  size_t smem = 2 * sizeof(float2) * wind;
+  size_t smem = 4 * sizeof(float2) * wind;
   if (smem > 48 * 1024) SAG_CHECK_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(hi - lo, rows);
-  launch_pdl(stft_kernel, grid, dim3(256), smem, st, x, n_samples, hop, p, lo, frame0, n_frames_out, reinterpret_cast<float2*>(cplx_out),
+  dim3 grid((hi - lo + 1) / 2, rows);
+  launch_pdl(stft_kernel, grid, dim3(256), smem, st, x, n_samples, hop, p, lo, hi, frame0, n_frames_out, reinterpret_cast<float2*>(cplx_out),
              mag0, n_mag, mag_out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
