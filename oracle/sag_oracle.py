@@ -663,3 +663,22 @@ def compute_lsd_dist(pred, gt, rate):
     for i in range(gt.shape[1]):
         dist[i] = np.sqrt(np.mean((power_spect(melspec(gt[:, i])) - power_spect(melspec(pred[:, i]))) ** 2))
     return dist
+
+
+def energy_map_frames(ambix, snd_rate, video_fps):
+    """myutils.py:251-275 (the heat-map arithmetic of gen_360video) with the oracle's own RMS maps."""
+    x = np.asarray(ambix, np.float64)[::5]
+    window_frames = int((5. / video_fps) * (snd_rate / 5.))
+    n_frames = x.shape[0] // window_frames
+    maps = []
+    for f in range(n_frames):
+        r = ambix_rms_map(x[f * window_frames:(f + 1) * window_frames], 5.)
+        maps.append((r - r.min()) / (r.max() - r.min() + 0.005))
+    out = []
+    for f in range(1, n_frames):
+        for i in range(5):
+            beta = i / 5.
+            rms = ((1 - beta) * maps[f - 1] + beta * maps[f]) * 2. - 0.7
+            rms[rms < 0] = 0
+            out.append(rms)
+    return np.stack(out, 0) if out else np.zeros((0, 37, 72))

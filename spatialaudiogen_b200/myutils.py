@@ -82,3 +82,40 @@ def save_params(args, model_dir=None):
 def img_prep_fcn():
     """reference myutils.py:88-89"""
     return lambda x: x / 255. - 0.5
+
+
+# ---- deploy post-processing (reference myutils.gen_360video, myutils.py:224-311): the parts that are arithmetic.
+# Splitting / muxing the streams (ffmpeg) and the spatial-media metadata injection are external tools and stay out.
+def ambix_to_stereo(ambix):
+    """myutils.py:285-291 ("binauralize"): left = W + Y, right = W - Y, peak-normalised to 0.95.  ambix (N, 4) [W, Y, Z, X]
+    -> (N, 2) float64."""
+    import numpy as np
+    ambix = np.asarray(ambix, np.float64)
+    stereo = np.stack([ambix[:, 0] + ambix[:, 1], ambix[:, 0] - ambix[:, 1]], 1)
+    return stereo / (np.abs(stereo).max() / 0.95)
+
+
+def energy_map_frames(ambix, snd_rate, video_fps, device=None):
+    """The heat maps gen_360video overlays on the video (myutils.py:251-275): the ambisonics are decimated by 5, decoded on
+    the 5-degree mesh (37 x 72 directions) and reduced to one RMS map per 5 video frames (the GPU kernel behind
+    metrics.ambix_rms_map); each map is min-max normalised with the +0.005 guard, consecutive maps are blended linearly over
+    the 5 video frames between them, then `2*rms - 0.7` clipped at 0.  Returns (n_video_frames, 37, 72) float32 in [0, 1.3):
+    the reference indexes its colour map with int(255*rms) (clipped) and blends with alpha = 0.6*rms."""
+    import numpy as np
+    import torch
+    from . import metrics as M
+    x = np.asarray(ambix, np.float32)[::5]                                  # SphericalAmbisonicsVisualizer(ambix[::5], snd_rate/5., 5./fps, 5.)
+    window_frames = int((5. / video_fps) * (snd_rate / 5.))                 # distance.py:30
+    n_frames = x.shape[0] // window_frames
+    if n_frames < 2:
+        return np.zeros((0, 37, 72), np.float32)
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+    chunks = torch.as_tensor(x[:n_frames * window_frames].reshape(n_frames, window_frames, 4)).to(dev)
+    rms = M.ambix_rms_map(chunks, 5.).cpu().numpy()
+    lo = rms.reshape(n_frames, -1).min(1)[:, None, None]
+    hi = rms.reshape(n_frames, -1).max(1)[:, None, None]
+    rms = (rms - lo) / (hi - lo + 0.005)                                    # myutils.py:256,262
+    beta = (np.arange(5, dtype=np.float32) / 5.)[None, :, None, None]       # myutils.py:269-270
+    out = (1 - beta) * rms[:-1, None] + beta * rms[1:, None]
+    out = out.reshape((-1,) + rms.shape[1:]) * 2. - 0.7                     # myutils.py:271
+    return np.maximum(out, 0.).astype(np.float32)

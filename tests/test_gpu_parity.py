@@ -508,6 +508,22 @@ def test_w2xyz_deploy_reads_a_video_folder(tmp_path):
     assert np.array_equal(out, ref)
 
 
+def test_deploy_post_processing_arithmetic():
+    """myutils.gen_360video without ffmpeg: stereo down-mix (myutils.py:285-291) and the 5-degree heat-map frames
+    (myutils.py:251-275) from the GPU energy maps."""
+    from spatialaudiogen_b200 import myutils
+    rng = np.random.RandomState(8)
+    ambix = (rng.randn(48000, 4) * np.array([0.2, 0.1, 0.05, 0.15])).astype(np.float32)        # 1 s of [W, Y, Z, X]
+    st = myutils.ambix_to_stereo(ambix)
+    assert st.shape == (48000, 2) and abs(np.abs(st).max() - 0.95) < 1e-12
+    a64 = ambix.astype(np.float64)
+    assert np.allclose(st[:, 0] / st[:, 1], (a64[:, 0] + a64[:, 1]) / (a64[:, 0] - a64[:, 1]))
+    maps = myutils.energy_map_frames(ambix, 48000, 10.)
+    ref = O.energy_map_frames(ambix, 48000, 10.)
+    assert maps.shape == ref.shape == (5 * (2 - 1), 37, 72)                 # 10 fps: one map per 0.5 s, 5 blended frames between two
+    assert np.abs(maps - ref).max() < 2e-4
+
+
 def test_evaluate_rows_follow_eval_detailed_columns(tmp_path):
     from spatialaudiogen_b200 import evaluate as E
     rng = np.random.RandomState(3)
