@@ -80,12 +80,49 @@ def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
         ambix = b['ambix']
         audio_input = ambix[:, :, :1].contiguous()                          # eval.py:69
         target = ambix[:, ss:ss + t, 1:].contiguous()                       # eval.py:70
-        pred = model.inference_ops(audio_input, video=b.get('video'), flow=b.get('flow'), is_training=False)
+        pred = torch.empty((ambix.shape[0], t, 3), dtype=torch.float32, device=ambix.device)
+        model.forward_into(audio_input, b.get('video'), b.get('flow'), pred)       # the hot loop (fused inverse STFT + mixing)
         rows, _ = metric_rows(pred, target, mono=audio_input[:, ss:ss + t], layout=b.get('mask'), audio_rate=audio_rate,
                               rms_maps=rms_maps)
         ids.extend(b['id'])
         out.append(rows)
     return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
+
+
+def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=False):
+    """The evaluation feeder (reference feeder.py:366-420 with for_eval=True, eval.py:43-60): every `folders[i]` (a per-video
+    folder, see readers.py) is read in order with the eval schedule -- every 10th entry of audio_pow.lst, no shuffling, no
+    rotations, silent chunks kept -- and the samples are grouped into batches of `batch_size` like `dequeue_many`.
+    channel_masks: {video id: (4,) mask} from meta/audio_layouts.txt (feeder.py:312-314), default all ones.  The last, short
+    batch is yielded too unless drop_remainder (the reference's queue raises OutOfRange on it)."""
+    from . import readers, myutils
+    from .definitions import VIDEO, FLOW
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+    pending = []
+
+    def flush(items):
+        b = {'id': [c['id'] for c in items],
+             'ambix': torch.as_tensor(np.stack([c['ambix'] for c in items]).astype(np.float32)).to(dev),
+             'mask': torch.as_tensor(np.stack([c['mask'] for c in items]).astype(np.float32)).to(dev)}
+        for k in (VIDEO, FLOW):
+            if k in params.encoders:
+                b[k] = torch.as_tensor(np.stack([c[k] for c in items]).astype(np.float32)).to(dev)
+        return b
+
+    for folder in folders:
+        r = readers.SampleReader(folder, ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
+                                 context=params.context, duration=0.1, return_video=VIDEO in params.encoders,
+                                 img_prep=myutils.img_prep_fcn(), return_flow=FLOW in params.encoders, skip_silence_thr=None,
+                                 shuffle=False, random_rotations=False, skip_rate=10)
+        mask = np.ones(4) if channel_masks is None else np.asarray(channel_masks.get(r.video_id, np.ones(4)))
+        for c in r.loop_chunks():
+            c['mask'] = mask
+            pending.append(c)
+            if len(pending) == batch_size:
+                yield flush(pending)
+                pending = []
+    if pending and not drop_remainder:
+        yield flush(pending)
 
 
 def write_eval_detailed(path, sample_ids, rows):

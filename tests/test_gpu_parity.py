@@ -508,6 +508,31 @@ def test_w2xyz_deploy_reads_a_video_folder(tmp_path):
     assert np.array_equal(out, ref)
 
 
+def test_evaluate_from_video_folders(tmp_path):
+    """eval.py end to end on disk data: folder_batches (eval schedule: every 10th audio_pow.lst entry) -> evaluate_batches
+    -> eval-detailed.txt rows; equal to running the same windows through the model and metric_rows by hand."""
+    from spatialaudiogen_b200 import evaluate as E, readers as R, SptAudioGen
+    from test_host import _make_video_folder
+    folder, full = _make_video_folder(str(tmp_path), seconds=4)
+    with open(os.path.join(folder, 'audio_pow.lst'), 'w') as f:          # preprocessing writes one entry per 0.1 s
+        for k in range(30):
+            f.write('%.1f %.3f\n' % (0.5 + 0.1 * k, 0.3))
+    enc = ['audio', 'video']
+    m = SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(Wt.init_weights(enc, separation='unet_mask', seed=4, stress=True))
+    batches = list(E.folder_batches([folder], _P(enc), batch_size=16, channel_masks={'vidA': np.array([1., 1., 0., 1.])}))
+    assert len(batches) == 1 and batches[0]['id'] == ['vidA 0.5', 'vidA 1.5', 'vidA 2.5']
+    assert tuple(batches[0]['ambix'].shape) == (3, 52799, 4) and tuple(batches[0]['video'].shape) == (3, 1, 224, 448, 3)
+    ids, rows = E.evaluate_batches(m, batches, rms_maps=True)
+    assert ids == batches[0]['id'] and tuple(rows.shape) == (3, 28) and not torch.isnan(rows).any()
+    amb = batches[0]['ambix']
+    pred = m.inference_ops(amb[:, :, :1].contiguous(), video=batches[0]['video'])
+    ref_rows, _ = E.metric_rows(pred, amb[:, 24000:28800, 1:].contiguous(), mono=amb[:, 24000:28800, :1].contiguous(),
+                                layout=batches[0]['mask'], rms_maps=True)
+    assert torch.allclose(rows, ref_rows, rtol=2e-3, atol=1e-5)
+    E.write_eval_detailed(str(tmp_path / 'eval-detailed.txt'), ids, rows)
+    assert open(str(tmp_path / 'eval-detailed.txt')).read().splitlines()[1].startswith('vidA 0.5 | ')
+
+
 def test_deploy_post_processing_arithmetic():
     """myutils.gen_360video without ffmpeg: stereo down-mix (myutils.py:285-291) and the 5-degree heat-map frames
     (myutils.py:251-275) from the GPU energy maps."""
