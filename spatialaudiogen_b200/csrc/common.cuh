@@ -75,14 +75,12 @@ __device__ __forceinline__ void pdl_prologue() {
 bool pdl_enabled();
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at;
-  memset(&at, 0, sizeof(at));
+  cudaLaunchAttribute at = {};
   at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at.val.programmaticStreamSerializationAllowed = 1;
   if (pdl_enabled()) { cfg.attrs = &at; cfg.numAttrs = 1; }

@@ -222,12 +222,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO),
-// descriptor version 1 (sm_100), layout type 2.  `addr` may be advanced by 32 bytes per UMMA_K inside the atom.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
 // fp32 -> bf16 hi (round to nearest even) and the bf16 of the remainder; 8 values -> two 16-byte vectors
 __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -274,40 +268,6 @@ __device__ __forceinline__ void store_bf2_4(void* yhi, int64_t plane, int64_t e,
   split4(v, hi, lo);
   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yhi) + e) = hi;
   if (planes == 2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(yhi) + plane) + e) = lo;
-}
-
-// sum of v[c] over the 32 lanes for 16 columns at once (transposing butterfly, 16 shuffles): afterwards the lanes
-// with an even index hold the total of column ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
-__device__ __forceinline__ float warp_colsum16(const float* v, int lane) {
-  float a[8];
-  const bool u16 = lane & 16;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float send = u16 ? v[i] : v[i + 8];
-    float keep = u16 ? v[i + 8] : v[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  float b[4];
-  const bool u8 = lane & 8;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float send = u8 ? a[i] : a[i + 4];
-    float keep = u8 ? a[i + 4] : a[i];
-    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  float c[2];
-  const bool u4 = lane & 4;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float send = u4 ? b[i] : b[i + 2];
-    float keep = u4 ? b[i + 2] : b[i];
-    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const bool u2 = lane & 2;
-  float send = u2 ? c[0] : c[1];
-  float keep = u2 ? c[1] : c[0];
-  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  return d + __shfl_xor_sync(0xffffffffu, d, 1);
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
@@ -1189,8 +1149,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   int64_t clusters = (max_ctas > 0 ? max_ctas : num_sms()) / CL;
   if (clusters < 1) clusters = 1;
   if (n_work < clusters) clusters = n_work;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
   cfg.blockDim = dim3(UM_THREADS);
   cfg.dynamicSmemBytes = smem;
