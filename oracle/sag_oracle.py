@@ -5,14 +5,23 @@ reference's TF-1.4 graph for the path named in BASELINE.json:north_star.  It is 
 only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
 The product (spatialaudiogen_b200/) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
- and cannot be executed here (python2 + tensorflow-gpu==1.4.0rc1, neither
-installable).  The arithmetic lives in the un-vendored dependency TensorFlow 1.4.0rc1
-(requirements.txt:10); its published op semantics are restated below by hand.
-The oracle is anchored instead by (i) the analytic invariants of SURVEY.md 8c (tests/test_oracle.py),
-(ii) a semantic known-answer test of the ResNet-18 trunk with the reference's own resnet18.npy and
-test images (run in the build container, results committed under tests/golden/), and (iii) fp64-vs-fp32
-self-agreement.
+PINNING.  The reference ships no tests, golden vectors or fixtures for this path and its
+TF graph cannot be executed here (python2 + tensorflow-gpu==1.4.0rc1, neither installable).  What CAN run here is
+the reference's own python around the graph, and that is what pins this file (tests/test_reference_goldens.py against
+tests/golden/reference_goldens.npz, generated in the build container by tests/golden/make_reference_goldens.py from
+/root/reference through a purely syntactic python-2 shim):
+  * pinned by the reference's numpy / scipy code: a1 derived constants (model.py:24-60), a12 envelope distance
+    (myutils.py:109-116), a13 mesh / SH matrix / energy maps (distance.py, common.py, decoder.py, position.py),
+    f2 reader logic (feeder.py:50-161), load_params (myutils.py:40-85);
+  * pinned by the reference's graph-building code (indexing, crops, reshapes, reductions) run eagerly on a numpy stand-in
+    for the dozen elementary TF ops it calls: a2 stft, a8 istft (myutils.py:119-211), a11 evaluation_ops
+    (model.py:62-154);
+  * PARITY UNPINNED for the dense layers (a3-a7: tf.nn.convolution / conv2d_transpose / batch_norm / max_pool / matmul
+    of the un-vendored TensorFlow 1.4.0rc1, requirements.txt:10): their published op semantics are
+    restated below by hand and anchored by (i) the analytic invariants of SURVEY.md 8c (tests/test_oracle.py), (ii) a
+    semantic known-answer test of the ResNet-18 trunk with the reference's own resnet18.npy and test images (run in the
+    build container, results committed under tests/golden/), and (iii) fp64-vs-fp32 self-agreement; likewise for the
+    restated third-party pieces of the widened rows (pyemd's EMD-hat: its defining LP; librosa's mel spectrogram).
 
 Every function cites the reference file:line (relative to /root/reference) it follows.
 Python-2 integer division of the reference is written `//` here.

@@ -1,0 +1,148 @@
+"""The oracle (and the product's host-side code) against vectors computed by the REFERENCE'S OWN functions
+(tests/golden/reference_goldens.npz, generated in the build container by tests/golden/make_reference_goldens.py from
+/root/reference through a syntactic python-2 shim).  This pins the rows whose reference implementation is plain numpy /
+scipy: a1 constants, a12 envelope distance, a13 mesh / SH matrix / energy maps, f2 reader logic, load_params -- and,
+with the reference's TF graph-building code run eagerly on a numpy stand-in for the elementary ops it calls, a2 stft,
+a8 istft and the a11 evaluation metrics."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sag_oracle as O
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_goldens.npz'))
+
+
+def test_a1_derived_constants_match_reference_init():
+    for row in G['a1_configs_and_dims']:
+        order, ar, vr, ctx, dur, win = int(row[0]), int(row[1]), int(row[2]), float(row[3]), float(row[4]), float(row[5])
+        m = O.SptAudioGen({}, ambi_order=order, audio_rate=ar, video_rate=vr, context=ctx, sample_duration=dur, encoders=['audio'],
+                          separation='none', params=O.SptAudioGenParams(sep_fft_window=win))
+        assert [m.num_ambi_channels, m.snd_contx, m.snd_dur, m.snd_size, m.wind_size] == [int(v) for v in row[6:]]
+
+
+def test_a13_mesh_sh_matrix_and_energy_maps_match_reference():
+    for res in (30, 5):
+        phi, nu = O.spherical_mesh(res)
+        assert np.array_equal(phi, G['a13_phi_mesh_%d' % res]) and np.array_equal(nu, G['a13_nu_mesh_%d' % res])
+    phi, nu = O.spherical_mesh(30)
+    pts = [O._position_polar_roundtrip(p, n) for p, n in zip(phi.reshape(-1), nu.reshape(-1))]
+    Y = O.spherical_harmonics_matrix([p[0] for p in pts], [p[1] for p in pts], 1)
+    assert np.abs(Y - G['a13_sh_matrix_30']).max() < 1e-15
+    ambi = G['a13_ambi'].astype(np.float64)
+    for res in (30, 5):
+        assert np.abs(O.ambix_rms_map(ambi, float(res)) - G['a13_rms_map_%d' % res]).max() < 1e-14
+    assert np.abs(O.ambix_rms_map(ambi * np.array([1., 1., 0., 1.]), 30.) - G['a13_rms_map_30_wxy']).max() < 1e-14
+
+
+def test_a12_envelope_distance_matches_reference():
+    got = O.compute_envelope_dist(G['a12_pred'], G['a12_gt'])
+    # (the reference hands scipy.signal.hilbert float32 signals: its transform runs in single precision)
+    assert np.allclose(np.asarray(got), G['a12_env_dist'], rtol=1e-6, atol=0)
+
+
+def test_load_params_matches_reference(tmp_path):
+    from spatialaudiogen_b200 import myutils
+    open(str(tmp_path / 'train-params.txt'), 'w').write(str(G['params_text']))
+    p = myutils.load_params(str(tmp_path))
+    for k, v in ast.literal_eval(str(G['params_repr'])):
+        assert getattr(p, k) == v, (k, getattr(p, k), v)
+
+
+def test_f2_audio_reader_padding_and_flow_dequantisation_match_reference(tmp_path):
+    """The product's host readers on the same tiny clip (4 one-second files at 200 Hz) the reference's AudioReader.get
+    was run on, and on the same quantised flow frames."""
+    from spatialaudiogen_b200 import readers as R
+    from scipy.io import wavfile
+    clip, rate = G['f2_clip'], 200
+    folder = str(tmp_path / 'ambix')
+    os.makedirs(folder)
+    for i in range(4):                                                   # float wav files: exact round trip of the array
+        wavfile.write(os.path.join(folder, '%06d.wav' % i), rate, clip[i * rate:(i + 1) * rate].astype(np.float64))
+    ar = R.AudioReader(folder, rate, ambi_order=1)
+    assert (ar.num_files, ar.num_channels, ar.num_frames) == (4, 4, 800)
+    for i, (t0, size) in enumerate(G['f2_audio_cases']):
+        got = ar.get(float(t0), int(size))
+        assert got.shape == G['f2_audio_out_%d' % i].shape and np.array_equal(got, G['f2_audio_out_%d' % i]), (i, t0, size)
+    assert np.abs(ar.get(0.5, 64, rotation=0.7) - G['f2_audio_rot']).max() < 1e-15
+    fr = object.__new__(R.FlowReader)
+
+    class FakeReader(object):
+        rate = 10.
+
+        def get_by_index(self, start_time, size, rotation=None):
+            return G['f2_flow_raw'].copy()
+    fr.reader, fr.rate, fr.lims = FakeReader(), 10., G['f2_flow_lims']
+    assert np.array_equal(fr.get_by_index(1.3, 2), G['f2_flow_out'])
+
+
+def _audio_a2():
+    return (G['a2_audio_q12'].astype(np.float64) / 4096).astype(np.float32)               # (1, 1, 52799)
+
+
+def test_a2_a8_stft_istft_match_reference_graph_code():
+    s = O.stft(torch.as_tensor(_audio_a2()), 1024, 4)
+    assert tuple(s.shape) == (1, 1, 200, 1024)
+    s = s.numpy()
+    ref = G['a2_stft_bins_stride37']
+    assert np.abs(s[0, 0, :, ::37] - ref).max() < 3e-6 * np.abs(ref).max()
+    assert np.allclose(np.abs(s[0, 0]).sum(-1), G['a2_stft_abs_sum_per_frame'], rtol=1e-5)
+    small = O.stft(torch.as_tensor(G['a2_small_in']), 64, 4).numpy()
+    assert small.shape == G['a2_small_stft'].shape and np.abs(small - G['a2_small_stft']).max() < 3e-6 * np.abs(G['a2_small_stft']).max()
+    y = O.istft(torch.as_tensor(G['a8_small_in']), 4).numpy()
+    assert y.shape == G['a8_small_istft'].shape and np.abs(y - G['a8_small_istft']).max() < 3e-6 * np.abs(G['a8_small_istft']).max()
+    # istft(stft(x)[89:117]) = 0.5 * x[23552:29952], in the reference's own numbers
+    ref = G['a8_istft_of_stft_frames_89_117']
+    assert ref.shape == (1, 6400) and np.abs(ref[0] - 0.5 * _audio_a2()[0, 0, 23552:29952]).max() < 1e-6
+    y = O.istft(torch.as_tensor(O.stft(torch.as_tensor(_audio_a2()), 1024, 4).numpy()[0, :, 89:117]), 4).numpy()
+    assert np.abs(y - ref).max() < 1e-6
+
+
+def _a11_inputs():
+    return ((G['a11_pred_q12'].astype(np.float64) / 4096).astype(np.float32), (G['a11_gt_q12'].astype(np.float64) / 4096).astype(np.float32),
+            G['a11_mask'])
+
+
+def test_a11_evaluation_ops_match_reference_graph_code():
+    pred, gt, mask = _a11_inputs()
+    m = O.SptAudioGen({}, encoders=['audio'], separation='none')
+    metrics, stft_ps, lsd_ps, mse_ps, snr_ps = m.evaluation_ops(pred, gt, None, mask)
+    for got, key in ((stft_ps, 'a11_stft_ps'), (lsd_ps, 'a11_lsd_ps'), (mse_ps, 'a11_mse_ps'), (snr_ps, 'a11_snr_ps')):
+        assert np.allclose(np.asarray(got), G[key], rtol=2e-5), key
+    names = ast.literal_eval(str(G['a11_metric_names']))
+    for k, v in zip(names, G['a11_metric_values']):
+        assert abs(float(metrics[k]) - v) < 3e-5 * max(1.0, abs(v)), (k, float(metrics[k]), v)
+
+
+@pytest.mark.gpu
+def test_gpu_stft_istft_metrics_against_reference_graph_code():
+    """The CUDA STFT / inverse STFT / metrics kernels directly against the numbers of the reference's own code."""
+    from spatialaudiogen_b200 import myutils, metrics as M
+    s = myutils.stft(torch.as_tensor(_audio_a2()).cuda(), 1024, 4)
+    ref = G['a2_stft_bins_stride37']
+    assert np.abs(s[0, 0, :, ::37].cpu().numpy() - ref).max() < 3e-6 * np.abs(ref).max()
+    small = myutils.stft(torch.as_tensor(G['a2_small_in']).cuda(), 64, 4).cpu().numpy()
+    assert np.abs(small - G['a2_small_stft']).max() < 3e-6 * np.abs(G['a2_small_stft']).max()
+    y = myutils.istft(torch.as_tensor(G['a8_small_in']).cuda(), 4).cpu().numpy()
+    assert np.abs(y - G['a8_small_istft']).max() < 3e-6 * np.abs(G['a8_small_istft']).max()
+    y = myutils.istft(s[0, :, 89:117].contiguous(), 4).cpu().numpy()
+    assert np.abs(y - G['a8_istft_of_stft_frames_89_117']).max() < 2e-6
+    pred, gt, mask = _a11_inputs()
+    r = M.window_metrics(torch.as_tensor(pred).cuda(), torch.as_tensor(gt).cuda())
+    for key, name in (('stft', 'a11_stft_ps'), ('lsd', 'a11_lsd_ps'), ('mse', 'a11_mse_ps'), ('snr', 'a11_snr_ps')):
+        assert np.allclose(r[key].cpu().numpy(), G[name], rtol=2e-4), key
+
+
+@pytest.mark.gpu
+def test_gpu_kernels_against_reference_goldens():
+    """The CUDA kernels behind rows a12 / a13 directly against the reference's numbers (no oracle in between)."""
+    from spatialaudiogen_b200 import metrics as M
+    env = M.window_metrics(torch.as_tensor(G['a12_pred'])[None].cuda(), torch.as_tensor(G['a12_gt'])[None].cuda())['env'][0].cpu().numpy()
+    assert np.allclose(env, G['a12_env_dist'], rtol=2e-4)
+    ambi = torch.as_tensor(G['a13_ambi'])[None].cuda()
+    for res in (30, 5):
+        got = M.ambix_rms_map(ambi, float(res))[0].cpu().numpy()
+        assert np.abs(got - G['a13_rms_map_%d' % res]).max() < 1e-5 * G['a13_rms_map_%d' % res].max()
