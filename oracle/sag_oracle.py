@@ -16,12 +16,21 @@ tests/golden/reference_goldens.npz, generated in the build container by tests/go
   * pinned by the reference's graph-building code (indexing, crops, reshapes, reductions) run eagerly on a numpy stand-in
     for the dozen elementary TF ops it calls: a2 stft, a8 istft (myutils.py:119-211), a11 evaluation_ops
     (model.py:62-154);
-  * PARITY UNPINNED for the dense layers (a3-a7: tf.nn.convolution / conv2d_transpose / batch_norm / max_pool / matmul
-    of the un-vendored TensorFlow 1.4.0rc1, requirements.txt:10): their published op semantics are
-    restated below by hand and anchored by (i) the analytic invariants of SURVEY.md 8c (tests/test_oracle.py), (ii) a
-    semantic known-answer test of the ResNet-18 trunk with the reference's own resnet18.npy and test images (run in the
-    build container, results committed under tests/golden/), and (iii) fp64-vs-fp32 self-agreement; likewise for the
-    restated third-party pieces of the widened rows (pyemd's EMD-hat: its defining LP; librosa's mel spectrogram).
+  * pinned by the reference's MODEL-BUILDING code -- SptAudioGen.inference_ops with audio_encoder_ops,
+    visual_encoding_ops, bottleneck_ops, localization_ops, separation_ops (model.py:161-434), the layer wrappers
+    (pyutils/tflib/wrappers/core.py:10-220) and ResNet18 (pyutils/tflib/models/image/resnet.py:110-249) -- executed
+    verbatim and eagerly at full size (B=2, audio-only and audio+video+flow) with the weights served by the scoped
+    variable names it asks for: a3-a7, a9, a10 wiring (scopes, the 30 / 214 variable names and shapes, layer order,
+    strides, paddings, crops, concat / tile / reshape order, mask and mixing arithmetic; restore_pretrained checked
+    against the reference's resnet18.npy).  This file agrees with it to 5e-8 (float64) / 2e-5 (float32);
+  * STILL RESTATED BY HAND, beneath that: the TF kernels themselves (tf.nn.convolution / conv2d_transpose / max_pool /
+    contrib batch_norm / matmul of the un-vendored TensorFlow 1.4.0rc1, requirements.txt:10), evaluated in the generator
+    by tap-by-tap float64 numpy loops from their published semantics -- independent of the torch
+    calls below but not executed from TensorFlow.  They are anchored by (i) the analytic invariants of SURVEY.md 8c
+    (tests/test_oracle.py) and (ii) a semantic known-answer test of the ResNet-18 trunk with the reference's own
+    resnet18.npy and test images (correct ImageNet classes; tests/golden/); likewise the restated third-party pieces
+    of the widened rows (pyemd's EMD-hat: its defining LP; librosa's mel spectrogram).  For those op kernels alone the
+    header says it plainly: parity unpinned against TensorFlow itself.
 
 Every function cites the reference file:line (relative to /root/reference) it follows.
 Python-2 integer division of the reference is written `//` here.

@@ -19,6 +19,15 @@ What is pinned (and by which reference code):
   f2   clip-edge padding / file offsets  feeder.py:50-105        AudioReader.get (wav decoding stubbed by arrays)
        flow de-quantisation              feeder.py:138-161       FlowReader.get_by_index
   --   train-params.txt parsing          myutils.py:40-85        load_params
+  a3-a7, a9, a10  encoders, bottleneck,  model.py:161-434, pyutils/tflib/wrappers/core.py:10-220,
+       localisation, mask decoder, mix   pyutils/tflib/models/image/resnet.py:110-249   (SptAudioGen.inference_ops)
+       -- the reference's model-building code (scopes, variable names and shapes, layer order, strides, paddings, crops,
+       concat / tile / reshape order, mask and mixing arithmetic) executed eagerly: tf.variable_scope / model_variable
+       serve the weights BY THE NAME the reference's code asks for, and the TF kernels it calls (nn.convolution,
+       conv2d_transpose, max_pool, contrib batch_norm, matmul ...) are evaluated by fake_tf_graph below in float64 from
+       TensorFlow-1.4's documented semantics.  Those op semantics are restated here, not executed from TensorFlow;
+       everything above them is the reference's own code.  restore_pretrained (resnet.py:238-249) is run against the
+       reference's resnet18.npy, which pins the tower's variable names and shapes.
 """
 import importlib.abc
 import importlib.util
@@ -51,6 +60,14 @@ def py2_to_py3(src):
         # python-2 integer division at the three sites of myutils.stft / istft where both operands are ints
         line = line.replace('range(0, wind_size, wind_size / n_overlap)', 'range(0, wind_size, wind_size // n_overlap)')
         line = line.replace('skip = n_freqs / n_overlap', 'skip = n_freqs // n_overlap')
+        # model.py: python-2 list-returning zip and integer division; core.py: TF dtype attribute; resnet.py: numpy>=1.17
+        if 'in reversed(zip(' in line and line.rstrip().endswith(')):'):
+            line = line.replace('in reversed(zip(', 'in reversed(list(zip(').rstrip()[:-1] + '):'
+        line = line.replace('self.snd_dur/sz[1]', 'self.snd_dur//sz[1]')
+        line = re.sub(r'ss = self\.snd_contx / 2$', 'ss = self.snd_contx // 2', line)
+        line = line.replace('x.dtype.base_dtype', 'x.dtype')
+        line = line.replace("np.load(os.path.join(PWD, 'resnet18.npy')).all()",
+                            "np.load(os.path.join(PWD, 'resnet18.npy'), allow_pickle=True, encoding='latin1').item()")
         out.append(line)
     return '\n'.join(out) + '\n'
 
@@ -81,11 +98,20 @@ class RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
                 return
         else:
             fn = base + '.py'
-        # pyutils/tflib is the TF layer library: nothing of it is executed here
-        if module.__name__.startswith('pyutils.tflib'):
-            module.__getattr__ = lambda k: mock.MagicMock()
-            module.__path__ = []
+        # pyutils/tflib is the TF layer library: only wrappers/core.py and models/image/resnet.py are executed (the
+        # package __init__ files pull in the trainer, recurrent layers, ...: skipped)
+        name = module.__name__
+        if name.startswith('pyutils.tflib') and name not in ('pyutils.tflib.wrappers.core', 'pyutils.tflib.models.image.resnet'):
+            if name == 'pyutils.tflib.wrappers':                  # wrappers/__init__.py: `from core import fully_connected, ...`
+                core = importlib.import_module('pyutils.tflib.wrappers.core')
+                for k in ('fully_connected', 'conv_2d', 'deconv_2d', 'conv_1d'):
+                    setattr(module, k, getattr(core, k))
+            elif os.path.isdir(base):
+                pass                                              # plain namespace: submodules import through the finder
+            else:
+                module.__getattr__ = lambda k: mock.MagicMock()   # e.g. models/image/preprocessing.py
             return
+        module.__file__ = fn
         exec(compile(py2_to_py3(open(fn).read()), fn, 'exec'), module.__dict__)
 
 
@@ -100,6 +126,8 @@ class _T(np.ndarray):
 
 
 class _Shape(tuple):
+    ndims = property(len)
+
     def as_list(self):
         return [int(v) for v in self]
 
@@ -138,12 +166,165 @@ def fake_tf():
     return tf
 
 
+def _same_pads(n, k, s):
+    # TF 'SAME': output ceil(n / s); total padding max((out - 1) * s + k - n, 0), the odd unit goes after
+    out = -(-n // s)
+    tot = max((out - 1) * s + k - n, 0)
+    return tot // 2, tot - tot // 2
+
+
+def _windows(x, kh, kw, sh, sw, padding, fill):
+    if padding == 'SAME':
+        ph, pw = _same_pads(x.shape[1], kh, sh), _same_pads(x.shape[2], kw, sw)
+        x = np.pad(x, ((0, 0), ph, pw, (0, 0)), constant_values=fill)
+    else:
+        assert padding == 'VALID'
+    oh, ow = (x.shape[1] - kh) // sh + 1, (x.shape[2] - kw) // sw + 1
+    for a in range(kh):
+        for b in range(kw):
+            yield a, b, x[:, a:a + (oh - 1) * sh + 1:sh, b:b + (ow - 1) * sw + 1:sw, :]
+
+
+def fake_tf_graph(tf, weights, created):
+    """The variable / layer half of the stand-in: enough of TF-1.4 to run the reference's model.inference_ops,
+    wrappers/core.py and resnet.py verbatim.  Variables are looked up in `weights` by the full scoped name the reference's
+    code produces (KeyError / shape assertion if it asks for anything else) and logged in `created`; the NHWC kernels are
+    tap-by-tap float64 numpy loops (deliberately not the oracle's torch calls)."""
+    import contextlib
+    scope = []
+
+    class Scope(object):
+        def __init__(self, name):
+            self.name, self.original_name_scope = name, name + '/'
+
+    @contextlib.contextmanager
+    def variable_scope(name_or_scope=None, default_name=None, values=None, reuse=None):
+        scope.append(name_or_scope if name_or_scope is not None else default_name)
+        try:
+            yield Scope('/'.join(scope))
+        finally:
+            scope.pop()
+
+    class Var(object):                                                # what tf.get_collection hands restore_pretrained
+        def __init__(self, name, shape):
+            self.op, self.shape = types.SimpleNamespace(name=name), tuple(shape)
+
+    def model_variable(name, shape=None, dtype=None, initializer=None, regularizer=None, trainable=True):
+        full = '/'.join(scope + [name])
+        arr = np.asarray(weights[full], np.float64)
+        assert shape is None or tuple(int(v) for v in shape) == arr.shape, (full, shape, arr.shape)
+        created.append(Var(full, arr.shape))
+        return _t(arr)
+
+    def convolution(input, filter, strides=None, dilation_rate=None, padding='VALID'):
+        assert dilation_rate is None
+        x, w = np.asarray(input, np.float64), np.asarray(filter, np.float64)
+        kh, kw = w.shape[:2]
+        out = 0.
+        for a, b, win in _windows(x, kh, kw, int(strides[0]), int(strides[1]), padding, 0.):
+            out = out + win @ w[a, b]
+        return _t(out)
+
+    def conv2d_transpose(value, filter, output_shape, strides, padding='SAME'):
+        assert padding == 'VALID'                                      # filter: (kh, kw, out, in)
+        x, w = np.asarray(value, np.float64), np.asarray(filter, np.float64)
+        sh, sw = int(strides[1]), int(strides[2])
+        out = np.zeros([int(v) for v in output_shape])
+        n, h, wd = x.shape[:3]
+        assert out.shape == (n, (h - 1) * sh + w.shape[0], (wd - 1) * sw + w.shape[1], w.shape[2])
+        for a in range(w.shape[0]):
+            for b in range(w.shape[1]):
+                out[:, a:a + (h - 1) * sh + 1:sh, b:b + (wd - 1) * sw + 1:sw, :] += x @ w[a, b].T
+        return _t(out)
+
+    def max_pool(value, ksize, strides, padding):
+        x, out = np.asarray(value, np.float64), None
+        for a, b, win in _windows(x, ksize[1], ksize[2], strides[1], strides[2], padding, -np.inf):
+            out = win.copy() if out is None else np.maximum(out, win)
+        return _t(out)
+
+    def batch_norm(x, decay=0.999, center=True, scale=False, epsilon=0.001, param_initializers=None, is_training=True,
+                   trainable=True, reuse=None, scope=None):
+        # tf.contrib.layers.batch_norm: variables beta, gamma, moving_mean, moving_variance under `scope`; with
+        # is_training the batch moments (biased variance) over every axis but the last normalise the activations.
+        with variable_scope(scope, 'BatchNorm'):
+            c = [int(np.asarray(x).shape[-1])]
+            beta = model_variable('beta', c) if center else 0.
+            gamma = model_variable('gamma', c) if scale else 1.
+            mean, var = model_variable('moving_mean', c), model_variable('moving_variance', c)
+        x = np.asarray(x, np.float64)
+        if is_training:
+            ax = tuple(range(x.ndim - 1))
+            mean, var = x.mean(ax), x.var(ax)
+        return _t((x - np.asarray(mean)) / np.sqrt(np.asarray(var) + epsilon) * np.asarray(gamma) + np.asarray(beta))
+
+    tf.variable_scope = variable_scope
+    tf.nn = types.SimpleNamespace(relu=lambda x: _t(np.maximum(np.asarray(x), 0.)), bias_add=lambda x, b: _t(np.asarray(x) + np.asarray(b)),
+                                  convolution=convolution, conv2d_transpose=conv2d_transpose, max_pool=max_pool)
+    tf.matmul = lambda a, b: _t(np.asarray(a) @ np.asarray(b))
+    tf.tile = lambda x, m: _t(np.tile(np.asarray(x), [int(v) for v in m]))
+    tf.sigmoid = lambda x: _t(1. / (1. + np.exp(-np.asarray(x))))
+    tf.identity = lambda x: x
+    tf.truncated_normal_initializer = tf.constant_initializer = lambda *a, **k: None
+    tf.contrib, tf.GraphKeys, tf.__path__ = mock.MagicMock(), mock.MagicMock(), []
+    tf.get_collection = lambda key: list(created)
+    assigned = []
+
+    def assign(var, value):
+        assert tuple(np.shape(value)) == var.shape, (var.op.name, np.shape(value), var.shape)
+        assigned.append(var.op.name)
+        return var.op.name
+    tf.assign, tf.assigned = assign, assigned
+    mods = {'tensorflow.contrib': tf.contrib, 'tensorflow.contrib.framework': None, 'tensorflow.contrib.framework.python': None,
+            'tensorflow.contrib.framework.python.ops': types.SimpleNamespace(variables=types.SimpleNamespace(model_variable=model_variable)),
+            'tensorflow.contrib.layers.python': None,
+            'tensorflow.contrib.layers.python.layers': types.SimpleNamespace(utils=types.SimpleNamespace(
+                collect_named_outputs=lambda coll, alias, x: x, last_dimension=lambda shape, min_rank=1: int(shape[-1]),
+                n_positive_integers=lambda n, v: (int(v),) * n if np.isscalar(v) else tuple(int(i) for i in v))),
+            'tensorflow.contrib.layers': types.SimpleNamespace(l2_regularizer=lambda s: None, batch_norm=batch_norm)}
+    for k, v in mods.items():
+        m = types.ModuleType(k)
+        m.__dict__.update(vars(v) if isinstance(v, types.SimpleNamespace) else {})
+        m.__path__ = []
+        sys.modules[k] = m
+    sys.modules['tensorflow.contrib'].layers = sys.modules['tensorflow.contrib.layers']
+    return tf
+
+
+WEIGHTS, CREATED = {}, []
+
+
 def install():
-    sys.modules['tensorflow'] = fake_tf()
+    sys.modules['tensorflow'] = fake_tf_graph(fake_tf(), WEIGHTS, CREATED)
     for s in STUBS:
         if s not in sys.modules:
             sys.modules[s] = mock.MagicMock()
     sys.meta_path.insert(0, RefFinder())
+
+
+MODEL_SEED = 7
+
+
+def model_inputs(seed, batch):
+    """Seeded inputs of the full-size model case (the test regenerates them from the same recipe)."""
+    r = np.random.RandomState(seed)
+    n = 52799
+    tone = 0.2 * np.sin(2 * np.pi * 523.25 * np.arange(n) / 48000.)[None, :, None]
+    audio = (np.round(np.clip(0.1 * r.randn(batch, n, 1) + tone, -1, 1) * 4096) / 4096).astype(np.float32)
+    video = (r.randint(0, 256, size=(batch, 1, 224, 448, 3)) / 255.).astype(np.float32)
+    flow = (r.randint(0, 256, size=(batch, 1, 224, 448, 3)) / 255. - 0.5).astype(np.float32)
+    return audio, video, flow
+
+
+def torch_f64():
+    import torch
+    return torch.float64
+
+
+def tf_assigned():
+    out = list(sys.modules['tensorflow'].assigned)
+    del sys.modules['tensorflow'].assigned[:]
+    return out
 
 
 def main():
@@ -245,6 +426,46 @@ def main():
     G['a11_stft_ps'], G['a11_lsd_ps'], G['a11_mse_ps'], G['a11_snr_ps'] = [np.asarray(v) for v in (stft_ps, lsd_ps, mse_ps, snr_ps)]
     G['a11_metric_names'] = np.asarray(repr(list(metrics.keys())))
     G['a11_metric_values'] = np.asarray([float(np.asarray(v)) for v in metrics.values()])
+
+    # ---- a3-a7, a9, a10: the reference's model-building code, run eagerly (fake_tf_graph) -----------------------------------
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from spatialaudiogen_b200 import weights as PW
+    from oracle import sag_oracle as O
+    from pyutils.tflib.models.image import resnet as Rr
+    pre = np.load(os.path.join(REF, 'pyutils/tflib/models/image/resnet18.npy'), allow_pickle=True, encoding='latin1').item()
+    for tag, encoders in (('a', ['audio']), ('avf', ['audio', 'video', 'flow'])):
+        W = PW.init_weights(encoders, 'unet_mask', seed=MODEL_SEED, stress=True)
+        WEIGHTS.clear(), WEIGHTS.update(W)
+        del CREATED[:]
+        audio, video, flow = model_inputs(MODEL_SEED, 2)
+        ref_model = Rm.SptAudioGen(1, encoders=list(encoders), separation='unet_mask', params=Rm.SptAudioGenParams())
+        kw = dict(video=_t(video.astype(np.float64)), flow=_t(flow.astype(np.float64))) if 'video' in encoders else {}
+        ambix = np.asarray(ref_model.inference_ops(_t(audio.astype(np.float64)), is_training=False, **kw))
+        names = [(v.op.name, v.shape) for v in CREATED]
+        assert sorted(n for n, _ in names) == sorted(W.keys()), set(W.keys()) ^ set(n for n, _ in names)
+        assert all(W[n].shape == s for n, s in names)
+        G['m_%s_variables' % tag] = np.asarray(repr(names))
+        G['m_%s_weight_checksum' % tag] = np.asarray([float(np.asarray(v, np.float64).sum()) for v in W.values()])
+        G['m_%s_ambix' % tag] = ambix.astype(np.float32)
+        G['m_%s_sep_stride97' % tag] = np.asarray(ref_model.sep_channels)[:, 0, :, ::97].astype(np.float32)
+        G['m_%s_loc_w_stride480' % tag] = np.asarray(ref_model.loc_channels[0])[:, ::480].astype(np.float32)
+        G['m_%s_loc_b_stride480' % tag] = np.asarray(ref_model.loc_channels[1])[:, ::480].astype(np.float32)
+        G['m_%s_inp_spect_sum' % tag] = np.asarray(ref_model.inp_spect).sum(-1).astype(np.float32)
+        if 'video' in encoders:
+            for k in ('video', 'flow'):
+                G['m_%s_%s_conv1_stride' % (tag, k)] = np.asarray(ref_model.ends[k + '_encoder/conv'])[:, ::8, ::8, ::4].astype(np.float32)
+                G['m_%s_%s_conv5_2_stride16' % (tag, k)] = np.asarray(ref_model.ends[k + '_encoder/conv5_2'])[..., ::16].astype(np.float32)
+            # visual_encoding_ops ran restore_pretrained against the reference's resnet18.npy (resnet.py:238-249):
+            tower = sorted(n[len('video_encoder/'):] for n, _ in names if n.startswith('video_encoder/'))
+            assert sorted(tf_assigned()) == sorted(n for n, _ in names if n.split('/')[0] in ('video_encoder', 'flow_encoder'))
+            assert set(tower) <= set(pre.keys()) and all(tuple(pre[k].shape) == W['video_encoder/' + k].shape for k in tower)
+            G['m_resnet18_npy_keys_used'] = np.asarray(repr(tower))
+        # generation-time cross-check of the oracle (float64) on the same inputs
+        om = O.SptAudioGen(W, 1, encoders=list(encoders), separation='unet_mask', dtype=torch_f64())
+        oa = om.inference_ops(audio, *( [video, flow] if 'video' in encoders else [])).numpy()
+        err = np.abs(oa - ambix).max() / np.abs(ambix).max()
+        print('model[%s]: %d variables, |ambix| max %.3g, oracle(float64) vs reference-code rel err %.2e' % (tag, len(names), np.abs(ambix).max(), err))
+        assert err < 1e-4
 
     np.savez_compressed(OUT, **G)
     print('wrote %s: %d arrays, %d bytes' % (OUT, len(G), os.path.getsize(OUT)))

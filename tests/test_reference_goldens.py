@@ -146,3 +146,86 @@ def test_gpu_kernels_against_reference_goldens():
     for res in (30, 5):
         got = M.ambix_rms_map(ambi, float(res))[0].cpu().numpy()
         assert np.abs(got - G['a13_rms_map_%d' % res]).max() < 1e-5 * G['a13_rms_map_%d' % res].max()
+
+
+# ---- a3-a7, a9, a10: the reference's model-building code (model.py, wrappers/core.py, resnet.py) run eagerly -------------
+
+MODEL_SEED = 7
+
+
+def _model_inputs(seed, batch):                                       # same recipe as make_reference_goldens.model_inputs
+    r = np.random.RandomState(seed)
+    n = 52799
+    tone = 0.2 * np.sin(2 * np.pi * 523.25 * np.arange(n) / 48000.)[None, :, None]
+    audio = (np.round(np.clip(0.1 * r.randn(batch, n, 1) + tone, -1, 1) * 4096) / 4096).astype(np.float32)
+    video = (r.randint(0, 256, size=(batch, 1, 224, 448, 3)) / 255.).astype(np.float32)
+    flow = (r.randint(0, 256, size=(batch, 1, 224, 448, 3)) / 255. - 0.5).astype(np.float32)
+    return audio, video, flow
+
+
+def _model_case(tag):
+    from spatialaudiogen_b200 import weights as PW
+    encoders = ['audio'] if tag == 'a' else ['audio', 'video', 'flow']
+    W = PW.init_weights(encoders, 'unet_mask', seed=MODEL_SEED, stress=True)
+    chk = np.asarray([float(np.asarray(v, np.float64).sum()) for v in W.values()])
+    assert np.array_equal(chk, G['m_%s_weight_checksum' % tag]), 'weights.init_weights changed: regenerate the goldens'
+    audio, video, flow = _model_inputs(MODEL_SEED, 2)
+    return encoders, W, audio, (video, flow) if tag == 'avf' else ()
+
+
+def _maxrel(got, ref):
+    return float(np.abs(np.asarray(got, np.float64) - ref).max() / np.abs(ref).max())
+
+
+@pytest.mark.parametrize('tag', ['a', 'avf'])
+def test_checkpoint_layout_is_what_the_reference_code_creates(tag):
+    """Every variable the reference's model code asked tf for -- full scoped name and shape -- is what the product's
+    checkpoint layout (weights.variable_shapes) declares, and nothing else; the ResNet towers' names are keys of the
+    reference's resnet18.npy (restore_pretrained)."""
+    from spatialaudiogen_b200 import weights as PW
+    created = dict(ast.literal_eval(str(G['m_%s_variables' % tag])))
+    mine = PW.variable_shapes(['audio'] if tag == 'a' else ['audio', 'video', 'flow'], 'unet_mask')
+    assert {k: tuple(v) for k, v in mine.items()} == created
+    assert len(created) == (30 if tag == 'a' else 214)
+    if tag == 'avf':
+        tower = ast.literal_eval(str(G['m_resnet18_npy_keys_used']))
+        assert tower == sorted(k[len('video_encoder/'):] for k in mine if k.startswith('video_encoder/'))
+
+
+@pytest.mark.parametrize('tag', ['a', 'avf'])
+def test_oracle_forward_matches_reference_model_code(tag):
+    """oracle.SptAudioGen.inference_ops (float32, torch ops) against the ambisonics, separated tracks, localisation
+    weights and tower activations that the reference's own inference_ops produced on the same weights and inputs."""
+    encoders, W, audio, vis = _model_case(tag)
+    m = O.SptAudioGen(W, 1, encoders=encoders, separation='unet_mask')
+    y = m.inference_ops(audio, *vis).numpy()
+    assert y.shape == G['m_%s_ambix' % tag].shape == (2, 4800, 3)
+    assert _maxrel(y, G['m_%s_ambix' % tag]) < 2e-5
+    assert _maxrel(m.sep_channels.numpy()[:, 0, :, ::97], G['m_%s_sep_stride97' % tag]) < 2e-5
+    assert _maxrel(m.loc_channels[0].numpy()[:, ::480], G['m_%s_loc_w_stride480' % tag]) < 2e-5
+    assert _maxrel(m.loc_channels[1].numpy()[:, ::480], G['m_%s_loc_b_stride480' % tag]) < 2e-5
+    assert _maxrel(m.ends['stft'].abs().numpy().sum(-1), G['m_%s_inp_spect_sum' % tag]) < 1e-5
+    if tag == 'avf':
+        for k in ('video', 'flow'):
+            assert _maxrel(m.ends[k + '_encoder/conv'].numpy()[:, ::8, ::8, ::4], G['m_avf_%s_conv1_stride' % k]) < 2e-5
+            assert _maxrel(m.ends[k + '_encoder/conv5_2'].numpy()[..., ::16], G['m_avf_%s_conv5_2_stride16' % k]) < 5e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag,precision,tol', [('a', 'fp32', 1e-4), ('a', 'bf16x3', 1e-3), ('avf', 'fp32', 1e-4), ('avf', 'bf16x3', 1e-3)])
+def test_gpu_forward_against_reference_model_code(tag, precision, tol):
+    """The CUDA forward (two-kernel inference_ops and the fused deploy / eval hot loop forward_into) directly against the
+    output of the reference's own model code -- no oracle in between.  Tolerance: north_star's 1e-3 relative on the
+    waveform for the tensor-core path, 1e-4 for the fp32 FFMA path."""
+    from spatialaudiogen_b200.model import SptAudioGen
+    encoders, W, audio, vis = _model_case(tag)
+    m = SptAudioGen(1, encoders=encoders, separation='unet_mask', precision=precision).load_weights(W)
+    a = torch.as_tensor(audio).cuda()
+    kw = dict(video=torch.as_tensor(vis[0]).cuda(), flow=torch.as_tensor(vis[1]).cuda()) if vis else {}
+    y = m.inference_ops(a, **kw).cpu().numpy()
+    assert _maxrel(y, G['m_%s_ambix' % tag]) < tol
+    assert _maxrel(m.sep_channels.cpu().numpy()[:, 0, :, ::97], G['m_%s_sep_stride97' % tag]) < tol
+    out = torch.empty(2, 4800, 3, device='cuda')
+    m.forward_into(a, kw.get('video'), kw.get('flow'), out)
+    torch.cuda.synchronize()
+    assert _maxrel(out.cpu().numpy(), G['m_%s_ambix' % tag]) < tol
