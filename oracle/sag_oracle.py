@@ -22,7 +22,9 @@ tests/golden/reference_goldens.npz, generated in the build container by tests/go
     verbatim and eagerly at full size (B=2, audio-only and audio+video+flow) with the weights served by the scoped
     variable names it asks for: a3-a7, a9, a10 wiring (scopes, the 30 / 214 variable names and shapes, layer order,
     strides, paddings, crops, concat / tile / reshape order, mask and mixing arithmetic; restore_pretrained checked
-    against the reference's resnet18.npy).  This file agrees with it to 5e-8 (float64) / 2e-5 (float32);
+    against the reference's resnet18.npy).  This file agrees with it to 5e-8 (float64) / 2e-5 (float32); likewise the
+    deploy loop (deploy.py:90-152 W2XYZ.deploy: batches of 10, zero-padded tail, mono crop, rows [W,Y,Z,X]) run around
+    that model code, and the EMD columns' wrapper (distance.py:100-143) run around a pyemd stand-in;
   * STILL RESTATED BY HAND, beneath that: the TF kernels themselves (tf.nn.convolution / conv2d_transpose / max_pool /
     contrib batch_norm / matmul of the un-vendored TensorFlow 1.4.0rc1, requirements.txt:10), evaluated in the generator
     by tap-by-tap float64 numpy loops from their published semantics -- independent of the torch

@@ -13,6 +13,7 @@ What is pinned (and by which reference code):
   a1   derived constants                 model.py:24-60          SptAudioGen.__init__
   a12  Hilbert-envelope distance         myutils.py:109-116      compute_envelope_dist
   a13  mesh, SH matrix, RMS energy maps  distance.py:9-52, common.py:121-178, decoder.py:9-28, position.py:5-38
+       EMD columns (emd/dir, emd/dir2)   distance.py:100-143     emd / ambix_emd around a pyemd stand-in (its defining LP)
   a2   framed STFT                       myutils.py:119-147      stft            } the reference's graph-building code run
   a8   inverse STFT                      myutils.py:181-211      istft           } eagerly on a numpy stand-in for the dozen
   a11  STFT distance, LSD, MSE, SNR      model.py:62-154         evaluation_ops  } elementary TF ops it calls (fake_tf)
@@ -28,6 +29,8 @@ What is pinned (and by which reference code):
        TensorFlow-1.4's documented semantics.  Those op semantics are restated here, not executed from TensorFlow;
        everything above them is the reference's own code.  restore_pretrained (resnet.py:238-249) is run against the
        reference's resnet18.npy, which pins the tower's variable names and shapes.
+  --   deploy loop                       deploy.py:90-152        W2XYZ.deploy (batches of 10, zero-padded tail, mono crop,
+       row layout) around the model code above; the disk reader and tf.Session are the only stand-ins
 """
 import importlib.abc
 import importlib.util
@@ -64,7 +67,7 @@ def py2_to_py3(src):
         if 'in reversed(zip(' in line and line.rstrip().endswith(')):'):
             line = line.replace('in reversed(zip(', 'in reversed(list(zip(').rstrip()[:-1] + '):'
         line = line.replace('self.snd_dur/sz[1]', 'self.snd_dur//sz[1]')
-        line = re.sub(r'ss = self\.snd_contx / 2$', 'ss = self.snd_contx // 2', line)
+        line = re.sub(r'ss = self\.(model\.)?snd_contx / 2$', r'ss = self.\1snd_contx // 2', line)
         line = line.replace('x.dtype.base_dtype', 'x.dtype')
         line = line.replace("np.load(os.path.join(PWD, 'resnet18.npy')).all()",
                             "np.load(os.path.join(PWD, 'resnet18.npy'), allow_pickle=True, encoding='latin1').item()")
@@ -74,7 +77,7 @@ def py2_to_py3(src):
 
 class RefFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     """Imports `myutils`, `feeder`, `model`, `definitions`, `pyutils.*` from /root/reference through py2_to_py3."""
-    ROOTS = ('myutils', 'feeder', 'model', 'definitions', 'pyutils')
+    ROOTS = ('myutils', 'feeder', 'model', 'definitions', 'pyutils', 'deploy')
 
     def find_spec(self, name, path, target=None):
         if name.split('.')[0] not in self.ROOTS:
@@ -316,6 +319,17 @@ def model_inputs(seed, batch):
     return audio, video, flow
 
 
+DEPLOY_WINDOWS = 11
+
+
+def deploy_inputs(seed, n):
+    """n consecutive windows of a 4-channel clip + video frames (the test regenerates them from the same recipe)."""
+    r = np.random.RandomState(seed)
+    amb = np.round(np.clip(0.1 * r.randn(n, 52799, 4), -1, 1) * 4096) / 4096
+    vid = (r.randint(0, 256, size=(n, 1, 224, 448, 3)) / 255.).astype(np.float32)
+    return amb, vid
+
+
 def torch_f64():
     import torch
     return torch.float64
@@ -358,6 +372,15 @@ def main():
         G['a13_rms_map_%d' % res] = vis.get_next_frame()
     masked = ambi.astype(np.float64) * np.array([1., 1., 0., 1.])                  # a WXY clip (feeder.py:312-314, eval.py:147-148)
     G['a13_rms_map_30_wxy'] = Rd.SphericalAmbisonicsVisualizer(masked, 48000, window=0.1, angular_res=30.).get_next_frame()
+
+    # a13 EMD columns (distance.py:100-143 `emd` / `ambix_emd`): the reference's wrapper (ground distance, the two mass
+    # normalisations, frame loop) around a pyemd stand-in that solves pyemd.emd's defining EMD-hat LP with scipy / HiGHS
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import sag_oracle as O
+    sys.modules['pyemd'] = types.SimpleNamespace(emd=lambda a, b, d: O.emd_hat_lp(a, b, d))
+    ambi2 = (0.8 * ambi + np.random.RandomState(5).randn(4800, 4) * np.array([0.02, 0.06, 0.05, 0.03])).astype(np.float32)
+    G['a13_ambi2'] = ambi2
+    G['a13_emd_dir_dir2'] = np.asarray(Rd.ambix_emd(ambi2.astype(np.float64), ambi.astype(np.float64), 48000, ang_res=30))
 
     # ---- a12: Hilbert-envelope distance (myutils.py:109-116) -------------------------------------------------------
     import myutils as Ru
@@ -466,6 +489,45 @@ def main():
         err = np.abs(oa - ambix).max() / np.abs(ambix).max()
         print('model[%s]: %d variables, |ambix| max %.3g, oracle(float64) vs reference-code rel err %.2e' % (tag, len(names), np.abs(ambix).max(), err))
         assert err < 1e-4
+
+    # ---- deploy.py:90-152: the reference's deploy loop (batches of 10, zero-padded tail, mono crop, row layout) around
+    # its own model code; the disk reader and the session are the only stand-ins -----------------------------------------
+    import deploy as Rdep
+    enc = ['audio', 'video']
+    W = PW.init_weights(enc, 'unet_mask', seed=MODEL_SEED + 1, stress=True)
+    WEIGHTS.clear(), WEIGHTS.update(W)
+    amb, vid = deploy_inputs(MODEL_SEED + 1, DEPLOY_WINDOWS)
+    chunks = [{'id': 'clip', 'ambix': amb[i], 'video': vid[i]} for i in range(DEPLOY_WINDOWS)]
+
+    class FakeSampleReader(object):
+        def __init__(self, folder, **kw):
+            assert kw['return_video'] and not kw['return_flow'] and not kw['shuffle'] and kw['duration'] == 0.1
+            self.chunks_t, self.queue = [kw['start_time'] + 0.05 + 0.1 * i for i in range(len(chunks))], list(chunks)
+
+        def get(self):
+            return self.queue.pop(0) if self.queue else None
+    Rdep.SampleReader = FakeSampleReader
+    dep = object.__new__(Rdep.W2XYZ)                                   # __init__ builds placeholders / Saver / Session
+    dep.params = types.SimpleNamespace(ambi_order=1, audio_rate=48000, video_rate=10, context=1.0, encoders=enc)
+    dep.duration, dep.batch_size = 0.1, 10                              # deploy.py:49-50
+    dep.model = Rm.SptAudioGen(ambi_order=1, audio_rate=48000, video_rate=10, context=1.0, sample_duration=0.1, encoders=list(enc),
+                               separation='unet_mask', params=Rm.SptAudioGenParams())
+    dep.tba = {'audio': 'ph_audio', 'video': 'ph_video'}
+    batches = []
+
+    def sess_run(fetch, feed_dict):
+        batches.append(int(feed_dict['ph_audio'].shape[0]))
+        return np.asarray(dep.model.inference_ops(is_training=False, audio=_t(np.asarray(feed_dict['ph_audio'], np.float64)),
+                                                  video=_t(np.asarray(feed_dict['ph_video'], np.float64))))
+    dep.sess, dep.ambi_pred_t = types.SimpleNamespace(run=sess_run), None
+    rows = dep.deploy('/clip', 3.0, DEPLOY_WINDOWS * 0.1)
+    assert batches == [10, 10] and rows.shape == (DEPLOY_WINDOWS * 4800, 4) and rows.dtype == np.float64
+    assert np.array_equal(rows[:, 0], amb[:, 24000:28800, 0].reshape(-1))           # W column = the mono crop, exactly
+    G['deploy_pred_stride3'] = rows[::3, 1:].astype(np.float32)                    # Y, Z, X of every third output sample
+    od = O.deploy_assemble(O.SptAudioGen(W, 1, encoders=enc, separation='unet_mask', dtype=torch_f64()), amb, video_windows=vid)
+    err = np.abs(od - rows).max() / np.abs(rows).max()
+    print('deploy loop: %d windows, oracle.deploy_assemble(float64) vs reference deploy.py rel err %.2e' % (DEPLOY_WINDOWS, err))
+    assert err < 1e-4
 
     np.savez_compressed(OUT, **G)
     print('wrote %s: %d arrays, %d bytes' % (OUT, len(G), os.path.getsize(OUT)))

@@ -38,6 +38,21 @@ def test_a13_mesh_sh_matrix_and_energy_maps_match_reference():
     assert np.abs(O.ambix_rms_map(ambi * np.array([1., 1., 0., 1.]), 30.) - G['a13_rms_map_30_wxy']).max() < 1e-14
 
 
+def test_a13_emd_columns_match_reference_wrapper():
+    """emd/dir and emd/dir2 of one window: the reference's distance.ambix_emd / emd (ground distance, normalisations, frame
+    loop) with pyemd.emd stood in by its defining LP.  Checked: the oracle's restatement, and the product's host path
+    (metrics.ambix_emd_from_maps -> sag_emd_hat, the min-cost-flow solver in libsag.so; no GPU involved) on the
+    reference's own energy maps."""
+    maps_of = lambda a: O.ambix_rms_map(a, 30.)                        # (itself pinned by the test above)
+    ref = G['a13_emd_dir_dir2']
+    a2, a1 = G['a13_ambi2'].astype(np.float64), G['a13_ambi'].astype(np.float64)
+    got = O.ambix_emd(a2, a1, 30.)
+    assert np.allclose(got, ref, rtol=1e-9, atol=1e-12)
+    from spatialaudiogen_b200 import metrics as M
+    d1, d2 = M.ambix_emd_from_maps(maps_of(a2)[None], maps_of(a1)[None], 30.)
+    assert np.allclose([d1[0], d2[0]], ref, rtol=1e-9, atol=1e-12)
+
+
 def test_a12_envelope_distance_matches_reference():
     got = O.compute_envelope_dist(G['a12_pred'], G['a12_gt'])
     # (the reference hands scipy.signal.hilbert float32 signals: its transform runs in single precision)
@@ -229,3 +244,49 @@ def test_gpu_forward_against_reference_model_code(tag, precision, tol):
     m.forward_into(a, kw.get('video'), kw.get('flow'), out)
     torch.cuda.synchronize()
     assert _maxrel(out.cpu().numpy(), G['m_%s_ambix' % tag]) < tol
+
+
+# ---- deploy.py:90-152: the reference's deploy loop around its own model code ---------------------------------------------
+
+DEPLOY_WINDOWS = 11
+
+
+def _deploy_inputs(seed, n):                                          # same recipe as make_reference_goldens.deploy_inputs
+    r = np.random.RandomState(seed)
+    amb = np.round(np.clip(0.1 * r.randn(n, 52799, 4), -1, 1) * 4096) / 4096
+    vid = (r.randint(0, 256, size=(n, 1, 224, 448, 3)) / 255.).astype(np.float32)
+    return amb, vid
+
+
+def test_oracle_deploy_assemble_matches_reference_deploy_loop():
+    """oracle.deploy_assemble (the CPU checker of the deploy row) against the reference's own deploy loop + model code."""
+    from spatialaudiogen_b200 import weights as PW
+    enc = ['audio', 'video']
+    W = PW.init_weights(enc, 'unet_mask', seed=MODEL_SEED + 1, stress=True)
+    amb, vid = _deploy_inputs(MODEL_SEED + 1, DEPLOY_WINDOWS)
+    rows = O.deploy_assemble(O.SptAudioGen(W, 1, encoders=enc, separation='unet_mask'), amb, video_windows=vid)
+    assert rows.dtype == np.float64 and rows.shape == (DEPLOY_WINDOWS * 4800, 4)
+    assert np.array_equal(rows[:, 0], amb[:, 24000:28800, 0].reshape(-1))
+    assert _maxrel(rows[::3, 1:], G['deploy_pred_stride3']) < 5e-5
+
+
+@pytest.mark.gpu
+def test_gpu_w2xyz_against_reference_deploy_loop():
+    """W2XYZ.deploy_windows against the rows the reference's own W2XYZ.deploy produced for 11 windows of an audio+video
+    model: a full batch of 10 and a tail of 1 zero-padded to 10 (with batch-statistics BN in the video tower the padding
+    changes the tail's output, so this pins it), W = the exact mono crop, rows [W, Y, Z, X] in float64."""
+    from spatialaudiogen_b200 import weights as PW
+    from spatialaudiogen_b200.deploy import W2XYZ
+    from types import SimpleNamespace
+    enc = ['audio', 'video']
+    W = PW.init_weights(enc, 'unet_mask', seed=MODEL_SEED + 1, stress=True)
+    amb, vid = _deploy_inputs(MODEL_SEED + 1, DEPLOY_WINDOWS)
+    params = SimpleNamespace(encoders=enc, separation='unet_mask', ambi_order=1, audio_rate=48000, video_rate=10, context=1.0,
+                             num_sep_tracks=32, fft_window=0.025, context_units=[64, 128, 128], freq_mask_units=[256], loc_units=[512, 512])
+    rows = W2XYZ(params=params, weights=W).deploy_windows(amb, video_windows=vid)
+    assert rows.dtype == np.float64 and rows.shape == (DEPLOY_WINDOWS * 4800, 4)
+    assert np.array_equal(rows[:, 0], amb[:, 24000:28800, 0].reshape(-1))
+    ref = G['deploy_pred_stride3']
+    assert _maxrel(rows[::3, 1:], ref) < 1e-3
+    tail = slice(10 * 4800 // 3 + 1, None)                             # the zero-padded batch on its own
+    assert _maxrel(rows[::3, 1:][tail], ref[tail]) < 1e-3
