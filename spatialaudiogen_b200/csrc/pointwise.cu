@@ -62,27 +62,43 @@ __device__ __forceinline__ void bn_scale_shift_to_smem(const BnStats& bn, int c,
   __syncthreads();
 }
 
-__global__ void bn_apply_stats_kernel(const float4* __restrict__ x, const BnStats bn, const ActView res, int relu, const ActView y,
-                                      int64_t n4, int c) {
+// Memory-level parallelism: a thread fetches BN_UNROLL vectors (and their residuals) before it touches any of them -- with one
+// 16-byte load in flight per thread the kernel sat at 35-44 % of the HBM rate on scoreboard stalls (profiles/r1_small_kernels_ncu.txt).
+constexpr int BN_UNROLL = 4;
+__global__ void __launch_bounds__(256, 4) bn_apply_stats_kernel(const float4* __restrict__ x, const BnStats bn, const ActView res, int relu,
+                                                                const ActView y, int64_t n4, int c) {
   extern __shared__ float s_ss[];
   float* s_scale = s_ss;
   float* s_shift = s_ss + c;
   pdl_prologue();
   bn_scale_shift_to_smem(bn, c, s_scale, s_shift);
   const int c4 = c / 4;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    int cc = (int)(i % c4) * 4;
-    float4 v = __ldg(x + i);
-    const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc);
-    const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc);
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (res.p != nullptr) {
-      float4 r = load_act4(res.p, res.fmt, res.plane, i * 4);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  const bool has_res = res.p != nullptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += BN_UNROLL * stride) {
+    float4 v[BN_UNROLL], r[BN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {                    // vector i0 + u*stride: all loads first
+      const int64_t i = i0 + (int64_t)u * stride;
+      if (i < n4) {
+        v[u] = __ldg(x + i);
+        if (has_res) r[u] = load_act4(res.p, res.fmt, res.plane, i * 4);
+      }
     }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    store_act4(y.p, y.fmt, y.plane, i * 4, v);
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const int64_t i = i0 + (int64_t)u * stride;
+      if (i < n4) {
+        const int cc = (int)(i % c4) * 4;
+        const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc);
+        const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc);
+        float4 w = v[u];
+        w.x = fmaf(w.x, sc.x, sh.x); w.y = fmaf(w.y, sc.y, sh.y); w.z = fmaf(w.z, sc.z, sh.z); w.w = fmaf(w.w, sc.w, sh.w);
+        if (has_res) { w.x += r[u].x; w.y += r[u].y; w.z += r[u].z; w.w += r[u].w; }
+        if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+        store_act4(y.p, y.fmt, y.plane, i * 4, w);
+      }
+    }
   }
 }
 
@@ -140,8 +156,11 @@ __global__ void bn_relu_maxpool_kernel(const float* __restrict__ x, const float*
   }
 }
 
-__global__ void bn_relu_maxpool_stats_kernel(const float* __restrict__ x, const BnStats bn, int n, int h, int w, int c, int oh,
-                                             int ow, int pt, int pl, const ActView y) {
+// The nine taps are fetched branch-free: an out-of-range tap is clamped onto the nearest row / column, which is itself a tap of the
+// same window, so the maximum is unchanged (max is idempotent) and the nine 16-byte loads are all in flight before the first use --
+// the skip-by-branch form issued them one basic block at a time and ran at a third of the HBM rate.
+__global__ void __launch_bounds__(256, 4) bn_relu_maxpool_stats_kernel(const float* __restrict__ x, const BnStats bn, int n, int h, int w,
+                                                                       int c, int oh, int ow, int pt, int pl, const ActView y) {
   extern __shared__ float s_ss[];
   float* s_scale = s_ss;
   float* s_shift = s_ss + c;
@@ -156,22 +175,23 @@ __global__ void bn_relu_maxpool_stats_kernel(const float* __restrict__ x, const 
     int ox = (int)(r % ow); r /= ow;
     int oy = (int)(r % oh);
     int b = (int)(r / oh);
+    float4 v[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = min(max(oy * 2 + dy - pt, 0), h - 1);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = min(max(ox * 2 + dx - pl, 0), w - 1);
+        v[dy * 3 + dx] = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * h + iy) * w + ix) * c + cc));
+      }
+    }
     const float4 sc = *reinterpret_cast<const float4*>(s_scale + cc);
     const float4 sh = *reinterpret_cast<const float4*>(s_shift + cc);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      int iy = oy * 2 + dy - pt;
-      if (iy < 0 || iy >= h) continue;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        int ix = ox * 2 + dx - pl;
-        if (ix < 0 || ix >= w) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * h + iy) * w + ix) * c + cc));
-        v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-        v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-      }
+    for (int t = 0; t < 9; ++t) {
+      m.x = fmaxf(m.x, fmaxf(fmaf(v[t].x, sc.x, sh.x), 0.f)); m.y = fmaxf(m.y, fmaxf(fmaf(v[t].y, sc.y, sh.y), 0.f));
+      m.z = fmaxf(m.z, fmaxf(fmaf(v[t].z, sc.z, sh.z), 0.f)); m.w = fmaxf(m.w, fmaxf(fmaf(v[t].w, sc.w, sh.w), 0.f));
     }
     store_act4(y.p, y.fmt, y.plane, i * 4, m);
   }
