@@ -29,6 +29,7 @@ What is pinned (and by which reference code):
        TensorFlow-1.4's documented semantics.  Those op semantics are restated here, not executed from TensorFlow;
        everything above them is the reference's own code.  restore_pretrained (resnet.py:238-249) is run against the
        reference's resnet18.npy, which pins the tower's variable names and shapes.
+  f4   overlay maps, stereo down-mix     myutils.py:224-311      gen_360video (ffmpeg, video files, colour map and resize recorded)
   --   deploy loop                       deploy.py:90-152        W2XYZ.deploy (batches of 10, zero-padded tail, mono crop,
        row layout) around the model code above; the disk reader and tf.Session are the only stand-ins
 """
@@ -319,6 +320,13 @@ def model_inputs(seed, batch):
     return audio, video, flow
 
 
+def f4_clip():
+    """3 s of first-order ambisonics whose dominant direction moves (the test regenerates it from the same recipe)."""
+    clip = (np.random.RandomState(11).randn(3 * 48000, 4) * np.array([0.2, 0.1, 0.03, 0.15])).astype(np.float32)
+    clip[48000:96000, 1] *= 3.
+    return clip
+
+
 DEPLOY_WINDOWS = 11
 
 
@@ -449,6 +457,40 @@ def main():
     G['a11_stft_ps'], G['a11_lsd_ps'], G['a11_mse_ps'], G['a11_snr_ps'] = [np.asarray(v) for v in (stft_ps, lsd_ps, mse_ps, snr_ps)]
     G['a11_metric_names'] = np.asarray(repr(list(metrics.keys())))
     G['a11_metric_values'] = np.asarray([float(np.asarray(v)) for v in metrics.values()])
+
+    # ---- f4: gen_360video's overlay / down-mix arithmetic (myutils.py:224-311); ffmpeg, the video files, the colour map and
+    # the image resize are stood in by recorders, everything between them is the reference's code ------------------------
+    import pyutils.iolib.audio as Ria
+    import pyutils.iolib.video as Riv
+    clip = f4_clip()
+    rec = {'alpha': [], 'index': [], 'stereo': None}
+
+    class FakeVideoReader(object):
+        def __init__(self, fn, rate=None):
+            self.fps, self.frame_shape, self.left = 10, (37, 72, 3), 23
+
+        def get(self):
+            self.left -= 1
+            return np.zeros(self.frame_shape, np.uint8) if self.left >= 0 else None
+
+    def fake_resize(img, shape):
+        rec['alpha' if img.shape[-1] == 1 else 'index'].append(np.array(img))
+        return np.zeros(tuple(shape) + (img.shape[-1],))
+    Riv.VideoReader, Riv.VideoWriter = FakeVideoReader, lambda fn, fps: types.SimpleNamespace(write_frame=lambda f: None)
+    Ria.load_wav = lambda fn, rate=None: (clip.astype(np.float64), 48000)
+    Ria.save_wav = lambda fn, data, rate: rec.__setitem__('stereo', np.array(data))
+    sys.modules['matplotlib'].pyplot.cm.YlOrRd = lambda v: np.stack([v, v, v, v], 1)      # colour = index / 255
+    sys.modules['skimage.transform'].resize = fake_resize
+    real_os = Ru.os
+    Ru.os = types.SimpleNamespace(system=lambda cmd: 0, remove=lambda fn: None, chdir=lambda d: None, getcwd=real_os.getcwd, path=real_os.path)
+    try:
+        Ru.gen_360video('a.wav', 'v.mp4', 'out.mp4', inject_meta=True, overlay_map=True, binauralize=True)
+    finally:
+        Ru.os = real_os
+    assert len(rec['alpha']) == len(rec['index']) == 23
+    G['f4_rms_frames'] = np.stack(rec['alpha'], 0)[..., 0].astype(np.float32)             # the clipped 2*rms - 0.7 maps
+    G['f4_colour_index'] = np.round(np.stack(rec['index'], 0)[..., 0] * 255).astype(np.uint8)
+    G['f4_stereo_stride97'] = rec['stereo'][::97]
 
     # ---- a3-a7, a9, a10: the reference's model-building code, run eagerly (fake_tf_graph) -----------------------------------
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))

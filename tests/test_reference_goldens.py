@@ -290,3 +290,36 @@ def test_gpu_w2xyz_against_reference_deploy_loop():
     assert _maxrel(rows[::3, 1:], ref) < 1e-3
     tail = slice(10 * 4800 // 3 + 1, None)                             # the zero-padded batch on its own
     assert _maxrel(rows[::3, 1:][tail], ref[tail]) < 1e-3
+
+
+# ---- f4: gen_360video's overlay / down-mix arithmetic (myutils.py:224-311) --------------------------------------------
+
+def _f4_clip():                                                        # same recipe as make_reference_goldens.f4_clip
+    clip = (np.random.RandomState(11).randn(3 * 48000, 4) * np.array([0.2, 0.1, 0.03, 0.15])).astype(np.float32)
+    clip[48000:96000, 1] *= 3.
+    return clip
+
+
+def test_f4_overlay_maps_and_stereo_downmix_match_reference_gen_360video():
+    """The reference's gen_360video run with ffmpeg / video files / colour map / image resize stood in by recorders: the
+    heat-map frames it blends over the video (decimation by 5, 5-degree mesh, min-max normalisation with the 0.005 guard,
+    5-frame linear blend, 2*rms - 0.7 clipped), the colour-map index it derives from them, and the "binauralize" stereo
+    down-mix -- against the oracle's and the product's host arithmetic."""
+    from spatialaudiogen_b200 import myutils
+    clip = _f4_clip()
+    ref = G['f4_rms_frames']
+    assert ref.shape == (23, 37, 72)                                    # the fake video ran out after 23 frames
+    got = O.energy_map_frames(clip, 48000, 10.)
+    assert got.shape == (25, 37, 72) and np.abs(got[:23] - ref).max() < 2e-6
+    idx = np.minimum((got[:23] * 255).astype(int), 255)                 # myutils.py:273-274
+    assert np.mean(idx != G['f4_colour_index']) < 1e-4                  # (float32-rounded golden: a handful of ties at most)
+    st = myutils.ambix_to_stereo(clip)
+    assert np.abs(st[::97] - G['f4_stereo_stride97']).max() < 1e-12 and abs(np.abs(st).max() - 0.95) < 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_overlay_maps_against_reference_gen_360video():
+    """myutils.energy_map_frames (the K8 energy-map kernel + the host blend) directly against the reference's frames."""
+    from spatialaudiogen_b200 import myutils
+    got = myutils.energy_map_frames(_f4_clip(), 48000, 10.)
+    assert got.shape == (25, 37, 72) and np.abs(got[:23] - G['f4_rms_frames']).max() < 1e-3
