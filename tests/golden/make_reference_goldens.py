@@ -19,6 +19,7 @@ What is pinned (and by which reference code):
   a11  STFT distance, LSD, MSE, SNR      model.py:62-154         evaluation_ops  } elementary TF ops it calls (fake_tf)
   f2   clip-edge padding / file offsets  feeder.py:50-105        AudioReader.get (wav decoding stubbed by arrays)
        flow de-quantisation              feeder.py:138-161       FlowReader.get_by_index
+       chunk schedule + reader requests  feeder.py:164-278       SampleReader (file readers recorded)
   --   train-params.txt parsing          myutils.py:40-85        load_params
   a3-a7, a9, a10  encoders, bottleneck,  model.py:161-434, pyutils/tflib/wrappers/core.py:10-220,
        localisation, mask decoder, mix   pyutils/tflib/models/image/resnet.py:110-249   (SptAudioGen.inference_ops)
@@ -432,6 +433,43 @@ def main():
     fr.lims = np.stack([np.linspace(0.5, 1.5, 40), np.linspace(10., 30., 40)], 1)
     G['f2_flow_raw'], G['f2_flow_lims'] = raw, fr.lims
     G['f2_flow_out'] = fr.get_by_index(1.3, 2)
+
+    # ---- f2: SampleReader's chunk schedule and the reader calls it makes (feeder.py:164-278), file readers recorded -----------
+    calls = []
+
+    class FakeReader(object):
+        frame_shape = (224, 448, 3)
+
+        def __init__(self, *a, **k):
+            calls.append(('init', type(self).__name__) + tuple(os.path.basename(str(v)) if isinstance(v, str) else v for v in a[:3] if not callable(v)))
+
+        def get(self, start, size, rotation=None):
+            calls.append(('get', float(start), int(size), rotation))
+            return np.zeros((size, 4))
+
+        def get_by_index(self, start, size, rotation=None):
+            calls.append((type(self).__name__, float(start), int(size), rotation))
+            return np.zeros((size, 2, 2, 3))
+    Rf.AudioReader, Rf.VideoReader, Rf.FlowReader = (type(n, (FakeReader,), {}) for n in ('AudioReader', 'VideoReader', 'FlowReader'))
+    folder = os.path.join(tempfile.mkdtemp(), 'clip_xyz')
+    os.makedirs(folder)
+    sched = ''.join('%.2f %.6f\n' % (0.55 + 0.1 * i, p) for i, p in enumerate(np.random.RandomState(3).uniform(0, 0.02, 60)))
+    open(os.path.join(folder, 'audio_pow.lst'), 'w').write(sched)
+    G['f2_sched_audio_pow_lst'] = np.asarray(sched)
+    cases = [dict(shuffle=False, random_rotations=False), dict(shuffle=False, random_rotations=False, skip_rate=10),
+             dict(shuffle=False, random_rotations=False, skip_silence_thr=0.01, return_flow=True),
+             dict(shuffle=False, random_rotations=False, start_time=2.0, sample_duration=1.5, skip_silence_thr=None, skip_rate=None),
+             dict(shuffle=False, random_rotations=False, start_time=0.3, sample_duration=1.0),
+             dict(shuffle=False, random_rotations=False, num_threads=4, thread_id=2, return_video=False),
+             dict(shuffle=False, random_rotations=False, audio_rate=16000, video_rate=5, context=2.0, duration=0.2, skip_rate=7)]
+    out = []
+    for kw in cases:
+        del calls[:]
+        sr = Rf.SampleReader(folder, **kw)
+        got = [sr.get() for _ in range(3)]
+        out.append(dict(kwargs=kw, chunks_t=list(sr.chunks_t), audio_size=sr.audio_size, video_size=sr.video_size,
+                        ids=[c['id'] if c else None for c in got], calls=list(calls)))
+    G['f2_sched_cases'] = np.asarray(repr(out))
 
     # ---- a2 / a8 / a11: the reference's own graph code for stft / istft / evaluation_ops, run eagerly (fake_tf) --------
     x = np.round(np.clip(0.1 * rng.randn(1, 1, 52799) + 0.3 * np.sin(2 * np.pi * 440 * np.arange(52799) / 48000.), -1, 1) * 4096) / 4096

@@ -323,3 +323,44 @@ def test_gpu_overlay_maps_against_reference_gen_360video():
     from spatialaudiogen_b200 import myutils
     got = myutils.energy_map_frames(_f4_clip(), 48000, 10.)
     assert got.shape == (25, 37, 72) and np.abs(got[:23] - G['f4_rms_frames']).max() < 1e-3
+
+
+# ---- f2: SampleReader's chunk schedule and reader calls (feeder.py:164-278) -----------------------------------------------
+
+def test_f2_sample_reader_schedule_and_calls_match_reference(tmp_path, monkeypatch):
+    """readers.SampleReader on the audio_pow.lst the reference's SampleReader was run on, for the same argument sets
+    (skip_rate, silence threshold, start / duration window, thread slices, other rates): identical chunk times, window
+    sizes, sample ids and the same (start, size, rotation) requests to the audio / video / flow readers, in the same order.
+    (One deliberate difference: with return_video=False the product does not open the video folder at all.)"""
+    from spatialaudiogen_b200 import readers as R
+    calls = []
+
+    class FakeReader(object):
+        frame_shape = (224, 448, 3)
+
+        def __init__(self, *a, **k):
+            calls.append(('init', type(self).__name__) + tuple(os.path.basename(str(v)) if isinstance(v, str) else v for v in a[:3] if not callable(v)))
+
+        def get(self, start, size, rotation=None):
+            calls.append(('get', float(start), int(size), rotation))
+            return np.zeros((size, 4))
+
+        def get_by_index(self, start, size, rotation=None):
+            calls.append((type(self).__name__, float(start), int(size), rotation))
+            return np.zeros((size, 2, 2, 3))
+    for n in ('AudioReader', 'VideoReader', 'FlowReader'):
+        monkeypatch.setattr(R, n, type(n, (FakeReader,), {}))
+    folder = str(tmp_path / 'clip_xyz')
+    os.makedirs(folder)
+    open(os.path.join(folder, 'audio_pow.lst'), 'w').write(str(G['f2_sched_audio_pow_lst']))
+    cases = ast.literal_eval(str(G['f2_sched_cases']))
+    assert len(cases) == 7
+    for ref in cases:
+        del calls[:]
+        sr = R.SampleReader(folder, **ref['kwargs'])
+        got = [sr.get() for _ in range(3)]
+        assert sr.chunks_t == ref['chunks_t'], ref['kwargs']
+        assert (sr.audio_size, sr.video_size) == (ref['audio_size'], ref['video_size'])
+        assert [c['id'] if c else None for c in got] == ref['ids']
+        want = [c for c in ref['calls'] if ref['kwargs'].get('return_video', True) or c[:2] != ('init', 'VideoReader')]
+        assert calls == want, ref['kwargs']
