@@ -19,6 +19,7 @@ What is pinned (and by which reference code):
   a11  STFT distance, LSD, MSE, SNR      model.py:62-154         evaluation_ops  } elementary TF ops it calls (fake_tf)
   f2   clip-edge padding / file offsets  feeder.py:50-105        AudioReader.get (wav decoding stubbed by arrays)
        flow de-quantisation              feeder.py:138-161       FlowReader.get_by_index
+       frame indexing, rotation roll     feeder.py:106-132       VideoReader.get_by_index (jpg decoding stubbed by arrays)
        chunk schedule + reader requests  feeder.py:164-278       SampleReader (file readers recorded)
   --   train-params.txt parsing          myutils.py:40-85        load_params
   a3-a7, a9, a10  encoders, bottleneck,  model.py:161-434, pyutils/tflib/wrappers/core.py:10-220,
@@ -433,6 +434,20 @@ def main():
     fr.lims = np.stack([np.linspace(0.5, 1.5, 40), np.linspace(10., 30., 40)], 1)
     G['f2_flow_raw'], G['f2_flow_lims'] = raw, fr.lims
     G['f2_flow_out'] = fr.get_by_index(1.3, 2)
+
+    # ---- f2: VideoReader.get_by_index (feeder.py:106-132): frame indexing, img_prep, rotation roll; jpg decoding stood in ----
+    vfolder = tempfile.mkdtemp()
+    vframes = np.random.RandomState(4).randint(0, 256, size=(30, 6, 16, 3)).astype(np.uint8)
+    for i in range(30):
+        open(os.path.join(vfolder, '%06d.jpg' % i), 'w').close()
+    Rf.sio = types.SimpleNamespace(imread=lambda fn: vframes[int(os.path.basename(fn)[:6])])
+    vr = Rf.VideoReader(vfolder, 10, Ru.img_prep_fcn())
+    G['f2_video_frames'] = vframes
+    vcases = [(0.0, 1, None), (1.26, 3, None), (-0.3, 2, None), (2.0, 1, 0.7), (0.5, 2, -2.0), (1.0, 1, 3.1)]
+    G['f2_video_cases'] = np.asarray(repr(vcases))
+    G['f2_video_meta'] = np.asarray([vr.num_frames, vr.duration, vr.rate] + list(vr.frame_shape), np.float64)
+    for i, (t0, size, rot) in enumerate(vcases):
+        G['f2_video_out_%d' % i] = vr.get_by_index(t0, size, rot)
 
     # ---- f2: SampleReader's chunk schedule and the reader calls it makes (feeder.py:164-278), file readers recorded -----------
     calls = []

@@ -364,3 +364,18 @@ def test_f2_sample_reader_schedule_and_calls_match_reference(tmp_path, monkeypat
         assert [c['id'] if c else None for c in got] == ref['ids']
         want = [c for c in ref['calls'] if ref['kwargs'].get('return_video', True) or c[:2] != ('init', 'VideoReader')]
         assert calls == want, ref['kwargs']
+
+
+def test_f2_video_reader_indexing_and_rotation_match_reference(tmp_path, monkeypatch):
+    """readers.VideoReader.get_by_index on the frames the reference's VideoReader was run on (jpg decoding stood in on both
+    sides): first frame = max(int(t * rate), 0), img_prep, single-frame axis, rotation as a roll of the width axis."""
+    from spatialaudiogen_b200 import readers as R, myutils
+    frames = G['f2_video_frames']
+    for i in range(frames.shape[0]):
+        open(str(tmp_path / ('%06d.jpg' % i)), 'w').close()
+    monkeypatch.setattr(R, '_imread', lambda fn: frames[int(os.path.basename(fn)[:6])])
+    vr = R.VideoReader(str(tmp_path), 10, myutils.img_prep_fcn())
+    assert [vr.num_frames, vr.duration, vr.rate] + list(vr.frame_shape) == list(G['f2_video_meta'])
+    for i, (t0, size, rot) in enumerate(ast.literal_eval(str(G['f2_video_cases']))):
+        got = vr.get_by_index(t0, size, rot)
+        assert got.shape == G['f2_video_out_%d' % i].shape and np.array_equal(got, G['f2_video_out_%d' % i]), (t0, size, rot)
