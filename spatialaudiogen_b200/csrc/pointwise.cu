@@ -381,11 +381,14 @@ __global__ void space_to_depth16_kernel(const float* __restrict__ x, int n, int 
     for (int e = 0; e < 16; ++e) v[e] = 0.f;
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
+      // border pixels read a clamped (valid) address and are zeroed by a select: no branch between the 4*C loads
       const int iy = 2 * y2 + (sub >> 1) - pt, ix = 2 * x2 + (sub & 1) - pl;
-      if ((unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w) {
-        const float* p = x + (((int64_t)b * h + iy) * w + ix) * C;
+      const bool inside = (unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w;
+      const float* p = x + (((int64_t)b * h + min(max(iy, 0), h - 1)) * w + min(max(ix, 0), w - 1)) * C;
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) v[sub * C + ch] = __ldg(p + ch);
+      for (int ch = 0; ch < C; ++ch) {
+        const float t = __ldg(p + ch);
+        v[sub * C + ch] = inside ? t : 0.f;
       }
     }
 #pragma unroll

@@ -1,10 +1,11 @@
 """Host emulation of the streaming BN kernels' per-thread code (no GPU, no oracle).
 
-The bodies of `bn_apply_stats_kernel` and `bn_relu_maxpool_stats_kernel` (csrc/pointwise.cu) -- their grid-stride /
+The bodies of `bn_apply_stats_kernel`, `bn_relu_maxpool_stats_kernel` and `space_to_depth16_kernel` (csrc/pointwise.cu) -- their grid-stride /
 unrolled loops, index arithmetic, clamped taps and the split-bf16 load / store helpers -- are cut out of the shipped
 source TEXT, the CUDA keywords are mapped onto plain C++ (threadIdx / blockIdx become globals that a host loop walks
 through every thread of the grid), compiled with g++ and compared with numpy formulas of the same operators
-(reference core.py:209-210 batch-norm with batch statistics, resnet.py:135 3x3/2 SAME max-pool).  It checks exactly what
+(reference core.py:209-210 batch-norm with batch statistics, resnet.py:135 3x3/2 SAME max-pool; the 2x2 space-to-depth
+of the zero-bordered frame that turns resnet.py:133's 7x7/2 conv into a 4x4/1 one).  It checks exactly what
 a GPU-less change to those loops can break: every element visited once, right channel, right tap set, right planes."""
 import ctypes as C
 import os
@@ -73,6 +74,15 @@ extern "C" void emu_maxpool(const float* x, const double* sum, const double* sqs
     bn_relu_maxpool_stats_kernel(x, mk(sum, sqs, g, be, inv), n, h, w, c, oh, ow, pt, pl, view(y, y_fmt, y_plane));
   });
 }
+extern "C" void emu_s2d(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, void* y, int y_fmt, int64_t y_plane,
+                        int grid, int block) {
+  for_each_thread(grid, block, [&] {
+    if (c == 1) space_to_depth16_kernel<1>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (c == 2) space_to_depth16_kernel<2>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (c == 3) space_to_depth16_kernel<3>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else space_to_depth16_kernel<4>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+  });
+}
 '''
 
 
@@ -85,7 +95,8 @@ def _host_source():
     t = open(SRC).read()
     parts = [_cut(t, '__device__ __forceinline__ void store_act4(', 'static int g_num_sms'),
              _cut(t, 'constexpr int BN_UNROLL', 'int launch_bn_apply_stats('),
-             _cut(t, '__global__ void __launch_bounds__(256, 4) bn_relu_maxpool_stats_kernel(', 'int launch_bn_relu_maxpool_stats(')]
+             _cut(t, '__global__ void __launch_bounds__(256, 4) bn_relu_maxpool_stats_kernel(', 'int launch_bn_relu_maxpool_stats('),
+             _cut(t, 'template <int C>\n__global__ void space_to_depth16_kernel(', 'int launch_space_to_depth16(')]
     body = '\n'.join(parts)
     body = re.sub(r'__global__\s+void\s+(__launch_bounds__\([^)]*\)\s*)?', 'static void ', body)
     body = body.replace('__device__ __forceinline__', 'static inline').replace('extern __shared__ float s_ss[];', '')
@@ -199,3 +210,25 @@ def test_bn_relu_maxpool_thread_code(emu, n, h, w, c, grid, block, y_fmt):
     else:
         hi, lo = _planes_to_f32(y, m)
         assert np.allclose((hi + lo).reshape(want.shape), want, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('n,h,w,c,pt,pl,grid,block', [(2, 8, 12, 3, 2, 2, 3, 16), (1, 7, 5, 3, 3, 3, 2, 8), (1, 6, 6, 1, 0, 0, 1, 5), (2, 5, 9, 4, 2, 3, 4, 32),
+                                                     (1, 224 // 8, 448 // 8, 3, 2, 2, 2, 64), (1, 4, 4, 2, 1, 0, 7, 3)])
+@pytest.mark.parametrize('y_fmt', [0, 1])
+def test_space_to_depth16_thread_code(emu, n, h, w, c, pt, pl, grid, block, y_fmt):
+    rng = np.random.RandomState(h * 31 + w + c)
+    x = rng.randn(n, h, w, c).astype(np.float32)
+    h2, w2 = (h + pt + 3) // 2 + 1, (w + pl + 3) // 2 + 1                  # a frame with a zero border on every side
+    big = np.zeros((n, 2 * h2 + 2, 2 * w2 + 2, c), np.float32)
+    big[:, pt:pt + h, pl:pl + w] = x
+    want = np.zeros((n, h2, w2, 16), np.float32)
+    for sub in range(4):
+        want[..., sub * c:(sub + 1) * c] = big[:, (sub >> 1):(sub >> 1) + 2 * h2:2, (sub & 1):(sub & 1) + 2 * w2:2][:, :h2, :w2]
+    m = n * h2 * w2 * 16
+    y = np.full(m, np.nan, np.float32) if y_fmt == 0 else np.full(2 * m, 0xffff, np.uint16)
+    emu.emu_s2d(_p(x), n, h, w, c, pt, pl, h2, w2, _p(y), y_fmt, C.c_int64(2 * m if y_fmt else 0), grid, block)
+    if y_fmt == 0:
+        assert np.array_equal(y.reshape(want.shape), want)
+    else:
+        hi, lo = _planes_to_f32(y, m)
+        assert np.allclose((hi + lo).reshape(want.shape), want, rtol=2e-5, atol=0) and np.array_equal((hi + lo).reshape(want.shape) == 0, want == 0)
