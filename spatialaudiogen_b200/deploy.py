@@ -7,8 +7,6 @@ windows from disk through feeder.SampleReader; here the windows are handed in as
 on-disk reader is a "next" row.  `sess.run` becomes one sag_forward per batch on the caller's stream,
 with the host<->device copies on pinned buffers.
 """
-import os
-
 import numpy as np
 import torch
 

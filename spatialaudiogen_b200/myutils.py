@@ -1,7 +1,6 @@
 """The DSP helpers and parameter parsing of the reference's myutils.py that sit on the inference path, with the same
 names and argument meaning: stft / istft (myutils.py:119-147, 181-211) run as fused shared-memory FFT kernels in
 libsag.so; load_params / img_prep_fcn (myutils.py:40-89) are host-side and kept verbatim in behaviour."""
-import ctypes as C
 
 import numpy as np
 import torch
