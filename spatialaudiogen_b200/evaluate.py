@@ -125,6 +125,29 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
         yield flush(pending)
 
 
+def evaluate_model_dir(model_dir, subset_fn=None, overwrite=False, db_dir=None, audio_layouts_fn='meta/audio_layouts.txt', batch_size=16,
+                       drop_remainder=False, precision=None, device=None):
+    """eval.py:29-215 `main`: the model of `model_dir` (train-params.txt + checkpoint, restored by name) over the per-video
+    folders of the dataset directory (`db_dir`, default the one recorded in train-params.txt) restricted to `subset_fn`, with
+    the eval schedule and the channel masks of `audio_layouts_fn`; writes `<model_dir>/eval-detailed.txt` (refusing to
+    overwrite it unless asked, eval.py:31-32) and returns (sample ids, rows (N, 28) CUDA).  The reference's queue drops the
+    last, short batch; here it is evaluated unless drop_remainder."""
+    import os
+    from . import myutils, readers
+    from .deploy import W2XYZ
+    eval_fn = os.path.join(model_dir, 'eval-detailed.txt')
+    assert os.path.exists(model_dir), 'Model dir does not exist.'
+    assert overwrite or not os.path.exists(eval_fn), 'Evaluation file already exists.'
+    params = myutils.load_params(model_dir)
+    folders = readers.sample_folders(db_dir if db_dir is not None else params.db_dir, subset_fn)
+    masks = readers.load_channel_masks(audio_layouts_fn) if audio_layouts_fn is not None and os.path.exists(audio_layouts_fn) else None
+    model = W2XYZ(model_dir, params=params, precision=precision, device=device).model      # same construction / restore as eval.py:75-118
+    batches = folder_batches(folders, params, batch_size=batch_size, channel_masks=masks, device=model.device, drop_remainder=drop_remainder)
+    ids, rows = evaluate_batches(model, batches, audio_rate=params.audio_rate, rms_maps=True)
+    write_eval_detailed(eval_fn, ids, rows)
+    return ids, rows
+
+
 def write_eval_detailed(path, sample_ids, rows):
     """eval.py:212-215: header `SampleID | names`, then `<id> | v1 ... v28` (space-pipe-space separator)."""
     rows = np.asarray(rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows)

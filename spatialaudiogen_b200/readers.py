@@ -133,6 +133,32 @@ class FlowReader(object):
         return chunk
 
 
+def sample_folders(directory, subset_fn=None):
+    """feeder.py:12-47 (FilenameProvider, one epoch, no shuffling): the per-video folders of `directory` in os.listdir order,
+    restricted to the ids listed one per line in `subset_fn` (meta/subsets/*.lst)."""
+    sample_ids = os.listdir(directory)
+    if len(sample_ids) == 0:
+        raise ValueError('Dataset directory is empty.')
+    if subset_fn is not None:
+        if not os.path.exists(subset_fn):
+            raise IOError('subset file %s does not exist' % subset_fn)
+        subset = set(open(subset_fn).read().splitlines())
+        sample_ids = [y for y in sample_ids if y in subset]
+    return [os.path.join(directory, y) for y in sample_ids]
+
+
+def load_channel_masks(audio_layouts_fn):
+    """feeder.py:312-314: meta/audio_layouts.txt (`<video id> <WXYZ|WXY>` per line) -> {video id: (4,) mask over [W, Y, Z, X]};
+    a WXY recording has no height channel (mask [1, 1, 0, 1])."""
+    masks = {'WXYZ': np.array([1., 1., 1., 1.]), 'WXY': np.array([1., 1., 0., 1.])}
+    out = {}
+    for line in open(audio_layouts_fn).read().splitlines():
+        if line.strip():
+            vid, layout = line.split()[:2]
+            out[vid] = masks[layout]
+    return out
+
+
 class SampleReader(object):
     """feeder.py:164-278: iterates the chunk times of `<folder>/audio_pow.lst`."""
     def __init__(self, folder, ambi_order=1, audio_rate=48000, video_rate=10, context=1.0, duration=0.1, return_video=True,

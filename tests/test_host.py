@@ -3,6 +3,7 @@ reference's fall-backs (myutils.py:40-85), constants (definitions.py), checkpoin
 import os
 
 import numpy as np
+import pytest
 
 from spatialaudiogen_b200 import definitions as Df
 from spatialaudiogen_b200 import weights as Wt
@@ -121,3 +122,68 @@ def test_sample_reader_follows_the_reference_schedule_and_padding(tmp_path):
     assert R.SampleReader(folder, shuffle=False, start_time=1.0, sample_duration=2.0, return_video=False).chunks_t == [1.5, 2.5]
     rot = R.AudioReader(os.path.join(folder, 'ambix'), 48000).get(0.0, 100, rotation=np.pi / 2)   # yaw by 90 deg: Y' = X, X' = -Y
     assert np.allclose(rot[:, 1], full[:100, 3]) and np.allclose(rot[:, 3], -full[:100, 1]) and np.allclose(rot[:, [0, 2]], full[:100, [0, 2]])
+
+
+def test_sample_folders_and_channel_masks(tmp_path):
+    """feeder.py:12-47 (FilenameProvider) and feeder.py:312-314 (audio layout masks)."""
+    from spatialaudiogen_b200 import readers as R
+    db = tmp_path / 'db'
+    for vid in ('aaa', 'bbb', 'ccc'):
+        os.makedirs(str(db / vid))
+    subset = tmp_path / 'subset.lst'
+    subset.write_text('ccc\naaa\nzzz\n')
+    got = R.sample_folders(str(db), str(subset))
+    assert got == [os.path.join(str(db), y) for y in os.listdir(str(db)) if y in ('aaa', 'ccc')] and len(got) == 2
+    assert len(R.sample_folders(str(db))) == 3
+    os.makedirs(str(tmp_path / 'empty'))
+    with pytest.raises(ValueError):
+        R.sample_folders(str(tmp_path / 'empty'))
+    with pytest.raises(IOError):
+        R.sample_folders(str(db), str(tmp_path / 'missing.lst'))
+    lay = tmp_path / 'audio_layouts.txt'
+    lay.write_text('aaa WXYZ\nbbb WXY\n\nccc WXYZ\n')
+    m = R.load_channel_masks(str(lay))
+    assert sorted(m) == ['aaa', 'bbb', 'ccc'] and list(m['bbb']) == [1., 1., 0., 1.] and list(m['aaa']) == [1., 1., 1., 1.]
+
+
+def test_evaluate_model_dir_wiring(tmp_path, monkeypatch):
+    """eval.py:29-215 `main`, host side only (the model and the GPU loops are stood in): folder list from db_dir + subset,
+    channel masks, refusal to overwrite eval-detailed.txt, file layout."""
+    import torch
+    from spatialaudiogen_b200 import evaluate as E, deploy as D
+    md, db = tmp_path / 'model', tmp_path / 'db'
+    os.makedirs(str(md))
+    for vid in ('v1', 'v2'):
+        os.makedirs(str(db / vid))
+    (md / 'train-params.txt').write_text("encoders: ['audio']\nseparation: unet_mask\nambi_order: 1\naudio_rate: 48000\nvideo_rate: 10\n"
+                                         "context: 1.0\nsample_dur: 0.1\nlr: 0.0001\nn_iters: 10\nbatch_size: 32\nlr_decay: 0.5\nlr_iters: 30000\n"
+                                         "db_dir: %s\n" % str(db))
+    (tmp_path / 'subset.lst').write_text('v2\n')
+    (tmp_path / 'layouts.txt').write_text('v2 WXY\n')
+    seen = {}
+
+    class FakeW2XYZ(object):
+        def __init__(self, model_dir, params=None, precision=None, device=None):
+            self.model = type('M', (), {'device': 'cpu'})()
+            seen['model_dir'] = model_dir
+
+    def fake_folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=False):
+        seen.update(folders=folders, masks=channel_masks, batch_size=batch_size, drop=drop_remainder)
+        return iter([])
+
+    def fake_evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
+        seen.update(audio_rate=audio_rate, rms_maps=rms_maps)
+        return ['v2 0.5', 'v2 1.5'], torch.arange(56, dtype=torch.float32).reshape(2, 28)
+    monkeypatch.setattr(D, 'W2XYZ', FakeW2XYZ)
+    monkeypatch.setattr(E, 'folder_batches', fake_folder_batches)
+    monkeypatch.setattr(E, 'evaluate_batches', fake_evaluate_batches)
+    ids, rows = E.evaluate_model_dir(str(md), subset_fn=str(tmp_path / 'subset.lst'), audio_layouts_fn=str(tmp_path / 'layouts.txt'))
+    assert seen['folders'] == [os.path.join(str(db), 'v2')] and list(seen['masks']['v2']) == [1., 1., 0., 1.]
+    assert seen['rms_maps'] is True and seen['audio_rate'] == 48000 and seen['batch_size'] == 16
+    lines = open(str(md / 'eval-detailed.txt')).read().splitlines()
+    assert lines[0].startswith('SampleID | amplitude/predicted amplitude/gt mse/avg') and len(lines) == 3
+    assert lines[1].startswith('v2 0.5 | 0.0 1.0 2.0') and len(lines[1].split(' | ')[1].split()) == 28
+    with pytest.raises(AssertionError):
+        E.evaluate_model_dir(str(md), subset_fn=str(tmp_path / 'subset.lst'))
+    E.evaluate_model_dir(str(md), subset_fn=str(tmp_path / 'subset.lst'), overwrite=True, audio_layouts_fn=None)
+    assert seen['masks'] is None
