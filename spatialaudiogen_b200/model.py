@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .stages import StageOps
 from .definitions import *          # noqa: F401,F403  (AUDIO, VIDEO, FLOW, ENCODERS, NO_SEPARATION, FREQ_MASK, ...)
 from .definitions import (AUDIO, VIDEO, FLOW, ENCODERS, NO_SEPARATION, FREQ_MASK, FFT_WINDOW, FFT_OVERLAP_R,
                           NUM_SEP_TRACKS_DEF, CTX_FEATS_FCUNITS_DEF, LOC_FCUNITS_DEF, SEP_FREQ_MASK_FCUNITS_DEF,
@@ -35,8 +36,9 @@ class SptAudioGenParams:
         self.sep_fft_window = sep_fft_window
 
 
-class SptAudioGen(object):
-    """reference model.py:24-434.  Extra keyword arguments (not in the reference): `precision`
+class SptAudioGen(StageOps):
+    """reference model.py:24-434.  (The per-stage methods audio_encoder_ops / visual_encoding_ops / bottleneck_ops /
+    localization_ops / separation_ops live in stages.StageOps.)  Extra keyword arguments (not in the reference): `precision`
     ('fp32' | 'tf32' | 'bf16' | 'bf16x3': arithmetic of the dense contractions), `device`, `frame_size`."""
 
     def __init__(self, ambi_order,

@@ -187,3 +187,49 @@ def test_evaluate_model_dir_wiring(tmp_path, monkeypatch):
         E.evaluate_model_dir(str(md), subset_fn=str(tmp_path / 'subset.lst'))
     E.evaluate_model_dir(str(md), subset_fn=str(tmp_path / 'subset.lst'), overwrite=True, audio_layouts_fn=None)
     assert seen['masks'] is None
+
+
+def test_stage_methods_glue_matches_oracle(monkeypatch):
+    """stages.StageOps (the reference's audio_encoder_ops / visual_encoding_ops / bottleneck_ops / localization_ops /
+    separation_ops): the crops, reshapes, tiles, concat order and the mask arithmetic between the dense primitives, with
+    the four primitives (one C-ABI call each on the GPU) stood in by the oracle's CPU ops, against oracle.SptAudioGen."""
+    import types
+    import torch
+    from oracle import sag_oracle as O
+    from spatialaudiogen_b200 import stages as S
+    enc = ['audio', 'video']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=5, stress=True)
+    om = O.SptAudioGen(W, 1, encoders=enc, separation='unet_mask')
+
+    class Fake(S.StageOps):
+        pass
+    m = Fake()
+    m.ambi_order, m.separation, m.snd_contx, m.snd_dur, m.params = 1, 'unet_mask', om.snd_contx, om.snd_dur, om.params
+    ss, tt = om.encoder_crop()
+    mss, mtt, mskip = om.mask_crop()
+    m.dims = types.SimpleNamespace(enc_ss=ss, enc_tt=tt, mask_ss=mss, mask_tt=mtt, mask_skip=mskip, final_crop=om.final_crop())
+    m._conv = lambda scope, x, stride, same, relu: O.conv_2d(om.W, scope, x, stride, 'SAME' if same else 'VALID', relu)
+    m._deconv = lambda scope, x, stride, relu: O.deconv_2d(om.W, scope, x, stride, relu)
+    m._fc = lambda scope, x, relu=True: O.fully_connected(om.W, scope, x, relu)
+    m._resnet = lambda scope, x: O.resnet18(om.W, scope, x)[0]
+    monkeypatch.setattr(S.myutils, 'istft', O.istft)
+    rng = np.random.RandomState(1)
+    audio = torch.as_tensor((rng.randn(2, 52799, 1) * 0.1).astype(np.float32))
+    video = torch.as_tensor(rng.rand(2, 1, 224, 448, 3).astype(np.float32) - 0.5)
+    ref = om.inference_ops(audio, video)
+    mono = audio.permute(0, 2, 1)
+    s = O.stft(mono, om.wind_size, 4)
+    a_enc = m.audio_encoder_ops(s)
+    assert len(a_enc) == 6 and all(torch.equal(a, b) for a, b in zip(a_enc, om.ends['audio_encoder']))
+    v = m.visual_encoding_ops(video, is_training=False, finetune=True, scope='video_encoder')
+    feats = m.bottleneck_ops({'audio': a_enc, 'video': v}, True)
+    assert torch.equal(feats, om.ends['bottleneck'])
+    w, b = m.localization_ops(feats)
+    assert tuple(w.shape) == (2, 4800, 3, 1, 32) and tuple(b.shape) == (2, 4800, 3, 1)
+    assert torch.equal(w, om.loc_channels[0]) and torch.equal(b, om.loc_channels[1])
+    x_sep = m.separation_ops(mono, s, a_enc, feats)
+    assert tuple(x_sep.shape) == (2, 1, 32, 4800) and torch.equal(x_sep, om.sep_channels)
+    y = (w * x_sep.permute(0, 3, 1, 2).unsqueeze(2)).sum(4).sum(3) + b[:, :, :, 0]          # model.py:424-432
+    assert torch.equal(y, ref)
+    m.separation = 'none'
+    assert torch.equal(m.separation_ops(mono, s, None, None), mono[:, :, 24000:28800].unsqueeze(1))

@@ -5,6 +5,8 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1
 echo "pytest exit $?"; tail -5 gpurun_out/r2_pytest.log | cut -c1-300
+SAG_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k stage_methods > gpurun_out/r2_stage.log 2>&1
+echo "stage methods exit $?"; tail -15 gpurun_out/r2_stage.log | cut -c1-300
 timeout 300 python bench.py --steps 30 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 echo "bench exit $?"; cut -c1-400 gpurun_out/r2_bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_l.log 2>&1
