@@ -114,6 +114,10 @@ int sag_tensor_name(const sag_handle* h, int i, char* buf, int buflen);
 /* options: "skip_unused" (default 1: STFT frames / mask rows that cannot reach the cropped output are not
  * computed; the result is bit-identical), "precision" (SAG_PREC_*), "profile" (0/1, see sag_get_profile). */
 int sag_set_option(sag_handle* h, const char* key, int value);
+/* Tile plan of the tcgen05 contraction kernel for a [M x K] x [K x N] product (conv: M = B*OH*OW, K = kh*kw*Cin, N = Cout):
+ * tile width (32 | 64 | 128 | 256 GEMM columns per CTA tile) and K split.  Pure host arithmetic; lets tests / profiles name
+ * the kernel instantiation a layer runs at a given batch size. */
+int sag_plan_contraction(int k, int n, int64_t m, int* tile_width, int* k_split);
 /* how many kernels the last sag_forward launched (bench.py gpu_launches) */
 int sag_last_launch_count(const sag_handle* h);
 /* With option "profile" = 1 every launch group of sag_forward is bracketed by CUDA events on the caller's stream.

@@ -59,6 +59,7 @@ PROTOTYPES = {
     'sag_num_tensors': (_I, [_P]),
     'sag_tensor_name': (_I, [_P, _I, C.c_char_p, _I]),
     'sag_last_launch_count': (_I, [_P]),
+    'sag_plan_contraction': (_I, [_I, _I, _L, C.POINTER(_I), C.POINTER(_I)]),
     'sag_get_profile': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     'sag_stft': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P]),
     'sag_istft': (_I, [_P, _I, _I, _I, _I, _P, _P]),

@@ -242,6 +242,13 @@ int sag_get_tensor_format(const sag_handle* h, const char* name, int* format, in
 
 int sag_last_launch_count(const sag_handle* h) { return h ? h->last_launches : SAG_EINVAL; }
 
+int sag_plan_contraction(int k, int n, int64_t m, int* tile_width, int* k_split) {
+  SAG_REQUIRE(k > 0 && n > 0 && m > 0, SAG_EINVAL, "sag_plan_contraction: bad shape %d x %d over %lld rows", k, n, (long long)m);
+  if (tile_width) *tile_width = umma_tile_width(k, n, m);
+  if (k_split) *k_split = umma_split_k(k, n, m, nullptr);
+  return SAG_OK;
+}
+
 int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, double* bytes, int* launches) {
   SAG_REQUIRE(h != nullptr, SAG_EINVAL, "sag_get_profile: NULL handle");
   SAG_REQUIRE(category >= 0 && category < PROF_NCAT, SAG_EINVAL, "sag_get_profile: category %d outside [0,%d)", category, (int)PROF_NCAT);

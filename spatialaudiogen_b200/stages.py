@@ -9,9 +9,8 @@ contractions run in the handle's precision on the same kernels as the forward; t
 between them -- pure data movement in the reference graph too -- are torch views and copies on the caller's stream, and so
 is the sigmoid-mask product of separation_ops (the forward fuses it into the inverse-STFT kernel).
 
-Status: added at the end of round 1 after the GPU budget was spent -- the glue is checked on the CPU against the oracle
-with the four primitives stood in (tests/test_host.py), the end-to-end GPU test is tests/test_gpu_parity.py::
-test_stage_methods_match_oracle (enabled with SAG_TEST_UNVERIFIED=1 until it has run once on a B200)."""
+Tests: the glue on the CPU against the oracle with the four primitives stood in (tests/test_host.py); end to end on the GPU
+in tests/test_gpu_parity.py::test_stage_methods_match_oracle."""
 import ctypes as C
 
 import torch
@@ -76,6 +75,10 @@ class StageOps(object):
     def _resnet(self, scope, x):
         """ResNet18.inference_ops(truncate_at='conv5_2'), batch-statistics BN (resnet.py:123-190).  x (N, H, W, 3)."""
         x = L.f32(x, self.device)
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self._frame[0], self._frame[1], 3):
+            # sag_resnet18 takes no spatial arguments: it reads B * frame_h * frame_w * 3 floats of the handle's frame size
+            raise ValueError('visual tower input must be (N, %d, %d, 3) -- the frame_size this model was built with -- got %s'
+                             % (self._frame[0], self._frame[1], tuple(x.shape)))
         n, h, wd, _ = x.shape
         y = torch.empty((n, -(-h // 32), -(-wd // 32), 512), dtype=torch.float32, device=self.device)
         ws = self._workspace(n)

@@ -606,8 +606,6 @@ def test_inference_stream_matches_per_batch_calls():
         assert _rel(y, ref) < 2e-4      # not bit-equal: batch-norm sums are accumulated with atomics (order varies, ~2e-5)
 
 
-@pytest.mark.skipif(os.environ.get('SAG_TEST_UNVERIFIED') != '1',
-                    reason='added after the round-1 GPU budget was spent: run once on a B200 with SAG_TEST_UNVERIFIED=1, then drop this gate')
 def test_stage_methods_match_oracle():
     """The reference's per-stage methods (stages.StageOps) on the GPU primitives against the oracle's stages."""
     from spatialaudiogen_b200 import myutils
