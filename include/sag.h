@@ -14,7 +14,9 @@
  *    layouts are the reference's (NHWC activations, HWIO conv weights, [kh,kw,Cout,Cin] transposed-conv
  *    weights, [in,out] FC weights; complex64 as interleaved float pairs).
  *  - the caller owns inputs, outputs and the workspace; the handle owns packed weights and descriptors.
- *    No allocation happens inside sag_forward.
+ *    No allocation happens inside sag_forward: sag_workspace_bytes(h, batch), called after sag_finalize_weights, plans
+ *    the batch (it packs the tensor-core weight images whose tile width depends on the row count -- device allocation and a
+ *    synchronising pack kernel); sag_forward fails with SAG_ESTATE if that has not happened for its batch size / precision.
  *  - `stream` is a cudaStream_t passed as void*; all launches go to it, nothing synchronises.
  *  - a handle is not thread safe: one handle per (device, stream).
  */
@@ -37,7 +39,7 @@ extern "C" {
 
 /* arithmetic type of the dense contractions (convs / transposed convs / FCs) */
 #define SAG_PREC_FP32 0   /* FFMA, fp32 in / fp32 accumulate (parity path) */
-#define SAG_PREC_TF32 1   /* tcgen05 kind::tf32, fp32 storage, fp32 accumulate in TMEM */
+                          /* (1 is unassigned: a tf32 mode was never built -- bf16x3 is both faster and more accurate) */
 #define SAG_PREC_BF16 2   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
 #define SAG_PREC_BF16X3 3 /* tcgen05 kind::f16, operands split hi+lo (3 MMAs per K step): fp32-grade result */
 
@@ -94,11 +96,23 @@ int sag_weight_name(const sag_handle* h, int i, char* buf, int buflen, int64_t* 
 int sag_finalize_weights(sag_handle* h, void* stream);   /* repack into kernel layouts; idempotent */
 
 /* ---- the forward: sess.run(ambi_pred_t, feed_dict) (deploy.py:141, eval.py:145) ------------------ */
+/* Bytes of workspace a forward of `batch` windows needs (0 on error) -- and, once the weights are finalized, the planning
+ * step of that batch size (see "Conventions"): call it again after changing the precision or reloading weights. */
 size_t sag_workspace_bytes(const sag_handle* h, int batch);
 /* audio (B,snd_size,1); video / flow (B,1,H,W,3) or NULL when the encoder is absent;
  * ambix_out (B,snd_dur,3) = channels (Y,Z,X) (model.py:424-432). */
 int sag_forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* ambix_out,
                 void* workspace, size_t workspace_bytes, int batch, void* stream);
+/* The same forward fed with the frames as the reference's readers decode them from disk -- uint8 (B,1,H,W,3) -- instead of the
+ * float32 tensors its feeder prepares on the host: the preparation runs inside the frame-ingest kernel (4x fewer bytes over
+ * PCIe / HBM per frame).  SAG_FRAMES_U8 video: myutils.img_prep_fcn, x/255 - 0.5 (myutils.py:88-89), bit-identical to
+ * feeding the prepared float32 frame.  SAG_FRAMES_U8 flow: FlowReader.get_by_index (feeder.py:147-161): channel 0 = angle,
+ * channel 2 = magnitude quantised to the frame's (min, max) = flow_limits[b] (device doubles, (B,2), the rows of
+ * flow_limits.npy) -> (mag cos, mag sin, mag).  SAG_FRAMES_F32 = what sag_forward takes. */
+#define SAG_FRAMES_F32 0
+#define SAG_FRAMES_U8 1
+int sag_forward_frames(sag_handle* h, const float* audio, const void* video, int video_format, const void* flow, int flow_format,
+                       const double* flow_limits, float* ambix_out, void* workspace, size_t workspace_bytes, int batch, void* stream);
 /* Intermediate tensors of the last sag_forward (model.py `self.ends`, `sep_channels`, `loc_channels`).
  * The pointer aliases the workspace and is valid until the next forward.  shape has up to 5 entries. */
 int sag_get_tensor(const sag_handle* h, const char* name, const float** dev_ptr, int64_t* shape5, int* rank,
@@ -133,6 +147,13 @@ int sag_last_launch_count(const sag_handle* h);
 #define SAG_PROF_MIX 6
 #define SAG_PROF_NCAT 7
 int sag_get_profile(sag_handle* h, int category, double* ms, double* flops, double* bytes, int* launches);
+/* The individual records of the last profiled forward, in launch order: layer name (reference scope), category, CUDA-event
+ * time in microseconds, useful flops (each product of the reference graph that can reach the output, once), issued flops
+ * (what the kernel multiplies: zero taps / border cells of the sub-pixel transposed convs, conv1's K padded 147 -> 256),
+ * algorithmic bytes, tile width and K split of the contraction kernel (0 for other kernels). */
+int sag_num_profile_records(const sag_handle* h);
+int sag_get_profile_record(sag_handle* h, int i, char* name, int name_len, int* category, double* us, double* flops,
+                           double* flops_issued, double* bytes, int* tile_width, int* k_split);
 
 /* ---- stage entry points (tests / ncu); each replaces the named reference op -------------------- */
 /* myutils.stft (myutils.py:119-147): x (rows,n_samples) -> out complex (rows, n_frames_out, wind) for frames

@@ -9,8 +9,9 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libsag.so')
 
-SAG_PREC_FP32, SAG_PREC_TF32, SAG_PREC_BF16, SAG_PREC_BF16X3 = 0, 1, 2, 3
-PRECISIONS = {'fp32': SAG_PREC_FP32, 'tf32': SAG_PREC_TF32, 'bf16': SAG_PREC_BF16, 'bf16x3': SAG_PREC_BF16X3}
+SAG_PREC_FP32, SAG_PREC_BF16, SAG_PREC_BF16X3 = 0, 2, 3
+PRECISIONS = {'fp32': SAG_PREC_FP32, 'bf16': SAG_PREC_BF16, 'bf16x3': SAG_PREC_BF16X3}
+SAG_FRAMES_F32, SAG_FRAMES_U8 = 0, 1
 SAG_SEP_NONE, SAG_SEP_UNET_MASK = 0, 1
 
 
@@ -54,6 +55,7 @@ PROTOTYPES = {
     'sag_finalize_weights': (_I, [_P, _P]),
     'sag_workspace_bytes': (_S, [_P, _I]),
     'sag_forward': (_I, [_P, _P, _P, _P, _P, _P, _S, _I, _P]),
+    'sag_forward_frames': (_I, [_P, _P, _P, _I, _P, _I, _P, _P, _P, _S, _I, _P]),
     'sag_get_tensor': (_I, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_L), C.POINTER(_I), C.POINTER(_L)]),
     'sag_get_tensor_format': (_I, [_P, C.c_char_p, C.POINTER(_I), C.POINTER(_L)]),
     'sag_num_tensors': (_I, [_P]),
@@ -61,6 +63,9 @@ PROTOTYPES = {
     'sag_last_launch_count': (_I, [_P]),
     'sag_plan_contraction': (_I, [_I, _I, _L, C.POINTER(_I), C.POINTER(_I)]),
     'sag_get_profile': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
+    'sag_num_profile_records': (_I, [_P]),
+    'sag_get_profile_record': (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(_I)]),
     'sag_stft': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P, _P]),
     'sag_istft': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     'sag_conv2d': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
@@ -112,7 +117,7 @@ def check(code):
 
 
 def ptr(t):
-    """Device pointer of a contiguous float32 CUDA tensor (None -> NULL)."""
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
     if t is None:
         return None
     if not (isinstance(t, torch.Tensor) and t.is_cuda):

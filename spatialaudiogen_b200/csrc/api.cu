@@ -18,6 +18,8 @@ bool is_deconv_weight(const std::string& n) {
   return n.rfind("separation/deconv", 0) == 0 && n.size() > 8 && n.compare(n.size() - 8, 8, "/weights") == 0;
 }
 
+bool valid_precision(int p) { return p == SAG_PREC_FP32 || p == SAG_PREC_BF16 || p == SAG_PREC_BF16X3; }
+
 void free_tensor(DevTensor& t) {
   if (t.p) cudaFree(t.p);
   t.p = nullptr;
@@ -59,7 +61,7 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
   SAG_REQUIRE(cfg->n_loc_fc >= 0 && cfg->n_loc_fc <= 4, SAG_EINVAL, "sag_create: n_loc_fc %d outside [0,4]", cfg->n_loc_fc);
   SAG_REQUIRE(cfg->separation == SAG_SEP_NONE || cfg->separation == SAG_SEP_UNET_MASK, SAG_EINVAL,
               "Unknown separation mode.");                                            // model.py:351
-  SAG_REQUIRE(cfg->precision >= SAG_PREC_FP32 && cfg->precision <= SAG_PREC_BF16X3, SAG_EINVAL, "sag_create: unknown precision %d", cfg->precision);
+  SAG_REQUIRE(valid_precision(cfg->precision), SAG_EINVAL, "sag_create: unknown precision %d", cfg->precision);
   SAG_REQUIRE(cfg->sep_num_tracks >= 1 && cfg->sep_num_tracks <= 256, SAG_EINVAL, "sag_create: sep_num_tracks %d", cfg->sep_num_tracks);
   SAG_REQUIRE(cfg->frame_h > 0 && cfg->frame_w > 0, SAG_EINVAL, "sag_create: bad frame size");
   int ndev = 0;
@@ -102,7 +104,7 @@ int sag_set_option(sag_handle* h, const char* key, int value) {
   if (k == "tma_gather") { h->tma_gather = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "profile") { h->prof.on = value != 0; if (!value) h->prof.clear(); return SAG_OK; }
   if (k == "precision") {
-    SAG_REQUIRE(value >= SAG_PREC_FP32 && value <= SAG_PREC_BF16X3, SAG_EINVAL, "unknown precision %d", value);
+    SAG_REQUIRE(valid_precision(value), SAG_EINVAL, "unknown precision %d", value);
     h->cfg.precision = value;
     return SAG_OK;
   }
@@ -181,23 +183,28 @@ int sag_finalize_weights(sag_handle* h, void* stream) {
 }
 
 // ---- forward --------------------------------------------------------------------------------------------------
-size_t sag_workspace_bytes(const sag_handle* h, int batch) {
-  if (h == nullptr || batch <= 0) return 0;
+size_t sag_workspace_bytes(const sag_handle* h_in, int batch) {
+  if (h_in == nullptr || batch <= 0) return 0;
+  sag_handle* h = const_cast<sag_handle*>(h_in);
   Arena ar;
   ar.dry = true;
-  int r = forward(const_cast<sag_handle*>(h), nullptr, nullptr, nullptr, nullptr, ar, batch, 0);
+  // once the weights are in place this is also where the batch is PLANNED: the tensor-core operand images whose tile width
+  // depends on the row count are packed here (device allocation + a synchronising pack kernel), never inside sag_forward
+  ar.prepare = h->finalized != 0 && h->cfg.precision != SAG_PREC_FP32;
+  if (ar.prepare && cudaSetDevice(h->device) != cudaSuccess) { set_error("sag_workspace_bytes: cudaSetDevice failed"); return 0; }
+  int r = forward(h, nullptr, FrameSrc(), FrameSrc(), nullptr, ar, batch, 0);
   if (r != SAG_OK) return 0;
   return ar.peak + ar.scratch_need + 768;
 }
 
-int sag_forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* ambix_out,
-                void* workspace, size_t workspace_bytes, int batch, void* stream) {
+static int forward_checked(sag_handle* h, const float* audio, const FrameSrc& video, const FrameSrc& flow, float* ambix_out, void* workspace,
+                           size_t workspace_bytes, int batch, void* stream) {
   SAG_REQUIRE(h != nullptr && audio != nullptr && ambix_out != nullptr && workspace != nullptr, SAG_EINVAL, "sag_forward: NULL argument");
   SAG_REQUIRE(h->finalized, SAG_ESTATE, "sag_forward: call sag_finalize_weights first");
   SAG_REQUIRE(batch > 0, SAG_EINVAL, "sag_forward: batch must be positive");
   Arena dry;
   dry.dry = true;
-  SAG_TRY(forward(h, nullptr, nullptr, nullptr, nullptr, dry, batch, 0));
+  SAG_TRY(forward(h, nullptr, FrameSrc(), FrameSrc(), nullptr, dry, batch, 0));
   const size_t need = dry.peak + dry.scratch_need + 768;
   SAG_REQUIRE(need <= workspace_bytes, SAG_ENOMEM, "sag_forward: workspace of %zu bytes is too small, need %zu", workspace_bytes, need);
   Arena ar;
@@ -208,6 +215,22 @@ int sag_forward(sag_handle* h, const float* audio, const float* video, const flo
   ar.base = reinterpret_cast<char*>(base);
   ar.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   return forward(h, audio, video, flow, ambix_out, ar, batch, as_stream(stream));
+}
+
+int sag_forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* ambix_out,
+                void* workspace, size_t workspace_bytes, int batch, void* stream) {
+  return forward_checked(h, audio, FrameSrc(video), FrameSrc(flow), ambix_out, workspace, workspace_bytes, batch, stream);
+}
+
+int sag_forward_frames(sag_handle* h, const float* audio, const void* video, int video_format, const void* flow, int flow_format,
+                       const double* flow_limits, float* ambix_out, void* workspace, size_t workspace_bytes, int batch, void* stream) {
+  SAG_REQUIRE((video_format == SAG_FRAMES_F32 || video_format == SAG_FRAMES_U8) && (flow_format == SAG_FRAMES_F32 || flow_format == SAG_FRAMES_U8),
+              SAG_EINVAL, "sag_forward_frames: unknown frame format");
+  SAG_REQUIRE(flow == nullptr || flow_format == SAG_FRAMES_F32 || flow_limits != nullptr, SAG_EINVAL,
+              "sag_forward_frames: quantised flow frames need their (min, max) limits (feeder.py:147-152)");
+  const FrameSrc v(video, video_format == SAG_FRAMES_U8 ? FRAMES_U8_VIDEO : FRAMES_F32, nullptr);
+  const FrameSrc f(flow, flow_format == SAG_FRAMES_U8 ? FRAMES_U8_FLOW : FRAMES_F32, flow_limits);
+  return forward_checked(h, audio, v, f, ambix_out, workspace, workspace_bytes, batch, stream);
 }
 
 int sag_num_tensors(const sag_handle* h) { return h ? (int)h->end_order.size() : SAG_EINVAL; }
@@ -246,6 +269,27 @@ int sag_plan_contraction(int k, int n, int64_t m, int* tile_width, int* k_split)
   SAG_REQUIRE(k > 0 && n > 0 && m > 0, SAG_EINVAL, "sag_plan_contraction: bad shape %d x %d over %lld rows", k, n, (long long)m);
   if (tile_width) *tile_width = umma_tile_width(k, n, m);
   if (k_split) *k_split = umma_split_k(k, n, m, nullptr);
+  return SAG_OK;
+}
+
+int sag_num_profile_records(const sag_handle* h) { return h ? (int)h->prof.recs.size() : SAG_EINVAL; }
+
+int sag_get_profile_record(sag_handle* h, int i, char* name, int name_len, int* category, double* us, double* flops, double* flops_issued,
+                           double* bytes, int* tile_width, int* k_split) {
+  SAG_REQUIRE(h != nullptr, SAG_EINVAL, "sag_get_profile_record: NULL handle");
+  SAG_REQUIRE(i >= 0 && i < (int)h->prof.recs.size(), SAG_EINVAL, "sag_get_profile_record: record %d of %d", i, (int)h->prof.recs.size());
+  ProfRec& r = h->prof.recs[i];
+  SAG_CHECK_CUDA(cudaEventSynchronize(r.e1));
+  float dt = 0.f;
+  SAG_CHECK_CUDA(cudaEventElapsedTime(&dt, r.e0, r.e1));
+  if (name != nullptr && name_len > 0) snprintf(name, name_len, "%s", r.name);
+  if (category) *category = r.cat;
+  if (us) *us = dt * 1e3;
+  if (flops) *flops = r.flops;
+  if (flops_issued) *flops_issued = r.issued;
+  if (bytes) *bytes = r.bytes;
+  if (tile_width) *tile_width = r.tile;
+  if (k_split) *k_split = r.split;
   return SAG_OK;
 }
 
@@ -385,8 +429,9 @@ int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, fl
   SAG_REQUIRE(batch > 0, SAG_EINVAL, "sag_resnet18: batch must be positive");
   Arena dry;
   dry.dry = true;
+  dry.prepare = h->cfg.precision != SAG_PREC_FP32;      // stage entry point: builds the operand images it needs itself
   Act yact;
-  SAG_TRY(resnet18_tower(h, scope, nullptr, batch, h->cfg.frame_h, h->cfg.frame_w, &yact, dry, 0));
+  SAG_TRY(resnet18_tower(h, scope, FrameSrc(), batch, h->cfg.frame_h, h->cfg.frame_w, &yact, dry, 0));
   const size_t need = dry.peak + dry.scratch_need + 768;
   SAG_REQUIRE(need <= workspace_bytes, SAG_ENOMEM, "sag_resnet18: workspace of %zu bytes is too small, need %zu", workspace_bytes, need);
   Arena ar;
@@ -398,7 +443,7 @@ int sag_resnet18(sag_handle* h, const char* scope, const float* x, int batch, fl
   ar.cap = workspace_bytes - (base - reinterpret_cast<uintptr_t>(workspace));
   h->ends.clear();
   h->end_order.clear();
-  SAG_TRY(resnet18_tower(h, scope, x, batch, h->cfg.frame_h, h->cfg.frame_w, &yact, ar, as_stream(stream)));
+  SAG_TRY(resnet18_tower(h, scope, FrameSrc(x), batch, h->cfg.frame_h, h->cfg.frame_w, &yact, ar, as_stream(stream)));
   const int fh = (h->cfg.frame_h + 31) / 32, fw = (h->cfg.frame_w + 31) / 32;
   return launch_act_to_f32(yact.v, y, (int64_t)batch * fh * fw * 512, as_stream(stream));
 }

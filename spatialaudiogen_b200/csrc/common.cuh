@@ -48,7 +48,9 @@ extern thread_local int g_launch_count;   // kernels launched by this thread sin
 
 // ---- optional per-launch CUDA-event profiling (sag_set_option "profile"): bench.py's roofline numbers ----
 enum ProfCat { PROF_CONV = 0, PROF_DECONV, PROF_FC, PROF_STFT, PROF_ISTFT, PROF_POINTWISE, PROF_MIX, PROF_NCAT };
-struct ProfRec { int cat; double flops; double bytes; cudaEvent_t e0, e1; };
+// flops: useful work (every product of the reference graph that can reach the output, once); issued: what the kernel
+// multiplies (sub-pixel transposed convs carry zero taps / border cells, conv1's space-to-depth form pads K 147 -> 256)
+struct ProfRec { int cat; double flops; double bytes; cudaEvent_t e0, e1; double issued; char name[48]; int tile, split; };
 struct Profiler {
   bool on = false;
   std::vector<ProfRec> recs;
@@ -58,7 +60,8 @@ extern thread_local Profiler* g_prof;   // set by forward() while profiling is e
 struct ProfScope {                      // records an event pair around the launches issued in its lifetime
   cudaStream_t st;
   int idx = -1;
-  ProfScope(int cat, double flops, double bytes, cudaStream_t s);
+  ProfScope(int cat, double flops, double bytes, cudaStream_t s, const char* name = nullptr, double issued = -1.0, int tile = 0,
+            int split = 0);
   ~ProfScope();
 };
 
@@ -115,8 +118,10 @@ struct GatherGeom {
 struct Epilogue {
   const float* bias;      // [Cout] or null
   int relu;
-  double* stat_sum;       // [Cout] accumulators for batch-norm statistics or null
-  double* stat_sqs;
+  double* stat_sum;       // [Cout] batch-norm statistics (sum, sum of squares over the rows) or null.  FFMA path: accumulated
+  double* stat_sqs;       // with atomics into zeroed buffers; tcgen05 path: written once, summed in a fixed order
+  void* stat_ws;          // tcgen05 path: umma_stat_ws_bytes() of scratch for that fixed-order reduction; its first 512 bytes
+                          // (arrival counters) must be zero before the first launch that uses it -- launches leave them zero
 };
 
 // TF 'SAME' padding (asymmetric): returns pad_before; out = ceil(in/s)
@@ -175,6 +180,8 @@ extern thread_local int g_umma_pair;  // -1: SAG_UMMA_PAIR env (default off); 0/
 extern thread_local int g_umma_tma;   // -1: SAG_UMMA_TMA env (default on); 0/1: forced for this thread's launches
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
+// bytes of Epilogue::stat_ws a contraction of this shape needs for its batch-norm statistics
+size_t umma_stat_ws_bytes(int K, int N, int64_t M);
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st);
 
@@ -214,10 +221,22 @@ int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int
                      cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,
                cudaStream_t st);
-// (n,h,w,c<=4) fp32 -> 2x2 space-to-depth of the image placed at (pt,pl) inside a zero canvas: (n,h2,w2,16) with channel
+// A batch of input frames (n,h,w,3): prepared fp32, or the uint8 frame as decoded from the jpg (video: x/255 - 0.5,
+// myutils.py:88-89; flow: quantised (angle, -, magnitude) + per-frame (min, max) limits, feeder.py:147-161) prepared on the device
+enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2 };
+struct FrameSrc {
+  const void* p = nullptr;
+  int kind = FRAMES_F32;
+  const double* lims = nullptr;      // FRAMES_U8_FLOW: device (n,2) doubles
+  FrameSrc() {}
+  FrameSrc(const float* f) : p(f) {}
+  FrameSrc(const void* q, int k, const double* l) : p(q), kind(k), lims(l) {}
+};
+// (n,h,w,c<=4) frames -> 2x2 space-to-depth of the image placed at (pt,pl) inside a zero canvas: (n,h2,w2,16) with channel
 // (py*2+px)*c + ch = canvas[2*y2+py][2*x2+px][ch], zero beyond 4*c
-int launch_space_to_depth16(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
+int launch_space_to_depth16(const FrameSrc& src, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
                             cudaStream_t st);
+int launch_frames_to_f32(const FrameSrc& src, int n, int h, int w, float* out, cudaStream_t st);
 int launch_pack_deconv_weights(const float* w_hwoi, float* out, int taps, int cout, int cin, cudaStream_t st);
 
 // fft.cu

@@ -74,6 +74,11 @@ struct UmmaArgs {
   int NT, Z;              // N tiles, K splits
   int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
+  // cross-CTA batch-norm sums in a fixed order (stat_reduce below): per-CTA partials, per-group partials, arrival counters
+  float* st_part;
+  double* st_gpart;
+  unsigned* st_cnt;
+  int st_gs;              // CTAs per group
 };
 // im2col tensor maps of the two activation planes (SRC_TMA); kernel parameter, read by the TMA unit
 struct alignas(64) TmaPair { CUtensorMap hi, lo; };
@@ -268,6 +273,48 @@ __device__ __forceinline__ void store_bf2_4(void* yhi, int64_t plane, int64_t e,
   split4(v, hi, lo);
   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yhi) + e) = hi;
   if (planes == 2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(yhi) + plane) + e) = lo;
+}
+
+// ---- cross-CTA column sums in a fixed order (run-to-run bit-reproducible batch-norm statistics) ---------------------
+// Every CTA of the grid calls this once, with all its threads, after its own sums s_sum / s_sqs[0..n) (shared memory, folded in
+// a fixed order) are complete.  It publishes them as partials[cta][2n]; the LAST CTA to arrive in each group of `gs`
+// consecutive CTAs adds the group's partials in CTA order (double), the last group to finish adds the group sums in group
+// order and writes out_sum / out_sqs.  Which CTA does the adding depends on timing, what is added in which order does not.
+// counters[0] = groups done, counters[1 + g] = CTAs of group g done; all zero on entry, reset to zero on exit.
+__device__ __forceinline__ void stat_reduce(float* __restrict__ partials, double* __restrict__ gpart, unsigned* __restrict__ counters, int gs,
+                                            int cta, int n_ctas, const float* s_sum, const float* s_sqs, int n, double* __restrict__ out_sum,
+                                            double* __restrict__ out_sqs) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n2 = 2 * n;
+  float* mine = partials + (size_t)cta * n2;
+  for (int i = tid; i < n; i += nthr) { mine[i] = s_sum[i]; mine[n + i] = s_sqs[i]; }
+  __threadfence();
+  __syncthreads();
+  const int grp = cta / gs, n_groups = (n_ctas + gs - 1) / gs;
+  const int g0 = grp * gs, g1 = min(g0 + gs, n_ctas);
+  if (tid == 0) s_last = (atomicAdd(counters + 1 + grp, 1u) == (unsigned)(g1 - g0 - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < n2; i += nthr) {
+    double acc = 0.0;
+    for (int c = g0; c < g1; ++c) acc += (double)__ldcg(partials + (size_t)c * n2 + i);
+    gpart[(size_t)grp * n2 + i] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counters, 1u) == (unsigned)(n_groups - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < n2; i += nthr) {
+    double acc = 0.0;
+    for (int g = 0; g < n_groups; ++g) acc += __ldcg(gpart + (size_t)g * n2 + i);
+    if (i < n) out_sum[i] = acc;
+    else out_sqs[i - n] = acc;
+  }
+  for (int i = tid; i <= n_groups; i += nthr) counters[i] = 0u;      // ready for the next launch on this stream
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
@@ -887,12 +934,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (stats) {
-    for (int i = tid; i < a.Ntot; i += UM_THREADS) {
-      atomicAdd(a.stat_sum + i, (double)s_sum[i]);
-      atomicAdd(a.stat_sqs + i, (double)s_sqs[i]);
-    }
-  }
+  if (stats) stat_reduce(a.st_part, a.st_gpart, a.st_cnt, a.st_gs, (int)blockIdx.x, (int)gridDim.x, s_sum, s_sqs, a.Ntot, a.stat_sum, a.stat_sqs);
 }
 
 // ---- weight packing: Wk fp32 [K][N] (row stride ldw) -> per (N tile, K chunk) bf16 hi (+lo) planes in the swizzled
@@ -996,13 +1038,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   const int rows = (int)((M - r0) < SK_ROWS ? (M - r0) : SK_ROWS);
   const int ncg = (a.Ntot + 3) / 4;
   const bool stats = a.stat_sum != nullptr;
-  if (stats) {
-    for (int i = threadIdx.x; i < a.Ntot; i += blockDim.x) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
-    __syncthreads();
-  }
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssqs[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool fixed_cg = (blockDim.x % ncg) == 0;
-  int last_n = -1;
   float* yf = reinterpret_cast<float*>(a.y);
   const int total = rows * ncg;
   const int64_t zs = M * a.n_pad;
@@ -1074,30 +1110,31 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
         else yf[eoff] = v[e];
       }
     }
-    if (stats) {
-      if (fixed_cg) {
+    if (stats) {          // (the host only asks for statistics when 256 % column groups == 0: a thread keeps one column group)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { ssum[e] += v[e]; ssqs[e] = fmaf(v[e], v[e], ssqs[e]); }
-        last_n = n;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < a.Ntot) { atomicAdd(&s_sum[n + e], v[e]); atomicAdd(&s_sqs[n + e], v[e] * v[e]); }
-      }
+      for (int e = 0; e < 4; ++e) { ssum[e] += v[e]; ssqs[e] = fmaf(v[e], v[e], ssqs[e]); }
     }
    }
   }
   if (stats) {
-    if (fixed_cg && last_n >= 0) {
+    // block sums in a fixed order: every thread's register sums go to shared memory, thread c < ncg adds the 256/ncg
+    // contributors of column group c in thread order; then the cross-block reduction (stat_reduce), also in a fixed order
+    __shared__ float s_tp[256][8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s_tp[threadIdx.x][e] = ssum[e]; s_tp[threadIdx.x][4 + e] = ssqs[e]; }
+    __syncthreads();
+    if ((int)threadIdx.x < ncg) {
+      float ts[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int t = threadIdx.x; t < (int)blockDim.x; t += ncg) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ts[e] += s_tp[t][e]; tq[e] += s_tp[t][4 + e]; }
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (last_n + e < a.Ntot) { atomicAdd(&s_sum[last_n + e], ssum[e]); atomicAdd(&s_sqs[last_n + e], ssqs[e]); }
+        if ((int)threadIdx.x * 4 + e < a.Ntot) { s_sum[threadIdx.x * 4 + e] = ts[e]; s_sqs[threadIdx.x * 4 + e] = tq[e]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < a.Ntot; i += blockDim.x) {
-      atomicAdd(a.stat_sum + i, (double)s_sum[i]);
-      atomicAdd(a.stat_sqs + i, (double)s_sqs[i]);
-    }
+    stat_reduce(a.st_part, a.st_gpart, a.st_cnt, a.st_gs, (int)blockIdx.x, (int)gridDim.x, s_sum, s_sqs, a.Ntot, a.stat_sum, a.stat_sqs);
   }
 }
 
@@ -1115,6 +1152,18 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+int reduce_rows_per_block(int64_t M, bool stats) {
+  int64_t rpb = M / (2 * num_sms());              // rows per block: keep >= 2 blocks per SM, at most 16 rows
+  if (rpb > 16) rpb = 16;
+  if (rpb < 1) rpb = 1;
+  if (stats && cdiv64(M, rpb) > 4096) rpb = cdiv64(M, 4096);      // the reduction tree has 64 x 64 slots
+  return (int)rpb;
+}
+int max_conv_ctas() {
+  static const int max_ctas = env_int("SAG_UMMA_MAX_CTAS", 0);
+  return max_ctas > 0 ? max_ctas : num_sms();
 }
 
 template <int BN, int NSPLIT, int SRC, bool PAIR>
@@ -1145,8 +1194,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   const int64_t MT = cdiv64(M, UM_BM);
   constexpr int CL = PAIR ? 2 : 1;                                  // CTA pair: a cluster of two SMs of one TPC per work item
   const int64_t n_work = cdiv64(MT, CL) * nt * Z;                   // per cluster
-  static const int max_ctas = env_int("SAG_UMMA_MAX_CTAS", 0);      // test knob: force many work items per CTA
-  int64_t clusters = (max_ctas > 0 ? max_ctas : num_sms()) / CL;
+  int64_t clusters = max_conv_ctas() / CL;                          // (SAG_UMMA_MAX_CTAS: test knob, forces many work items per CTA)
   if (clusters < 1) clusters = 1;
   if (n_work < clusters) clusters = n_work;
   cudaLaunchConfig_t cfg = {};
@@ -1461,6 +1509,20 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   return p.Z;
 }
 
+// ---- workspace of the fixed-order statistics reduction (stat_reduce): [128 counters | group sums | per-CTA partials] ----
+struct StatLayout { int bound, gs; size_t off_gpart, off_part, bytes; };
+static StatLayout stat_layout(int N, int64_t M, int Z) {
+  StatLayout l;
+  l.bound = Z > 1 ? (int)cdiv64(M, reduce_rows_per_block(M, true)) : max_conv_ctas();
+  l.gs = 1;
+  while (l.gs * l.gs < l.bound) ++l.gs;
+  l.off_gpart = 512;
+  l.off_part = l.off_gpart + (size_t)(l.gs + 2) * 2 * N * sizeof(double);
+  l.bytes = (l.off_part + (size_t)l.bound * 2 * N * sizeof(float) + 255) & ~(size_t)255;
+  return l;
+}
+size_t umma_stat_ws_bytes(int K, int N, int64_t M) { return stat_layout(N, M, plan_tile(K, N, M).Z).bytes; }
+
 thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
 thread_local int g_umma_pair = -1;  // -1: SAG_UMMA_PAIR (default off); 0 / 1: forced (sag_set_option "cta_pair")
 
@@ -1572,6 +1634,16 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;
   SAG_REQUIRE(w.KC >= 1, SAG_EINVAL, "tcgen05 path: empty contraction");
   SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);
+  if (ep.stat_sum != nullptr) {
+    SAG_REQUIRE(ep.stat_ws != nullptr, SAG_EINVAL, "tcgen05 path: statistics need Epilogue::stat_ws");
+    SAG_REQUIRE(Z == 1 || 256 % cdiv(w.N, 4) == 0, SAG_EUNSUPPORTED, "tcgen05 path: split-K statistics over %d columns", w.N);
+    const StatLayout l = stat_layout(w.N, M, Z);
+    char* base = reinterpret_cast<char*>(ep.stat_ws);
+    a.st_cnt = reinterpret_cast<unsigned*>(base);
+    a.st_gpart = reinterpret_cast<double*>(base + l.off_gpart);
+    a.st_part = reinterpret_cast<float*>(base + l.off_part);
+    a.st_gs = l.gs;
+  }
   int r;
   switch (w.BN) {
     case 32: r = launch_bn<32>(g, a, tm, w.NT, w.planes, src, Z, st); break;
@@ -1582,9 +1654,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   SAG_TRY(r);
   if (Z > 1) {
-    int rpb = (int)(M / (2 * num_sms()));           // rows per block: keep >= 2 blocks per SM, at most 16 rows
-    if (rpb > 16) rpb = 16;
-    if (rpb < 1) rpb = 1;
+    const int rpb = reduce_rows_per_block(M, ep.stat_sum != nullptr);
     launch_pdl(splitk_reduce_kernel, dim3((unsigned)cdiv64(M, rpb)), dim3(256), 0, st, g, a, Z, rpb);
     SAG_LAUNCH_CHECK();
   }

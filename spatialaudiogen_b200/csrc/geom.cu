@@ -30,10 +30,13 @@ void Profiler::clear() {
   recs.clear();
 }
 
-ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t s) : st(s) {
+ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t s, const char* name, double issued, int tile, int split) : st(s) {
   if (g_prof == nullptr || !g_prof->on) return;
   ProfRec r;
   r.cat = cat; r.flops = flops; r.bytes = bytes;
+  r.issued = issued < 0 ? flops : issued;
+  r.tile = tile; r.split = split;
+  snprintf(r.name, sizeof(r.name), "%s", name ? name : "");
   if (cudaEventCreate(&r.e0) != cudaSuccess) return;
   if (cudaEventCreate(&r.e1) != cudaSuccess) { cudaEventDestroy(r.e0); return; }
   cudaEventRecord(r.e0, st);

@@ -159,6 +159,7 @@ struct Fwd {
   cudaStream_t st;
   int prec;
   int cat = PROF_CONV;
+  void* stat_ws = nullptr;      // scratch of the fixed-order batch-norm statistics reduction (tcgen05 path)
   bool dry() const { return ar.dry; }
   bool tc() const { return prec != SAG_PREC_FP32; }
 
@@ -181,10 +182,26 @@ struct Fwd {
   const float* W(const std::string& name, int* err) {
     auto it = h->weights.find(name);
     if (it == h->weights.end()) {
-      if (!dry()) { set_error("weight '%s' has not been loaded", name.c_str()); *err = SAG_ESTATE; }
+      if (!dry() || ar.prepare) { set_error("weight '%s' has not been loaded", name.c_str()); *err = SAG_ESTATE; }
       return nullptr;
     }
     return it->second.p;
+  }
+  // the tensor-core operand image of a layer: built in the prepare pass (sag_workspace_bytes), only looked up afterwards
+  template <class PackFn>
+  int image(const std::string& scope, int K, int N, int64_t Mrows, PackFn pack, const UmmaWeights** out) {
+    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(K, N, Mrows));
+    auto it = h->umma.find(key);
+    if (it == h->umma.end()) {
+      SAG_REQUIRE(ar.prepare, SAG_ESTATE,
+                  "the tensor-core weight image of '%s' for this batch size / precision has not been built: call "
+                  "sag_workspace_bytes(h, batch) after sag_finalize_weights (sag_forward does not allocate)", scope.c_str());
+      UmmaWeights uw;
+      SAG_TRY(pack(&uw));
+      it = h->umma.emplace(key, uw).first;
+    }
+    *out = &it->second;
+    return SAG_OK;
   }
   const float* Wp(const std::string& name, int* err) {     // packed variant (deconv: [tap][Cin][Cout])
     auto it = h->packed.find(name);
@@ -225,29 +242,29 @@ struct Fwd {
       g.T = kh; g.Cin = kw * cin;
       for (int r = 0; r < kh; ++r) { g.dy[r] = (short)r; g.dx[r] = 0; g.widx[r] = (short)r; }
     }
-    float* scratch = tc() ? splitk(g.T * g.Cin, cout, (int64_t)g.N * g.PH * g.PW) : nullptr;
-    if (dry()) return SAG_OK;
+    const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
+    float* scratch = tc() ? splitk(g.T * g.Cin, cout, Mrows) : nullptr;
+    if (dry() && !(ar.prepare && tc())) return SAG_OK;
     int err = SAG_OK;
     const float* w = W(scope + "/weights", &err);
     const float* b = bias ? W(scope + "/biases", &err) : nullptr;
     SAG_TRY(err);
-    Epilogue ep{b, relu, ssum, ssqs};
-    const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
+    const UmmaWeights* img = nullptr;
+    if (tc()) {
+      const int Kg = g.T * g.Cin;
+      SAG_TRY(image(scope, Kg, cout, Mrows, [&](UmmaWeights* uw) { return umma_pack_weights(w, Kg, cout, cout, prec, Mrows, uw, st); }, &img));
+    }
+    if (dry()) return SAG_OK;
+    Epilogue ep{b, relu, ssum, ssqs, stat_ws};
+    const double M = (double)Mrows, K = (double)g.T * g.Cin;
     const double esz_in = x.v.fmt == ACT_BF2 ? (x.v.plane ? 4.0 : 2.0) : 4.0, esz_out = y.v.fmt == ACT_BF2 ? (y.v.plane ? 4.0 : 2.0) : 4.0;
-    ProfScope ps(cat, 2.0 * M * K * cout, esz_in * (double)n * hh * ww * cin + 4.0 * K * cout + esz_out * M * cout, st);
+    ProfScope ps(cat, 2.0 * M * K * cout, esz_in * (double)n * hh * ww * cin + 4.0 * K * cout + esz_out * M * cout, st, scope.c_str(), -1.0,
+                 img ? img->BN : 0, img ? umma_split_k(img->K, img->N, Mrows, nullptr) : 0);
     if (!tc()) {
       SAG_REQUIRE(x.v.fmt == ACT_F32 && y.v.fmt == ACT_F32, SAG_EINVAL, "fp32 contraction on a split-bf16 tensor");
       return launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st);
     }
-    const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
-    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, cout, Mrows));
-    auto it = h->umma.find(key);
-    if (it == h->umma.end()) {                    // first use: build the tensor-core operand image of this layer
-      UmmaWeights uw;
-      SAG_TRY(umma_pack_weights(w, g.T * g.Cin, cout, cout, prec, Mrows, &uw, st));
-      it = h->umma.emplace(key, uw).first;
-    }
-    return launch_gather_gemm_umma(x.v, it->second, y.v, g, ep, 0, 0, scratch, st);
+    return launch_gather_gemm_umma(x.v, *img, y.v, g, ep, 0, 0, scratch, st);
   }
 
   // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
@@ -260,7 +277,7 @@ struct Fwd {
       SAG_TRY(make_deconv_subpixel_geom(&g0, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc, &a0, &b0));
       scratch = splitk(g0.T * cin, sh * sw * cout, (int64_t)g0.N * g0.PH * g0.PW);
     }
-    if (dry()) return SAG_OK;
+    if (dry() && !(ar.prepare && tc())) return SAG_OK;
     int err = SAG_OK;
     const float* b = W(scope + "/biases", &err);
     SAG_TRY(err);
@@ -273,20 +290,25 @@ struct Fwd {
       SAG_TRY(make_deconv_subpixel_geom(&g, n, hh, ww, cin, x.ld, kh, kw, sh, sw, row0, row1, y_sn, y_sh, y_sw, y_sc,
                                         &oh_lim, &ow_lim));
       const int64_t Mrows = (int64_t)g.N * g.PH * g.PW;
-      const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, sh * sw * cout, Mrows));
-      auto it = h->umma.find(key);
-      if (it == h->umma.end()) {
-        const float* w_tf = W(scope + "/weights", &err);
-        SAG_TRY(err);
-        UmmaWeights uw;
-        SAG_TRY(umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, &uw, st));
-        it = h->umma.emplace(key, uw).first;
-      }
-      g.Cout = it->second.N;
-      const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
-      ProfScope ps(PROF_DECONV, 2.0 * M * K * g.Cout, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st);
-      return launch_gather_gemm_umma(x.v, it->second, y.v, g, ep, oh_lim, ow_lim, scratch, st);
+      const float* w_tf = W(scope + "/weights", &err);
+      SAG_TRY(err);
+      const UmmaWeights* img = nullptr;
+      SAG_TRY(image(scope, g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
+        return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &img));
+      if (dry()) return SAG_OK;
+      g.Cout = img->N;
+      const double M = (double)Mrows, K = (double)g.T * g.Cin;
+      // useful work: every input pixel that has at least one tap inside the requested output rows, times all kh x kw taps
+      // (the reference's transposed conv restricted to those input rows; BASELINE.md section 2: deconv1 233.0 M MAC per window);
+      // issued: the sub-pixel GEMM as launched (zero taps of ceil(k/s)*s > k kernels and border cells included)
+      int in_rows = 0;
+      for (int i = 0; i < hh; ++i) in_rows += (i * sh < row1 && i * sh + kh > row0) ? 1 : 0;
+      const double useful = 2.0 * (double)n * in_rows * ww * kh * kw * (double)cin * cout;
+      ProfScope ps(PROF_DECONV, useful, 4.0 * ((double)n * hh * ww * cin + K * g.Cout + M * g.Cout), st, scope.c_str(),
+                   2.0 * M * K * g.Cout, img->BN, umma_split_k(img->K, img->N, Mrows, nullptr));
+      return launch_gather_gemm_umma(x.v, *img, y.v, g, ep, oh_lim, ow_lim, scratch, st);
     }
+    if (dry()) return SAG_OK;
     const float* w = Wp(scope + "/weights", &err);
     SAG_TRY(err);
     for (int py = 0; py < sh; ++py)
@@ -297,7 +319,7 @@ struct Fwd {
         if (r == 1) continue;
         SAG_TRY(r);
         const double M = (double)g.N * g.PH * g.PW, K = (double)g.T * g.Cin;
-        ProfScope ps(PROF_DECONV, 2.0 * M * K * cout, 4.0 * (M * cin / (sh * sw) + K * cout + M * cout), st);
+        ProfScope ps(PROF_DECONV, 2.0 * M * K * cout, 4.0 * (M * cin / (sh * sw) + K * cout + M * cout), st, scope.c_str());
         SAG_TRY(launch_gather_gemm_ffma(x.f32(), w, y.f32(), g, ep, st));
       }
     return SAG_OK;
@@ -328,7 +350,7 @@ static BnBuf take_bn(double*& pool, int c) {
 // ResNet18.inference_ops(truncate_at='conv5_2') with batch statistics (resnet.py:123-190; model.py:189-201).
 // x: fp32 (B,H,W,3).  The result lands in `y_out` when given (must be in the precision's activation format), else in a
 // fresh arena tensor; *y_act receives it.
-int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int Wd, Act* y_act, Arena& ar,
+int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc, int B, int H, int Wd, Act* y_act, Arena& ar,
                    cudaStream_t st) {
   Fwd f{h, ar, st, h->cfg.precision};
   const std::string p = scope + "/";
@@ -347,7 +369,21 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   int64_t n_stat = 2 * 64;
   for (const BlockDef& b : kBlocks) n_stat += 4 * b.cout;
   double* stat_pool = ar.alloc<double>(n_stat);
-  if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(double) * n_stat, st));
+  if (f.tc()) {
+    // tcgen05 path: every layer's sums are written once by a fixed-order reduction through this scratch (largest layer's need);
+    // only its arrival counters have to start at zero
+    size_t need = umma_stat_ws_bytes(256, 64, (int64_t)B * ((H + 1) / 2) * ((Wd + 1) / 2));
+    int hh = ((H + 1) / 2 + 1) / 2, ww = ((Wd + 1) / 2 + 1) / 2;
+    for (const BlockDef& b : kBlocks) {
+      if (b.first) { hh = (hh + 1) / 2; ww = (ww + 1) / 2; }
+      need = std::max(need, umma_stat_ws_bytes(9 * b.cin, b.cout, (int64_t)B * hh * ww));
+      need = std::max(need, umma_stat_ws_bytes(9 * b.cout, b.cout, (int64_t)B * hh * ww));
+    }
+    f.stat_ws = ar.alloc<char>((int64_t)need);
+    if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(f.stat_ws, 0, 512, st));
+  } else if (!ar.dry) {
+    SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(double) * n_stat, st));   // FFMA path accumulates with atomics
+  }
   const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;   // bytes per activation element
 
   // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
@@ -356,6 +392,12 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   Act c1 = f.alloc_f32((int64_t)B * OH1 * OW1, 64);
   BnBuf b1 = take_bn(stat_pool, 64);
   if (!f.tc()) {
+    const float* x = reinterpret_cast<const float*>(xsrc.p);
+    if (xsrc.kind != FRAMES_F32) {                      // uint8 frames: prepare them as fp32 first (exact-fp32 parity path)
+      float* xf = ar.alloc<float>((int64_t)B * H * Wd * 3);
+      if (!ar.dry) SAG_TRY(launch_frames_to_f32(xsrc, B, H, Wd, xf, st));
+      x = xf;
+    }
     SAG_TRY(f.conv(Act(x, 3), B, H, Wd, 3, p + "conv1/conv", 7, 7, 64, 2, 2, 1, false, 0, c1, b1.sum, b1.sqs, &oh, &ow));
   } else {
     // tensor-core route: the stride-2 7x7 convolution over 3 channels becomes a stride-1 4x4 convolution over the 2x2
@@ -372,25 +414,24 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     g.osy = 1; g.osx = 1; g.y_sc = 1; g.y_sw = 64; g.y_sh = (int64_t)ow * 64; g.y_sn = (int64_t)oh * ow * 64;
     g.Cout = 64; g.T = 4;
     for (int t = 0; t < 4; ++t) { g.dy[t] = (short)t; g.dx[t] = 0; g.widx[t] = (short)t; }
-    float* scratch = f.splitk(g.T * g.Cin, 64, (int64_t)B * oh * ow);
-    if (!ar.dry) {
+    const int64_t Mrows = (int64_t)B * oh * ow;
+    float* scratch = f.splitk(g.T * g.Cin, 64, Mrows);
+    if (!ar.dry || ar.prepare) {
       const float* w = f.W(p + "conv1/conv/weights", &err);
       SAG_TRY(err);
-      const int64_t Mrows = (int64_t)B * oh * ow;
-      const std::string key = p + "conv1/conv#" + std::to_string(f.prec) + "#" + std::to_string(umma_tile_width(g.T * g.Cin, 64, Mrows));
-      auto it = h->umma.find(key);
-      if (it == h->umma.end()) {
-        UmmaWeights uw;
-        SAG_TRY(umma_pack_conv_s2d(w, 7, 7, 3, 64, f.prec, Mrows, &uw, st));
-        it = h->umma.emplace(key, uw).first;
+      const UmmaWeights* img = nullptr;
+      SAG_TRY(f.image(p + "conv1/conv", g.T * g.Cin, 64, Mrows, [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.prec, Mrows, uw, st); }, &img));
+      if (!ar.dry) {
+        {
+          const double in_b = xsrc.kind == FRAMES_F32 ? 4.0 : 1.0;
+          ProfScope ps(PROF_POINTWISE, 0, in_b * B * (double)H * Wd * 3 + act_b * B * (double)H2 * W2 * 16, st, "frame ingest (space-to-depth)");
+          SAG_TRY(launch_space_to_depth16(xsrc, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
+        }
+        Epilogue ep{nullptr, 0, b1.sum, b1.sqs, f.stat_ws};
+        ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)H2 * W2 * 16 + 4.0 * B * (double)oh * ow * 64, st,
+                     (p + "conv1/conv").c_str(), 2.0 * B * oh * ow * 256.0 * 64, img->BN, 1);
+        SAG_TRY(launch_gather_gemm_umma(xp.v, *img, c1.v, g, ep, 0, 0, scratch, st));
       }
-      {
-        ProfScope ps(PROF_POINTWISE, 0, 4.0 * B * (double)H * Wd * 3 + act_b * B * (double)H2 * W2 * 16, st);
-        SAG_TRY(launch_space_to_depth16(x, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
-      }
-      Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
-      ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)H2 * W2 * 16 + 4.0 * B * (double)oh * ow * 64, st);
-      SAG_TRY(launch_gather_gemm_umma(xp.v, it->second, c1.v, g, ep, 0, 0, scratch, st));
     }
   }
   f.tap(scope + "/conv1_raw", c1, {B, oh, ow, 64});
@@ -399,7 +440,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
   int ph = (oh + 1) / 2, pw = (ow + 1) / 2;
   Act cur = f.alloc_act((int64_t)B * ph * pw, 64);
   if (!ar.dry) {
-    ProfScope ps(PROF_POINTWISE, 0, B * 64.0 * (4.0 * oh * ow + act_b * ph * pw), st);
+    ProfScope ps(PROF_POINTWISE, 0, B * 64.0 * (4.0 * oh * ow + act_b * ph * pw), st, "conv1 bn+relu+maxpool");
     SAG_TRY(launch_bn_relu_maxpool_stats(c1.f32(), st1, B, oh, ow, 64, cur.v, st));
   }
   f.tap(scope + "/pool1", cur, {B, ph, pw, 64});
@@ -425,13 +466,13 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
     SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, s1.sum, s1.sqs, &oh, &ow));
     SAG_TRY(bn_stats(q + "/conv_1", s1, npix, &t1));
     if (!ar.dry) {
-      ProfScope ps(PROF_POINTWISE, 0, (4.0 + act_b) * npix * b.cout, st);
+      ProfScope ps(PROF_POINTWISE, 0, (4.0 + act_b) * npix * b.cout, st, (std::string(b.name) + "/conv_1 bn+relu").c_str());
       SAG_TRY(launch_bn_apply_stats(r1.f32(), t1, ActView(), 1, a1.v, npix, b.cout, st));
     }
     SAG_TRY(f.conv(a1, B, nh, nw, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, s2.sum, s2.sqs, &oh, &ow));
     SAG_TRY(bn_stats(q + "/conv_2", s2, npix, &t2));
     if (!ar.dry) {
-      ProfScope ps(PROF_POINTWISE, 0, (4.0 + 2.0 * act_b) * npix * b.cout, st);
+      ProfScope ps(PROF_POINTWISE, 0, (4.0 + 2.0 * act_b) * npix * b.cout, st, (std::string(b.name) + "/conv_2 bn+add+relu").c_str());
       SAG_TRY(launch_bn_apply_stats(r2.f32(), t2, shortcut, 1, out.v, npix, b.cout, st));
     }
     f.tap(scope + "/" + b.name, out, {B, nh, nw, b.cout});
@@ -444,7 +485,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int 
 // ------------------------------------------------------------------------------------------------------------------
 // SptAudioGen.inference_ops (model.py:356-434)
 // ------------------------------------------------------------------------------------------------------------------
-int forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* out, Arena& ar, int B,
+int forward(sag_handle* h, const float* audio, const FrameSrc& video, const FrameSrc& flow, float* out, Arena& ar, int B,
             cudaStream_t st) {
   const sag_config& c = h->cfg;
   const sag_dims& d = h->dims;
@@ -482,7 +523,7 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   Act mag = f.alloc_act((int64_t)B * n_enc * wind, 1);
   if (!ar.dry) {
     ProfScope ps(PROF_STFT, 5.0 * wind * std::log2((double)wind) * B * (full ? d.n_stft_frames : n_enc),
-                 4.0 * B * (double)d.snd_size + act_b * B * (double)n_enc * wind + (unet ? 8.0 * B * n_msk * wind : 0.0), st);
+                 4.0 * B * (double)d.snd_size + act_b * B * (double)n_enc * wind + (unet ? 8.0 * B * n_msk * wind : 0.0), st, "stft");
     if (full)
       SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag.v, st));
     else
@@ -532,9 +573,9 @@ int forward(sag_handle* h, const float* audio, const float* video, const float* 
   }
   for (int v = 0; v < 2; ++v) {
     if (!(v == 0 ? c.enc_video : c.enc_flow)) continue;
-    const float* inp = v == 0 ? video : flow;
+    const FrameSrc& inp = v == 0 ? video : flow;
     const std::string k = v == 0 ? "video" : "flow";
-    if (!ar.dry) SAG_REQUIRE(inp != nullptr, SAG_EINVAL, "forward: %s input is NULL but the encoder is enabled", k.c_str());
+    if (!ar.dry) SAG_REQUIRE(inp.p != nullptr, SAG_EINVAL, "forward: %s input is NULL but the encoder is enabled", k.c_str());
     const int fh = (c.frame_h + 31) / 32, fw = (c.frame_w + 31) / 32;
     Act vf;
     SAG_TRY(resnet18_tower(h, k + "_encoder", inp, B, c.frame_h, c.frame_w, &vf, ar, st));

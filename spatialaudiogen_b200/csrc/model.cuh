@@ -24,6 +24,9 @@ struct Arena {
   char* base = nullptr;
   size_t cap = 0, off = 0, peak = 0;
   bool dry = false;
+  // dry && prepare: additionally build (allocate + pack) the tensor-core weight images this batch size needs -- the only
+  // place they are created; the real pass fails if one is missing (no allocation inside sag_forward)
+  bool prepare = false;
   bool failed = false;
   // split-K scratch shared by all layers of a pass (they run back to back on one stream): the dry pass records the
   // largest request in scratch_need, the real pass gets that many bytes at `scratch`
@@ -82,9 +85,9 @@ namespace sag {
 
 int build_expected(sag_handle* h);
 int derive_dims(const sag_config& c, sag_dims* d);
-int forward(sag_handle* h, const float* audio, const float* video, const float* flow, float* out, Arena& ar, int B,
+int forward(sag_handle* h, const float* audio, const FrameSrc& video, const FrameSrc& flow, float* out, Arena& ar, int B,
             cudaStream_t st);
-int resnet18_tower(sag_handle* h, const std::string& scope, const float* x, int B, int H, int W, Act* y, Arena& ar,
+int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& x, int B, int H, int W, Act* y, Arena& ar,
                    cudaStream_t st);
 int launch_act_to_f32(const ActView& src, float* dst, int64_t n, cudaStream_t st);   // pointwise.cu
 const char* last_error_cstr();

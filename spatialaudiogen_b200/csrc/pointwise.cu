@@ -364,11 +364,51 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
   return SAG_OK;
 }
 
-// ---- (n,h,w,c) -> 2x2 space-to-depth of the zero-bordered image, 16 channels per pixel ----
-template <int C>
-__global__ void space_to_depth16_kernel(const float* __restrict__ x, int n, int h, int w, int pt, int pl, int h2, int w2,
-                                        const ActView out) {
+// ---- frame ingest: (n,h,w,c) -> 2x2 space-to-depth of the zero-bordered image, 16 channels per pixel ----
+// The source is either the prepared fp32 frame or the uint8 frame as decoded from the jpg, prepared here:
+//   FRAMES_U8 video: myutils.img_prep_fcn (myutils.py:88-89)  x/255. - 0.5, evaluated in double like numpy and rounded once to
+//                    fp32 (what feeding the float64 array into the float32 placeholder does) -- a 256-entry table per block;
+//   FRAMES_U8 flow : FlowReader.get_by_index (feeder.py:147-161): channel 2 = magnitude de-quantised with the frame's
+//                    (min, max) limits (float32 chunk x float64 limits, rounded to fp32 after each in-place step), channel 0 =
+//                    angle * 2pi/255 in fp32, result (mag cos, mag sin, mag).
+template <int C, int KIND>
+__device__ __forceinline__ void load_frame_pixel(const void* __restrict__ x, int64_t pix, const float* lut, double lim_scale, double lim_min,
+                                                 float* v) {
+  if (KIND == FRAMES_F32) {
+    const float* p = reinterpret_cast<const float*>(x) + pix * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) v[ch] = __ldg(p + ch);
+  } else {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(x) + pix * C;
+    unsigned char u[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) u[ch] = __ldg(p + ch);
+    if (KIND == FRAMES_U8_VIDEO) {
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = lut[u[ch]];
+    } else {
+      float m = (float)((double)(float)u[C - 1] * lim_scale);       // chunk[..., 2] *= (m_max - m_min) / 255.
+      m = (float)((double)m + lim_min);                              // chunk[..., 2] += m_min
+      const float ang = (float)u[0] * (float)(2.0 * 3.14159265358979323846 / 255.0);
+      float sn, cs;
+      sincosf(ang, &sn, &cs);
+      v[0] = m * cs;
+      if (C > 1) v[1] = m * sn;
+      if (C > 2) v[C - 1] = m;
+    }
+  }
+}
+__device__ __forceinline__ void frame_lut_to_smem(float* lut) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)((double)i / 255.0 - 0.5);
+  __syncthreads();
+}
+
+template <int C, int KIND>
+__global__ void space_to_depth16_kernel(const void* __restrict__ x, const double* __restrict__ lims, int n, int h, int w, int pt, int pl,
+                                        int h2, int w2, const ActView out) {
+  __shared__ float s_lut[256];
   pdl_prologue();
+  if (KIND == FRAMES_U8_VIDEO) frame_lut_to_smem(s_lut);
   const int64_t total = (int64_t)n * h2 * w2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -376,6 +416,8 @@ __global__ void space_to_depth16_kernel(const float* __restrict__ x, int n, int 
     const int64_t r = i / w2;
     const int y2 = (int)(r % h2);
     const int b = (int)(r / h2);
+    double lscale = 0.0, lmin = 0.0;
+    if (KIND == FRAMES_U8_FLOW) { lmin = lims[2 * b]; lscale = (lims[2 * b + 1] - lmin) / 255.0; }
     float v[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = 0.f;
@@ -384,31 +426,67 @@ __global__ void space_to_depth16_kernel(const float* __restrict__ x, int n, int 
       // border pixels read a clamped (valid) address and are zeroed by a select: no branch between the 4*C loads
       const int iy = 2 * y2 + (sub >> 1) - pt, ix = 2 * x2 + (sub & 1) - pl;
       const bool inside = (unsigned)iy < (unsigned)h && (unsigned)ix < (unsigned)w;
-      const float* p = x + (((int64_t)b * h + min(max(iy, 0), h - 1)) * w + min(max(ix, 0), w - 1)) * C;
+      float t[C];
+      load_frame_pixel<C, KIND>(x, ((int64_t)b * h + min(max(iy, 0), h - 1)) * w + min(max(ix, 0), w - 1), s_lut, lscale, lmin, t);
 #pragma unroll
-      for (int ch = 0; ch < C; ++ch) {
-        const float t = __ldg(p + ch);
-        v[sub * C + ch] = inside ? t : 0.f;
-      }
+      for (int ch = 0; ch < C; ++ch) v[sub * C + ch] = inside ? t[ch] : 0.f;
     }
 #pragma unroll
     for (int e = 0; e < 16; e += 4) store_act4(out.p, out.fmt, out.plane, i * 16 + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
   }
 }
 
-int launch_space_to_depth16(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
+template <int C>
+static void launch_s2d_kind(int kind, unsigned blocks, cudaStream_t st, const void* x, const double* lims, int n, int h, int w, int pt, int pl,
+                            int h2, int w2, const ActView& out) {
+  if (kind == FRAMES_U8_VIDEO) launch_pdl(space_to_depth16_kernel<C, FRAMES_U8_VIDEO>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
+  else if (kind == FRAMES_U8_FLOW) launch_pdl(space_to_depth16_kernel<C, FRAMES_U8_FLOW>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
+  else launch_pdl(space_to_depth16_kernel<C, FRAMES_F32>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
+}
+
+int launch_space_to_depth16(const FrameSrc& src, int n, int h, int w, int c, int pt, int pl, int h2, int w2, const ActView& out,
                             cudaStream_t st) {
   SAG_REQUIRE(c >= 1 && 4 * c <= 16, SAG_EINVAL, "space_to_depth16: %d channels", c);
+  SAG_REQUIRE(src.kind != FRAMES_U8_FLOW || (c == 3 && src.lims != nullptr), SAG_EINVAL, "quantised flow frames need 3 channels and their limits");
   const int64_t total = (int64_t)n * h2 * w2;
   int64_t blocks = cdiv64(total, 256);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   switch (c) {
-    case 1: launch_pdl(space_to_depth16_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
-    case 2: launch_pdl(space_to_depth16_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
-    case 3: launch_pdl(space_to_depth16_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
-    default: launch_pdl(space_to_depth16_kernel<4>, dim3((unsigned)blocks), dim3(256), 0, st, x, n, h, w, pt, pl, h2, w2, out); break;
+    case 1: launch_s2d_kind<1>(src.kind == FRAMES_U8_FLOW ? FRAMES_F32 : src.kind, (unsigned)blocks, st, src.p, src.lims, n, h, w, pt, pl, h2, w2, out); break;
+    case 2: launch_s2d_kind<2>(src.kind == FRAMES_U8_FLOW ? FRAMES_F32 : src.kind, (unsigned)blocks, st, src.p, src.lims, n, h, w, pt, pl, h2, w2, out); break;
+    case 3: launch_s2d_kind<3>(src.kind, (unsigned)blocks, st, src.p, src.lims, n, h, w, pt, pl, h2, w2, out); break;
+    default: launch_s2d_kind<4>(src.kind == FRAMES_U8_FLOW ? FRAMES_F32 : src.kind, (unsigned)blocks, st, src.p, src.lims, n, h, w, pt, pl, h2, w2, out); break;
   }
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// uint8 frames -> the prepared fp32 frames (exact-fp32 FFMA path, stage entry points): same arithmetic as above
+template <int KIND>
+__global__ void frames_to_f32_kernel(const void* __restrict__ x, const double* __restrict__ lims, int64_t pixels_per_image, int64_t total,
+                                     float* __restrict__ out) {
+  __shared__ float s_lut[256];
+  pdl_prologue();
+  if (KIND == FRAMES_U8_VIDEO) frame_lut_to_smem(s_lut);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    double lscale = 0.0, lmin = 0.0;
+    if (KIND == FRAMES_U8_FLOW) { const int64_t b = i / pixels_per_image; lmin = lims[2 * b]; lscale = (lims[2 * b + 1] - lmin) / 255.0; }
+    float t[3];
+    load_frame_pixel<3, KIND>(x, i, s_lut, lscale, lmin, t);
+    out[i * 3] = t[0]; out[i * 3 + 1] = t[1]; out[i * 3 + 2] = t[2];
+  }
+}
+
+int launch_frames_to_f32(const FrameSrc& src, int n, int h, int w, float* out, cudaStream_t st) {
+  SAG_REQUIRE(src.kind == FRAMES_U8_VIDEO || (src.kind == FRAMES_U8_FLOW && src.lims != nullptr), SAG_EINVAL, "frames_to_f32: bad source");
+  const int64_t total = (int64_t)n * h * w;
+  int64_t blocks = cdiv64(total, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (src.kind == FRAMES_U8_VIDEO) launch_pdl(frames_to_f32_kernel<FRAMES_U8_VIDEO>, dim3((unsigned)blocks), dim3(256), 0, st, src.p, src.lims, (int64_t)h * w, total, out);
+  else launch_pdl(frames_to_f32_kernel<FRAMES_U8_FLOW>, dim3((unsigned)blocks), dim3(256), 0, st, src.p, src.lims, (int64_t)h * w, total, out);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }

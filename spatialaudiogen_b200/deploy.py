@@ -46,68 +46,115 @@ class W2XYZ(object):
         self.model.load_weights(weights)
         B, dev = self.batch_size, self.model.device
         H, W = self.model.dims_frame()
-        # pinned staging + device buffers, allocated once (the reference's placeholders, deploy.py:69-76)
+        # pinned staging + device buffers, allocated once (the reference's placeholders, deploy.py:69-76); visual frames have a
+        # float32 set (prepared frames) and a uint8 set (frames as decoded from disk, prepared by the ingest kernel)
         self._h = {AUDIO: torch.zeros((B, self.audio_size, 1), dtype=torch.float32).pin_memory()}
         for k in (VIDEO, FLOW):
             if k in params.encoders:
                 self._h[k] = torch.zeros((B, self.video_size, H, W, 3), dtype=torch.float32).pin_memory()
+                self._h[k + '_u8'] = torch.zeros((B, self.video_size, H, W, 3), dtype=torch.uint8).pin_memory()
+        if FLOW in params.encoders:
+            self._h['flow_limits'] = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
         self._d = {k: torch.empty_like(v, device=dev) for k, v in self._h.items()}
         self._out = torch.empty((B, self.model.snd_dur, 3), dtype=torch.float32, device=dev)
         self._out_h = torch.empty((B, self.model.snd_dur, 3), dtype=torch.float32).pin_memory()
 
-    def run_batch(self, audio, video=None, flow=None):
+    def run_batch(self, audio, video=None, flow=None, flow_limits=None):
         """One `sess.run(ambi_pred_t, feed_dict)` (deploy.py:141): host arrays of n <= batch_size windows in, host
-        (n, snd_dur, 3) predictions out.  The batch is zero-padded to batch_size like the reference."""
+        (n, snd_dur, 3) predictions out.  The batch is zero-padded to batch_size like the reference.  video / flow: prepared
+        float32 frames, or the uint8 frames as decoded from disk (flow then with `flow_limits` (n, 2), the frames' rows of
+        flow_limits.npy); uint8 frames of a FULL batch are uploaded as they are and prepared on the device, a short batch is
+        prepared on the host first, because the reference pads with zeros AFTER its preparation (deploy.py:127-139)."""
         n = audio.shape[0]
         srcs = {AUDIO: audio, VIDEO: video, FLOW: flow}
+        use = {}
         with torch.cuda.device(self.model.device):
-            for k, h in self._h.items():
+            for k in (AUDIO, VIDEO, FLOW):
+                if k not in self._h:
+                    continue
                 if srcs[k] is None:
                     raise ValueError('%s windows required by encoders=%s' % (k, self.params.encoders))
-                h[:n].copy_(torch.as_tensor(np.asarray(srcs[k], dtype=np.float32)))
+                x = np.asarray(srcs[k])
+                if k != AUDIO and x.dtype == np.uint8:
+                    if k == FLOW and flow_limits is None:
+                        raise ValueError('uint8 flow frames need flow_limits')
+                    if n == self.batch_size:
+                        self._h[k + '_u8'].copy_(torch.from_numpy(np.ascontiguousarray(x)))
+                        self._d[k + '_u8'].copy_(self._h[k + '_u8'], non_blocking=True)
+                        use[k] = self._d[k + '_u8']
+                        if k == FLOW:
+                            self._h['flow_limits'].copy_(torch.as_tensor(np.asarray(flow_limits, np.float64)))
+                            self._d['flow_limits'].copy_(self._h['flow_limits'], non_blocking=True)
+                        continue
+                    x = myutils.img_prep_fcn()(x) if k == VIDEO else readers.dequantize_flow(x, flow_limits)
+                h = self._h[k]
+                h[:n].copy_(torch.as_tensor(np.asarray(x, dtype=np.float32)))
                 if n != self.batch_size:
                     h[n:].zero_()
                 self._d[k].copy_(h, non_blocking=True)
-            self.model.forward_into(self._d[AUDIO], self._d.get(VIDEO), self._d.get(FLOW), self._out)
+                use[k] = self._d[k]
+            lims = self._d['flow_limits'] if (FLOW in use and use[FLOW].dtype == torch.uint8) else None
+            self.model.forward_into(use[AUDIO], use.get(VIDEO), use.get(FLOW), self._out, lims)
             self._out_h.copy_(self._out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return self._out_h[:n].numpy().copy()
 
-    def deploy_windows(self, ambix_windows, video_windows=None, flow_windows=None):
-        """The loop of deploy.py:112-151.  ambix_windows (N, audio_size, C>=1) with W in channel 0; video / flow
-        (N, video_size, H, W, 3).  Returns (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
-        ambix_windows = np.asarray(ambix_windows)
-        N = ambix_windows.shape[0]
+    def deploy_stream(self, windows):
+        """The loop of deploy.py:112-151 over an ITERATOR of windows -- dicts {'ambix': (audio_size, C>=1) with W in channel 0
+        [, 'video', 'flow': (video_size, H, W, 3) float32 or uint8, 'flow_limits': (video_size, 2)]} -- consumed batch_size at a
+        time like the reference does, so host memory holds one batch of inputs plus the growing output.  Returns
+        (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
         ss = self.model.snd_contx // 2
         mono, pred = [], []
-        for b0 in range(0, N, self.batch_size):
-            a = np.asarray(ambix_windows[b0:b0 + self.batch_size], np.float64)
+        batch = []
+
+        def flush():
+            a = np.stack([np.asarray(c['ambix'], np.float64) for c in batch], 0)
             n = a.shape[0]
-            v = None if video_windows is None else video_windows[b0:b0 + n]
-            f = None if flow_windows is None else flow_windows[b0:b0 + n]
-            out = self.run_batch(a[:, :, :1], v, f)
+            v = np.stack([c['video'] for c in batch], 0) if VIDEO in self.params.encoders else None
+            f = np.stack([c['flow'] for c in batch], 0) if FLOW in self.params.encoders else None
+            fl = np.stack([np.asarray(c['flow_limits']).reshape(-1, 2)[0] for c in batch], 0) if (f is not None and 'flow_limits' in batch[0]) else None
+            out = self.run_batch(a[:, :, :1], v, f, fl)
             pred.append(out.reshape(n * out.shape[1], out.shape[2]))
             mono.append(np.copy(a[:, ss:ss + self.model.snd_dur, :1]).reshape(-1, 1))
-        mono = np.concatenate(mono, 0)
-        return np.concatenate((mono, np.concatenate(pred, 0)), 1)          # float64, like numpy promotes in deploy.py:151
+            del batch[:]
+
+        for c in windows:
+            batch.append(c)
+            if len(batch) == self.batch_size:
+                flush()
+        if batch:
+            flush()
+        if not pred:
+            return np.zeros((0, 4))
+        return np.concatenate((np.concatenate(mono, 0), np.concatenate(pred, 0)), 1)   # float64, like numpy promotes in deploy.py:151
+
+    def deploy_windows(self, ambix_windows, video_windows=None, flow_windows=None):
+        """deploy_stream over arrays: ambix_windows (N, audio_size, C>=1); video / flow (N, video_size, H, W, 3)."""
+        def it():
+            for i in range(len(ambix_windows)):
+                c = {'ambix': ambix_windows[i]}
+                if video_windows is not None:
+                    c['video'] = video_windows[i]
+                if flow_windows is not None:
+                    c['flow'] = flow_windows[i]
+                yield c
+        return self.deploy_stream(it())
 
     def deploy(self, input_folder, deploy_start, deploy_duration):
         """deploy.py:90-152: read the windows of `input_folder` (the per-video folder layout of readers.SampleReader)
         scheduled by its audio_pow.lst from `deploy_start` for `deploy_duration` seconds -- the schedule is shifted so
-        that the first window sits exactly at deploy_start (deploy.py:108-109) -- and generate their ambisonics.
+        that the first window sits exactly at deploy_start (deploy.py:108-109) -- and generate their ambisonics, batch by
+        batch (the reader is consumed lazily; video frames travel as uint8 and are prepared on the device).
         Returns (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
         p = self.params
         reader = readers.SampleReader(input_folder, ambi_order=p.ambi_order, audio_rate=p.audio_rate, video_rate=p.video_rate,
                                       context=p.context, duration=self.duration, return_video=VIDEO in p.encoders,
-                                      img_prep=myutils.img_prep_fcn(), return_flow=FLOW in p.encoders, start_time=deploy_start,
+                                      img_prep=None, return_flow=FLOW in p.encoders, start_time=deploy_start,
                                       sample_duration=deploy_duration, skip_silence_thr=None, shuffle=False,
                                       random_rotations=False, skip_rate=None)
         if not reader.chunks_t:
             raise ValueError('%s has no windows in [%s, %s)' % (input_folder, deploy_start, deploy_start + deploy_duration))
         dt = reader.chunks_t[0] - deploy_start
         reader.chunks_t = [t - dt for t in reader.chunks_t]
-        chunks = list(reader.loop_chunks())
-        ambix = np.stack([c['ambix'] for c in chunks], 0)
-        video = np.stack([c['video'] for c in chunks], 0).astype(np.float32) if VIDEO in p.encoders else None
-        flow = np.stack([c['flow'] for c in chunks], 0).astype(np.float32) if FLOW in p.encoders else None
-        return self.deploy_windows(ambix, video, flow)
+        return self.deploy_stream(reader.loop_chunks())

@@ -46,7 +46,7 @@ def _perm(device):
     return _PERM_CACHE[key]
 
 
-def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False, mel_lsd=True):
+def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps=False, mel_lsd=True, emd=True):
     """pred, target (B, T, 3) CUDA, channels (Y, Z, X).  Returns (rows (B, 28) CUDA float32 in ALL_METRICS order,
     maps or None).  maps = (rms_pred, rms_gt), each (B, 7, 12): energy maps of [W | pred or gt] * layout
     (eval.py:147-148, 190), needs `mono` (B, T, 1)."""
@@ -65,9 +65,10 @@ def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps
             raise ValueError('rms_maps needs the W channel (mono)')
         lay = torch.ones((B, 1, 4), device=pred.device) if layout is None else torch.as_tensor(layout, device=pred.device).float()[:, None, :]
         maps = (M.ambix_rms_map(torch.cat((mono, pred), 2) * lay, 30.), M.ambix_rms_map(torch.cat((mono, target), 2) * lay, 30.))
-        # emd/dir, emd/dir2 (eval.py:190-193): exact EMD of the two 84-node maps, solved on the host like the reference
-        d1, d2 = M.ambix_emd_from_maps(maps[0], maps[1], 30.)
-        rows[:, _COL['emd/dir']:_COL['emd/dir2'] + 1] = torch.as_tensor(np.stack((d1, d2), 1), dtype=torch.float32).to(rows.device)
+        if emd:
+            # emd/dir, emd/dir2 (eval.py:190-193): exact EMD of the two 84-node maps, solved on the host like the reference
+            d1, d2 = M.ambix_emd_from_maps(maps[0], maps[1], 30.)
+            rows[:, _COL['emd/dir']:_COL['emd/dir2'] + 1] = torch.as_tensor(np.stack((d1, d2), 1), dtype=torch.float32).to(rows.device)
     return rows, maps
 
 
@@ -89,12 +90,14 @@ def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
     return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
 
 
-def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=False):
+def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True):
     """The evaluation feeder (reference feeder.py:366-420 with for_eval=True, eval.py:43-60): every `folders[i]` (a per-video
     folder, see readers.py) is read in order with the eval schedule -- every 10th entry of audio_pow.lst, no shuffling, no
     rotations, silent chunks kept -- and the samples are grouped into batches of `batch_size` like `dequeue_many`.
     channel_masks: {video id: (4,) mask} from meta/audio_layouts.txt (feeder.py:312-314), default all ones.  The last, short
-    batch is yielded too unless drop_remainder (the reference's queue raises OutOfRange on it)."""
+    batch is dropped by default, like the reference (its `dequeue_many` never returns it, feeder.py:412-419): the visual towers use
+    batch statistics, so rows computed from a smaller batch correspond to nothing the reference computes.  drop_remainder=False
+    yields it anyway (its dict carries 'short_batch': True)."""
     from . import readers, myutils
     from .definitions import VIDEO, FLOW
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
@@ -122,16 +125,18 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
                 yield flush(pending)
                 pending = []
     if pending and not drop_remainder:
-        yield flush(pending)
+        b = flush(pending)
+        b['short_batch'] = True
+        yield b
 
 
 def evaluate_model_dir(model_dir, subset_fn=None, overwrite=False, db_dir=None, audio_layouts_fn='meta/audio_layouts.txt', batch_size=16,
-                       drop_remainder=False, precision=None, device=None):
+                       drop_remainder=True, precision=None, device=None):
     """eval.py:29-215 `main`: the model of `model_dir` (train-params.txt + checkpoint, restored by name) over the per-video
     folders of the dataset directory (`db_dir`, default the one recorded in train-params.txt) restricted to `subset_fn`, with
     the eval schedule and the channel masks of `audio_layouts_fn`; writes `<model_dir>/eval-detailed.txt` (refusing to
-    overwrite it unless asked, eval.py:31-32) and returns (sample ids, rows (N, 28) CUDA).  The reference's queue drops the
-    last, short batch; here it is evaluated unless drop_remainder."""
+    overwrite it unless asked, eval.py:31-32) and returns (sample ids, rows (N, 28) CUDA).  Like the reference's queue, the
+    last, short batch is dropped (drop_remainder=False evaluates it too)."""
     import os
     from . import myutils, readers
     from .deploy import W2XYZ

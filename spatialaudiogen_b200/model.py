@@ -39,7 +39,7 @@ class SptAudioGenParams:
 class SptAudioGen(StageOps):
     """reference model.py:24-434.  (The per-stage methods audio_encoder_ops / visual_encoding_ops / bottleneck_ops /
     localization_ops / separation_ops live in stages.StageOps.)  Extra keyword arguments (not in the reference): `precision`
-    ('fp32' | 'tf32' | 'bf16' | 'bf16x3': arithmetic of the dense contractions), `device`, `frame_size`."""
+    ('fp32' | 'bf16' | 'bf16x3': arithmetic of the dense contractions), `device`, `frame_size`."""
 
     def __init__(self, ambi_order,
                  audio_rate=48000,
@@ -161,6 +161,8 @@ class SptAudioGen(StageOps):
                 self._w[name] = a
             L.check(lib.sag_finalize_weights(self._h, L.stream()))
         self._weights_ready = True
+        self._ws_batch = 0              # re-plan: the packed tensor-core images of reloaded layers are rebuilt in sag_workspace_bytes
+        self.__dict__.pop('_wd', None)
         return self
 
     def set_option(self, key, value):
@@ -183,12 +185,27 @@ class SptAudioGen(StageOps):
             self._ws_batch = B
         return self._ws
 
-    def forward_into(self, audio, video, flow, out):
-        """sag_forward on pre-staged contiguous float32 CUDA tensors (no allocation, no copies, no sync)."""
+    def forward_into(self, audio, video, flow, out, flow_limits=None):
+        """sag_forward on pre-staged contiguous CUDA tensors (no allocation, no copies, no sync).  audio / out are float32;
+        video / flow are either the float32 frames the reference's feeder prepares, or the uint8 frames as decoded from disk
+        (video: x/255 - 0.5 applied on the device, myutils.py:88-89; flow: de-quantised on the device with `flow_limits`, a
+        (B, 2) float64 CUDA tensor of the frames' (min, max) rows of flow_limits.npy, feeder.py:147-161)."""
         B = audio.shape[0]
         ws = self._workspace(B)
-        L.check(L.lib().sag_forward(self._h, L.ptr(audio), L.ptr(video), L.ptr(flow), L.ptr(out), C.c_void_p(ws.data_ptr()),
-                                    ws.numel(), B, L.stream()))
+        u8 = [t is not None and t.dtype == torch.uint8 for t in (video, flow)]
+        for t in (audio, out) + tuple(x for x, q in zip((video, flow), u8) if x is not None and not q):
+            if t.dtype != torch.float32:
+                raise TypeError('expected float32 (or uint8 frames), got %s' % t.dtype)
+        if not any(u8):
+            L.check(L.lib().sag_forward(self._h, L.ptr(audio), L.ptr(video), L.ptr(flow), L.ptr(out), C.c_void_p(ws.data_ptr()),
+                                        ws.numel(), B, L.stream()))
+            return out
+        if u8[1]:
+            if flow_limits is None or flow_limits.dtype != torch.float64 or tuple(flow_limits.shape) != (B, 2):
+                raise ValueError('uint8 flow frames need flow_limits: a (B, 2) float64 CUDA tensor')
+        L.check(L.lib().sag_forward_frames(self._h, L.ptr(audio), L.ptr(video), int(u8[0]), L.ptr(flow), int(u8[1]),
+                                           L.ptr(flow_limits) if u8[1] else None, L.ptr(out), C.c_void_p(ws.data_ptr()), ws.numel(), B,
+                                           L.stream()))
         return out
 
     def inference_ops(self, audio, video=None, flow=None, is_training=True):
@@ -233,7 +250,8 @@ class SptAudioGen(StageOps):
         """The driver loop around `sess.run` (reference deploy.py:112-148, eval.py:140-201) as a generator: `batches`
         yields dicts of HOST tensors {'audio': (B, snd_size, 1)[, 'video', 'flow': (B, 1, H, W, 3)]} (pinned memory
         makes the copies asynchronous); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
-        `depth` steps) is yielded in order.  Host->device copies of step i+1 and the device->host copy of step i-1 run
+        `depth` steps) is yielded in order.  'video' / 'flow' may be the uint8 frames as decoded from disk (a quarter of the
+        PCIe bytes; they are prepared on the device, see forward_into) -- uint8 flow comes with 'flow_limits' (B, 2) float64.  Host->device copies of step i+1 and the device->host copy of step i-1 run
         on their own streams while step i computes, so the PCIe transfers hide behind the forward."""
         if not self._weights_ready:
             raise RuntimeError('load_weights() must be called before inference_stream()')
@@ -247,8 +265,11 @@ class SptAudioGen(StageOps):
             pending = []                                   # (slot index) in flight, oldest first
 
             def make_slot(b):
-                sl = {'in': {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in b.items()
-                             if k in (AUDIO, VIDEO, FLOW)},
+                def _dt(k, v):
+                    v = torch.as_tensor(v)
+                    return v.dtype if (k == 'flow_limits' or (k in (VIDEO, FLOW) and v.dtype == torch.uint8)) else torch.float32
+                sl = {'in': {k: torch.empty(tuple(torch.as_tensor(v).shape), dtype=_dt(k, v), device=dev) for k, v in b.items()
+                             if k in (AUDIO, VIDEO, FLOW, 'flow_limits')},
                       'out': torch.empty((b[AUDIO].shape[0], self.snd_dur, 3), dtype=torch.float32, device=dev),
                       'host': torch.empty((b[AUDIO].shape[0], self.snd_dur, 3), dtype=torch.float32).pin_memory(),
                       'in_ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'out_ready': torch.cuda.Event(),
@@ -277,7 +298,7 @@ class SptAudioGen(StageOps):
                         t.copy_(torch.as_tensor(b[k]), non_blocking=True)
                     sl['in_ready'].record(side)
                 main.wait_event(sl['in_ready'])
-                self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'])
+                self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'], sl['in'].get('flow_limits'))
                 sl['done'].record(main)
                 sl['free'].record(main)
                 with torch.cuda.stream(back):
@@ -363,5 +384,8 @@ class SptAudioGen(StageOps):
         return metrics, stft_ps, lsd_ps, mse_ps, snr_ps
 
     def loss_ops(self, metrics_t, step_t=None):
-        """reference model.py:156-159: the training loss is the STFT distance (training itself is out of scope)."""
-        return metrics_t['stft/avg']
+        """reference model.py:156-159: the training losses, keyed like the reference's OrderedDict -- the STFT distance
+        (training itself is out of scope; this only keeps code that reads `losses['stft/mse']` working)."""
+        losses = OrderedDict()
+        losses['stft/mse'] = metrics_t['stft/avg']
+        return losses

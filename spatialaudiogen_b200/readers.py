@@ -110,6 +110,23 @@ class VideoReader(object):
         return chunk
 
 
+def dequantize_flow(chunk_u8, limits):
+    """feeder.py:147-161 on (T, H, W, 3) uint8 frames (channel 0 = angle, 2 = magnitude) with their (T, 2) (min, max) rows of
+    flow_limits.npy -> float32 (mag cos, mag sin, mag).  (The device does the same inside the frame-ingest kernel.)"""
+    chunk = np.asarray(chunk_u8).astype(np.float32)
+    lead = chunk.shape[:-3]
+    chunk = chunk.reshape((-1,) + chunk.shape[-3:])
+    limits = np.asarray(limits).reshape(-1, 2)
+    m_min = limits[:, 0].reshape((-1, 1, 1))
+    m_max = limits[:, 1].reshape((-1, 1, 1))
+    chunk[:, :, :, 2] *= (m_max - m_min) / 255.              # magnitude back to its range
+    chunk[:, :, :, 2] += m_min
+    chunk[:, :, :, 0] *= (2 * np.pi) / 255.                  # angle
+    chunk[:, :, :, 1] = chunk[:, :, :, 2] * np.sin(chunk[:, :, :, 0])
+    chunk[:, :, :, 0] = chunk[:, :, :, 2] * np.cos(chunk[:, :, :, 0])
+    return chunk.reshape(lead + chunk.shape[-3:])
+
+
 class FlowReader(object):
     """feeder.py:138-161."""
     def __init__(self, flow_dir, flow_lims_fn, rate=None, flow_prep=None):
@@ -120,17 +137,9 @@ class FlowReader(object):
         self.flow_prep = flow_prep if flow_prep is not None else lambda x: x
 
     def get_by_index(self, start_time, size, rotation=None):
-        chunk = self.reader.get_by_index(start_time, size, rotation).astype(np.float32)
+        chunk = self.reader.get_by_index(start_time, size, rotation)
         ss = max(int(start_time * self.rate), 0)
-        t = chunk.shape[0]
-        m_min = self.lims[ss:ss + t, 0].reshape((-1, 1, 1))
-        m_max = self.lims[ss:ss + t, 1].reshape((-1, 1, 1))
-        chunk[:, :, :, 2] *= (m_max - m_min) / 255.              # magnitude back to its range
-        chunk[:, :, :, 2] += m_min
-        chunk[:, :, :, 0] *= (2 * np.pi) / 255.                  # angle
-        chunk[:, :, :, 1] = chunk[:, :, :, 2] * np.sin(chunk[:, :, :, 0])
-        chunk[:, :, :, 0] = chunk[:, :, :, 2] * np.cos(chunk[:, :, :, 0])
-        return chunk
+        return dequantize_flow(chunk, self.lims[ss:ss + chunk.shape[0]])
 
 
 def sample_folders(directory, subset_fn=None):

@@ -117,3 +117,50 @@ def test_reference_batch_sizes_bf16x3(B):
     m.forward_into(cu(a), cu(v), None, out)
     assert _rel(out, yr) < 1e-3
     assert _rel(m.inference_ops(cu(a), video=cu(v)), yr) < 1e-3
+
+
+def test_uint8_frames_are_bit_identical_to_prepared_float_frames():
+    """sag_forward_frames: the frames as decoded from disk (uint8), prepared by the ingest kernel, against sag_forward on the
+    frames the reference's feeder prepares on the host -- video x/255 - 0.5 (myutils.py:88-89) must be bit-identical; the
+    de-quantised flow (feeder.py:147-161) agrees to the float32 sin/cos of the two math libraries."""
+    from spatialaudiogen_b200 import readers as R
+    B = 4
+    rng = np.random.RandomState(5)
+    enc = ['audio', 'video', 'flow']
+    _, m = _pair(enc, 31, 'bf16x3', stress=True)
+    a = cu(_audio(B, 120))
+    vu = rng.randint(0, 256, size=(B, 1, 224, 448, 3)).astype(np.uint8)
+    fu = rng.randint(0, 256, size=(B, 1, 224, 448, 3)).astype(np.uint8)
+    lims = np.stack([rng.uniform(0, 1, B), rng.uniform(5, 25, B)], 1)
+    vf = (vu / 255. - 0.5).astype(np.float32)
+    ff = R.dequantize_flow(fu, lims)
+    y_f = torch.empty((B, 4800, 3), device='cuda')
+    y_u = torch.empty((B, 4800, 3), device='cuda')
+    m.forward_into(a, cu(vf), cu(ff), y_f)
+    m.forward_into(a, cu(vu), cu(ff), y_u)                       # uint8 video, prepared float flow
+    assert torch.equal(y_f, y_u)
+    m.forward_into(a, cu(vu), cu(fu), y_u, cu(lims))             # both uint8
+    assert _rel(y_u, y_f) < 1e-4
+    m.set_option('precision', 'fp32')                            # the exact-fp32 path prepares the frames in a kernel of its own
+    m.forward_into(a, cu(vf), cu(ff), y_f)
+    m.forward_into(a, cu(vu), cu(ff), y_u)
+    assert _rel(y_u, y_f) < 1e-5                                 # same frames bit for bit; the FFMA path's statistics use atomics
+    with pytest.raises(ValueError):
+        m.forward_into(a, cu(vu), cu(fu), y_u)                   # quantised flow without its limits
+
+
+def test_forward_fails_loudly_without_the_batch_plan():
+    """sag_forward never allocates: the tensor-core weight images are built by sag_workspace_bytes(h, batch); calling the
+    forward for a batch size that was not planned is an error, not a silent allocation."""
+    from spatialaudiogen_b200 import _lib as L
+    _, m = _pair(['audio'], 3, 'bf16x3', stress=False)
+    a = cu(_audio(2, 1))
+    out = torch.empty((2, 4800, 3), device='cuda')
+    m.forward_into(a, None, None, out)                           # plans B=2 through _workspace()
+    a5 = cu(_audio(40, 2))                                        # another tile plan (M = 40 * ...): never planned
+    out5 = torch.empty((40, 4800, 3), device='cuda')
+    ws = torch.empty(4 << 30, dtype=torch.uint8, device='cuda')
+    rc = L.lib().sag_forward(m._h, L.ptr(a5), None, None, L.ptr(out5), C.c_void_p(ws.data_ptr()), ws.numel(), 40, L.stream())
+    assert rc == L.SAG_ESTATE and b'sag_workspace_bytes' in L.lib().sag_last_error()
+    m.forward_into(a5, None, None, out5)                         # the façade plans it, then it runs
+    torch.cuda.synchronize()

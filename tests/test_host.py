@@ -167,7 +167,7 @@ def test_evaluate_model_dir_wiring(tmp_path, monkeypatch):
             self.model = type('M', (), {'device': 'cpu'})()
             seen['model_dir'] = model_dir
 
-    def fake_folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=False):
+    def fake_folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True):
         seen.update(folders=folders, masks=channel_masks, batch_size=batch_size, drop=drop_remainder)
         return iter([])
 

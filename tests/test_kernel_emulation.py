@@ -38,6 +38,8 @@ struct ActView { void* p = nullptr; int fmt = ACT_F32; int64_t plane = 0; };
 struct BnStats { const double* sum = nullptr; const double* sqs = nullptr; const float* gamma = nullptr; const float* beta = nullptr;
                  double inv_count = 0.0; float eps = 1e-3f; };
 static float s_ss[16384];
+enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2 };
+static void emu_fill_lut(float* lut);
 // the block prologue (bn_scale_shift_to_smem) needs a barrier: here every emulated thread fills the whole table itself
 static void emu_scale_shift(const BnStats& bn, int c, float* s_scale, float* s_shift) {
   for (int i = 0; i < c; ++i) {
@@ -74,13 +76,22 @@ extern "C" void emu_maxpool(const float* x, const double* sum, const double* sqs
     bn_relu_maxpool_stats_kernel(x, mk(sum, sqs, g, be, inv), n, h, w, c, oh, ow, pt, pl, view(y, y_fmt, y_plane));
   });
 }
-extern "C" void emu_s2d(const float* x, int n, int h, int w, int c, int pt, int pl, int h2, int w2, void* y, int y_fmt, int64_t y_plane,
-                        int grid, int block) {
+// the block-wide table fill of the kernel (one entry per thread, then a barrier): here one emulated thread fills it all
+static void emu_fill_lut(float* lut) {
+  const Dim t = threadIdx, b = blockDim;
+  threadIdx.x = 0; blockDim.x = 1;
+  frame_lut_to_smem(lut);
+  threadIdx = t; blockDim = b;
+}
+extern "C" void emu_s2d(const void* x, const double* lims, int kind, int n, int h, int w, int c, int pt, int pl, int h2, int w2, void* y,
+                        int y_fmt, int64_t y_plane, int grid, int block) {
   for_each_thread(grid, block, [&] {
-    if (c == 1) space_to_depth16_kernel<1>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
-    else if (c == 2) space_to_depth16_kernel<2>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
-    else if (c == 3) space_to_depth16_kernel<3>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
-    else space_to_depth16_kernel<4>(x, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    if (kind == FRAMES_U8_VIDEO) space_to_depth16_kernel<3, FRAMES_U8_VIDEO>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (kind == FRAMES_U8_FLOW) space_to_depth16_kernel<3, FRAMES_U8_FLOW>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (c == 1) space_to_depth16_kernel<1, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (c == 2) space_to_depth16_kernel<2, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (c == 3) space_to_depth16_kernel<3, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else space_to_depth16_kernel<4, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
   });
 }
 '''
@@ -96,7 +107,9 @@ def _host_source():
     parts = [_cut(t, '__device__ __forceinline__ void store_act4(', 'static int g_num_sms'),
              _cut(t, 'constexpr int BN_UNROLL', 'int launch_bn_apply_stats('),
              _cut(t, '__global__ void __launch_bounds__(256, 4) bn_relu_maxpool_stats_kernel(', 'int launch_bn_relu_maxpool_stats('),
-             _cut(t, 'template <int C>\n__global__ void space_to_depth16_kernel(', 'int launch_space_to_depth16(')]
+             _cut(t, 'template <int C, int KIND>\n__device__ __forceinline__ void load_frame_pixel(', 'template <int C>\nstatic void launch_s2d_kind(')
+             .replace('__syncthreads();', '').replace('__shared__ float s_lut[256];', 'static float s_lut[256];')
+             .replace('frame_lut_to_smem(s_lut);', 'emu_fill_lut(s_lut);')]
     body = '\n'.join(parts)
     body = re.sub(r'__global__\s+void\s+(__launch_bounds__\([^)]*\)\s*)?', 'static void ', body)
     body = body.replace('__device__ __forceinline__', 'static inline').replace('extern __shared__ float s_ss[];', '')
@@ -226,9 +239,46 @@ def test_space_to_depth16_thread_code(emu, n, h, w, c, pt, pl, grid, block, y_fm
         want[..., sub * c:(sub + 1) * c] = big[:, (sub >> 1):(sub >> 1) + 2 * h2:2, (sub & 1):(sub & 1) + 2 * w2:2][:, :h2, :w2]
     m = n * h2 * w2 * 16
     y = np.full(m, np.nan, np.float32) if y_fmt == 0 else np.full(2 * m, 0xffff, np.uint16)
-    emu.emu_s2d(_p(x), n, h, w, c, pt, pl, h2, w2, _p(y), y_fmt, C.c_int64(2 * m if y_fmt else 0), grid, block)
+    emu.emu_s2d(_p(x), None, 0, n, h, w, c, pt, pl, h2, w2, _p(y), y_fmt, C.c_int64(2 * m if y_fmt else 0), grid, block)
     if y_fmt == 0:
         assert np.array_equal(y.reshape(want.shape), want)
     else:
         hi, lo = _planes_to_f32(y, m)
         assert np.allclose((hi + lo).reshape(want.shape), want, rtol=2e-5, atol=0) and np.array_equal((hi + lo).reshape(want.shape) == 0, want == 0)
+
+
+@pytest.mark.parametrize('kind', [1, 2])
+def test_uint8_frame_ingest_thread_code(emu, kind):
+    """The uint8 frame sources of the ingest kernel against the reference's host preparation written out in numpy:
+    video = img_prep_fcn (myutils.py:88-89: x/255. - 0.5 in float64, rounded to float32 when fed) -- bit-exact;
+    flow = FlowReader.get_by_index (feeder.py:147-161) on a float32 chunk with float64 limits -- to float32 sin/cos accuracy."""
+    rng = np.random.RandomState(kind)
+    n, h, w, c, pt, pl = 2, 6, 10, 3, 2, 2
+    u = rng.randint(0, 256, size=(n, h, w, c)).astype(np.uint8)
+    u[0, 0, 0] = (0, 0, 0)
+    u[0, 0, 1] = (255, 255, 255)
+    lims = np.stack([rng.uniform(0, 2, n), rng.uniform(5, 30, n)], 1).astype(np.float64)
+    if kind == 1:
+        x = (u / 255. - 0.5).astype(np.float32)
+    else:
+        chunk = u.astype(np.float32)
+        m_min, m_max = lims[:, 0].reshape((-1, 1, 1)), lims[:, 1].reshape((-1, 1, 1))
+        chunk[:, :, :, 2] *= (m_max - m_min) / 255.
+        chunk[:, :, :, 2] += m_min
+        chunk[:, :, :, 0] *= (2 * np.pi) / 255.
+        chunk[:, :, :, 1] = chunk[:, :, :, 2] * np.sin(chunk[:, :, :, 0])
+        chunk[:, :, :, 0] = chunk[:, :, :, 2] * np.cos(chunk[:, :, :, 0])
+        x = chunk
+    h2, w2 = (h + pt + 3) // 2 + 1, (w + pl + 3) // 2 + 1
+    big = np.zeros((n, 2 * h2 + 2, 2 * w2 + 2, c), np.float32)
+    big[:, pt:pt + h, pl:pl + w] = x
+    want = np.zeros((n, h2, w2, 16), np.float32)
+    for sub in range(4):
+        want[..., sub * c:(sub + 1) * c] = big[:, (sub >> 1):(sub >> 1) + 2 * h2:2, (sub & 1):(sub & 1) + 2 * w2:2][:, :h2, :w2]
+    y = np.full(n * h2 * w2 * 16, np.nan, np.float32)
+    emu.emu_s2d(_p(u), _p(lims), kind, n, h, w, c, pt, pl, h2, w2, _p(y), 0, C.c_int64(0), 3, 16)
+    if kind == 1:
+        assert np.array_equal(y.reshape(want.shape), want)
+    else:
+        assert np.allclose(y.reshape(want.shape), want, rtol=2e-6, atol=2e-6)
+        assert np.array_equal(y.reshape(want.shape)[..., 2::3][..., :4], want[..., 2::3][..., :4])      # magnitudes: exact
