@@ -407,9 +407,9 @@ int sag_batchnorm_train(const float* x, int64_t rows, int c, const float* gamma,
   SAG_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr && y != nullptr && scratch != nullptr, SAG_EINVAL, "sag_batchnorm_train: NULL argument");
   SAG_REQUIRE(rows > 0 && c > 0, SAG_EINVAL, "sag_batchnorm_train: bad dims");
   cudaStream_t st = as_stream(stream);
-  double* sum = reinterpret_cast<double*>(scratch);
-  double* sqs = sum + c;
-  SAG_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(double) * 2 * c, st));
+  unsigned long long* sum = reinterpret_cast<unsigned long long*>(scratch);      // [c][2] + [c][2] fixed-point words = 4*c*8 bytes
+  unsigned long long* sqs = sum + 2 * c;
+  SAG_CHECK_CUDA(cudaMemsetAsync(sum, 0, sizeof(unsigned long long) * 4 * c, st));
   SAG_TRY(launch_channel_stats(x, rows, c, sum, sqs, st));
   BnStats bn;
   bn.sum = sum; bn.sqs = sqs; bn.gamma = gamma; bn.beta = beta;

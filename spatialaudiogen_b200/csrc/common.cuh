@@ -118,11 +118,30 @@ struct GatherGeom {
 struct Epilogue {
   const float* bias;      // [Cout] or null
   int relu;
-  double* stat_sum;       // [Cout] batch-norm statistics (sum, sum of squares over the rows) or null.  FFMA path: accumulated
-  double* stat_sqs;       // with atomics into zeroed buffers; tcgen05 path: written once, summed in a fixed order
-  void* stat_ws;          // tcgen05 path: umma_stat_ws_bytes() of scratch for that fixed-order reduction; its first 512 bytes
-                          // (arrival counters) must be zero before the first launch that uses it -- launches leave them zero
+  // batch-norm statistics (sum, sum of squares over the rows) or null: [Cout][2] fixed-point accumulators (fx_atomic_add),
+  // zeroed by the caller, accumulated with integer atomics -- exact, hence independent of the arrival order of the CTAs
+  unsigned long long* stat_sum;
+  unsigned long long* stat_sqs;
 };
+
+// Exact fixed-point accumulation of float partial sums: word 0 = integer part (two's complement), word 1 = fraction * 2^40.
+// A float at or above 2^-17 in magnitude is represented exactly (24-bit mantissa), smaller ones are truncated to the 2^-40 grid;
+// integer addition is associative, so the total does not depend on the order in which CTAs arrive.  Up to 2^12 partials
+// (fraction word stays below 2^52), partial sums below 2^62.
+#ifdef __CUDACC__
+__device__ __forceinline__ void fx_atomic_add(unsigned long long* acc2, float p) {
+  const double d = (double)p;
+  const double fl = floor(d);
+  atomicAdd(acc2, (unsigned long long)(long long)fl);
+  atomicAdd(acc2 + 1, (unsigned long long)((d - fl) * 1099511627776.0));
+}
+#endif
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline double fx_value(const unsigned long long* acc2) {
+  return (double)(long long)acc2[0] + (double)acc2[1] * (1.0 / 1099511627776.0);
+}
 
 // TF 'SAME' padding (asymmetric): returns pad_before; out = ceil(in/s)
 static inline int same_pad_before(int in, int k, int s, int* out) {
@@ -151,6 +170,10 @@ struct UmmaWeights {
   float* col_bias = nullptr;
   int vec4 = 0;
   int64_t M_hint = 0;   // row count the tile width was chosen for
+  // tiled tensor map of the packed image (rows of 128 bytes, boxes of BN/2 rows) for the CTA-pair kernel, which fetches its
+  // weight blocks with .cta_group::2 tensor copies (a CUtensorMap, kept opaque here); wmap_ok == 0: not available
+  alignas(64) unsigned char wmap[128] = {0};
+  int wmap_ok = 0;
 };
 void umma_free(UmmaWeights* w);
 // tile width of a contraction with N columns over M rows (a single M tile takes narrow tiles: see conv_umma.cu)
@@ -180,8 +203,6 @@ extern thread_local int g_umma_pair;  // -1: SAG_UMMA_PAIR env (default off); 0/
 extern thread_local int g_umma_tma;   // -1: SAG_UMMA_TMA env (default on); 0/1: forced for this thread's launches
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
-// bytes of Epilogue::stat_ws a contraction of this shape needs for its batch-norm statistics
-size_t umma_stat_ws_bytes(int K, int N, int64_t M);
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st);
 
@@ -204,8 +225,8 @@ int make_deconv_subpixel_geom(GatherGeom* g, int n, int h, int w, int cin, int64
 // scale / shift in their prologue (no separate finalize launch).  scale = gamma*rsqrt(var+eps), shift = beta - mean*scale,
 // biased variance (contrib batch_norm, core.py:209-210).
 struct BnStats {
-  const double* sum = nullptr;
-  const double* sqs = nullptr;
+  const unsigned long long* sum = nullptr;      // [C][2] fixed-point sums (fx_atomic_add / fx_value)
+  const unsigned long long* sqs = nullptr;
   const float* gamma = nullptr;
   const float* beta = nullptr;
   double inv_count = 0.0;
@@ -216,7 +237,7 @@ int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& resi
 int launch_bn_relu_maxpool_stats(const float* x, const BnStats& bn, int n, int h, int w, int c, const ActView& y, cudaStream_t st);
 int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shift, int n, int h, int w, int c,
                            const ActView& y, cudaStream_t st);   // 3x3/2 SAME; scale==null -> plain max-pool
-int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st);
+int launch_channel_stats(const float* x, int64_t rows, int c, unsigned long long* sum, unsigned long long* sqs, cudaStream_t st);
 int launch_tile_rows(const ActView& src, int64_t src_ld, const ActView& dst, int64_t dst_ld, int groups, int reps, int c,
                      cudaStream_t st);   // dst[(g*reps+r)*dst_ld + :c] = src[g*src_ld + :c]
 int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int t, int segments, float* out,

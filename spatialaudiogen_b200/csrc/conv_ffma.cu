@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(NTHREADS) gather_gemm_ffma_kernel(const float*
     __syncthreads();
     for (int c = tid; c < BN; c += NTHREADS) {
       if (co0 + c < g.Cout) {
-        atomicAdd(ep.stat_sum + co0 + c, (double)s_sum[c]);
-        atomicAdd(ep.stat_sqs + co0 + c, (double)s_sqs[c]);
+        fx_atomic_add(ep.stat_sum + 2 * (co0 + c), s_sum[c]);
+        fx_atomic_add(ep.stat_sqs + 2 * (co0 + c), s_sqs[c]);
       }
     }
   }

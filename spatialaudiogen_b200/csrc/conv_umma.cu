@@ -57,8 +57,8 @@ struct UmmaArgs {
   int out_bf2;
   const float* bias;      // indexed by GEMM column (already expanded for mapped outputs) or null
   int relu;
-  double* stat_sum;
-  double* stat_sqs;
+  unsigned long long* stat_sum;      // fixed-point accumulators, two words per column (fx_atomic_add)
+  unsigned long long* stat_sqs;
   const int* col_off;     // mapped output (sub-pixel transposed conv): element offset per column, or null
   const short* col_dy;
   const short* col_dx;
@@ -74,14 +74,11 @@ struct UmmaArgs {
   int NT, Z;              // N tiles, K splits
   int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
-  // cross-CTA batch-norm sums in a fixed order (stat_reduce below): per-CTA partials, per-group partials, arrival counters
-  float* st_part;
-  double* st_gpart;
-  unsigned* st_cnt;
-  int st_gs;              // CTAs per group
+  int pair_ok;            // host: the tiled weight map exists (CTA pairs fetch their weight blocks through it)
 };
-// im2col tensor maps of the two activation planes (SRC_TMA); kernel parameter, read by the TMA unit
-struct alignas(64) TmaPair { CUtensorMap hi, lo; };
+// im2col tensor maps of the two activation planes (SRC_TMA) + the tiled map of the packed weight image (CTA pairs: 128-byte
+// rows, boxes of BN/2 rows); kernel parameter, read by the TMA unit
+struct alignas(64) TmaPair { CUtensorMap hi, lo, w; };
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,6 +129,29 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst_smem, const CUtensorM
       "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
+}
+// CTA-pair variants (.cta_group::2): the copy lands in the executing CTA's shared memory, its bytes complete on an mbarrier
+// that may live in the peer CTA (the pair leader's full barrier): no relay between the CTAs
+__device__ __forceinline__ void tma_im2col_4d_2sm(uint32_t dst_smem, const CUtensorMap* tmap, int c, int w, int h, int n,
+                                                  uint32_t bar_cluster, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d_2sm(uint32_t dst_smem, const CUtensorMap* tmap, int x, int y, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {      // same offset in CTA `rank` of the cluster
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -275,48 +295,6 @@ __device__ __forceinline__ void store_bf2_4(void* yhi, int64_t plane, int64_t e,
   if (planes == 2) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(yhi) + plane) + e) = lo;
 }
 
-// ---- cross-CTA column sums in a fixed order (run-to-run bit-reproducible batch-norm statistics) ---------------------
-// Every CTA of the grid calls this once, with all its threads, after its own sums s_sum / s_sqs[0..n) (shared memory, folded in
-// a fixed order) are complete.  It publishes them as partials[cta][2n]; the LAST CTA to arrive in each group of `gs`
-// consecutive CTAs adds the group's partials in CTA order (double), the last group to finish adds the group sums in group
-// order and writes out_sum / out_sqs.  Which CTA does the adding depends on timing, what is added in which order does not.
-// counters[0] = groups done, counters[1 + g] = CTAs of group g done; all zero on entry, reset to zero on exit.
-__device__ __forceinline__ void stat_reduce(float* __restrict__ partials, double* __restrict__ gpart, unsigned* __restrict__ counters, int gs,
-                                            int cta, int n_ctas, const float* s_sum, const float* s_sqs, int n, double* __restrict__ out_sum,
-                                            double* __restrict__ out_sqs) {
-  __shared__ int s_last;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int n2 = 2 * n;
-  float* mine = partials + (size_t)cta * n2;
-  for (int i = tid; i < n; i += nthr) { mine[i] = s_sum[i]; mine[n + i] = s_sqs[i]; }
-  __threadfence();
-  __syncthreads();
-  const int grp = cta / gs, n_groups = (n_ctas + gs - 1) / gs;
-  const int g0 = grp * gs, g1 = min(g0 + gs, n_ctas);
-  if (tid == 0) s_last = (atomicAdd(counters + 1 + grp, 1u) == (unsigned)(g1 - g0 - 1)) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < n2; i += nthr) {
-    double acc = 0.0;
-    for (int c = g0; c < g1; ++c) acc += (double)__ldcg(partials + (size_t)c * n2 + i);
-    gpart[(size_t)grp * n2 + i] = acc;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(counters, 1u) == (unsigned)(n_groups - 1)) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = tid; i < n2; i += nthr) {
-    double acc = 0.0;
-    for (int g = 0; g < n_groups; ++g) acc += __ldcg(gpart + (size_t)g * n2 + i);
-    if (i < n) out_sum[i] = acc;
-    else out_sqs[i - n] = acc;
-  }
-  for (int i = tid; i <= n_groups; i += nthr) counters[i] = 0u;      // ready for the next launch on this stream
-}
-
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // SRC: 0 = fp32 activations, element-wise gather; 1 = fp32, every 8-element K group lies inside one tap and is
 // contiguous + 16-byte aligned (Cin % 8 == 0): vector gather; 2 = split-bf16 planes, same alignment rule: cp.async gather.
@@ -362,7 +340,6 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES;
   const uint32_t bar_tfull = bars + 16 * UM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t bar_pfull = bars + 16 * UM_MAX_STAGES + 48;  // pair leader: the peer CTA's operands of stage s have landed
   const uint32_t stile = (bars + UM_BAR_BYTES + 15u) & ~15u;                 // epilogue staging tile (128 x 144 B)
   const uint32_t tiles = (stile + UM_STAGING_BYTES + 1023u) & ~1023u;        // operand stage ring
   const int S = a.stages;
@@ -383,14 +360,13 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         // every producer thread + the expect_tx arrival of the B copy; TMA gather: the expect_tx arrival alone
-        mbar_init(bar_full + 8 * s, TMA_ANY ? 1 : UM_PRODUCER_WARPS * 32 + 1);
+        mbar_init(bar_full + 8 * s, TMA_ANY ? (PAIR ? 2 : 1) : UM_PRODUCER_WARPS * 32 + 1);   // pair: the producers of both CTAs
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(bar_tfull + 8 * b, 1);                       // one tcgen05.commit per tile
         mbar_init(bar_tempty + 8 * b, PAIR ? 2 * EW : EW);     // the epilogue warps (of both CTAs) have drained the accumulator
       }
-      for (int s = 0; s < S; ++s) mbar_init(bar_pfull + 8 * s, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -423,6 +399,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       int stage = 0;
       uint32_t phase = 0;
       long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
+      const uint32_t lead_full = PAIR ? map_to_cta(bar_full, 0) : bar_full;      // the pair leader's full barriers (cluster address)
       for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
         int mt, nt, z;
         decode_work(wk, mt, nt, z);
@@ -441,25 +418,36 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           if (elect_one()) {
             const int kk = kc * UM_BK;
             const uint32_t st_base = tiles + (uint32_t)stage * STAGE_BYTES;
-            const uint32_t bar = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(bar, PLANES * UM_A_PLANE + B_BYTES);
-            {
-              const int t = kk / g.Cin;
-              const int ci0 = kk - t * g.Cin;
-              const uint16_t ow = (uint16_t)(g.dx[t] - a.tma_w0), oh = (uint16_t)(g.dy[t] - a.tma_h0);
-              tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
-              if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
-            }
-            const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
+            const int t = kk / g.Cin;
+            const int ci0 = kk - t * g.Cin;
+            const uint16_t ow = (uint16_t)(g.dx[t] - a.tma_w0), oh = (uint16_t)(g.dy[t] - a.tma_h0);
             const uint32_t bx = st_base + PLANES * UM_A_PLANE;
             if (!PAIR) {
+              const uint32_t bar = bar_full + 8 * stage;
+              mbar_arrive_expect_tx(bar, PLANES * UM_A_PLANE + B_BYTES);
+              tma_im2col_4d(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
+              if (PLANES == 2) tma_im2col_4d(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
+              const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
               bulk_g2s(bx, wsrc, B_BYTES, bar);
-            } else if (NSPLIT == 2) {
-              bulk_g2s(bx, wsrc + crank * B_PLANE, BX_ROWS * 128, bar);                              // B_hi | B_lo
-              bulk_g2s(bx + BX_ROWS * 128, wsrc + crank * (BN / 2) * 128, BY_ROWS * 128, bar);        // my half of B_hi
             } else {
-              bulk_g2s(bx, wsrc + crank * (BN / 2) * 128, BX_ROWS * 128, bar);                       // my half of B_hi
-              if (PLANES == 2) bulk_g2s(bx + BX_ROWS * 128, wsrc + B_PLANE + crank * (BN / 2) * 128, BY_ROWS * 128, bar);
+              // CTA pair: this CTA's operands land in its own shared memory, their bytes complete on the LEADER's full barrier
+              // (one arrival + expected bytes from each CTA's producer) -- the leader's MMA warp waits on that barrier alone
+              const uint32_t bar = lead_full + 8 * stage;
+              mbar_arrive_expect_tx_cluster(bar, PLANES * UM_A_PLANE + B_BYTES);
+              tma_im2col_4d_2sm(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
+              if (PLANES == 2) tma_im2col_4d_2sm(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
+              // packed weight image as rows of 128 bytes: tile (nt, kc) starts at row (nt*KC + kc)*PLANES*BN; boxes of BN/2 rows
+              const int wrow = (nt * a.KC + kc) * (PLANES * BN);
+              constexpr int HB = BN / 2;
+              if (NSPLIT == 2) {
+                // block X = B_hi (rank 0) / B_lo (rank 1), block Y = my half of B_hi
+                tma_tile_2d_2sm(bx, &tm.w, 0, wrow + (int)crank * BN, bar);
+                tma_tile_2d_2sm(bx + HB * 128, &tm.w, 0, wrow + (int)crank * BN + HB, bar);
+                tma_tile_2d_2sm(bx + BX_ROWS * 128, &tm.w, 0, wrow + (int)crank * HB, bar);
+              } else {
+                tma_tile_2d_2sm(bx, &tm.w, 0, wrow + (int)crank * HB, bar);                              // my half of B_hi
+                if (PLANES == 2) tma_tile_2d_2sm(bx + BX_ROWS * 128, &tm.w, 0, wrow + BN + (int)crank * HB, bar);   // my half of B_lo
+              }
             }
           }
           __syncwarp();
@@ -470,21 +458,6 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 2] = tr_wait;
         a.trace[blockIdx.x * 16 + 3] = clock64() - tr_t0;
         a.trace[blockIdx.x * 16 + 6] = tr_chunks;
-      }
-    } else if (PAIR && warp == 1 && crank != 0) {
-      // relay (peer CTA of a pair): once this CTA's operands of a stage have landed, tell the leader's MMA warp
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
-        int mt, nt, z;
-        decode_work(wk, mt, nt, z);
-        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
-        for (int kc = kc_begin; kc < kc_end; ++kc) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          if (lane == 0) mbar_arrive_remote(bar_pfull + 8 * stage, 0);
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
-        }
       }
     }
   } else if (!TMA_ANY && warp < UM_PRODUCER_WARPS) {
@@ -633,7 +606,6 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         for (int kc = kc_begin; kc < kc_end; ++kc) {
           const long long tr_w0 = a.trace ? clock64() : 0;
           mbar_wait(bar_full + 8 * stage, phase);
-          if (PAIR) mbar_wait_cluster(bar_pfull + 8 * stage, phase);      // the peer's half of the operands
           if (a.trace) tr_wait += clock64() - tr_w0;
           if (SRC == SRC_BF2) fence_proxy_async();   // cp.async (generic proxy) writes observed through the barrier
           tc_fence_after();
@@ -934,7 +906,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (stats) stat_reduce(a.st_part, a.st_gpart, a.st_cnt, a.st_gs, (int)blockIdx.x, (int)gridDim.x, s_sum, s_sqs, a.Ntot, a.stat_sum, a.stat_sqs);
+  if (stats) {
+    // per-CTA sums (folded above in a fixed order) -> global, as exact fixed-point integer atomics: order-independent, so the
+    // statistics -- and everything downstream -- are bit-reproducible from run to run
+    for (int i = tid; i < a.Ntot; i += UM_THREADS) {
+      fx_atomic_add(a.stat_sum + 2 * i, s_sum[i]);
+      fx_atomic_add(a.stat_sqs + 2 * i, s_sqs[i]);
+    }
+  }
 }
 
 // ---- weight packing: Wk fp32 [K][N] (row stride ldw) -> per (N tile, K chunk) bf16 hi (+lo) planes in the swizzled
@@ -1118,7 +1097,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   }
   if (stats) {
     // block sums in a fixed order: every thread's register sums go to shared memory, thread c < ncg adds the 256/ncg
-    // contributors of column group c in thread order; then the cross-block reduction (stat_reduce), also in a fixed order
+    // contributors of column group c in thread order; across blocks: exact fixed-point atomics (order-independent)
     __shared__ float s_tp[256][8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { s_tp[threadIdx.x][e] = ssum[e]; s_tp[threadIdx.x][4 + e] = ssqs[e]; }
@@ -1134,7 +1113,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
         if ((int)threadIdx.x * 4 + e < a.Ntot) { s_sum[threadIdx.x * 4 + e] = ts[e]; s_sqs[threadIdx.x * 4 + e] = tq[e]; }
     }
     __syncthreads();
-    stat_reduce(a.st_part, a.st_gpart, a.st_cnt, a.st_gs, (int)blockIdx.x, (int)gridDim.x, s_sum, s_sqs, a.Ntot, a.stat_sum, a.stat_sqs);
+    for (int i = threadIdx.x; i < a.Ntot; i += blockDim.x) {
+      fx_atomic_add(a.stat_sum + 2 * i, s_sum[i]);
+      fx_atomic_add(a.stat_sqs + 2 * i, s_sqs[i]);
+    }
   }
 }
 
@@ -1154,11 +1136,10 @@ int num_sms() {
   return n;
 }
 
-int reduce_rows_per_block(int64_t M, bool stats) {
+int reduce_rows_per_block(int64_t M) {
   int64_t rpb = M / (2 * num_sms());              // rows per block: keep >= 2 blocks per SM, at most 16 rows
   if (rpb > 16) rpb = 16;
   if (rpb < 1) rpb = 1;
-  if (stats && cdiv64(M, rpb) > 4096) rpb = cdiv64(M, 4096);      // the reduction tree has 64 x 64 slots
   return (int)rpb;
 }
 int max_conv_ctas() {
@@ -1259,7 +1240,7 @@ int launch_ns(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt,
         // conv2_x 66 -> 90 us, conv1 130 -> 170 us on B200 (SAG_UMMA_PAIR=1 / sag_set_option "cta_pair").
         static const int pair_env = env_int("SAG_UMMA_PAIR", 0);
         const int64_t MT = cdiv64((int64_t)g.N * g.PH * g.PW, UM_BM);
-        if ((g_umma_pair < 0 ? pair_env : g_umma_pair) && MT >= 2) return launch_cfg<BN, NSPLIT, SRC_TMA, true>(g, a, tm, nt, Z, st);
+        if ((g_umma_pair < 0 ? pair_env : g_umma_pair) && MT >= 2 && a.pair_ok) return launch_cfg<BN, NSPLIT, SRC_TMA, true>(g, a, tm, nt, Z, st);
         return launch_cfg<BN, NSPLIT, SRC_TMA, false>(g, a, tm, nt, Z, st);
       } else {
         return launch_cfg<BN, NSPLIT, SRC_BF2, false>(g, a, tm, nt, Z, st);  // (the host never picks TMA for 32-wide tiles)
@@ -1354,6 +1335,38 @@ static TilePlan plan_tile(int K, int N, int64_t M) {
   return best;
 }
 
+// cuTensorMapEncodeTiled / cuTensorMapEncodeIm2col through the runtime's driver entry point lookup: libsag.so carries no
+// link-time dependency on libcuda.so (it must load -- and report "no device" -- on machines without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// the packed weight image as a 2-D bf16 tensor of 128-byte rows, fetched in boxes of BN/2 rows (no swizzle: the image is
+// already in the shared-memory layout)
+static void make_weight_map(UmmaWeights* w) {
+  static_assert(sizeof(CUtensorMap) == sizeof(w->wmap), "CUtensorMap size");
+  w->wmap_ok = 0;
+  const EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr || w->packed == nullptr || w->BN < 64) return;
+  const cuuint64_t rows = (cuuint64_t)w->NT * w->KC * w->planes * w->BN;
+  const cuuint64_t dims[2] = {64, rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)(w->BN / 2)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(w->wmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w->packed, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  w->wmap_ok = r == CUDA_SUCCESS ? 1 : 0;
+}
+
 void umma_free(UmmaWeights* w) {
   if (w->packed) cudaFree(w->packed);
   if (w->col_off) cudaFree(w->col_off);
@@ -1384,6 +1397,7 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
                                                               reinterpret_cast<uint8_t*>(w.packed));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(w.packed); set_error("umma_pack_weights: %s", cudaGetErrorString(e)); return SAG_ECUDA; }
+    make_weight_map(&w);
   }
   *out = w;
   return SAG_OK;
@@ -1509,20 +1523,6 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   return p.Z;
 }
 
-// ---- workspace of the fixed-order statistics reduction (stat_reduce): [128 counters | group sums | per-CTA partials] ----
-struct StatLayout { int bound, gs; size_t off_gpart, off_part, bytes; };
-static StatLayout stat_layout(int N, int64_t M, int Z) {
-  StatLayout l;
-  l.bound = Z > 1 ? (int)cdiv64(M, reduce_rows_per_block(M, true)) : max_conv_ctas();
-  l.gs = 1;
-  while (l.gs * l.gs < l.bound) ++l.gs;
-  l.off_gpart = 512;
-  l.off_part = l.off_gpart + (size_t)(l.gs + 2) * 2 * N * sizeof(double);
-  l.bytes = (l.off_part + (size_t)l.bound * 2 * N * sizeof(float) + 255) & ~(size_t)255;
-  return l;
-}
-size_t umma_stat_ws_bytes(int K, int N, int64_t M) { return stat_layout(N, M, plan_tile(K, N, M).Z).bytes; }
-
 thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
 thread_local int g_umma_pair = -1;  // -1: SAG_UMMA_PAIR (default off); 0 / 1: forced (sag_set_option "cta_pair")
 
@@ -1622,6 +1622,8 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   TmaPair tm;
   memset(&tm, 0, sizeof(tm));
+  memcpy(&tm.w, w.wmap, sizeof(tm.w));
+  a.pair_ok = w.wmap_ok;
   static const int tma_env = env_int("SAG_UMMA_TMA", 1);
   if (src == SRC_BF2 && w.BN >= 64 && (g_umma_tma < 0 ? tma_env : g_umma_tma) && make_im2col_maps(x, g, &tm, &a.tma_w0, &a.tma_h0))
     src = SRC_TMA;
@@ -1634,16 +1636,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;
   SAG_REQUIRE(w.KC >= 1, SAG_EINVAL, "tcgen05 path: empty contraction");
   SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);
-  if (ep.stat_sum != nullptr) {
-    SAG_REQUIRE(ep.stat_ws != nullptr, SAG_EINVAL, "tcgen05 path: statistics need Epilogue::stat_ws");
-    SAG_REQUIRE(Z == 1 || 256 % cdiv(w.N, 4) == 0, SAG_EUNSUPPORTED, "tcgen05 path: split-K statistics over %d columns", w.N);
-    const StatLayout l = stat_layout(w.N, M, Z);
-    char* base = reinterpret_cast<char*>(ep.stat_ws);
-    a.st_cnt = reinterpret_cast<unsigned*>(base);
-    a.st_gpart = reinterpret_cast<double*>(base + l.off_gpart);
-    a.st_part = reinterpret_cast<float*>(base + l.off_part);
-    a.st_gs = l.gs;
-  }
+  SAG_REQUIRE(ep.stat_sum == nullptr || Z == 1 || 256 % cdiv(w.N, 4) == 0, SAG_EUNSUPPORTED, "tcgen05 path: split-K statistics over %d columns", w.N);
   int r;
   switch (w.BN) {
     case 32: r = launch_bn<32>(g, a, tm, w.NT, w.planes, src, Z, st); break;
@@ -1654,7 +1647,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   }
   SAG_TRY(r);
   if (Z > 1) {
-    const int rpb = reduce_rows_per_block(M, ep.stat_sum != nullptr);
+    const int rpb = reduce_rows_per_block(M);
     launch_pdl(splitk_reduce_kernel, dim3((unsigned)cdiv64(M, rpb)), dim3(256), 0, st, g, a, Z, rpb);
     SAG_LAUNCH_CHECK();
   }

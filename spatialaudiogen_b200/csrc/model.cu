@@ -159,7 +159,6 @@ struct Fwd {
   cudaStream_t st;
   int prec;
   int cat = PROF_CONV;
-  void* stat_ws = nullptr;      // scratch of the fixed-order batch-norm statistics reduction (tcgen05 path)
   bool dry() const { return ar.dry; }
   bool tc() const { return prec != SAG_PREC_FP32; }
 
@@ -233,7 +232,7 @@ struct Fwd {
 
   // tfw.conv_2d (core.py:156-220) on an NHWC view: x has pixel stride x.ld, y has pixel stride y.ld.
   int conv(const Act& x, int n, int hh, int ww, int cin, const std::string& scope, int kh, int kw, int cout, int sh,
-           int sw, int same, bool bias, int relu, const Act& y, double* ssum, double* ssqs, int* oh, int* ow) {
+           int sw, int same, bool bias, int relu, const Act& y, unsigned long long* ssum, unsigned long long* ssqs, int* oh, int* ow) {
     GatherGeom g;
     SAG_TRY(make_conv_geom(&g, n, hh, ww, cin, x.ld, kh, kw, cout, sh, sw, same, y.ld, oh, ow));
     if (tc() && !same && x.ld == cin && cin < 8 && (kw * cin) % 8 == 0) {
@@ -255,7 +254,7 @@ struct Fwd {
       SAG_TRY(image(scope, Kg, cout, Mrows, [&](UmmaWeights* uw) { return umma_pack_weights(w, Kg, cout, cout, prec, Mrows, uw, st); }, &img));
     }
     if (dry()) return SAG_OK;
-    Epilogue ep{b, relu, ssum, ssqs, stat_ws};
+    Epilogue ep{b, relu, ssum, ssqs};
     const double M = (double)Mrows, K = (double)g.T * g.Cin;
     const double esz_in = x.v.fmt == ACT_BF2 ? (x.v.plane ? 4.0 : 2.0) : 4.0, esz_out = y.v.fmt == ACT_BF2 ? (y.v.plane ? 4.0 : 2.0) : 4.0;
     ProfScope ps(cat, 2.0 * M * K * cout, esz_in * (double)n * hh * ww * cin + 4.0 * K * cout + esz_out * M * cout, st, scope.c_str(), -1.0,
@@ -337,13 +336,14 @@ struct Fwd {
 };
 
 // contrib batch_norm(is_training=True) statistics -> per-channel scale/shift (core.py:209-210)
-struct BnBuf { double* sum; double* sqs; };
-// all statistics accumulators of a tower live in one block that is cleared with a single memset
-static BnBuf take_bn(double*& pool, int c) {
+struct BnBuf { unsigned long long* sum; unsigned long long* sqs; };
+// all statistics accumulators of a tower (two fixed-point words per channel and sum) live in one block that is cleared with
+// a single memset
+static BnBuf take_bn(unsigned long long*& pool, int c) {
   BnBuf b;
   b.sum = pool;
-  b.sqs = pool + c;
-  pool += 2 * c;
+  b.sqs = pool + 2 * c;
+  pool += 4 * c;
   return b;
 }
 
@@ -368,22 +368,8 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
   // statistics accumulators: conv1 (64) + two per block
   int64_t n_stat = 2 * 64;
   for (const BlockDef& b : kBlocks) n_stat += 4 * b.cout;
-  double* stat_pool = ar.alloc<double>(n_stat);
-  if (f.tc()) {
-    // tcgen05 path: every layer's sums are written once by a fixed-order reduction through this scratch (largest layer's need);
-    // only its arrival counters have to start at zero
-    size_t need = umma_stat_ws_bytes(256, 64, (int64_t)B * ((H + 1) / 2) * ((Wd + 1) / 2));
-    int hh = ((H + 1) / 2 + 1) / 2, ww = ((Wd + 1) / 2 + 1) / 2;
-    for (const BlockDef& b : kBlocks) {
-      if (b.first) { hh = (hh + 1) / 2; ww = (ww + 1) / 2; }
-      need = std::max(need, umma_stat_ws_bytes(9 * b.cin, b.cout, (int64_t)B * hh * ww));
-      need = std::max(need, umma_stat_ws_bytes(9 * b.cout, b.cout, (int64_t)B * hh * ww));
-    }
-    f.stat_ws = ar.alloc<char>((int64_t)need);
-    if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(f.stat_ws, 0, 512, st));
-  } else if (!ar.dry) {
-    SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(double) * n_stat, st));   // FFMA path accumulates with atomics
-  }
+  unsigned long long* stat_pool = ar.alloc<unsigned long long>(2 * n_stat);      // two fixed-point words per sum
+  if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(unsigned long long) * 2 * n_stat, st));
   const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;   // bytes per activation element
 
   // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
@@ -427,7 +413,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
           ProfScope ps(PROF_POINTWISE, 0, in_b * B * (double)H * Wd * 3 + act_b * B * (double)H2 * W2 * 16, st, "frame ingest (space-to-depth)");
           SAG_TRY(launch_space_to_depth16(xsrc, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
         }
-        Epilogue ep{nullptr, 0, b1.sum, b1.sqs, f.stat_ws};
+        Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
         ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)H2 * W2 * 16 + 4.0 * B * (double)oh * ow * 64, st,
                      (p + "conv1/conv").c_str(), 2.0 * B * oh * ow * 256.0 * 64, img->BN, 1);
         SAG_TRY(launch_gather_gemm_umma(xp.v, *img, c1.v, g, ep, 0, 0, scratch, st));

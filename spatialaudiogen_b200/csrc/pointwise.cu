@@ -52,8 +52,8 @@ static int num_sms() {
 //      scale = gamma*rsqrt(var+eps), shift = beta - mean*scale (biased variance); y = act(x*scale + shift [+ res])
 __device__ __forceinline__ void bn_scale_shift_to_smem(const BnStats& bn, int c, float* s_scale, float* s_shift) {
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const double mean = bn.sum[i] * bn.inv_count;
-    double var = bn.sqs[i] * bn.inv_count - mean * mean;
+    const double mean = fx_value(bn.sum + 2 * i) * bn.inv_count;
+    double var = fx_value(bn.sqs + 2 * i) * bn.inv_count - mean * mean;
     if (var < 0) var = 0;
     const double sc = (double)__ldg(bn.gamma + i) / sqrt(var + (double)bn.eps);
     s_scale[i] = (float)sc;
@@ -227,8 +227,8 @@ int launch_bn_relu_maxpool(const float* x, const float* scale, const float* shif
 
 // ---- per-channel sum / sum of squares over rows (stand-alone BN statistics) ----
 // block = 256 threads = 8 row lanes x 32 channel lanes(x4 via float4 when possible): generic scalar version
-__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t rows, int c, double* __restrict__ sum,
-                                     double* __restrict__ sqs) {
+__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t rows, int c, unsigned long long* __restrict__ sum,
+                                     unsigned long long* __restrict__ sqs) {
   // each block handles a contiguous slab of rows; thread t covers channels t, t+blockDim, ...
   int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -242,13 +242,13 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, int64_t rows, 
       q = fmaf(v, v, q);
     }
     if (r1 > r0) {
-      atomicAdd(sum + ch, (double)s);
-      atomicAdd(sqs + ch, (double)q);
+      fx_atomic_add(sum + 2 * ch, s);
+      fx_atomic_add(sqs + 2 * ch, q);
     }
   }
 }
 
-int launch_channel_stats(const float* x, int64_t rows, int c, double* sum, double* sqs, cudaStream_t st) {
+int launch_channel_stats(const float* x, int64_t rows, int c, unsigned long long* sum, unsigned long long* sqs, cudaStream_t st) {
   int threads = c >= 256 ? 256 : (c >= 128 ? 128 : (c >= 64 ? 64 : 32));
   int64_t blocks = cdiv64(rows, 64);
   int64_t cap = (int64_t)num_sms() * 8;
