@@ -169,6 +169,7 @@ struct UmmaWeights {
   short* col_dx = nullptr;
   float* col_bias = nullptr;
   int vec4 = 0;
+  int run8 = 0;         // mapped output: every group of 8 columns is 8 consecutive floats of one output row
   int64_t M_hint = 0;   // row count the tile width was chosen for
   // tiled tensor map of the packed image (rows of 128 bytes, boxes of BN/2 rows) for the CTA-pair kernel, which fetches its
   // weight blocks with .cta_group::2 tensor copies (a CUtensorMap, kept opaque here); wmap_ok == 0: not available

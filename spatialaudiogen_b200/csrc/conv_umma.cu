@@ -75,10 +75,15 @@ struct UmmaArgs {
   int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
   int pair_ok;            // host: the tiled weight map exists (CTA pairs fetch their weight blocks through it)
+  // how a staged 128 x 32 pass leaves the CTA: 0 = LSU copy-out (any output format / mapping); 1 = one TMA tensor store per
+  // pass (dense fp32 rows, or the split-K partials); 2 = bulk stores of contiguous 4 KB runs (sub-pixel transposed conv
+  // whose tile is one grid row: the 128 rows x 8 pixels of a column group are 1024 consecutive floats of the output)
+  int out_mode;
+  int64_t m_pad;          // rows of one split-K partial slab (M rounded up to whole tiles)
 };
 // im2col tensor maps of the two activation planes (SRC_TMA) + the tiled map of the packed weight image (CTA pairs: 128-byte
 // rows, boxes of BN/2 rows); kernel parameter, read by the TMA unit
-struct alignas(64) TmaPair { CUtensorMap hi, lo, w; };
+struct alignas(64) TmaPair { CUtensorMap hi, lo, w, o; };     // o: tiled map of the output (out_mode 1)
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -144,6 +149,45 @@ __device__ __forceinline__ void tma_tile_2d_2sm(uint32_t dst_smem, const CUtenso
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(x), "r"(y)
       : "memory");
+}
+// shared -> global through the TMA unit (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t src_smem, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Column sums over the 32 lanes of a warp of CPT values per lane (16 or 32): butterfly that halves the live values per
+// step, so CPT + (CPT == 16) shuffles instead of 5*CPT.  Returns the total of column ((lane >> 1) & 15) [CPT 16] /
+// column lane [CPT 32].
+template <int CPT>
+__device__ __forceinline__ float warp_column_sums(float (&v)[CPT], int lane) {
+  static_assert(CPT == 16 || CPT == 32, "CPT");
+  int n = CPT;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int h = n >> 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < CPT / 2; ++i) {
+        if (i < h) {
+          const float send = upper ? v[i] : v[i + h];
+          const float keep = upper ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  return v[0];
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {      // same offset in CTA `rank` of the cluster
   uint32_t remote;
@@ -333,14 +377,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   __shared__ float s_sum[UM_MAX_N], s_sqs[UM_MAX_N];     // batch-norm partial sums of this CTA, by absolute column
   __shared__ long long s_yoff[UM_BM];                    // per-row output element offset of the tile in the epilogue
   __shared__ int s_oy[UM_BM], s_ox[UM_BM];
-  __shared__ float s_part[8][64];             // per-epilogue-warp column sums / sums of squares of a pass
+  __shared__ float s_part[2][8][64];          // per-epilogue-warp column sums / sums of squares of a pass (by pass parity)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = smem_u32(um_smem);
   const uint32_t bar_full = bars, bar_empty = bars + 8 * UM_MAX_STAGES;
   const uint32_t bar_tfull = bars + 16 * UM_MAX_STAGES, bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t stile = (bars + UM_BAR_BYTES + 15u) & ~15u;                 // epilogue staging tile (128 x 144 B)
+  const uint32_t stile = (bars + UM_BAR_BYTES + 1023u) & ~1023u;             // epilogue staging tile (128 x 144 B; 1024-byte aligned: swizzled TMA stores)
   const uint32_t tiles = (stile + UM_STAGING_BYTES + 1023u) & ~1023u;        // operand stage ring
   const int S = a.stages;
 
@@ -360,7 +404,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         // every producer thread + the expect_tx arrival of the B copy; TMA gather: the expect_tx arrival alone
-        mbar_init(bar_full + 8 * s, TMA_ANY ? (PAIR ? 2 : 1) : UM_PRODUCER_WARPS * 32 + 1);   // pair: the producers of both CTAs
+        mbar_init(bar_full + 8 * s, TMA_ANY ? 1 : UM_PRODUCER_WARPS * 32 + 1);
         mbar_init(bar_empty + 8 * s, 1);                       // one tcgen05.commit
       }
       for (int b = 0; b < 2; ++b) {
@@ -430,10 +474,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
               const uint8_t* wsrc = a.wpacked + ((size_t)nt * a.KC + kc) * (size_t)(PLANES * B_PLANE);
               bulk_g2s(bx, wsrc, B_BYTES, bar);
             } else {
-              // CTA pair: this CTA's operands land in its own shared memory, their bytes complete on the LEADER's full barrier
-              // (one arrival + expected bytes from each CTA's producer) -- the leader's MMA warp waits on that barrier alone
+              // CTA pair: this CTA's operands land in its own shared memory, their bytes complete on the LEADER's full barrier.
+              // The leader's producer makes the stage's single arrival and expects the bytes of BOTH CTAs; the peer only issues
+              // its copies (no cross-CTA arrive: a release at cluster scope per stage cost ~900 clk in the producer loop).  Bytes
+              // of the peer may land before the leader's expect_tx: the transaction count is signed, the phase cannot complete
+              // before the leader's arrival, and the peer cannot be a whole phase ahead (it waits on its own empty barrier,
+              // released by the same multicast commit as the leader's).
               const uint32_t bar = lead_full + 8 * stage;
-              mbar_arrive_expect_tx_cluster(bar, PLANES * UM_A_PLANE + B_BYTES);
+              if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (PLANES * UM_A_PLANE + B_BYTES));
               tma_im2col_4d_2sm(st_base, &tm.hi, ci0, cw, ch, (int)n, bar, ow, oh);
               if (PLANES == 2) tma_im2col_4d_2sm(st_base + UM_A_PLANE, &tm.lo, ci0, cw, ch, (int)n, bar, ow, oh);
               // packed weight image as rows of 128 bytes: tile (nt, kc) starts at row (nt*KC + kc)*PLANES*BN; boxes of BN/2 rows
@@ -721,7 +769,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
                            : "r"(stile + (uint32_t)rr * PITCH + (uint32_t)lc * 4u));
             }
             const int64_t rstride = raw ? (int64_t)a.n_pad : g.y_sw;
-            const int64_t base = (raw ? ((int64_t)z * M + m0) * a.n_pad : m0 * g.y_sw) + n;
+            const int64_t base = (raw ? ((int64_t)z * a.m_pad + m0) * a.n_pad : m0 * g.y_sw) + n;
 #pragma unroll
             for (int rd = 0; rd < RD; ++rd) {
               const int rr = rd * (EW * 4) + ew * 4 + lr;
@@ -818,8 +866,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           }
           // per-warp partials; the first epilogue warp folds them into the CTA sums after the barrier below, in a fixed
           // order (no atomics: the per-CTA statistics are run-to-run reproducible)
-          s_part[part][c] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
-          s_part[part][32 + c] = (cq[0] + cq[1]) + (cq[2] + cq[3]);
+          s_part[0][part][c] = (cs[0] + cs[1]) + (cs[2] + cs[3]);
+          s_part[0][part][32 + c] = (cq[0] + cq[1]) + (cq[2] + cq[3]);
         }
         long long tp4 = a.trace ? clock64() : 0;
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // staging tile and row table reusable
@@ -827,7 +875,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           // (the next pass rewrites s_part only after its own first barrier, which this warp has not reached yet)
           float ts = 0.f, tq = 0.f;
 #pragma unroll
-          for (int p = 0; p < EW; ++p) { ts += s_part[p][et]; tq += s_part[p][32 + et]; }
+          for (int p = 0; p < EW; ++p) { ts += s_part[0][p][et]; tq += s_part[0][p][32 + et]; }
           s_sum[n_base + c0 + et] += ts;
           s_sqs[n_base + c0 + et] += tq;
         }
@@ -881,6 +929,73 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
             for (int e = 0; e < CPT; ++e) v[e] = fmaxf(v[e], 0.f);
           }
         }
+        if (a.out_mode != 0) {
+          // ---- store through the TMA unit: no shared -> register -> global copy-out.  The staging tile is written in the layout
+          // the store reads (mode 1: 128-byte rows, SWIZZLE_128B like the tensor map; mode 2: four [128 rows][8 floats] blocks),
+          // one elected thread issues the store(s); batch-norm column sums come from the registers (warp butterfly).
+          const bool st_pass = stats && !split;
+          const int par = (c0 >> 5) & 1;
+          if (st_pass) {
+            float sq[CPT];
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) { if (row >= rows_valid) v[e] = 0.f; sq[e] = v[e] * v[e]; }
+            float sv[CPT];
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) sv[e] = v[e];
+            const float cs = warp_column_sums<CPT>(sv, lane), cq = warp_column_sums<CPT>(sq, lane);
+            // s_part[par][q-th contributor of the column's half][column of the pass]: the fold below adds the four lane
+            // quadrants of a column in a fixed order
+            if (CPT == 32) { s_part[par][q][lane] = cs; s_part[par][q][32 + lane] = cq; }
+            else if ((lane & 1) == 0) { s_part[par][q][half * 16 + (lane >> 1)] = cs; s_part[par][q][32 + half * 16 + (lane >> 1)] = cq; }
+          }
+          if (et == 0) bulk_wait_read0();            // the previous pass's store has finished reading the staging tile
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          if (a.out_mode == 1) {
+#pragma unroll
+            for (int e = 0; e < CPT; e += 4) {
+              const uint32_t chunk = (uint32_t)(half * CPT + e) >> 2;
+              st_shared_v4(stile + (uint32_t)row * 128u + ((chunk ^ ((uint32_t)row & 7u)) << 4),
+                           make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < CPT; e += 4) {
+              const uint32_t col = (uint32_t)(half * CPT + e);     // column of the pass: group col / 8, float col % 8 of the row's run
+              st_shared_v4(stile + (col >> 3) * 4096u + (uint32_t)row * 32u + (col & 7u) * 4u,
+                           make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+            }
+          }
+          fence_proxy_async();                         // generic-proxy writes -> visible to the TMA unit
+          long long tp1 = a.trace ? clock64() : 0;
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          if (et == 0) {
+            if (a.out_mode == 1) {
+              // rows / columns beyond the tensor are clipped by the tensor map (split-K partial slabs are padded to whole tiles)
+              tma_store_2d(&tm.o, stile, n_base + c0, (int)(split ? (int64_t)z * a.m_pad + m0 : m0));
+            } else {
+              const int gi_row = (int)(m0 / UM_BM);                   // tile = grid row (n, i): PW == 128
+              const int nimg = gi_row / g.PH, irow = gi_row - nimg * g.PH;
+              const int oy = g.oy0 + irow * g.osy;
+              float* ybase = yf + (int64_t)nimg * g.y_sn + (int64_t)oy * g.y_sh;
+#pragma unroll
+              for (int gi = 0; gi < 4; ++gi) {
+                const int ncol = n_base + c0 + 8 * gi;
+                if (ncol < a.Ntot && (unsigned)(oy + __ldg(a.col_dy + ncol)) < (unsigned)a.oh_lim)
+                  bulk_s2g(ybase + __ldg(a.col_off + ncol), stile + gi * 4096u, 4096u);
+              }
+            }
+            bulk_commit();
+          }
+          if (st_pass && et < 32 && n_base + c0 + et < a.Ntot) {
+            float ts = 0.f, tq = 0.f;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) { ts += s_part[par][p][et]; tq += s_part[par][p][32 + et]; }
+            s_sum[n_base + c0 + et] += ts;
+            s_sqs[n_base + c0 + et] += tq;
+          }
+          if (a.trace) { tr_p[0] += tp1 - tp0; tr_p[3] += clock64() - tp1; tr_p[4] += 1; }
+          continue;
+        }
 #pragma unroll
         for (int e = 0; e < CPT; e += 4)
           st_shared_v4(stile + (uint32_t)row * PITCH + (uint32_t)(half * CPT + e) * 4u,
@@ -891,6 +1006,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         emit_pass(c0, split);
       }
     }
+    if (a.out_mode != 0 && et == 0) bulk_wait0();      // every store of this CTA has been written out before the CTA exits
     if (a.trace && et == 0) {
       for (int i = 0; i < 5; ++i) a.trace[blockIdx.x * 16 + 8 + i] = tr_p[i];
       a.trace[blockIdx.x * 16 + 4] = tr_wait;
@@ -1020,7 +1136,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssqs[4] = {0.f, 0.f, 0.f, 0.f};
   float* yf = reinterpret_cast<float*>(a.y);
   const int total = rows * ncg;
-  const int64_t zs = M * a.n_pad;
+  const int64_t zs = a.m_pad * a.n_pad;
   for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
    // four (row, column group) items per thread per round: all partial loads are issued before any is consumed
    float4 accs[4];
@@ -1156,21 +1272,28 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   UmmaArgs a = a_in;
   a.NT = nt;
   a.Z = Z;
-  // one persistent CTA per SM: barriers + staging tile + alignment slack + as many operand stages as fit (<= 6)
-  const int fixed = UM_BAR_BYTES + 16 + UM_STAGING_BYTES + 1024;
-  int S = (214 * 1024 - fixed) / STAGE_BYTES;    // + ~12 KB of static shared memory: 214 KB dynamic stays under the 227 KB limit
+  // one persistent CTA per SM: barriers + staging tile + alignment slack + as many operand stages as fit (<= 6) in what the
+  // static shared memory of this instantiation leaves of the per-block opt-in maximum (227 KB on sm_100)
+  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC, PAIR>;
+  static int budget[64] = {0};                      // per device: the attribute lives in the device's context
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (budget[dev & 63] == 0) {
+    cudaFuncAttributes fa;
+    int optin = 0;
+    SAG_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    SAG_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int b = optin - (int)fa.sharedSizeBytes;
+    SAG_REQUIRE(b > 64 * 1024, SAG_ECUDA, "tcgen05 path: only %d bytes of dynamic shared memory available", b);
+    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    budget[dev & 63] = b;
+  }
+  const int fixed = UM_BAR_BYTES + 1024 + UM_STAGING_BYTES + 1024;
+  int S = (budget[dev & 63] - fixed) / STAGE_BYTES;
   if (S > 6) S = 6;    // the cp.async drain handles at most 5 groups in flight
   if (S < 2) S = 2;
   a.stages = S;
   const size_t smem = (size_t)fixed + (size_t)S * STAGE_BYTES;
-  auto kern = gather_gemm_umma_kernel<BN, NSPLIT, SRC, PAIR>;
-  static bool attr_set[64] = {false};               // per device: the attribute lives in the device's context
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
-    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024));
-    attr_set[dev & 63] = true;
-  }
   const int64_t M = (int64_t)g.N * g.PH * g.PW;
   const int64_t MT = cdiv64(M, UM_BM);
   constexpr int CL = PAIR ? 2 : 1;                                  // CTA pair: a cluster of two SMs of one TPC per work item
@@ -1195,6 +1318,21 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  if (PAIR) {
+    // a persistent grid must be co-resident: ask the driver how many 2-CTA clusters of this kernel fit at once (GPCs with an
+    // odd number of free SMs, SMs held by other work) and never launch more -- a cluster that has to wait for a second wave
+    // doubles the kernel's time
+    static int max_active[64] = {0};
+    if (max_active[dev & 63] == 0) {
+      int n = 0;
+      cfg.gridDim = dim3((unsigned)(num_sms() / CL * CL));
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / CL; }
+      max_active[dev & 63] = n;
+      if (env_int("SAG_UMMA_DEBUG", 0)) fprintf(stderr, "[umma] BN=%d NSPLIT=%d pair: max active clusters %d (smem %zu B)\n", BN, NSPLIT, n, smem);
+    }
+    if (clusters > max_active[dev & 63]) clusters = max_active[dev & 63];
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+  }
   // debug: SAG_UMMA_TRACE=<M tiles> prints where the three roles of the first launch with that many M tiles wait
   static const int trace_mt = env_int("SAG_UMMA_TRACE", 0);
   static int traced = 0;
@@ -1234,13 +1372,17 @@ int launch_ns(const GatherGeom& g, const UmmaArgs& a, const TmaPair& tm, int nt,
   switch (src) {
     case SRC_TMA:
       if constexpr (BN >= 64) {
-        // CTA pairs (cta_group::2, M = 256): two adjacent M tiles per cluster, each CTA feeds half of every weight tile
-        // (15-33 % fewer shared-memory bytes per K chunk).  Parity-tested, off by default: with 4 stages of ~44 KB the
-        // ring cannot cover the longer loop (peer relay + multicast commit on top of the TMA latency) -- measured
-        // conv2_x 66 -> 90 us, conv1 130 -> 170 us on B200 (SAG_UMMA_PAIR=1 / sag_set_option "cta_pair").
-        static const int pair_env = env_int("SAG_UMMA_PAIR", 0);
+        // CTA pairs (cta_group::2, M = 256): two adjacent M tiles per cluster, each CTA feeds half of every weight tile, so
+        // the weight bytes pulled through L2 and written to / read from shared memory halve.  Both CTAs' copies complete on
+        // the leader's barrier (2-SM TMA), commits are multicast.  Measured on B200 (profiles/README.md, round 2): 256-wide
+        // tiles with a long K loop gain 11 % (conv4_x 55.6 -> 49.5 us); 64- / 128-wide tiles are bound by the activation
+        // bytes, which pairs do not reduce (+-0 %), and short K loops lose 13-19 % to the cluster launch / lockstep.
+        // Default (-1 / unset): pairs exactly where they win.  SAG_UMMA_PAIR=0/1 or sag_set_option "cta_pair" force it.
+        static const int pair_env = env_int("SAG_UMMA_PAIR", -1);
         const int64_t MT = cdiv64((int64_t)g.N * g.PH * g.PW, UM_BM);
-        if ((g_umma_pair < 0 ? pair_env : g_umma_pair) && MT >= 2 && a.pair_ok) return launch_cfg<BN, NSPLIT, SRC_TMA, true>(g, a, tm, nt, Z, st);
+        const int want = g_umma_pair >= 0 ? g_umma_pair : pair_env;
+        const bool pair = want >= 0 ? want != 0 : (BN == 256 && a.KC / Z >= 16);
+        if (pair && MT >= 2 && a.pair_ok) return launch_cfg<BN, NSPLIT, SRC_TMA, true>(g, a, tm, nt, Z, st);
         return launch_cfg<BN, NSPLIT, SRC_TMA, false>(g, a, tm, nt, Z, st);
       } else {
         return launch_cfg<BN, NSPLIT, SRC_BF2, false>(g, a, tm, nt, Z, st);  // (the host never picks TMA for 32-wide tiles)
@@ -1459,6 +1601,15 @@ int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int
   for (int n = 0; n < N; n += 4)
     if (off[n] % 4 != 0) vec = false;
   w.vec4 = vec ? 1 : 0;
+  // groups of 8 columns that are 8 consecutive floats of one output row (planar outputs, stride 8 along the row): the
+  // bulk-run store of the epilogue (out_mode 2)
+  bool run8 = N % 32 == 0 && sw == 8 && y_sw == 1;
+  for (int n = 0; n + 7 < N && run8; n += 8) {
+    if (off[n] % 4 != 0) run8 = false;
+    for (int e = 1; e < 8; ++e)
+      if (off[n + e] != off[n] + e || dy[n + e] != dy[n] || dx[n + e] != dx[n] + e) run8 = false;
+  }
+  w.run8 = run8 ? 1 : 0;
   cudaError_t e = cudaSuccess;
   if ((e = cudaMalloc(&w.col_off, sizeof(int) * N)) != cudaSuccess || (e = cudaMalloc(&w.col_dy, sizeof(short) * N)) != cudaSuccess ||
       (e = cudaMalloc(&w.col_dx, sizeof(short) * N)) != cudaSuccess || (e = cudaMalloc(&w.col_bias, sizeof(float) * N)) != cudaSuccess) {
@@ -1519,7 +1670,8 @@ int umma_tile_width(int K, int N, int64_t M) { return plan_tile(K, N, M).BN; }
 // pulling Z partial tiles through L2 latency cannot compete with a reduce spread over the whole GPU.)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   const TilePlan p = plan_tile(K, N, M);
-  if (scratch_bytes) *scratch_bytes = p.Z > 1 ? sizeof(float) * (size_t)p.Z * (size_t)M * (size_t)(cdiv(N, p.BN) * p.BN) : 0;
+  // partial slabs are padded to whole 128-row tiles (the TMA store of a tile never crosses into the next slab)
+  if (scratch_bytes) *scratch_bytes = p.Z > 1 ? sizeof(float) * (size_t)p.Z * (size_t)(cdiv64(M, UM_BM) * UM_BM) * (size_t)(cdiv(N, p.BN) * p.BN) : 0;
   return p.Z;
 }
 
@@ -1634,6 +1786,28 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
   a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;
+  a.m_pad = cdiv64(M, UM_BM) * UM_BM;
+  // how the epilogue's passes leave the CTA (see UmmaArgs::out_mode)
+  static const int tma_out_env = env_int("SAG_UMMA_TMA_STORE", 1);
+  a.out_mode = 0;
+  if (tma_out_env) {
+    const EncodeTiledFn encode = encode_tiled_fn();
+    const bool raw = Z > 1;
+    if (encode != nullptr && (raw || (a.dense && a.vec_store && a.out_bf2 == 0 && w.col_off == nullptr))) {
+      const cuuint64_t dims[2] = {(cuuint64_t)(raw ? a.n_pad : w.N), (cuuint64_t)(raw ? (int64_t)Z * a.m_pad : M)};
+      const cuuint64_t strides[1] = {(cuuint64_t)(raw ? a.n_pad : g.y_sw) * 4};
+      const cuuint32_t box[2] = {32, (cuuint32_t)UM_BM};
+      const cuuint32_t estr[2] = {1, 1};
+      void* base = raw ? (void*)scratch : y.p;
+      if ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && strides[0] % 16 == 0 &&
+          encode(&tm.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        a.out_mode = 1;
+    } else if (!raw && w.col_off != nullptr && w.run8 && a.out_bf2 == 0 && g.PW == UM_BM && g.ox0 == 0 && g.osx == 8 && g.y_sw == 1 &&
+               ow_lim == UM_BM * 8 && aligned_y && g.y_sn % 4 == 0 && g.y_sh % 4 == 0) {
+      a.out_mode = 2;
+    }
+  }
   SAG_REQUIRE(w.KC >= 1, SAG_EINVAL, "tcgen05 path: empty contraction");
   SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);
   SAG_REQUIRE(ep.stat_sum == nullptr || Z == 1 || 256 % cdiv(w.N, 4) == 0, SAG_EUNSUPPORTED, "tcgen05 path: split-K statistics over %d columns", w.N);

@@ -97,6 +97,9 @@ static double emd_hat_one(const double* P, const double* Q, int n, const double*
     remaining -= amt;
     for (int i = 0; i < N; ++i) { pu[i] += std::min(dl[i], dt); pv[i] += std::min(dr[i], dt); }
   }
+  // all mass must have been shipped: a tripped iteration guard or an unreachable sink would leave a partial (too small) cost
+  // behind -- report it as NaN rather than as a plausible distance
+  if (remaining > total * 1e-9) return std::nan("");
   return result;
 }
 

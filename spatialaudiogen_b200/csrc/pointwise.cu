@@ -107,8 +107,10 @@ int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& resi
   SAG_REQUIRE(c % 4 == 0 && c <= 4096, SAG_EINVAL, "bn_apply: channels %d not a multiple of 4 (or too many)", c);
   int64_t n4 = rows * c / 4;
   if (n4 == 0) return SAG_OK;
-  int64_t blocks = cdiv64(n4, 256 * 2);                 // >= 2 vectors per thread amortise the prologue
-  int64_t cap = (int64_t)num_sms() * 16;
+  // one co-resident wave (4 blocks of 256 threads per SM, launch bounds): every block pays the scale / shift prologue once
+  // and streams BN_UNROLL vectors per thread per round; small tensors get exactly one round per thread
+  int64_t blocks = cdiv64(n4, 256 * BN_UNROLL);
+  int64_t cap = (int64_t)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   launch_pdl(bn_apply_stats_kernel, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, reinterpret_cast<const float4*>(x), bn,

@@ -259,7 +259,12 @@ def latest_checkpoint(model_dir):
         m = re.match(r'\s*model_checkpoint_path\s*:\s*"(.*)"', line)
         if m:
             p = m.group(1)
-            return p if os.path.isabs(p) else os.path.join(model_dir, p)
+            if not os.path.isabs(p):
+                return os.path.join(model_dir, p)
+            # an absolute path written on the training machine: when it does not exist here, the bundle of that name next to
+            # the `checkpoint` file is the one meant (model directories are copied around)
+            local = os.path.join(model_dir, os.path.basename(p))
+            return p if os.path.exists(p + '.index') or not os.path.exists(local + '.index') else local
     return None
 
 
