@@ -265,7 +265,7 @@ def workload_config(encoders, B, precision, args, world):
                       if len(encoders) > 1 else None,
             'weights': 'xavier random init (seed 1234); resnet towers: %s' % (
                 'the reference\'s resnet18.npy (model.py:198)' if os.path.exists(RESNET_NPY) else 'xavier (resnet18.npy not staged)'),
-            'step': 'sag_forward + sag_metrics over one batch',
+            'step': 'sag_forward + sag_metrics over one batch' + (' (replayed as one CUDA graph: host-launch-bound batch size)' if B <= 16 else ''),
             'l2': 'inputs rotate over %d distinct batches and each step streams >1 GB of activations through the '
                   'workspace (> 126 MB L2)' % args.rotate,
             'parallelism': 'clip-sharded, weights replicated, one all-gather of metric rows at the end of the pass'}
@@ -357,14 +357,39 @@ def main():
     ids = torch.tensor([[c, w0 + j] for (c, w0) in batch_ids for j in range(B)], dtype=torch.int64).reshape(-1, 2).to(dev)
     ss = RATE // 2
 
-    def step(i, store=None):
-        d = devb[i % R]
+    def step_eager(d, store=None):
         fwd(d)
         # the metric set of SURVEY.md 8d config 5 (config 5 adds the 84-direction RMS maps of [W | pred] and [W | gt])
         r, _ = E.metric_rows(out, d['target'], mono=d['audio'][:, ss:ss + SND_DUR] if maps_on else None, audio_rate=RATE,
                              rms_maps=maps_on, mel_lsd=False, emd=False)
         if store is not None:
             store.copy_(r)
+
+    # Small batches are bound by the host's launch rate (~70 kernels per step), not by the GPU: replay the whole step --
+    # forward + metrics, programmatic dependent launches included -- as one CUDA graph per rotating input slot.
+    use_graph = B <= 16 and os.environ.get('SAG_BENCH_GRAPH', '1') != '0'
+    graphs, rows_slot = [], []
+    if use_graph:
+        try:
+            for r in range(R):
+                rows_slot.append(torch.zeros((B, E.N_COLS), dtype=torch.float32, device=dev))
+                step_eager(devb[r], rows_slot[r])             # warm-up: plans the batch, sets kernel attributes
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_eager(devb[r], rows_slot[r])
+                graphs.append(g)
+        except RuntimeError as e:
+            sys.stderr.write('CUDA graph capture failed (%s): eager launches\n' % e)
+            use_graph, graphs = False, []
+
+    def step(i, store=None):
+        if use_graph:
+            graphs[i % R].replay()
+            if store is not None:
+                store.copy_(rows_slot[i % R])
+        else:
+            step_eager(devb[i % R], store)
 
     def barrier():
         if world > 1:

@@ -74,7 +74,14 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
   if (r == SAG_OK) r = build_expected(h);
   if (r == SAG_OK && cudaGetDevice(&h->device) != cudaSuccess) { set_error("cudaGetDevice failed"); r = SAG_ECUDA; }
   if (r == SAG_OK) r = fft_prepare(h->dims.wind_size);
-  if (r != SAG_OK) { delete h; return r; }
+  if (r == SAG_OK) {
+    static const bool overlap_env = [] { const char* v = getenv("SAG_OVERLAP"); return v == nullptr || atoi(v) != 0; }();
+    h->overlap = overlap_env ? 1 : 0;
+    bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { set_error("sag_create: could not create the side stream / events"); r = SAG_ECUDA; }
+  }
+  if (r != SAG_OK) { sag_destroy(h); return r; }
   *out = h;
   return SAG_OK;
 }
@@ -85,6 +92,9 @@ int sag_destroy(sag_handle* h) {
   for (auto& kv : h->packed) free_tensor(kv.second);
   for (auto& kv : h->umma) umma_free(&kv.second);
   h->prof.clear();
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
   return SAG_OK;
 }
@@ -103,6 +113,7 @@ int sag_set_option(sag_handle* h, const char* key, int value) {
   if (k == "cta_pair") { h->cta_pair = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "tma_gather") { h->tma_gather = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "profile") { h->prof.on = value != 0; if (!value) h->prof.clear(); return SAG_OK; }
+  if (k == "overlap") { h->overlap = value ? 1 : 0; return SAG_OK; }
   if (k == "precision") {
     SAG_REQUIRE(valid_precision(value), SAG_EINVAL, "unknown precision %d", value);
     h->cfg.precision = value;

@@ -968,7 +968,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           fence_proxy_async();                         // generic-proxy writes -> visible to the TMA unit
           long long tp1 = a.trace ? clock64() : 0;
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-          if (et == 0) {
+          if (et == 0 && rows_valid > 0) {            // (rows_valid == 0: the all-padding tile of an odd CTA pair stores nothing)
             if (a.out_mode == 1) {
               // rows / columns beyond the tensor are clipped by the tensor map (split-K partial slabs are padded to whole tiles)
               tma_store_2d(&tm.o, stile, n_base + c0, (int)(split ? (int64_t)z * a.m_pad + m0 : m0));

@@ -159,6 +159,7 @@ struct Fwd {
   cudaStream_t st;
   int prec;
   int cat = PROF_CONV;
+  bool private_scratch = false;   // layers that may run beside others on the side stream take their own split-K scratch
   bool dry() const { return ar.dry; }
   bool tc() const { return prec != SAG_PREC_FP32; }
 
@@ -226,6 +227,10 @@ struct Fwd {
   float* splitk(int K, int N, int64_t M) {
     size_t bytes = 0;
     umma_split_k(K, N, M, &bytes);
+    if (private_scratch) {          // (same allocation sequence in the dry and the real pass)
+      float* p = bytes > 0 ? reinterpret_cast<float*>(ar.alloc<char>((int64_t)bytes)) : nullptr;
+      return dry() ? nullptr : p;
+    }
     if (bytes > ar.scratch_need) ar.scratch_need = bytes;
     return (!dry() && bytes > 0 && bytes <= ar.scratch_cap) ? ar.scratch : nullptr;
   }
@@ -488,6 +493,27 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   g_umma_tma = h->tma_gather;
   g_umma_pair = h->cta_pair;
   const bool unet = c.separation == SAG_SEP_UNET_MASK;
+  // fork / join of the independent branches (see sag_handle::overlap); profiling runs them serially so that every launch
+  // scope is timed alone
+  const bool overlap = !ar.dry && h->overlap != 0 && h->side != nullptr && !h->prof.on;
+  const bool overlap_a = overlap && (c.enc_video || c.enc_flow);      // STFT + audio encoder beside the visual towers
+  Fwd fa{h, ar, overlap_a ? h->side : st, c.precision};
+  fa.private_scratch = true;
+  Fwd fl{h, ar, overlap ? h->side : st, c.precision};                 // localization FCs beside the decoder
+  fl.private_scratch = true;
+  auto fork = [&](bool on, cudaEvent_t e) -> int {
+    if (!on) return SAG_OK;
+    SAG_CHECK_CUDA(cudaEventRecord(e, st));
+    SAG_CHECK_CUDA(cudaStreamWaitEvent(h->side, e, 0));
+    return SAG_OK;
+  };
+  auto join = [&](bool on, cudaEvent_t e) -> int {
+    if (!on) return SAG_OK;
+    SAG_CHECK_CUDA(cudaEventRecord(e, h->side));
+    SAG_CHECK_CUDA(cudaStreamWaitEvent(st, e, 0));
+    return SAG_OK;
+  };
+  SAG_TRY(fork(overlap_a, h->ev[0]));
   // NO_SEPARATION keeps params.sep_num_tracks localization weights per output channel; the single mono track
   // broadcasts against them (model.py:430), i.e. the mono crop is replicated K times before the mixing.
   const int K = c.sep_num_tracks;
@@ -509,11 +535,11 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   Act mag = f.alloc_act((int64_t)B * n_enc * wind, 1);
   if (!ar.dry) {
     ProfScope ps(PROF_STFT, 5.0 * wind * std::log2((double)wind) * B * (full ? d.n_stft_frames : n_enc),
-                 4.0 * B * (double)d.snd_size + act_b * B * (double)n_enc * wind + (unet ? 8.0 * B * n_msk * wind : 0.0), st, "stft");
+                 4.0 * B * (double)d.snd_size + act_b * B * (double)n_enc * wind + (unet ? 8.0 * B * n_msk * wind : 0.0), fa.st, "stft");
     if (full)
-      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag.v, st));
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, 0, d.n_stft_frames, S_all, d.enc_ss, n_enc, mag.v, fa.st));
     else
-      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, d.mask_ss, unet ? n_msk : 0, S, d.enc_ss, n_enc, mag.v, st));
+      SAG_TRY(launch_stft(audio, B, d.snd_size, wind, hop, d.n_stft_frames, d.mask_ss, unet ? n_msk : 0, S, d.enc_ss, n_enc, mag.v, fa.st));
   }
   if (full) f.tap("stft", Act(S_all, 2), {B, 1, d.n_stft_frames, wind, 2});
   f.tap("audio_encoder/0", mag, {B, n_enc, wind, 1});
@@ -538,7 +564,7 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   }
   for (int l = 0; l < 5; ++l) {
     int oh, ow;
-    SAG_TRY(f.conv(enc[l], B, eh[l], ew[l], ecn[l], "audio_encoder/conv" + std::to_string(l + 1), kAudioKernel[l][0],
+    SAG_TRY(fa.conv(enc[l], B, eh[l], ew[l], ecn[l], "audio_encoder/conv" + std::to_string(l + 1), kAudioKernel[l][0],
                    kAudioKernel[l][1], ecn[l + 1], kAudioStride[l][0], kAudioStride[l][1], 0, true, 1, enc[l + 1], nullptr,
                    nullptr, &oh, &ow));
     f.tap("audio_encoder/" + std::to_string(l + 1), enc[l + 1], {B, eh[l + 1], ew[l + 1], ecn[l + 1]});
@@ -553,8 +579,8 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   // bottleneck audio (model.py:207-230): (B,3,6*512) -> fc 1024, as a (1 x ew5) VALID conv over the strided enc5
   {
     int oh, ow;
-    SAG_TRY(f.conv(enc[5], B * nt, 1, ew[5], ecn[5], "bottleneck/audio-fc", 1, ew[5], 1024, 1, 1, 0, true, 1,
-                   feats.channels(foff), nullptr, nullptr, &oh, &ow));
+    SAG_TRY(fa.conv(enc[5], B * nt, 1, ew[5], ecn[5], "bottleneck/audio-fc", 1, ew[5], 1024, 1, 1, 0, true, 1,
+                    feats.channels(foff), nullptr, nullptr, &oh, &ow));
     foff += 1024;
   }
   for (int v = 0; v < 2; ++v) {
@@ -574,7 +600,9 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
     if (!ar.dry) SAG_TRY(launch_tile_rows(vfc.v, 512, feats.channels(foff).v, D, B, nt, 512, st));     // tf.tile (model.py:232)
     foff += 512;
   }
+  SAG_TRY(join(overlap_a, h->ev[1]));      // the audio half of `feats` (and the STFT rows the inverse transform reads) are in place
   f.tap("bottleneck", feats, {B, nt, D});
+  SAG_TRY(fork(overlap, h->ev[2]));
 
   // ---- localization (model.py:241-271) -----------------------------------------------------------------------
   const int n3 = 3 * (K + 1);
@@ -584,16 +612,17 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
     int in = D;
     for (int i = 0; i < c.n_loc_fc; ++i) {
       Act y = f.alloc_act((int64_t)B * nt, c.loc_fc_units[i]);
-      SAG_TRY(f.fc(x, B * nt, in, "localization/fc" + std::to_string(i + 1), c.loc_fc_units[i], 1, y));
+      SAG_TRY(fl.fc(x, B * nt, in, "localization/fc" + std::to_string(i + 1), c.loc_fc_units[i], 1, y));
       x = y;
       in = c.loc_fc_units[i];
     }
-    SAG_TRY(f.fc(x, B * nt, in, "localization/fc" + std::to_string(c.n_loc_fc + 1), n3, 0, Act(loc, n3)));
+    SAG_TRY(fl.fc(x, B * nt, in, "localization/fc" + std::to_string(c.n_loc_fc + 1), n3, 0, Act(loc, n3)));
   }
   f.tap("localization", Act(loc, K + 1), {B, nt, 3, 1, K + 1});
 
   // ---- separation (model.py:273-354) --------------------------------------------------------------------------
   float* x_sep = ar.alloc<float>((int64_t)B * K * T);
+  bool joined = false;
   if (!unet) {
     // NO_SEPARATION: x_sep = mono[snd_contx/2 : +snd_dur] (model.py:274-280); audio is (B,snd_size,1)
     if (!ar.dry) SAG_TRY(launch_tile_rows(ActView(audio + d.snd_contx / 2), d.snd_size, ActView(x_sep), T, B, K, T, st));
@@ -625,6 +654,8 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
     // sigmoid mask x STFT -> istft -> crop (model.py:334-347; myutils.py:181-211)
     // frames [mask_ss, mask_tt) of the full STFT / rows [mask_ss-skip, ..) of the full mask are strided views the
     // kernel does not take: compact them first (test-only path, skip_unused == 0).
+    SAG_TRY(join(overlap, h->ev[3]));        // localization weights are in place (the inverse STFT + mixing reads them)
+    joined = true;
     float* S2 = full ? ar.alloc<float>((int64_t)B * n_msk * wind * 2) : S;
     float* m2 = full ? ar.alloc<float>((int64_t)B * K * n_msk * OW) : mask;
     const bool fuse_mix = istft_mix_supported(K, T, nt, wind) != 0;
@@ -655,6 +686,7 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   else f.tap("separation/all_channels", Act(x_sep, T), {B, 1, 1, T}, (int64_t)K * T);
 
   // ---- decode (model.py:424-432) -------------------------------------------------------------------------------
+  if (!joined) SAG_TRY(join(overlap, h->ev[3]));
   if (!ar.dry) {
     ProfScope ps(PROF_MIX, 6.0 * B * K * T, 4.0 * B * ((double)K * T + 3.0 * T), st);
     SAG_TRY(launch_mix(x_sep, loc, B, K, T, nt, out, st));

@@ -79,6 +79,13 @@ struct sag_handle {
   int cta_pair = -1;     // tcgen05 path on CTA pairs (cta_group::2): -1 default (off), 0 / 1 forced
   int tma_gather = -1;   // activation gather of the tcgen05 path: -1 default (TMA im2col where it applies), 0 cp.async, 1 TMA
   int skip_unused = 1;   // skip mask rows / frames that cannot reach the cropped output (bit-identical result)
+  // Branches of the forward that do not depend on each other run on a second stream of the handle, forked from and joined
+  // back into the caller's stream with events (still fully asynchronous to the host; captured by CUDA graphs as a fork /
+  // join): STFT + audio encoder + audio-fc beside the visual towers, the localization FCs beside the U-Net decoder.  Those
+  // are chains of small grids that leave most SMs idle on their own and fill the tails of the towers' persistent kernels.
+  int overlap = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace sag {

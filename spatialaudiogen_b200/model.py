@@ -208,6 +208,20 @@ class SptAudioGen(StageOps):
                                            L.stream()))
         return out
 
+    def capture_graph(self, audio, video, flow, out, flow_limits=None):
+        """One forward on these (static) device buffers as a CUDA graph: at small batches the forward is a chain of ~60 short
+        kernels and the host cannot enqueue them as fast as the GPU runs them (B=1: 0.33 ms of launches for 0.1 ms of work); a
+        graph replays the whole chain -- programmatic dependent launches included -- with one call.  Returns the
+        torch.cuda.CUDAGraph; refill the buffers, then `.replay()` on the stream that orders the refill.  The uncaptured warm-up
+        call plans the batch (sag_workspace_bytes) and sets the kernel attributes, so nothing allocates during the capture."""
+        with torch.cuda.device(self.device):
+            self.forward_into(audio, video, flow, out, flow_limits)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.forward_into(audio, video, flow, out, flow_limits)
+        return g
+
     def inference_ops(self, audio, video=None, flow=None, is_training=True):
         """reference model.py:356-434.  audio (B, snd_size, 1); video / flow (B, 1, H, W, 3); returns the
         (B, snd_dur, 3) first-order channels (Y, Z, X) as a CUDA tensor.  `is_training` is accepted for API
@@ -246,12 +260,14 @@ class SptAudioGen(StageOps):
     def dims_frame(self):
         return self._frame
 
-    def inference_stream(self, batches, depth=2):
+    def inference_stream(self, batches, depth=2, use_graph=None):
         """The driver loop around `sess.run` (reference deploy.py:112-148, eval.py:140-201) as a generator: `batches`
         yields dicts of HOST tensors {'audio': (B, snd_size, 1)[, 'video', 'flow': (B, 1, H, W, 3)]} (pinned memory
         makes the copies asynchronous); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
         `depth` steps) is yielded in order.  'video' / 'flow' may be the uint8 frames as decoded from disk (a quarter of the
-        PCIe bytes; they are prepared on the device, see forward_into) -- uint8 flow comes with 'flow_limits' (B, 2) float64.  Host->device copies of step i+1 and the device->host copy of step i-1 run
+        PCIe bytes; they are prepared on the device, see forward_into) -- uint8 flow comes with 'flow_limits' (B, 2) float64.
+        use_graph: replay each slot's forward as a CUDA graph (capture_graph); default: batches of at most 16 windows, where
+        the host's launch rate, not the GPU, bounds the step (the reference's deploy loop feeds 10, its eval loop 16).  Host->device copies of step i+1 and the device->host copy of step i-1 run
         on their own streams while step i computes, so the PCIe transfers hide behind the forward."""
         if not self._weights_ready:
             raise RuntimeError('load_weights() must be called before inference_stream()')
@@ -275,6 +291,7 @@ class SptAudioGen(StageOps):
                       'in_ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'out_ready': torch.cuda.Event(),
                       'free': torch.cuda.Event()}
                 sl['free'].record(main)
+                sl['graph'] = None
                 return sl
 
             def finish(idx):
@@ -298,7 +315,19 @@ class SptAudioGen(StageOps):
                         t.copy_(torch.as_tensor(b[k]), non_blocking=True)
                     sl['in_ready'].record(side)
                 main.wait_event(sl['in_ready'])
-                self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'], sl['in'].get('flow_limits'))
+                graph = use_graph if use_graph is not None else b[AUDIO].shape[0] <= 16
+                if graph and sl['graph'] is None:
+                    try:                                   # (warm-up forward + capture; this first use also produces the result)
+                        sl['graph'] = self.capture_graph(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'],
+                                                         sl['in'].get('flow_limits'))
+                    except RuntimeError as e:              # capture unsupported: stay eager, say so once
+                        import warnings
+                        warnings.warn('CUDA graph capture of the forward failed (%s); running eagerly' % e)
+                        sl['graph'] = False
+                if graph and sl['graph']:
+                    sl['graph'].replay()
+                else:
+                    self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'], sl['in'].get('flow_limits'))
                 sl['done'].record(main)
                 sl['free'].record(main)
                 with torch.cuda.stream(back):

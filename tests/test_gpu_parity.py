@@ -612,6 +612,32 @@ def test_inference_stream_matches_per_batch_calls():
         assert _rel(y, ref) < 2e-5
 
 
+def test_cuda_graph_replay_equals_eager_forward():
+    """capture_graph / inference_stream(use_graph=True): the replayed chain (programmatic dependent launches included) returns
+    what the eager calls return, bit for bit, also after the buffers are refilled."""
+    from spatialaudiogen_b200 import SptAudioGen
+    enc = ['audio', 'video']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=8, stress=True)
+    m = SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(W)
+    for B in (1, 10):
+        a, v = cu(_audio(B, 70)), cu(_video(B, 71))
+        out_g, out_e = torch.empty((B, 4800, 3), device='cuda'), torch.empty((B, 4800, 3), device='cuda')
+        g = m.capture_graph(a, v, None, out_g)
+        for seed in (72, 73):
+            a.copy_(cu(_audio(B, seed)))
+            v.copy_(cu(_video(B, seed + 10)))
+            out_g.zero_()
+            g.replay()
+            m.forward_into(a, v, None, out_e)
+            torch.cuda.synchronize()
+            assert torch.equal(out_g, out_e) and float(out_e.abs().max()) > 0
+    batches = [{'audio': torch.as_tensor(_audio(2, 80 + i)).pin_memory(), 'video': torch.as_tensor(_video(2, 90 + i)).pin_memory()}
+               for i in range(5)]
+    eager = [y.clone() for y in m.inference_stream(iter(batches), use_graph=False)]
+    graph = [y.clone() for y in m.inference_stream(iter(batches), use_graph=True)]
+    assert all(torch.equal(x, y) for x, y in zip(eager, graph))
+
+
 def test_forward_is_bit_reproducible():
     """Run-to-run determinism of the tensor-core forward at a split-K batch (B=2) and at the benchmarked batch (B=32)."""
     from spatialaudiogen_b200 import SptAudioGen
