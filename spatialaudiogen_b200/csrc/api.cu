@@ -77,7 +77,11 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
   if (r == SAG_OK) {
     static const bool overlap_env = [] { const char* v = getenv("SAG_OVERLAP"); return v == nullptr || atoi(v) != 0; }();
     h->overlap = overlap_env ? 1 : 0;
-    bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
+    // highest priority: its short grids take the SMs the persistent tower kernels free at their tails before the next tower
+    // kernel's CTAs do, so the side chain advances at every kernel boundary of the main stream
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { set_error("sag_create: could not create the side stream / events"); r = SAG_ECUDA; }
   }
@@ -114,6 +118,7 @@ int sag_set_option(sag_handle* h, const char* key, int value) {
   if (k == "tma_gather") { h->tma_gather = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "profile") { h->prof.on = value != 0; if (!value) h->prof.clear(); return SAG_OK; }
   if (k == "overlap") { h->overlap = value ? 1 : 0; return SAG_OK; }
+  if (k == "fuse_gains") { h->fuse_gains = value ? 1 : 0; return SAG_OK; }
   if (k == "precision") {
     SAG_REQUIRE(valid_precision(value), SAG_EINVAL, "unknown precision %d", value);
     h->cfg.precision = value;

@@ -122,6 +122,12 @@ struct Epilogue {
   // zeroed by the caller, accumulated with integer atomics -- exact, hence independent of the arrival order of the CTAs
   unsigned long long* stat_sum;
   unsigned long long* stat_sqs;
+  // mask-gain fusion (deconv1 of the U-Net decoder, model.py:326-334 + 424-432 by linearity): instead of the 32 track logits
+  // of a time-frequency bin the epilogue writes G[o, seg] = sum_k W[o, k, seg] * sigmoid(logit_k) for the 3 x 3 (channel,
+  // localization segment) pairs: gains (rows, 9, frames, bins) from gain_loc (rows, 3 segments, 3*(tracks+1)); null = off
+  const float* gain_loc;
+  float* gains;
+  int64_t gain_plane;     // frames * bins
 };
 
 // Exact fixed-point accumulation of float partial sums: word 0 = integer part (two's complement), word 1 = fraction * 2^40.
@@ -170,6 +176,7 @@ struct UmmaWeights {
   float* col_bias = nullptr;
   int vec4 = 0;
   int run8 = 0;         // mapped output: every group of 8 columns is 8 consecutive floats of one output row
+  int order = 0;        // column order of a sub-pixel transposed conv (decode_subpixel_column in conv_umma.cu)
   int64_t M_hint = 0;   // row count the tile width was chosen for
   // tiled tensor map of the packed image (rows of 128 bytes, boxes of BN/2 rows) for the CTA-pair kernel, which fetches its
   // weight blocks with .cta_group::2 tensor copies (a CUtensorMap, kept opaque here); wmap_ok == 0: not available

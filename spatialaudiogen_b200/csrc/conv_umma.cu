@@ -77,9 +77,14 @@ struct UmmaArgs {
   int pair_ok;            // host: the tiled weight map exists (CTA pairs fetch their weight blocks through it)
   // how a staged 128 x 32 pass leaves the CTA: 0 = LSU copy-out (any output format / mapping); 1 = one TMA tensor store per
   // pass (dense fp32 rows, or the split-K partials); 2 = bulk stores of contiguous 4 KB runs (sub-pixel transposed conv
-  // whose tile is one grid row: the 128 rows x 8 pixels of a column group are 1024 consecutive floats of the output)
+  // whose tile is one grid row: the 128 rows x 8 pixels of a column group are 1024 consecutive floats of the output);
+  // 3 = the track logits never leave the SM: sigmoid + the 32 -> 9 localization-weighted sums in registers, 9 runs of 4 KB out
   int out_mode;
   int64_t m_pad;          // rows of one split-K partial slab (M rounded up to whole tiles)
+  // out_mode 3: mask-gain fusion (Epilogue::gains): column order 2, 256-wide tiles, tile = one grid row of one window
+  const float* gain_loc;
+  float* gains;
+  int64_t gain_plane;
 };
 // im2col tensor maps of the two activation planes (SRC_TMA) + the tiled map of the packed weight image (CTA pairs: 128-byte
 // rows, boxes of BN/2 rows); kernel parameter, read by the TMA unit
@@ -890,6 +895,83 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       if (a.trace) tr_wait += clock64() - tr_w0;
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      if constexpr (BN == 256 && EW == 8 && NSPLIT != 2) {
+        if (a.out_mode == 3) {
+          // ---- mask-gain fusion (model.py:334 sigmoid mask, :424-432 mixing, folded by linearity like mask_gains_kernel in
+          // fft.cu): the tile is grid row (window nimg, row irow) x sub-pixel row py = nt; column order 2 hands this thread
+          // (tile row = frequency cell j, half) the 32 track logits of sub-pixels px = 4*half + pp, pp = 0..3, two passes each.
+          // G[gi] = sum_k w[gi][k] * sigmoid(logit_k) in track order -- the same fmaf chain as mask_gains_kernel, so the gains
+          // are bit-identical to the two-kernel path.  36 accumulators per thread; the logits are never stored.
+          float* s_w = &s_part[0][0][0];              // [32 tracks][12]: the 9 weights of a track side by side (no statistics here)
+          const int gi_row = mt < MT ? mt : MT - 1;   // (the all-padding tile of an odd CTA pair reads valid weights, stores nothing)
+          const int nimg = gi_row / g.PH, irow = gi_row - nimg * g.PH;
+          const int fo = g.oy0 + irow * g.osy + nt;   // output row (STFT frame) of this tile
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");       // the previous tile's readers of s_w / the staging tile are done
+          for (int i = et; i < 12 * 32; i += EW * 32) {
+            const int kk = i / 12, gi = i - kk * 12;
+            s_w[i] = gi < 9 ? __ldg(a.gain_loc + ((int64_t)nimg * 9 + gi) * 33 + kk) : 0.f;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          float acc[4][9];
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+            for (int gi = 0; gi < 9; ++gi) acc[pp][gi] = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const int cc = (pp * 2 + sub) * 32 + half * 16;
+              float v[16];
+              tmem_ld16(tmem_row + (uint32_t)cc, v);
+              if (pp == 3 && sub == 1) {               // last read of this accumulator: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
+              }
+              const float4* b4p = reinterpret_cast<const float4*>(a.bias + n_base + cc);
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = __ldg(b4p + (e >> 2));
+                v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float sg = 1.f / (1.f + expf(-v[e]));                  // tf.sigmoid (model.py:334)
+                const float4* w4 = reinterpret_cast<const float4*>(s_w + (sub * 16 + e) * 12);
+                const float4 wa = w4[0], wb = w4[1], wc = w4[2];
+                const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};
+#pragma unroll
+                for (int gi = 0; gi < 9; ++gi) acc[pp][gi] = fmaf(w[gi], sg, acc[pp][gi]);
+              }
+            }
+          }
+          // write-out: per gain plane the tile is one run of 128 cells x 8 sub-pixels = 4 KB; four planes per round through the
+          // staging tile, then one bulk store each
+          const bool valid_f = rows_valid > 0 && (unsigned)fo < (unsigned)a.oh_lim;
+#pragma unroll
+          for (int r0 = 0; r0 < 9; r0 += 4) {
+            if (et == 0) bulk_wait_read0();
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi)
+              if (r0 + gi < 9)
+                st_shared_v4(stile + gi * 4096u + (uint32_t)row * 32u + (uint32_t)half * 16u,
+                             make_uint4(__float_as_uint(acc[0][r0 + gi]), __float_as_uint(acc[1][r0 + gi]), __float_as_uint(acc[2][r0 + gi]),
+                                        __float_as_uint(acc[3][r0 + gi])));
+            fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+            if (et == 0 && valid_f) {
+#pragma unroll
+              for (int gi = 0; gi < 4; ++gi)
+                if (r0 + gi < 9)
+                  bulk_s2g(a.gains + ((int64_t)nimg * 9 + r0 + gi) * a.gain_plane + (int64_t)fo * (UM_BM * 8), stile + gi * 4096u, 4096u);
+              bulk_commit();
+            }
+          }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[CPT];
@@ -1068,6 +1150,19 @@ __global__ void umma_pack_weights_kernel(const float* __restrict__ wk, int K, in
   }
 }
 
+// GEMM column n of a sub-pixel transposed conv -> (sub-pixel row py, sub-pixel column px, output channel co)
+//   order 0: n = (py*sw + px)*Cout + co                  NHWC outputs: a pixel's channels are contiguous
+//   order 1: n = (py*Cout + co)*sw + px                  planar outputs: a row's sub-pixels are contiguous
+//   order 2: (sw == 8, Cout == 32) n = py*256 + c, c = pass*32 + half*16 + e -> px = 4*half + pass/2, co = 16*(pass%2) + e:
+//            the epilogue thread that drains columns [half*16, half*16+16) of every 32-column pass of a 256-wide tile
+//            sees, over two consecutive passes, all 32 tracks of ONE sub-pixel -- and over the eight passes four
+//            neighbouring sub-pixels (the mask-gain fusion of out_mode 3)
+__host__ __device__ inline void decode_subpixel_column(int order, int n, int cout, int sw, int* py, int* px, int* co) {
+  if (order == 0) { *co = n % cout; const int ph = n / cout; *px = ph % sw; *py = ph / sw; }
+  else if (order == 1) { *px = n % sw; const int q = n / sw; *co = q % cout; *py = q / cout; }
+  else { *py = n >> 8; const int c = n & 255, pass = c >> 5, half = (c >> 4) & 1, e = c & 15; *px = 4 * half + (pass >> 1); *co = ((pass & 1) << 4) + e; }
+}
+
 // tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin] (core.py:118) -> sub-pixel GEMM matrix Wk[(a*tx+b)*Cin + ci][n]:
 //   n = (py*sw + px)*Cout + co   (order 0, NHWC outputs)   or   n = (py*Cout + co)*sw + px   (order 1, planar outputs)
 //   value = w[py + sh*a, px + sw*b, co, ci], zero where the kernel index falls outside [0,kh) x [0,kw).
@@ -1083,8 +1178,7 @@ __global__ void subpixel_weights_kernel(const float* __restrict__ w, int kh, int
     const int t = (int)(r / cin);
     const int ta = t / tx, tb = t % tx;
     int py, px, co;
-    if (order == 0) { co = n % cout; int ph = n / cout; px = ph % sw; py = ph / sw; }
-    else { px = n % sw; int q = n / sw; co = q % cout; py = q / cout; }
+    decode_subpixel_column(order, n, cout, sw, &py, &px, &co);
     const int p = py + sh * ta, qq = px + sw * tb;
     wk[idx] = (p < kh && qq < kw) ? __ldg(w + (((int64_t)p * kw + qq) * cout + co) * cin + ci) : 0.f;
   }
@@ -1116,7 +1210,8 @@ __global__ void s2d_weights_kernel(const float* __restrict__ w, int kh, int kw, 
 __global__ void expand_bias_kernel(const float* __restrict__ bias, int cout, int sw, int N, int order, float* __restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  int co = order == 0 ? n % cout : (n / sw) % cout;
+  int py, px, co;
+  decode_subpixel_column(order, n, cout, sw, &py, &px, &co);
   out[n] = __ldg(bias + co);
 }
 
@@ -1586,8 +1681,7 @@ int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int
   bool vec = true;
   for (int n = 0; n < N; ++n) {
     int py, px, co;
-    if (order == 0) { co = n % cout; int ph = n / cout; px = ph % sw; py = ph / sw; }
-    else { px = n % sw; int q = n / sw; co = q % cout; py = q / cout; }
+    decode_subpixel_column(order, n, cout, sw, &py, &px, &co);
     off[n] = (int)(py * y_sh + px * y_sw + co * y_sc);
     dy[n] = (short)py;
     dx[n] = (short)px;
@@ -1610,6 +1704,8 @@ int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int
       if (off[n + e] != off[n] + e || dy[n + e] != dy[n] || dx[n + e] != dx[n] + e) run8 = false;
   }
   w.run8 = run8 ? 1 : 0;
+  w.order = order;
+  if (order == 2) { SAG_REQUIRE(cout == 32 && sw == 8 && w.BN == 256, SAG_EUNSUPPORTED, "deconv: column order 2 needs 32 channels, stride 8 and 256-wide tiles"); w.vec4 = 0; }
   cudaError_t e = cudaSuccess;
   if ((e = cudaMalloc(&w.col_off, sizeof(int) * N)) != cudaSuccess || (e = cudaMalloc(&w.col_dy, sizeof(short) * N)) != cudaSuccess ||
       (e = cudaMalloc(&w.col_dx, sizeof(short) * N)) != cudaSuccess || (e = cudaMalloc(&w.col_bias, sizeof(float) * N)) != cudaSuccess) {
@@ -1803,10 +1899,20 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
           encode(&tm.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
         a.out_mode = 1;
+    } else if (ep.gains != nullptr) {
+      // (checked below: the fusion has no fallback inside this launch -- the caller picks the unfused path instead)
     } else if (!raw && w.col_off != nullptr && w.run8 && a.out_bf2 == 0 && g.PW == UM_BM && g.ox0 == 0 && g.osx == 8 && g.y_sw == 1 &&
                ow_lim == UM_BM * 8 && aligned_y && g.y_sn % 4 == 0 && g.y_sh % 4 == 0) {
       a.out_mode = 2;
     }
+  }
+  if (ep.gains != nullptr) {
+    SAG_REQUIRE(w.order == 2 && w.BN == 256 && src == SRC_TMA && Z == 1 && g.PW == UM_BM && g.ox0 == 0 && g.osx == 8 &&
+                ow_lim == UM_BM * 8 && w.N % 256 == 0 && ep.gain_loc != nullptr && w.col_bias != nullptr &&
+                (reinterpret_cast<uintptr_t>(ep.gains) & 15) == 0 && ep.gain_plane % 4 == 0,
+                SAG_EUNSUPPORTED, "tcgen05 path: this launch cannot fuse the mask gains");
+    a.out_mode = 3;
+    a.gain_loc = ep.gain_loc; a.gains = ep.gains; a.gain_plane = ep.gain_plane;
   }
   SAG_REQUIRE(w.KC >= 1, SAG_EINVAL, "tcgen05 path: empty contraction");
   SAG_REQUIRE(ep.stat_sum == nullptr || w.N <= UM_MAX_N, SAG_EUNSUPPORTED, "tcgen05 path: statistics over %d columns", w.N);

@@ -434,10 +434,10 @@ size_t istft_mix_gain_floats(int rows, int n_frames, int wind, int segments) { r
 
 // S (rows, n_frames, wind) complex, mask (rows*tracks, n_frames, wind) logits, loc (rows, segments, 3*(tracks+1));
 // gains: scratch of istft_mix_gain_floats() floats; out (rows, t_out, 3) = samples [crop0, crop0 + t_out) of the mixed
-// inverse STFT.
+// inverse STFT.  mask == null: `gains` already holds the folded masks (deconv1's fused epilogue wrote them).
 int launch_istft_mix(const float* S, const float* mask, const float* loc, float* gains, int rows, int tracks, int n_frames, int wind,
                      int n_overlap, int crop0, int t_out, int segments, float* out, cudaStream_t st) {
-  SAG_REQUIRE(rows > 0 && n_overlap > 0 && wind % n_overlap == 0 && mask != nullptr && loc != nullptr && gains != nullptr, SAG_EINVAL, "istft_mix: bad arguments");
+  SAG_REQUIRE(rows > 0 && n_overlap > 0 && wind % n_overlap == 0 && loc != nullptr && gains != nullptr, SAG_EINVAL, "istft_mix: bad arguments");
   SAG_REQUIRE(istft_mix_supported(tracks, t_out, segments, wind), SAG_EUNSUPPORTED, "istft_mix: %d samples / %d segments / %d tracks", t_out, segments, tracks);
   const int hop = wind / n_overlap;
   const int nf = (n_frames / n_overlap) * n_overlap;      // myutils.py:187-188
@@ -445,9 +445,11 @@ int launch_istft_mix(const float* S, const float* mask, const float* loc, float*
   SAG_REQUIRE(nf > 0 && crop0 >= 0 && crop0 + t_out <= full, SAG_EINVAL, "istft_mix: crop [%d,%d) outside the %d output samples", crop0, crop0 + t_out, full);
   FftPlan p;
   SAG_TRY(get_plan(wind, &p));
-  launch_pdl(mask_gains_kernel, dim3(n_frames * (wind / 1024), rows), dim3(256), sizeof(float) * 12 * tracks, st, mask, loc, tracks,
-             n_frames, wind, segments, gains);
-  SAG_LAUNCH_CHECK();
+  if (mask != nullptr) {
+    launch_pdl(mask_gains_kernel, dim3(n_frames * (wind / 1024), rows), dim3(256), sizeof(float) * 12 * tracks, st, mask, loc, tracks,
+               n_frames, wind, segments, gains);
+    SAG_LAUNCH_CHECK();
+  }
   const size_t smem = 6 * sizeof(float2) * (size_t)wind;
   SAG_REQUIRE(smem <= 220 * 1024, SAG_EUNSUPPORTED, "istft_mix: %zu bytes of shared memory needed", smem);
   SAG_CHECK_CUDA(cudaFuncSetAttribute(istft_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -272,8 +272,11 @@ struct Fwd {
   }
 
   // tfw.deconv_2d VALID (core.py:96-153), output rows [row0,row1) only, arbitrary output strides.
+  // gain_mode: 0 = plain; 1 = (prepare pass only) also build the column-order-2 image of the mask-gain fusion; 2 = run the
+  // fused launch: no logits are written, `gains` (rows, 9, row1-row0, OW) <- `gain_loc` (see Epilogue)
   int deconv(const Act& x, int n, int hh, int ww, int cin, const std::string& scope, int kh, int kw, int cout, int sh,
-             int sw, int relu, const Act& y, int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw, int64_t y_sc) {
+             int sw, int relu, const Act& y, int row0, int row1, int64_t y_sn, int64_t y_sh, int64_t y_sw, int64_t y_sc,
+             int gain_mode = 0, const float* gain_loc = nullptr, float* gains = nullptr) {
     float* scratch = nullptr;
     if (tc()) {
       GatherGeom g0;
@@ -297,8 +300,15 @@ struct Fwd {
       const float* w_tf = W(scope + "/weights", &err);
       SAG_TRY(err);
       const UmmaWeights* img = nullptr;
-      SAG_TRY(image(scope, g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
-        return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &img));
+      if (gain_mode != 2)
+        SAG_TRY(image(scope, g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
+          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &img));
+      if (gain_mode != 0) {                       // the same layer with its columns in the order the fused epilogue drains them
+        const UmmaWeights* gimg = nullptr;
+        SAG_TRY(image(scope + "#gains", g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
+          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, 2, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &gimg));
+        if (gain_mode == 2) { img = gimg; ep.gain_loc = gain_loc; ep.gains = gains; ep.gain_plane = (int64_t)(row1 - row0) * oh_ow_w(ow_lim); }
+      }
       if (dry()) return SAG_OK;
       g.Cout = img->N;
       const double M = (double)Mrows, K = (double)g.T * g.Cin;
@@ -328,6 +338,8 @@ struct Fwd {
       }
     return SAG_OK;
   }
+
+  static int64_t oh_ow_w(int ow_lim) { return ow_lim; }
 
   // tfw.fully_connected (core.py:43-93) on rows with stride x.ld / y.ld
   int fc(const Act& x, int rows, int in, const std::string& scope, int out, int relu, const Act& y) {
@@ -647,19 +659,34 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
     const int r0 = full ? 0 : d.mask_ss - d.mask_skip, r1 = full ? OH : d.mask_tt - d.mask_skip;
     const int nr = r1 - r0;
     float* mask = ar.alloc<float>((int64_t)B * K * nr * OW);
+    const bool fuse_mix = istft_mix_supported(K, T, nt, wind) != 0;
+    float* gains = fuse_mix ? ar.alloc<float>((int64_t)istft_mix_gain_floats(B, n_msk, wind, nt)) : nullptr;
+    // Mask-gain fusion: in the hot loop (inverse STFT and mixing fused, no x_sep) only the 9 localization-weighted sums of the
+    // 32 sigmoid masks are needed per time-frequency bin, so deconv1's epilogue forms them in registers and the 117 MB of
+    // logits (B=32) are never written or re-read.  Needs the 256-wide TMA-fed tile whose column order the epilogue relies on;
+    // inference_ops (keep_sep_channels: the reference's `ends` expose the logits and x_sep) keeps the two-kernel path.
+    int ty1 = cdiv(kAudioKernel[0][0], kAudioStride[0][0]), tx1 = cdiv(kAudioKernel[0][1], kAudioStride[0][1]);
+    const int64_t M1 = (int64_t)B * ((r1 - 1) / kAudioStride[0][0] - r0 / kAudioStride[0][0] + 1) * cdiv(OW, kAudioStride[0][1]);
+    const bool can_gain = f.tc() && !full && fuse_mix && nt == 3 && K == 32 && kAudioStride[0][1] == 8 && OW == 1024 && h->tma_gather != 0 &&
+                          umma_tile_width(ty1 * tx1 * (int)cat[1].ld, kAudioStride[0][0] * kAudioStride[0][1] * K, M1) == 256;
+    const int gain_mode = !can_gain ? 0 : (ar.dry ? 1 : ((h->keep_sep_channels || !h->fuse_gains) ? 0 : 2));
+    if (gain_mode == 2) {                      // the fused epilogue reads the localization weights
+      SAG_TRY(join(overlap, h->ev[3]));
+      joined = true;
+    }
     SAG_TRY(f.deconv(cat[1], B, eh[1], ew[1], (int)cat[1].ld, "separation/deconv1", kAudioKernel[0][0], kAudioKernel[0][1], K,
                      kAudioStride[0][0], kAudioStride[0][1], 0, Act(mask, 1), r0, r1, (int64_t)K * nr * OW, OW, 1,
-                     (int64_t)nr * OW));
-    f.tap("separation/mask_logits", Act(mask, OW), {B, K, nr, OW});
+                     (int64_t)nr * OW, gain_mode, loc, gains));
+    if (gain_mode != 2) f.tap("separation/mask_logits", Act(mask, OW), {B, K, nr, OW});
     // sigmoid mask x STFT -> istft -> crop (model.py:334-347; myutils.py:181-211)
     // frames [mask_ss, mask_tt) of the full STFT / rows [mask_ss-skip, ..) of the full mask are strided views the
     // kernel does not take: compact them first (test-only path, skip_unused == 0).
-    SAG_TRY(join(overlap, h->ev[3]));        // localization weights are in place (the inverse STFT + mixing reads them)
-    joined = true;
+    if (!joined) {
+      SAG_TRY(join(overlap, h->ev[3]));      // localization weights are in place (the inverse STFT + mixing reads them)
+      joined = true;
+    }
     float* S2 = full ? ar.alloc<float>((int64_t)B * n_msk * wind * 2) : S;
     float* m2 = full ? ar.alloc<float>((int64_t)B * K * n_msk * OW) : mask;
-    const bool fuse_mix = istft_mix_supported(K, T, nt, wind) != 0;
-    float* gains = fuse_mix ? ar.alloc<float>((int64_t)istft_mix_gain_floats(B, n_msk, wind, nt)) : nullptr;
     if (!ar.dry) {
       if (full) {
         SAG_CHECK_CUDA(cudaMemcpy2DAsync(S2, sizeof(float) * n_msk * wind * 2, S_all + (int64_t)d.mask_ss * wind * 2,
@@ -673,7 +700,7 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
         // production path: inverse STFT and mixing fused by linearity (x_sep is never formed)
         ProfScope ps(PROF_ISTFT, 5.0 * wind * std::log2((double)wind) * B * 1.5 * n_msk + 18.0 * B * K * (double)n_msk * wind,
                      4.0 * B * ((double)K * n_msk * wind + 2.0 * n_msk * wind + 3.0 * T), st);
-        SAG_TRY(launch_istft_mix(S2, m2, loc, gains, B, K, n_msk, wind, 4, d.final_crop, T, nt, out, st));
+        SAG_TRY(launch_istft_mix(S2, gain_mode == 2 ? nullptr : m2, loc, gains, B, K, n_msk, wind, 4, d.final_crop, T, nt, out, st));
         h->last_launches = g_launch_count;
         return SAG_OK;
       }

@@ -84,6 +84,7 @@ struct sag_handle {
   // join): STFT + audio encoder + audio-fc beside the visual towers, the localization FCs beside the U-Net decoder.  Those
   // are chains of small grids that leave most SMs idle on their own and fill the tails of the towers' persistent kernels.
   int overlap = 1;
+  int fuse_gains = 1;    // fold sigmoid + the 32 -> 9 localization-weighted sums into deconv1's epilogue where the tile plan allows
   cudaStream_t side = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

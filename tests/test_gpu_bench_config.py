@@ -164,3 +164,25 @@ def test_forward_fails_loudly_without_the_batch_plan():
     assert rc == L.SAG_ESTATE and b'sag_workspace_bytes' in L.lib().sag_last_error()
     m.forward_into(a5, None, None, out5)                         # the façade plans it, then it runs
     torch.cuda.synchronize()
+
+
+def test_mask_gain_fusion_is_bit_identical_to_the_two_kernel_path():
+    """At the benchmarked batch deconv1's epilogue folds sigmoid + the 32 -> 9 localization-weighted sums (mask_gains_kernel's
+    arithmetic, same fmaf order) and never writes the logits: same gains, hence the same waveform bit for bit -- with and
+    without the side-stream overlap, and also on CTA pairs."""
+    B = 32
+    ref, m = _pair(['audio', 'video'], 99, 'bf16x3', stress=True)
+    a, v = cu(_audio(B, 130)), cu(_video(B, 131))
+    outs = {}
+    for fuse, ov, pair in ((1, 1, -1), (0, 1, -1), (1, 0, -1), (1, 1, 1)):
+        m.set_option('fuse_gains', fuse)
+        m.set_option('overlap', ov)
+        m.set_option('cta_pair', pair)
+        o = torch.empty((B, 4800, 3), device='cuda')
+        m.forward_into(a, v, None, o)
+        torch.cuda.synchronize()
+        outs[(fuse, ov, pair)] = o
+    assert torch.equal(outs[(1, 1, -1)], outs[(0, 1, -1)])
+    assert torch.equal(outs[(1, 1, -1)], outs[(1, 0, -1)])
+    assert _rel(outs[(1, 1, 1)], outs[(1, 1, -1)]) < 1e-4          # pairs regroup the batch-norm partial sums
+    assert _rel(outs[(1, 1, -1)], ref.inference_ops(a.cpu().numpy(), video=v.cpu().numpy())) < 1e-3
