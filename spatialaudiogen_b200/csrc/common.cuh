@@ -142,6 +142,19 @@ __device__ __forceinline__ void fx_atomic_add(unsigned long long* acc2, float p)
   atomicAdd(acc2 + 1, (unsigned long long)((d - fl) * 1099511627776.0));
 }
 #endif
+#ifdef __CUDACC__
+// tf.sigmoid (model.py:334) for the mask path, on the special-function unit: 1 / (1 + 2^(-x * log2 e)) with ex2.approx and
+// rcp.approx (relative error ~3e-7, five instructions).  mask_gains_kernel (fft.cu) and the fused deconv1 epilogue
+// (conv_umma.cu) both use exactly this sequence, so the two paths produce the same gains bit for bit.
+__device__ __forceinline__ float sigmoid_sfu(float x) {
+  float e, r;
+  const float t = __fmul_rn(x, -1.4426950408889634f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  const float d = __fadd_rn(1.f, e);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
+#endif
 #if defined(__CUDACC__)
 __host__ __device__
 #endif

@@ -937,7 +937,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
               }
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const float sg = 1.f / (1.f + expf(-v[e]));                  // tf.sigmoid (model.py:334)
+                const float sg = sigmoid_sfu(v[e]);                         // tf.sigmoid (model.py:334)
                 const float4* w4 = reinterpret_cast<const float4*>(s_w + (sub * 16 + e) * 12);
                 const float4 wa = w4[0], wb = w4[1], wc = w4[2];
                 const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};

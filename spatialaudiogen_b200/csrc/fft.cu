@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(256) mask_gains_kernel(const float* __restrict
     for (int u = 0; u < 8; ++u) {
       if (k0 + u >= tracks) break;
       float4 sg;                                             // tf.sigmoid (model.py:334)
-      sg.x = 1.f / (1.f + expf(-m[u].x)); sg.y = 1.f / (1.f + expf(-m[u].y));
-      sg.z = 1.f / (1.f + expf(-m[u].z)); sg.w = 1.f / (1.f + expf(-m[u].w));
+      sg.x = sigmoid_sfu(m[u].x); sg.y = sigmoid_sfu(m[u].y);
+      sg.z = sigmoid_sfu(m[u].z); sg.w = sigmoid_sfu(m[u].w);
       const float4* w4 = reinterpret_cast<const float4*>(s_w + (k0 + u) * 12);
       const float4 wa = w4[0], wb = w4[1], wc = w4[2];
       const float w[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x};

@@ -53,93 +53,116 @@ def _imread(fn):
 
 
 class AudioReader(object):
-    """feeder.py:50-105."""
+    """The `ambix/` folder of a clip -- one wav file per second -- as one zero-padded timeline (reference feeder.py:50-105).
+
+    `get(t, n)` returns the n samples that start at time t; samples before the clip or past its last file are zeros.  Like the
+    reference, positions are truncated, not rounded: the first sample is int(t * rate) of the clip, and the offset inside the
+    file that holds it is int((t - second) * rate)."""
+
     def __init__(self, audio_folder, rate=None, ambi_order=1):
         self.audio_folder = audio_folder
-        fns = [f for f in os.listdir(audio_folder) if f.endswith('.wav')]
-        self.num_files = len(fns)
-        data, file_rate = load_wav(os.path.join(audio_folder, sorted(fns)[0]))
+        names = sorted(f for f in os.listdir(audio_folder) if f.endswith('.wav'))
+        self.num_files = len(names)
+        probe, file_rate = load_wav(os.path.join(audio_folder, names[0]))
         self.rate = float(file_rate) if rate is None else rate
-        self.num_channels = min((data.shape[1], (ambi_order + 1) ** 2))
+        self.num_channels = min(probe.shape[1], (ambi_order + 1) ** 2)
         self.duration = self.num_files
         self.num_frames = int(self.duration * self.rate)
 
+    def _file(self, second):
+        return load_wav('{}/{:06d}.wav'.format(self.audio_folder, second), self.rate)[0]
+
+    def _copy_span(self, out, dst, t0, count):
+        """`count` samples starting at time t0 >= 0 (inside the clip) into out[dst:], file by file."""
+        second = int(t0)
+        skip = int((t0 - second) * self.rate)                     # offset inside the first file
+        last = min(int(np.ceil(t0 + count / float(self.rate))), self.num_files)
+        while count > 0 and second < last:
+            data = self._file(second)[skip:skip + count, :self.num_channels]
+            out[dst:dst + data.shape[0]] = data
+            dst += data.shape[0]
+            count -= data.shape[0]
+            second, skip = second + 1, 0
+
     def get(self, start_time, size, rotation=None):
-        """`size` samples starting at `start_time` seconds; whatever falls before 0 or after the last file is zero
-        (feeder.py:66-90).  The offset inside the first file is int(frac(start_time) * rate), like the reference."""
         out = np.zeros((size, self.num_channels))
-        lead = max(-int(start_time * self.rate), 0)              # samples before the start of the clip
-        t0 = 0. if lead > 0 else start_time
-        want = size - lead
-        first_frame = 0 if lead > 0 else int(start_time * self.rate)
-        want -= max(first_frame + want - self.num_frames, 0)      # samples beyond the end of the clip
-        if want > 0:
-            sec0 = int(t0)
-            sec1 = min(int(np.ceil(t0 + want / float(self.rate))), self.num_files)
-            parts = [load_wav('{}/{:06d}.wav'.format(self.audio_folder, i), self.rate)[0] for i in range(sec0, sec1)]
-            data = parts[0] if len(parts) == 1 else np.concatenate(parts, axis=0)
-            ss = int((t0 - sec0) * self.rate)
-            data = data[ss:ss + want, :self.num_channels]
-            out[lead:lead + data.shape[0]] = data
-        if rotation is not None:                                 # feeder.py:92-102: yaw rotation of (W, Y, Z, X)
+        first = int(start_time * self.rate)                        # (truncation toward zero, also for negative times)
+        lead = max(-first, 0)                                      # zeros before the start of the clip
+        t0, first = (0., 0) if lead > 0 else (start_time, first)
+        count = size - lead
+        count -= max(first + count - self.num_frames, 0)           # zeros past the end of the clip
+        if count > 0:
+            self._copy_span(out, lead, t0, count)
+        if rotation is not None:                                   # yaw of the sound field about the vertical axis (feeder.py:92-102)
             assert -np.pi <= rotation < np.pi
             c, s = np.cos(rotation), np.sin(rotation)
-            out = np.dot(out, np.array([[1, 0, 0, 0], [0, c, 0, s], [0, 0, 1, 0], [0, -s, 0, c]]).T)
+            out = np.dot(out, np.array([[1, 0, 0, 0], [0, c, 0, s], [0, 0, 1, 0], [0, -s, 0, c]]).T)      # rows act on (W, Y, Z, X)
         return out
 
 
 class VideoReader(object):
-    """feeder.py:108-135."""
+    """The `video/` (or `flow/`) folder of a clip: numbered jpg frames at 10 per second (reference feeder.py:108-135).
+    Without `img_prep` the frames come back as decoded -- uint8 -- which is what the device-side ingest takes
+    (SptAudioGen.forward_into prepares them in the frame-ingest kernel)."""
+    RAW_RATE = 10.
+
     def __init__(self, video_folder, rate=None, img_prep=None):
-        raw_rate = 10.
         self.video_folder = video_folder
-        self.rate = rate if rate is not None else raw_rate
-        self.img_prep = img_prep if img_prep is not None else lambda x: x
-        frame_fns = [fn for fn in os.listdir(video_folder) if fn.endswith('.jpg')]
-        self.num_frames = len(frame_fns)
-        self.duration = self.num_frames / raw_rate
-        self.frame_shape = self.img_prep(_imread(os.path.join(video_folder, sorted(frame_fns)[0]))).shape
+        self.rate = self.RAW_RATE if rate is None else rate
+        self.img_prep = img_prep if img_prep is not None else (lambda x: x)
+        names = sorted(f for f in os.listdir(video_folder) if f.endswith('.jpg'))
+        self.num_frames = len(names)
+        self.duration = self.num_frames / self.RAW_RATE
+        self.frame_shape = self.img_prep(_imread(os.path.join(video_folder, names[0]))).shape
+
+    def frame(self, index):
+        return self.img_prep(_imread(os.path.join(self.video_folder, '{:06d}.jpg'.format(index))))
 
     def get_by_index(self, start_time, size, rotation=None):
-        ss = max(int(start_time * self.rate), 0)
-        chunk = [self.img_prep(_imread(os.path.join(self.video_folder, '{:06d}.jpg'.format(fno)))) for fno in range(ss, ss + size)]
-        chunk = np.stack(chunk, 0) if len(chunk) > 1 else chunk[0][np.newaxis]
-        if rotation is not None:
-            roll = -int(rotation / (2. * np.pi) * self.frame_shape[1])
-            chunk = np.roll(chunk, roll, axis=2)
+        first = max(int(start_time * self.rate), 0)
+        chunk = np.stack([self.frame(first + k) for k in range(size)], 0)
+        if rotation is not None:                                   # the same yaw as the audio: a roll along the panorama's width
+            chunk = np.roll(chunk, -int(rotation / (2. * np.pi) * self.frame_shape[1]), axis=2)
         return chunk
 
 
 def dequantize_flow(chunk_u8, limits):
-    """feeder.py:147-161 on (T, H, W, 3) uint8 frames (channel 0 = angle, 2 = magnitude) with their (T, 2) (min, max) rows of
-    flow_limits.npy -> float32 (mag cos, mag sin, mag).  (The device does the same inside the frame-ingest kernel.)"""
+    """feeder.py:147-161 on (..., H, W, 3) uint8 flow frames (channel 0 = angle, 2 = magnitude) with one (min, max) row of
+    flow_limits.npy per frame -> float32 (mag cos, mag sin, mag).  (The device does the same inside the frame-ingest kernel.)"""
     chunk = np.asarray(chunk_u8).astype(np.float32)
-    lead = chunk.shape[:-3]
-    chunk = chunk.reshape((-1,) + chunk.shape[-3:])
+    shape = chunk.shape
+    chunk = chunk.reshape((-1,) + shape[-3:])
     limits = np.asarray(limits).reshape(-1, 2)
-    m_min = limits[:, 0].reshape((-1, 1, 1))
-    m_max = limits[:, 1].reshape((-1, 1, 1))
-    chunk[:, :, :, 2] *= (m_max - m_min) / 255.              # magnitude back to its range
-    chunk[:, :, :, 2] += m_min
-    chunk[:, :, :, 0] *= (2 * np.pi) / 255.                  # angle
-    chunk[:, :, :, 1] = chunk[:, :, :, 2] * np.sin(chunk[:, :, :, 0])
-    chunk[:, :, :, 0] = chunk[:, :, :, 2] * np.cos(chunk[:, :, :, 0])
-    return chunk.reshape(lead + chunk.shape[-3:])
+    lo, hi = limits[:, 0].reshape((-1, 1, 1)), limits[:, 1].reshape((-1, 1, 1))
+    mag, ang = chunk[:, :, :, 2], chunk[:, :, :, 0]                # (views: the in-place steps below round like the reference's)
+    mag *= (hi - lo) / 255.
+    mag += lo
+    ang *= (2 * np.pi) / 255.
+    chunk[:, :, :, 1] = mag * np.sin(ang)
+    chunk[:, :, :, 0] = mag * np.cos(ang)
+    return chunk.reshape(shape)
 
 
 class FlowReader(object):
-    """feeder.py:138-161."""
-    def __init__(self, flow_dir, flow_lims_fn, rate=None, flow_prep=None):
+    """Optical flow stored as 8-bit frames + per-frame magnitude limits (reference feeder.py:138-161).  raw=True returns the
+    quantised frames and their limits (what the device-side ingest takes) instead of de-quantising on the host."""
+
+    def __init__(self, flow_dir, flow_lims_fn, rate=None, flow_prep=None, raw=False):
         self.reader = VideoReader(flow_dir, rate=rate)
         self.lims = np.load(flow_lims_fn)
         self.rate = self.reader.rate
         self.duration = self.reader.duration
-        self.flow_prep = flow_prep if flow_prep is not None else lambda x: x
+        self.flow_prep = flow_prep if flow_prep is not None else (lambda x: x)
+        self.raw = raw
+
+    def limits(self, start_time, size):
+        first = max(int(start_time * self.rate), 0)
+        return self.lims[first:first + size]
 
     def get_by_index(self, start_time, size, rotation=None):
         chunk = self.reader.get_by_index(start_time, size, rotation)
-        ss = max(int(start_time * self.rate), 0)
-        return dequantize_flow(chunk, self.lims[ss:ss + chunk.shape[0]])
+        lims = self.limits(start_time, chunk.shape[0])
+        return (chunk, lims) if getattr(self, 'raw', False) else dequantize_flow(chunk, lims)
 
 
 def sample_folders(directory, subset_fn=None):
@@ -168,67 +191,83 @@ def load_channel_masks(audio_layouts_fn):
     return out
 
 
+def chunk_schedule(times, powers, skip_rate=None, skip_silence_thr=None, start_time=0.5, sample_duration=None, num_threads=1,
+                   thread_id=0):
+    """Which entries of a clip's audio_pow.lst a reader visits (reference feeder.py:208-236), as array filters applied in the
+    reference's order: every skip_rate-th entry, then entries louder than the silence threshold, then the [start_time,
+    start_time + sample_duration) window (a start of 0.5 or less keeps everything), then this thread's contiguous slice."""
+    t, p = np.asarray(times, np.float64), np.asarray(powers, np.float64)
+    if skip_rate is not None:
+        t, p = t[::skip_rate], p[::skip_rate]
+    if skip_silence_thr is not None:
+        t = t[p > skip_silence_thr]
+    if start_time > 0.5:
+        t = t[t >= start_time]
+    if sample_duration is not None:
+        t = t[t < start_time + sample_duration]
+    if num_threads > 1:
+        cut = np.linspace(0, len(t), num_threads + 1).astype(int)
+        t = t[cut[thread_id]:cut[thread_id + 1]]
+    return [float(x) for x in t]
+
+
 class SampleReader(object):
-    """feeder.py:164-278: iterates the chunk times of `<folder>/audio_pow.lst`."""
+    """One clip's windows in schedule order (reference feeder.py:164-278): `get()` returns {'id', 'ambix'[, 'video'][, 'flow']}
+    for the next scheduled time, None at the end; `loop_chunks(n)` iterates.  The audio window starts context/2 before the
+    scheduled time; all readers of a window share one random yaw when random_rotations is on.  raw_flow=True yields the
+    quantised flow frames plus 'flow_limits' instead of float frames."""
+
     def __init__(self, folder, ambi_order=1, audio_rate=48000, video_rate=10, context=1.0, duration=0.1, return_video=True,
                  img_prep=None, return_flow=False, flow_prep=None, skip_silence_thr=None, shuffle=True, start_time=0.5,
-                 sample_duration=None, skip_rate=None, random_rotations=True, num_threads=1, thread_id=0):
-        a2v = float(audio_rate) / video_rate
-        snd_dur, vid_dur, snd_ctx = duration * audio_rate, duration * video_rate, context * audio_rate
-        self.video_id = os.path.split(folder)[-1]
-        assert a2v == int(a2v)
-        assert abs(snd_dur - round(snd_dur)) < 1e-6 and abs(vid_dur - round(vid_dur)) < 1e-6 and abs(snd_ctx - round(snd_ctx)) < 1e-6
+                 sample_duration=None, skip_rate=None, random_rotations=True, num_threads=1, thread_id=0, raw_flow=False):
+        n_audio, n_video, n_context = duration * audio_rate, duration * video_rate, context * audio_rate
+        assert float(audio_rate) / video_rate == int(float(audio_rate) / video_rate)
+        for v in (n_audio, n_video, n_context):
+            assert abs(v - round(v)) < 1e-6                       # whole numbers of samples / frames
+        self.folder, self.video_id = folder, os.path.split(folder)[-1]
+        self.duration, self.context = duration, context
+        self.audio_rate, self.video_rate = audio_rate, video_rate
+        self.return_video, self.return_flow, self.random_rotations, self.raw_flow = return_video, return_flow, random_rotations, raw_flow
         self.audio_reader = AudioReader(os.path.join(folder, 'ambix'), audio_rate, ambi_order)
         self.video_reader = VideoReader(os.path.join(folder, 'video'), video_rate, img_prep) if return_video else None
         if return_flow:
             flow_dir = os.path.join(folder, 'flow')
             self.flow_reader = FlowReader(flow_dir, os.path.join(flow_dir, 'flow_limits.npy'), video_rate, flow_prep)
-        self.folder, self.duration, self.context = folder, duration, context
-        self.audio_rate, self.video_rate = audio_rate, video_rate
-        self.audio_size = int(round(snd_dur)) + int(round(snd_ctx)) - 1
-        self.video_size = int(round(vid_dur))
+            if raw_flow:
+                self.flow_reader.raw = True
+        self.audio_size = int(round(n_audio)) + int(round(n_context)) - 1
+        self.video_size = int(round(n_video))
         self.video_shape = self.video_reader.frame_shape if return_video else None
-        self.return_video, self.return_flow, self.random_rotations = return_video, return_flow, random_rotations
-        lines = [l.strip().split() for l in open(os.path.join(folder, 'audio_pow.lst')) if l.strip()]
-        chunks_t, chunks_pow = [float(l[0]) for l in lines], [float(l[1]) for l in lines]
-        if skip_rate is not None:
-            keep = range(0, len(chunks_t), skip_rate)
-            chunks_t, chunks_pow = [chunks_t[i] for i in keep], [chunks_pow[i] for i in keep]
-        if skip_silence_thr is not None:
-            chunks_t = [t for t, p in zip(chunks_t, chunks_pow) if p > skip_silence_thr]
-        if start_time > 0.5:
-            chunks_t = [t for t in chunks_t if t >= start_time]
-        if sample_duration is not None:
-            chunks_t = [t for t in chunks_t if t < start_time + sample_duration]
-        if num_threads > 1:
-            lims = np.linspace(0, len(chunks_t), num_threads + 1).astype(int)
-            chunks_t = chunks_t[lims[thread_id]:lims[thread_id + 1]]
+        table = np.loadtxt(os.path.join(folder, 'audio_pow.lst'), ndmin=2)
+        self.chunks_t = chunk_schedule(table[:, 0], table[:, 1], skip_rate, skip_silence_thr, start_time, sample_duration,
+                                       num_threads, thread_id)
         if shuffle:
-            random.shuffle(chunks_t)
-        self.chunks_t = chunks_t
+            random.shuffle(self.chunks_t)
         self.head = -1
 
     def get(self):
         self.head += 1
         if self.head >= len(self.chunks_t):
             return None
-        self.cur_t = cur_t = self.chunks_t[self.head]
-        rotation = random.random() * 2 * np.pi - np.pi if self.random_rotations else None
-        chunks = {'id': self.video_id + ' ' + str(cur_t)}
-        chunks['ambix'] = self.audio_reader.get(cur_t - self.context / 2, self.audio_size, rotation)
+        t = self.cur_t = self.chunks_t[self.head]
+        yaw = random.random() * 2 * np.pi - np.pi if self.random_rotations else None
+        window = {'id': self.video_id + ' ' + str(t),
+                  'ambix': self.audio_reader.get(t - self.context / 2, self.audio_size, yaw)}
         if self.return_video:
-            chunks['video'] = self.video_reader.get_by_index(cur_t, self.video_size, rotation)
+            window['video'] = self.video_reader.get_by_index(t, self.video_size, yaw)
         if self.return_flow:
-            chunks['flow'] = self.flow_reader.get_by_index(cur_t, self.video_size, rotation)
-        return chunks
+            flow = self.flow_reader.get_by_index(t, self.video_size, yaw)
+            if self.raw_flow:
+                window['flow'], window['flow_limits'] = flow
+            else:
+                window['flow'] = flow
+        return window
 
     def loop_chunks(self, n=np.inf):
-        k = 0
-        while True:
-            k += 1
-            if k > n:
-                break
-            chunks = self.get()
-            if chunks is None:
-                break
-            yield chunks
+        served = 0
+        while served < n:
+            window = self.get()
+            if window is None:
+                return
+            served += 1
+            yield window
