@@ -152,7 +152,7 @@ class W2XYZ(object):
                                       context=p.context, duration=self.duration, return_video=VIDEO in p.encoders,
                                       img_prep=None, return_flow=FLOW in p.encoders, start_time=deploy_start,
                                       sample_duration=deploy_duration, skip_silence_thr=None, shuffle=False,
-                                      random_rotations=False, skip_rate=None)
+                                      random_rotations=False, skip_rate=None, raw_flow=True)
         if not reader.chunks_t:
             raise ValueError('%s has no windows in [%s, %s)' % (input_folder, deploy_start, deploy_start + deploy_duration))
         dt = reader.chunks_t[0] - deploy_start

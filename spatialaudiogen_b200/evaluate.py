@@ -82,7 +82,7 @@ def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
         audio_input = ambix[:, :, :1].contiguous()                          # eval.py:69
         target = ambix[:, ss:ss + t, 1:].contiguous()                       # eval.py:70
         pred = torch.empty((ambix.shape[0], t, 3), dtype=torch.float32, device=ambix.device)
-        model.forward_into(audio_input, b.get('video'), b.get('flow'), pred)       # the hot loop (fused inverse STFT + mixing)
+        model.forward_into(audio_input, b.get('video'), b.get('flow'), pred, b.get('flow_limits'))   # the hot loop (fused inverse STFT + mixing)
         rows, _ = metric_rows(pred, target, mono=audio_input[:, ss:ss + t], layout=b.get('mask'), audio_rate=audio_rate,
                               rms_maps=rms_maps)
         ids.extend(b['id'])
@@ -104,19 +104,22 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
     pending = []
 
     def flush(items):
+        # frames travel as decoded (uint8; flow with its per-frame limits) and are prepared by the ingest kernel on the device
         b = {'id': [c['id'] for c in items],
              'ambix': torch.as_tensor(np.stack([c['ambix'] for c in items]).astype(np.float32)).to(dev),
              'mask': torch.as_tensor(np.stack([c['mask'] for c in items]).astype(np.float32)).to(dev)}
         for k in (VIDEO, FLOW):
             if k in params.encoders:
-                b[k] = torch.as_tensor(np.stack([c[k] for c in items]).astype(np.float32)).to(dev)
+                b[k] = torch.as_tensor(np.ascontiguousarray(np.stack([c[k] for c in items]))).to(dev)
+        if FLOW in params.encoders:
+            b['flow_limits'] = torch.as_tensor(np.stack([np.asarray(c['flow_limits'], np.float64).reshape(-1, 2)[0] for c in items])).to(dev)
         return b
 
     for folder in folders:
         r = readers.SampleReader(folder, ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
                                  context=params.context, duration=0.1, return_video=VIDEO in params.encoders,
-                                 img_prep=myutils.img_prep_fcn(), return_flow=FLOW in params.encoders, skip_silence_thr=None,
-                                 shuffle=False, random_rotations=False, skip_rate=10)
+                                 img_prep=None, return_flow=FLOW in params.encoders, skip_silence_thr=None,
+                                 shuffle=False, random_rotations=False, skip_rate=10, raw_flow=True)
         mask = np.ones(4) if channel_masks is None else np.asarray(channel_masks.get(r.video_id, np.ones(4)))
         for c in r.loop_chunks():
             c['mask'] = mask

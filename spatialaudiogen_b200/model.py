@@ -222,11 +222,12 @@ class SptAudioGen(StageOps):
                 self.forward_into(audio, video, flow, out, flow_limits)
         return g
 
-    def inference_ops(self, audio, video=None, flow=None, is_training=True):
+    def inference_ops(self, audio, video=None, flow=None, is_training=True, flow_limits=None):
         """reference model.py:356-434.  audio (B, snd_size, 1); video / flow (B, 1, H, W, 3); returns the
         (B, snd_dur, 3) first-order channels (Y, Z, X) as a CUDA tensor.  `is_training` is accepted for API
         compatibility: the reference never forwards it to the visual towers (they always use batch statistics,
-        model.py:197) and no other layer depends on it."""
+        model.py:197) and no other layer depends on it.  video / flow may also be the uint8 frames as decoded from disk (see
+        forward_into; uint8 flow with `flow_limits`)."""
         if not self._weights_ready:
             raise RuntimeError('load_weights() must be called before inference_ops()')
         with torch.cuda.device(self.device):
@@ -239,7 +240,8 @@ class SptAudioGen(StageOps):
                 if key in self.encoders:
                     if t is None:
                         raise ValueError('%s input required by encoders=%s' % (key, self.encoders))
-                    t = L.f32(t, self.device)
+                    t = torch.as_tensor(t)
+                    t = t.to(self.device).contiguous() if t.dtype == torch.uint8 else L.f32(t, self.device)
                     want = (B, 1, self.dims_frame()[0], self.dims_frame()[1], 3)
                     if tuple(t.shape) != want:
                         raise ValueError('%s must be %s, got %s' % (key, want, tuple(t.shape)))
@@ -251,7 +253,9 @@ class SptAudioGen(StageOps):
             # forward_into / inference_stream / W2XYZ (the deploy and eval hot loops) use the fused kernel
             self.set_option('keep_sep_channels', 1)
             try:
-                self.forward_into(audio, ins.get(VIDEO), ins.get(FLOW), out)
+                if flow_limits is not None:
+                    flow_limits = torch.as_tensor(flow_limits, dtype=torch.float64).to(self.device).contiguous()
+                self.forward_into(audio, ins.get(VIDEO), ins.get(FLOW), out, flow_limits)
             finally:
                 self.set_option('keep_sep_channels', 0)
             self._collect_ends()
