@@ -522,7 +522,7 @@ def main():
             break
         except Exception:
             continue
-    products = {'bf16x3': 3, 'bf16': 1}.get(precision)
+    products = {'bf16x3': 3, 'bf16': 1, 'mixed': 3}.get(precision)
     roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf,
                 'traffic': traffic, 'traffic_source': traffic_src,
                 'algorithmic_bytes_per_launch': (agg['conv'][2] + agg['deconv'][2] + agg['fc'][2]) / max(dense_n, 1),
@@ -553,7 +553,7 @@ def main():
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': n_max, 'warmup': max(3, args.warmup),
             'ms_per_step': ms / max(n_max, 1), 'higher_is_better': True, 'scaling': 'weak' if args.config in (1, 2, 3) else 'strong',
             'vs_baseline': None,
-            'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'bf16x3': 'bf16x3(f32-grade)'}.get(precision, precision),
+            'dtype': {'fp32': 'f32', 'bf16': 'bf16', 'bf16x3': 'bf16x3(f32-grade)', 'mixed': 'bf16x3(f32-grade), decoder deconv5-2 bf16'}.get(precision, precision),
             'data': 'synthetic', 'config': workload_config(encoders, B, precision, args, world),
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'clocks': clocks}
     line.update(extra)

@@ -9,8 +9,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libsag.so')
 
-SAG_PREC_FP32, SAG_PREC_BF16, SAG_PREC_BF16X3 = 0, 2, 3
-PRECISIONS = {'fp32': SAG_PREC_FP32, 'bf16': SAG_PREC_BF16, 'bf16x3': SAG_PREC_BF16X3}
+SAG_PREC_FP32, SAG_PREC_BF16, SAG_PREC_BF16X3, SAG_PREC_MIXED = 0, 2, 3, 4
+PRECISIONS = {'fp32': SAG_PREC_FP32, 'bf16': SAG_PREC_BF16, 'bf16x3': SAG_PREC_BF16X3, 'mixed': SAG_PREC_MIXED}
 SAG_FRAMES_F32, SAG_FRAMES_U8 = 0, 1
 SAG_SEP_NONE, SAG_SEP_UNET_MASK = 0, 1
 

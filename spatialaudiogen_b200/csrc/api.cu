@@ -18,7 +18,7 @@ bool is_deconv_weight(const std::string& n) {
   return n.rfind("separation/deconv", 0) == 0 && n.size() > 8 && n.compare(n.size() - 8, 8, "/weights") == 0;
 }
 
-bool valid_precision(int p) { return p == SAG_PREC_FP32 || p == SAG_PREC_BF16 || p == SAG_PREC_BF16X3; }
+bool valid_precision(int p) { return p == SAG_PREC_FP32 || p == SAG_PREC_BF16 || p == SAG_PREC_BF16X3 || p == SAG_PREC_MIXED; }
 
 void free_tensor(DevTensor& t) {
   if (t.p) cudaFree(t.p);

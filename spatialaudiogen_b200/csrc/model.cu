@@ -138,6 +138,7 @@ int build_expected(sag_handle* h) {
 int launch_gather_gemm(int precision, const float* x, const float* w, float* y, const GatherGeom& g, const Epilogue& ep,
                        cudaStream_t st) {
   if (precision == SAG_PREC_FP32) return launch_gather_gemm_ffma(x, w, y, g, ep, st);
+  if (precision == SAG_PREC_MIXED) precision = SAG_PREC_BF16X3;      // (the per-layer plan only names layers of the forward)
   // one-shot tcgen05 contraction (stage entry points): pack, run, release
   for (int t = 0; t < g.T; ++t)
     SAG_REQUIRE(g.widx[t] == t, SAG_EUNSUPPORTED, "tcgen05 path needs weights in tap order");
@@ -162,6 +163,14 @@ struct Fwd {
   bool private_scratch = false;   // layers that may run beside others on the side stream take their own split-K scratch
   bool dry() const { return ar.dry; }
   bool tc() const { return prec != SAG_PREC_FP32; }
+  bool split_planes() const { return prec == SAG_PREC_BF16X3 || prec == SAG_PREC_MIXED; }     // activations carry hi + lo planes
+  // arithmetic of one layer's contraction under the handle's precision (SAG_PREC_MIXED: see include/sag.h)
+  int layer_prec(const std::string& scope) const {
+    if (prec != SAG_PREC_MIXED) return prec;
+    for (const char* s : {"separation/deconv5", "separation/deconv4", "separation/deconv3", "separation/deconv2"})
+      if (scope == s) return SAG_PREC_BF16;
+    return SAG_PREC_BF16X3;
+  }
 
   // activation buffer in the format the contractions of this precision read
   Act alloc_act(int64_t pixels, int64_t ld) {
@@ -170,7 +179,7 @@ struct Fwd {
     if (!tc()) {
       a.v = ActView(ar.alloc<float>(pixels * ld));
     } else {
-      const int planes = prec == SAG_PREC_BF16X3 ? 2 : 1;
+      const int planes = split_planes() ? 2 : 1;
       const int64_t plane_bytes = ((pixels * ld * 2 + 255) / 256) * 256;
       char* p = ar.alloc<char>(plane_bytes * planes);
       a.v = ActView(p, ACT_BF2, planes == 2 ? plane_bytes : 0);
@@ -190,7 +199,8 @@ struct Fwd {
   // the tensor-core operand image of a layer: built in the prepare pass (sag_workspace_bytes), only looked up afterwards
   template <class PackFn>
   int image(const std::string& scope, int K, int N, int64_t Mrows, PackFn pack, const UmmaWeights** out) {
-    const std::string key = scope + "#" + std::to_string(prec) + "#" + std::to_string(umma_tile_width(K, N, Mrows));
+    const std::string base = scope.substr(0, scope.find('#'));
+    const std::string key = scope + "#" + std::to_string(layer_prec(base)) + "#" + std::to_string(umma_tile_width(K, N, Mrows));
     auto it = h->umma.find(key);
     if (it == h->umma.end()) {
       SAG_REQUIRE(ar.prepare, SAG_ESTATE,
@@ -256,7 +266,7 @@ struct Fwd {
     const UmmaWeights* img = nullptr;
     if (tc()) {
       const int Kg = g.T * g.Cin;
-      SAG_TRY(image(scope, Kg, cout, Mrows, [&](UmmaWeights* uw) { return umma_pack_weights(w, Kg, cout, cout, prec, Mrows, uw, st); }, &img));
+      SAG_TRY(image(scope, Kg, cout, Mrows, [&](UmmaWeights* uw) { return umma_pack_weights(w, Kg, cout, cout, layer_prec(scope), Mrows, uw, st); }, &img));
     }
     if (dry()) return SAG_OK;
     Epilogue ep{b, relu, ssum, ssqs};
@@ -302,11 +312,11 @@ struct Fwd {
       const UmmaWeights* img = nullptr;
       if (gain_mode != 2)
         SAG_TRY(image(scope, g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
-          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &img));
+          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, order, y_sh, y_sw, y_sc, layer_prec(scope), Mrows, uw, st); }, &img));
       if (gain_mode != 0) {                       // the same layer with its columns in the order the fused epilogue drains them
         const UmmaWeights* gimg = nullptr;
         SAG_TRY(image(scope + "#gains", g.T * g.Cin, sh * sw * cout, Mrows, [&](UmmaWeights* uw) {
-          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, 2, y_sh, y_sw, y_sc, prec, Mrows, uw, st); }, &gimg));
+          return umma_pack_deconv(w_tf, b, kh, kw, cout, cin, sh, sw, 2, y_sh, y_sw, y_sc, layer_prec(scope), Mrows, uw, st); }, &gimg));
         if (gain_mode == 2) { img = gimg; ep.gain_loc = gain_loc; ep.gains = gains; ep.gain_plane = (int64_t)(row1 - row0) * oh_ow_w(ow_lim); }
       }
       if (dry()) return SAG_OK;
@@ -387,7 +397,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
   for (const BlockDef& b : kBlocks) n_stat += 4 * b.cout;
   unsigned long long* stat_pool = ar.alloc<unsigned long long>(2 * n_stat);      // two fixed-point words per sum
   if (!ar.dry) SAG_CHECK_CUDA(cudaMemsetAsync(stat_pool, 0, sizeof(unsigned long long) * 2 * n_stat, st));
-  const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;   // bytes per activation element
+  const double act_b = f.tc() ? (f.split_planes() ? 4.0 : 2.0) : 4.0;   // bytes per activation element
 
   // conv1 7x7/2 SAME + BN + ReLU, max-pool 3x3/2 SAME (resnet.py:133-135)
   int oh, ow;
@@ -423,7 +433,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
       const float* w = f.W(p + "conv1/conv/weights", &err);
       SAG_TRY(err);
       const UmmaWeights* img = nullptr;
-      SAG_TRY(f.image(p + "conv1/conv", g.T * g.Cin, 64, Mrows, [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.prec, Mrows, uw, st); }, &img));
+      SAG_TRY(f.image(p + "conv1/conv", g.T * g.Cin, 64, Mrows, [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.layer_prec(p + "conv1/conv"), Mrows, uw, st); }, &img));
       if (!ar.dry) {
         {
           const double in_b = xsrc.kind == FRAMES_F32 ? 4.0 : 1.0;
@@ -531,7 +541,7 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
   const int K = c.sep_num_tracks;
   const int wind = d.wind_size, hop = wind / 4;
   const int T = d.snd_dur;
-  const double act_b = f.tc() ? (f.prec == SAG_PREC_BF16X3 ? 4.0 : 2.0) : 4.0;
+  const double act_b = f.tc() ? (f.split_planes() ? 4.0 : 2.0) : 4.0;
 
   // ---- STFT (model.py:369; myutils.py:119-147) ----------------------------------------------------------------
   const int n_enc = d.enc_tt - d.enc_ss;                  // 127
