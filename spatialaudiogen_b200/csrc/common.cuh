@@ -222,6 +222,7 @@ struct ActView {
 };
 extern thread_local int g_umma_pair;  // -1: SAG_UMMA_PAIR env (default off); 0/1: forced: CTA pairs (cta_group::2) on the TMA path
 extern thread_local int g_umma_tma;   // -1: SAG_UMMA_TMA env (default on); 0/1: forced for this thread's launches
+extern thread_local int g_umma_halo;  // -1: SAG_UMMA_HALO env (default on); 0/1: forced: halo-resident kernel for the 3x3 stride-1 convs
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,

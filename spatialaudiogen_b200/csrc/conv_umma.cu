@@ -1114,6 +1114,253 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   }
 }
 
+// ---- halo-resident 3x3 convolution ----------------------------------------------------------------------------------
+// The 3x3 / stride-1 / SAME convolutions of the ResNet trunk (resnet.py:224-236) through im2col copies fetch every activation
+// nine times through L2 and the TMA unit (lts__t_bytes 6x the algorithmic bytes, profiles/r1_dominant_kernel_traffic.json), and
+// the bytes a CTA can keep in flight in its operand ring over the L2 latency bound the whole kernel.  Here an output tile is a
+// TW x TH patch of one image (TW * TH = 128 rows of the MMA, TW a multiple of 8) and, per 64-channel chunk, the producer
+// fetches three TILED boxes of TW x (TH + 2) pixels -- one per horizontal tap dx, already shifted by dx, halo rows included,
+// zero-filled outside the image -- each serving the three vertical taps: tap (dy, dx) is the block of 128 rows that starts
+// (dy + 1) * TW rows into box dx, a 1024-byte-aligned offset, so the shared-memory descriptors are the ordinary SWIZZLE_128B
+// K-major ones.  Activation bytes per tile and chunk: 3 * (TH + 2) / TH boxes instead of 9 (2.7-3.4x fewer).  Weights stream
+// through their own ring (one packed chunk per tap, as in the im2col kernel).  The accumulator tile leaves through a 4-D TMA
+// tensor store (box = 32 channels x TW x TH, clipped at the image border); batch-norm sums come from the registers.
+// bf16x3 only (two MMAs per K step, CONCAT scheme), no bias (ResNet convolutions have none), fp32 NHWC output.
+struct HaloArgs {
+  const uint8_t* wpacked;
+  unsigned long long* stat_sum;
+  unsigned long long* stat_sqs;
+  int NIMG, H, W, TW, TH, TX, TY;     // images, image size, tile shape, tiles per image
+  int CC;                             // 64-channel chunks of the input
+  int Ntot, NT;                       // output channels, N tiles
+  int SA, SB;                         // activation boxes / weight chunks in flight
+};
+struct alignas(64) HaloMaps { CUtensorMap hi, lo, o; };
+constexpr int HL_THREADS = 12 * 32;    // warp 0 producer, warp 1 MMA + TMEM, warps 4-11 epilogue (two per TMEM lane quadrant)
+constexpr int HL_MAX_SA = 4, HL_MAX_SB = 8;
+
+__device__ __forceinline__ void tma_tile_4d(uint32_t dst_smem, const CUtensorMap* tmap, int c, int x, int y, int n, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, uint32_t src_smem, int c, int x, int y, int n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c), "r"(x), "r"(y), "r"(n)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const HaloArgs a, const __grid_constant__ HaloMaps tm) {
+  static_assert(BN == 64 || BN == 128, "halo kernel: 64- or 128-wide tiles (two accumulators of 2*BN TMEM columns)");
+  constexpr int B_BYTES = 2 * BN * 128;                       // [B_hi | B_lo] of one K chunk
+  constexpr uint32_t TMEM_COLS = 4 * BN;                      // two accumulators x (hi.hi | hi.lo) blocks
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);   // LBO, SBO = 1024 B, version, SWIZZLE_128B
+  extern __shared__ __align__(16) uint8_t hl_smem[];
+  __shared__ float s_sum[512], s_sqs[512];
+  __shared__ float s_part[2][4][64];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = smem_u32(hl_smem);
+  const uint32_t bar_afull = bars, bar_aempty = bars + 8 * HL_MAX_SA;
+  const uint32_t bar_bfull = bars + 16 * HL_MAX_SA, bar_bempty = bar_bfull + 8 * HL_MAX_SB;
+  const uint32_t bar_tfull = bar_bempty + 8 * HL_MAX_SB, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
+  const uint32_t stile = (bars + 256 + 1023u) & ~1023u;       // 16 KB staging tile (swizzled TMA store)
+  const uint32_t a_plane = (uint32_t)(a.TH + 2) * (uint32_t)a.TW * 128u;   // one bf16 plane of one box
+  const uint32_t a_slot = 2 * a_plane;
+  const uint32_t a_base = stile + 16384u;
+  const uint32_t b_base = a_base + (uint32_t)a.SA * a_slot;
+  const int SA = a.SA, SB = a.SB;
+  const int tiles = a.NIMG * a.TY * a.TX;
+  const int n_work = tiles * a.NT;
+
+  for (int i = tid; i < 512; i += HL_THREADS) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_prologue();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // work item -> (tile of one image, n tile): tiles fastest, so neighbouring CTAs share the weight chunks in L2
+  auto decode = [&](int wk, int& nimg, int& y0, int& x0, int& nt) {
+    const int t = wk % tiles;
+    nt = wk / tiles;
+    const int per = a.TY * a.TX;
+    nimg = t / per;
+    const int r = t - nimg * per;
+    y0 = (r / a.TX) * a.TH;
+    x0 = (r % a.TX) * a.TW;
+  };
+
+  if (warp == 0) {
+    // ================================ producer ================================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      int nimg, y0, x0, nt;
+      decode(wk, nimg, y0, x0, nt);
+      for (int c = 0; c < a.CC; ++c) {
+#pragma unroll 1
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
+          if (elect_one()) {
+            const uint32_t dst = a_base + (uint32_t)sa * a_slot, bar = bar_afull + 8 * sa;
+            mbar_arrive_expect_tx(bar, a_slot);
+            tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+            tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(bar_bempty + 8 * sb, pb ^ 1);
+            if (elect_one()) {
+              const int kc = (dy * 3 + dx) * a.CC + c;         // packed K order: tap-major, then channel chunk
+              const uint32_t bar = bar_bfull + 8 * sb;
+              mbar_arrive_expect_tx(bar, B_BYTES);
+              bulk_g2s(b_base + (uint32_t)sb * B_BYTES, a.wpacked + ((size_t)nt * (9 * a.CC) + kc) * (size_t)B_BYTES, B_BYTES, bar);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it_local = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+      const int b = it_local & 1;
+      const uint32_t use = (uint32_t)(it_local >> 1);
+      mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(b * 2 * BN);
+      uint32_t first = 0;
+      for (int c = 0; c < a.CC; ++c) {
+#pragma unroll 1
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(bar_afull + 8 * sa, pa);
+          const uint32_t slot = a_base + (uint32_t)sa * a_slot;
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(bar_bfull + 8 * sb, pb);
+            tc_fence_after();
+            const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows (dy + 1 - 1) * TW .. of the box: tap dy - 1
+            const uint32_t bb = b_base + (uint32_t)sb * B_BYTES;
+            const uint64_t da_hi = DESC_HI | (uint64_t)((ab & 0x3FFFFu) >> 4);
+            const uint64_t da_lo = DESC_HI | (uint64_t)(((ab + a_plane) & 0x3FFFFu) >> 4);
+            const uint64_t db = DESC_HI | (uint64_t)((bb & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                umma_bf16(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));   // [A_hi.B_hi | A_hi.B_lo]
+                umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                             // += A_lo.B_hi
+              }
+              umma_commit(bar_bempty + 8 * sb);
+              if (dy == 2) umma_commit(bar_aempty + 8 * sa);
+              if (dy == 2 && dx == 2 && c + 1 == a.CC) umma_commit(bar_tfull + 8 * b);
+            }
+            __syncwarp();
+            first = 1u;
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int q = warp & 3, half = warp >= 8 ? 0 : 1;     // TMEM lane quadrant = warp % 4; two warps per quadrant, 16 of a pass's 32 columns each
+    const int et = (half * 4 + q) * 32 + lane;
+    const int row = q * 32 + lane;
+    const int rr = row / a.TW, rc = row - rr * a.TW;      // position of this row's pixel inside the tile
+    int it_local = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+      int nimg, y0, x0, nt;
+      decode(wk, nimg, y0, x0, nt);
+      const int b = it_local & 1;
+      const uint32_t use = (uint32_t)(it_local >> 1);
+      const bool valid = y0 + rr < a.H && x0 + rc < a.W;  // pixels of a border tile beyond the image: clipped by the store, masked here
+      const int n_base = nt * BN;
+      mbar_wait(bar_tfull + 8 * b, use & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + (uint32_t)(b * 2 * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int cc = c0 + half * 16;
+        const int par = (c0 >> 5) & 1;
+        float v[16], u[16];
+        tmem_ld16(tmem_row + (uint32_t)cc, v);
+        tmem_ld16(tmem_row + (uint32_t)(BN + cc), u);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] += u[e];
+        if (c0 + 32 >= BN) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        {
+          float sv[16], sq[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { sv[e] = valid ? v[e] : 0.f; sq[e] = sv[e] * sv[e]; }
+          const float cs = warp_column_sums<16>(sv, lane), cq = warp_column_sums<16>(sq, lane);
+          if ((lane & 1) == 0) { s_part[par][q][half * 16 + (lane >> 1)] = cs; s_part[par][q][32 + half * 16 + (lane >> 1)] = cq; }
+        }
+        if (et == 0) bulk_wait_read0();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const uint32_t chunk = (uint32_t)(half * 16 + e) >> 2;
+          st_shared_v4(stile + (uint32_t)row * 128u + ((chunk ^ ((uint32_t)row & 7u)) << 4),
+                       make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
+          bulk_commit();
+        }
+        if (et < 32 && n_base + c0 + et < a.Ntot) {
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) { ts += s_part[par][p][et]; tq += s_part[par][p][32 + et]; }
+          s_sum[n_base + c0 + et] += ts;
+          s_sqs[n_base + c0 + et] += tq;
+        }
+      }
+    }
+    if (et == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (a.stat_sum != nullptr) {
+    for (int i = tid; i < a.Ntot; i += HL_THREADS) {
+      fx_atomic_add(a.stat_sum + 2 * i, s_sum[i]);
+      fx_atomic_add(a.stat_sqs + 2 * i, s_sqs[i]);
+    }
+  }
+}
+
 // ---- weight packing: Wk fp32 [K][N] (row stride ldw) -> per (N tile, K chunk) bf16 hi (+lo) planes in the swizzled
 //      K-major layout the MMA reads, so a stage's B operand is one contiguous bulk copy ----
 __global__ void umma_pack_weights_kernel(const float* __restrict__ wk, int K, int N, int64_t ldw, int BN, int KC, int NT,
@@ -1830,6 +2077,104 @@ static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm,
   return true;
 }
 
+// ---- halo-resident 3x3 convolution: eligibility, tile shape, tensor maps, launch -----------------------------------------
+thread_local int g_umma_halo = -1;  // -1: SAG_UMMA_HALO (default on); 0 / 1: forced (sag_set_option "halo_conv")
+
+template <int BN>
+static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cudaStream_t st) {
+  auto kern = halo_conv_umma_kernel<BN>;
+  static int budget[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (budget[dev & 63] == 0) {
+    cudaFuncAttributes fa;
+    int optin = 0;
+    SAG_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    SAG_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int b = optin - (int)fa.sharedSizeBytes;
+    SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    budget[dev & 63] = b;
+  }
+  constexpr int B_BYTES = 2 * BN * 128;
+  const size_t fixed = 256 + 1024 + 16384;
+  HaloArgs args = a;
+  args.SA = 3;
+  long sb = ((long)budget[dev & 63] - (long)fixed - 3 * (long)a_slot) / B_BYTES;
+  if (sb < 2) { args.SA = 2; sb = ((long)budget[dev & 63] - (long)fixed - 2 * (long)a_slot) / B_BYTES; }
+  SAG_REQUIRE(sb >= 2, SAG_EUNSUPPORTED, "halo conv: the tile does not fit the shared memory");
+  args.SB = sb > HL_MAX_SB ? HL_MAX_SB : (int)sb;
+  const size_t smem = fixed + (size_t)args.SA * a_slot + (size_t)args.SB * B_BYTES;
+  const int n_work = a.NIMG * a.TY * a.TX * a.NT;
+  const int grid = n_work < max_conv_ctas() ? n_work : max_conv_ctas();
+  launch_pdl(kern, dim3((unsigned)grid), dim3(HL_THREADS), smem, st, args, tm);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+// returns SAG_OK and sets *done when the layer ran on the halo kernel; *done == false: not eligible, take the im2col kernel
+static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep, int Z,
+                         cudaStream_t st, bool* done) {
+  *done = false;
+  static const int halo_env = env_int("SAG_UMMA_HALO", 1);
+  if (!(g_umma_halo < 0 ? halo_env : g_umma_halo)) return SAG_OK;
+  if (Z != 1 || g.T != 9 || g.isy != 1 || g.isx != 1 || g.PH != g.H || g.PW != g.W || g.Cin % 64 != 0 || g.x_ld % 8 != 0 || g.x_row != 0) return SAG_OK;
+  for (int t = 0; t < 9; ++t)
+    if (g.dy[t] != t / 3 - 1 || g.dx[t] != t % 3 - 1) return SAG_OK;
+  if (x.fmt != ACT_BF2 || x.plane == 0 || (reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return SAG_OK;
+  if (w.planes != 2 || (w.BN != 64 && w.BN != 128) || w.N > 512 || w.col_off != nullptr || w.K != 9 * g.Cin) return SAG_OK;
+  if (ep.bias != nullptr || ep.relu || y.fmt != ACT_F32 || g.y_sc != 1 || g.y_sw % 4 != 0 || g.oy0 != 0 || g.ox0 != 0 || g.osy != 1 || g.osx != 1 ||
+      g.y_sh != (int64_t)g.W * g.y_sw || g.y_sn != (int64_t)g.H * g.y_sh || (reinterpret_cast<uintptr_t>(y.p) & 15) != 0)
+    return SAG_OK;
+  // tile shape: least padding, then the tallest (fewest halo rows per output row).  The activation bytes saved must outweigh
+  // the padded tiles: layers with small images (conv4_x: 14 x 28, conv5_x: 7 x 14) stay on the im2col kernel, whose tiles
+  // run across image boundaries.
+  int TW = 0, TH = 0;
+  double best = 1e30;
+  for (int tw = 8; tw <= 64; tw *= 2) {
+    const int th = UM_BM / tw;
+    const double padded = (double)(cdiv(g.W, tw) * tw) * (cdiv(g.H, th) * th) / ((double)g.W * g.H);
+    const double score = padded * (1.0 + 0.01 * (th + 2.0) / th);
+    if (score < best) { best = score; TW = tw; TH = th; }
+  }
+  const double padded = (double)(cdiv(g.W, TW) * TW) * (cdiv(g.H, TH) * TH) / ((double)g.W * g.H);
+  if (padded > 1.2) return SAG_OK;
+  const EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr) return SAG_OK;
+  HaloMaps tm;
+  memset(&tm, 0, sizeof(tm));
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, (cuuint64_t)g.W * g.x_ld * 2, (cuuint64_t)g.H * g.W * g.x_ld * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + 2), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+      void* base = reinterpret_cast<char*>(x.p) + (pl == 0 ? 0 : x.plane);
+      if (encode(pl == 0 ? &tm.hi : &tm.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SAG_OK;
+    }
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)w.N, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.y_sw * 4, (cuuint64_t)g.y_sh * 4, (cuuint64_t)g.y_sn * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&tm.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return SAG_OK;
+  }
+  HaloArgs a;
+  memset(&a, 0, sizeof(a));
+  a.wpacked = reinterpret_cast<const uint8_t*>(w.packed);
+  a.stat_sum = ep.stat_sum; a.stat_sqs = ep.stat_sqs;
+  a.NIMG = g.N; a.H = g.H; a.W = g.W; a.TW = TW; a.TH = TH; a.TX = cdiv(g.W, TW); a.TY = cdiv(g.H, TH);
+  a.CC = g.Cin / 64; a.Ntot = w.N; a.NT = w.NT;
+  const size_t a_slot = 2 * (size_t)(TH + 2) * TW * 128;
+  SAG_TRY(w.BN == 64 ? launch_halo<64>(a, tm, a_slot, st) : launch_halo<128>(a, tm, a_slot, st));
+  *done = true;
+  return SAG_OK;
+}
+
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st) {
   SAG_REQUIRE(w.packed != nullptr || w.KC == 0, SAG_ESTATE, "tcgen05 path: weights are not packed");
@@ -1878,6 +2223,11 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   const TilePlan plan = plan_tile(w.K, w.N, M);
   SAG_REQUIRE(w.BN == plan.BN, SAG_ESTATE, "tcgen05 path: weights were packed for a different row count (tile %d, planned %d)", w.BN, plan.BN);
   const int Z = scratch != nullptr ? plan.Z : 1;
+  {
+    bool done = false;
+    SAG_TRY(try_halo_conv(x, w, y, g, ep, Z, st, &done));
+    if (done) return SAG_OK;
+  }
   if (Z > 1) a.partial = scratch;
   // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
   a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&

@@ -511,9 +511,10 @@ int forward(sag_handle* h, const float* audio, const FrameSrc& video, const Fram
     h->prof.clear();
     g_prof = &h->prof;
   }
-  struct ProfGuard { ~ProfGuard() { g_prof = nullptr; g_umma_tma = -1; g_umma_pair = -1; } } prof_guard;   // stage entry points never see a stale profiler
+  struct ProfGuard { ~ProfGuard() { g_prof = nullptr; g_umma_tma = -1; g_umma_pair = -1; g_umma_halo = -1; } } prof_guard;   // stage entry points never see a stale profiler
   g_umma_tma = h->tma_gather;
   g_umma_pair = h->cta_pair;
+  g_umma_halo = h->halo_conv;
   const bool unet = c.separation == SAG_SEP_UNET_MASK;
   // fork / join of the independent branches (see sag_handle::overlap); profiling runs them serially so that every launch
   // scope is timed alone

@@ -170,7 +170,7 @@ class SptAudioGen(StageOps):
             self.precision = value
             value = L.PRECISIONS[value]
         L.check(L.lib().sag_set_option(self._h, key.encode(), int(value)))
-        if key not in ('keep_sep_channels', 'profile', 'cta_pair', 'overlap', 'fuse_gains'):     # (these do not change the workspace plan)
+        if key not in ('keep_sep_channels', 'profile', 'cta_pair', 'overlap', 'fuse_gains', 'halo_conv'):     # (these do not change the workspace plan)
             self._ws_batch = 0
 
     # ---- forward ---------------------------------------------------------------------------------------------

@@ -675,3 +675,32 @@ def test_stage_methods_match_oracle():
     assert _rel(x_sep, ref.sep_channels) < 1e-3
     y = (w * x_sep.permute(0, 3, 1, 2).unsqueeze(2)).sum(4).sum(3) + b[:, :, :, 0]
     assert _rel(y, yr) < 1e-3
+
+
+def test_halo_resident_conv_matches_the_im2col_kernel_and_the_oracle():
+    """The 3x3 / stride-1 convolutions of the ResNet trunk on the halo-resident kernel (tiled TMA boxes shared by three vertical
+    taps, 4-D tensor store, statistics from registers) against the im2col kernel and the fp64 oracle; odd batch and a frame size
+    whose tiles overhang the image border (the clipped store / masked statistics path)."""
+    from spatialaudiogen_b200 import SptAudioGen
+    enc = ['audio', 'video']
+    for frame, B in (((224, 448), 3), ((160, 208), 2)):
+        W = Wt.init_weights(enc, separation='unet_mask', seed=21, stress=True)
+        if frame != (224, 448):                                              # the video-fc input follows the frame size
+            fh, fw = -(-frame[0] // 32), -(-frame[1] // 32)
+            rng = np.random.RandomState(3)
+            W['bottleneck/video-fc/weights'] = (rng.randn(fh * fw * 128, 512) * 0.01).astype(np.float32)
+        m = SptAudioGen(1, encoders=enc, separation='unet_mask', frame_size=frame).load_weights(W)
+        a, v = cu(_audio(B, 150)), cu(_video(B, 151, frame[0], frame[1]))
+        res = {}
+        for halo in (1, 0):
+            m.set_option('halo_conv', halo)
+            y = m.inference_ops(a, video=v).clone()
+            res[halo] = (y, {k: m.ends[k].clone() for k in ('video_encoder/conv2_1', 'video_encoder/conv2_2', 'video_encoder/conv3_2', 'video_encoder/conv5_2')})
+        for k in res[1][1]:
+            assert _rel(res[1][1][k], res[0][1][k]) < 2e-5, k
+        assert _rel(res[1][0], res[0][0]) < 1e-4
+        if frame == (224, 448):
+            ref = O.SptAudioGen(W, encoders=enc, separation='unet_mask', dtype=torch.float64)
+            yr = ref.inference_ops(a.cpu().numpy(), video=v.cpu().numpy())
+            assert _rel(res[1][1]['video_encoder/conv3_2'], ref.ends['video_encoder/conv3_2']) < 1e-4
+            assert _rel(res[1][0], yr) < 1e-3
