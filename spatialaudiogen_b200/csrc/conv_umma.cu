@@ -1135,7 +1135,7 @@ struct HaloArgs {
   int Ntot, NT;                       // output channels, N tiles
   int SA, SB;                         // activation boxes / weight chunks in flight
 };
-struct alignas(64) HaloMaps { CUtensorMap hi, lo, o; };
+struct alignas(64) HaloMaps { CUtensorMap hi, lo, o, w; };     // w: tiled map of the packed weights (pairs)
 constexpr int HL_THREADS = 12 * 32;    // warp 0 producer, warp 1 MMA + TMEM, warps 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int HL_MAX_SA = 4, HL_MAX_SB = 8;
 
@@ -1144,19 +1144,32 @@ __device__ __forceinline__ void tma_tile_4d(uint32_t dst_smem, const CUtensorMap
                "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
                : "memory");
 }
+__device__ __forceinline__ void tma_tile_4d_2sm(uint32_t dst_smem, const CUtensorMap* tmap, int c, int x, int y, int n, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c), "r"(x), "r"(y), "r"(n)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, uint32_t src_smem, int c, int x, int y, int n) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
                "r"(src_smem), "r"(c), "r"(x), "r"(y), "r"(n)
                : "memory");
 }
 
-template <int BN>
+// PAIR: two CTAs of a cluster (cta_group::2) take two neighbouring tiles of the same n tile; one MMA instruction of the leader
+// spans both (M = 256), each CTA feeds half of the rows of every weight operand -- rank 0 the B_hi, rank 1 the B_lo block of
+// the 2*BN-wide MMA, and each its half of B_hi for the BN-wide one -- so the weight bytes per CTA drop 16 -> 12 KB per tap
+// (BN = 64) and the number of MMA instructions per tile halves.  Copies of both CTAs complete on the leader's barriers.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const HaloArgs a, const __grid_constant__ HaloMaps tm) {
   static_assert(BN == 64 || BN == 128, "halo kernel: 64- or 128-wide tiles (two accumulators of 2*BN TMEM columns)");
-  constexpr int B_BYTES = 2 * BN * 128;                       // [B_hi | B_lo] of one K chunk
+  constexpr int BX_ROWS = BN, BY_ROWS = PAIR ? BN / 2 : BN;   // pair: block X = B_hi | B_lo by rank, block Y = my half of B_hi
+  constexpr int B_BYTES = (BX_ROWS + BY_ROWS) * 128;           // alone: [B_hi | B_lo] of one K chunk
   constexpr uint32_t TMEM_COLS = 4 * BN;                      // two accumulators x (hi.hi | hi.lo) blocks
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((128u >> 4) << 24);
+  constexpr uint32_t UM_M = PAIR ? 256u : 128u;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((UM_M >> 4) << 24);
+  constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((UM_M >> 4) << 24);
+  constexpr int CL = PAIR ? 2 : 1;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);   // LBO, SBO = 1024 B, version, SWIZZLE_128B
   extern __shared__ __align__(16) uint8_t hl_smem[];
   __shared__ float s_sum[512], s_sqs[512];
@@ -1174,30 +1187,36 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
   const uint32_t b_base = a_base + (uint32_t)a.SA * a_slot;
   const int SA = a.SA, SB = a.SB;
   const int tiles = a.NIMG * a.TY * a.TX;
-  const int n_work = tiles * a.NT;
+  const int tile_groups = (tiles + CL - 1) / CL;             // pair: two neighbouring tiles per cluster (the last may be padding)
+  const int n_work = tile_groups * a.NT;                      // work items per cluster
+  const int wk0 = blockIdx.x / CL, wk_step = gridDim.x / CL;
 
   for (int i = tid; i < 512; i += HL_THREADS) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
       for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
+      for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8 * CL); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   pdl_prologue();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // work item -> (tile of one image, n tile): tiles fastest, so neighbouring CTAs share the weight chunks in L2
-  auto decode = [&](int wk, int& nimg, int& y0, int& x0, int& nt) {
-    const int t = wk % tiles;
-    nt = wk / tiles;
+  auto decode = [&](int wk, int& nimg, int& y0, int& x0, int& nt, bool& real) {
+    int t = (wk % tile_groups) * CL + (int)crank;
+    nt = wk / tile_groups;
+    real = t < tiles;                                         // (the padding tile of an odd pair reloads the last tile, stores nothing)
+    if (!real) t = tiles - 1;
     const int per = a.TY * a.TX;
     nimg = t / per;
     const int r = t - nimg * per;
@@ -1209,18 +1228,30 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
     // ================================ producer ================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    const uint32_t lead_bars = PAIR ? map_to_cta(bars, 0) : bars;             // the leader's barriers (cluster address)
+    const uint32_t lead_afull = lead_bars + (bar_afull - bars), lead_bfull = lead_bars + (bar_bfull - bars);
+    for (int wk = wk0; wk < n_work; wk += wk_step) {
       int nimg, y0, x0, nt;
-      decode(wk, nimg, y0, x0, nt);
+      bool real;
+      decode(wk, nimg, y0, x0, nt, real);
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
         for (int dx = 0; dx < 3; ++dx) {
           mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
           if (elect_one()) {
-            const uint32_t dst = a_base + (uint32_t)sa * a_slot, bar = bar_afull + 8 * sa;
-            mbar_arrive_expect_tx(bar, a_slot);
-            tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
-            tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+            const uint32_t dst = a_base + (uint32_t)sa * a_slot;
+            if (!PAIR) {
+              const uint32_t bar = bar_afull + 8 * sa;
+              mbar_arrive_expect_tx(bar, a_slot);
+              tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+              tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+            } else {
+              // the leader's producer makes the single arrival and expects the bytes of both CTAs (see the im2col kernel)
+              const uint32_t bar = lead_afull + 8 * sa;
+              if (crank == 0) mbar_arrive_expect_tx(bar_afull + 8 * sa, 2 * a_slot);
+              tma_tile_4d_2sm(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+              tma_tile_4d_2sm(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+            }
           }
           __syncwarp();
           if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -1229,9 +1260,20 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
             mbar_wait(bar_bempty + 8 * sb, pb ^ 1);
             if (elect_one()) {
               const int kc = (dy * 3 + dx) * a.CC + c;         // packed K order: tap-major, then channel chunk
-              const uint32_t bar = bar_bfull + 8 * sb;
-              mbar_arrive_expect_tx(bar, B_BYTES);
-              bulk_g2s(b_base + (uint32_t)sb * B_BYTES, a.wpacked + ((size_t)nt * (9 * a.CC) + kc) * (size_t)B_BYTES, B_BYTES, bar);
+              const uint32_t dst = b_base + (uint32_t)sb * B_BYTES;
+              if (!PAIR) {
+                const uint32_t bar = bar_bfull + 8 * sb;
+                mbar_arrive_expect_tx(bar, B_BYTES);
+                bulk_g2s(dst, a.wpacked + ((size_t)nt * (9 * a.CC) + kc) * (size_t)(2 * BN * 128), B_BYTES, bar);
+              } else {
+                const uint32_t bar = lead_bfull + 8 * sb;
+                if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * sb, 2 * B_BYTES);
+                const int wrow = (nt * (9 * a.CC) + kc) * (2 * BN);     // rows of 128 bytes; boxes of BN/2 rows
+                constexpr int HB = BN / 2;
+                tma_tile_2d_2sm(dst, &tm.w, 0, wrow + (int)crank * BN, bar);                       // block X: B_hi (rank 0) / B_lo (rank 1)
+                tma_tile_2d_2sm(dst + HB * 128, &tm.w, 0, wrow + (int)crank * BN + HB, bar);
+                tma_tile_2d_2sm(dst + BX_ROWS * 128, &tm.w, 0, wrow + (int)crank * HB, bar);      // block Y: my half of B_hi
+              }
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -1240,11 +1282,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+    // ================================ MMA issuer (pair: the leader only) ================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it_local = 0;
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+    if (!PAIR || crank == 0)
+    for (int wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       const int b = it_local & 1;
       const uint32_t use = (uint32_t)(it_local >> 1);
       mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);
@@ -1260,20 +1303,33 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
           for (int dy = 0; dy < 3; ++dy) {
             mbar_wait(bar_bfull + 8 * sb, pb);
             tc_fence_after();
-            const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows (dy + 1 - 1) * TW .. of the box: tap dy - 1
+            const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows dy * TW .. of the box: vertical tap dy - 1
             const uint32_t bb = b_base + (uint32_t)sb * B_BYTES;
             const uint64_t da_hi = DESC_HI | (uint64_t)((ab & 0x3FFFFu) >> 4);
             const uint64_t da_lo = DESC_HI | (uint64_t)(((ab + a_plane) & 0x3FFFFu) >> 4);
             const uint64_t db = DESC_HI | (uint64_t)((bb & 0x3FFFFu) >> 4);
+            const uint64_t dby = DESC_HI | (uint64_t)(((bb + BX_ROWS * 128) & 0x3FFFFu) >> 4);    // pair: the halves of B_hi
             if (elect_one()) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                umma_bf16(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));   // [A_hi.B_hi | A_hi.B_lo]
-                umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                             // += A_lo.B_hi
+                if (PAIR) {
+                  umma_bf16_2(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));
+                  umma_bf16_2(tmem_acc, da_lo + 2 * k4, dby + 2 * k4, IDESC, 1u);
+                } else {
+                  umma_bf16(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));   // [A_hi.B_hi | A_hi.B_lo]
+                  umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                             // += A_lo.B_hi
+                }
               }
-              umma_commit(bar_bempty + 8 * sb);
-              if (dy == 2) umma_commit(bar_aempty + 8 * sa);
-              if (dy == 2 && dx == 2 && c + 1 == a.CC) umma_commit(bar_tfull + 8 * b);
+              const bool last = dy == 2 && dx == 2 && c + 1 == a.CC;
+              if (PAIR) {
+                umma_commit2(bar_bempty + 8 * sb);
+                if (dy == 2) umma_commit2(bar_aempty + 8 * sa);
+                if (last) umma_commit2(bar_tfull + 8 * b);
+              } else {
+                umma_commit(bar_bempty + 8 * sb);
+                if (dy == 2) umma_commit(bar_aempty + 8 * sa);
+                if (last) umma_commit(bar_tfull + 8 * b);
+              }
             }
             __syncwarp();
             first = 1u;
@@ -1290,12 +1346,13 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
     const int row = q * 32 + lane;
     const int rr = row / a.TW, rc = row - rr * a.TW;      // position of this row's pixel inside the tile
     int it_local = 0;
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it_local) {
+    for (int wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int nimg, y0, x0, nt;
-      decode(wk, nimg, y0, x0, nt);
+      bool real;
+      decode(wk, nimg, y0, x0, nt, real);
       const int b = it_local & 1;
       const uint32_t use = (uint32_t)(it_local >> 1);
-      const bool valid = y0 + rr < a.H && x0 + rc < a.W;  // pixels of a border tile beyond the image: clipped by the store, masked here
+      const bool valid = real && y0 + rr < a.H && x0 + rc < a.W;   // pixels of a border tile beyond the image: clipped by the store, masked here
       const int n_base = nt * BN;
       mbar_wait(bar_tfull + 8 * b, use & 1);
       tc_fence_after();
@@ -1312,7 +1369,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         if (c0 + 32 >= BN) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+          if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
         }
         {
           float sv[16], sq[16];
@@ -1331,7 +1388,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
+        if (et == 0 && real) {
           tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
           bulk_commit();
         }
@@ -1348,10 +1405,12 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();          // no CTA leaves while the peer may still signal its barriers or read its operands
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (a.stat_sum != nullptr) {
     for (int i = tid; i < a.Ntot; i += HL_THREADS) {
@@ -2080,9 +2139,9 @@ static bool make_im2col_maps(const ActView& x, const GatherGeom& g, TmaPair* tm,
 // ---- halo-resident 3x3 convolution: eligibility, tile shape, tensor maps, launch -----------------------------------------
 thread_local int g_umma_halo = -1;  // -1: SAG_UMMA_HALO (default on); 0 / 1: forced (sag_set_option "halo_conv")
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cudaStream_t st) {
-  auto kern = halo_conv_umma_kernel<BN>;
+  auto kern = halo_conv_umma_kernel<BN, PAIR>;
   static int budget[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -2095,7 +2154,8 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     budget[dev & 63] = b;
   }
-  constexpr int B_BYTES = 2 * BN * 128;
+  constexpr int B_BYTES = (BN + (PAIR ? BN / 2 : BN)) * 128;
+  constexpr int CL = PAIR ? 2 : 1;
   const size_t fixed = 256 + 1024 + 16384;
   HaloArgs args = a;
   args.SA = 3;
@@ -2104,9 +2164,27 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   SAG_REQUIRE(sb >= 2, SAG_EUNSUPPORTED, "halo conv: the tile does not fit the shared memory");
   args.SB = sb > HL_MAX_SB ? HL_MAX_SB : (int)sb;
   const size_t smem = fixed + (size_t)args.SA * a_slot + (size_t)args.SB * B_BYTES;
-  const int n_work = a.NIMG * a.TY * a.TX * a.NT;
-  const int grid = n_work < max_conv_ctas() ? n_work : max_conv_ctas();
-  launch_pdl(kern, dim3((unsigned)grid), dim3(HL_THREADS), smem, st, args, tm);
+  const int tiles = a.NIMG * a.TY * a.TX;
+  const int n_work = cdiv(tiles, CL) * a.NT;
+  int clusters = max_conv_ctas() / CL;
+  if (clusters < 1) clusters = 1;
+  if (n_work < clusters) clusters = n_work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(HL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  memset(attrs, 0, sizeof(attrs));
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CL;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args, tm));
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }
@@ -2115,8 +2193,10 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
 static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep, int Z,
                          cudaStream_t st, bool* done) {
   *done = false;
-  static const int halo_env = env_int("SAG_UMMA_HALO", 1);
-  if (!(g_umma_halo < 0 ? halo_env : g_umma_halo)) return SAG_OK;
+  // -1 (default): on where no tile overhangs the image; 1: forced wherever the layer is eligible (tests); 0: off
+  static const int halo_env = env_int("SAG_UMMA_HALO", -1);
+  const int halo_want = g_umma_halo >= 0 ? g_umma_halo : halo_env;
+  if (halo_want == 0) return SAG_OK;
   if (Z != 1 || g.T != 9 || g.isy != 1 || g.isx != 1 || g.PH != g.H || g.PW != g.W || g.Cin % 64 != 0 || g.x_ld % 8 != 0 || g.x_row != 0) return SAG_OK;
   for (int t = 0; t < 9; ++t)
     if (g.dy[t] != t / 3 - 1 || g.dx[t] != t % 3 - 1) return SAG_OK;
@@ -2137,7 +2217,7 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
     if (score < best) { best = score; TW = tw; TH = th; }
   }
   const double padded = (double)(cdiv(g.W, TW) * TW) * (cdiv(g.H, TH) * TH) / ((double)g.W * g.H);
-  if (padded > 1.2) return SAG_OK;
+  if (padded > (halo_want > 0 ? 1.3 : 1.001)) return SAG_OK;      // measured: conv3_x with 14 % padded tiles loses 20 % (profiles/README.md); conv2_x (none) gains
   const EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return SAG_OK;
   HaloMaps tm;
@@ -2170,7 +2250,16 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   a.NIMG = g.N; a.H = g.H; a.W = g.W; a.TW = TW; a.TH = TH; a.TX = cdiv(g.W, TW); a.TY = cdiv(g.H, TH);
   a.CC = g.Cin / 64; a.Ntot = w.N; a.NT = w.NT;
   const size_t a_slot = 2 * (size_t)(TH + 2) * TW * 128;
-  SAG_TRY(w.BN == 64 ? launch_halo<64>(a, tm, a_slot, st) : launch_halo<128>(a, tm, a_slot, st));
+  // CTA pairs (two neighbouring tiles per cluster, half the weight bytes and half the MMA instructions per tile): default on
+  static const int pair_env = env_int("SAG_UMMA_PAIR", -1);
+  const int want = g_umma_pair >= 0 ? g_umma_pair : pair_env;
+  const bool pair = (want < 0 || want != 0) && w.wmap_ok && g.N * a.TY * a.TX >= 2;
+  if (pair) {
+    memcpy(&tm.w, w.wmap, sizeof(tm.w));
+    SAG_TRY(w.BN == 64 ? (launch_halo<64, true>(a, tm, a_slot, st)) : (launch_halo<128, true>(a, tm, a_slot, st)));
+  } else {
+    SAG_TRY(w.BN == 64 ? (launch_halo<64, false>(a, tm, a_slot, st)) : (launch_halo<128, false>(a, tm, a_slot, st)));
+  }
   *done = true;
   return SAG_OK;
 }

@@ -683,7 +683,7 @@ def test_halo_resident_conv_matches_the_im2col_kernel_and_the_oracle():
     whose tiles overhang the image border (the clipped store / masked statistics path)."""
     from spatialaudiogen_b200 import SptAudioGen
     enc = ['audio', 'video']
-    for frame, B in (((224, 448), 3), ((160, 208), 2)):
+    for frame, B in (((224, 448), 3), ((208, 432), 2)):       # 52 x 108 feature maps: 16 x 8 tiles overhang both borders
         W = Wt.init_weights(enc, separation='unet_mask', seed=21, stress=True)
         if frame != (224, 448):                                              # the video-fc input follows the frame size
             fh, fw = -(-frame[0] // 32), -(-frame[1] // 32)
@@ -693,12 +693,17 @@ def test_halo_resident_conv_matches_the_im2col_kernel_and_the_oracle():
         a, v = cu(_audio(B, 150)), cu(_video(B, 151, frame[0], frame[1]))
         res = {}
         for halo in (1, 0):
-            m.set_option('halo_conv', halo)
+            m.set_option('halo_conv', halo)                                      # 1 = forced wherever eligible (default: zero-padding shapes only)
             y = m.inference_ops(a, video=v).clone()
             res[halo] = (y, {k: m.ends[k].clone() for k in ('video_encoder/conv2_1', 'video_encoder/conv2_2', 'video_encoder/conv3_2', 'video_encoder/conv5_2')})
         for k in res[1][1]:
-            assert _rel(res[1][1][k], res[0][1][k]) < 2e-5, k
+            assert _rel(res[1][1][k], res[0][1][k]) < 1e-4, k           # (different accumulation order over the taps)
         assert _rel(res[1][0], res[0][0]) < 1e-4
+        m.set_option('cta_pair', 0)                                              # the single-CTA variant of the halo kernel
+        m.set_option('halo_conv', 1)
+        y1 = m.inference_ops(a, video=v).clone()
+        assert _rel(m.ends['video_encoder/conv2_2'], res[1][1]['video_encoder/conv2_2']) < 1e-4 and _rel(y1, res[1][0]) < 1e-4
+        m.set_option('cta_pair', -1)
         if frame == (224, 448):
             ref = O.SptAudioGen(W, encoders=enc, separation='unet_mask', dtype=torch.float64)
             yr = ref.inference_ops(a.cpu().numpy(), video=v.cpu().numpy())
