@@ -81,8 +81,9 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
     // kernel's CTAs do, so the side chain advances at every kernel boundary of the main stream
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    bool ok = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    bool ok = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { set_error("sag_create: could not create the side stream / events"); r = SAG_ECUDA; }
   }
   if (r != SAG_OK) { sag_destroy(h); return r; }
@@ -96,9 +97,10 @@ int sag_destroy(sag_handle* h) {
   for (auto& kv : h->packed) free_tensor(kv.second);
   for (auto& kv : h->umma) umma_free(&kv.second);
   h->prof.clear();
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
   delete h;
   return SAG_OK;
 }

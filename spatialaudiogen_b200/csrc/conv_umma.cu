@@ -1132,6 +1132,7 @@ struct HaloArgs {
   unsigned long long* stat_sqs;
   int NIMG, H, W, TW, TH, TX, TY;     // images, image size, tile shape, tiles per image
   int CC;                             // 64-channel chunks of the input
+  int NDX, NDY, DX0, DY0;             // taps: dx in [DX0, DX0 + NDX) (one box each), dy in [DY0, DY0 + NDY) (blocks of a box)
   int Ntot, NT;                       // output channels, N tiles
   int SA, SB;                         // activation boxes / weight chunks in flight
 };
@@ -1181,7 +1182,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
   const uint32_t bar_bfull = bars + 16 * HL_MAX_SA, bar_bempty = bar_bfull + 8 * HL_MAX_SB;
   const uint32_t bar_tfull = bar_bempty + 8 * HL_MAX_SB, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
   const uint32_t stile = (bars + 256 + 1023u) & ~1023u;       // 16 KB staging tile (swizzled TMA store)
-  const uint32_t a_plane = (uint32_t)(a.TH + 2) * (uint32_t)a.TW * 128u;   // one bf16 plane of one box
+  const uint32_t a_plane = (uint32_t)(a.TH + a.NDY - 1) * (uint32_t)a.TW * 128u;   // one bf16 plane of one box
   const uint32_t a_slot = 2 * a_plane;
   const uint32_t a_base = stile + 16384u;
   const uint32_t b_base = a_base + (uint32_t)a.SA * a_slot;
@@ -1236,39 +1237,39 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       decode(wk, nimg, y0, x0, nt, real);
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int dx = 0; dx < a.NDX; ++dx) {
           mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
           if (elect_one()) {
             const uint32_t dst = a_base + (uint32_t)sa * a_slot;
             if (!PAIR) {
               const uint32_t bar = bar_afull + 8 * sa;
               mbar_arrive_expect_tx(bar, a_slot);
-              tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
-              tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+              tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
+              tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
             } else {
               // the leader's producer makes the single arrival and expects the bytes of both CTAs (see the im2col kernel)
               const uint32_t bar = lead_afull + 8 * sa;
               if (crank == 0) mbar_arrive_expect_tx(bar_afull + 8 * sa, 2 * a_slot);
-              tma_tile_4d_2sm(dst, &tm.hi, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
-              tma_tile_4d_2sm(dst + a_plane, &tm.lo, c * 64, x0 + dx - 1, y0 - 1, nimg, bar);
+              tma_tile_4d_2sm(dst, &tm.hi, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
+              tma_tile_4d_2sm(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
             }
           }
           __syncwarp();
           if (++sa == SA) { sa = 0; pa ^= 1; }
 #pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy) {
+          for (int dy = 0; dy < a.NDY; ++dy) {
             mbar_wait(bar_bempty + 8 * sb, pb ^ 1);
             if (elect_one()) {
-              const int kc = (dy * 3 + dx) * a.CC + c;         // packed K order: tap-major, then channel chunk
+              const int kc = (dy * a.NDX + dx) * a.CC + c;     // packed K order: tap-major (rows, then columns), then channel chunk
               const uint32_t dst = b_base + (uint32_t)sb * B_BYTES;
               if (!PAIR) {
                 const uint32_t bar = bar_bfull + 8 * sb;
                 mbar_arrive_expect_tx(bar, B_BYTES);
-                bulk_g2s(dst, a.wpacked + ((size_t)nt * (9 * a.CC) + kc) * (size_t)(2 * BN * 128), B_BYTES, bar);
+                bulk_g2s(dst, a.wpacked + ((size_t)nt * (a.NDX * a.NDY * a.CC) + kc) * (size_t)(2 * BN * 128), B_BYTES, bar);
               } else {
                 const uint32_t bar = lead_bfull + 8 * sb;
                 if (crank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * sb, 2 * B_BYTES);
-                const int wrow = (nt * (9 * a.CC) + kc) * (2 * BN);     // rows of 128 bytes; boxes of BN/2 rows
+                const int wrow = (nt * (a.NDX * a.NDY * a.CC) + kc) * (2 * BN);     // rows of 128 bytes; boxes of BN/2 rows
                 constexpr int HB = BN / 2;
                 tma_tile_2d_2sm(dst, &tm.w, 0, wrow + (int)crank * BN, bar);                       // block X: B_hi (rank 0) / B_lo (rank 1)
                 tma_tile_2d_2sm(dst + HB * 128, &tm.w, 0, wrow + (int)crank * BN + HB, bar);
@@ -1296,11 +1297,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       uint32_t first = 0;
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
-        for (int dx = 0; dx < 3; ++dx) {
+        for (int dx = 0; dx < a.NDX; ++dx) {
           mbar_wait(bar_afull + 8 * sa, pa);
           const uint32_t slot = a_base + (uint32_t)sa * a_slot;
 #pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy) {
+          for (int dy = 0; dy < a.NDY; ++dy) {
             mbar_wait(bar_bfull + 8 * sb, pb);
             tc_fence_after();
             const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows dy * TW .. of the box: vertical tap dy - 1
@@ -1320,14 +1321,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
                   umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                             // += A_lo.B_hi
                 }
               }
-              const bool last = dy == 2 && dx == 2 && c + 1 == a.CC;
+              const bool last = dy + 1 == a.NDY && dx + 1 == a.NDX && c + 1 == a.CC;
               if (PAIR) {
                 umma_commit2(bar_bempty + 8 * sb);
-                if (dy == 2) umma_commit2(bar_aempty + 8 * sa);
+                if (dy + 1 == a.NDY) umma_commit2(bar_aempty + 8 * sa);
                 if (last) umma_commit2(bar_tfull + 8 * b);
               } else {
                 umma_commit(bar_bempty + 8 * sb);
-                if (dy == 2) umma_commit(bar_aempty + 8 * sa);
+                if (dy + 1 == a.NDY) umma_commit(bar_aempty + 8 * sa);
                 if (last) umma_commit(bar_tfull + 8 * b);
               }
             }
@@ -2197,14 +2198,23 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   static const int halo_env = env_int("SAG_UMMA_HALO", -1);
   const int halo_want = g_umma_halo >= 0 ? g_umma_halo : halo_env;
   if (halo_want == 0) return SAG_OK;
-  if (Z != 1 || g.T != 9 || g.isy != 1 || g.isx != 1 || g.PH != g.H || g.PW != g.W || g.Cin % 64 != 0 || g.x_ld % 8 != 0 || g.x_row != 0) return SAG_OK;
-  for (int t = 0; t < 9; ++t)
-    if (g.dy[t] != t / 3 - 1 || g.dx[t] != t % 3 - 1) return SAG_OK;
+  if (Z != 1 || g.isy != 1 || g.isx != 1 || g.Cin % 64 != 0 || g.x_ld % 8 != 0) return SAG_OK;
+  // taps must form a full NDX x NDY rectangle in row-major order (3 x 3 SAME convolutions: dx, dy in -1..1; ResNet conv1 in its
+  // space-to-depth form: one column of four rows, the four horizontal taps being the overlapping 64-channel pixel)
+  int ndx = 0, ndy = 0;
+  const int dx0 = g.dx[0], dy0 = g.dy[0];
+  for (int t = 0; t < g.T && g.dy[t] == dy0; ++t) ++ndx;
+  if (ndx < 1 || g.T % ndx != 0) return SAG_OK;
+  ndy = g.T / ndx;
+  for (int t = 0; t < g.T; ++t)
+    if (g.dy[t] != dy0 + t / ndx || g.dx[t] != dx0 + t % ndx) return SAG_OK;
+  if (ndy < 2 || ndx > 3 || ndy > 4) return SAG_OK;
   if (x.fmt != ACT_BF2 || x.plane == 0 || (reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return SAG_OK;
-  if (w.planes != 2 || (w.BN != 64 && w.BN != 128) || w.N > 512 || w.col_off != nullptr || w.K != 9 * g.Cin) return SAG_OK;
+  if (w.planes != 2 || (w.BN != 64 && w.BN != 128) || w.N > 512 || w.col_off != nullptr || w.K != g.T * g.Cin) return SAG_OK;
   if (ep.bias != nullptr || ep.relu || y.fmt != ACT_F32 || g.y_sc != 1 || g.y_sw % 4 != 0 || g.oy0 != 0 || g.ox0 != 0 || g.osy != 1 || g.osx != 1 ||
-      g.y_sh != (int64_t)g.W * g.y_sw || g.y_sn != (int64_t)g.H * g.y_sh || (reinterpret_cast<uintptr_t>(y.p) & 15) != 0)
+      g.y_sh != (int64_t)g.PW * g.y_sw || g.y_sn != (int64_t)g.PH * g.y_sh || (reinterpret_cast<uintptr_t>(y.p) & 15) != 0)
     return SAG_OK;
+  const int OH = g.PH, OW = g.PW;                    // output grid (== the image for SAME 3 x 3; the padded image is larger for conv1)
   // tile shape: least padding, then the tallest (fewest halo rows per output row).  The activation bytes saved must outweigh
   // the padded tiles: layers with small images (conv4_x: 14 x 28, conv5_x: 7 x 14) stay on the im2col kernel, whose tiles
   // run across image boundaries.
@@ -2212,20 +2222,22 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   double best = 1e30;
   for (int tw = 8; tw <= 64; tw *= 2) {
     const int th = UM_BM / tw;
-    const double padded = (double)(cdiv(g.W, tw) * tw) * (cdiv(g.H, th) * th) / ((double)g.W * g.H);
-    const double score = padded * (1.0 + 0.01 * (th + 2.0) / th);
+    const double padded = (double)(cdiv(OW, tw) * tw) * (cdiv(OH, th) * th) / ((double)OW * OH);
+    const double score = padded * (1.0 + 0.01 * (th + ndy - 1.0) / th);
     if (score < best) { best = score; TW = tw; TH = th; }
   }
-  const double padded = (double)(cdiv(g.W, TW) * TW) * (cdiv(g.H, TH) * TH) / ((double)g.W * g.H);
+  const double padded = (double)(cdiv(OW, TW) * TW) * (cdiv(OH, TH) * TH) / ((double)OW * OH);
   if (padded > (halo_want > 0 ? 1.3 : 1.001)) return SAG_OK;      // measured: conv3_x with 14 % padded tiles loses 20 % (profiles/README.md); conv2_x (none) gains
   const EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return SAG_OK;
   HaloMaps tm;
   memset(&tm, 0, sizeof(tm));
   {
+    // (x_row != 0: pixels overlap -- conv1's 64-channel pixels at a 16-channel pitch, see resnet18_tower)
+    const cuuint64_t x_row = g.x_row != 0 ? (cuuint64_t)g.x_row : (cuuint64_t)g.W * g.x_ld;
     const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-    const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, (cuuint64_t)g.W * g.x_ld * 2, (cuuint64_t)g.H * g.W * g.x_ld * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + 2), 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, x_row * 2, (cuuint64_t)g.H * x_row * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + ndy - 1), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int pl = 0; pl < 2; ++pl) {
       void* base = reinterpret_cast<char*>(x.p) + (pl == 0 ? 0 : x.plane);
@@ -2235,7 +2247,7 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
     }
   }
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)w.N, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    const cuuint64_t dims[4] = {(cuuint64_t)w.N, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)g.N};
     const cuuint64_t strides[3] = {(cuuint64_t)g.y_sw * 4, (cuuint64_t)g.y_sh * 4, (cuuint64_t)g.y_sn * 4};
     const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -2247,9 +2259,10 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   memset(&a, 0, sizeof(a));
   a.wpacked = reinterpret_cast<const uint8_t*>(w.packed);
   a.stat_sum = ep.stat_sum; a.stat_sqs = ep.stat_sqs;
-  a.NIMG = g.N; a.H = g.H; a.W = g.W; a.TW = TW; a.TH = TH; a.TX = cdiv(g.W, TW); a.TY = cdiv(g.H, TH);
+  a.NIMG = g.N; a.H = OH; a.W = OW; a.TW = TW; a.TH = TH; a.TX = cdiv(OW, TW); a.TY = cdiv(OH, TH);
   a.CC = g.Cin / 64; a.Ntot = w.N; a.NT = w.NT;
-  const size_t a_slot = 2 * (size_t)(TH + 2) * TW * 128;
+  a.NDX = ndx; a.NDY = ndy; a.DX0 = dx0; a.DY0 = dy0;
+  const size_t a_slot = 2 * (size_t)(TH + ndy - 1) * TW * 128;
   // CTA pairs (two neighbouring tiles per cluster, half the weight bytes and half the MMA instructions per tile): default on
   static const int pair_env = env_int("SAG_UMMA_PAIR", -1);
   const int want = g_umma_pair >= 0 ? g_umma_pair : pair_env;

@@ -380,6 +380,9 @@ static BnBuf take_bn(unsigned long long*& pool, int c) {
 int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc, int B, int H, int Wd, Act* y_act, Arena& ar,
                    cudaStream_t st) {
   Fwd f{h, ar, st, h->cfg.precision};
+  const bool overlap_sc = !ar.dry && h->overlap != 0 && h->side2 != nullptr && !h->prof.on;
+  Fwd fsc{h, ar, overlap_sc ? h->side2 : st, h->cfg.precision};      // the shortcut convolutions (see below)
+  fsc.private_scratch = true;
   const std::string p = scope + "/";
   const float eps = 1e-3f;
   int err = SAG_OK;
@@ -466,8 +469,15 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
     const int64_t npix = (int64_t)B * nh * nw;
     ActView shortcut = cur.v;
     if (b.first) {                                      // resnet.py:211-212: 1x1/s conv, no BN, no bias
+      // a short grid that only the block's final residual add reads: on its own stream it fills SMs beside conv_1 / its
+      // normalisation pass instead of holding up the main chain (fork here, join before conv_2's normalisation)
       Act sc = f.alloc_f32(npix, b.cout);
-      SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, nullptr, nullptr, &oh, &ow));
+      if (overlap_sc) {
+        SAG_CHECK_CUDA(cudaEventRecord(h->ev[4], st));
+        SAG_CHECK_CUDA(cudaStreamWaitEvent(h->side2, h->ev[4], 0));
+      }
+      SAG_TRY(fsc.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, nullptr, nullptr, &oh, &ow));
+      if (overlap_sc) SAG_CHECK_CUDA(cudaEventRecord(h->ev[5], h->side2));
       shortcut = sc.v;
     }
     Act r1 = f.alloc_f32(npix, b.cout);
@@ -484,6 +494,7 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
     }
     SAG_TRY(f.conv(a1, B, nh, nw, b.cout, q + "/conv_2", 3, 3, b.cout, 1, 1, 1, false, 0, r2, s2.sum, s2.sqs, &oh, &ow));
     SAG_TRY(bn_stats(q + "/conv_2", s2, npix, &t2));
+    if (b.first && overlap_sc) SAG_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev[5], 0));
     if (!ar.dry) {
       ProfScope ps(PROF_POINTWISE, 0, (4.0 + 2.0 * act_b) * npix * b.cout, st, (std::string(b.name) + "/conv_2 bn+add+relu").c_str());
       SAG_TRY(launch_bn_apply_stats(r2.f32(), t2, shortcut, 1, out.v, npix, b.cout, st));

@@ -87,7 +87,8 @@ struct sag_handle {
   int overlap = 1;
   int fuse_gains = 1;    // fold sigmoid + the 32 -> 9 localization-weighted sums into deconv1's epilogue where the tile plan allows
   cudaStream_t side = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side2 = nullptr;   // the 1x1 / stride-2 shortcut convolutions of the ResNet blocks, beside conv_1 / conv_2 of their block
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace sag {
