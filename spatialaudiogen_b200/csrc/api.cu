@@ -82,7 +82,7 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     bool ok = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-              cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+              cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { set_error("sag_create: could not create the side stream / events"); r = SAG_ECUDA; }
   }

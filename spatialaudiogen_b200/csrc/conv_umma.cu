@@ -1181,10 +1181,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
   const uint32_t bar_afull = bars, bar_aempty = bars + 8 * HL_MAX_SA;
   const uint32_t bar_bfull = bars + 16 * HL_MAX_SA, bar_bempty = bar_bfull + 8 * HL_MAX_SB;
   const uint32_t bar_tfull = bar_bempty + 8 * HL_MAX_SB, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
-  const uint32_t stile = (bars + 256 + 1023u) & ~1023u;       // 16 KB staging tile (swizzled TMA store)
+  const uint32_t stile0 = (bars + 256 + 1023u) & ~1023u;      // two 16 KB staging tiles (swizzled TMA stores, alternating passes)
   const uint32_t a_plane = (uint32_t)(a.TH + a.NDY - 1) * (uint32_t)a.TW * 128u;   // one bf16 plane of one box
   const uint32_t a_slot = 2 * a_plane;
-  const uint32_t a_base = stile + 16384u;
+  const uint32_t a_base = stile0 + 32768u;
   const uint32_t b_base = a_base + (uint32_t)a.SA * a_slot;
   const int SA = a.SA, SB = a.SB;
   const int tiles = a.NIMG * a.TY * a.TX;
@@ -1347,6 +1347,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
     const int row = q * 32 + lane;
     const int rr = row / a.TW, rc = row - rr * a.TW;      // position of this row's pixel inside the tile
     int it_local = 0;
+    uint32_t pass_no = 0;                                 // passes of this CTA so far: alternates the staging tile
     for (int wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int nimg, y0, x0, nt;
       bool real;
@@ -1359,9 +1360,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * 2 * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32, ++pass_no) {
         const int cc = c0 + half * 16;
-        const int par = (c0 >> 5) & 1;
+        const int par = (int)(pass_no & 1u);
+        const uint32_t stile = stile0 + (uint32_t)par * 16384u;
         float v[16], u[16];
         tmem_ld16(tmem_row + (uint32_t)cc, v);
         tmem_ld16(tmem_row + (uint32_t)(BN + cc), u);
@@ -1379,7 +1381,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
           const float cs = warp_column_sums<16>(sv, lane), cq = warp_column_sums<16>(sq, lane);
           if ((lane & 1) == 0) { s_part[par][q][half * 16 + (lane >> 1)] = cs; s_part[par][q][32 + half * 16 + (lane >> 1)] = cq; }
         }
-        if (et == 0) bulk_wait_read0();
+        // this staging tile was last read by the store issued two passes ago: with the other tile's store still allowed in
+        // flight, the wait is (almost) never a stall -- the store latency no longer sits between two passes
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
@@ -1389,9 +1393,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0 && real) {
-          tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
-          bulk_commit();
+        if (et == 0) {
+          if (real) tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
+          bulk_commit();                                   // (one group per pass, also an empty one: wait_group counts groups)
         }
         if (et < 32 && n_base + c0 + et < a.Ntot) {
           float ts = 0.f, tq = 0.f;
@@ -2157,7 +2161,7 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   }
   constexpr int B_BYTES = (BN + (PAIR ? BN / 2 : BN)) * 128;
   constexpr int CL = PAIR ? 2 : 1;
-  const size_t fixed = 256 + 1024 + 16384;
+  const size_t fixed = 256 + 1024 + 32768;
   HaloArgs args = a;
   args.SA = 3;
   long sb = ((long)budget[dev & 63] - (long)fixed - 3 * (long)a_slot) / B_BYTES;
@@ -2209,6 +2213,9 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   for (int t = 0; t < g.T; ++t)
     if (g.dy[t] != dy0 + t / ndx || g.dx[t] != dx0 + t % ndx) return SAG_OK;
   if (ndy < 2 || ndx > 3 || ndy > 4) return SAG_OK;
+  // conv1 (one tap column, four rows): its time is set by the 205 MB of raw fp32 output, not by operand bytes -- measured 125.6 us
+  // on the im2col kernel, 127-136 us here -- so it takes this kernel only when forced (tests)
+  if (ndx == 1 && halo_want <= 0) return SAG_OK;
   if (x.fmt != ACT_BF2 || x.plane == 0 || (reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return SAG_OK;
   if (w.planes != 2 || (w.BN != 64 && w.BN != 128) || w.N > 512 || w.col_off != nullptr || w.K != g.T * g.Cin) return SAG_OK;
   if (ep.bias != nullptr || ep.relu || y.fmt != ACT_F32 || g.y_sc != 1 || g.y_sw % 4 != 0 || g.oy0 != 0 || g.ox0 != 0 || g.osy != 1 || g.osx != 1 ||
@@ -2263,6 +2270,7 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   a.CC = g.Cin / 64; a.Ntot = w.N; a.NT = w.NT;
   a.NDX = ndx; a.NDY = ndy; a.DX0 = dx0; a.DY0 = dy0;
   const size_t a_slot = 2 * (size_t)(TH + ndy - 1) * TW * 128;
+  if (34048 + 2 * a_slot + 2 * (size_t)(2 * w.BN * 128) > 220 * 1024) return SAG_OK;      // two boxes + two weight chunks must fit
   // CTA pairs (two neighbouring tiles per cluster, half the weight bytes and half the MMA instructions per tile): default on
   static const int pair_env = env_int("SAG_UMMA_PAIR", -1);
   const int want = g_umma_pair >= 0 ? g_umma_pair : pair_env;

@@ -380,7 +380,10 @@ static BnBuf take_bn(unsigned long long*& pool, int c) {
 int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc, int B, int H, int Wd, Act* y_act, Arena& ar,
                    cudaStream_t st) {
   Fwd f{h, ar, st, h->cfg.precision};
-  const bool overlap_sc = !ar.dry && h->overlap != 0 && h->side2 != nullptr && !h->prof.on;
+  // (measured on B200: 1892 audio-s/s with the shortcuts in line, 1827-1880 and noisy with them on their own stream -- the fork /
+  // join costs more than the 15-19 us grids it hides; kept behind SAG_OVERLAP_SC=1)
+  static const bool sc_env = [] { const char* v = getenv("SAG_OVERLAP_SC"); return v != nullptr && atoi(v) != 0; }();
+  const bool overlap_sc = sc_env && !ar.dry && h->overlap != 0 && h->side2 != nullptr && !h->prof.on;
   Fwd fsc{h, ar, overlap_sc ? h->side2 : st, h->cfg.precision};      // the shortcut convolutions (see below)
   fsc.private_scratch = true;
   const std::string p = scope + "/";
@@ -468,17 +471,14 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
     const int nh = (ch + s - 1) / s, nw = (cw + s - 1) / s;
     const int64_t npix = (int64_t)B * nh * nw;
     ActView shortcut = cur.v;
+    Act sc_act;
     if (b.first) {                                      // resnet.py:211-212: 1x1/s conv, no BN, no bias
       // a short grid that only the block's final residual add reads: on its own stream it fills SMs beside conv_1 / its
       // normalisation pass instead of holding up the main chain (fork here, join before conv_2's normalisation)
-      Act sc = f.alloc_f32(npix, b.cout);
-      if (overlap_sc) {
-        SAG_CHECK_CUDA(cudaEventRecord(h->ev[4], st));
-        SAG_CHECK_CUDA(cudaStreamWaitEvent(h->side2, h->ev[4], 0));
-      }
-      SAG_TRY(fsc.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc, nullptr, nullptr, &oh, &ow));
-      if (overlap_sc) SAG_CHECK_CUDA(cudaEventRecord(h->ev[5], h->side2));
-      shortcut = sc.v;
+      sc_act = f.alloc_f32(npix, b.cout);
+      if (overlap_sc) SAG_CHECK_CUDA(cudaEventRecord(h->ev[4], st));        // `cur` is complete here; the launch follows conv_1's
+      else SAG_TRY(fsc.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc_act, nullptr, nullptr, &oh, &ow));
+      shortcut = sc_act.v;
     }
     Act r1 = f.alloc_f32(npix, b.cout);
     Act a1 = f.alloc_act(npix, b.cout);
@@ -487,6 +487,11 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
     BnBuf s1 = take_bn(stat_pool, b.cout), s2 = take_bn(stat_pool, b.cout);
     BnStats t1, t2;
     SAG_TRY(f.conv(cur, B, ch, cw, cc, q + "/conv_1", 3, 3, b.cout, s, s, 1, false, 0, r1, s1.sum, s1.sqs, &oh, &ow));
+    if (b.first && overlap_sc) {                        // queued behind conv_1: it takes the SMs conv_1's tail and the passes below leave idle
+      SAG_CHECK_CUDA(cudaStreamWaitEvent(h->side2, h->ev[4], 0));
+      SAG_TRY(fsc.conv(cur, B, ch, cw, cc, q + "/shortcut", 1, 1, b.cout, s, s, 1, false, 0, sc_act, nullptr, nullptr, &oh, &ow));
+      SAG_CHECK_CUDA(cudaEventRecord(h->ev[5], h->side2));
+    }
     SAG_TRY(bn_stats(q + "/conv_1", s1, npix, &t1));
     if (!ar.dry) {
       ProfScope ps(PROF_POINTWISE, 0, (4.0 + act_b) * npix * b.cout, st, (std::string(b.name) + "/conv_1 bn+relu").c_str());
