@@ -241,7 +241,7 @@ def run_reference(args, encoders):
 def default_precision_name(args):
     if args.precision != 'auto':
         return args.precision
-    return os.environ.get('SAG_PRECISION', 'bf16x3')     # == spatialaudiogen_b200._lib.default_precision()
+    return os.environ.get('SAG_PRECISION', 'mixed')
 
 
 RESNET_NPY = os.path.join(ROOT, 'tests', 'golden', '_ref', 'resnet18.npy')   # staged by __graft_entry__.build() (git-ignored)
@@ -312,7 +312,10 @@ def main():
     B = args.batch
     precision = args.precision
     if precision == 'auto':
-        precision = L.default_precision() if hasattr(L, 'default_precision') else 'fp32'
+        # the per-layer plan measured in tests/test_gpu_bench_config.py::test_precision_plan_error_table_b32: bf16x3 (fp32-grade
+        # split operands) everywhere except the U-Net decoder's deconv5..2 (one bf16 product); waveform error at this
+        # configuration 6.6e-5 of max|y| with either -- the north-star tolerance is 1e-3.  SAG_PRECISION / --precision override.
+        precision = os.environ.get('SAG_PRECISION', 'mixed')
     model = SptAudioGen(1, encoders=encoders, separation='unet_mask', precision=precision, device=dev)
     model.load_weights(Wt.init_weights(encoders, separation='unet_mask', seed=1234,
                                        resnet_npy=RESNET_NPY if os.path.exists(RESNET_NPY) else None))
