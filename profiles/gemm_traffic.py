@@ -25,7 +25,7 @@ def main(path, out):
     starts = [i for i, k in enumerate(order) if 'gather_gemm_umma_kernel<32,' in launches[k]['name'].replace('(int)', '')]
     assert len(starts) >= 1, 'no forward in the capture'
     sel = [launches[k] for k in order[starts[0]:(starts[1] if len(starts) > 1 else len(order))]]
-    gemm = [l for l in sel if 'gather_gemm_umma_kernel' in l['name']]
+    gemm = [l for l in sel if 'gather_gemm_umma_kernel' in l['name'] or 'halo_conv_umma_kernel' in l['name']]
     red = [l for l in sel if 'splitk_reduce' in l['name']]
 
     def tot(ls, m):
