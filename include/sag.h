@@ -136,6 +136,14 @@ int sag_set_option(sag_handle* h, const char* key, int value);
  * tile width (32 | 64 | 128 | 256 GEMM columns per CTA tile) and K split.  Pure host arithmetic; lets tests / profiles name
  * the kernel instantiation a layer runs at a given batch size. */
 int sag_plan_contraction(int k, int n, int64_t m, int* tile_width, int* k_split);
+/* Stream-K (layers whose tiles fill the last wave of the persistent grid badly: conv4_x / conv5_x at 32 windows): the
+ * (tile, K chunk) units are dealt out evenly over the CTA clusters and the pieces of a tile meet in the epilogue of the CTA that
+ * finishes it.  sag_plan_stream_k: 1 if the planner picks it for this shape on the forward's main stream.
+ * sag_stream_k_schedule: the pieces of cluster `cluster` of `clusters` over `tiles` tiles of `k_chunks` chunks, in execution
+ * order -- items[j] = {tile, first chunk, end chunk, leaves a partial (1) or finishes the tile (0), first cluster holding an
+ * earlier piece of the tile (-1: none)}; returns the number of pieces (the kernel runs this same code).  Host arithmetic. */
+int sag_plan_stream_k(int k, int n, int64_t m);
+int sag_stream_k_schedule(int64_t tiles, int k_chunks, int clusters, int cluster, int* items, int max_items);
 /* how many kernels the last sag_forward launched (bench.py gpu_launches) */
 int sag_last_launch_count(const sag_handle* h);
 /* With option "profile" = 1 every launch group of sag_forward is bracketed by CUDA events on the caller's stream.

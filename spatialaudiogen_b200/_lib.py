@@ -62,6 +62,8 @@ PROTOTYPES = {
     'sag_tensor_name': (_I, [_P, _I, C.c_char_p, _I]),
     'sag_last_launch_count': (_I, [_P]),
     'sag_plan_contraction': (_I, [_I, _I, _L, C.POINTER(_I), C.POINTER(_I)]),
+    'sag_plan_stream_k': (_I, [_I, _I, _L]),
+    'sag_stream_k_schedule': (_I, [_L, _I, _I, _I, C.POINTER(_I), _I]),
     'sag_get_profile': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     'sag_num_profile_records': (_I, [_P]),
     'sag_get_profile_record': (_I, [_P, _I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -84,6 +84,9 @@ int sag_create(sag_handle** out, const sag_config* cfg) {
     bool ok = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    // stream-K flags of the main stream's contractions (zero between launches)
+    ok = ok && cudaMalloc(&h->sk_flags, UMMA_SK_FLAGS * sizeof(int)) == cudaSuccess &&
+         cudaMemset(h->sk_flags, 0, UMMA_SK_FLAGS * sizeof(int)) == cudaSuccess;
     if (!ok) { set_error("sag_create: could not create the side stream / events"); r = SAG_ECUDA; }
   }
   if (r != SAG_OK) { sag_destroy(h); return r; }
@@ -101,6 +104,7 @@ int sag_destroy(sag_handle* h) {
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->sk_flags) cudaFree(h->sk_flags);
   delete h;
   return SAG_OK;
 }
@@ -289,6 +293,17 @@ int sag_plan_contraction(int k, int n, int64_t m, int* tile_width, int* k_split)
   if (tile_width) *tile_width = umma_tile_width(k, n, m);
   if (k_split) *k_split = umma_split_k(k, n, m, nullptr);
   return SAG_OK;
+}
+
+int sag_plan_stream_k(int k, int n, int64_t m) {
+  SAG_REQUIRE(k > 0 && n > 0 && m > 0, SAG_EINVAL, "sag_plan_stream_k: bad shape %d x %d over %lld rows", k, n, (long long)m);
+  return umma_stream_k(k, n, m) ? 1 : 0;
+}
+
+int sag_stream_k_schedule(int64_t tiles, int k_chunks, int clusters, int cluster, int* items, int max_items) {
+  SAG_REQUIRE(tiles > 0 && k_chunks > 0 && clusters > 0 && cluster >= 0 && cluster < clusters && (items != nullptr || max_items == 0),
+              SAG_EINVAL, "sag_stream_k_schedule: bad argument");
+  return streamk_schedule(tiles, k_chunks, clusters, cluster, items, max_items);
 }
 
 int sag_num_profile_records(const sag_handle* h) { return h ? (int)h->prof.recs.size() : SAG_EINVAL; }

@@ -128,7 +128,11 @@ struct Epilogue {
   const float* gain_loc;
   float* gains;
   int64_t gain_plane;     // frames * bins
+  // stream-K (tcgen05 path): UMMA_SK_FLAGS zeroed ints owned by the caller's stream (a kernel leaves them zeroed); null = the
+  // launch never deals K chunks of a tile out to several CTAs
+  int* sk_flags;
 };
+constexpr int UMMA_SK_FLAGS = 1024;
 
 // Exact fixed-point accumulation of float partial sums: word 0 = integer part (two's complement), word 1 = fraction * 2^40.
 // A float at or above 2^-17 in magnitude is represented exactly (24-bit mantissa), smaller ones are truncated to the 2^-40 grid;
@@ -225,6 +229,9 @@ extern thread_local int g_umma_tma;   // -1: SAG_UMMA_TMA env (default on); 0/1:
 extern thread_local int g_umma_halo;  // -1: SAG_UMMA_HALO env (default on); 0/1: forced: halo-resident kernel for the 3x3 stride-1 convs
 // scratch: split-K workspace of at least the bytes umma_split_k reports (null: never split)
 int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes);
+// stream-K pieces of one cluster in execution order (items: [n][5] = tile, first chunk, end chunk, produce, fix_first); returns n
+bool umma_stream_k(int K, int N, int64_t M);      // the planner deals this shape out as stream-K (given flags + scratch)
+int streamk_schedule(int64_t tiles, int kc, int clusters, int cluster, int* items, int max_items);
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
                             int oh_lim, int ow_lim, float* scratch, cudaStream_t st);
 

@@ -74,6 +74,7 @@ struct UmmaArgs {
   int NT, Z;              // N tiles, K splits
   int tma_w0, tma_h0;     // SRC_TMA: smallest tap displacement (= lower corner of the im2col bounding box)
   long long* trace;       // SAG_UMMA_TRACE (debug): per-CTA cycle counters of the three roles
+  int dbg;                // SAG_UMMA_EPI_DEBUG (timing experiments, results invalid): 1 no statistics, 2 no TMA store, 4 no staging writes
   int pair_ok;            // host: the tiled weight map exists (CTA pairs fetch their weight blocks through it)
   // how a staged 128 x 32 pass leaves the CTA: 0 = LSU copy-out (any output format / mapping); 1 = one TMA tensor store per
   // pass (dense fp32 rows, or the split-K partials); 2 = bulk stores of contiguous 4 KB runs (sub-pixel transposed conv
@@ -85,6 +86,11 @@ struct UmmaArgs {
   const float* gain_loc;
   float* gains;
   int64_t gain_plane;
+  // stream-K (sk_flags != null, Z == 1): the (tile, K chunk) units are dealt out evenly over the clusters, a cluster's range is
+  // cut at tile boundaries; a piece that does not end its tile leaves its raw accumulators in the CTA's slab and raises the
+  // CTA's flag, the piece that ends the tile adds the slabs of the pieces before it in its epilogue (fixed order: reproducible)
+  int* sk_flags;          // one per CTA, zero between launches (the consumer clears what it has seen)
+  float* sk_slab;         // [CTA][128][BN] fp32
 };
 // im2col tensor maps of the two activation planes (SRC_TMA) + the tiled map of the packed weight image (CTA pairs: 128-byte
 // rows, boxes of BN/2 rows); kernel parameter, read by the TMA unit
@@ -296,6 +302,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same without the wait: several loads in flight, then one tmem_ld_wait() before the first use
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // fp32 -> bf16 hi (round to nearest even) and the bf16 of the remainder; 8 values -> two 16-byte vectors
 __device__ __forceinline__ void split8(const float* f, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -353,6 +373,45 @@ constexpr int SRC_F32 = 0, SRC_F32_VEC = 1, SRC_BF2 = 2, SRC_TMA = 3;
 // Persistent: one CTA per SM walks the work list (m tile, n tile, K split) with a static stride; the three roles run
 // decoupled through mbarriers, so the operand ring never drains between tiles and the epilogue of tile i overlaps the
 // MMAs of tile i+1 (two TMEM accumulators).
+// Stream-K work of one cluster: its units [u0, u1) of the tiles * KC (tile, K chunk) units, as n pieces of consecutive tiles.
+// Order within the cluster: the piece that leaves its tile unfinished first (its consumer finds the slab ready), whole tiles
+// next, the piece that finishes a tile begun by the clusters before it last.  (Host + device: sag_stream_k_schedule runs the
+// same code for the CPU tests.)
+struct SkRange {
+  int64_t u0, u1, t0, U, G, c;
+  int KC, n;
+  bool rot;
+  __host__ __device__ void init(int64_t tiles, int kc, int64_t clusters, int64_t cluster) {
+    KC = kc; G = clusters; c = cluster;
+    U = tiles * kc;
+    u0 = c * U / G;
+    u1 = (c + 1) * U / G;
+    t0 = 0; n = 0; rot = false;
+    if (u1 > u0) {
+      t0 = u0 / KC;
+      n = (int)((u1 - 1) / KC - t0 + 1);
+      rot = (u1 % KC) != 0 && n > 1;
+    }
+  }
+  // j-th piece in execution order: tile, K chunks [kb, ke); produce: the piece does not end its tile (raw accumulators ->
+  // slab, raise the flag); fix_first >= 0: the piece ends a tile begun elsewhere -- clusters fix_first .. c-1 hold the rest
+  __host__ __device__ void item(int64_t j, int64_t* tile, int* kb, int* ke, bool* produce, int* fix_first) const {
+    int64_t i = 0;
+    if (n > 1) i = rot ? (j == 0 ? n - 1 : (j == n - 1 ? 0 : j)) : (j == n - 1 ? 0 : j + 1);
+    const int64_t t = t0 + i, tb = t * KC;
+    *tile = t;
+    *kb = (int)((u0 > tb ? u0 : tb) - tb);
+    *ke = (int)((u1 < tb + KC ? u1 : tb + KC) - tb);
+    *produce = *ke < KC;
+    *fix_first = -1;
+    if (!*produce && *kb > 0) {
+      int64_t f = c - 1;
+      while (f > 0 && f * U / G > tb) --f;
+      *fix_first = (int)f;
+    }
+  }
+};
+
 template <int BN, int NSPLIT, int SRC, bool PAIR>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
@@ -435,11 +494,30 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   // work item -> (m tile, n tile, split): m fastest, so neighbouring CTAs share the weight tile in L2; the CTAs of a
   // cluster take adjacent m tiles of the same (n tile, split) and walk their K chunks in lockstep (mt may be >= MT
   // for the last group: that CTA then runs an all-padding tile to keep the lockstep)
-  auto decode_work = [&](int64_t wk, int& mt, int& nt, int& z) {
-    mt = (int)(wk % MG) * CL + (int)crank;
+  struct WorkItem {
+    int mt, nt, z, kc_begin, kc_end;
+    bool produce;      // stream-K piece that does not end its tile: raw accumulators -> slab, raise the flag
+    int fix_first;     // stream-K piece that ends a tile begun elsewhere: first cluster holding an earlier piece (-1: none)
+  };
+  const bool sk = a.sk_flags != nullptr;
+  const int64_t sk_c = blockIdx.x / CL;
+  SkRange skr;
+  skr.init(sk ? (int64_t)MG * NT : 0, a.KC, gridDim.x / CL, sk_c);
+  const int64_t n_items = sk ? (int64_t)skr.n : (wk0 < n_work ? (n_work - wk0 + wk_step - 1) / wk_step : 0);
+  auto item_at = [&](int64_t j, WorkItem& it) {
+    int64_t wk;
+    it.produce = false;
+    it.fix_first = -1;
+    if (!sk) wk = wk0 + j * wk_step;
+    else skr.item(j, &wk, &it.kc_begin, &it.kc_end, &it.produce, &it.fix_first);
+    it.mt = (int)(wk % MG) * CL + (int)crank;
     const int64_t r = wk / MG;
-    nt = (int)(r % NT);
-    z = (int)(r / NT);
+    it.nt = (int)(r % NT);
+    it.z = (int)(r / NT);
+    if (!sk) {
+      it.kc_begin = (int)((int64_t)it.z * a.KC / Z);
+      it.kc_end = (int)((int64_t)(it.z + 1) * a.KC / Z);
+    }
   };
 
   if (TMA_ANY && warp < 4) {
@@ -449,10 +527,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       uint32_t phase = 0;
       long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
       const uint32_t lead_full = PAIR ? map_to_cta(bar_full, 0) : bar_full;      // the pair leader's full barriers (cluster address)
-      for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
-        int mt, nt, z;
-        decode_work(wk, mt, nt, z);
-        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+      for (int64_t wj = 0; wj < n_items; ++wj) {
+        WorkItem wi;
+        item_at(wj, wi);
+        const int mt = wi.mt, nt = wi.nt, kc_begin = wi.kc_begin, kc_end = wi.kc_end;
         // base input pixel of the tile's first row (the padding tile of an odd pair reloads the last tile; its rows
         // are never stored)
         const uint32_t mu = (uint32_t)((int64_t)(mt < MT ? mt : MT - 1) * UM_BM);
@@ -520,11 +598,11 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     int stage = 0;
     uint32_t phase = 0;
     long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
-    for (int64_t wk = wk0; wk < n_work; wk += wk_step) {
-      int mt, nt, z;
-      decode_work(wk, mt, nt, z);
+    for (int64_t wj = 0; wj < n_items; ++wj) {
+      WorkItem wi;
+      item_at(wj, wi);
+      const int mt = wi.mt, nt = wi.nt, kc_begin = wi.kc_begin, kc_end = wi.kc_end;
       const int64_t m0 = (int64_t)mt * UM_BM;
-      const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
       int iy0[4], ix0[4];
       int64_t img[4];                           // element offset of the row's image
       bool rok[4];
@@ -645,10 +723,10 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       int64_t it_local = 0;
       long long tr_wait = 0, tr_wacc = 0, tr_t0 = clock64();
       constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);   // LBO, SBO, version, SW128
-      for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
-        int mt, nt, z;
-        decode_work(wk, mt, nt, z);
-        const int kc_begin = (int)((int64_t)z * a.KC / Z), kc_end = (int)((int64_t)(z + 1) * a.KC / Z);
+      for (int64_t wj = 0; wj < n_items; ++wj, ++it_local) {
+        WorkItem wi;
+        item_at(wj, wi);
+        const int kc_begin = wi.kc_begin, kc_end = wi.kc_end;
         const int b = (int)(it_local & 1);
         const uint32_t use = (uint32_t)(it_local >> 1);
         const long long tr_a0 = a.trace ? clock64() : 0;
@@ -730,9 +808,14 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     int64_t it_local = 0;
     long long tr_wait = 0, tr_t0 = clock64();
     long long tr_p[5] = {0, 0, 0, 0, 0};
-    for (int64_t wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
-      int mt, nt, z;
-      decode_work(wk, mt, nt, z);
+    for (int64_t wj = 0; wj < n_items; ++wj, ++it_local) {
+      WorkItem wi;
+      item_at(wj, wi);
+      const int mt = wi.mt, nt = wi.nt, z = wi.z;
+      // stream-K slabs hold a tile as [pass][4-column group][epilogue thread] float4s: producer and consumer are the same thread
+      // index of two CTAs, so both sides move 512 contiguous bytes per warp instruction
+      const bool rawp = wi.produce;                // piece bound for this CTA's slab
+      float4* const my_slab = reinterpret_cast<float4*>(a.sk_slab) + (size_t)blockIdx.x * (UM_BM * BN / 4);
       const int64_t m0 = (int64_t)mt * UM_BM;
       const int n_base = nt * BN;
       const int b = (int)(it_local & 1);
@@ -895,6 +978,66 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       if (a.trace) tr_wait += clock64() - tr_w0;
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      if (wi.fix_first >= 0) {
+        // the pieces before this one (clusters fix_first .. sk_c - 1, same CTA rank): wait for their slabs, clear the flags for
+        // the next launch (each flag has this one consumer)
+        if (et == 0) {
+          for (int c = wi.fix_first; c < (int)sk_c; ++c) {
+            int* f = a.sk_flags + c * CL + (int)crank;
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+              if (seen == 0) __nanosleep(64);
+            } while (seen == 0);
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(0) : "memory");
+          }
+        }
+        const long long tq0 = a.trace ? clock64() : 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (a.trace) tr_p[2] += clock64() - tq0;     // (trace: time blocked on the flags)
+      }
+      if (rawp) {
+        // ---- stream-K piece that leaves its tile unfinished: raw accumulators -> slab, 64 columns (all TMEM loads in flight) at a time
+        const long long tq0 = a.trace ? clock64() : 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          float v[2][CPT];
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int e = 0; e < CPT; e += 16) tmem_ld16_nowait(tmem_row + (uint32_t)(c0 + 32 * p + half * CPT + e), v[p] + e);
+          if (CONCAT) {
+            float u[2][CPT];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int e = 0; e < CPT; e += 16) tmem_ld16_nowait(tmem_row + (uint32_t)(BN + c0 + 32 * p + half * CPT + e), u[p] + e);
+            tmem_ld_wait();
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+              for (int e = 0; e < CPT; ++e) v[p][e] += u[p][e];
+          } else {
+            tmem_ld_wait();
+          }
+          if (c0 + 64 >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
+          }
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int e = 0; e < CPT; e += 4)
+              __stcg(my_slab + ((size_t)((c0 >> 5) + p) * (CPT / 4) + (e >> 2)) * (EW * 32) + et, make_float4(v[p][e], v[p][e + 1], v[p][e + 2], v[p][e + 3]));
+        }
+        // the slab is complete: every thread's stores are ordered before the flag (fence by the writers, barrier, release store)
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (et == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.sk_flags + blockIdx.x), "r"(1) : "memory");
+        if (a.trace) tr_p[1] += clock64() - tq0;     // (trace: raw pieces)
+        continue;
+      }
       if constexpr (BN == 256 && EW == 8 && NSPLIT != 2) {
         if (a.out_mode == 3) {
           // ---- mask-gain fusion (model.py:334 sigmoid mask, :424-432 mixing, folded by linearity like mask_gains_kernel in
@@ -972,6 +1115,20 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           continue;
         }
       }
+      float4 pf[2][CPT / 4];                       // stream-K fix-up: slab values of the next pass (first two earlier pieces)
+      auto slab_of = [&](int c) { return reinterpret_cast<const float4*>(a.sk_slab) + (size_t)(c * CL + (int)crank) * (UM_BM * BN / 4); };
+      auto fetch_pf = [&](int c0) {
+        const int np = (int)sk_c - wi.fix_first;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (p < np) {
+            const float4* ps = slab_of(wi.fix_first + p) + (size_t)(c0 >> 5) * (CPT / 4) * (EW * 32) + et;
+#pragma unroll
+            for (int e4 = 0; e4 < CPT / 4; ++e4) pf[p][e4] = __ldcg(ps + (size_t)e4 * (EW * 32));
+          }
+        }
+      };
+      if (wi.fix_first >= 0) fetch_pf(0);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[CPT];
@@ -990,6 +1147,26 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
+        }
+        if (wi.fix_first >= 0) {
+          // the earlier pieces of the tile: the first two slabs were fetched a pass ahead (pf), further ones (a tile spread over
+          // more than three clusters) are read here; added in cluster order
+          const int np = (int)sk_c - wi.fix_first;
+#pragma unroll
+          for (int e4 = 0; e4 < CPT / 4; ++e4) { v[4 * e4] += pf[0][e4].x; v[4 * e4 + 1] += pf[0][e4].y; v[4 * e4 + 2] += pf[0][e4].z; v[4 * e4 + 3] += pf[0][e4].w; }
+          if (np > 1) {
+#pragma unroll
+            for (int e4 = 0; e4 < CPT / 4; ++e4) { v[4 * e4] += pf[1][e4].x; v[4 * e4 + 1] += pf[1][e4].y; v[4 * e4 + 2] += pf[1][e4].z; v[4 * e4 + 3] += pf[1][e4].w; }
+          }
+          for (int c = wi.fix_first + 2; c < (int)sk_c; ++c) {
+            const float4* ps = slab_of(c) + (size_t)(c0 >> 5) * (CPT / 4) * (EW * 32) + et;
+            float4 f[CPT / 4];
+#pragma unroll
+            for (int e4 = 0; e4 < CPT / 4; ++e4) f[e4] = __ldcg(ps + (size_t)e4 * (EW * 32));
+#pragma unroll
+            for (int e4 = 0; e4 < CPT / 4; ++e4) { v[4 * e4] += f[e4].x; v[4 * e4 + 1] += f[e4].y; v[4 * e4 + 2] += f[e4].z; v[4 * e4 + 3] += f[e4].w; }
+          }
+          if (c0 + 32 < BN) fetch_pf(c0 + 32);       // the next pass's slab values travel while this pass is stored
         }
         if (!split && (a.bias != nullptr || a.relu)) {
           const int n0 = n_base + cc;
@@ -1015,7 +1192,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           // ---- store through the TMA unit: no shared -> register -> global copy-out.  The staging tile is written in the layout
           // the store reads (mode 1: 128-byte rows, SWIZZLE_128B like the tensor map; mode 2: four [128 rows][8 floats] blocks),
           // one elected thread issues the store(s); batch-norm column sums come from the registers (warp butterfly).
-          const bool st_pass = stats && !split;
+          const bool st_pass = stats && !split && !(a.dbg & 1);
           const int par = (c0 >> 5) & 1;
           if (st_pass) {
             float sq[CPT];
@@ -1032,7 +1209,8 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           }
           if (et == 0) bulk_wait_read0();            // the previous pass's store has finished reading the staging tile
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-          if (a.out_mode == 1) {
+          if (a.dbg & 4) {
+          } else if (a.out_mode == 1) {
 #pragma unroll
             for (int e = 0; e < CPT; e += 4) {
               const uint32_t chunk = (uint32_t)(half * CPT + e) >> 2;
@@ -1050,7 +1228,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           fence_proxy_async();                         // generic-proxy writes -> visible to the TMA unit
           long long tp1 = a.trace ? clock64() : 0;
           asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
-          if (et == 0 && rows_valid > 0) {            // (rows_valid == 0: the all-padding tile of an odd CTA pair stores nothing)
+          if (et == 0 && rows_valid > 0 && !(a.dbg & 6)) {            // (rows_valid == 0: the all-padding tile of an odd CTA pair stores nothing)
             if (a.out_mode == 1) {
               // rows / columns beyond the tensor are clipped by the tensor map (split-K partial slabs are padded to whole tiles)
               tma_store_2d(&tm.o, stile, n_base + c0, (int)(split ? (int64_t)z * a.m_pad + m0 : m0));
@@ -1706,7 +1884,14 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   const int64_t n_work = cdiv64(MT, CL) * nt * Z;                   // per cluster
   int64_t clusters = max_conv_ctas() / CL;                          // (SAG_UMMA_MAX_CTAS: test knob, forces many work items per CTA)
   if (clusters < 1) clusters = 1;
-  if (n_work < clusters) clusters = n_work;
+  if (a.sk_flags != nullptr) {
+    // stream-K: every cluster gets work (>= 2 units each), a CTA has one slab and one flag
+    if (clusters * CL > UMMA_SK_FLAGS) clusters = UMMA_SK_FLAGS / CL;
+    if (clusters * CL > num_sms()) clusters = num_sms() / CL;
+    if (n_work * a.KC < 2 * clusters) clusters = std::max<int64_t>(1, n_work * a.KC / 2);
+  } else if (n_work < clusters) {
+    clusters = n_work;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
   cfg.blockDim = dim3(UM_THREADS);
@@ -1848,6 +2033,15 @@ static const ForcedCfg* forced_for(int N, int64_t M) {
 // a K split adds the partial round trip through L2 and the reduce launch.  A single M tile (fully connected layers
 // on a batch of windows) is weight-streaming bound: narrow tiles + a deep split spread the weights over all SMs.
 struct TilePlan { int BN, Z; };
+// Stream-K (see plan_streamk) is off unless SAG_UMMA_STREAMK=1: measured on B200 it shortens conv4_x / conv5_x by 0-2 us each
+// in isolation and LENGTHENS the forward (1745 vs 1811 audio-s/s): the contraction is bound by shared-memory bandwidth, not by
+// the SM count, the idle third of the SMs was hosting the audio chain of the side stream, and the two
+// serial epilogues at the end of every stream-K kernel (raw piece, fix-up) eat the balanced main loop's gain.  Read at every
+// call (tests switch it on for the layers they check); a handle must be planned and run under the same setting.
+static bool streamk_enabled() {
+  const char* v = getenv("SAG_UMMA_STREAMK");
+  return v != nullptr && atoi(v) != 0;
+}
 static TilePlan plan_tile(int K, int N, int64_t M) {
   static const int wide = env_int("SAG_UMMA_BN256", 1);
   static const int narrow_fc = env_int("SAG_UMMA_NARROW_FC", 1);
@@ -1880,8 +2074,37 @@ static TilePlan plan_tile(int K, int N, int64_t M) {
     }
     if (ci == 0 || bt < best_t * 0.95) { best_t = bt; best = TilePlan{BN, bz}; }
   }
+  // Stream-K on CTA pairs with 256-wide tiles (plan_streamk below): the K chunks of the few wide tiles are dealt out over all
+  // pairs, so the wide tile's halved weight traffic no longer costs whole idle waves (conv5_x at 32 windows: 26 pair tiles on 74
+  // pairs).  Cost: the cluster's share of chunks at the pair rate (measured 1612 clk per 256 x 256 x 64 chunk) + the two
+  // serial epilogues at the end (raw piece, then the fix-up) + launch.
+  const int64_t MT = cdiv64(M, UM_BM);
+  if (streamk_enabled() && wide && !f && N >= 256 && KC >= 16 && MT >= 8) {
+    const int64_t units = cdiv64(MT, 2) * cdiv(N, 256) * KC, G = max_conv_ctas() / 2;
+    if (G >= 2 && units >= 4 * G) {
+      const double t = (double)cdiv64(units, G) * 0.82 + 13.0 + 5.0;
+      if (t < best_t * 0.9) best = TilePlan{256, 1};
+    }
+  }
   return best;
 }
+
+// Stream-K: when the tiles of an unsplit plan fill the last wave of the persistent grid badly (conv4_x at 32 windows: 49 tile
+// pairs on 74 CTA pairs, conv5_x: 100 tiles on 148 CTAs -- a third of the SMs idle), the (tile, K chunk) units are dealt out
+// evenly instead and the pieces of a tile meet in the epilogue of the CTA that finishes it (UmmaArgs::sk_flags).
+static bool plan_streamk(int K, int N, int64_t M, const TilePlan& p) {
+  const bool on = streamk_enabled();
+  static const int thr = env_int("SAG_UMMA_STREAMK_EFF", 80);       // use it below this wave efficiency (percent)
+  const int KC = cdiv(K, UM_BK);
+  if (!on || p.Z != 1 || p.BN < 64 || KC < 8) return false;
+  const int64_t MT = cdiv64(M, UM_BM);
+  const int CL = (p.BN == 256 && KC >= 16 && MT >= 2) ? 2 : 1;       // (the pair rule of launch_ns)
+  const int64_t T = cdiv64(MT, CL) * cdiv(N, p.BN), G = max_conv_ctas() / CL;
+  if (G < 2 || T * KC < 4 * G) return false;
+  const int64_t waves = cdiv64(T, G);
+  return T * 100 < waves * G * thr;
+}
+static size_t streamk_slab_bytes(int BN) { return sizeof(float) * (size_t)num_sms() * UM_BM * (size_t)BN; }
 
 // cuTensorMapEncodeTiled / cuTensorMapEncodeIm2col through the runtime's driver entry point lookup: libsag.so carries no
 // link-time dependency on libcuda.so (it must load -- and report "no device" -- on machines without a driver)
@@ -2079,7 +2302,23 @@ int umma_split_k(int K, int N, int64_t M, size_t* scratch_bytes) {
   const TilePlan p = plan_tile(K, N, M);
   // partial slabs are padded to whole 128-row tiles (the TMA store of a tile never crosses into the next slab)
   if (scratch_bytes) *scratch_bytes = p.Z > 1 ? sizeof(float) * (size_t)p.Z * (size_t)(cdiv64(M, UM_BM) * UM_BM) * (size_t)(cdiv(N, p.BN) * p.BN) : 0;
+  if (scratch_bytes && plan_streamk(K, N, M, p)) *scratch_bytes = streamk_slab_bytes(p.BN);      // (stream-K plans have Z == 1)
   return p.Z;
+}
+
+bool umma_stream_k(int K, int N, int64_t M) { return plan_streamk(K, N, M, plan_tile(K, N, M)); }
+
+int streamk_schedule(int64_t tiles, int kc, int clusters, int cluster, int* items, int max_items) {
+  SkRange r;
+  r.init(tiles, kc, clusters, cluster);
+  for (int j = 0; j < r.n && j < max_items; ++j) {
+    int64_t t;
+    int kb, ke, ff;
+    bool produce;
+    r.item(j, &t, &kb, &ke, &produce, &ff);
+    items[5 * j] = (int)t; items[5 * j + 1] = kb; items[5 * j + 2] = ke; items[5 * j + 3] = produce ? 1 : 0; items[5 * j + 4] = ff;
+  }
+  return r.n;
 }
 
 thread_local int g_umma_tma = -1;   // -1: SAG_UMMA_TMA (default on); 0 / 1: forced (sag_set_option "tma_gather")
@@ -2338,7 +2577,14 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     SAG_TRY(try_halo_conv(x, w, y, g, ep, Z, st, &done));
     if (done) return SAG_OK;
   }
+  static const int epi_dbg = env_int("SAG_UMMA_EPI_DEBUG", 0);
+  a.dbg = epi_dbg;
   if (Z > 1) a.partial = scratch;
+  if (Z == 1 && scratch != nullptr && ep.sk_flags != nullptr && w.col_off == nullptr && ep.gains == nullptr &&
+      plan_streamk(w.K, w.N, M, plan)) {
+    a.sk_flags = ep.sk_flags;
+    a.sk_slab = scratch;
+  }
   // output pixel m sits at element m*y_sw: the epilogue needs no (n, i, j) decode
   a.dense = (w.col_off == nullptr && g.osy == 1 && g.osx == 1 && g.oy0 == 0 && g.ox0 == 0 &&
              g.y_sh == (int64_t)g.PW * g.y_sw && g.y_sn == (int64_t)g.PH * g.y_sh) ? 1 : 0;

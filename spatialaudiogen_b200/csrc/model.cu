@@ -146,8 +146,14 @@ int launch_gather_gemm(int precision, const float* x, const float* w, float* y, 
   SAG_TRY(umma_pack_weights(w, g.T * g.Cin, g.Cout, g.Cout, precision, (int64_t)g.N * g.PH * g.PW, &uw, st));
   size_t sbytes = 0;
   float* scratch = nullptr;
-  if (umma_split_k(uw.K, uw.N, (int64_t)g.N * g.PH * g.PW, &sbytes) > 1 && cudaMalloc(&scratch, sbytes) != cudaSuccess) scratch = nullptr;
-  int r = launch_gather_gemm_umma(x, uw, y, g, ep, 0, 0, scratch, st);
+  umma_split_k(uw.K, uw.N, (int64_t)g.N * g.PH * g.PW, &sbytes);
+  if (sbytes > 0 && cudaMalloc(&scratch, sbytes + UMMA_SK_FLAGS * sizeof(int)) != cudaSuccess) scratch = nullptr;
+  Epilogue ep2 = ep;
+  if (scratch != nullptr) {       // split-K partials / stream-K slabs, then the stream-K flags
+    ep2.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + sbytes);
+    cudaMemsetAsync(ep2.sk_flags, 0, UMMA_SK_FLAGS * sizeof(int), st);
+  }
+  int r = launch_gather_gemm_umma(x, uw, y, g, ep2, 0, 0, scratch, st);
   cudaStreamSynchronize(st);
   if (scratch) cudaFree(scratch);
   umma_free(&uw);
@@ -270,6 +276,7 @@ struct Fwd {
     }
     if (dry()) return SAG_OK;
     Epilogue ep{b, relu, ssum, ssqs};
+    ep.sk_flags = private_scratch ? nullptr : h->sk_flags;      // (side-stream layers run beside others: no shared flags)
     const double M = (double)Mrows, K = (double)g.T * g.Cin;
     const double esz_in = x.v.fmt == ACT_BF2 ? (x.v.plane ? 4.0 : 2.0) : 4.0, esz_out = y.v.fmt == ACT_BF2 ? (y.v.plane ? 4.0 : 2.0) : 4.0;
     ProfScope ps(cat, 2.0 * M * K * cout, esz_in * (double)n * hh * ww * cin + 4.0 * K * cout + esz_out * M * cout, st, scope.c_str(), -1.0,

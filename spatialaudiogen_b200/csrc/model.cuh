@@ -89,6 +89,7 @@ struct sag_handle {
   cudaStream_t side = nullptr;
   cudaStream_t side2 = nullptr;   // the 1x1 / stride-2 shortcut convolutions of the ResNet blocks, beside conv_1 / conv_2 of their block
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* sk_flags = nullptr;        // stream-K flags (Epilogue::sk_flags) of the contractions on the caller's stream
 };
 
 namespace sag {

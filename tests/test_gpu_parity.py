@@ -182,6 +182,27 @@ def test_conv2d_tcgen05(case, prec):
     assert _conv_case(_L(), *case, prec=prec) < UMMA_TOL[prec]
 
 
+# stream-K: shapes whose tiles fill the last wave of the persistent grid badly are dealt out by K chunk; the pieces of a tile meet
+# in the epilogue of the CTA that finishes it (bias / ReLU after the fix-up).  Ragged M, several N tiles, odd piece counts.
+STREAM_K_CASES = [
+    (32, 7, 14, 512, 3, 3, 512, 1, 1, 1, 0, 0),       # resnet conv5_x at the benchmarked batch: 100 tiles of 72 chunks on 148 CTAs
+    (16, 14, 28, 256, 3, 3, 256, 1, 1, 1, 1, 1),      # 98 tiles, bias + ReLU after the fix-up
+    (21, 13, 27, 128, 3, 3, 256, 1, 1, 1, 1, 0),      # last M tile partly filled
+    (29, 7, 13, 256, 3, 3, 384, 1, 1, 1, 0, 1),       # three N tiles
+]
+
+
+@pytest.mark.parametrize('prec', [3, 2])
+@pytest.mark.parametrize('case', STREAM_K_CASES)
+def test_conv2d_tcgen05_stream_k(case, prec, monkeypatch):
+    monkeypatch.setenv('SAG_UMMA_STREAMK', '1')          # off by default; read at every call
+    L = _L()
+    n, h, w, cin, kh, kw, cout = case[:7]
+    assert L.lib().sag_plan_stream_k(kh * kw * cin, cout, n * h * w) == 1
+    assert _conv_case(L, *case, prec=prec) < UMMA_TOL[prec]
+    assert _conv_case(L, *case, prec=prec, seed=1) < UMMA_TOL[prec]        # other data
+
+
 @pytest.mark.parametrize('prec', [3, 2])
 @pytest.mark.parametrize('case', DECONV_CASES)
 def test_deconv2d_tcgen05(case, prec):
@@ -652,6 +673,28 @@ def test_forward_is_bit_reproducible():
             m.forward_into(a, v, None, o)
             outs.append(o)
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_forward_stream_k_matches_the_tile_schedule_and_is_bit_reproducible(monkeypatch):
+    """Stream-K (opt-in) on conv4_x / conv5_x of the benchmarked batch: the pieces of a tile meet in the finishing CTA's epilogue
+    (batch-norm statistics + TMA-store path), the flags are left cleared, so repeated forwards agree bit for bit."""
+    from spatialaudiogen_b200 import SptAudioGen
+    enc = ['audio', 'video']
+    W = Wt.init_weights(enc, separation='unet_mask', seed=6, stress=True)
+    B = 32
+    a, v = cu(_audio(B, 60)), cu(_video(B, 61))
+    ref = torch.empty((B, 4800, 3), device='cuda')
+    SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(W).forward_into(a, v, None, ref)
+    monkeypatch.setenv('SAG_UMMA_STREAMK', '1')
+    assert _L().lib().sag_plan_stream_k(9 * 512, 512, B * 7 * 14) == 1
+    m = SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(W)      # planned and run under the same setting
+    outs = []
+    for _ in range(3):
+        o = torch.empty((B, 4800, 3), device='cuda')
+        m.forward_into(a, v, None, o)
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert _rel(outs[0], ref.double().cpu()) < 2e-5            # other summation order of the K chunks
 
 
 def test_stage_methods_match_oracle():
