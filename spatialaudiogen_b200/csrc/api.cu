@@ -122,6 +122,7 @@ int sag_set_option(sag_handle* h, const char* key, int value) {
   if (k == "keep_sep_channels") { h->keep_sep_channels = value ? 1 : 0; return SAG_OK; }
   if (k == "cta_pair") { h->cta_pair = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "tma_gather") { h->tma_gather = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
+  if (k == "int_frames") { h->int_frames = value ? 1 : 0; return SAG_OK; }
   if (k == "halo_conv") { h->halo_conv = value < 0 ? -1 : (value ? 1 : 0); return SAG_OK; }
   if (k == "profile") { h->prof.on = value != 0; if (!value) h->prof.clear(); return SAG_OK; }
   if (k == "overlap") { h->overlap = value ? 1 : 0; return SAG_OK; }

@@ -195,6 +195,7 @@ struct UmmaWeights {
   int run8 = 0;         // mapped output: every group of 8 columns is 8 consecutive floats of one output row
   int order = 0;        // column order of a sub-pixel transposed conv (decode_subpixel_column in conv_umma.cu)
   int64_t M_hint = 0;   // row count the tile width was chosen for
+  int a_single = 0;     // the activation this image multiplies has ONE exact bf16 plane (uint8 frames as 2k - 255): A x (B_hi + B_lo)
   // tiled tensor map of the packed image (rows of 128 bytes, boxes of BN/2 rows) for the CTA-pair kernel, which fetches its
   // weight blocks with .cta_group::2 tensor copies (a CUtensorMap, kept opaque here); wmap_ok == 0: not available
   alignas(64) unsigned char wmap[128] = {0};
@@ -207,8 +208,10 @@ int umma_tile_width(int K, int N, int64_t M);
 // the image will be used for (selects the tile width)
 int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
 // stride-2 conv weights HWIO re-expressed for the 2x2 space-to-depth image with 16-channel pixels (K = ceil(kh/2)*ceil(kw/2)*16)
-int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, UmmaWeights* out,
+int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, int int_frames, UmmaWeights* out,
                        cudaStream_t st);
+// conv1 on uint8 video frames as one exact bf16 plane of integers: true when the halo kernel takes the layer at this size
+bool umma_int_frames_supported(int n, int oh, int ow);
 // w_hwoi: device tf.nn.conv2d_transpose weights [kh,kw,Cout,Cin]; order 0: columns (py,px,co), 1: columns (py,co,px)
 int umma_pack_deconv(const float* w_hwoi, const float* bias, int kh, int kw, int cout, int cin, int sh, int sw, int order,
                      int64_t y_sh, int64_t y_sw, int64_t y_sc, int precision, int64_t M, UmmaWeights* out, cudaStream_t st);
@@ -273,7 +276,9 @@ int launch_mix(const float* x_sep, const float* loc, int batch, int tracks, int 
                cudaStream_t st);
 // A batch of input frames (n,h,w,3): prepared fp32, or the uint8 frame as decoded from the jpg (video: x/255 - 0.5,
 // myutils.py:88-89; flow: quantised (angle, -, magnitude) + per-frame (min, max) limits, feeder.py:147-161) prepared on the device
-enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2 };
+// FRAMES_U8_VIDEO_INT: uint8 video frames delivered as the integers 2k - 255 (exact in one bf16 plane; x/255 - 0.5 = (2k - 255)/510,
+// the 1/510 lives in the packed conv1 weights: umma_pack_conv_s2d `int_frames`) -- internal to resnet18_tower
+enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2, FRAMES_U8_VIDEO_INT = 3 };
 struct FrameSrc {
   const void* p = nullptr;
   int kind = FRAMES_F32;

@@ -39,8 +39,9 @@ constexpr int UM_BM = 128;                  // rows per tile (UMMA M, one TMEM l
 constexpr int UM_BK = 64;                   // K elements per stage = one 128-byte swizzle atom of bf16
 constexpr int UM_PRODUCER_WARPS = 8;         // warps 0-7
 constexpr int UM_EPI_WARP0 = 8;              // warps 8-11: epilogue (warp % 4 == TMEM lane quadrant); + warps 4-7 with the TMA producer
-constexpr int UM_MMA_WARP = 12;              // warp 12: TMEM allocation + MMA issue
+constexpr int UM_MMA_WARP = 12;              // warp 12: TMEM allocation + MMA issue (TMA producer: warp 1 -- twelve warps, so 168 registers each)
 constexpr int UM_THREADS = 13 * 32;
+__host__ __device__ constexpr int um_threads(int src) { return src == 3 ? 12 * 32 : UM_THREADS; }   // (3 = SRC_TMA: warp 0 produces, 1 issues the MMAs, 4-11 epilogue)
 constexpr int UM_MAX_N = 1024;               // widest GEMM with batch-norm statistics / per-CTA column sums
 constexpr int UM_STAGING_BYTES = UM_BM * (32 * 4 + 16);
 constexpr long long UM_ROW_INVALID = (long long)0x8000000000000000ull;   // row beyond M (mapped outputs may have negative bases)
@@ -413,7 +414,7 @@ struct SkRange {
 };
 
 template <int BN, int NSPLIT, int SRC, bool PAIR>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(um_threads(SRC), 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
@@ -463,8 +464,15 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   const bool stats = a.stat_sum != nullptr && a.partial == nullptr;
 
   // ---- one-time setup ----
-  if (stats) for (int i = tid; i < UM_MAX_N; i += UM_THREADS) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
-  if (warp == UM_MMA_WARP) {
+  if (a.trace && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[blockIdx.x * 16 + 13] = (long long)t;            // (trace: kernel entry of this CTA, ns)
+  }
+  constexpr int MMA_WARP = TMA_ANY ? 1 : UM_MMA_WARP;
+  constexpr int NTHREADS = um_threads(SRC);
+  if (stats) for (int i = tid; i < UM_MAX_N; i += NTHREADS) { s_sum[i] = 0.f; s_sqs[i] = 0.f; }
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         // every producer thread + the expect_tx arrival of the B copy; TMA gather: the expect_tx arrival alone
@@ -520,9 +528,9 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     }
   };
 
-  if (TMA_ANY && warp < 4) {
-    // ================================ producer (TMA im2col): warp 0, one elected lane (warps 1-3 idle) ================================
-    if (warp == 0) {
+  if (TMA_ANY && warp == 0) {
+    // ================================ producer (TMA im2col): warp 0, one elected lane (warps 2-3 idle) ================================
+    {
       int stage = 0;
       uint32_t phase = 0;
       long long tr_wait = 0, tr_t0 = clock64(), tr_chunks = 0;
@@ -712,7 +720,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
       a.trace[blockIdx.x * 16 + 3] = clock64() - tr_t0;
       a.trace[blockIdx.x * 16 + 6] = tr_chunks;
     }
-  } else if (warp == UM_MMA_WARP) {
+  } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ================================
     // The whole warp walks the loop (warp-uniform control flow keeps the shared-memory descriptors in uniform
     // registers); one elected lane issues the tcgen05 instructions.  In a CTA pair only the leader (rank 0) issues:
@@ -788,7 +796,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         a.trace[blockIdx.x * 16 + 7] = tr_wacc;
       }
     }
-  } else if (warp >= UM_EPI_WARP0 || (TMA_ANY && warp >= 4)) {
+  } else if ((!TMA_ANY && warp >= UM_EPI_WARP0 && warp < UM_MMA_WARP) || (TMA_ANY && warp >= 4)) {
     // ================================ epilogue ================================
     // EW warps: 4 (one per TMEM lane quadrant) next to the cp.async producers; 8 when the TMA unit gathers and warps 4-7
     // are free: two warps per quadrant, each draining half of the columns of a pass.  The pass is latency bound
@@ -808,6 +816,16 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
     int64_t it_local = 0;
     long long tr_wait = 0, tr_t0 = clock64();
     long long tr_p[5] = {0, 0, 0, 0, 0};
+    // 64-wide tiles with one N tile (conv1): a thread meets the same 2 x CPT columns in every tile, so the batch-norm sums stay in
+    // its registers over all tiles of the CTA and cross the warp once, after the last tile (the butterfly per pass was 20 % of
+    // conv1's epilogue, which paces that layer)
+    constexpr int DEFER_P = BN == 64 ? 2 : 1;
+    const bool defer_stats = BN == 64 && NT == 1 && stats && a.out_mode == 1 && a.partial == nullptr && !sk;
+    float racc[DEFER_P][CPT], rsq[DEFER_P][CPT];
+#pragma unroll
+    for (int p = 0; p < DEFER_P; ++p)
+#pragma unroll
+      for (int e = 0; e < CPT; ++e) { racc[p][e] = 0.f; rsq[p][e] = 0.f; }
     for (int64_t wj = 0; wj < n_items; ++wj, ++it_local) {
       WorkItem wi;
       item_at(wj, wi);
@@ -1129,7 +1147,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         }
       };
       if (wi.fix_first >= 0) fetch_pf(0);
-#pragma unroll 1
+#pragma unroll(BN == 64 ? 2 : 1)      // (64-wide: both passes unrolled, the deferred statistics stay in registers)
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[CPT];
         long long tp0 = a.trace ? clock64() : 0;
@@ -1192,8 +1210,19 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
           // ---- store through the TMA unit: no shared -> register -> global copy-out.  The staging tile is written in the layout
           // the store reads (mode 1: 128-byte rows, SWIZZLE_128B like the tensor map; mode 2: four [128 rows][8 floats] blocks),
           // one elected thread issues the store(s); batch-norm column sums come from the registers (warp butterfly).
-          const bool st_pass = stats && !split && !(a.dbg & 1);
+          bool st_pass = stats && !split && !(a.dbg & 1);
           const int par = (c0 >> 5) & 1;
+          if (BN == 64 && defer_stats) {
+            if (st_pass && row < rows_valid) {
+#pragma unroll
+              for (int p = 0; p < DEFER_P; ++p)
+                if (p == (c0 >> 5)) {
+#pragma unroll
+                  for (int e = 0; e < CPT; ++e) { racc[p][e] += v[e]; rsq[p][e] = fmaf(v[e], v[e], rsq[p][e]); }
+                }
+            }
+            st_pass = false;
+          }
           if (st_pass) {
             float sq[CPT];
 #pragma unroll
@@ -1266,9 +1295,27 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
         emit_pass(c0, split);
       }
     }
+    if (BN == 64 && defer_stats) {
+#pragma unroll
+      for (int p = 0; p < DEFER_P; ++p) {
+        const float cs = warp_column_sums<CPT>(racc[p], lane), cq = warp_column_sums<CPT>(rsq[p], lane);
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (CPT == 32) { s_part[0][q][lane] = cs; s_part[0][q][32 + lane] = cq; }
+        else if ((lane & 1) == 0) { s_part[0][q][half * 16 + (lane >> 1)] = cs; s_part[0][q][32 + half * 16 + (lane >> 1)] = cq; }
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (et < 32 && 32 * p + et < a.Ntot) {
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ts += s_part[0][k][et]; tq += s_part[0][k][32 + et]; }
+          s_sum[32 * p + et] += ts;
+          s_sqs[32 * p + et] += tq;
+        }
+      }
+    }
     if (a.out_mode != 0 && et == 0) bulk_wait0();      // every store of this CTA has been written out before the CTA exits
     if (a.trace && et == 0) {
       for (int i = 0; i < 5; ++i) a.trace[blockIdx.x * 16 + 8 + i] = tr_p[i];
+      { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.trace[blockIdx.x * 16 + 15] = (long long)t; }   // epilogue role done (ns)
       a.trace[blockIdx.x * 16 + 4] = tr_wait;
       a.trace[blockIdx.x * 16 + 5] = clock64() - tr_t0;
     }
@@ -1277,7 +1324,7 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   tc_fence_before();
   if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   else __syncthreads();
-  if (warp == UM_MMA_WARP) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
@@ -1285,10 +1332,15 @@ gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, 
   if (stats) {
     // per-CTA sums (folded above in a fixed order) -> global, as exact fixed-point integer atomics: order-independent, so the
     // statistics -- and everything downstream -- are bit-reproducible from run to run
-    for (int i = tid; i < a.Ntot; i += UM_THREADS) {
+    for (int i = tid; i < a.Ntot; i += NTHREADS) {
       fx_atomic_add(a.stat_sum + 2 * i, s_sum[i]);
       fx_atomic_add(a.stat_sqs + 2 * i, s_sqs[i]);
     }
+  }
+  if (a.trace && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.trace[blockIdx.x * 16 + 14] = (long long)t;            // (trace: kernel exit of this CTA, ns)
   }
 }
 
@@ -1313,6 +1365,10 @@ struct HaloArgs {
   int NDX, NDY, DX0, DY0;             // taps: dx in [DX0, DX0 + NDX) (one box each), dy in [DY0, DY0 + NDY) (blocks of a box)
   int Ntot, NT;                       // output channels, N tiles
   int SA, SB;                         // activation boxes / weight chunks in flight
+  // BRES: the packed weights of all taps stay in shared memory (SB = taps * CC slots, filled by the CTA's first tile, never
+  // released): layers with one N tile and few taps (conv1: 4 x 16 KB) stop re-streaming them per tile.  A1: the activation has one
+  // exact bf16 plane (uint8 frames as 2k - 255, resnet18_tower): no lo box, no A_lo x B_hi MMA.
+  int BRES, A1;
 };
 struct alignas(64) HaloMaps { CUtensorMap hi, lo, o, w; };     // w: tiled map of the packed weights (pairs)
 constexpr int HL_THREADS = 12 * 32;    // warp 0 producer, warp 1 MMA + TMEM, warps 4-11 epilogue (two per TMEM lane quadrant)
@@ -1361,7 +1417,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
   const uint32_t bar_tfull = bar_bempty + 8 * HL_MAX_SB, bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
   const uint32_t stile0 = (bars + 256 + 1023u) & ~1023u;      // two 16 KB staging tiles (swizzled TMA stores, alternating passes)
   const uint32_t a_plane = (uint32_t)(a.TH + a.NDY - 1) * (uint32_t)a.TW * 128u;   // one bf16 plane of one box
-  const uint32_t a_slot = 2 * a_plane;
+  const uint32_t a_slot = (a.A1 ? 1u : 2u) * a_plane;
   const uint32_t a_base = stile0 + 32768u;
   const uint32_t b_base = a_base + (uint32_t)a.SA * a_slot;
   const int SA = a.SA, SB = a.SB;
@@ -1413,6 +1469,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       int nimg, y0, x0, nt;
       bool real;
       decode(wk, nimg, y0, x0, nt, real);
+      const bool load_b = !a.BRES || wk == wk0;             // resident weights: the first tile fills the slots
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
         for (int dx = 0; dx < a.NDX; ++dx) {
@@ -1423,19 +1480,20 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
               const uint32_t bar = bar_afull + 8 * sa;
               mbar_arrive_expect_tx(bar, a_slot);
               tma_tile_4d(dst, &tm.hi, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
-              tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
+              if (!a.A1) tma_tile_4d(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
             } else {
               // the leader's producer makes the single arrival and expects the bytes of both CTAs (see the im2col kernel)
               const uint32_t bar = lead_afull + 8 * sa;
               if (crank == 0) mbar_arrive_expect_tx(bar_afull + 8 * sa, 2 * a_slot);
               tma_tile_4d_2sm(dst, &tm.hi, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
-              tma_tile_4d_2sm(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
+              if (!a.A1) tma_tile_4d_2sm(dst + a_plane, &tm.lo, c * 64, x0 + dx + a.DX0, y0 + a.DY0, nimg, bar);
             }
           }
           __syncwarp();
           if (++sa == SA) { sa = 0; pa ^= 1; }
 #pragma unroll 1
           for (int dy = 0; dy < a.NDY; ++dy) {
+            if (!load_b) continue;
             mbar_wait(bar_bempty + 8 * sb, pb ^ 1);
             if (elect_one()) {
               const int kc = (dy * a.NDX + dx) * a.CC + c;     // packed K order: tap-major (rows, then columns), then channel chunk
@@ -1473,6 +1531,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(b * 2 * BN);
       uint32_t first = 0;
+      const bool wait_b = !a.BRES || it_local == 0;         // resident weights: slot sb = tap, filled once
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
         for (int dx = 0; dx < a.NDX; ++dx) {
@@ -1480,7 +1539,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
           const uint32_t slot = a_base + (uint32_t)sa * a_slot;
 #pragma unroll 1
           for (int dy = 0; dy < a.NDY; ++dy) {
-            mbar_wait(bar_bfull + 8 * sb, pb);
+            if (wait_b) mbar_wait(bar_bfull + 8 * sb, pb);
             tc_fence_after();
             const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows dy * TW .. of the box: vertical tap dy - 1
             const uint32_t bb = b_base + (uint32_t)sb * B_BYTES;
@@ -1493,19 +1552,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
               for (int k4 = 0; k4 < 4; ++k4) {
                 if (PAIR) {
                   umma_bf16_2(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));
-                  umma_bf16_2(tmem_acc, da_lo + 2 * k4, dby + 2 * k4, IDESC, 1u);
+                  if (!a.A1) umma_bf16_2(tmem_acc, da_lo + 2 * k4, dby + 2 * k4, IDESC, 1u);
                 } else {
                   umma_bf16(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));   // [A_hi.B_hi | A_hi.B_lo]
-                  umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                             // += A_lo.B_hi
+                  if (!a.A1) umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);                 // += A_lo.B_hi
                 }
               }
               const bool last = dy + 1 == a.NDY && dx + 1 == a.NDX && c + 1 == a.CC;
               if (PAIR) {
-                umma_commit2(bar_bempty + 8 * sb);
+                if (!a.BRES) umma_commit2(bar_bempty + 8 * sb);
                 if (dy + 1 == a.NDY) umma_commit2(bar_aempty + 8 * sa);
                 if (last) umma_commit2(bar_tfull + 8 * b);
               } else {
-                umma_commit(bar_bempty + 8 * sb);
+                if (!a.BRES) umma_commit(bar_bempty + 8 * sb);
                 if (dy + 1 == a.NDY) umma_commit(bar_aempty + 8 * sa);
                 if (last) umma_commit(bar_tfull + 8 * b);
               }
@@ -1526,6 +1585,15 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
     const int rr = row / a.TW, rc = row - rr * a.TW;      // position of this row's pixel inside the tile
     int it_local = 0;
     uint32_t pass_no = 0;                                 // passes of this CTA so far: alternates the staging tile
+    // 64-wide tiles, one N tile (conv2_x): the batch-norm sums of a thread's 2 x 16 columns stay in registers over all tiles of
+    // the CTA and cross the warp once, after the last tile
+    constexpr int DEFER_P = BN == 64 ? 2 : 1;
+    const bool defer_stats = BN == 64 && a.NT == 1;
+    float racc[DEFER_P][16], rsq[DEFER_P][16];
+#pragma unroll
+    for (int p = 0; p < DEFER_P; ++p)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { racc[p][e] = 0.f; rsq[p][e] = 0.f; }
     for (int wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       int nimg, y0, x0, nt;
       bool real;
@@ -1537,14 +1605,15 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       mbar_wait(bar_tfull + 8 * b, use & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * 2 * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll(BN == 64 ? 2 : 1)      // (64-wide: both passes unrolled, the deferred statistics stay in registers)
       for (int c0 = 0; c0 < BN; c0 += 32, ++pass_no) {
         const int cc = c0 + half * 16;
         const int par = (int)(pass_no & 1u);
         const uint32_t stile = stile0 + (uint32_t)par * 16384u;
         float v[16], u[16];
-        tmem_ld16(tmem_row + (uint32_t)cc, v);
-        tmem_ld16(tmem_row + (uint32_t)(BN + cc), u);
+        tmem_ld16_nowait(tmem_row + (uint32_t)cc, v);                // both accumulator blocks in flight, one wait
+        tmem_ld16_nowait(tmem_row + (uint32_t)(BN + cc), u);
+        tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] += u[e];
         if (c0 + 32 >= BN) {
@@ -1552,17 +1621,25 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
           __syncwarp();
           if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(bar_tempty + 8 * b, 0); else mbar_arrive(bar_tempty + 8 * b); }
         }
-        {
+        if (BN == 64 && defer_stats) {
+          if (valid) {
+#pragma unroll
+            for (int p = 0; p < DEFER_P; ++p)
+              if (p == (c0 >> 5)) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { racc[p][e] += v[e]; rsq[p][e] = fmaf(v[e], v[e], rsq[p][e]); }
+              }
+          }
+        } else {
           float sv[16], sq[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) { sv[e] = valid ? v[e] : 0.f; sq[e] = sv[e] * sv[e]; }
           const float cs = warp_column_sums<16>(sv, lane), cq = warp_column_sums<16>(sq, lane);
           if ((lane & 1) == 0) { s_part[par][q][half * 16 + (lane >> 1)] = cs; s_part[par][q][32 + half * 16 + (lane >> 1)] = cq; }
         }
-        // this staging tile was last read by the store issued two passes ago: with the other tile's store still allowed in
-        // flight, the wait is (almost) never a stall -- the store latency no longer sits between two passes
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // ONE barrier per pass, two staging tiles: the store that last read THIS tile (two passes ago) was waited for by the
+        // issuing thread before it arrived at the previous pass's barrier (wait_group.read 0 below: at that point the youngest
+        // store is a whole pass old, so the wait is rarely a stall and the store latency does not sit between two passes)
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
           const uint32_t chunk = (uint32_t)(half * 16 + e) >> 2;
@@ -1570,17 +1647,34 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
                        make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
         }
         fence_proxy_async();
+        if (et == 0) bulk_wait_read0();                    // the previous pass's store has read the OTHER tile: the next pass may write it
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           if (real) tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
           bulk_commit();                                   // (one group per pass, also an empty one: wait_group counts groups)
         }
-        if (et < 32 && n_base + c0 + et < a.Ntot) {
+        if (!(BN == 64 && defer_stats) && et < 32 && n_base + c0 + et < a.Ntot) {
           float ts = 0.f, tq = 0.f;
 #pragma unroll
           for (int p = 0; p < 4; ++p) { ts += s_part[par][p][et]; tq += s_part[par][p][32 + et]; }
           s_sum[n_base + c0 + et] += ts;
           s_sqs[n_base + c0 + et] += tq;
+        }
+      }
+    }
+    if (BN == 64 && defer_stats) {
+#pragma unroll
+      for (int p = 0; p < DEFER_P; ++p) {
+        const float cs = warp_column_sums<16>(racc[p], lane), cq = warp_column_sums<16>(rsq[p], lane);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if ((lane & 1) == 0) { s_part[0][q][half * 16 + (lane >> 1)] = cs; s_part[0][q][32 + half * 16 + (lane >> 1)] = cq; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < 32 && 32 * p + et < a.Ntot) {
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ts += s_part[0][k][et]; tq += s_part[0][k][32 + et]; }
+          s_sum[32 * p + et] += ts;
+          s_sqs[32 * p + et] += tq;
         }
       }
     }
@@ -1676,7 +1770,7 @@ __global__ void subpixel_weights_kernel(const float* __restrict__ w, int kh, int
 // HWIO weights of a stride-2 convolution over C channels -> weights of the equivalent stride-1 convolution over the 2x2
 // space-to-depth image with 16 channels per pixel (channel (py*2+px)*C + c, zero beyond 4*C):
 //   out[(a*tw + b)*16 + ch][co] = w[2a+py][2b+px][c][co]   (zero when the kernel index falls outside kh x kw)
-__global__ void s2d_weights_kernel(const float* __restrict__ w, int kh, int kw, int cin, int cout, int th, int tw,
+__global__ void s2d_weights_kernel(const float* __restrict__ w, int kh, int kw, int cin, int cout, int th, int tw, float div,
                                    float* __restrict__ out) {
   const int64_t total = (int64_t)th * tw * 16 * cout;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1690,7 +1784,7 @@ __global__ void s2d_weights_kernel(const float* __restrict__ w, int kh, int kw, 
     if (ch < 4 * cin) {
       const int sub = ch / cin, c = ch - sub * cin;
       const int ky = 2 * a + (sub >> 1), kx = 2 * b + (sub & 1);
-      if (ky < kh && kx < kw) v = __ldg(w + (((int64_t)ky * kw + kx) * cin + c) * cout + co);
+      if (ky < kh && kx < kw) v = __ldg(w + (((int64_t)ky * kw + kx) * cin + c) * cout + co) / div;
     }
     out[idx] = v;
   }
@@ -1894,7 +1988,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CL));
-  cfg.blockDim = dim3(UM_THREADS);
+  cfg.blockDim = dim3(um_threads(SRC));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr;
@@ -1948,6 +2042,16 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
     fprintf(stderr, "[umma trace]   MMA thread   : total %9.0f clk, waiting for operands %9.0f, for a free accumulator %9.0f\n", d[1], d[0], d[7]);
     fprintf(stderr, "[umma trace]   producer t0  : total %9.0f clk, waiting for a free stage %9.0f\n", d[3], d[2]);
     fprintf(stderr, "[umma trace]   epilogue t0  : total %9.0f clk, waiting for an accumulator %9.0f\n", d[5], d[4]);
+    {
+      long long e0 = LLONG_MAX, e1 = 0, x0 = LLONG_MAX, x1 = 0, r0 = LLONG_MAX, r1 = 0;
+      for (size_t c = 0; c < n / 16; ++c) {
+        e0 = std::min(e0, tr[c * 16 + 13]); e1 = std::max(e1, tr[c * 16 + 13]);
+        x0 = std::min(x0, tr[c * 16 + 14]); x1 = std::max(x1, tr[c * 16 + 14]);
+        r0 = std::min(r0, tr[c * 16 + 15]); r1 = std::max(r1, tr[c * 16 + 15]);
+      }
+      fprintf(stderr, "[umma trace]   wall (us from the first CTA's entry): last entry %.1f, epilogue roles done %.1f .. %.1f, CTA exits %.1f .. %.1f\n",
+              (e1 - e0) * 1e-3, (r0 - e0) * 1e-3, (r1 - e0) * 1e-3, (x0 - e0) * 1e-3, (x1 - e0) * 1e-3);
+    }
     fprintf(stderr, "[umma trace]   epilogue t0  : tmem->smem %9.0f, copy-out %9.0f, statistics %9.0f, barriers %9.0f (sum over %0.f passes)\n",
             d[8], d[9], d[10], d[11], d[12]);
     SAG_LAUNCH_CHECK();
@@ -2174,7 +2278,7 @@ int umma_pack_weights(const float* wk, int K, int N, int64_t ldw, int precision,
   return SAG_OK;
 }
 
-int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, UmmaWeights* out,
+int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, int precision, int64_t M, int int_frames, UmmaWeights* out,
                        cudaStream_t st) {
   SAG_REQUIRE(4 * cin <= 16, SAG_EUNSUPPORTED, "space-to-depth route: %d input channels do not fit 16-channel pixels", cin);
   const int th = (kh + 1) / 2, tw = (kw + 1) / 2;
@@ -2183,8 +2287,10 @@ int umma_pack_conv_s2d(const float* w_hwio, int kh, int kw, int cin, int cout, i
   SAG_CHECK_CUDA(cudaMalloc(&wk, sizeof(float) * (size_t)total));
   int64_t blocks = cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  s2d_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, th, tw, wk);
+  // int_frames: the frames arrive as 2k - 255 = 510 * (k/255 - 0.5): the weights carry the 1/510 (one correctly rounded division)
+  s2d_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_hwio, kh, kw, cin, cout, th, tw, int_frames ? 510.f : 1.f, wk);
   int r = umma_pack_weights(wk, th * tw * 16, cout, cout, precision, M, out, st);
+  if (r == SAG_OK && int_frames) out->a_single = 1;
   cudaStreamSynchronize(st);
   cudaFree(wk);
   return r;
@@ -2402,11 +2508,22 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   constexpr int CL = PAIR ? 2 : 1;
   const size_t fixed = 256 + 1024 + 32768;
   HaloArgs args = a;
-  args.SA = 3;
-  long sb = ((long)budget[dev & 63] - (long)fixed - 3 * (long)a_slot) / B_BYTES;
-  if (sb < 2) { args.SA = 2; sb = ((long)budget[dev & 63] - (long)fixed - 2 * (long)a_slot) / B_BYTES; }
-  SAG_REQUIRE(sb >= 2, SAG_EUNSUPPORTED, "halo conv: the tile does not fit the shared memory");
-  args.SB = sb > HL_MAX_SB ? HL_MAX_SB : (int)sb;
+  const int taps = a.NDX * a.NDY * a.CC;
+  // weights resident when every tap fits beside two activation boxes (one N tile: the same chunks serve every tile of the CTA)
+  static const int bres_env = env_int("SAG_UMMA_HALO_BRES", 1);
+  args.BRES = (bres_env && a.NT == 1 && taps <= HL_MAX_SB &&
+               (long)fixed + 2 * (long)a_slot + (long)taps * B_BYTES <= (long)budget[dev & 63]) ? 1 : 0;
+  if (args.BRES) {
+    args.SB = taps;
+    long sa = ((long)budget[dev & 63] - (long)fixed - (long)taps * B_BYTES) / (long)a_slot;
+    args.SA = sa > HL_MAX_SA ? HL_MAX_SA : (int)sa;
+  } else {
+    args.SA = 3;
+    long sb = ((long)budget[dev & 63] - (long)fixed - 3 * (long)a_slot) / B_BYTES;
+    if (sb < 2) { args.SA = 2; sb = ((long)budget[dev & 63] - (long)fixed - 2 * (long)a_slot) / B_BYTES; }
+    SAG_REQUIRE(sb >= 2, SAG_EUNSUPPORTED, "halo conv: the tile does not fit the shared memory");
+    args.SB = sb > HL_MAX_SB ? HL_MAX_SB : (int)sb;
+  }
   const size_t smem = fixed + (size_t)args.SA * a_slot + (size_t)args.SB * B_BYTES;
   const int tiles = a.NIMG * a.TY * a.TX;
   const int n_work = cdiv(tiles, CL) * a.NT;
@@ -2454,8 +2571,10 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   if (ndy < 2 || ndx > 3 || ndy > 4) return SAG_OK;
   // conv1 (one tap column, four rows): its time is set by the 205 MB of raw fp32 output, not by operand bytes -- measured 125.6 us
   // on the im2col kernel, 127-136 us here -- so it takes this kernel only when forced (tests)
-  if (ndx == 1 && halo_want <= 0) return SAG_OK;
-  if (x.fmt != ACT_BF2 || x.plane == 0 || (reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return SAG_OK;
+  static const int conv1_env = env_int("SAG_UMMA_HALO_CONV1", 1);
+  if (ndx == 1 && halo_want <= 0 && !(halo_want < 0 && conv1_env)) return SAG_OK;
+  const bool a1 = w.a_single != 0;                   // one exact activation plane (integer frames)
+  if (x.fmt != ACT_BF2 || (x.plane == 0) != a1 || (reinterpret_cast<uintptr_t>(x.p) & 15) != 0 || (x.plane & 15) != 0) return SAG_OK;
   if (w.planes != 2 || (w.BN != 64 && w.BN != 128) || w.N > 512 || w.col_off != nullptr || w.K != g.T * g.Cin) return SAG_OK;
   if (ep.bias != nullptr || ep.relu || y.fmt != ACT_F32 || g.y_sc != 1 || g.y_sw % 4 != 0 || g.oy0 != 0 || g.ox0 != 0 || g.osy != 1 || g.osx != 1 ||
       g.y_sh != (int64_t)g.PW * g.y_sw || g.y_sn != (int64_t)g.PH * g.y_sh || (reinterpret_cast<uintptr_t>(y.p) & 15) != 0)
@@ -2485,7 +2604,7 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
     const cuuint64_t strides[3] = {(cuuint64_t)g.x_ld * 2, x_row * 2, (cuuint64_t)g.H * x_row * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + ndy - 1), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int pl = 0; pl < 2; ++pl) {
+    for (int pl = 0; pl < (a1 ? 1 : 2); ++pl) {
       void* base = reinterpret_cast<char*>(x.p) + (pl == 0 ? 0 : x.plane);
       if (encode(pl == 0 ? &tm.hi : &tm.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -2508,12 +2627,14 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   a.NIMG = g.N; a.H = OH; a.W = OW; a.TW = TW; a.TH = TH; a.TX = cdiv(OW, TW); a.TY = cdiv(OH, TH);
   a.CC = g.Cin / 64; a.Ntot = w.N; a.NT = w.NT;
   a.NDX = ndx; a.NDY = ndy; a.DX0 = dx0; a.DY0 = dy0;
-  const size_t a_slot = 2 * (size_t)(TH + ndy - 1) * TW * 128;
+  a.A1 = a1 ? 1 : 0;
+  const size_t a_slot = (a1 ? 1 : 2) * (size_t)(TH + ndy - 1) * TW * 128;
   if (34048 + 2 * a_slot + 2 * (size_t)(2 * w.BN * 128) > 220 * 1024) return SAG_OK;      // two boxes + two weight chunks must fit
   // CTA pairs (two neighbouring tiles per cluster, half the weight bytes and half the MMA instructions per tile): default on
   static const int pair_env = env_int("SAG_UMMA_PAIR", -1);
   const int want = g_umma_pair >= 0 ? g_umma_pair : pair_env;
-  const bool pair = (want < 0 || want != 0) && w.wmap_ok && g.N * a.TY * a.TX >= 2;
+  static const int conv1_pair_env = env_int("SAG_UMMA_HALO_CONV1_PAIR", 0);     // measured: 90.3 us alone, 107.2 us on pairs (resident weights: nothing left to share)
+  const bool pair = (want < 0 || want != 0) && w.wmap_ok && g.N * a.TY * a.TX >= 2 && !(ndx == 1 && want < 0 && !conv1_pair_env);
   if (pair) {
     memcpy(&tm.w, w.wmap, sizeof(tm.w));
     SAG_TRY(w.BN == 64 ? (launch_halo<64, true>(a, tm, a_slot, st)) : (launch_halo<128, true>(a, tm, a_slot, st)));
@@ -2522,6 +2643,17 @@ static int try_halo_conv(const ActView& x, const UmmaWeights& w, const ActView& 
   }
   *done = true;
   return SAG_OK;
+}
+
+bool umma_int_frames_supported(int n, int oh, int ow) {
+  static const int on = env_int("SAG_UMMA_INT_FRAMES", 1);
+  static const int halo_env = env_int("SAG_UMMA_HALO", -1);
+  static const int conv1_env = env_int("SAG_UMMA_HALO_CONV1", 1);
+  const int halo_want = g_umma_halo >= 0 ? g_umma_halo : halo_env;
+  if (!on || halo_want == 0 || (halo_want < 0 && !conv1_env) || encode_tiled_fn() == nullptr || n < 1) return false;
+  for (int tw = 8; tw <= 64; tw *= 2)                 // a tile shape without padded tiles (try_halo_conv's default rule)
+    if (ow % tw == 0 && oh % (UM_BM / tw) == 0 && 34048 + 2 * (size_t)(UM_BM / tw + 3) * tw * 128 + 4 * 16384 <= 220 * 1024) return true;
+  return false;
 }
 
 int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActView& y, const GatherGeom& g, const Epilogue& ep,
@@ -2559,7 +2691,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   if (x.fmt == ACT_BF2) {
     SAG_REQUIRE(vec, SAG_EUNSUPPORTED, "tcgen05 path: split-bf16 activations need 16-byte aligned 8-channel groups (Cin %d, ld %lld)",
                 g.Cin, (long long)g.x_ld);
-    SAG_REQUIRE(w.planes == 1 || x.plane != 0, SAG_EINVAL, "tcgen05 path: bf16x3 needs the lo plane of the activation");
+    SAG_REQUIRE(w.planes == 1 || x.plane != 0 || w.a_single, SAG_EINVAL, "tcgen05 path: bf16x3 needs the lo plane of the activation");
     src = SRC_BF2;
   }
   TmaPair tm;
@@ -2577,6 +2709,7 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
     SAG_TRY(try_halo_conv(x, w, y, g, ep, Z, st, &done));
     if (done) return SAG_OK;
   }
+  SAG_REQUIRE(!w.a_single, SAG_EUNSUPPORTED, "tcgen05 path: single-plane integer frames run on the halo kernel only (umma_int_frames_supported)");
   static const int epi_dbg = env_int("SAG_UMMA_EPI_DEBUG", 0);
   a.dbg = epi_dbg;
   if (Z > 1) a.partial = scratch;

@@ -432,7 +432,12 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
     // that overlap (pixel stride 16 channels): 4 taps (kernel rows) x 64 channels, K = 256, one 64-wide chunk per row
     int pt = same_pad_before(H, 7, 2, &oh), pl = same_pad_before(Wd, 7, 2, &ow);
     const int H2 = oh + 3, W2 = ow + 3;                     // rows / columns of the space-to-depth image a 4x4 window needs
+    // uint8 video frames: the pixels travel as the integers 2k - 255 in ONE exact bf16 plane (the 1/510 sits in the packed
+    // weights), so conv1 reads half the activation bytes and issues one MMA per K step instead of two
+    const bool int_ok = f.split_planes() && h->int_frames != 0 && umma_int_frames_supported(B, oh, ow);
+    const bool int_frames = xsrc.kind == FRAMES_U8_VIDEO && int_ok;
     Act xp = f.alloc_act((int64_t)B * H2 * W2, 16);
+    if (int_frames) xp.v.plane = 0;
     GatherGeom g;
     memset(&g, 0, sizeof(g));
     g.N = B; g.H = H2; g.W = ow; g.Cin = 64; g.x_ld = 16; g.x_row = (int64_t)W2 * 16;
@@ -446,12 +451,20 @@ int resnet18_tower(sag_handle* h, const std::string& scope, const FrameSrc& xsrc
       const float* w = f.W(p + "conv1/conv/weights", &err);
       SAG_TRY(err);
       const UmmaWeights* img = nullptr;
-      SAG_TRY(f.image(p + "conv1/conv", g.T * g.Cin, 64, Mrows, [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.layer_prec(p + "conv1/conv"), Mrows, uw, st); }, &img));
+      if (ar.prepare && int_ok && !int_frames) {       // the plan does not know the frame format of later calls: build both images
+        const UmmaWeights* other = nullptr;
+        SAG_TRY(f.image(p + "conv1/conv#int", g.T * g.Cin, 64, Mrows,
+                        [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.layer_prec(p + "conv1/conv"), Mrows, 1, uw, st); }, &other));
+      }
+      SAG_TRY(f.image(p + (int_frames ? "conv1/conv#int" : "conv1/conv"), g.T * g.Cin, 64, Mrows,
+                      [&](UmmaWeights* uw) { return umma_pack_conv_s2d(w, 7, 7, 3, 64, f.layer_prec(p + "conv1/conv"), Mrows, int_frames ? 1 : 0, uw, st); }, &img));
       if (!ar.dry) {
         {
           const double in_b = xsrc.kind == FRAMES_F32 ? 4.0 : 1.0;
           ProfScope ps(PROF_POINTWISE, 0, in_b * B * (double)H * Wd * 3 + act_b * B * (double)H2 * W2 * 16, st, "frame ingest (space-to-depth)");
-          SAG_TRY(launch_space_to_depth16(xsrc, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
+          FrameSrc xs = xsrc;
+          if (int_frames) xs.kind = FRAMES_U8_VIDEO_INT;
+          SAG_TRY(launch_space_to_depth16(xs, B, H, Wd, 3, pt, pl, H2, W2, xp.v, st));
         }
         Epilogue ep{nullptr, 0, b1.sum, b1.sqs};
         ProfScope ps(PROF_CONV, 2.0 * B * oh * ow * 147.0 * 64, act_b * B * (double)H2 * W2 * 16 + 4.0 * B * (double)oh * ow * 64, st,

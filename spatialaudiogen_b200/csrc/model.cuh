@@ -77,6 +77,7 @@ struct sag_handle {
   sag::Profiler prof;    // per-launch event timing of the last forward (option "profile")
   int keep_sep_channels = 0;   // 1: inverse STFT and mixing as two kernels so that `separation/all_channels` (x_sep) exists
   int cta_pair = -1;     // tcgen05 path on CTA pairs (cta_group::2): -1 default (off), 0 / 1 forced
+  int int_frames = 1;    // uint8 video frames reach conv1 as one exact bf16 plane of integers (0: as x/255 - 0.5 split in two planes, bit-identical to float frames)
   int halo_conv = -1;    // 3x3 / stride-1 convs on the halo-resident kernel: -1 default (on where eligible), 0 / 1 forced
   int tma_gather = -1;   // activation gather of the tcgen05 path: -1 default (TMA im2col where it applies), 0 cp.async, 1 TMA
   int skip_unused = 1;   // skip mask rows / frames that cannot reach the cropped output (bit-identical result)

@@ -388,6 +388,9 @@ __device__ __forceinline__ void load_frame_pixel(const void* __restrict__ x, int
     if (KIND == FRAMES_U8_VIDEO) {
 #pragma unroll
       for (int ch = 0; ch < C; ++ch) v[ch] = lut[u[ch]];
+    } else if (KIND == FRAMES_U8_VIDEO_INT) {
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch) v[ch] = (float)(2 * (int)u[ch] - 255);      // odd integers up to 255: exact in bf16
     } else {
       float m = (float)((double)(float)u[C - 1] * lim_scale);       // chunk[..., 2] *= (m_max - m_min) / 255.
       m = (float)((double)m + lim_min);                              // chunk[..., 2] += m_min
@@ -442,6 +445,7 @@ template <int C>
 static void launch_s2d_kind(int kind, unsigned blocks, cudaStream_t st, const void* x, const double* lims, int n, int h, int w, int pt, int pl,
                             int h2, int w2, const ActView& out) {
   if (kind == FRAMES_U8_VIDEO) launch_pdl(space_to_depth16_kernel<C, FRAMES_U8_VIDEO>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
+  else if (kind == FRAMES_U8_VIDEO_INT) launch_pdl(space_to_depth16_kernel<C, FRAMES_U8_VIDEO_INT>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
   else if (kind == FRAMES_U8_FLOW) launch_pdl(space_to_depth16_kernel<C, FRAMES_U8_FLOW>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
   else launch_pdl(space_to_depth16_kernel<C, FRAMES_F32>, dim3(blocks), dim3(256), 0, st, x, lims, n, h, w, pt, pl, h2, w2, out);
 }

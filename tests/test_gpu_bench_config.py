@@ -83,6 +83,28 @@ def test_config2_audio_video_b32(precision, tol):
         assert e < 1e-3, (k, e)
 
 
+def test_config2_uint8_frames_b32_integer_conv1():
+    """The benchmarked input format: uint8 frames.  conv1 runs on the halo kernel with resident weights and ONE exact activation
+    plane (2k - 255, the 1/510 in the packed weights): its raw output and the waveform against the fp64 oracle on x/255 - 0.5."""
+    B = 32
+    ref, m = _pair(['audio', 'video'], 1234, 'bf16x3', stress=False)
+    rng = np.random.RandomState(9)
+    a = _audio(B, 101)
+    vu = rng.randint(0, 256, size=(B, 1, 224, 448, 3)).astype(np.uint8)
+    yr = ref.inference_ops(a, video=vu / 255. - 0.5)
+    errs = {}
+    for opt in (1, 0):
+        m.set_option('int_frames', opt)
+        y = m.inference_ops(cu(a), video=cu(vu))
+        pool_ref = O.tf_max_pool_same_3x3s2(ref.ends['video_encoder/conv'])       # conv1 + BN + ReLU + max-pool (resnet.py:133-135)
+        errs[opt] = (_rel(y, yr), _rel(m.ends['video_encoder/pool1'], pool_ref),
+                     _rel(m.ends['video_encoder/conv5_2'], ref.ends['video_encoder/conv5_2']))
+    print('uint8 frames B=32: integer plane (waveform, pool1, conv5_2) = %s; split float planes = %s' %
+          (' '.join('%.2e' % e for e in errs[1]), ' '.join('%.2e' % e for e in errs[0])))
+    for opt in (1, 0):
+        assert errs[opt][0] < 1e-3 and errs[opt][1] < 5e-5 and errs[opt][2] < 1e-3, errs
+
+
 def test_config2_stress_weights_b32_bf16x3():
     """Same batch, every term of the forward exercised (random biases / BN affine, 100x fc3)."""
     B = 32
@@ -137,6 +159,11 @@ def test_uint8_frames_are_bit_identical_to_prepared_float_frames():
     y_f = torch.empty((B, 4800, 3), device='cuda')
     y_u = torch.empty((B, 4800, 3), device='cuda')
     m.forward_into(a, cu(vf), cu(ff), y_f)
+    # default: the uint8 pixels reach conv1 as the integers 2k - 255 in ONE exact bf16 plane, 1/510 folded into the weights --
+    # closer to the real product than the split float frame, hence not bit-identical to it
+    m.forward_into(a, cu(vu), cu(ff), y_u)
+    assert _rel(y_u, y_f) < 1e-4
+    m.set_option('int_frames', 0)                                # the same arithmetic as the float entry: x/255 - 0.5 split in two planes
     m.forward_into(a, cu(vu), cu(ff), y_u)                       # uint8 video, prepared float flow
     assert torch.equal(y_f, y_u)
     m.forward_into(a, cu(vu), cu(fu), y_u, cu(lims))             # both uint8

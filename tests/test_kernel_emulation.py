@@ -38,7 +38,7 @@ struct ActView { void* p = nullptr; int fmt = ACT_F32; int64_t plane = 0; };
 struct BnStats { const double* sum = nullptr; const double* sqs = nullptr; const float* gamma = nullptr; const float* beta = nullptr;
                  double inv_count = 0.0; float eps = 1e-3f; };
 static float s_ss[16384];
-enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2 };
+enum { FRAMES_F32 = 0, FRAMES_U8_VIDEO = 1, FRAMES_U8_FLOW = 2, FRAMES_U8_VIDEO_INT = 3 };
 static void emu_fill_lut(float* lut);
 // the block prologue (bn_scale_shift_to_smem) needs a barrier: here every emulated thread fills the whole table itself
 static void emu_scale_shift(const BnStats& bn, int c, float* s_scale, float* s_shift) {
@@ -87,6 +87,7 @@ extern "C" void emu_s2d(const void* x, const double* lims, int kind, int n, int 
                         int y_fmt, int64_t y_plane, int grid, int block) {
   for_each_thread(grid, block, [&] {
     if (kind == FRAMES_U8_VIDEO) space_to_depth16_kernel<3, FRAMES_U8_VIDEO>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
+    else if (kind == FRAMES_U8_VIDEO_INT) space_to_depth16_kernel<3, FRAMES_U8_VIDEO_INT>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
     else if (kind == FRAMES_U8_FLOW) space_to_depth16_kernel<3, FRAMES_U8_FLOW>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
     else if (c == 1) space_to_depth16_kernel<1, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
     else if (c == 2) space_to_depth16_kernel<2, FRAMES_F32>(x, lims, n, h, w, pt, pl, h2, w2, view(y, y_fmt, y_plane));
@@ -247,7 +248,7 @@ def test_space_to_depth16_thread_code(emu, n, h, w, c, pt, pl, grid, block, y_fm
         assert np.allclose((hi + lo).reshape(want.shape), want, rtol=2e-5, atol=0) and np.array_equal((hi + lo).reshape(want.shape) == 0, want == 0)
 
 
-@pytest.mark.parametrize('kind', [1, 2])
+@pytest.mark.parametrize('kind', [1, 2, 3])
 def test_uint8_frame_ingest_thread_code(emu, kind):
     """The uint8 frame sources of the ingest kernel against the reference's host preparation written out in numpy:
     video = img_prep_fcn (myutils.py:88-89: x/255. - 0.5 in float64, rounded to float32 when fed) -- bit-exact;
@@ -260,6 +261,8 @@ def test_uint8_frame_ingest_thread_code(emu, kind):
     lims = np.stack([rng.uniform(0, 2, n), rng.uniform(5, 30, n)], 1).astype(np.float64)
     if kind == 1:
         x = (u / 255. - 0.5).astype(np.float32)
+    elif kind == 3:
+        x = 2. * u.astype(np.float32) - 255.                 # the integer form: 510 * (u/255 - 0.5), exact in bf16
     else:
         chunk = u.astype(np.float32)
         m_min, m_max = lims[:, 0].reshape((-1, 1, 1)), lims[:, 1].reshape((-1, 1, 1))
@@ -277,8 +280,11 @@ def test_uint8_frame_ingest_thread_code(emu, kind):
         want[..., sub * c:(sub + 1) * c] = big[:, (sub >> 1):(sub >> 1) + 2 * h2:2, (sub & 1):(sub & 1) + 2 * w2:2][:, :h2, :w2]
     y = np.full(n * h2 * w2 * 16, np.nan, np.float32)
     emu.emu_s2d(_p(u), _p(lims), kind, n, h, w, c, pt, pl, h2, w2, _p(y), 0, C.c_int64(0), 3, 16)
-    if kind == 1:
+    if kind in (1, 3):
         assert np.array_equal(y.reshape(want.shape), want)
+        if kind == 3:
+            import torch
+            assert torch.equal(torch.from_numpy(want).bfloat16().float(), torch.from_numpy(want))     # one bf16 plane holds it exactly
     else:
         assert np.allclose(y.reshape(want.shape), want, rtol=2e-6, atol=2e-6)
         assert np.array_equal(y.reshape(want.shape)[..., 2::3][..., :4], want[..., 2::3][..., :4])      # magnitudes: exact
