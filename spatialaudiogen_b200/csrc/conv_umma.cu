@@ -1369,6 +1369,7 @@ struct HaloArgs {
   // released): layers with one N tile and few taps (conv1: 4 x 16 KB) stop re-streaming them per tile.  A1: the activation has one
   // exact bf16 plane (uint8 frames as 2k - 255, resnet18_tower): no lo box, no A_lo x B_hi MMA.
   int BRES, A1;
+  long long* trace;                   // SAG_HALO_TRACE (debug): per-CTA cycle counters of the three roles
 };
 struct alignas(64) HaloMaps { CUtensorMap hi, lo, o, w; };     // w: tiled map of the packed weights (pairs)
 constexpr int HL_THREADS = 12 * 32;    // warp 0 producer, warp 1 MMA + TMEM, warps 4-11 epilogue (two per TMEM lane quadrant)
@@ -1465,6 +1466,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
     uint32_t pa = 0, pb = 0;
     const uint32_t lead_bars = PAIR ? map_to_cta(bars, 0) : bars;             // the leader's barriers (cluster address)
     const uint32_t lead_afull = lead_bars + (bar_afull - bars), lead_bfull = lead_bars + (bar_bfull - bars);
+    long long tr_wait = 0;
+    const long long tr_t0 = clock64();
     for (int wk = wk0; wk < n_work; wk += wk_step) {
       int nimg, y0, x0, nt;
       bool real;
@@ -1473,7 +1476,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
         for (int dx = 0; dx < a.NDX; ++dx) {
+          const long long tw0 = a.trace ? clock64() : 0;
           mbar_wait(bar_aempty + 8 * sa, pa ^ 1);
+          if (a.trace) tr_wait += clock64() - tw0;
           if (elect_one()) {
             const uint32_t dst = a_base + (uint32_t)sa * a_slot;
             if (!PAIR) {
@@ -1518,16 +1523,21 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         }
       }
     }
+    if (a.trace && lane == 0) { a.trace[blockIdx.x * 8 + 0] = clock64() - tr_t0; a.trace[blockIdx.x * 8 + 1] = tr_wait; }
   } else if (warp == 1) {
     // ================================ MMA issuer (pair: the leader only) ================================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it_local = 0;
+    long long tr_wa = 0, tr_wt = 0;
+    const long long tr_t0 = clock64();
     if (!PAIR || crank == 0)
     for (int wk = wk0; wk < n_work; wk += wk_step, ++it_local) {
       const int b = it_local & 1;
       const uint32_t use = (uint32_t)(it_local >> 1);
+      const long long tw0 = a.trace ? clock64() : 0;
       mbar_wait(bar_tempty + 8 * b, (use & 1) ^ 1);
+      if (a.trace) tr_wt += clock64() - tw0;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(b * 2 * BN);
       uint32_t first = 0;
@@ -1535,7 +1545,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       for (int c = 0; c < a.CC; ++c) {
 #pragma unroll 1
         for (int dx = 0; dx < a.NDX; ++dx) {
+          const long long tw1 = a.trace ? clock64() : 0;
           mbar_wait(bar_afull + 8 * sa, pa);
+          if (a.trace) tr_wa += clock64() - tw1;
           const uint32_t slot = a_base + (uint32_t)sa * a_slot;
 #pragma unroll 1
           for (int dy = 0; dy < a.NDY; ++dy) {
@@ -1577,8 +1589,13 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         }
       }
     }
+    if (a.trace && lane == 0 && (!PAIR || crank == 0)) {
+      a.trace[blockIdx.x * 8 + 2] = clock64() - tr_t0; a.trace[blockIdx.x * 8 + 3] = tr_wa; a.trace[blockIdx.x * 8 + 4] = tr_wt;
+    }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
+    long long tr_we = 0;
+    const long long tr_t0 = clock64();
     const int q = warp & 3, half = warp >= 8 ? 0 : 1;     // TMEM lane quadrant = warp % 4; two warps per quadrant, 16 of a pass's 32 columns each
     const int et = (half * 4 + q) * 32 + lane;
     const int row = q * 32 + lane;
@@ -1602,7 +1619,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       const uint32_t use = (uint32_t)(it_local >> 1);
       const bool valid = real && y0 + rr < a.H && x0 + rc < a.W;   // pixels of a border tile beyond the image: clipped by the store, masked here
       const int n_base = nt * BN;
+      const long long tw0 = a.trace ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * b, use & 1);
+      if (a.trace) tr_we += clock64() - tw0;
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + (uint32_t)(b * 2 * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll(BN == 64 ? 2 : 1)      // (64-wide: both passes unrolled, the deferred statistics stay in registers)
@@ -1679,6 +1698,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
       }
     }
     if (et == 0) bulk_wait0();
+    if (a.trace && et == 0) { a.trace[blockIdx.x * 8 + 5] = clock64() - tr_t0; a.trace[blockIdx.x * 8 + 6] = tr_we; }
   }
 
   tc_fence_before();
@@ -2545,6 +2565,37 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  // debug: SAG_HALO_TRACE=<taps> prints where the three roles of the first launches with that many taps wait
+  static const int trace_taps = env_int("SAG_HALO_TRACE", 0);
+  static int traced = 0;
+  if (trace_taps > 0 && taps == trace_taps && traced < 2) {
+    ++traced;
+    const size_t n = (size_t)cfg.gridDim.x * 8;
+    long long* dtr = nullptr;
+    cudaMalloc(&dtr, n * sizeof(long long));
+    cudaMemset(dtr, 0, n * sizeof(long long));
+    args.trace = dtr;
+    cudaStreamSynchronize(st);
+    cudaLaunchKernelEx(&cfg, kern, args, tm);
+    cudaStreamSynchronize(st);
+    std::vector<long long> tr(n);
+    cudaMemcpy(tr.data(), dtr, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dtr);
+    double d[8] = {0};
+    int lead = 0;
+    for (size_t c = 0; c < n / 8; ++c) {
+      for (int i = 0; i < 8; ++i) d[i] += (double)tr[c * 8 + i];
+      if (tr[c * 8 + 2] > 0) ++lead;
+    }
+    const double nc = (double)(n / 8), nl = lead > 0 ? (double)lead : 1.0;
+    fprintf(stderr, "[halo trace] BN=%d pair=%d ctas=%u tiles=%d taps=%d SA=%d SB=%d BRES=%d A1=%d\n", BN, (int)PAIR, cfg.gridDim.x, tiles, taps, args.SA,
+            args.SB, args.BRES, args.A1);
+    fprintf(stderr, "[halo trace]   producer : total %9.0f clk, waiting for a free box %9.0f\n", d[0] / nc, d[1] / nc);
+    fprintf(stderr, "[halo trace]   MMA      : total %9.0f clk, waiting for a box %9.0f, for a free accumulator %9.0f\n", d[2] / nl, d[3] / nl, d[4] / nl);
+    fprintf(stderr, "[halo trace]   epilogue : total %9.0f clk, waiting for an accumulator %9.0f\n", d[5] / nc, d[6] / nc);
+    SAG_LAUNCH_CHECK();
+    return SAG_OK;
+  }
   SAG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args, tm));
   SAG_LAUNCH_CHECK();
   return SAG_OK;

@@ -65,6 +65,7 @@ __device__ __forceinline__ void bn_scale_shift_to_smem(const BnStats& bn, int c,
 // Memory-level parallelism: a thread fetches BN_UNROLL vectors (and their residuals) before it touches any of them -- with one
 // 16-byte load in flight per thread the kernel sat at 35-44 % of the HBM rate on scoreboard stalls (profiles/r1_small_kernels_ncu.txt).
 constexpr int BN_UNROLL = 4;
+template <bool BN_STREAM>
 __global__ void __launch_bounds__(256, 4) bn_apply_stats_kernel(const float4* __restrict__ x, const BnStats bn, const ActView res, int relu,
                                                                 const ActView y, int64_t n4, int c) {
   extern __shared__ float s_ss[];
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256, 4) bn_apply_stats_kernel(const float4* __
     for (int u = 0; u < BN_UNROLL; ++u) {                    // vector i0 + u*stride: all loads first
       const int64_t i = i0 + (int64_t)u * stride;
       if (i < n4) {
-        v[u] = __ldg(x + i);
+        v[u] = BN_STREAM ? __ldcs(x + i) : __ldg(x + i);      // raw conv output: dead after this read (evict-first)
         if (has_res) r[u] = load_act4(res.p, res.fmt, res.plane, i * 4);
       }
     }
@@ -113,8 +114,13 @@ int launch_bn_apply_stats(const float* x, const BnStats& bn, const ActView& resi
   int64_t cap = (int64_t)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  launch_pdl(bn_apply_stats_kernel, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, reinterpret_cast<const float4*>(x), bn,
-             residual, relu, y, n4, c);
+  static const bool stream = [] { const char* v = getenv("SAG_BN_STREAM"); return v == nullptr || atoi(v) != 0; }();
+  if (stream)
+    launch_pdl(bn_apply_stats_kernel<true>, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, reinterpret_cast<const float4*>(x), bn,
+               residual, relu, y, n4, c);
+  else
+    launch_pdl(bn_apply_stats_kernel<false>, dim3((unsigned)blocks), dim3(256), 2 * c * sizeof(float), st, reinterpret_cast<const float4*>(x), bn,
+               residual, relu, y, n4, c);
   SAG_LAUNCH_CHECK();
   return SAG_OK;
 }

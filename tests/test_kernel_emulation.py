@@ -33,6 +33,7 @@ struct Dim { unsigned x = 0, y = 0, z = 0; };
 static Dim threadIdx, blockIdx, blockDim, gridDim;
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 #define __ldg(p) (*(p))
+#define __ldcs(p) (*(p))
 enum { ACT_F32 = 0, ACT_BF2 = 1 };
 struct ActView { void* p = nullptr; int fmt = ACT_F32; int64_t plane = 0; };
 struct BnStats { const double* sum = nullptr; const double* sqs = nullptr; const float* gamma = nullptr; const float* beta = nullptr;
@@ -66,7 +67,7 @@ extern "C" void emu_bn_apply(const float* x, const double* sum, const double* sq
                              void* res, int res_fmt, int64_t res_plane, int relu, void* y, int y_fmt, int64_t y_plane, int64_t n4,
                              int c, int grid, int block) {
   for_each_thread(grid, block, [&] {
-    bn_apply_stats_kernel(reinterpret_cast<const float4*>(x), mk(sum, sqs, g, be, inv), view(res, res_fmt, res_plane), relu,
+    bn_apply_stats_kernel<true>(reinterpret_cast<const float4*>(x), mk(sum, sqs, g, be, inv), view(res, res_fmt, res_plane), relu,
                           view(y, y_fmt, y_plane), n4, c);
   });
 }
