@@ -2157,14 +2157,13 @@ static const ForcedCfg* forced_for(int N, int64_t M) {
 // a K split adds the partial round trip through L2 and the reduce launch.  A single M tile (fully connected layers
 // on a batch of windows) is weight-streaming bound: narrow tiles + a deep split spread the weights over all SMs.
 struct TilePlan { int BN, Z; };
-// Stream-K (see plan_streamk) is off unless SAG_UMMA_STREAMK=1: measured on B200 it shortens conv4_x / conv5_x by 0-2 us each
-// in isolation and LENGTHENS the forward (1745 vs 1811 audio-s/s): the contraction is bound by shared-memory bandwidth, not by
-// the SM count, the idle third of the SMs was hosting the audio chain of the side stream, and the two
-// serial epilogues at the end of every stream-K kernel (raw piece, fix-up) eat the balanced main loop's gain.  Read at every
-// call (tests switch it on for the layers they check); a handle must be planned and run under the same setting.
+// Stream-K (see plan_streamk): on unless SAG_UMMA_STREAMK=0.  Measured on B200 at 32 windows: conv5_x 57.6 -> 47.5 us, conv4_x
+// 53.6 -> 49.5 us, the forward 1880 -> 1937 audio-s/s.  (A first version lost: its raw-piece / fix-up epilogues ran serially at
+// the end of every kernel without pipelined TMEM loads or prefetched slabs, and 256-wide pairs for conv5_x gained nothing.)
+// Read at every call (tests switch it); a handle must be planned and run under the same setting.
 static bool streamk_enabled() {
   const char* v = getenv("SAG_UMMA_STREAMK");
-  return v != nullptr && atoi(v) != 0;
+  return v == nullptr || atoi(v) != 0;
 }
 static TilePlan plan_tile(int K, int N, int64_t M) {
   static const int wide = env_int("SAG_UMMA_BN256", 1);
@@ -2203,7 +2202,8 @@ static TilePlan plan_tile(int K, int N, int64_t M) {
   // pairs).  Cost: the cluster's share of chunks at the pair rate (measured 1612 clk per 256 x 256 x 64 chunk) + the two
   // serial epilogues at the end (raw piece, then the fix-up) + launch.
   const int64_t MT = cdiv64(M, UM_BM);
-  if (streamk_enabled() && wide && !f && N >= 256 && KC >= 16 && MT >= 8) {
+  static const int sk_wide = env_int("SAG_UMMA_STREAMK_WIDE", 0);      // (measured: conv5_x 57.5 us on 256-wide pairs, 50 us on 128-wide tiles)
+  if (sk_wide && streamk_enabled() && wide && !f && N >= 256 && KC >= 16 && MT >= 8) {
     const int64_t units = cdiv64(MT, 2) * cdiv(N, 256) * KC, G = max_conv_ctas() / 2;
     if (G >= 2 && units >= 4 * G) {
       const double t = (double)cdiv64(units, G) * 0.82 + 13.0 + 5.0;

@@ -195,7 +195,7 @@ STREAM_K_CASES = [
 @pytest.mark.parametrize('prec', [3, 2])
 @pytest.mark.parametrize('case', STREAM_K_CASES)
 def test_conv2d_tcgen05_stream_k(case, prec, monkeypatch):
-    monkeypatch.setenv('SAG_UMMA_STREAMK', '1')          # off by default; read at every call
+    monkeypatch.setenv('SAG_UMMA_STREAMK', '1')          # (the default; read at every call)
     L = _L()
     n, h, w, cin, kh, kw, cout = case[:7]
     assert L.lib().sag_plan_stream_k(kh * kw * cin, cout, n * h * w) == 1
@@ -676,7 +676,7 @@ def test_forward_is_bit_reproducible():
 
 
 def test_forward_stream_k_matches_the_tile_schedule_and_is_bit_reproducible(monkeypatch):
-    """Stream-K (opt-in) on conv4_x / conv5_x of the benchmarked batch: the pieces of a tile meet in the finishing CTA's epilogue
+    """Stream-K on conv4_x / conv5_x of the benchmarked batch: the pieces of a tile meet in the finishing CTA's epilogue
     (batch-norm statistics + TMA-store path), the flags are left cleared, so repeated forwards agree bit for bit."""
     from spatialaudiogen_b200 import SptAudioGen
     enc = ['audio', 'video']
@@ -684,6 +684,7 @@ def test_forward_stream_k_matches_the_tile_schedule_and_is_bit_reproducible(monk
     B = 32
     a, v = cu(_audio(B, 60)), cu(_video(B, 61))
     ref = torch.empty((B, 4800, 3), device='cuda')
+    monkeypatch.setenv('SAG_UMMA_STREAMK', '0')                 # whole tiles per CTA
     SptAudioGen(1, encoders=enc, separation='unet_mask').load_weights(W).forward_into(a, v, None, ref)
     monkeypatch.setenv('SAG_UMMA_STREAMK', '1')
     assert _L().lib().sag_plan_stream_k(9 * 512, 512, B * 7 * 14) == 1

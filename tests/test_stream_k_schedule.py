@@ -90,8 +90,9 @@ def test_execution_order_cannot_deadlock_and_partials_come_first(tiles, kc, clus
 
 def test_planner_picks_stream_k_for_the_badly_quantised_trunk_layers(monkeypatch):
     lib = L.lib()
-    assert lib.sag_plan_stream_k(9 * 256, 256, 32 * 14 * 28) == 0       # off unless asked for
-    monkeypatch.setenv('SAG_UMMA_STREAMK', '1')
+    monkeypatch.setenv('SAG_UMMA_STREAMK', '0')                         # the switch is read at every call
+    assert lib.sag_plan_stream_k(9 * 256, 256, 32 * 14 * 28) == 0
+    monkeypatch.delenv('SAG_UMMA_STREAMK')
     # B=32, 224x448 frames: conv4_x (3x3x256 -> 256 over 14x28), conv5_x (3x3x512 -> 512 over 7x14): a third of the SMs idle unsplit
     assert lib.sag_plan_stream_k(9 * 256, 256, 32 * 14 * 28) == 1
     assert lib.sag_plan_stream_k(9 * 512, 512, 32 * 7 * 14) == 1
