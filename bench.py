@@ -520,7 +520,7 @@ def main():
     for name in ('r2_dominant_kernel_traffic.json', 'r1_dominant_kernel_traffic.json'):
         try:                                              # DRAM bytes per launch of the same kernel family, from ncu
             tj = json.load(open(os.path.join(ROOT, 'profiles', name)))
-            if encoders == ['audio', 'video'] and B == 32 and precision == 'bf16x3':
+            if encoders == ['audio', 'video'] and B == 32 and precision in ('bf16x3', 'mixed'):
                 traffic, traffic_src = tj['traffic_bytes_per_launch'], 'profiles/%s (%s)' % (name, tj.get('source', 'ncu'))
             break
         except Exception:

@@ -2764,7 +2764,8 @@ int launch_gather_gemm_umma(const ActView& x, const UmmaWeights& w, const ActVie
   static const int epi_dbg = env_int("SAG_UMMA_EPI_DEBUG", 0);
   a.dbg = epi_dbg;
   if (Z > 1) a.partial = scratch;
-  if (Z == 1 && scratch != nullptr && ep.sk_flags != nullptr && w.col_off == nullptr && ep.gains == nullptr &&
+  static const int sk_mapped = env_int("SAG_UMMA_STREAMK_DECONV", 0);      // sub-pixel transposed convs (mapped outputs): measured deconv3 29.1 -> 33.3 us, others +-0 -- their epilogues pace them; off
+  if (Z == 1 && scratch != nullptr && ep.sk_flags != nullptr && (w.col_off == nullptr || sk_mapped) && ep.gains == nullptr &&
       plan_streamk(w.K, w.N, M, plan)) {
     a.sk_flags = ep.sk_flags;
     a.sk_slab = scratch;

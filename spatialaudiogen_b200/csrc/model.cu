@@ -306,6 +306,7 @@ struct Fwd {
     const float* b = W(scope + "/biases", &err);
     SAG_TRY(err);
     Epilogue ep{b, relu, nullptr, nullptr};
+    ep.sk_flags = private_scratch ? nullptr : h->sk_flags;
     if (tc()) {
       // one sub-pixel GEMM for the whole layer: N = sh*sw*cout columns, ceil(kh/sh)*ceil(kw/sw) taps
       const int order = y_sc == 1 ? 0 : 1;

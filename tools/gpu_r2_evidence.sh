@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence: bench lines (ours + reference arm), ncu launch list, DRAM / L2 traffic of the contraction launches of one
-# forward, one --set full capture of a conv2_x launch (halo-resident kernel on CTA pairs; 4 launches per forward, the 14th is in the 4th forward).  ncu runs use SAG_OVERLAP=0 so that the launch order is the serial one.
+# forward, one --set full capture of a conv2_x launch (halo-resident kernel on CTA pairs; conv1 + 4 conv2_x launches per forward, the 14th halo launch is a conv2_x of the 3rd forward).  ncu runs use SAG_OVERLAP=0 so that the launch order is the serial one.
 tag=${1:-r2ev}
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
