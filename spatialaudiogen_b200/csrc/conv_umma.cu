@@ -1370,6 +1370,7 @@ struct HaloArgs {
   // exact bf16 plane (uint8 frames as 2k - 255, resnet18_tower): no lo box, no A_lo x B_hi MMA.
   int BRES, A1;
   long long* trace;                   // SAG_HALO_TRACE (debug): per-CTA cycle counters of the three roles
+  int dbg;                            // SAG_HALO_DEBUG (timing experiments, results invalid): 1 no TMEM loads in the epilogue, 2 no staging / stores
 };
 struct alignas(64) HaloMaps { CUtensorMap hi, lo, o, w; };     // w: tiled map of the packed weights (pairs)
 constexpr int HL_THREADS = 12 * 32;    // warp 0 producer, warp 1 MMA + TMEM, warps 4-11 epilogue (two per TMEM lane quadrant)
@@ -1548,11 +1549,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
           const long long tw1 = a.trace ? clock64() : 0;
           mbar_wait(bar_afull + 8 * sa, pa);
           if (a.trace) tr_wa += clock64() - tw1;
+          tc_fence_after();
           const uint32_t slot = a_base + (uint32_t)sa * a_slot;
 #pragma unroll 1
           for (int dy = 0; dy < a.NDY; ++dy) {
-            if (wait_b) mbar_wait(bar_bfull + 8 * sb, pb);
-            tc_fence_after();
+            if (wait_b) {                                  // (resident weights: no wait, and no fence between the taps' MMAs)
+              mbar_wait(bar_bfull + 8 * sb, pb);
+              tc_fence_after();
+            }
             const uint32_t ab = slot + (uint32_t)dy * (uint32_t)a.TW * 128u;        // rows dy * TW .. of the box: vertical tap dy - 1
             const uint32_t bb = b_base + (uint32_t)sb * B_BYTES;
             const uint64_t da_hi = DESC_HI | (uint64_t)((ab & 0x3FFFFu) >> 4);
@@ -1630,9 +1634,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         const int par = (int)(pass_no & 1u);
         const uint32_t stile = stile0 + (uint32_t)par * 16384u;
         float v[16], u[16];
-        tmem_ld16_nowait(tmem_row + (uint32_t)cc, v);                // both accumulator blocks in flight, one wait
-        tmem_ld16_nowait(tmem_row + (uint32_t)(BN + cc), u);
-        tmem_ld_wait();
+        if (a.dbg & 1) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { v[e] = 0.f; u[e] = 0.f; }
+        } else {
+          tmem_ld16_nowait(tmem_row + (uint32_t)cc, v);              // both accumulator blocks in flight, one wait
+          tmem_ld16_nowait(tmem_row + (uint32_t)(BN + cc), u);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] += u[e];
         if (c0 + 32 >= BN) {
@@ -1659,17 +1668,19 @@ __global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const Hal
         // ONE barrier per pass, two staging tiles: the store that last read THIS tile (two passes ago) was waited for by the
         // issuing thread before it arrived at the previous pass's barrier (wait_group.read 0 below: at that point the youngest
         // store is a whole pass old, so the wait is rarely a stall and the store latency does not sit between two passes)
+        if (!(a.dbg & 2)) {
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const uint32_t chunk = (uint32_t)(half * 16 + e) >> 2;
-          st_shared_v4(stile + (uint32_t)row * 128u + ((chunk ^ ((uint32_t)row & 7u)) << 4),
-                       make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+          for (int e = 0; e < 16; e += 4) {
+            const uint32_t chunk = (uint32_t)(half * 16 + e) >> 2;
+            st_shared_v4(stile + (uint32_t)row * 128u + ((chunk ^ ((uint32_t)row & 7u)) << 4),
+                         make_uint4(__float_as_uint(v[e]), __float_as_uint(v[e + 1]), __float_as_uint(v[e + 2]), __float_as_uint(v[e + 3])));
+          }
         }
         fence_proxy_async();
         if (et == 0) bulk_wait_read0();                    // the previous pass's store has read the OTHER tile: the next pass may write it
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
-          if (real) tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
+          if (real && !(a.dbg & 2)) tma_store_4d(&tm.o, stile, n_base + c0, x0, y0, nimg);
           bulk_commit();                                   // (one group per pass, also an empty one: wait_group counts groups)
         }
         if (!(BN == 64 && defer_stats) && et < 32 && n_base + c0 + et < a.Ntot) {
@@ -2531,6 +2542,8 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   const int taps = a.NDX * a.NDY * a.CC;
   // weights resident when every tap fits beside two activation boxes (one N tile: the same chunks serve every tile of the CTA)
   static const int bres_env = env_int("SAG_UMMA_HALO_BRES", 1);
+  static const int halo_dbg = env_int("SAG_HALO_DEBUG", 0);
+  args.dbg = halo_dbg;
   args.BRES = (bres_env && a.NT == 1 && taps <= HL_MAX_SB &&
                (long)fixed + 2 * (long)a_slot + (long)taps * B_BYTES <= (long)budget[dev & 63]) ? 1 : 0;
   if (args.BRES) {
