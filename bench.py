@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-baseline-seconds', type=float, default=15.0)
     ap.add_argument('--rotate', type=int, default=4, help='distinct input batches cycled through (L2 hygiene)')
+    ap.add_argument('--lanes', type=int, default=int(os.environ.get('SAG_LANES', '3')),
+                    help='forwards in flight: consecutive batches alternate over this many (handle, workspace, stream) lanes, so the '
+                         'short grids of one batch (FCs, decoder, BN passes) fill the SMs the other batch leaves idle')
     args = ap.parse_args()
     dflt = {1: (1, 'audio'), 2: (32, 'audio,video'), 3: (32, 'audio,video,flow'), 4: (32, 'audio,video'), 5: (32, 'audio,video')}[args.config]
     if args.batch is None:
@@ -265,6 +268,7 @@ def workload_config(encoders, B, precision, args, world):
                       if len(encoders) > 1 else None,
             'weights': 'xavier random init (seed 1234); resnet towers: %s' % (
                 'the reference\'s resnet18.npy (model.py:198)' if os.path.exists(RESNET_NPY) else 'xavier (resnet18.npy not staged)'),
+            'lanes': max(1, args.lanes),
             'step': 'sag_forward + sag_metrics over one batch' + (' (replayed as one CUDA graph: host-launch-bound batch size)' if B <= 16 else ''),
             'l2': 'inputs rotate over %d distinct batches and each step streams >1 GB of activations through the '
                   'workspace (> 126 MB L2)' % args.rotate,
@@ -321,7 +325,8 @@ def main():
                                        resnet_npy=RESNET_NPY if os.path.exists(RESNET_NPY) else None))
 
     # R distinct synthetic batches, resident in HBM (value) and in pinned host memory (e2e)
-    R = max(1, args.rotate)
+    n_lanes = max(1, args.lanes)
+    R = (max(1, args.rotate) + n_lanes - 1) // n_lanes * n_lanes   # (a multiple of the lanes: slot r always runs on lane r % lanes)
     u8 = args.frames == 'u8'
     vkey, fkey = ('video_u8', 'flow_u8') if u8 else ('video', 'flow')
     host, devb = [], []
@@ -332,9 +337,15 @@ def main():
         devb.append({k: v.to(dev) for k, v in hb.items() if k in ('audio', 'target', vkey, fkey, 'flow_limits')})
     out = torch.empty((B, SND_DUR, 3), dtype=torch.float32, device=dev)
     out_host = torch.empty((B, SND_DUR, 3), dtype=torch.float32).pin_memory()
+    # lanes: lane 0 is (model, out, the current stream); every further lane has its own handle (same weights), workspace,
+    # output buffer and stream
+    lanes = [(model, out, None)]
+    for _ in range(1, n_lanes):
+        m2 = SptAudioGen(1, encoders=encoders, separation='unet_mask', precision=precision, device=dev).load_weights(model._w)
+        lanes.append((m2, torch.empty_like(out), torch.cuda.Stream(device=dev)))
 
-    def fwd(d):
-        model.forward_into(d['audio'], d.get(vkey), d.get(fkey), out, d.get('flow_limits') if u8 else None)
+    def fwd(d, lane=0):
+        lanes[lane][0].forward_into(d['audio'], d.get(vkey), d.get(fkey), lanes[lane][1], d.get('flow_limits') if u8 else None)
 
     # ---- the pass: which batches this rank processes ----
     if args.config == 4:                                  # YT-All-shaped stream: whole batches of one clip, clips round-robin
@@ -360,10 +371,10 @@ def main():
     ids = torch.tensor([[c, w0 + j] for (c, w0) in batch_ids for j in range(B)], dtype=torch.int64).reshape(-1, 2).to(dev)
     ss = RATE // 2
 
-    def step_eager(d, store=None):
-        fwd(d)
+    def step_eager(d, store=None, lane=0):
+        fwd(d, lane)
         # the metric set of SURVEY.md 8d config 5 (config 5 adds the 84-direction RMS maps of [W | pred] and [W | gt])
-        r, _ = E.metric_rows(out, d['target'], mono=d['audio'][:, ss:ss + SND_DUR] if maps_on else None, audio_rate=RATE,
+        r, _ = E.metric_rows(lanes[lane][1], d['target'], mono=d['audio'][:, ss:ss + SND_DUR] if maps_on else None, audio_rate=RATE,
                              rms_maps=maps_on, mel_lsd=False, emd=False)
         if store is not None:
             store.copy_(r)
@@ -376,31 +387,48 @@ def main():
         try:
             for r in range(R):
                 rows_slot.append(torch.zeros((B, E.N_COLS), dtype=torch.float32, device=dev))
-                step_eager(devb[r], rows_slot[r])             # warm-up: plans the batch, sets kernel attributes
+                step_eager(devb[r], rows_slot[r], r % n_lanes)   # warm-up: plans the batch, sets kernel attributes
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    step_eager(devb[r], rows_slot[r])
+                    step_eager(devb[r], rows_slot[r], r % n_lanes)
                 graphs.append(g)
         except RuntimeError as e:
             sys.stderr.write('CUDA graph capture failed (%s): eager launches\n' % e)
             use_graph, graphs = False, []
 
     def step(i, store=None):
-        if use_graph:
-            graphs[i % R].replay()
-            if store is not None:
-                store.copy_(rows_slot[i % R])
-        else:
-            step_eager(devb[i % R], store)
+        r = i % R
+        lane = r % n_lanes
+        with torch.cuda.stream(lanes[lane][2] or torch.cuda.current_stream()):
+            if use_graph:
+                graphs[r].replay()
+                if store is not None:
+                    store.copy_(rows_slot[r])
+            else:
+                step_eager(devb[r], store, lane)
+
+    def fork_lanes():                                     # the lanes' streams start after everything queued on the current stream ...
+        ev = torch.cuda.Event()
+        ev.record()
+        for _, _, s in lanes[1:]:
+            s.wait_event(ev)
+
+    def join_lanes():                                     # ... and the current stream continues after everything queued on them
+        for _, _, s in lanes[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            torch.cuda.current_stream().wait_event(ev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
+    fork_lanes()
+    for i in range(max(3, args.warmup) * n_lanes):
         step(i)
+    join_lanes()
     if world > 1:                                        # warm the collective too
         D.gather_rows(rows[:n_batches].reshape(-1, E.N_COLS), ids, max_rows=n_max * B)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -410,8 +438,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
+    fork_lanes()
     for i in range(n_batches):
         step(i, rows[i])
+    join_lanes()
     all_rows, all_ids = rows[:n_batches].reshape(-1, E.N_COLS), ids
     if world > 1:                                        # the pass's single collective: all ranks' metric rows
         all_rows, all_ids = D.gather_rows(rows[:n_batches].reshape(-1, E.N_COLS), ids, max_rows=n_max * B)
@@ -456,7 +486,7 @@ def main():
 
     def run_e2e(n):
         acc = 0.0
-        for y in model.inference_stream(host_batches(n), depth=int(os.environ.get('SAG_STREAM_DEPTH', '3'))):
+        for y in model.inference_stream(host_batches(n), depth=int(os.environ.get('SAG_STREAM_DEPTH', '3')), lanes=n_lanes):
             acc += float(y[0, 0, 0])                      # the caller consumes each waveform on the host
         return acc
 
@@ -475,7 +505,7 @@ def main():
     h2d = sum(int(host[0][src].numel() * host[0][src].element_size()) for src in e2e_keys.values())
     e2e = {'value': WINDOW_S * B * int(cnt.item()) / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms2 / max(n_e2e, 1),
-           'api': 'SptAudioGen.inference_stream(pinned host batches) -> host (B,4800,3) waveforms; copies overlap compute'}
+           'api': 'SptAudioGen.inference_stream(pinned host batches, lanes=%d) -> host (B,4800,3) waveforms; copies overlap compute' % n_lanes}
 
     # ---- roofline of the dominant kernel family, timed live with CUDA events on the launching stream ----
     peaks = {}

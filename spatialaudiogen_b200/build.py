@@ -35,9 +35,12 @@ def build(force=False, verbose=False):
     odir = os.path.join(HERE, 'build')
     os.makedirs(odir, exist_ok=True)
     procs = []
+    hdrs = glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(HERE, '..', 'include', '*.h'))
     for src in sources():
         obj = os.path.join(odir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in [src] + hdrs):
+            continue                                      # this object is newer than its source and every header
         cmd = [nvcc, '-c', src, '-o', obj, '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC'] + ARCH
         if verbose:
             cmd += ['-Xptxas', '-v']

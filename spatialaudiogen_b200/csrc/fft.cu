@@ -82,23 +82,60 @@ __device__ __forceinline__ void stft_emit(const float2 v, int i, int64_t cplx_ba
   }
 }
 
+// The samples of a CTA's two frames are ONE contiguous span of the 48 kHz stream (wind + hop samples): it is staged into
+// shared memory by the TMA unit (cp.async.bulk, one elected thread, mbarrier completion) -- rows of 52799 floats start at
+// any multiple of 4 bytes, so the copy starts at the 16-byte boundary below the span -- and windowed from there.
+__device__ __forceinline__ uint32_t stft_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, int n_samples, int hop, const FftPlan p,
                                                    int fbase, int fend, int frame0, int n_frames_out, float2* __restrict__ cplx_out,
                                                    int mag0, int n_mag, const ActView mag_out) {
   extern __shared__ __align__(16) float2 smem[];
+  __shared__ __align__(8) unsigned long long stage_bar;
   float2* buf0 = smem;
   float2* buf1 = smem + 2 * p.n;
-  pdl_prologue();
   const int n = p.n;
   const int fa = fbase + 2 * blockIdx.x, fb = fa + 1;
   const bool has_b = fb < fend;
   const int row = blockIdx.y;
   const float* xa = x + (int64_t)row * n_samples + (int64_t)fa * hop;
+  // aligned span [xs, xs + span) covering the frames' samples; the whole input is gridDim.y rows of n_samples floats
+  const int mis = (int)((reinterpret_cast<uintptr_t>(xa) & 15) >> 2);
+  const float* xs = xa - mis;
+  const int span = (mis + n + (has_b ? hop : 0) + 3) & ~3;
+  const bool staged = xs + span <= x + (int64_t)gridDim.y * n_samples && span <= 4 * n;   // (buf1 holds 4n floats)
+  const uint32_t bar = stft_smem_u32(&stage_bar);
+  if (staged && threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_prologue();
+  const float* raw = xa;
+  if (staged) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)span * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stft_smem_u32(buf1)),
+                   "l"(xs), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\nselp.u32 %0, 1, 0, q;\n}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+    raw = reinterpret_cast<const float*>(buf1) + mis;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float w = __ldg(p.hann + i);
-    buf0[i] = make_float2(__ldg(xa + i) * w, 0.f);
-    buf0[n + i] = make_float2(has_b ? __ldg(xa + hop + i) * w : 0.f, 0.f);
+    buf0[i] = make_float2(raw[i] * w, 0.f);
+    buf0[n + i] = make_float2(has_b ? raw[hop + i] * w : 0.f, 0.f);
   }
+  // (block_fft_nf synchronises before its first pass writes buf1: the staged samples are consumed by then)
   const float2* z = block_fft_nf(buf0, buf1, p, 2);
   // where the two frames go (-1: not wanted)
   auto bases = [&](int f, int64_t& cb, int64_t& mb) {

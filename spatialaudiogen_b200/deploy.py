@@ -99,32 +99,53 @@ class W2XYZ(object):
             torch.cuda.current_stream().synchronize()
         return self._out_h[:n].numpy().copy()
 
-    def deploy_stream(self, windows):
+    def deploy_stream(self, windows, lanes=3):
         """The loop of deploy.py:112-151 over an ITERATOR of windows -- dicts {'ambix': (audio_size, C>=1) with W in channel 0
         [, 'video', 'flow': (video_size, H, W, 3) float32 or uint8, 'flow_limits': (video_size, 2)]} -- consumed batch_size at a
-        time like the reference does, so host memory holds one batch of inputs plus the growing output.  Returns
-        (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
+        time like the reference does, so host memory holds a few batches of inputs plus the growing output.  Returns
+        (N*snd_dur, 4) float64 rows [W, Y, Z, X].  Full batches go through SptAudioGen.inference_stream (copies on their own
+        streams, `lanes` forwards in flight, the batch of 10 replayed as a CUDA graph; same bits as one run_batch per batch);
+        the short last batch, which the reference zero-pads AFTER preparing its frames, goes through run_batch."""
         ss = self.model.snd_contx // 2
         mono, pred = [], []
-        batch = []
+        enc = self.params.encoders
+        tail = []
 
-        def flush():
+        def pack(batch):
             a = np.stack([np.asarray(c['ambix'], np.float64) for c in batch], 0)
-            n = a.shape[0]
-            v = np.stack([c['video'] for c in batch], 0) if VIDEO in self.params.encoders else None
-            f = np.stack([c['flow'] for c in batch], 0) if FLOW in self.params.encoders else None
+            v = np.stack([c['video'] for c in batch], 0) if VIDEO in enc else None
+            f = np.stack([c['flow'] for c in batch], 0) if FLOW in enc else None
             fl = np.stack([np.asarray(c['flow_limits']).reshape(-1, 2)[0] for c in batch], 0) if (f is not None and 'flow_limits' in batch[0]) else None
-            out = self.run_batch(a[:, :, :1], v, f, fl)
-            pred.append(out.reshape(n * out.shape[1], out.shape[2]))
             mono.append(np.copy(a[:, ss:ss + self.model.snd_dur, :1]).reshape(-1, 1))
-            del batch[:]
+            return a, v, f, fl
 
-        for c in windows:
-            batch.append(c)
-            if len(batch) == self.batch_size:
-                flush()
-        if batch:
-            flush()
+        def full_batches():
+            batch = []
+            for c in windows:
+                batch.append(c)
+                if len(batch) == self.batch_size:
+                    a, v, f, fl = pack(batch)
+                    batch = []
+                    b = {AUDIO: torch.from_numpy(np.ascontiguousarray(a[:, :, :1], dtype=np.float32))}
+                    for k, x in ((VIDEO, v), (FLOW, f)):
+                        if x is None:
+                            continue
+                        if x.dtype != np.uint8:
+                            x = np.asarray(x, dtype=np.float32)
+                        elif k == FLOW and fl is None:
+                            raise ValueError('uint8 flow frames need flow_limits')
+                        b[k] = torch.from_numpy(np.ascontiguousarray(x))
+                    if FLOW in b and b[FLOW].dtype == torch.uint8:
+                        b['flow_limits'] = torch.from_numpy(np.ascontiguousarray(fl, dtype=np.float64))
+                    yield b
+            tail.extend(batch)
+
+        for y in self.model.inference_stream(full_batches(), lanes=lanes):
+            pred.append(y.numpy().reshape(-1, y.shape[2]).copy())
+        if tail:
+            a, v, f, fl = pack(tail)
+            out = self.run_batch(a[:, :, :1], v, f, fl)
+            pred.append(out.reshape(-1, out.shape[2]))
         if not pred:
             return np.zeros((0, 4))
         return np.concatenate((np.concatenate(mono, 0), np.concatenate(pred, 0)), 1)   # float64, like numpy promotes in deploy.py:151

@@ -91,6 +91,11 @@ class SptAudioGen(StageOps):
         if precision is None:
             precision = L.default_precision()
         self.precision = precision
+        self._ctor = dict(ambi_order=ambi_order, audio_rate=audio_rate, video_rate=video_rate, context=context,
+                          sample_duration=sample_duration, separation=separation, params=params, precision=precision,
+                          frame_size=tuple(frame_size))
+        self._opts = OrderedDict()      # sag_set_option calls so far (replayed onto the lane twins of inference_stream)
+        self._twins = []
         lib = L.lib()
         cfg = L.sag_config()
         L.check(lib.sag_config_default(C.byref(cfg)))
@@ -161,11 +166,16 @@ class SptAudioGen(StageOps):
                 self._w[name] = a
             L.check(lib.sag_finalize_weights(self._h, L.stream()))
         self._weights_ready = True
+        self._twins = []                # lane twins carry the old weights
         self._ws_batch = 0              # re-plan: the packed tensor-core images of reloaded layers are rebuilt in sag_workspace_bytes
         self.__dict__.pop('_wd', None)
         return self
 
     def set_option(self, key, value):
+        for t in self._twins:
+            t.set_option(key, value)
+        if key != 'profile':
+            self._opts[key] = value
         if key == 'precision' and isinstance(value, str):
             self.precision = value
             value = L.PRECISIONS[value]
@@ -264,7 +274,18 @@ class SptAudioGen(StageOps):
     def dims_frame(self):
         return self._frame
 
-    def inference_stream(self, batches, depth=2, use_graph=None):
+    def _lanes(self, n):
+        """[self, twin, ...]: n models with the same configuration, options and weights, each with its own native handle (side
+        streams, events, stream-K flags) and workspace, so that n forwards can be in flight on n streams."""
+        while len(self._twins) < n - 1:
+            t = SptAudioGen(encoders=list(self.encoders), device=self.device, **self._ctor)
+            t.load_weights(self._w)
+            for k, v in self._opts.items():
+                t.set_option(k, v)
+            self._twins.append(t)
+        return [self] + self._twins[:n - 1]
+
+    def inference_stream(self, batches, depth=2, use_graph=None, lanes=3):
         """The driver loop around `sess.run` (reference deploy.py:112-148, eval.py:140-201) as a generator: `batches`
         yields dicts of HOST tensors {'audio': (B, snd_size, 1)[, 'video', 'flow': (B, 1, H, W, 3)]} (pinned memory
         makes the copies asynchronous); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
@@ -272,12 +293,25 @@ class SptAudioGen(StageOps):
         PCIe bytes; they are prepared on the device, see forward_into) -- uint8 flow comes with 'flow_limits' (B, 2) float64.
         use_graph: replay each slot's forward as a CUDA graph (capture_graph); default: batches of at most 16 windows, where
         the host's launch rate, not the GPU, bounds the step (the reference's deploy loop feeds 10, its eval loop 16).  Host->device copies of step i+1 and the device->host copy of step i-1 run
-        on their own streams while step i computes, so the PCIe transfers hide behind the forward."""
+        on their own streams while step i computes, so the PCIe transfers hide behind the forward.
+        lanes: forwards in flight.  A forward is a serial chain of ~75 kernels of which the FCs, the decoder and the batch-norm
+        passes of the small feature maps fill a fraction of the 148 SMs; consecutive batches are independent (deploy.py:112-148),
+        so batch i+1 runs on its own stream, handle and workspace (a twin model with the same weights) and its kernels take the
+        SMs batch i leaves idle.  Results are bit-identical to one lane and are yielded in order."""
         if not self._weights_ready:
             raise RuntimeError('load_weights() must be called before inference_stream()')
         dev = self.device
+        lanes = max(1, int(lanes))
+        depth = max(int(depth), lanes + 1)
+        depth = (depth + lanes - 1) // lanes * lanes      # slot k always runs on lane k % lanes (its graph is captured there)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
+            models = self._lanes(lanes)
+            compute = [main] + [torch.cuda.Stream(device=dev) for _ in range(lanes - 1)]
+            start = torch.cuda.Event()
+            start.record(main)
+            for cs in compute[1:]:
+                cs.wait_event(start)                       # the lanes start after what the caller queued before this loop
             side = torch.cuda.Stream(device=dev)           # host -> device copies
             back = torch.cuda.Stream(device=dev)           # device -> host copies (own stream: a D2H waiting for its
                                                            # forward must not block the next step's H2D behind it)
@@ -304,44 +338,52 @@ class SptAudioGen(StageOps):
                 return sl['host']
 
             i = 0
-            for b in batches:
-                if len(slots) < depth:
-                    slots.append(make_slot(b))
-                idx = i % depth
-                if len(pending) == depth:                  # the slot we are about to reuse must have been consumed
+            try:
+                for b in batches:
+                    if len(slots) < depth:
+                        slots.append(make_slot(b))
+                    idx = i % depth
+                    if len(pending) == depth:                  # the slot we are about to reuse must have been consumed
+                        yield finish(pending.pop(0))
+                    sl = slots[idx]
+                    if sl['in'][AUDIO].shape != b[AUDIO].shape:
+                        raise ValueError('all batches of a stream must have the same shape')
+                    with torch.cuda.stream(side):
+                        side.wait_event(sl['free'])            # previous forward that read these inputs has finished
+                        for k, t in sl['in'].items():
+                            t.copy_(torch.as_tensor(b[k]), non_blocking=True)
+                        sl['in_ready'].record(side)
+                    m, cs = models[idx % lanes], compute[idx % lanes]
+                    with torch.cuda.stream(cs):
+                        cs.wait_event(sl['in_ready'])
+                        graph = use_graph if use_graph is not None else b[AUDIO].shape[0] <= 16
+                        if graph and sl['graph'] is None:
+                            try:                               # (warm-up forward + capture; this first use also produces the result)
+                                sl['graph'] = m.capture_graph(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'],
+                                                              sl['in'].get('flow_limits'))
+                            except RuntimeError as e:          # capture unsupported: stay eager, say so once
+                                import warnings
+                                warnings.warn('CUDA graph capture of the forward failed (%s); running eagerly' % e)
+                                sl['graph'] = False
+                        if graph and sl['graph']:
+                            sl['graph'].replay()
+                        else:
+                            m.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'], sl['in'].get('flow_limits'))
+                        sl['done'].record(cs)
+                        sl['free'].record(cs)
+                    with torch.cuda.stream(back):
+                        back.wait_event(sl['done'])
+                        sl['host'].copy_(sl['out'], non_blocking=True)
+                        sl['out_ready'].record(back)
+                    pending.append(idx)
+                    i += 1
+                while pending:
                     yield finish(pending.pop(0))
-                sl = slots[idx]
-                if sl['in'][AUDIO].shape != b[AUDIO].shape:
-                    raise ValueError('all batches of a stream must have the same shape')
-                with torch.cuda.stream(side):
-                    side.wait_event(sl['free'])            # previous forward that read these inputs has finished
-                    for k, t in sl['in'].items():
-                        t.copy_(torch.as_tensor(b[k]), non_blocking=True)
-                    sl['in_ready'].record(side)
-                main.wait_event(sl['in_ready'])
-                graph = use_graph if use_graph is not None else b[AUDIO].shape[0] <= 16
-                if graph and sl['graph'] is None:
-                    try:                                   # (warm-up forward + capture; this first use also produces the result)
-                        sl['graph'] = self.capture_graph(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'],
-                                                         sl['in'].get('flow_limits'))
-                    except RuntimeError as e:              # capture unsupported: stay eager, say so once
-                        import warnings
-                        warnings.warn('CUDA graph capture of the forward failed (%s); running eagerly' % e)
-                        sl['graph'] = False
-                if graph and sl['graph']:
-                    sl['graph'].replay()
-                else:
-                    self.forward_into(sl['in'][AUDIO], sl['in'].get(VIDEO), sl['in'].get(FLOW), sl['out'], sl['in'].get('flow_limits'))
-                sl['done'].record(main)
-                sl['free'].record(main)
-                with torch.cuda.stream(back):
-                    back.wait_event(sl['done'])
-                    sl['host'].copy_(sl['out'], non_blocking=True)
-                    sl['out_ready'].record(back)
-                pending.append(idx)
-                i += 1
-            while pending:
-                yield finish(pending.pop(0))
+            finally:
+                for cs in compute[1:]:                         # what the caller queues next follows every lane
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    main.wait_event(ev)
 
     def _view(self, name):
         lib = L.lib()

@@ -631,6 +631,17 @@ def test_inference_stream_matches_per_batch_calls():
         assert torch.equal(y, out.cpu())
         ref = m.inference_ops(b['audio'], video=b['video']).cpu()      # two-kernel inverse STFT + mixing: same values to rounding
         assert _rel(y, ref) < 2e-5
+    # forwards in flight (default: three lanes): one lane and two lanes, eager launches, return the same bits in the same order;
+    # options set on the model reach the lane twins
+    for lanes in (1, 2):
+        again = [y.clone() for y in m.inference_stream(iter(batches), lanes=lanes, use_graph=False)]
+        assert len(again) == 5 and all(torch.equal(x, y) for x, y in zip(outs, again)), lanes
+    m.set_option('precision', 'fp32')
+    exact = [y.clone() for y in m.inference_stream(iter(batches), use_graph=False)]
+    for b, y in zip(batches, exact):
+        m.forward_into(b['audio'].cuda(), b['video'].cuda(), None, out)
+        assert _rel(y, out.cpu()) < 1e-5                             # (the FFMA path sums its split-K pieces with float atomics)
+    assert not torch.equal(exact[1], outs[1])                        # (the fp32 path really ran on the twin)
 
 
 def test_cuda_graph_replay_equals_eager_forward():
