@@ -217,6 +217,29 @@ int sag_mel_lsd(const float* pred, const float* gt, int batch, int t, int audio_
 int sag_emd_hat(const double* first, const double* second, int n, const double* dist, double extra_mass_penalty, int count,
                 double* out);
 
+/* ---- JPEG frame decode ------------------------------------------------------------------------------
+ * The reference's feeder reads every video / flow frame with scipy.misc.imread (feeder.py:120-127): PIL over libjpeg with
+ * its default settings (JDCT_ISLOW inverse DCT, fancy chroma upsampling).  These entry points replace that call for a batch
+ * of frames: the entropy-coded segments are decoded on the host (a pool of `threads` threads, one file per task) into pinned
+ * staging, and dequantisation + inverse DCT + upsampling + YCbCr->RGB run as CUDA kernels that write the uint8
+ * (n, height, width, 3) frames sag_forward_frames ingests.  Bit-identical to PIL's decode.  Baseline sequential files
+ * (SOF0), 8 bit, 1 or 3 components in one interleaved scan, chroma sampled 1x1 / 2x1 / 2x2, restart intervals; anything else
+ * fails with SAG_EUNSUPPORTED. */
+typedef struct sag_jpeg sag_jpeg;
+/* frame geometry of a file in host memory: h_samp / v_samp = the largest sampling factors (2,2 for 4:2:0) */
+int sag_jpeg_info(const void* host_file, size_t size, int* width, int* height, int* components, int* h_samp, int* v_samp);
+/* host only: the quantised coefficients of a file, component after component, each a (blocks_high, blocks_wide, 64) int16
+ * array in natural (row-major) order on a block grid of whole MCUs, plus the components' quantisers (3 x 64, natural order) */
+int sag_jpeg_coefficients(const void* host_file, size_t size, int16_t* host_coef, size_t capacity, int* blocks_wide, int* blocks_high,
+                          uint16_t* host_qt);
+/* a decoder for batches of at most max_frames frames of height x width pixels on the current device (owns pinned staging
+ * and device scratch; not thread safe) */
+int sag_jpeg_create(sag_jpeg** dec, int max_frames, int height, int width);
+void sag_jpeg_destroy(sag_jpeg* dec);
+/* n files in host memory -> frames (device, uint8, (n, height, width, 3) RGB) on `stream`.  Returns once the kernels are
+ * queued; the files may be released on return.  threads <= 0: one per host core (at most 32). */
+int sag_jpeg_decode(sag_jpeg* dec, const void* const* host_files, const size_t* sizes, int n, uint8_t* frames, int threads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

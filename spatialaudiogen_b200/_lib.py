@@ -83,6 +83,11 @@ PROTOTYPES = {
     'sag_sh_rms': (_I, [_P, _I, _I, _F, _P, _P]),
     'sag_mel_lsd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     'sag_emd_hat': (_I, [_P, _P, _I, _P, C.c_double, _I, _P]),
+    'sag_jpeg_info': (_I, [_P, _S, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    'sag_jpeg_coefficients': (_I, [_P, _S, _P, _S, C.POINTER(_I), C.POINTER(_I), _P]),
+    'sag_jpeg_create': (_I, [C.POINTER(_P), _I, _I, _I]),
+    'sag_jpeg_destroy': (None, [_P]),
+    'sag_jpeg_decode': (_I, [_P, C.POINTER(_P), C.POINTER(_S), _I, _P, _I, _P]),
 }
 
 _lib = None

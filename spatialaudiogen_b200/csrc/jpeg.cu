@@ -1,0 +1,608 @@
+// Baseline JPEG frame decode for the readers: the reference reads every video / flow frame with
+// scipy.misc.imread (feeder.py:120-127) = PIL over libjpeg with its default settings (JDCT_ISLOW, fancy upsampling).
+//
+//   host   : marker parsing + Huffman decoding of the entropy-coded segment (a serial bit stream per file; files of a
+//            batch are decoded by a small pool of threads) straight into pinned staging -- quantised coefficients, 2 bytes
+//            each, the same number of bytes per 4:2:0 frame as its RGB pixels
+//   device : jpeg_idct_kernel        dequantise + 8x8 inverse DCT   (libjpeg jidctint.c jpeg_idct_islow, bit-exact)
+//            jpeg_rgb_kernel         chroma upsampling (jdsample.c h2v2 / h2v1 fancy triangle filters, edge rows replicated
+//                                    like jdmainct.c) + YCbCr -> RGB (jdcolor.c 16-bit fixed point), written as the uint8
+//                                    (n, H, W, 3) frames that sag_forward_frames ingests
+// Results are bit-identical to PIL's decode (tests/test_jpeg.py; oracle/jpeg_oracle.py restates the same algorithms).
+// Scope: SOF0, 8 bit, 1 or 3 components in one interleaved scan, chroma sampled 1x1 / 2x1 / 2x2, restart intervals.
+#include "common.cuh"
+#include <atomic>
+#include <thread>
+#include <algorithm>
+
+namespace sag {
+namespace {
+
+const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HuffTable {            // canonical code of one DHT table (jdhuff.c jpeg_make_d_derived_tbl)
+  bool present = false;
+  uint8_t symbols[256];
+  int32_t maxcode[18];        // largest code of each length (-1: none)
+  int32_t valoffset[17];      // symbol index of the first code of each length minus that code
+  uint16_t look[512];         // 9-bit lookahead: (length << 8) | symbol, 0 = longer than 9 bits
+};
+
+struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0; };
+
+struct Header {
+  int width = 0, height = 0, ncomp = 0;
+  Component comp[3];
+  uint16_t qt[4][64];          // natural order
+  bool qt_present[4] = {false, false, false, false};
+  HuffTable dc[4], ac[4];
+  int restart_interval = 0;
+  const uint8_t* ecs = nullptr;   // entropy-coded segment
+  size_t ecs_size = 0;
+  int hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
+  int bw[3], bh[3];            // block grid of each component (whole MCUs)
+};
+
+int build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int nsym) {
+  t.present = true;
+  memcpy(t.symbols, symbols, nsym);
+  memset(t.look, 0, sizeof(t.look));
+  int code = 0, k = 0;
+  for (int len = 1; len <= 16; ++len) {
+    t.valoffset[len] = k - code;
+    for (int i = 0; i < counts[len - 1]; ++i, ++code, ++k) {
+      if (len <= 9) {
+        const int lo = code << (9 - len);
+        for (int f = 0; f < (1 << (9 - len)); ++f) t.look[lo + f] = (uint16_t)((len << 8) | symbols[k]);
+      }
+    }
+    t.maxcode[len] = counts[len - 1] ? code - 1 : -1;
+    if (code > (1 << len)) return SAG_EINVAL;
+    code <<= 1;
+  }
+  t.maxcode[17] = 0x7fffffff;
+  return SAG_OK;
+}
+
+int parse_header(const uint8_t* d, size_t n, Header* h) {
+  SAG_REQUIRE(n >= 4 && d[0] == 0xFF && d[1] == 0xD8, SAG_EINVAL, "jpeg: not a JPEG file (no SOI marker)");
+  size_t p = 2;
+  bool have_sof = false;
+  for (;;) {
+    while (p < n && d[p] != 0xFF) ++p;
+    while (p < n && d[p] == 0xFF) ++p;
+    SAG_REQUIRE(p < n, SAG_EINVAL, "jpeg: file ends before the scan");
+    const int m = d[p++];
+    if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+    SAG_REQUIRE(m != 0xD9, SAG_EINVAL, "jpeg: EOI before the scan");
+    SAG_REQUIRE(p + 2 <= n, SAG_EINVAL, "jpeg: truncated marker segment");
+    const size_t len = ((size_t)d[p] << 8) | d[p + 1];
+    SAG_REQUIRE(len >= 2 && p + len <= n, SAG_EINVAL, "jpeg: truncated marker segment");
+    const uint8_t* s = d + p + 2;
+    const size_t sl = len - 2;
+    p += len;
+    if (m == 0xDB) {
+      size_t q = 0;
+      while (q < sl) {
+        const int pq = s[q] >> 4, tq = s[q] & 15;
+        SAG_REQUIRE(tq < 4 && q + 1 + (pq ? 128 : 64) <= sl, SAG_EINVAL, "jpeg: bad DQT segment");
+        for (int i = 0; i < 64; ++i)
+          h->qt[tq][kZigzag[i]] = pq ? (uint16_t)((s[q + 1 + 2 * i] << 8) | s[q + 2 + 2 * i]) : s[q + 1 + i];
+        h->qt_present[tq] = true;
+        q += 1 + (pq ? 128 : 64);
+      }
+    } else if (m == 0xC0 || m == 0xC1) {
+      SAG_REQUIRE(sl >= 6 && s[0] == 8, SAG_EUNSUPPORTED, "jpeg: only 8-bit samples are supported");
+      h->height = (s[1] << 8) | s[2];
+      h->width = (s[3] << 8) | s[4];
+      h->ncomp = s[5];
+      SAG_REQUIRE((h->ncomp == 1 || h->ncomp == 3) && sl >= (size_t)6 + 3 * h->ncomp, SAG_EUNSUPPORTED,
+                  "jpeg: %d components (1 or 3 supported)", h->ncomp);
+      for (int i = 0; i < h->ncomp; ++i) {
+        h->comp[i].id = s[6 + 3 * i];
+        h->comp[i].h = s[7 + 3 * i] >> 4;
+        h->comp[i].v = s[7 + 3 * i] & 15;
+        h->comp[i].tq = s[8 + 3 * i];
+        SAG_REQUIRE(h->comp[i].tq < 4 && h->comp[i].h >= 1 && h->comp[i].v >= 1, SAG_EINVAL, "jpeg: bad SOF segment");
+      }
+      have_sof = true;
+    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      SAG_REQUIRE(false, SAG_EUNSUPPORTED, "jpeg: only baseline sequential files (SOF0) are supported, found SOF%d", m - 0xC0);
+    } else if (m == 0xC4) {
+      size_t q = 0;
+      while (q < sl) {
+        SAG_REQUIRE(q + 17 <= sl, SAG_EINVAL, "jpeg: bad DHT segment");
+        const int cls = s[q] >> 4, tid = s[q] & 15;
+        int ns = 0;
+        for (int i = 0; i < 16; ++i) ns += s[q + 1 + i];
+        SAG_REQUIRE(cls < 2 && tid < 4 && ns <= 256 && q + 17 + ns <= sl, SAG_EINVAL, "jpeg: bad DHT segment");
+        SAG_REQUIRE(build_table(cls ? h->ac[tid] : h->dc[tid], s + q + 1, s + q + 17, ns) == SAG_OK, SAG_EINVAL,
+                    "jpeg: inconsistent Huffman table");
+        q += 17 + ns;
+      }
+    } else if (m == 0xDD) {
+      SAG_REQUIRE(sl >= 2, SAG_EINVAL, "jpeg: bad DRI segment");
+      h->restart_interval = (s[0] << 8) | s[1];
+    } else if (m == 0xDA) {
+      SAG_REQUIRE(have_sof, SAG_EINVAL, "jpeg: scan before the frame header");
+      SAG_REQUIRE(sl >= 1 && s[0] == h->ncomp && sl >= (size_t)1 + 2 * h->ncomp, SAG_EUNSUPPORTED,
+                  "jpeg: only one interleaved scan holding every component is supported");
+      for (int i = 0; i < h->ncomp; ++i) {
+        SAG_REQUIRE(s[1 + 2 * i] == h->comp[i].id, SAG_EUNSUPPORTED, "jpeg: scan components out of frame order");
+        h->comp[i].td = s[2 + 2 * i] >> 4;
+        h->comp[i].ta = s[2 + 2 * i] & 15;
+        SAG_REQUIRE(h->comp[i].td < 4 && h->comp[i].ta < 4 && h->dc[h->comp[i].td].present && h->ac[h->comp[i].ta].present &&
+                        h->qt_present[h->comp[i].tq],
+                    SAG_EINVAL, "jpeg: scan refers to a table the file does not define");
+      }
+      h->ecs = d + p;
+      h->ecs_size = n - p;
+      break;
+    }
+  }
+  SAG_REQUIRE(h->width > 0 && h->height > 0, SAG_EINVAL, "jpeg: empty image");
+  if (h->ncomp == 1) h->comp[0].h = h->comp[0].v = 1;          // a one-component scan is never interleaved: MCU = one block
+  h->hmax = h->vmax = 1;
+  for (int i = 0; i < h->ncomp; ++i) { h->hmax = std::max(h->hmax, h->comp[i].h); h->vmax = std::max(h->vmax, h->comp[i].v); }
+  for (int i = 0; i < h->ncomp; ++i) {
+    const int rh = h->hmax / h->comp[i].h, rv = h->vmax / h->comp[i].v;
+    const bool ok = rh * h->comp[i].h == h->hmax && rv * h->comp[i].v == h->vmax &&
+                    ((rh == 1 && rv == 1) || (rh == 2 && rv == 1) || (rh == 2 && rv == 2));
+    SAG_REQUIRE(ok && h->comp[i].h <= 2 && h->comp[i].v <= 2, SAG_EUNSUPPORTED,
+                "jpeg: component %d sampled %dx%d of %dx%d (supported: full, 2:1 horizontal, 2:1 both)", i, h->comp[i].h, h->comp[i].v,
+                h->hmax, h->vmax);
+    if (rh == 2) SAG_REQUIRE((h->width * h->comp[i].h + h->hmax - 1) / h->hmax >= 2, SAG_EUNSUPPORTED, "jpeg: image too narrow");
+  }
+  h->mcux = (h->width + 8 * h->hmax - 1) / (8 * h->hmax);
+  h->mcuy = (h->height + 8 * h->vmax - 1) / (8 * h->vmax);
+  for (int i = 0; i < h->ncomp; ++i) { h->bw[i] = h->mcux * h->comp[i].h; h->bh[i] = h->mcuy * h->comp[i].v; }
+  return SAG_OK;
+}
+
+// ---- entropy decoder (jdhuff.c decode_mcu) ---------------------------------------------------------------------------
+struct BitReader {
+  const uint8_t* d;
+  size_t n, p = 0;
+  uint64_t acc = 0;
+  int bits = 0;
+  BitReader(const uint8_t* d_, size_t n_) : d(d_), n(n_) {}
+  inline void fill() {                       // top up to at least 32 valid bits; past a marker the stream reads as zeros
+    while (bits <= 56) {
+      uint64_t b = 0;
+      if (p < n) {
+        b = d[p];
+        if (b == 0xFF) {
+          const int nxt = p + 1 < n ? d[p + 1] : 0xD9;
+          if (nxt == 0) p += 2; else b = 0;  // stuffed byte / marker: stay on it
+        } else {
+          ++p;
+        }
+      }
+      acc = (acc << 8) | b;
+      bits += 8;
+    }
+  }
+  inline uint32_t peek(int k) { return (uint32_t)((acc >> (bits - k)) & ((1u << k) - 1)); }
+  inline void skip(int k) { bits -= k; }
+  inline uint32_t get(int k) { const uint32_t v = peek(k); bits -= k; return v; }
+  void restart() {                           // discard the partial byte, skip the RSTn marker
+    acc = 0;
+    bits = 0;
+    while (p + 1 < n && !(d[p] == 0xFF && d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7)) ++p;
+    p += 2;
+  }
+};
+
+inline int huff_decode(BitReader& br, const HuffTable& t) {
+  if (br.bits < 32) br.fill();
+  const uint16_t e = t.look[br.peek(9)];
+  if (e) { br.skip(e >> 8); return e & 255; }
+  int len = 10;
+  int32_t code = (int32_t)br.peek(10);
+  while (len <= 16 && code > t.maxcode[len]) { ++len; code = (int32_t)br.peek(len); }
+  if (len > 16) return -1;
+  br.skip(len);
+  return t.symbols[(code + t.valoffset[len]) & 255];
+}
+
+inline int extend(int r, int s) { return r < (1 << (s - 1)) ? r - (1 << s) + 1 : r; }   // jdhuff.h HUFF_EXTEND
+
+// coef[c]: bh[c] x bw[c] blocks of 64 int16 in natural order, zero-initialised by the caller
+int decode_scan(const Header& h, int16_t* const coef[3]) {
+  BitReader br(h.ecs, h.ecs_size);
+  int pred[3] = {0, 0, 0};
+  int left = h.restart_interval;
+  for (int my = 0; my < h.mcuy; ++my) {
+    for (int mx = 0; mx < h.mcux; ++mx) {
+      if (h.restart_interval && left == 0) {
+        br.restart();
+        pred[0] = pred[1] = pred[2] = 0;
+        left = h.restart_interval;
+      }
+      for (int c = 0; c < h.ncomp; ++c) {
+        const Component& cp = h.comp[c];
+        const HuffTable& dc = h.dc[cp.td];
+        const HuffTable& ac = h.ac[cp.ta];
+        for (int by = 0; by < cp.v; ++by) {
+          for (int bx = 0; bx < cp.h; ++bx) {
+            int16_t* blk = coef[c] + ((size_t)(my * cp.v + by) * h.bw[c] + (mx * cp.h + bx)) * 64;
+            int s = huff_decode(br, dc);
+            if (s < 0 || s > 15) { set_error("jpeg: corrupt entropy-coded data (DC)"); return SAG_EINVAL; }
+            if (s) { br.fill(); pred[c] += extend((int)br.get(s), s); }
+            blk[0] = (int16_t)pred[c];
+            for (int k = 1; k < 64; ++k) {
+              const int rs = huff_decode(br, ac);
+              if (rs < 0) { set_error("jpeg: corrupt entropy-coded data (AC)"); return SAG_EINVAL; }
+              const int r = rs >> 4;
+              s = rs & 15;
+              if (s) {
+                k += r;
+                if (br.bits < 32) br.fill();
+                blk[kZigzag[k & 63]] = (int16_t)extend((int)br.get(s), s);
+              } else if (r == 15) {
+                k += 15;
+              } else {
+                break;
+              }
+            }
+          }
+        }
+      }
+      --left;
+    }
+  }
+  return SAG_OK;
+}
+
+// ---- device side --------------------------------------------------------------------------------------------------------
+struct JpegImage {            // one frame of a batch (device copy)
+  int ncomp, hmax, vmax;
+  int h[3], v[3], bw[3], bh[3];
+  long long coef_off[3];      // int16 elements into the coefficient buffer
+  long long plane_off[3];     // bytes into the plane buffer; row stride bw * 8
+  long long block_base[4];    // running count of the blocks of components 0..2 (block_base[3] = all)
+};
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// one pass of jpeg_idct_islow over eight values (jidctint.c; CONST_BITS 13)
+__device__ __forceinline__ void islow_1d(const int* in, int* out, int shift) {
+  int z2 = in[2], z3 = in[6];
+  int z1 = (z2 + z3) * 4433;
+  int tmp2 = z1 + z3 * (-15137);
+  int tmp3 = z1 + z2 * 6270;
+  z2 = in[0];
+  z3 = in[4];
+  int tmp0 = (z2 + z3) << 13, tmp1 = (z2 - z3) << 13;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = in[7];
+  tmp1 = in[5];
+  tmp2 = in[3];
+  tmp3 = in[1];
+  z1 = tmp0 + tmp3;
+  z2 = tmp1 + tmp2;
+  z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * 9633;
+  tmp0 *= 2446;
+  tmp1 *= 16819;
+  tmp2 *= 25172;
+  tmp3 *= 12299;
+  z1 *= -7373;
+  z2 *= -20995;
+  z3 = z3 * (-16069) + z5;
+  z4 = z4 * (-3196) + z5;
+  tmp0 += z1 + z3;
+  tmp1 += z2 + z4;
+  tmp2 += z2 + z3;
+  tmp3 += z1 + z4;
+  out[0] = descale(tmp10 + tmp3, shift);
+  out[7] = descale(tmp10 - tmp3, shift);
+  out[1] = descale(tmp11 + tmp2, shift);
+  out[6] = descale(tmp11 - tmp2, shift);
+  out[2] = descale(tmp12 + tmp1, shift);
+  out[5] = descale(tmp12 - tmp1, shift);
+  out[3] = descale(tmp13 + tmp0, shift);
+  out[4] = descale(tmp13 - tmp0, shift);
+}
+
+// grid (ceil(blocks of the largest frame / 32), n): 8 threads per 8x8 block -- thread j transforms column j, then row j
+constexpr int kIdctBlocksPerCta = 32;
+__global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImage* __restrict__ images, const int16_t* __restrict__ coef,
+                                                        const uint16_t* __restrict__ qt, uint8_t* __restrict__ planes) {
+  __shared__ int ws[kIdctBlocksPerCta][64 + 8];        // (+8: rows of 9 words, conflict-free column writes)
+  const JpegImage& im = images[blockIdx.y];
+  const int lb = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const long long b = (long long)blockIdx.x * kIdctBlocksPerCta + lb;
+  const bool live = b < im.block_base[3];
+  int c = 0;
+  if (live) { while (b >= im.block_base[c + 1]) ++c; }
+  const long long bi = live ? b - im.block_base[c] : 0;
+  int v[8], o[8];
+  if (live) {
+    const int16_t* src = coef + im.coef_off[c] + bi * 64;
+    const uint16_t* q = qt + ((long long)blockIdx.y * 3 + c) * 64;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = (int)src[r * 8 + j] * (int)q[r * 8 + j];       // column j, dequantised
+    islow_1d(v, o, 13 - 2);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ws[lb][r * 9 + j] = o[r];
+  }
+  __syncthreads();
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ws[lb][j * 9 + k];                              // row j of the workspace
+    islow_1d(v, o, 13 + 2 + 3);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int x = (((o[k] & 1023) ^ 512) - 512) + 128;                                     // range_limit[x & RANGE_MASK]
+      x = min(max(x, 0), 255);
+      if (k < 4) lo |= (uint32_t)x << (8 * k); else hi |= (uint32_t)x << (8 * (k - 4));
+    }
+    const int bx = (int)(bi % im.bw[c]), by = (int)(bi / im.bw[c]);
+    uint8_t* dst = planes + im.plane_off[c] + ((long long)(by * 8 + j) * im.bw[c] + bx) * 8;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  }
+}
+
+// sample of component c at full resolution (jdsample.c fancy upsamplers)
+__device__ __forceinline__ int jpeg_sample(const JpegImage& im, const uint8_t* __restrict__ planes, int c, int x, int y, int width,
+                                           int height) {
+  const uint8_t* p = planes + im.plane_off[c];
+  const int stride = im.bw[c] * 8;
+  const int rh = im.hmax / im.h[c], rv = im.vmax / im.v[c];
+  if (rh == 1) return p[(long long)y * stride + x];
+  const int dw = (width * im.h[c] + im.hmax - 1) / im.hmax;     // downsampled_width: the real samples of a row
+  const int cx = x >> 1;
+  if (rv == 1) {                                                // h2v1_fancy_upsample
+    const uint8_t* r = p + (long long)y * stride;
+    const int s = r[cx];
+    if (x & 1) return cx == dw - 1 ? s : (3 * s + r[cx + 1] + 2) >> 2;
+    return cx == 0 ? s : (3 * s + r[cx - 1] + 1) >> 2;
+  }
+  const int dh = (height * im.v[c] + im.vmax - 1) / im.vmax;    // h2v2_fancy_upsample
+  const int cy = y >> 1;
+  const int ny = (y & 1) ? min(cy + 1, dh - 1) : max(cy - 1, 0);
+  const uint8_t* r0 = p + (long long)cy * stride;
+  const uint8_t* r1 = p + (long long)ny * stride;
+  const int s = 3 * r0[cx] + r1[cx];
+  if (x & 1) return cx == dw - 1 ? (4 * s + 7) >> 4 : (3 * s + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+  return cx == 0 ? (4 * s + 8) >> 4 : (3 * s + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
+}
+
+// grid (ceil(W / 4 / 64), H, n): four pixels (12 bytes) per thread
+__global__ void __launch_bounds__(64) jpeg_rgb_kernel(const JpegImage* __restrict__ images, const uint8_t* __restrict__ planes, int width,
+                                                      int height, uint8_t* __restrict__ frames) {
+  const JpegImage& im = images[blockIdx.z];
+  const int y = blockIdx.y;
+  const int x0 = (blockIdx.x * 64 + threadIdx.x) * 4;
+  if (x0 >= width) return;
+  uint8_t px[12];
+  const int cnt = min(4, width - x0);
+  for (int i = 0; i < cnt; ++i) {
+    const int x = x0 + i;
+    const int yy = jpeg_sample(im, planes, 0, x, y, width, height);
+    int r = yy, g = yy, b = yy;
+    if (im.ncomp == 3) {                                        // jdcolor.c ycc_rgb_convert (SCALEBITS 16)
+      const int cb = jpeg_sample(im, planes, 1, x, y, width, height) - 128;
+      const int cr = jpeg_sample(im, planes, 2, x, y, width, height) - 128;
+      r = yy + ((91881 * cr + 32768) >> 16);
+      g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+      b = yy + ((116130 * cb + 32768) >> 16);
+    }
+    px[3 * i + 0] = (uint8_t)min(max(r, 0), 255);
+    px[3 * i + 1] = (uint8_t)min(max(g, 0), 255);
+    px[3 * i + 2] = (uint8_t)min(max(b, 0), 255);
+  }
+  uint8_t* dst = frames + (((long long)blockIdx.z * height + y) * width + x0) * 3;
+  if (cnt == 4 && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0)) {
+    uint32_t w[3];
+    memcpy(w, px, 12);
+    reinterpret_cast<uint32_t*>(dst)[0] = w[0];
+    reinterpret_cast<uint32_t*>(dst)[1] = w[1];
+    reinterpret_cast<uint32_t*>(dst)[2] = w[2];
+  } else {
+    for (int i = 0; i < 3 * cnt; ++i) dst[i] = px[i];
+  }
+}
+
+}  // namespace
+}  // namespace sag
+
+struct sag_jpeg {
+  int max_frames = 0, height = 0, width = 0, device = 0;
+  size_t coef_cap = 0, plane_cap = 0;      // per frame: int16 elements / bytes (4:4:4 worst case, whole 16x16 MCUs)
+  int16_t* h_coef = nullptr;               // pinned staging
+  uint16_t* h_qt = nullptr;
+  sag::JpegImage* h_img = nullptr;
+  int16_t* d_coef = nullptr;
+  uint16_t* d_qt = nullptr;
+  sag::JpegImage* d_img = nullptr;
+  uint8_t* d_planes = nullptr;
+  cudaEvent_t staged = nullptr;            // the previous call's host -> device copies have left the staging buffers
+  bool staged_pending = false;
+};
+
+using namespace sag;
+
+extern "C" {
+
+int sag_jpeg_info(const void* host_file, size_t size, int* width, int* height, int* components, int* h_samp, int* v_samp) {
+  SAG_REQUIRE(host_file != nullptr, SAG_EINVAL, "jpeg: null file");
+  Header* h = new Header();
+  const int rc = parse_header(static_cast<const uint8_t*>(host_file), size, h);
+  if (rc == SAG_OK) {
+    if (width) *width = h->width;
+    if (height) *height = h->height;
+    if (components) *components = h->ncomp;
+    if (h_samp) *h_samp = h->hmax;
+    if (v_samp) *v_samp = h->vmax;
+  }
+  delete h;
+  return rc;
+}
+
+int sag_jpeg_coefficients(const void* host_file, size_t size, int16_t* host_coef, size_t capacity, int* blocks_wide, int* blocks_high,
+                          uint16_t* host_qt) {
+  SAG_REQUIRE(host_file != nullptr && host_coef != nullptr, SAG_EINVAL, "jpeg: null argument");
+  Header* h = new Header();
+  int rc = parse_header(static_cast<const uint8_t*>(host_file), size, h);
+  if (rc == SAG_OK) {
+    size_t need = 0;
+    for (int c = 0; c < h->ncomp; ++c) need += (size_t)h->bw[c] * h->bh[c] * 64;
+    if (need > capacity) {
+      set_error("jpeg: coefficient buffer holds %zu values, the file needs %zu", capacity, need);
+      rc = SAG_ENOMEM;
+    } else {
+      memset(host_coef, 0, need * sizeof(int16_t));
+      int16_t* cp[3] = {nullptr, nullptr, nullptr};
+      size_t off = 0;
+      for (int c = 0; c < h->ncomp; ++c) { cp[c] = host_coef + off; off += (size_t)h->bw[c] * h->bh[c] * 64; }
+      rc = decode_scan(*h, cp);
+      for (int c = 0; c < 3; ++c) {
+        if (blocks_wide) blocks_wide[c] = c < h->ncomp ? h->bw[c] : 0;
+        if (blocks_high) blocks_high[c] = c < h->ncomp ? h->bh[c] : 0;
+        if (host_qt && c < h->ncomp) memcpy(host_qt + 64 * c, h->qt[h->comp[c].tq], 128);
+      }
+    }
+  }
+  delete h;
+  return rc;
+}
+
+int sag_jpeg_create(sag_jpeg** out, int max_frames, int height, int width) {
+  SAG_REQUIRE(out != nullptr && max_frames > 0 && height > 0 && width > 0 && height < 65536 && width < 65536, SAG_EINVAL,
+              "jpeg: bad decoder geometry");
+  sag_jpeg* d = new sag_jpeg();
+  d->max_frames = max_frames;
+  d->height = height;
+  d->width = width;
+  const size_t hp = ((size_t)height + 15) / 16 * 16, wp = ((size_t)width + 15) / 16 * 16;
+  d->coef_cap = 3 * hp * wp;
+  d->plane_cap = 3 * hp * wp;
+  *out = d;
+  cudaError_t e = cudaGetDevice(&d->device);
+  if (e == cudaSuccess) e = cudaHostAlloc(&d->h_coef, d->coef_cap * max_frames * sizeof(int16_t), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&d->h_qt, (size_t)max_frames * 3 * 64 * sizeof(uint16_t), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&d->h_img, (size_t)max_frames * sizeof(JpegImage), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_coef, d->coef_cap * max_frames * sizeof(int16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_qt, (size_t)max_frames * 3 * 64 * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_img, (size_t)max_frames * sizeof(JpegImage));
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_planes, d->plane_cap * max_frames);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->staged, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    set_error("jpeg: %s while creating the decoder: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    sag_jpeg_destroy(d);
+    *out = nullptr;
+    return SAG_ECUDA;
+  }
+  return SAG_OK;
+}
+
+void sag_jpeg_destroy(sag_jpeg* d) {
+  if (d == nullptr) return;
+  if (d->staged) { cudaEventSynchronize(d->staged); cudaEventDestroy(d->staged); }
+  cudaFreeHost(d->h_coef);
+  cudaFreeHost(d->h_qt);
+  cudaFreeHost(d->h_img);
+  cudaFree(d->d_coef);
+  cudaFree(d->d_qt);
+  cudaFree(d->d_img);
+  cudaFree(d->d_planes);
+  delete d;
+}
+
+int sag_jpeg_decode(sag_jpeg* d, const void* const* host_files, const size_t* sizes, int n, uint8_t* frames, int threads, void* stream) {
+  SAG_REQUIRE(d != nullptr && host_files != nullptr && sizes != nullptr && frames != nullptr, SAG_EINVAL, "jpeg: null argument");
+  SAG_REQUIRE(n > 0 && n <= d->max_frames, SAG_EINVAL, "jpeg: %d frames, the decoder was created for at most %d", n, d->max_frames);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->staged_pending) {                                     // the staging buffers are about to be overwritten
+    SAG_CHECK_CUDA(cudaEventSynchronize(d->staged));
+    d->staged_pending = false;
+  }
+  // headers (serial: microseconds), then the layout of the batch: frames packed back to back
+  std::vector<Header> hdr(n);
+  size_t coef_total = 0, plane_total = 0;
+  long long max_blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    SAG_REQUIRE(host_files[i] != nullptr, SAG_EINVAL, "jpeg: file %d is null", i);
+    SAG_TRY(parse_header(static_cast<const uint8_t*>(host_files[i]), sizes[i], &hdr[i]));
+    SAG_REQUIRE(hdr[i].width == d->width && hdr[i].height == d->height, SAG_EINVAL, "jpeg: file %d is %dx%d, the decoder reads %dx%d frames",
+                i, hdr[i].width, hdr[i].height, d->width, d->height);
+    JpegImage& im = d->h_img[i];
+    memset(&im, 0, sizeof(im));
+    im.ncomp = hdr[i].ncomp;
+    im.hmax = hdr[i].hmax;
+    im.vmax = hdr[i].vmax;
+    long long blocks = 0;
+    for (int c = 0; c < 3; ++c) {
+      im.block_base[c] = blocks;
+      if (c < hdr[i].ncomp) {
+        im.h[c] = hdr[i].comp[c].h;
+        im.v[c] = hdr[i].comp[c].v;
+        im.bw[c] = hdr[i].bw[c];
+        im.bh[c] = hdr[i].bh[c];
+        im.coef_off[c] = (long long)coef_total;
+        im.plane_off[c] = (long long)plane_total;
+        const size_t nb = (size_t)im.bw[c] * im.bh[c];
+        coef_total += nb * 64;
+        plane_total += nb * 64;
+        blocks += (long long)nb;
+        memcpy(d->h_qt + ((size_t)i * 3 + c) * 64, hdr[i].qt[hdr[i].comp[c].tq], 128);
+      } else {
+        im.h[c] = im.v[c] = 1;
+      }
+    }
+    im.block_base[3] = blocks;
+    max_blocks = std::max(max_blocks, blocks);
+  }
+  SAG_REQUIRE(coef_total <= d->coef_cap * (size_t)d->max_frames, SAG_ENOMEM, "jpeg: coefficient staging too small");
+  // entropy decoding: one file per task, a few host threads
+  std::atomic<int> next(0), failed(0);
+  std::string first_error;
+  std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+  auto work = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) break;
+      const JpegImage& im = d->h_img[i];
+      int16_t* cp[3] = {nullptr, nullptr, nullptr};
+      size_t cnt = 0;
+      for (int c = 0; c < im.ncomp; ++c) { cp[c] = d->h_coef + im.coef_off[c]; cnt += (size_t)im.bw[c] * im.bh[c] * 64; }
+      memset(cp[0], 0, cnt * sizeof(int16_t));                  // (a frame's components are contiguous)
+      if (decode_scan(hdr[i], cp) != SAG_OK) {
+        failed.store(1);
+        while (err_lock.test_and_set()) {}
+        if (first_error.empty()) first_error = "file " + std::to_string(i) + ": " + sag_last_error();
+        err_lock.clear();
+      }
+    }
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(std::min(nt, n), 32));
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt - 1; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  }
+  SAG_REQUIRE(!failed.load(), SAG_EINVAL, "%s", first_error.c_str());
+  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_coef, d->h_coef, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_qt, d->h_qt, (size_t)n * 3 * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_img, d->h_img, (size_t)n * sizeof(JpegImage), cudaMemcpyHostToDevice, st));
+  SAG_CHECK_CUDA(cudaEventRecord(d->staged, st));
+  d->staged_pending = true;
+  jpeg_idct_kernel<<<dim3((unsigned)((max_blocks + kIdctBlocksPerCta - 1) / kIdctBlocksPerCta), n), 256, 0, st>>>(d->d_img, d->d_coef, d->d_qt,
+                                                                                                                 d->d_planes);
+  SAG_LAUNCH_CHECK();
+  jpeg_rgb_kernel<<<dim3((unsigned)((d->width + 255) / 256), d->height, n), 64, 0, st>>>(d->d_img, d->d_planes, d->width, d->height, frames);
+  SAG_LAUNCH_CHECK();
+  return SAG_OK;
+}
+
+}  // extern "C"

@@ -90,18 +90,20 @@ def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
     return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
 
 
-def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True):
+def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True, gpu_jpeg=True):
     """The evaluation feeder (reference feeder.py:366-420 with for_eval=True, eval.py:43-60): every `folders[i]` (a per-video
     folder, see readers.py) is read in order with the eval schedule -- every 10th entry of audio_pow.lst, no shuffling, no
     rotations, silent chunks kept -- and the samples are grouped into batches of `batch_size` like `dequeue_many`.
     channel_masks: {video id: (4,) mask} from meta/audio_layouts.txt (feeder.py:312-314), default all ones.  The last, short
     batch is dropped by default, like the reference (its `dequeue_many` never returns it, feeder.py:412-419): the visual towers use
     batch statistics, so rows computed from a smaller batch correspond to nothing the reference computes.  drop_remainder=False
-    yields it anyway (its dict carries 'short_batch': True)."""
+    yields it anyway (its dict carries 'short_batch': True).  gpu_jpeg: the frames' jpg files are decoded on the GPU, a batch at a
+    time (readers.JpegDecoder: bit-identical to the PIL decode of gpu_jpeg=False; baseline files only -- others raise)."""
     from . import readers, myutils
     from .definitions import VIDEO, FLOW
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
     pending = []
+    decoders = {}
 
     def flush(items):
         # frames travel as decoded (uint8; flow with its per-frame limits) and are prepared by the ingest kernel on the device
@@ -109,7 +111,14 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
              'ambix': torch.as_tensor(np.stack([c['ambix'] for c in items]).astype(np.float32)).to(dev),
              'mask': torch.as_tensor(np.stack([c['mask'] for c in items]).astype(np.float32)).to(dev)}
         for k in (VIDEO, FLOW):
-            if k in params.encoders:
+            if k in params.encoders and gpu_jpeg:
+                files = [f for c in items for f in c[k]]
+                if k not in decoders:
+                    h, w = readers.jpeg_info(files[0])[:2]
+                    decoders[k] = readers.JpegDecoder(batch_size * len(items[0][k]), h, w, device=dev)
+                frames = decoders[k].decode(files)
+                b[k] = frames.view(len(items), len(items[0][k]), frames.shape[1], frames.shape[2], 3)
+            elif k in params.encoders:
                 b[k] = torch.as_tensor(np.ascontiguousarray(np.stack([c[k] for c in items]))).to(dev)
         if FLOW in params.encoders:
             b['flow_limits'] = torch.as_tensor(np.stack([np.asarray(c['flow_limits'], np.float64).reshape(-1, 2)[0] for c in items])).to(dev)
@@ -119,7 +128,7 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
         r = readers.SampleReader(folder, ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
                                  context=params.context, duration=0.1, return_video=VIDEO in params.encoders,
                                  img_prep=None, return_flow=FLOW in params.encoders, skip_silence_thr=None,
-                                 shuffle=False, random_rotations=False, skip_rate=10, raw_flow=True)
+                                 shuffle=False, random_rotations=False, skip_rate=10, raw_flow=True, jpeg_files=gpu_jpeg)
         mask = np.ones(4) if channel_masks is None else np.asarray(channel_masks.get(r.video_id, np.ones(4)))
         for c in r.loop_chunks():
             c['mask'] = mask

@@ -12,7 +12,10 @@ Layout written by the reference's preprocessing (scraping/preprocess.py:98-204),
 behaviour: audio chunks are zero-padded before the start / after the end of the clip (feeder.py:66-90), video chunks
 start at max(int(t * rate), 0), flow is de-quantised to (mag cos, mag sin, mag) (feeder.py:147-161).  Decoding runs on
 the host like the reference's feeder threads (scipy wav reader, PIL JPEG decoder); the arrays it yields are what
-`W2XYZ.deploy` / `evaluate.evaluate_batches` upload.  Files at another sample rate are rejected instead of resampled
+`W2XYZ.deploy` / `evaluate.evaluate_batches` upload.  With `jpeg_files=True` the visual readers hand out the jpg FILES instead
+(bytes, undecoded) and `JpegDecoder` decodes a whole batch of them on the GPU -- Huffman decoding by a pool of host threads
+in libsag.so, inverse DCT / chroma upsampling / colour conversion as CUDA kernels -- into the uint8 frames the ingest kernel
+takes, bit-identical to PIL's decode (tests/test_jpeg.py).  Files at another sample rate are rejected instead of resampled
 (the reference resamples with resampy 'kaiser_fast', which is not available; its own preprocessing already writes
 the model's rate).
 """
@@ -50,6 +53,64 @@ def _imread(fn):
     from PIL import Image
     with Image.open(fn) as im:
         return np.asarray(im.convert('RGB'))
+
+
+def _read_file(fn):
+    with open(fn, 'rb') as f:
+        return f.read()
+
+
+def jpeg_info(data):
+    """(height, width, components, h_samp, v_samp) of a jpg file held in `data` (bytes), read by libsag's marker parser."""
+    import ctypes as C
+    from . import _lib as L
+    v = [C.c_int() for _ in range(5)]
+    L.check(L.lib().sag_jpeg_info(data, len(data), *[C.byref(x) for x in v]))
+    w, h, nc, hs, vs = [x.value for x in v]
+    return h, w, nc, hs, vs
+
+
+class JpegDecoder(object):
+    """Batches of jpg files -> uint8 RGB frames on the GPU: what `scipy.misc.imread` does per frame in the reference's feeder
+    (feeder.py:120-127), bit-identical to PIL / libjpeg (islow inverse DCT, fancy upsampling).  libsag.so decodes the entropy-coded
+    segments with a pool of host threads and runs the rest as CUDA kernels on the current stream (include/sag.h sag_jpeg_*).
+    Baseline sequential files only (what ffmpeg's mjpeg encoder and PIL write by default); others raise."""
+
+    def __init__(self, max_frames, height, width, device=None, threads=0):
+        import ctypes as C
+        import torch
+        from . import _lib as L
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_frames, self.height, self.width, self.threads = int(max_frames), int(height), int(width), int(threads)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().sag_jpeg_create(C.byref(self._h), self.max_frames, self.height, self.width))
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None) is not None and self._h.value:
+                from . import _lib as L
+                L.lib().sag_jpeg_destroy(self._h)
+                self._h.value = None
+        except Exception:
+            pass
+
+    def decode(self, files, out=None):
+        """files: a list of at most max_frames `bytes` objects, each one jpg file.  Returns (len(files), height, width, 3) uint8
+        on the device (`out` if given), valid in stream order on the current stream."""
+        import ctypes as C
+        import torch
+        from . import _lib as L
+        n = len(files)
+        if out is None:
+            out = torch.empty((n, self.height, self.width, 3), dtype=torch.uint8, device=self.device)
+        if out.dtype != torch.uint8 or tuple(out.shape) != (n, self.height, self.width, 3) or not out.is_contiguous():
+            raise ValueError('out must be a contiguous uint8 (%d, %d, %d, 3) CUDA tensor' % (n, self.height, self.width))
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(f), C.c_void_p) for f in files])
+        sizes = (C.c_size_t * n)(*[len(f) for f in files])
+        with torch.cuda.device(self.device):
+            L.check(L.lib().sag_jpeg_decode(self._h, ptrs, sizes, n, L.ptr(out), self.threads, L.stream()))
+        return out
 
 
 class AudioReader(object):
@@ -106,20 +167,29 @@ class VideoReader(object):
     (SptAudioGen.forward_into prepares them in the frame-ingest kernel)."""
     RAW_RATE = 10.
 
-    def __init__(self, video_folder, rate=None, img_prep=None):
+    def __init__(self, video_folder, rate=None, img_prep=None, jpeg_files=False):
         self.video_folder = video_folder
         self.rate = self.RAW_RATE if rate is None else rate
         self.img_prep = img_prep if img_prep is not None else (lambda x: x)
+        self.jpeg_files = jpeg_files                              # hand out the files (bytes) for JpegDecoder instead of frames
         names = sorted(f for f in os.listdir(video_folder) if f.endswith('.jpg'))
         self.num_frames = len(names)
         self.duration = self.num_frames / self.RAW_RATE
-        self.frame_shape = self.img_prep(_imread(os.path.join(video_folder, names[0]))).shape
+        if jpeg_files:
+            h, w = jpeg_info(_read_file(os.path.join(video_folder, names[0])))[:2]
+            self.frame_shape = (h, w, 3)
+        else:
+            self.frame_shape = self.img_prep(_imread(os.path.join(video_folder, names[0]))).shape
 
     def frame(self, index):
         return self.img_prep(_imread(os.path.join(self.video_folder, '{:06d}.jpg'.format(index))))
 
     def get_by_index(self, start_time, size, rotation=None):
         first = max(int(start_time * self.rate), 0)
+        if self.jpeg_files:
+            if rotation is not None:
+                raise ValueError('jpeg_files readers do not rotate (roll the decoded frames on the device instead)')
+            return [_read_file(os.path.join(self.video_folder, '{:06d}.jpg'.format(first + k))) for k in range(size)]
         chunk = np.stack([self.frame(first + k) for k in range(size)], 0)
         if rotation is not None:                                   # the same yaw as the audio: a roll along the panorama's width
             chunk = np.roll(chunk, -int(rotation / (2. * np.pi) * self.frame_shape[1]), axis=2)
@@ -147,8 +217,8 @@ class FlowReader(object):
     """Optical flow stored as 8-bit frames + per-frame magnitude limits (reference feeder.py:138-161).  raw=True returns the
     quantised frames and their limits (what the device-side ingest takes) instead of de-quantising on the host."""
 
-    def __init__(self, flow_dir, flow_lims_fn, rate=None, flow_prep=None, raw=False):
-        self.reader = VideoReader(flow_dir, rate=rate)
+    def __init__(self, flow_dir, flow_lims_fn, rate=None, flow_prep=None, raw=False, jpeg_files=False):
+        self.reader = VideoReader(flow_dir, rate=rate, jpeg_files=jpeg_files)
         self.lims = np.load(flow_lims_fn)
         self.rate = self.reader.rate
         self.duration = self.reader.duration
@@ -161,7 +231,7 @@ class FlowReader(object):
 
     def get_by_index(self, start_time, size, rotation=None):
         chunk = self.reader.get_by_index(start_time, size, rotation)
-        lims = self.limits(start_time, chunk.shape[0])
+        lims = self.limits(start_time, len(chunk))
         return (chunk, lims) if getattr(self, 'raw', False) else dequantize_flow(chunk, lims)
 
 
@@ -215,11 +285,13 @@ class SampleReader(object):
     """One clip's windows in schedule order (reference feeder.py:164-278): `get()` returns {'id', 'ambix'[, 'video'][, 'flow']}
     for the next scheduled time, None at the end; `loop_chunks(n)` iterates.  The audio window starts context/2 before the
     scheduled time; all readers of a window share one random yaw when random_rotations is on.  raw_flow=True yields the
-    quantised flow frames plus 'flow_limits' instead of float frames."""
+    quantised flow frames plus 'flow_limits' instead of float frames; jpeg_files=True yields the undecoded jpg files (lists of
+    bytes) under 'video' / 'flow' for JpegDecoder."""
 
     def __init__(self, folder, ambi_order=1, audio_rate=48000, video_rate=10, context=1.0, duration=0.1, return_video=True,
                  img_prep=None, return_flow=False, flow_prep=None, skip_silence_thr=None, shuffle=True, start_time=0.5,
-                 sample_duration=None, skip_rate=None, random_rotations=True, num_threads=1, thread_id=0, raw_flow=False):
+                 sample_duration=None, skip_rate=None, random_rotations=True, num_threads=1, thread_id=0, raw_flow=False,
+                 jpeg_files=False):
         n_audio, n_video, n_context = duration * audio_rate, duration * video_rate, context * audio_rate
         assert float(audio_rate) / video_rate == int(float(audio_rate) / video_rate)
         for v in (n_audio, n_video, n_context):
@@ -229,10 +301,12 @@ class SampleReader(object):
         self.audio_rate, self.video_rate = audio_rate, video_rate
         self.return_video, self.return_flow, self.random_rotations, self.raw_flow = return_video, return_flow, random_rotations, raw_flow
         self.audio_reader = AudioReader(os.path.join(folder, 'ambix'), audio_rate, ambi_order)
-        self.video_reader = VideoReader(os.path.join(folder, 'video'), video_rate, img_prep) if return_video else None
+        if jpeg_files and (random_rotations or (return_flow and not raw_flow)):
+            raise ValueError('jpeg_files needs random_rotations=False and raw_flow=True (undecoded files cannot be rolled or de-quantised on the host)')
+        self.video_reader = VideoReader(os.path.join(folder, 'video'), video_rate, img_prep, jpeg_files=jpeg_files) if return_video else None
         if return_flow:
             flow_dir = os.path.join(folder, 'flow')
-            self.flow_reader = FlowReader(flow_dir, os.path.join(flow_dir, 'flow_limits.npy'), video_rate, flow_prep)
+            self.flow_reader = FlowReader(flow_dir, os.path.join(flow_dir, 'flow_limits.npy'), video_rate, flow_prep, jpeg_files=jpeg_files)
             if raw_flow:
                 self.flow_reader.raw = True
         self.audio_size = int(round(n_audio)) + int(round(n_context)) - 1

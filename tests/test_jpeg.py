@@ -1,0 +1,162 @@
+"""JPEG frame decode: the reference reads frames with scipy.misc.imread = PIL over libjpeg
+(feeder.py:120-127).  The oracle (oracle/jpeg_oracle.py, a restatement of libjpeg's baseline decoder) is pinned bit-exactly
+against PIL's own decode; libsag's host entropy decoder against the oracle's coefficients; the GPU decode (through the C ABI)
+against PIL, bit-exactly."""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import jpeg_oracle as J
+from spatialaudiogen_b200 import _lib as L
+
+REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', '_ref')
+gpu = pytest.mark.gpu
+
+
+def _picture(h, w, seed=0, noise=12.):
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 100 * np.sin(x / 17. + y / 29. + seed), 127 + 90 * np.cos(x / 11. - y / 23.), 127 + 80 * np.sin(x / 7.) * np.cos(y / 13.)], -1)
+    return np.clip(img + rng.randn(h, w, 3) * noise, 0, 255).astype(np.uint8)
+
+
+def _jpeg(img, **kw):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, 'JPEG', **kw)
+    return b.getvalue()
+
+
+def _pil(data):
+    return np.asarray(Image.open(io.BytesIO(data)).convert('RGB'))
+
+
+def _cases():
+    out = [('frame 4:2:0 q90', _jpeg(_picture(224, 448), quality=90, subsampling=2)),
+           ('frame 4:4:4 q75', _jpeg(_picture(224, 448, 1), quality=75, subsampling=0)),
+           ('4:2:2 64x80', _jpeg(_picture(64, 80, 2), quality=50, subsampling=1)),
+           ('4:2:0 odd 37x53', _jpeg(_picture(37, 53, 3), quality=85, subsampling=2)),
+           ('4:2:2 odd 41x67', _jpeg(_picture(41, 67, 4), quality=95, subsampling=1)),
+           ('4:4:4 odd 33x49', _jpeg(_picture(33, 49, 5), quality=60, subsampling=0)),
+           ('one MCU', _jpeg(_picture(16, 16, 6), quality=30, subsampling=2)),
+           ('grey', _jpeg(_picture(40, 56, 7)[:, :, 0], quality=80)),
+           ('noise q100', _jpeg(np.random.RandomState(8).randint(0, 256, (48, 64, 3)).astype(np.uint8), quality=100, subsampling=2)),
+           ('optimised tables', _jpeg(_picture(56, 72, 9), quality=70, subsampling=2, optimize=True))]
+    try:                                               # restart intervals (Pillow >= 10.2 writes DRI on request)
+        d = _jpeg(_picture(64, 96, 10), quality=80, subsampling=2, restart_marker_blocks=3)
+        if b'\xff\xdd' in d:
+            out.append(('restart interval 3', d))
+    except TypeError:
+        pass
+    for f in ('puzzle.jpeg', 'tiger.jpeg', 'cat.jpg'):  # the reference's own photographs (staged by build(); absent -> skipped)
+        fn = os.path.join(REF_DIR, f)
+        if os.path.exists(fn):
+            out.append(('reference ' + f, open(fn, 'rb').read()))
+    return out
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize('name,data', [c for c in CASES if len(c[1]) < 60000], ids=[c[0] for c in CASES if len(c[1]) < 60000])
+def test_oracle_decode_is_bit_identical_to_pil(name, data):
+    assert np.array_equal(J.decode(data), _pil(data))
+
+
+def _native_coefficients(data):
+    hdr = J.parse(data)
+    cap = 3 * ((hdr['height'] + 15) // 16 * 16) * ((hdr['width'] + 15) // 16 * 16)
+    buf = np.zeros(cap, np.int16)
+    bw, bh, qt = (C.c_int * 3)(), (C.c_int * 3)(), np.zeros(192, np.uint16)
+    L.check(L.lib().sag_jpeg_coefficients(data, len(data), buf.ctypes.data, buf.size, bw, bh, qt.ctypes.data))
+    return hdr, buf, list(bw), list(bh), qt
+
+
+@pytest.mark.parametrize('name,data', [c for c in CASES if len(c[1]) < 60000], ids=[c[0] for c in CASES if len(c[1]) < 60000])
+def test_host_entropy_decoder_matches_the_oracle(name, data):
+    hdr, buf, bw, bh, qt = _native_coefficients(data)
+    off = 0
+    for c, ref in enumerate(J.coefficients(hdr)):
+        assert (bh[c], bw[c]) == ref.shape[:2]
+        assert np.array_equal(buf[off:off + ref.size].reshape(ref.shape), ref)
+        assert np.array_equal(qt[64 * c:64 * c + 64], hdr['qt'][hdr['comps'][c][3]])
+        off += ref.size
+    v = [C.c_int() for _ in range(5)]
+    L.check(L.lib().sag_jpeg_info(data, len(data), *[C.byref(x) for x in v]))
+    assert (v[0].value, v[1].value, v[2].value) == (hdr['width'], hdr['height'], len(hdr['comps']))
+
+
+def test_unsupported_and_broken_files_fail_loudly():
+    lib = L.lib()
+    prog = _jpeg(_picture(32, 32), quality=80, progressive=True)
+    with pytest.raises(L.SagError) as e:
+        L.check(lib.sag_jpeg_info(prog, len(prog), None, None, None, None, None))
+    assert e.value.code == L.SAG_EUNSUPPORTED and 'baseline' in str(e.value)
+    with pytest.raises(ValueError):
+        J.decode(prog)
+    good = CASES[2][1]
+    with pytest.raises(ValueError):
+        L.check(lib.sag_jpeg_info(b'not a jpeg', 10, None, None, None, None, None))
+    with pytest.raises(ValueError):                                                  # the file ends inside its tables
+        L.check(lib.sag_jpeg_info(good[:100], 100, None, None, None, None, None))
+    buf = np.zeros(16, np.int16)
+    with pytest.raises(L.SagError) as e:                                              # caller's buffer too small
+        L.check(lib.sag_jpeg_coefficients(good, len(good), buf.ctypes.data, buf.size, None, None, None))
+    assert e.value.code == L.SAG_ENOMEM
+    # a truncated scan decodes (missing data reads as zeros, like libjpeg's warning path) and never reads past the buffer
+    hdr, _, _, _, _ = _native_coefficients(good[:len(good) // 2])
+    assert hdr['width'] == 80
+
+
+# ---- GPU ----------------------------------------------------------------------------------------------------------------
+@gpu
+def test_gpu_decode_is_bit_identical_to_pil():
+    from spatialaudiogen_b200 import readers as R
+    for name, data in CASES:
+        ref = _pil(data)
+        dec = R.JpegDecoder(2, ref.shape[0], ref.shape[1])
+        out = dec.decode([data, data]).cpu().numpy()
+        assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref), name
+
+
+@gpu
+def test_gpu_decode_of_a_mixed_batch_of_frames():
+    """A batch of 32 frames of the dataset's size with every sampling / quality mixed, decoded into a caller's buffer, twice
+    (the decoder's staging is reused) and with one host thread."""
+    from spatialaudiogen_b200 import readers as R
+    files = [_jpeg(_picture(224, 448, 20 + i, noise=4. * (i % 5)), quality=(35, 60, 90, 97)[i % 4], subsampling=i % 3) for i in range(32)]
+    files[7] = _jpeg(_picture(224, 448, 99)[:, :, 1], quality=85)                    # a grey frame among them
+    ref = np.stack([_pil(f) for f in files])
+    dec = R.JpegDecoder(32, 224, 448)
+    out = torch.empty((32, 224, 448, 3), dtype=torch.uint8, device='cuda')
+    assert dec.decode(files, out=out) is out
+    assert np.array_equal(out.cpu().numpy(), ref)
+    rev = dec.decode(files[::-1][:20])
+    assert np.array_equal(rev.cpu().numpy(), ref[::-1][:20])
+    one = R.JpegDecoder(32, 224, 448, threads=1).decode(files)
+    assert torch.equal(one, out)
+    with pytest.raises(ValueError):                                                  # a frame of another size
+        dec.decode([_jpeg(_picture(64, 80), quality=80)])
+    with pytest.raises(ValueError):
+        dec.decode(files + files[:1])                                                # more than max_frames
+
+
+@gpu
+def test_folder_batches_with_gpu_decode_equal_the_pil_readers(tmp_path):
+    from spatialaudiogen_b200 import evaluate as E
+    from test_host import _make_video_folder
+    from test_gpu_parity import _P
+    folder, _ = _make_video_folder(str(tmp_path), seconds=4, flow=True)
+    with open(os.path.join(folder, 'audio_pow.lst'), 'w') as f:
+        for k in range(30):
+            f.write('%.1f %.3f\n' % (0.5 + 0.1 * k, 0.3))
+    enc = ['audio', 'video', 'flow']
+    a = list(E.folder_batches([folder], _P(enc), batch_size=16, drop_remainder=False, gpu_jpeg=True))
+    b = list(E.folder_batches([folder], _P(enc), batch_size=16, drop_remainder=False, gpu_jpeg=False))
+    assert len(a) == len(b) == 1 and a[0]['id'] == b[0]['id']
+    for k in ('video', 'flow', 'ambix', 'flow_limits'):
+        assert a[0][k].dtype == b[0][k].dtype and torch.equal(a[0][k], b[0][k]), k
