@@ -239,6 +239,15 @@ void sag_jpeg_destroy(sag_jpeg* dec);
 /* n files in host memory -> frames (device, uint8, (n, height, width, 3) RGB) on `stream`.  Returns once the kernels are
  * queued; the files may be released on return.  threads <= 0: one per host core (at most 32). */
 int sag_jpeg_decode(sag_jpeg* dec, const void* const* host_files, const size_t* sizes, int n, uint8_t* frames, int threads, void* stream);
+/* "device_huffman" (default 1): the entropy-coded segments are decoded on the GPU too -- each frame's bit stream is cut into
+ * subsequences decoded in parallel, whose decoders fall into step with the true one by themselves (a few rounds until every
+ * subsequence starts where its predecessor ended) -- so only the compressed bytes cross PCIe; 0: host entropy decoding. */
+int sag_jpeg_set_option(sag_jpeg* dec, const char* key, int value);
+/* synchronisation rounds each of the first n frames of the last device-side decode took (synchronises with the device) */
+int sag_jpeg_sync_rounds(sag_jpeg* dec, int* host_rounds, int n);
+/* host only, for tests: the device's parallel entropy decoder run thread by thread on the host (`nthreads` = its CTA size);
+ * same output as sag_jpeg_coefficients */
+int sag_jpeg_coefficients_parallel(const void* host_file, size_t size, int nthreads, int16_t* host_coef, size_t capacity, int* rounds);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,9 @@ PROTOTYPES = {
     'sag_jpeg_create': (_I, [C.POINTER(_P), _I, _I, _I]),
     'sag_jpeg_destroy': (None, [_P]),
     'sag_jpeg_decode': (_I, [_P, C.POINTER(_P), C.POINTER(_S), _I, _P, _I, _P]),
+    'sag_jpeg_set_option': (_I, [_P, C.c_char_p, _I]),
+    'sag_jpeg_sync_rounds': (_I, [_P, C.POINTER(_I), _I]),
+    'sag_jpeg_coefficients_parallel': (_I, [_P, _S, _I, _P, _S, C.POINTER(_I)]),
 }
 
 _lib = None

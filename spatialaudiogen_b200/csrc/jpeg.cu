@@ -14,6 +14,8 @@
 #include <atomic>
 #include <thread>
 #include <algorithm>
+#include <functional>
+#include <memory>
 
 namespace sag {
 namespace {
@@ -409,6 +411,328 @@ __global__ void __launch_bounds__(64) jpeg_rgb_kernel(const JpegImage* __restric
   }
 }
 
+
+// ---- parallel entropy decoding on the device --------------------------------------------------------------------------------
+// A Huffman-coded scan is one serial bit stream, but its decoder resynchronises by itself: started at an arbitrary bit with a
+// guessed state it falls into step with the true decoder after a few symbols.  The unstuffed stream of each frame is cut
+// into subsequences of a few hundred bits, one per thread (Weissenberger & Schmidt's scheme):
+//   round 0   every subsequence is decoded from its first bit as if a block started there; the state at its end -- (bit
+//             position of the next symbol, block of the MCU, zig-zag index) -- is recorded
+//   round r   every subsequence is decoded again from the recorded end state of its predecessor, if that changed; the first
+//             subsequence of a restart segment always starts from the true state, so after r rounds the first r subsequences
+//             are exact, and in practice two or three rounds make every state consistent -- which is the stopping rule
+//   scan      blocks completed per subsequence -> index of the block each subsequence starts in
+//   write     a last decode stores the coefficients (DC as differences) at their places in the frame's block grids
+//   DC        prefix sums of the DC differences per component in scan order, restarted at every restart segment
+// All phases are __host__ __device__ functions of (thread, threads): the kernel runs them with one CTA per frame and
+// __syncthreads between phases; sag_jpeg_coefficients_parallel runs the same code thread by thread on the host (tests).
+struct SubState { int p; short b, z; };
+__host__ __device__ inline bool same_state(const SubState& a, const SubState& b) { return a.p == b.p && a.b == b.b && a.z == b.z; }
+
+struct JpegSub {              // one subsequence
+  int begin_bit, end_bit;     // in the frame's unstuffed stream
+  int first;                  // starts a restart segment: the true initial state is known
+  int seg_block0, seg_block1; // scan-order indices of the segment's first block and of the one past its last
+};
+
+struct JpegStream {           // the scan of one frame
+  long long data_off;         // byte offset of the unstuffed stream in the batch's buffer (padded with 16 zero bytes)
+  int sub0, n_subs;           // its rows of the batch's JpegSub table
+  int bpm;                    // blocks per MCU
+  int blk_comp[6], blk_x[6], blk_y[6];
+  int mcux, n_mcus;
+  int restart_mcus;           // MCUs per restart segment (0: one segment)
+  int dc_tab[3], ac_tab[3];   // rows of the batch's table array
+};
+
+struct HuffView { const HuffTable* dc[3]; const HuffTable* ac[3]; };
+
+__host__ __device__ inline uint32_t peek32(const uint8_t* s, int p) {
+  const uint8_t* b = s + (p >> 3);
+  const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | (uint64_t)b[4];
+  return (uint32_t)(v >> (8 - (p & 7)));
+}
+
+// one Huffman symbol at the top of `w`: its code length (>= 1, so the decoder always advances) and value
+__host__ __device__ inline int huff_symbol(const HuffTable& t, uint32_t w, int* len) {
+  const uint16_t e = t.look[w >> 23];
+  if (e) { *len = e >> 8; return e & 255; }
+  for (int l = 10; l <= 16; ++l) {
+    const int32_t code = (int32_t)(w >> (32 - l));
+    if (code <= t.maxcode[l]) { *len = l; return t.symbols[(code + t.valoffset[l]) & 255]; }
+  }
+  *len = 16;                  // no such code (only off the true path, or in a corrupt file)
+  return 0;
+}
+
+__host__ __device__ inline int16_t* block_ptr(const JpegStream& js, const JpegImage& im, int16_t* coef, long long q) {
+  const int m = (int)(q / js.bpm), bi = (int)(q % js.bpm);
+  const int c = js.blk_comp[bi];
+  const int bx = (m % js.mcux) * im.h[c] + js.blk_x[bi], by = (m / js.mcux) * im.v[c] + js.blk_y[bi];
+  return coef + im.coef_off[c] + ((long long)by * im.bw[c] + bx) * 64;
+}
+
+// Decodes from state `st` up to bit `end_bit`; returns the number of blocks completed.  WRITE: q = scan-order index of the block
+// the state is in, q_end = one past the segment's last block; coefficients go to their places (DC as the difference).
+template <bool WRITE>
+__host__ __device__ inline int decode_span(const uint8_t* s, const HuffView& hv, const JpegStream& js, SubState& st, int end_bit,
+                                           long long q, long long q_end, const JpegImage* im, int16_t* coef, const uint8_t* zigzag) {
+  int p = st.p, b = st.b, z = st.z, done = 0;
+  int16_t* blk = nullptr;
+  if (WRITE && q < q_end) blk = block_ptr(js, *im, coef, q);
+  while (p < end_bit) {
+    if (WRITE && q >= q_end) break;                     // only padding bits are left in this restart segment
+    const int c = js.blk_comp[b];
+    const uint32_t w = peek32(s, p);
+    int len;
+    if (z == 0) {
+      const int sz = huff_symbol(*hv.dc[c], w, &len) & 15;
+      if (WRITE) {
+        const int r = sz ? (int)((w << len) >> (32 - sz)) : 0;
+        blk[0] = (int16_t)(sz ? (r < (1 << (sz - 1)) ? r - (1 << sz) + 1 : r) : 0);
+      }
+      p += len + sz;
+      z = 1;
+    } else {
+      const int rs = huff_symbol(*hv.ac[c], w, &len);
+      const int r = rs >> 4, sz = rs & 15;
+      p += len + sz;
+      if (sz) {
+        z += r;
+        if (WRITE) {
+          const int v = (int)((w << len) >> (32 - sz));
+          blk[zigzag[z & 63]] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
+        }
+        z += 1;
+      } else if (r == 15) {
+        z += 16;
+      } else {
+        z = 64;
+      }
+    }
+    if (z >= 64) {
+      z = 0;
+      b = b + 1 == js.bpm ? 0 : b + 1;
+      ++done;
+      if (WRITE) { ++q; if (q < q_end) blk = block_ptr(js, *im, coef, q); }
+    }
+  }
+  st.p = p;
+  st.b = (short)b;
+  st.z = (short)z;
+  return done;
+}
+
+struct HuffScratch {          // per subsequence of the batch (device memory)
+  SubState* exit[2];
+  SubState* entry;
+  int* nblk;
+  int* base;
+};
+
+// one synchronisation round over the frame's subsequences; returns whether this thread re-decoded anything
+__host__ __device__ inline int phase_sync(int tid, int nthreads, int round, int cur, const uint8_t* s, const HuffView& hv, const JpegStream& js,
+                                          const JpegSub* subs, const HuffScratch& sc) {
+  int changed = 0;
+  for (int k = tid; k < js.n_subs; k += nthreads) {
+    const int j = js.sub0 + k;
+    const JpegSub& sb = subs[j];
+    SubState e;
+    if (sb.first || round == 0) { e.p = sb.begin_bit; e.b = 0; e.z = 0; }
+    else e = sc.exit[cur][j - 1];
+    if (round > 0 && same_state(e, sc.entry[j])) { sc.exit[cur ^ 1][j] = sc.exit[cur][j]; continue; }
+    sc.entry[j] = e;
+    sc.nblk[j] = decode_span<false>(s, hv, js, e, sb.end_bit, 0, 0, nullptr, nullptr, nullptr);
+    sc.exit[cur ^ 1][j] = e;
+    changed = 1;
+  }
+  return changed;
+}
+
+// segmented exclusive scan of nblk -> base, in three steps (local, carries by thread 0, apply); total / reset: nthreads ints each
+__host__ __device__ inline void phase_scan_local(int tid, int nthreads, const JpegStream& js, const JpegSub* subs, const HuffScratch& sc, int* total,
+                                                 int* reset) {
+  const int per = (js.n_subs + nthreads - 1) / nthreads;
+  int run = 0, has_reset = 0;
+  for (int k = tid * per; k < min((tid + 1) * per, js.n_subs); ++k) {
+    const int j = js.sub0 + k;
+    if (subs[j].first) { run = subs[j].seg_block0; has_reset = 1; }
+    sc.base[j] = run;
+    run += sc.nblk[j];
+  }
+  total[tid] = run;
+  reset[tid] = has_reset;
+}
+__host__ __device__ inline void phase_scan_carry(int nthreads, int* total, const int* reset) {     // total[t] <- carry into thread t
+  int carry = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    const int mine = total[t];
+    total[t] = carry;
+    carry = reset[t] ? mine : carry + mine;
+  }
+}
+__host__ __device__ inline void phase_scan_apply(int tid, int nthreads, const JpegStream& js, const JpegSub* subs, const HuffScratch& sc, const int* total) {
+  const int per = (js.n_subs + nthreads - 1) / nthreads;
+  for (int k = tid * per; k < min((tid + 1) * per, js.n_subs); ++k) {
+    const int j = js.sub0 + k;
+    if (subs[j].first) break;
+    sc.base[j] += total[tid];
+  }
+}
+
+__host__ __device__ inline void phase_write(int tid, int nthreads, const uint8_t* s, const HuffView& hv, const JpegStream& js, const JpegSub* subs,
+                                            const HuffScratch& sc, const JpegImage& im, int16_t* coef, const uint8_t* zigzag) {
+  for (int k = tid; k < js.n_subs; k += nthreads) {
+    const int j = js.sub0 + k;
+    SubState e = sc.entry[j];
+    decode_span<true>(s, hv, js, e, subs[j].end_bit, sc.base[j], subs[j].seg_block1, &im, coef, zigzag);
+  }
+}
+
+// DC prediction of component c: inclusive sums of the differences in scan order, restarted every `seg` blocks (0: never)
+__host__ __device__ inline int16_t* dc_block(const JpegStream& js, const JpegImage& im, int16_t* coef, int c, int k) {
+  const int nb = im.h[c] * im.v[c];
+  const int m = k / nb, i = k % nb;
+  const int bx = (m % js.mcux) * im.h[c] + i % im.h[c], by = (m / js.mcux) * im.v[c] + i / im.h[c];
+  return coef + im.coef_off[c] + ((long long)by * im.bw[c] + bx) * 64;
+}
+__host__ __device__ inline void phase_dc_local(int tid, int nthreads, const JpegStream& js, const JpegImage& im, int16_t* coef, int c, int* total,
+                                               int* reset) {
+  const int nb = im.h[c] * im.v[c], n = js.n_mcus * nb, seg = js.restart_mcus * nb;
+  const int per = (n + nthreads - 1) / nthreads;
+  int run = 0, has_reset = 0;
+  for (int k = tid * per; k < min((tid + 1) * per, n); ++k) {
+    if (seg > 0 && k % seg == 0) { run = 0; has_reset = 1; }
+    int16_t* d = dc_block(js, im, coef, c, k);
+    run += *d;
+    *d = (int16_t)run;
+  }
+  total[tid] = run;
+  reset[tid] = has_reset;
+}
+__host__ __device__ inline void phase_dc_apply(int tid, int nthreads, const JpegStream& js, const JpegImage& im, int16_t* coef, int c, const int* total) {
+  const int nb = im.h[c] * im.v[c], n = js.n_mcus * nb, seg = js.restart_mcus * nb;
+  const int per = (n + nthreads - 1) / nthreads;
+  if (total[tid] == 0) return;
+  for (int k = tid * per; k < min((tid + 1) * per, n); ++k) {
+    if (seg > 0 && k % seg == 0) break;
+    int16_t* d = dc_block(js, im, coef, c, k);
+    *d = (int16_t)(*d + total[tid]);
+  }
+}
+
+__constant__ uint8_t c_zigzag[64];
+
+constexpr int kHuffThreads = 256;
+// grid (n frames): one CTA per frame
+__global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegStream* __restrict__ streams, const JpegSub* __restrict__ subs,
+                                                                    const HuffTable* __restrict__ tables, const JpegImage* __restrict__ images,
+                                                                    const uint8_t* __restrict__ data, HuffScratch sc, int16_t* __restrict__ coef,
+                                                                    int* __restrict__ rounds_out) {
+  __shared__ __align__(16) unsigned char tab_raw[6 * sizeof(HuffTable)];
+  __shared__ int total[kHuffThreads], reset[kHuffThreads];
+  __shared__ JpegStream js;
+  __shared__ JpegImage im;
+  const int tid = threadIdx.x;
+  if (tid == 0) { js = streams[blockIdx.x]; im = images[blockIdx.x]; }
+  __syncthreads();
+  HuffTable* tab = reinterpret_cast<HuffTable*>(tab_raw);
+  for (int t = 0; t < 2 * im.ncomp; ++t) {               // the frame's tables into shared memory (word copies)
+    const int row = t < im.ncomp ? js.dc_tab[t] : js.ac_tab[t - im.ncomp];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables + row);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tab + t);
+    for (int i = tid; i < (int)(sizeof(HuffTable) / 4); i += kHuffThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  HuffView hv;
+  for (int c = 0; c < 3; ++c) { hv.dc[c] = tab + min(c, im.ncomp - 1); hv.ac[c] = tab + im.ncomp + min(c, im.ncomp - 1); }
+  const uint8_t* s = data + js.data_off;
+  int cur = 0, round = 0;
+  for (;; ++round) {
+    const int changed = phase_sync(tid, kHuffThreads, round, cur, s, hv, js, subs, sc);
+    cur ^= 1;
+    if (!__syncthreads_or(changed)) break;
+  }
+  if (tid == 0 && rounds_out != nullptr) rounds_out[blockIdx.x] = round;
+  phase_scan_local(tid, kHuffThreads, js, subs, sc, total, reset);
+  __syncthreads();
+  if (tid == 0) phase_scan_carry(kHuffThreads, total, reset);
+  __syncthreads();
+  phase_scan_apply(tid, kHuffThreads, js, subs, sc, total);
+  __syncthreads();
+  phase_write(tid, kHuffThreads, s, hv, js, subs, sc, im, coef, c_zigzag);
+  __syncthreads();
+  for (int c = 0; c < im.ncomp; ++c) {
+    phase_dc_local(tid, kHuffThreads, js, im, coef, c, total, reset);
+    __syncthreads();
+    if (tid == 0) phase_scan_carry(kHuffThreads, total, reset);
+    __syncthreads();
+    phase_dc_apply(tid, kHuffThreads, js, im, coef, c, total);
+    __syncthreads();
+  }
+}
+
+// ---- host preparation of a scan for the parallel decoder -------------------------------------------------------------------
+// Unstuffs the entropy-coded segment (FF 00 -> FF), drops the RSTn markers and records where each restart segment starts.
+void unstuff(const Header& h, std::vector<uint8_t>& out, std::vector<int>& seg_start) {
+  out.clear();
+  seg_start.assign(1, 0);
+  const uint8_t* d = h.ecs;
+  const size_t n = h.ecs_size;
+  out.reserve(n + 16);
+  size_t p = 0;
+  while (p < n) {
+    const uint8_t* f = static_cast<const uint8_t*>(memchr(d + p, 0xFF, n - p));
+    const size_t q = f ? (size_t)(f - d) : n;
+    out.insert(out.end(), d + p, d + q);
+    if (!f) break;
+    const int nxt = q + 1 < n ? d[q + 1] : 0xD9;
+    if (nxt == 0) { out.push_back(0xFF); p = q + 2; }
+    else if (nxt >= 0xD0 && nxt <= 0xD7) { seg_start.push_back((int)out.size()); p = q + 2; }
+    else if (nxt == 0xFF) { p = q + 1; }
+    else break;                                           // EOI or another marker: the scan ends here
+  }
+}
+
+int g_min_sub_bytes = 256;     // measured on B200, 32 frames of 224x448 at quality 90: 64 B -> 11-22 rounds, 256 B -> 3-6, fastest
+int sub_bytes_for(size_t stream_bytes) {                  // at most 2048 subsequences per frame, at least g_min_sub_bytes each
+  size_t sb = (stream_bytes + 2047) / 2048;
+  sb = std::max<size_t>((size_t)g_min_sub_bytes, (sb + 3) / 4 * 4);
+  return (int)sb;
+}
+
+// fills js (except data_off / sub0 / table rows) and appends the frame's subsequences
+void plan_stream(const Header& h, const std::vector<int>& seg_start, int stream_bytes, JpegStream* js, std::vector<JpegSub>* subs) {
+  memset(js, 0, sizeof(*js));
+  js->bpm = 0;
+  for (int c = 0; c < h.ncomp; ++c)
+    for (int y = 0; y < h.comp[c].v; ++y)
+      for (int x = 0; x < h.comp[c].h; ++x) { js->blk_comp[js->bpm] = c; js->blk_x[js->bpm] = x; js->blk_y[js->bpm] = y; ++js->bpm; }
+  js->mcux = h.mcux;
+  js->n_mcus = h.mcux * h.mcuy;
+  js->restart_mcus = h.restart_interval;
+  const int total_blocks = js->n_mcus * js->bpm;
+  const int seg_blocks = h.restart_interval ? h.restart_interval * js->bpm : total_blocks;
+  const int sb = sub_bytes_for((size_t)stream_bytes);
+  const int first_row = (int)subs->size();
+  for (size_t g = 0; g < seg_start.size(); ++g) {
+    const int b0 = seg_start[g], b1 = g + 1 < seg_start.size() ? seg_start[g + 1] : stream_bytes;
+    const long long q0 = (long long)g * seg_blocks;
+    if (q0 >= total_blocks) break;                        // (markers past the last MCU)
+    for (int o = b0; o < b1 || o == b0; o += sb) {
+      JpegSub s;
+      s.begin_bit = o * 8;
+      s.end_bit = std::min(o + sb, std::max(b1, b0)) * 8;
+      s.first = o == b0;
+      s.seg_block0 = (int)q0;
+      s.seg_block1 = (int)std::min<long long>(q0 + seg_blocks, total_blocks);
+      subs->push_back(s);
+      if (b1 <= b0) break;
+    }
+  }
+  js->n_subs = (int)subs->size() - first_row;
+}
+
 }  // namespace
 }  // namespace sag
 
@@ -424,6 +748,20 @@ struct sag_jpeg {
   uint8_t* d_planes = nullptr;
   cudaEvent_t staged = nullptr;            // the previous call's host -> device copies have left the staging buffers
   bool staged_pending = false;
+  // device entropy decoding (option "device_huffman", default on): the unstuffed scans travel instead of the coefficients
+  int device_huffman = 1;
+  size_t stream_cap = 0, sub_cap = 0, table_cap = 0;
+  uint8_t* h_stream = nullptr;             // pinned
+  uint8_t* d_stream = nullptr;
+  sag::JpegSub* h_subs = nullptr;          // pinned
+  sag::JpegSub* d_subs = nullptr;
+  sag::JpegStream* h_js = nullptr;         // pinned, max_frames
+  sag::JpegStream* d_js = nullptr;
+  sag::HuffTable* h_tables = nullptr;      // pinned
+  sag::HuffTable* d_tables = nullptr;
+  char* d_scratch = nullptr;               // SubState x 3 + int x 2 per subsequence
+  int* d_rounds = nullptr;                 // synchronisation rounds of each frame of the last decode
+  int last_n = 0;
 };
 
 using namespace sag;
@@ -493,6 +831,10 @@ int sag_jpeg_create(sag_jpeg** out, int max_frames, int height, int width) {
   if (e == cudaSuccess) e = cudaMalloc(&d->d_img, (size_t)max_frames * sizeof(JpegImage));
   if (e == cudaSuccess) e = cudaMalloc(&d->d_planes, d->plane_cap * max_frames);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->staged, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaHostAlloc(&d->h_js, (size_t)max_frames * sizeof(JpegStream), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_js, (size_t)max_frames * sizeof(JpegStream));
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_rounds, (size_t)max_frames * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_zigzag, kZigzag, 64);
   if (e != cudaSuccess) {
     set_error("jpeg: %s while creating the decoder: %s", cudaGetErrorName(e), cudaGetErrorString(e));
     sag_jpeg_destroy(d);
@@ -512,7 +854,122 @@ void sag_jpeg_destroy(sag_jpeg* d) {
   cudaFree(d->d_qt);
   cudaFree(d->d_img);
   cudaFree(d->d_planes);
+  cudaFreeHost(d->h_stream);
+  cudaFreeHost(d->h_subs);
+  cudaFreeHost(d->h_js);
+  cudaFreeHost(d->h_tables);
+  cudaFree(d->d_stream);
+  cudaFree(d->d_subs);
+  cudaFree(d->d_js);
+  cudaFree(d->d_tables);
+  cudaFree(d->d_scratch);
+  cudaFree(d->d_rounds);
   delete d;
+}
+
+int sag_jpeg_set_option(sag_jpeg* d, const char* key, int value) {
+  SAG_REQUIRE(d != nullptr && key != nullptr, SAG_EINVAL, "jpeg: null argument");
+  if (strcmp(key, "device_huffman") == 0) { d->device_huffman = value != 0; return SAG_OK; }
+  if (strcmp(key, "sub_bytes") == 0) {                    // (process wide) shortest subsequence of the device entropy decoder
+    SAG_REQUIRE(value >= 32 && value <= 65536, SAG_EINVAL, "jpeg: sub_bytes must be in [32, 65536]");
+    g_min_sub_bytes = value;
+    return SAG_OK;
+  }
+  SAG_REQUIRE(false, SAG_EINVAL, "jpeg: unknown option %s", key);
+}
+
+int sag_jpeg_sync_rounds(sag_jpeg* d, int* host_rounds, int n) {
+  SAG_REQUIRE(d != nullptr && host_rounds != nullptr && n >= 0 && n <= d->last_n, SAG_EINVAL, "jpeg: the last device decode held %d frames",
+              d ? d->last_n : 0);
+  SAG_CHECK_CUDA(cudaMemcpy(host_rounds, d->d_rounds, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+  return SAG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// pinned + device buffer pair that grows on demand (the caller has synchronised with the copies that read the old one)
+template <class T>
+int grow(T** host, T** dev, size_t* cap, size_t need) {
+  if (need <= *cap) return SAG_OK;
+  const size_t want = need + need / 2 + 1024;
+  if (*host) SAG_CHECK_CUDA(cudaFreeHost(*host));
+  if (*dev) SAG_CHECK_CUDA(cudaFree(*dev));
+  *host = nullptr;
+  *dev = nullptr;
+  *cap = 0;
+  SAG_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(host), want * sizeof(T), cudaHostAllocDefault));
+  SAG_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), want * sizeof(T)));
+  *cap = want;
+  return SAG_OK;
+}
+
+HuffScratch carve_scratch(char* base, size_t subs) {
+  HuffScratch sc;
+  sc.exit[0] = reinterpret_cast<SubState*>(base);
+  sc.exit[1] = sc.exit[0] + subs;
+  sc.entry = sc.exit[1] + subs;
+  sc.nblk = reinterpret_cast<int*>(sc.entry + subs);
+  sc.base = sc.nblk + subs;
+  return sc;
+}
+constexpr size_t kScratchPerSub = 3 * sizeof(SubState) + 2 * sizeof(int);
+}  // namespace
+
+extern "C" {
+
+// The device algorithm run thread by thread on the host (tests; `nthreads` plays the CTA size): same phase functions, same
+// tables, same subsequence plan.  rounds: synchronisation rounds until every state was consistent.
+int sag_jpeg_coefficients_parallel(const void* host_file, size_t size, int nthreads, int16_t* host_coef, size_t capacity, int* rounds) {
+  SAG_REQUIRE(host_file != nullptr && host_coef != nullptr && nthreads > 0, SAG_EINVAL, "jpeg: bad argument");
+  std::unique_ptr<Header> h(new Header());
+  SAG_TRY(parse_header(static_cast<const uint8_t*>(host_file), size, h.get()));
+  JpegImage im;
+  memset(&im, 0, sizeof(im));
+  im.ncomp = h->ncomp;
+  size_t need = 0;
+  for (int c = 0; c < 3; ++c) {
+    im.h[c] = im.v[c] = 1;
+    if (c < h->ncomp) {
+      im.h[c] = h->comp[c].h; im.v[c] = h->comp[c].v; im.bw[c] = h->bw[c]; im.bh[c] = h->bh[c];
+      im.coef_off[c] = (long long)need;
+      need += (size_t)h->bw[c] * h->bh[c] * 64;
+    }
+  }
+  SAG_REQUIRE(need <= capacity, SAG_ENOMEM, "jpeg: coefficient buffer holds %zu values, the file needs %zu", capacity, need);
+  memset(host_coef, 0, need * sizeof(int16_t));
+  std::vector<uint8_t> stream;
+  std::vector<int> seg;
+  unstuff(*h, stream, seg);
+  const int nbytes = (int)stream.size();
+  stream.resize(stream.size() + 16, 0);
+  JpegStream js;
+  std::vector<JpegSub> subs;
+  plan_stream(*h, seg, nbytes, &js, &subs);
+  js.sub0 = 0;
+  HuffView hv;
+  for (int c = 0; c < 3; ++c) { const int cc = std::min(c, h->ncomp - 1); hv.dc[c] = &h->dc[h->comp[cc].td]; hv.ac[c] = &h->ac[h->comp[cc].ta]; }
+  std::vector<char> raw(kScratchPerSub * subs.size() + 64);
+  HuffScratch sc = carve_scratch(raw.data(), subs.size());
+  std::vector<int> total(nthreads), reset(nthreads);
+  int cur = 0, round = 0;
+  for (;; ++round) {
+    int changed = 0;
+    for (int t = 0; t < nthreads; ++t) changed |= phase_sync(t, nthreads, round, cur, stream.data(), hv, js, subs.data(), sc);
+    cur ^= 1;
+    if (!changed) break;
+  }
+  if (rounds) *rounds = round;
+  for (int t = 0; t < nthreads; ++t) phase_scan_local(t, nthreads, js, subs.data(), sc, total.data(), reset.data());
+  phase_scan_carry(nthreads, total.data(), reset.data());
+  for (int t = 0; t < nthreads; ++t) phase_scan_apply(t, nthreads, js, subs.data(), sc, total.data());
+  for (int t = 0; t < nthreads; ++t) phase_write(t, nthreads, stream.data(), hv, js, subs.data(), sc, im, host_coef, kZigzag);
+  for (int c = 0; c < im.ncomp; ++c) {
+    for (int t = 0; t < nthreads; ++t) phase_dc_local(t, nthreads, js, im, host_coef, c, total.data(), reset.data());
+    phase_scan_carry(nthreads, total.data(), reset.data());
+    for (int t = 0; t < nthreads; ++t) phase_dc_apply(t, nthreads, js, im, host_coef, c, total.data());
+  }
+  return SAG_OK;
 }
 
 int sag_jpeg_decode(sag_jpeg* d, const void* const* host_files, const size_t* sizes, int n, uint8_t* frames, int threads, void* stream) {
@@ -560,14 +1017,80 @@ int sag_jpeg_decode(sag_jpeg* d, const void* const* host_files, const size_t* si
     max_blocks = std::max(max_blocks, blocks);
   }
   SAG_REQUIRE(coef_total <= d->coef_cap * (size_t)d->max_frames, SAG_ENOMEM, "jpeg: coefficient staging too small");
-  // entropy decoding: one file per task, a few host threads
-  std::atomic<int> next(0), failed(0);
-  std::string first_error;
-  std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
-  auto work = [&]() {
-    for (;;) {
-      const int i = next.fetch_add(1);
-      if (i >= n) break;
+  // (device entropy decoding leaves the host ~30 us of work per frame: a pool only pays when the caller asks for one)
+  int nt = threads > 0 ? threads : (d->device_huffman ? 1 : (int)std::thread::hardware_concurrency());
+  nt = std::max(1, std::min(std::min(nt, n), 32));
+  auto run_pool = [&](const std::function<void(int)>& task) {      // task(i) for every frame, on nt threads
+    std::atomic<int> next(0);
+    auto work = [&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) task(i); };
+    if (nt == 1) { work(); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt - 1; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  };
+  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_qt, d->h_qt, (size_t)n * 3 * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_img, d->h_img, (size_t)n * sizeof(JpegImage), cudaMemcpyHostToDevice, st));
+  if (d->device_huffman) {
+    // host: unstuff the scans (memchr-paced copies) and lay out the subsequences; device: everything else
+    size_t bound = 0;
+    for (int i = 0; i < n; ++i) bound += (hdr[i].ecs_size + 16 + 15) / 16 * 16;
+    SAG_TRY(grow(&d->h_stream, &d->d_stream, &d->stream_cap, bound));
+    std::vector<size_t> off(n);
+    size_t o = 0;
+    for (int i = 0; i < n; ++i) { off[i] = o; o += (hdr[i].ecs_size + 16 + 15) / 16 * 16; }
+    std::vector<std::vector<JpegSub>> subs(n);
+    run_pool([&](int i) {
+      std::vector<uint8_t> stream;
+      std::vector<int> seg;
+      unstuff(hdr[i], stream, seg);
+      memcpy(d->h_stream + off[i], stream.data(), stream.size());
+      memset(d->h_stream + off[i] + stream.size(), 0, (hdr[i].ecs_size + 16 + 15) / 16 * 16 - stream.size());
+      plan_stream(hdr[i], seg, (int)stream.size(), &d->h_js[i], &subs[i]);
+      d->h_js[i].data_off = (long long)off[i];
+    });
+    size_t n_subs = 0;
+    for (int i = 0; i < n; ++i) { d->h_js[i].sub0 = (int)n_subs; n_subs += subs[i].size(); }
+    if (n_subs > d->sub_cap) {
+      if (d->d_scratch) SAG_CHECK_CUDA(cudaFree(d->d_scratch));
+      d->d_scratch = nullptr;
+    }
+    SAG_TRY(grow(&d->h_subs, &d->d_subs, &d->sub_cap, n_subs));
+    if (!d->d_scratch) SAG_CHECK_CUDA(cudaMalloc(&d->d_scratch, kScratchPerSub * d->sub_cap + 64));
+    for (int i = 0; i < n; ++i) memcpy(d->h_subs + d->h_js[i].sub0, subs[i].data(), subs[i].size() * sizeof(JpegSub));
+    // the batch's distinct Huffman tables (frames of one encoder share theirs)
+    std::vector<const HuffTable*> uniq;
+    auto row_of = [&](const HuffTable& t) {
+      for (size_t k = 0; k < uniq.size(); ++k)
+        if (memcmp(uniq[k], &t, sizeof(HuffTable)) == 0) return (int)k;
+      uniq.push_back(&t);
+      return (int)uniq.size() - 1;
+    };
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < 3; ++c) {
+        const int cc = std::min(c, hdr[i].ncomp - 1);
+        d->h_js[i].dc_tab[c] = row_of(hdr[i].dc[hdr[i].comp[cc].td]);
+        d->h_js[i].ac_tab[c] = row_of(hdr[i].ac[hdr[i].comp[cc].ta]);
+      }
+    SAG_TRY(grow(&d->h_tables, &d->d_tables, &d->table_cap, uniq.size()));
+    for (size_t k = 0; k < uniq.size(); ++k) memcpy(d->h_tables + k, uniq[k], sizeof(HuffTable));
+    SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_stream, d->h_stream, o, cudaMemcpyHostToDevice, st));
+    SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_subs, d->h_subs, n_subs * sizeof(JpegSub), cudaMemcpyHostToDevice, st));
+    SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_js, d->h_js, (size_t)n * sizeof(JpegStream), cudaMemcpyHostToDevice, st));
+    SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_tables, d->h_tables, uniq.size() * sizeof(HuffTable), cudaMemcpyHostToDevice, st));
+    SAG_CHECK_CUDA(cudaEventRecord(d->staged, st));
+    d->staged_pending = true;
+    SAG_CHECK_CUDA(cudaMemsetAsync(d->d_coef, 0, coef_total * sizeof(int16_t), st));
+    jpeg_huffman_kernel<<<n, kHuffThreads, 0, st>>>(d->d_js, d->d_subs, d->d_tables, d->d_img, d->d_stream, carve_scratch(d->d_scratch, d->sub_cap),
+                                                    d->d_coef, d->d_rounds);
+    SAG_LAUNCH_CHECK();
+    d->last_n = n;
+  } else {
+    // entropy decoding on the host: one file per task
+    std::atomic<int> failed(0);
+    std::string first_error;
+    std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+    run_pool([&](int i) {
       const JpegImage& im = d->h_img[i];
       int16_t* cp[3] = {nullptr, nullptr, nullptr};
       size_t cnt = 0;
@@ -579,24 +1102,13 @@ int sag_jpeg_decode(sag_jpeg* d, const void* const* host_files, const size_t* si
         if (first_error.empty()) first_error = "file " + std::to_string(i) + ": " + sag_last_error();
         err_lock.clear();
       }
-    }
-  };
-  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min(std::min(nt, n), 32));
-  if (nt == 1) {
-    work();
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nt - 1; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
+    });
+    SAG_REQUIRE(!failed.load(), SAG_EINVAL, "%s", first_error.c_str());
+    SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_coef, d->h_coef, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    SAG_CHECK_CUDA(cudaEventRecord(d->staged, st));
+    d->staged_pending = true;
+    d->last_n = 0;
   }
-  SAG_REQUIRE(!failed.load(), SAG_EINVAL, "%s", first_error.c_str());
-  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_coef, d->h_coef, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_qt, d->h_qt, (size_t)n * 3 * 64 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-  SAG_CHECK_CUDA(cudaMemcpyAsync(d->d_img, d->h_img, (size_t)n * sizeof(JpegImage), cudaMemcpyHostToDevice, st));
-  SAG_CHECK_CUDA(cudaEventRecord(d->staged, st));
-  d->staged_pending = true;
   jpeg_idct_kernel<<<dim3((unsigned)((max_blocks + kIdctBlocksPerCta - 1) / kIdctBlocksPerCta), n), 256, 0, st>>>(d->d_img, d->d_coef, d->d_qt,
                                                                                                                  d->d_planes);
   SAG_LAUNCH_CHECK();

@@ -76,7 +76,9 @@ class JpegDecoder(object):
     segments with a pool of host threads and runs the rest as CUDA kernels on the current stream (include/sag.h sag_jpeg_*).
     Baseline sequential files only (what ffmpeg's mjpeg encoder and PIL write by default); others raise."""
 
-    def __init__(self, max_frames, height, width, device=None, threads=0):
+    def __init__(self, max_frames, height, width, device=None, threads=0, device_huffman=True):
+        """device_huffman: decode the entropy-coded segments on the GPU too (parallel, self-synchronising subsequences: only the
+        compressed bytes cross PCIe); False: on `threads` host threads (0: one per core), the coefficients cross PCIe."""
         import ctypes as C
         import torch
         from . import _lib as L
@@ -85,6 +87,19 @@ class JpegDecoder(object):
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(L.lib().sag_jpeg_create(C.byref(self._h), self.max_frames, self.height, self.width))
+        self.set_option('device_huffman', int(bool(device_huffman)))
+
+    def set_option(self, key, value):
+        from . import _lib as L
+        L.check(L.lib().sag_jpeg_set_option(self._h, key.encode(), int(value)))
+
+    def sync_rounds(self, n):
+        """Synchronisation rounds the device entropy decoder needed for each of the first n frames of the last decode."""
+        import ctypes as C
+        from . import _lib as L
+        r = (C.c_int * n)()
+        L.check(L.lib().sag_jpeg_sync_rounds(self._h, r, n))
+        return list(r)
 
     def __del__(self):
         try:

@@ -90,6 +90,21 @@ def test_host_entropy_decoder_matches_the_oracle(name, data):
     assert (v[0].value, v[1].value, v[2].value) == (hdr['width'], hdr['height'], len(hdr['comps']))
 
 
+@pytest.mark.parametrize('name,data', CASES, ids=[c[0] for c in CASES])
+def test_parallel_entropy_decoder_emulated_on_the_host(name, data):
+    """The device's entropy decoder (subsequences decoded speculatively, synchronisation rounds, block-index scan, write pass,
+    DC prefix sums) run thread by thread on the host through the C ABI -- the same __host__ __device__ phase functions the kernel
+    runs -- against the serial decoder, for CTA sizes that give a thread one, a few or many subsequences."""
+    hdr, ref, bw, bh, _ = _native_coefficients(data)
+    n = sum(bw[c] * bh[c] * 64 for c in range(3))
+    for nthreads in (1, 7, 256):
+        out = np.full(ref.size, -7, np.int16)
+        rounds = C.c_int()
+        L.check(L.lib().sag_jpeg_coefficients_parallel(data, len(data), nthreads, out.ctypes.data, out.size, C.byref(rounds)))
+        assert np.array_equal(out[:n], ref[:n]), nthreads
+        assert 1 <= rounds.value <= 2050
+
+
 def test_unsupported_and_broken_files_fail_loudly():
     lib = L.lib()
     prog = _jpeg(_picture(32, 32), quality=80, progressive=True)
@@ -118,9 +133,12 @@ def test_gpu_decode_is_bit_identical_to_pil():
     from spatialaudiogen_b200 import readers as R
     for name, data in CASES:
         ref = _pil(data)
-        dec = R.JpegDecoder(2, ref.shape[0], ref.shape[1])
-        out = dec.decode([data, data]).cpu().numpy()
-        assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref), name
+        for device_huffman in (True, False):
+            dec = R.JpegDecoder(2, ref.shape[0], ref.shape[1], device_huffman=device_huffman)
+            out = dec.decode([data, data]).cpu().numpy()
+            assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref), (name, device_huffman)
+            if device_huffman:
+                assert all(1 <= r <= 2050 for r in dec.sync_rounds(2))
 
 
 @gpu
@@ -137,8 +155,11 @@ def test_gpu_decode_of_a_mixed_batch_of_frames():
     assert np.array_equal(out.cpu().numpy(), ref)
     rev = dec.decode(files[::-1][:20])
     assert np.array_equal(rev.cpu().numpy(), ref[::-1][:20])
-    one = R.JpegDecoder(32, 224, 448, threads=1).decode(files)
+    one = R.JpegDecoder(32, 224, 448, threads=1, device_huffman=False).decode(files)   # host entropy decoding, one thread
     assert torch.equal(one, out)
+    # a truncated file still decodes (missing data reads as zeros) and cannot write outside its frame
+    cut = dec.decode([files[0][:len(files[0]) // 2], files[1]])
+    assert torch.equal(cut[1], out[1]) and torch.equal(cut[0, :64], out[0, :64]) and not torch.equal(cut[0], out[0])
     with pytest.raises(ValueError):                                                  # a frame of another size
         dec.decode([_jpeg(_picture(64, 80), quality=80)])
     with pytest.raises(ValueError):

@@ -32,7 +32,7 @@ for _ in range(3):
 pil_ms = (time.perf_counter() - t) / 3 * 1e3
 print('PIL, one thread: %.2f ms per batch (%.3f ms per frame)' % (pil_ms, pil_ms / 32))
 for threads in (1, 4, 8, 16, 0):
-    dec = R.JpegDecoder(32, 224, 448, threads=threads)
+    dec = R.JpegDecoder(32, 224, 448, threads=threads, device_huffman=False)
     out = torch.empty((32, 224, 448, 3), dtype=torch.uint8, device='cuda')
     for _ in range(3):
         dec.decode(files, out=out)
@@ -43,11 +43,32 @@ for threads in (1, 4, 8, 16, 0):
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t) / 10 * 1e3
     assert np.array_equal(out.cpu().numpy(), ref)
-    print('JpegDecoder threads=%2d: %.2f ms per batch end to end (bit-identical to PIL)' % (threads, ms))
+    print('JpegDecoder, host entropy decoding, threads=%2d: %.2f ms per batch end to end (bit-identical to PIL)' % (threads, ms))
+for sub in (64, 128, 256, 512):
+    for threads in (1, 0):
+        dec = R.JpegDecoder(32, 224, 448, threads=threads)
+        dec.set_option('sub_bytes', sub)
+        for _ in range(3):
+            dec.decode(files, out=out)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(10):
+            dec.decode(files, out=out)
+        host_ms = (time.perf_counter() - t) / 10 * 1e3
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t) / 10 * 1e3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dec.decode(files, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref)
+        print('JpegDecoder, device entropy decoding, sub_bytes=%3d host threads=%2d: %.2f ms per batch (host part %.2f ms; device span of one '
+              'decode %.3f ms; rounds %s)' % (sub, threads, ms, host_ms, e0.elapsed_time(e1), sorted(set(dec.sync_rounds(32)))))
 # device part alone: events around a decode whose host part has already run are not separable through the public call, so time
 # two back-to-back decodes and subtract the host time measured with the GPU idle
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-dec = R.JpegDecoder(32, 224, 448)
+dec = R.JpegDecoder(32, 224, 448, device_huffman=False)
 torch.cuda.synchronize()
 e0.record()
 dec.decode(files, out=out)
