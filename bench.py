@@ -339,10 +339,10 @@ def main():
     out_host = torch.empty((B, SND_DUR, 3), dtype=torch.float32).pin_memory()
     # lanes: lane 0 is (model, out, the current stream); every further lane has its own handle (same weights), workspace,
     # output buffer and stream
-    lanes = [(model, out, None)]
-    for _ in range(1, n_lanes):
-        m2 = SptAudioGen(1, encoders=encoders, separation='unet_mask', precision=precision, device=dev).load_weights(model._w)
-        lanes.append((m2, torch.empty_like(out), torch.cuda.Stream(device=dev)))
+    for kv in filter(None, os.environ.get('SAG_BENCH_OPTS', '').split(',')):      # development: "overlap=0,cta_pair=1"
+        model.set_option(kv.split('=')[0], int(kv.split('=')[1]))
+    twins = model._lanes(n_lanes)                         # [model, twin, ...]: same configuration, options and weights
+    lanes = [(model, out, None)] + [(m2, torch.empty_like(out), torch.cuda.Stream(device=dev)) for m2 in twins[1:]]
 
     def fwd(d, lane=0):
         lanes[lane][0].forward_into(d['audio'], d.get(vkey), d.get(fkey), lanes[lane][1], d.get('flow_limits') if u8 else None)

@@ -88,6 +88,9 @@ const char* sag_version(void);
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int sag_config_default(sag_config* cfg);
+/* CRC-32C (Castagnoli) of host bytes, continuing from `crc` (0 to start): the tensor checksums of the TensorFlow V2 bundles
+ * that tf.train.Saver writes and deploy.py:79-87 restores (tf_checkpoint.read_bundle verifies them). Host code. */
+uint32_t sag_crc32c(const void* host_data, size_t size, uint32_t crc);
 int sag_create(sag_handle** out, const sag_config* cfg);         /* model.py:24-60 + deploy.py:42-77 */
 int sag_destroy(sag_handle* h);
 int sag_get_dims(const sag_handle* h, sag_dims* out);

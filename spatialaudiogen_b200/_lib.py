@@ -45,6 +45,7 @@ PROTOTYPES = {
     'sag_last_error': (C.c_char_p, []),
     'sag_version': (C.c_char_p, []),
     'sag_config_default': (_I, [C.POINTER(sag_config)]),
+    'sag_crc32c': (C.c_uint32, [_P, _S, C.c_uint32]),
     'sag_create': (_I, [C.POINTER(_P), C.POINTER(sag_config)]),
     'sag_destroy': (_I, [_P]),
     'sag_get_dims': (_I, [_P, C.POINTER(sag_dims)]),

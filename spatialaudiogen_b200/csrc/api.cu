@@ -32,6 +32,36 @@ extern "C" {
 const char* sag_last_error(void) { return last_error_cstr(); }
 const char* sag_version(void) { return "spatialaudiogen_b200 libsag 0.1 (sm_100a)"; }
 
+// CRC-32C (Castagnoli) of host bytes, continuing from `crc` (0 to start): the payload checksums of TensorFlow V2 checkpoint
+// bundles (tf_checkpoint.read_bundle verifies every tensor it restores; deploy.py:79-87).  Slicing by 8.
+uint32_t sag_crc32c(const void* host_data, size_t size, uint32_t crc) {
+  static uint32_t table[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 255];
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(host_data);
+  crc = ~crc;
+  while (size >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    v ^= crc;
+    crc = table[7][v & 255] ^ table[6][(v >> 8) & 255] ^ table[5][(v >> 16) & 255] ^ table[4][(v >> 24) & 255] ^
+          table[3][(v >> 32) & 255] ^ table[2][(v >> 40) & 255] ^ table[1][(v >> 48) & 255] ^ table[0][v >> 56];
+    p += 8;
+    size -= 8;
+  }
+  while (size--) crc = table[0][(crc ^ *p++) & 255] ^ (crc >> 8);
+  return ~crc;
+}
+
 int sag_config_default(sag_config* cfg) {
   SAG_REQUIRE(cfg != nullptr, SAG_EINVAL, "sag_config_default: NULL");
   memset(cfg, 0, sizeof(*cfg));

@@ -90,7 +90,52 @@ def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
     return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
 
 
-def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True, gpu_jpeg=True):
+def prefetch(iterable, depth=2):
+    """The reference's feeder thread + queue (feeder.py:281-435: reader threads fill a bounded queue the session dequeues from) for
+    one producer: `iterable` is consumed on a background thread, at most `depth` items ahead of the caller; items arrive in order,
+    an exception in the producer is re-raised in the caller at the same position.  depth <= 0: no thread."""
+    if depth <= 0:
+        for x in iterable:
+            yield x
+        return
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    end, stop = object(), threading.Event()
+
+    def put(x):
+        while not stop.is_set():
+            try:
+                q.put(x, timeout=0.1)
+                return True
+            except queue.Full:
+                pass
+        return False
+
+    def run():
+        try:
+            for x in iterable:
+                if not put((None, x)):
+                    return
+            put((None, end))
+        except BaseException as e:                              # noqa: B902 (handed to the consumer)
+            put((e, None))
+
+    t = threading.Thread(target=run, name='sag-feeder', daemon=True)
+    t.start()
+    try:
+        while True:
+            err, x = q.get()
+            if err is not None:
+                raise err
+            if x is end:
+                return
+            yield x
+    finally:
+        stop.set()                                              # an abandoned generator releases its producer
+
+
+def folder_batches(folders, params, batch_size=16, channel_masks=None, device=None, drop_remainder=True, gpu_jpeg=True, prefetch_depth=2):
     """The evaluation feeder (reference feeder.py:366-420 with for_eval=True, eval.py:43-60): every `folders[i]` (a per-video
     folder, see readers.py) is read in order with the eval schedule -- every 10th entry of audio_pow.lst, no shuffling, no
     rotations, silent chunks kept -- and the samples are grouped into batches of `batch_size` like `dequeue_many`.
@@ -98,11 +143,11 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
     batch is dropped by default, like the reference (its `dequeue_many` never returns it, feeder.py:412-419): the visual towers use
     batch statistics, so rows computed from a smaller batch correspond to nothing the reference computes.  drop_remainder=False
     yields it anyway (its dict carries 'short_batch': True).  gpu_jpeg: the frames' jpg files are decoded on the GPU, a batch at a
-    time (readers.JpegDecoder: bit-identical to the PIL decode of gpu_jpeg=False; baseline files only -- others raise)."""
+    time (readers.JpegDecoder: bit-identical to the PIL decode of gpu_jpeg=False; baseline files only -- others raise).
+    prefetch_depth: batches of files read ahead by a feeder thread (wav / jpg file reads overlap the GPU; 0: read inline)."""
     from . import readers, myutils
     from .definitions import VIDEO, FLOW
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else device
-    pending = []
     decoders = {}
 
     def flush(items):
@@ -124,21 +169,27 @@ def folder_batches(folders, params, batch_size=16, channel_masks=None, device=No
             b['flow_limits'] = torch.as_tensor(np.stack([np.asarray(c['flow_limits'], np.float64).reshape(-1, 2)[0] for c in items])).to(dev)
         return b
 
-    for folder in folders:
-        r = readers.SampleReader(folder, ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
-                                 context=params.context, duration=0.1, return_video=VIDEO in params.encoders,
-                                 img_prep=None, return_flow=FLOW in params.encoders, skip_silence_thr=None,
-                                 shuffle=False, random_rotations=False, skip_rate=10, raw_flow=True, jpeg_files=gpu_jpeg)
-        mask = np.ones(4) if channel_masks is None else np.asarray(channel_masks.get(r.video_id, np.ones(4)))
-        for c in r.loop_chunks():
-            c['mask'] = mask
-            pending.append(c)
-            if len(pending) == batch_size:
-                yield flush(pending)
-                pending = []
-    if pending and not drop_remainder:
-        b = flush(pending)
-        b['short_batch'] = True
+    def host_batches():                                        # host side only: file reads, wav parsing (runs on the feeder thread)
+        pending = []
+        for folder in folders:
+            r = readers.SampleReader(folder, ambi_order=params.ambi_order, audio_rate=params.audio_rate, video_rate=params.video_rate,
+                                     context=params.context, duration=0.1, return_video=VIDEO in params.encoders,
+                                     img_prep=None, return_flow=FLOW in params.encoders, skip_silence_thr=None,
+                                     shuffle=False, random_rotations=False, skip_rate=10, raw_flow=True, jpeg_files=gpu_jpeg)
+            mask = np.ones(4) if channel_masks is None else np.asarray(channel_masks.get(r.video_id, np.ones(4)))
+            for c in r.loop_chunks():
+                c['mask'] = mask
+                pending.append(c)
+                if len(pending) == batch_size:
+                    yield pending
+                    pending = []
+        if pending and not drop_remainder:
+            yield pending
+
+    for items in prefetch(host_batches(), prefetch_depth):
+        b = flush(items)
+        if len(items) < batch_size:
+            b['short_batch'] = True
         yield b
 
 

@@ -17,6 +17,7 @@ Third-party format, restated from its published specification; TensorFlow itself
 reader is pinned by round trips against the writer and by the format's own checksums (parity unpinned against real
 TF output -- DESIGN.md section 5).  Pure host code: no kernels, no oracle.
 """
+import ctypes as C
 import os
 import re
 import struct
@@ -49,9 +50,24 @@ _CRC_TABLE = _make_table()
 _CRC_TABLE_L = [int(x) for x in _CRC_TABLE]
 
 
+_native_crc = None
+
+
 def crc32c(data, crc=0):
-    """CRC-32C of `data` (bytes-like).  Byte-at-a-time table walk: fine for index blocks and small tensors; large
-    tensors are only checked when the caller asks for it."""
+    """CRC-32C of `data` (bytes-like), continuing from `crc`.  Long buffers (tensor payloads: 25 MB for `video-fc`) go through
+    libsag.so's slicing-by-8 routine when the library is built; otherwise, and for the short index blocks, a byte-at-a-time
+    table walk in Python."""
+    global _native_crc
+    mv = memoryview(data).cast('B')
+    if len(mv) >= 1024 and _native_crc is not False:
+        if _native_crc is None:
+            try:
+                from . import _lib
+                _native_crc = _lib.lib().sag_crc32c
+            except Exception:
+                _native_crc = False
+        if _native_crc:
+            return int(_native_crc(bytes(mv) if mv.readonly else (C.c_char * len(mv)).from_buffer(mv), len(mv), crc))
     crc ^= 0xFFFFFFFF
     t = _CRC_TABLE_L
     for b in memoryview(data).cast('B'):
@@ -279,9 +295,9 @@ def list_variables(prefix, verify=True):
     return out
 
 
-def read_bundle(prefix, names=None, verify_data=False):
+def read_bundle(prefix, names=None, verify_data=True):
     """OrderedDict name -> ndarray of the tensors in `<prefix>.index` / `.data-*` (all, or those in `names`).
-    Index blocks are always checksummed; tensor payloads when verify_data (slow in pure Python for large tensors)."""
+    Index blocks are always checksummed; tensor payloads too unless verify_data=False."""
     entries = read_table(prefix + '.index', verify=True)
     header = dict(entries).get(b'')
     num_shards = 1

@@ -233,3 +233,40 @@ def test_stage_methods_glue_matches_oracle(monkeypatch):
     assert torch.equal(y, ref)
     m.separation = 'none'
     assert torch.equal(m.separation_ops(mono, s, None, None), mono[:, :, 24000:28800].unsqueeze(1))
+
+
+def test_prefetch_feeder_thread_keeps_order_and_propagates_errors():
+    """evaluate.prefetch (the reference's feeder thread + bounded queue, feeder.py:281-435, for one producer)."""
+    import threading
+    import time
+    import pytest
+    from spatialaudiogen_b200 import evaluate as E
+    main = threading.get_ident()
+    seen = []
+
+    def produce(n, fail_at=None):
+        for i in range(n):
+            seen.append(threading.get_ident())
+            if i == fail_at:
+                raise KeyError('item %d' % i)
+            yield i
+
+    assert list(E.prefetch(produce(50), 3)) == list(range(50)) and all(t != main for t in seen)      # on another thread, in order
+    del seen[:]
+    assert list(E.prefetch(produce(5), 0)) == list(range(5)) and all(t == main for t in seen)        # depth 0: inline
+    got = []
+    with pytest.raises(KeyError):
+        for x in E.prefetch(produce(10, fail_at=4), 2):
+            got.append(x)
+    assert got == [0, 1, 2, 3]                                                                       # the error arrives in position
+    # bounded: the producer runs at most depth (+1 in hand) items ahead of a slow consumer; an abandoned generator stops it
+    del seen[:]
+    g = E.prefetch(produce(1000), 2)
+    assert next(g) == 0
+    time.sleep(0.3)
+    assert len(seen) <= 5
+    g.close()
+    time.sleep(0.3)
+    n = len(seen)
+    time.sleep(0.2)
+    assert len(seen) == n and n < 20
