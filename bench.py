@@ -381,7 +381,8 @@ def main():
 
     # Small batches are bound by the host's launch rate (~70 kernels per step), not by the GPU: replay the whole step --
     # forward + metrics, programmatic dependent launches included -- as one CUDA graph per rotating input slot.
-    use_graph = B <= 16 and os.environ.get('SAG_BENCH_GRAPH', '1') != '0'
+    graph_env = os.environ.get('SAG_BENCH_GRAPH', '1')             # 0: never, 1: host-bound batch sizes (<= 16), 2: always
+    use_graph = (B <= 16 or graph_env == '2') and graph_env != '0'
     graphs, rows_slot = [], []
     if use_graph:
         try:
@@ -478,7 +479,8 @@ def main():
         e2e_keys['flow'] = fkey
         if u8:
             e2e_keys['flow_limits'] = 'flow_limits'
-    n_e2e = min(n_batches, 200) if args.config in (4, 5) else args.steps
+    # (at least 100 steps: the loop keeps several batches in flight, and a 20-step sample is mostly pipeline fill and drain)
+    n_e2e = min(n_batches, 200) if args.config in (4, 5) else max(args.steps, 100)
 
     def host_batches(n):
         for i in range(n):
@@ -486,7 +488,8 @@ def main():
 
     def run_e2e(n):
         acc = 0.0
-        for y in model.inference_stream(host_batches(n), depth=int(os.environ.get('SAG_STREAM_DEPTH', '3')), lanes=n_lanes):
+        for y in model.inference_stream(host_batches(n), depth=int(os.environ.get('SAG_STREAM_DEPTH', '3')), lanes=n_lanes,
+                                        use_graph={'0': False, '2': True}.get(graph_env)):
             acc += float(y[0, 0, 0])                      # the caller consumes each waveform on the host
         return acc
 
@@ -504,7 +507,7 @@ def main():
     ms2 = float(ms2.item())
     h2d = sum(int(host[0][src].numel() * host[0][src].element_size()) for src in e2e_keys.values())
     e2e = {'value': WINDOW_S * B * int(cnt.item()) / (ms2 * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-           'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms2 / max(n_e2e, 1),
+           'd2h_bytes_per_step': int(out_host.numel() * 4), 'ms_per_step': ms2 / max(n_e2e, 1), 'steps': n_e2e,
            'api': 'SptAudioGen.inference_stream(pinned host batches, lanes=%d) -> host (B,4800,3) waveforms; copies overlap compute' % n_lanes}
 
     # ---- roofline of the dominant kernel family, timed live with CUDA events on the launching stream ----

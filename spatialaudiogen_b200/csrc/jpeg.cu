@@ -447,11 +447,35 @@ struct JpegStream {           // the scan of one frame
 
 struct HuffView { const HuffTable* dc[3]; const HuffTable* ac[3]; };
 
-__host__ __device__ inline uint32_t peek32(const uint8_t* s, int p) {
-  const uint8_t* b = s + (p >> 3);
-  const uint64_t v = ((uint64_t)b[0] << 32) | ((uint64_t)b[1] << 24) | ((uint64_t)b[2] << 16) | ((uint64_t)b[3] << 8) | (uint64_t)b[4];
-  return (uint32_t)(v >> (8 - (p & 7)));
-}
+// The stream as big-endian 32-bit words with the two words around the read position cached in registers: a symbol costs a
+// global load only when the position crosses a word (streams start 16-byte aligned and are padded with 16 zero bytes).
+struct BitWindow {
+  const uint32_t* words;
+  int idx;
+  uint32_t w0, w1;
+  __host__ __device__ static inline uint32_t be(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+  }
+  __host__ __device__ inline void init(const uint8_t* s, int p) {
+    words = reinterpret_cast<const uint32_t*>(s);
+    idx = p >> 5;
+    w0 = be(words[idx]);
+    w1 = be(words[idx + 1]);
+  }
+  __host__ __device__ inline uint32_t peek32(int p) {     // the 32 bits that start at bit p (p never moves backwards)
+    const int i = p >> 5;
+    if (i != idx) {
+      if (i == idx + 1) { w0 = w1; w1 = be(words[i + 1]); }
+      else { w0 = be(words[i]); w1 = be(words[i + 1]); }
+      idx = i;
+    }
+    return (uint32_t)(((((uint64_t)w0) << 32) | (uint64_t)w1) >> (32 - (p & 31)));
+  }
+};
 
 // one Huffman symbol at the top of `w`: its code length (>= 1, so the decoder always advances) and value
 __host__ __device__ inline int huff_symbol(const HuffTable& t, uint32_t w, int* len) {
@@ -478,12 +502,14 @@ template <bool WRITE>
 __host__ __device__ inline int decode_span(const uint8_t* s, const HuffView& hv, const JpegStream& js, SubState& st, int end_bit,
                                            long long q, long long q_end, const JpegImage* im, int16_t* coef, const uint8_t* zigzag) {
   int p = st.p, b = st.b, z = st.z, done = 0;
+  BitWindow bw;
+  bw.init(s, p);
   int16_t* blk = nullptr;
   if (WRITE && q < q_end) blk = block_ptr(js, *im, coef, q);
   while (p < end_bit) {
     if (WRITE && q >= q_end) break;                     // only padding bits are left in this restart segment
     const int c = js.blk_comp[b];
-    const uint32_t w = peek32(s, p);
+    const uint32_t w = bw.peek32(p);
     int len;
     if (z == 0) {
       const int sz = huff_symbol(*hv.dc[c], w, &len) & 15;

@@ -72,22 +72,46 @@ def metric_rows(pred, target, mono=None, layout=None, audio_rate=48000, rms_maps
     return rows, maps
 
 
-def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False):
+def evaluate_batches(model, batches, audio_rate=48000, rms_maps=False, lanes=3):
     """eval.py:140-201 for an iterable of dicts {'id': list, 'ambix': (B, snd_size, 4), 'video'/'flow': ..., 'mask': (B,4)}
-    (CUDA float32 tensors).  Returns (ids, rows (N, 28) CUDA)."""
+    (CUDA float32 tensors; uint8 frames as decoded).  Returns (ids, rows (N, 28) CUDA).  Consecutive batches are independent, so up
+    to `lanes` of them are in flight, each on its own stream with a twin of the model (SptAudioGen._lanes: same weights and
+    options); rows come back in batch order and do not depend on `lanes`."""
     ids, out = [], []
     ss, t = model.snd_contx // 2, model.snd_dur                            # eval.py:67-68
-    for b in batches:
-        ambix = b['ambix']
-        audio_input = ambix[:, :, :1].contiguous()                          # eval.py:69
-        target = ambix[:, ss:ss + t, 1:].contiguous()                       # eval.py:70
-        pred = torch.empty((ambix.shape[0], t, 3), dtype=torch.float32, device=ambix.device)
-        model.forward_into(audio_input, b.get('video'), b.get('flow'), pred, b.get('flow_limits'))   # the hot loop (fused inverse STFT + mixing)
-        rows, _ = metric_rows(pred, target, mono=audio_input[:, ss:ss + t], layout=b.get('mask'), audio_rate=audio_rate,
-                              rms_maps=rms_maps)
-        ids.extend(b['id'])
-        out.append(rows)
-    return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
+    lanes = max(1, int(lanes))
+    with torch.cuda.device(model.device):
+        main = torch.cuda.current_stream()
+        models = model._lanes(lanes)
+        streams = [main] + [torch.cuda.Stream(device=model.device) for _ in range(lanes - 1)]
+        try:
+            for i, b in enumerate(batches):
+                m, st = models[i % lanes], streams[i % lanes]
+                ready = torch.cuda.Event()
+                ready.record(main)                                          # the batch was produced on the caller's stream
+                with torch.cuda.stream(st):
+                    st.wait_event(ready)
+                    ambix = b['ambix']
+                    audio_input = ambix[:, :, :1].contiguous()              # eval.py:69
+                    target = ambix[:, ss:ss + t, 1:].contiguous()           # eval.py:70
+                    pred = torch.empty((ambix.shape[0], t, 3), dtype=torch.float32, device=ambix.device)
+                    m.forward_into(audio_input, b.get('video'), b.get('flow'), pred, b.get('flow_limits'))   # the hot loop (fused inverse STFT + mixing)
+                    rows, _ = metric_rows(pred, target, mono=audio_input[:, ss:ss + t], layout=b.get('mask'), audio_rate=audio_rate,
+                                          rms_maps=rms_maps)
+                    if st is not main:
+                        for v in b.values():                                # memory of the caller's stream read on this one
+                            if isinstance(v, torch.Tensor) and v.is_cuda:
+                                v.record_stream(st)
+                ids.extend(b['id'])
+                out.append(rows)
+        finally:
+            for st in streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+        for r in out:
+            r.record_stream(main)
+        return ids, (torch.cat(out, 0) if out else torch.empty((0, N_COLS)))
 
 
 def prefetch(iterable, depth=2):

@@ -546,6 +546,11 @@ def test_evaluate_from_video_folders(tmp_path):
     assert tuple(batches[0]['ambix'].shape) == (3, 52799, 4) and tuple(batches[0]['video'].shape) == (3, 1, 224, 448, 3)
     ids, rows = E.evaluate_batches(m, batches, rms_maps=True)
     assert ids == batches[0]['id'] and tuple(rows.shape) == (3, 28) and not torch.isnan(rows).any()
+    # batches in flight on lane twins: same rows in the same order, whatever the number of lanes
+    many = [batches[0]] * 5
+    ids1, rows1 = E.evaluate_batches(m, many, rms_maps=True, lanes=1)
+    ids3, rows3 = E.evaluate_batches(m, many, rms_maps=True, lanes=3)
+    assert ids1 == ids3 == batches[0]['id'] * 5 and torch.equal(rows1, rows3) and torch.equal(rows1[:3], rows)
     amb = batches[0]['ambix']
     pred = m.inference_ops(amb[:, :, :1].contiguous(), video=batches[0]['video'])
     ref_rows, _ = E.metric_rows(pred, amb[:, 24000:28800, 1:].contiguous(), mono=amb[:, 24000:28800, :1].contiguous(),
