@@ -327,6 +327,7 @@ def main():
     # R distinct synthetic batches, resident in HBM (value) and in pinned host memory (e2e)
     n_lanes = max(1, args.lanes)
     R = (max(1, args.rotate) + n_lanes - 1) // n_lanes * n_lanes   # (a multiple of the lanes: slot r always runs on lane r % lanes)
+    args.rotate = R
     u8 = args.frames == 'u8'
     vkey, fkey = ('video_u8', 'flow_u8') if u8 else ('video', 'flow')
     host, devb = [], []
