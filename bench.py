@@ -494,8 +494,13 @@ def main():
             acc += float(y[0, 0, 0])                      # the caller consumes each waveform on the host
         return acc
 
-    run_e2e(3)
+    run_e2e(4 * n_lanes + 3)                             # warm-up: every slot of the loop (pinned / device buffers, graphs) is touched
     barrier()
+    for _ in range(int(os.environ.get('SAG_E2E_REPEAT', '0'))):      # development: spread of the e2e sample within one process
+        t0 = time.perf_counter()
+        run_e2e(n_e2e)
+        torch.cuda.synchronize()
+        sys.stderr.write('e2e repeat: %.1f audio-s/s\n' % (WINDOW_S * B * n_e2e / (time.perf_counter() - t0)))
     e0.record()
     run_e2e(n_e2e)
     e1.record()

@@ -105,16 +105,32 @@ class W2XYZ(object):
         time like the reference does, so host memory holds a few batches of inputs plus the growing output.  Returns
         (N*snd_dur, 4) float64 rows [W, Y, Z, X].  Full batches go through SptAudioGen.inference_stream (copies on their own
         streams, `lanes` forwards in flight, the batch of 10 replayed as a CUDA graph; same bits as one run_batch per batch);
-        the short last batch, which the reference zero-pads AFTER preparing its frames, goes through run_batch."""
+        the short last batch, which the reference zero-pads AFTER preparing its frames, goes through run_batch.  Windows whose
+        'video' / 'flow' are lists of jpg FILES (bytes: SampleReader(jpeg_files=True)) are decoded on the GPU, a batch at a time
+        (readers.JpegDecoder, bit-identical to the PIL decode)."""
         ss = self.model.snd_contx // 2
         mono, pred = [], []
         enc = self.params.encoders
         tail = []
 
+        decoders = {}
+
+        def frames(batch, k):
+            if k not in enc:
+                return None
+            if not isinstance(batch[0][k], (list, tuple)):
+                return np.stack([c[k] for c in batch], 0)
+            files = [f for c in batch for f in c[k]]            # undecoded jpg files: a whole batch goes to the GPU
+            if k not in decoders:
+                h, w = readers.jpeg_info(files[0])[:2]
+                decoders[k] = readers.JpegDecoder(self.batch_size * len(batch[0][k]), h, w, device=self.model.device)
+            with torch.cuda.device(self.model.device):
+                x = decoders[k].decode(files)
+            return x.view(len(batch), len(batch[0][k]), x.shape[1], x.shape[2], 3)
+
         def pack(batch):
             a = np.stack([np.asarray(c['ambix'], np.float64) for c in batch], 0)
-            v = np.stack([c['video'] for c in batch], 0) if VIDEO in enc else None
-            f = np.stack([c['flow'] for c in batch], 0) if FLOW in enc else None
+            v, f = frames(batch, VIDEO), frames(batch, FLOW)
             fl = np.stack([np.asarray(c['flow_limits']).reshape(-1, 2)[0] for c in batch], 0) if (f is not None and 'flow_limits' in batch[0]) else None
             mono.append(np.copy(a[:, ss:ss + self.model.snd_dur, :1]).reshape(-1, 1))
             return a, v, f, fl
@@ -130,10 +146,13 @@ class W2XYZ(object):
                     for k, x in ((VIDEO, v), (FLOW, f)):
                         if x is None:
                             continue
+                        if k == FLOW and x.dtype in (np.uint8, torch.uint8) and fl is None:
+                            raise ValueError('uint8 flow frames need flow_limits')
+                        if isinstance(x, torch.Tensor):         # decoded on the GPU
+                            b[k] = x
+                            continue
                         if x.dtype != np.uint8:
                             x = np.asarray(x, dtype=np.float32)
-                        elif k == FLOW and fl is None:
-                            raise ValueError('uint8 flow frames need flow_limits')
                         b[k] = torch.from_numpy(np.ascontiguousarray(x))
                     if FLOW in b and b[FLOW].dtype == torch.uint8:
                         b['flow_limits'] = torch.from_numpy(np.ascontiguousarray(fl, dtype=np.float64))
@@ -144,6 +163,7 @@ class W2XYZ(object):
             pred.append(y.numpy().reshape(-1, y.shape[2]).copy())
         if tail:
             a, v, f, fl = pack(tail)
+            v, f = [x.cpu().numpy() if isinstance(x, torch.Tensor) else x for x in (v, f)]
             out = self.run_batch(a[:, :, :1], v, f, fl)
             pred.append(out.reshape(-1, out.shape[2]))
         if not pred:
@@ -162,18 +182,19 @@ class W2XYZ(object):
                 yield c
         return self.deploy_stream(it())
 
-    def deploy(self, input_folder, deploy_start, deploy_duration):
+    def deploy(self, input_folder, deploy_start, deploy_duration, gpu_jpeg=True):
         """deploy.py:90-152: read the windows of `input_folder` (the per-video folder layout of readers.SampleReader)
         scheduled by its audio_pow.lst from `deploy_start` for `deploy_duration` seconds -- the schedule is shifted so
         that the first window sits exactly at deploy_start (deploy.py:108-109) -- and generate their ambisonics, batch by
-        batch (the reader is consumed lazily; video frames travel as uint8 and are prepared on the device).
+        batch (the reader is consumed lazily; gpu_jpeg: the frames' jpg files are decoded on the GPU -- baseline files only --
+        else by PIL and travel as uint8; either way they are prepared on the device).
         Returns (N*snd_dur, 4) float64 rows [W, Y, Z, X]."""
         p = self.params
         reader = readers.SampleReader(input_folder, ambi_order=p.ambi_order, audio_rate=p.audio_rate, video_rate=p.video_rate,
                                       context=p.context, duration=self.duration, return_video=VIDEO in p.encoders,
                                       img_prep=None, return_flow=FLOW in p.encoders, start_time=deploy_start,
                                       sample_duration=deploy_duration, skip_silence_thr=None, shuffle=False,
-                                      random_rotations=False, skip_rate=None, raw_flow=True)
+                                      random_rotations=False, skip_rate=None, raw_flow=True, jpeg_files=gpu_jpeg)
         if not reader.chunks_t:
             raise ValueError('%s has no windows in [%s, %s)' % (input_folder, deploy_start, deploy_start + deploy_duration))
         dt = reader.chunks_t[0] - deploy_start

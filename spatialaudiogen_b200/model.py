@@ -288,7 +288,8 @@ class SptAudioGen(StageOps):
     def inference_stream(self, batches, depth=2, use_graph=None, lanes=3):
         """The driver loop around `sess.run` (reference deploy.py:112-148, eval.py:140-201) as a generator: `batches`
         yields dicts of HOST tensors {'audio': (B, snd_size, 1)[, 'video', 'flow': (B, 1, H, W, 3)]} (pinned memory
-        makes the copies asynchronous); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
+        makes the copies asynchronous; CUDA tensors -- e.g. frames decoded on the GPU by readers.JpegDecoder on the caller's stream --
+        are taken with device copies ordered after that stream); for each one a HOST (B, snd_dur, 3) float32 tensor (pinned, reused every
         `depth` steps) is yielded in order.  'video' / 'flow' may be the uint8 frames as decoded from disk (a quarter of the
         PCIe bytes; they are prepared on the device, see forward_into) -- uint8 flow comes with 'flow_limits' (B, 2) float64.
         use_graph: replay each slot's forward as a CUDA graph (capture_graph); default: batches of at most 16 windows, where
@@ -307,11 +308,13 @@ class SptAudioGen(StageOps):
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
             models = self._lanes(lanes)
-            compute = [main] + [torch.cuda.Stream(device=dev) for _ in range(lanes - 1)]
+            # every lane computes on a stream of its own (one lane: the caller's stream), so that the caller's stream only orders
+            compute = [main] if lanes == 1 else [torch.cuda.Stream(device=dev) for _ in range(lanes)]
             start = torch.cuda.Event()
             start.record(main)
-            for cs in compute[1:]:
-                cs.wait_event(start)                       # the lanes start after what the caller queued before this loop
+            for cs in compute:
+                if cs is not main:
+                    cs.wait_event(start)                   # the lanes start after what the caller queued before this loop
             side = torch.cuda.Stream(device=dev)           # host -> device copies
             back = torch.cuda.Stream(device=dev)           # device -> host copies (own stream: a D2H waiting for its
                                                            # forward must not block the next step's H2D behind it)
@@ -348,10 +351,19 @@ class SptAudioGen(StageOps):
                     sl = slots[idx]
                     if sl['in'][AUDIO].shape != b[AUDIO].shape:
                         raise ValueError('all batches of a stream must have the same shape')
+                    srcs = {k: torch.as_tensor(b[k]) for k in sl['in']}
+                    produced = None
+                    if any(t.is_cuda for t in srcs.values()):  # device-resident inputs (frames decoded on the GPU): the copies
+                        produced = torch.cuda.Event()          # follow what the caller queued on its stream to produce them
+                        produced.record(main)
                     with torch.cuda.stream(side):
                         side.wait_event(sl['free'])            # previous forward that read these inputs has finished
+                        if produced is not None:
+                            side.wait_event(produced)
                         for k, t in sl['in'].items():
-                            t.copy_(torch.as_tensor(b[k]), non_blocking=True)
+                            t.copy_(srcs[k], non_blocking=True)
+                            if srcs[k].is_cuda:
+                                srcs[k].record_stream(side)
                         sl['in_ready'].record(side)
                     m, cs = models[idx % lanes], compute[idx % lanes]
                     with torch.cuda.stream(cs):
@@ -380,10 +392,11 @@ class SptAudioGen(StageOps):
                 while pending:
                     yield finish(pending.pop(0))
             finally:
-                for cs in compute[1:]:                         # what the caller queues next follows every lane
-                    ev = torch.cuda.Event()
-                    ev.record(cs)
-                    main.wait_event(ev)
+                for cs in compute:                             # what the caller queues next follows every lane
+                    if cs is not main:
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                        main.wait_event(ev)
 
     def _view(self, name):
         lib = L.lib()

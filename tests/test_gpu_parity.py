@@ -527,6 +527,14 @@ def test_w2xyz_deploy_reads_a_video_folder(tmp_path):
     chunks = list(r.loop_chunks())
     ref = w.deploy_windows(np.stack([c['ambix'] for c in chunks]), np.stack([c['video'] for c in chunks]).astype(np.float32))
     assert np.array_equal(out, ref)
+    # two full batches of 10 + a tail of 5: the frames' jpg files decoded on the GPU (full batches stay on the device, lanes in
+    # flight) against the PIL readers
+    with open(os.path.join(folder, 'audio_pow.lst'), 'w') as f:
+        for k in range(30):
+            f.write('%.1f %.3f\n' % (0.5 + 0.1 * k, 0.3))
+    gpu = w.deploy(folder, 0.5, 2.5, gpu_jpeg=True)
+    pil = w.deploy(folder, 0.5, 2.5, gpu_jpeg=False)
+    assert gpu.shape == (25 * 4800, 4) and np.array_equal(gpu, pil)
 
 
 def test_evaluate_from_video_folders(tmp_path):
