@@ -343,7 +343,9 @@ def main():
     for kv in filter(None, os.environ.get('SAG_BENCH_OPTS', '').split(',')):      # development: "overlap=0,cta_pair=1"
         model.set_option(kv.split('=')[0], int(kv.split('=')[1]))
     twins = model._lanes(n_lanes)                         # [model, twin, ...]: same configuration, options and weights
-    lanes = [(model, out, None)] + [(m2, torch.empty_like(out), torch.cuda.Stream(device=dev)) for m2 in twins[1:]]
+    prio = [int(x) for x in os.environ.get('SAG_LANE_PRIO', '0,0,0,0,0,0,0,0').split(',')]      # development: stream priority per lane
+    lanes = [(model, out, None)] + [(m2, torch.empty_like(out), torch.cuda.Stream(device=dev, priority=prio[i + 1]))
+                                    for i, m2 in enumerate(twins[1:])]
 
     def fwd(d, lane=0):
         lanes[lane][0].forward_into(d['audio'], d.get(vkey), d.get(fkey), lanes[lane][1], d.get('flow_limits') if u8 else None)

@@ -439,13 +439,15 @@ struct JpegStream {           // the scan of one frame
   long long data_off;         // byte offset of the unstuffed stream in the batch's buffer (padded with 16 zero bytes)
   int sub0, n_subs;           // its rows of the batch's JpegSub table
   int bpm;                    // blocks per MCU
+  unsigned comp_nib;          // component of block i of an MCU in bits 4i..4i+3 (what the decode loop reads)
   int blk_comp[6], blk_x[6], blk_y[6];
   int mcux, n_mcus;
   int restart_mcus;           // MCUs per restart segment (0: one segment)
   int dc_tab[3], ac_tab[3];   // rows of the batch's table array
 };
 
-struct HuffView { const HuffTable* dc[3]; const HuffTable* ac[3]; };
+// the frame's tables, contiguous: DC of components 0..ncomp-1, then AC (addresses by arithmetic: no pointer array in local memory)
+struct HuffView { const HuffTable* base; int ncomp; };
 
 // The stream as big-endian 32-bit words with the two words around the read position cached in registers: a symbol costs a
 // global load only when the position crosses a word (streams start 16-byte aligned and are padded with 16 zero bytes).
@@ -473,7 +475,11 @@ struct BitWindow {
       else { w0 = be(words[i]); w1 = be(words[i + 1]); }
       idx = i;
     }
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(w1, w0, p & 31);             // high word of (w0:w1) << (p % 32): one instruction
+#else
     return (uint32_t)(((((uint64_t)w0) << 32) | (uint64_t)w1) >> (32 - (p & 31)));
+#endif
   }
 };
 
@@ -502,43 +508,40 @@ template <bool WRITE>
 __host__ __device__ inline int decode_span(const uint8_t* s, const HuffView& hv, const JpegStream& js, SubState& st, int end_bit,
                                            long long q, long long q_end, const JpegImage* im, int16_t* coef, const uint8_t* zigzag) {
   int p = st.p, b = st.b, z = st.z, done = 0;
+  const int bpm = js.bpm, ncomp = hv.ncomp;             // (loop invariants in registers: js lives in shared memory)
+  const unsigned nib = js.comp_nib;
+  const HuffTable* const tabs = hv.base;
   BitWindow bw;
   bw.init(s, p);
   int16_t* blk = nullptr;
   if (WRITE && q < q_end) blk = block_ptr(js, *im, coef, q);
   while (p < end_bit) {
     if (WRITE && q >= q_end) break;                     // only padding bits are left in this restart segment
-    const int c = js.blk_comp[b];
+    const int c = (int)((nib >> (4 * b)) & 15u);
     const uint32_t w = bw.peek32(p);
+    // one path for DC and AC symbols (threads of a warp sit at different places of their blocks): a DC symbol is its size
+    // (<= 11, so its "run" nibble is 0), an AC symbol (run << 4) | size
     int len;
-    if (z == 0) {
-      const int sz = huff_symbol(*hv.dc[c], w, &len) & 15;
+    const int rs = huff_symbol(tabs[z == 0 ? c : ncomp + c], w, &len);
+    const int r = rs >> 4, sz = rs & 15;
+    p += len + sz;
+    if (sz) {
+      z += r;
       if (WRITE) {
-        const int r = sz ? (int)((w << len) >> (32 - sz)) : 0;
-        blk[0] = (int16_t)(sz ? (r < (1 << (sz - 1)) ? r - (1 << sz) + 1 : r) : 0);
+        const int v = (int)((w << len) >> (32 - sz));
+        blk[zigzag[z & 63]] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
       }
-      p += len + sz;
-      z = 1;
+      z += 1;
+    } else if (z == 0) {
+      z = 1;                      // DC difference 0 (the block is zero-initialised)
+    } else if (r == 15) {
+      z += 16;
     } else {
-      const int rs = huff_symbol(*hv.ac[c], w, &len);
-      const int r = rs >> 4, sz = rs & 15;
-      p += len + sz;
-      if (sz) {
-        z += r;
-        if (WRITE) {
-          const int v = (int)((w << len) >> (32 - sz));
-          blk[zigzag[z & 63]] = (int16_t)(v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v);
-        }
-        z += 1;
-      } else if (r == 15) {
-        z += 16;
-      } else {
-        z = 64;
-      }
+      z = 64;
     }
     if (z >= 64) {
       z = 0;
-      b = b + 1 == js.bpm ? 0 : b + 1;
+      b = b + 1 == bpm ? 0 : b + 1;
       ++done;
       if (WRITE) { ++q; if (q < q_end) blk = block_ptr(js, *im, coef, q); }
     }
@@ -671,7 +674,8 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegSt
   }
   __syncthreads();
   HuffView hv;
-  for (int c = 0; c < 3; ++c) { hv.dc[c] = tab + min(c, im.ncomp - 1); hv.ac[c] = tab + im.ncomp + min(c, im.ncomp - 1); }
+  hv.base = tab;
+  hv.ncomp = im.ncomp;
   const uint8_t* s = data + js.data_off;
   int cur = 0, round = 0;
   for (;; ++round) {
@@ -733,7 +737,11 @@ void plan_stream(const Header& h, const std::vector<int>& seg_start, int stream_
   js->bpm = 0;
   for (int c = 0; c < h.ncomp; ++c)
     for (int y = 0; y < h.comp[c].v; ++y)
-      for (int x = 0; x < h.comp[c].h; ++x) { js->blk_comp[js->bpm] = c; js->blk_x[js->bpm] = x; js->blk_y[js->bpm] = y; ++js->bpm; }
+      for (int x = 0; x < h.comp[c].h; ++x) {
+        js->blk_comp[js->bpm] = c; js->blk_x[js->bpm] = x; js->blk_y[js->bpm] = y;
+        js->comp_nib |= (unsigned)c << (4 * js->bpm);
+        ++js->bpm;
+      }
   js->mcux = h.mcux;
   js->n_mcus = h.mcux * h.mcuy;
   js->restart_mcus = h.restart_interval;
@@ -973,8 +981,11 @@ int sag_jpeg_coefficients_parallel(const void* host_file, size_t size, int nthre
   std::vector<JpegSub> subs;
   plan_stream(*h, seg, nbytes, &js, &subs);
   js.sub0 = 0;
+  std::vector<HuffTable> tabs(2 * h->ncomp);
+  for (int c = 0; c < h->ncomp; ++c) { tabs[c] = h->dc[h->comp[c].td]; tabs[h->ncomp + c] = h->ac[h->comp[c].ta]; }
   HuffView hv;
-  for (int c = 0; c < 3; ++c) { const int cc = std::min(c, h->ncomp - 1); hv.dc[c] = &h->dc[h->comp[cc].td]; hv.ac[c] = &h->ac[h->comp[cc].ta]; }
+  hv.base = tabs.data();
+  hv.ncomp = h->ncomp;
   std::vector<char> raw(kScratchPerSub * subs.size() + 64);
   HuffScratch sc = carve_scratch(raw.data(), subs.size());
   std::vector<int> total(nthreads), reset(nthreads);
