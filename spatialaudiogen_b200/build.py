@@ -44,6 +44,8 @@ def build(force=False, verbose=False):
         cmd = [nvcc, '-c', src, '-o', obj, '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC'] + ARCH
         if verbose:
             cmd += ['-Xptxas', '-v']
+        if os.path.basename(src) == 'conv_umma.cu' and os.environ.get('SAG_CONV_REG128'):      # development: register cap of the tcgen05 kernels
+            cmd += ['-DSAG_CONV_REG128']
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:

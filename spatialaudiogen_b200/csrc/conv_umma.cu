@@ -413,8 +413,17 @@ struct SkRange {
   }
 };
 
+// SAG_CONV_REG128 (development): declare 512 threads per block to ptxas, which caps the TMA-fed kernels at 128 registers and leaves
+// a quarter of the register file to CTAs of other kernels (batch-norm passes of another lane) on the same SM
+#ifdef SAG_CONV_REG128
+#define SAG_UM_LB(src) ((src) == 3 ? 512 : um_threads(src))
+#define SAG_HL_LB 512
+#else
+#define SAG_UM_LB(src) um_threads(src)
+#define SAG_HL_LB HL_THREADS
+#endif
 template <int BN, int NSPLIT, int SRC, bool PAIR>
-__global__ void __launch_bounds__(um_threads(SRC), 1)
+__global__ void __launch_bounds__(SAG_UM_LB(SRC), 1)
 gather_gemm_umma_kernel(const __grid_constant__ GatherGeom g, const UmmaArgs a, const __grid_constant__ TmaPair tm) {
   constexpr bool VEC = SRC == SRC_F32_VEC;
   constexpr int PLANES = NSPLIT >= 2 ? 2 : 1;
@@ -1397,7 +1406,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, uint32_t s
 // the 2*BN-wide MMA, and each its half of B_hi for the BN-wide one -- so the weight bytes per CTA drop 16 -> 12 KB per tap
 // (BN = 64) and the number of MMA instructions per tile halves.  Copies of both CTAs complete on the leader's barriers.
 template <int BN, bool PAIR>
-__global__ void __launch_bounds__(HL_THREADS, 1) halo_conv_umma_kernel(const HaloArgs a, const __grid_constant__ HaloMaps tm) {
+__global__ void __launch_bounds__(SAG_HL_LB, 1) halo_conv_umma_kernel(const HaloArgs a, const __grid_constant__ HaloMaps tm) {
   static_assert(BN == 64 || BN == 128, "halo kernel: 64- or 128-wide tiles (two accumulators of 2*BN TMEM columns)");
   constexpr int BX_ROWS = BN, BY_ROWS = PAIR ? BN / 2 : BN;   // pair: block X = B_hi | B_lo by rank, block Y = my half of B_hi
   constexpr int B_BYTES = (BX_ROWS + BY_ROWS) * 128;           // alone: [B_hi | B_lo] of one K chunk
@@ -1992,7 +2001,7 @@ int launch_cfg(const GatherGeom& g, const UmmaArgs& a_in, const TmaPair& tm, int
     int optin = 0;
     SAG_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
     SAG_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int b = optin - (int)fa.sharedSizeBytes;
+    const int b = optin - (int)fa.sharedSizeBytes - env_int("SAG_UMMA_SMEM_RESERVE", 0);   // (development: shared memory left to co-resident CTAs of other kernels)
     SAG_REQUIRE(b > 64 * 1024, SAG_ECUDA, "tcgen05 path: only %d bytes of dynamic shared memory available", b);
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     budget[dev & 63] = b;
@@ -2531,7 +2540,7 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
     int optin = 0;
     SAG_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
     SAG_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int b = optin - (int)fa.sharedSizeBytes;
+    const int b = optin - (int)fa.sharedSizeBytes - env_int("SAG_UMMA_SMEM_RESERVE", 0);   // (development: shared memory left to co-resident CTAs of other kernels)
     SAG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     budget[dev & 63] = b;
   }
