@@ -1379,6 +1379,7 @@ struct HaloArgs {
   // exact bf16 plane (uint8 frames as 2k - 255, resnet18_tower): no lo box, no A_lo x B_hi MMA.
   int BRES, A1;
   long long* trace;                   // SAG_HALO_TRACE (debug): per-CTA cycle counters of the three roles
+  int fast_taps;                      // resident weights: all vertical taps of a box issued by one elected block (SAG_HALO_FAST_TAPS, default 1)
   int dbg;                            // SAG_HALO_DEBUG (timing experiments, results invalid): 1 no TMEM loads in the epilogue, 2 no staging / stores
 };
 struct alignas(64) HaloMaps { CUtensorMap hi, lo, o, w; };     // w: tiled map of the packed weights (pairs)
@@ -1560,6 +1561,47 @@ __global__ void __launch_bounds__(SAG_HL_LB, 1) halo_conv_umma_kernel(const Halo
           if (a.trace) tr_wa += clock64() - tw1;
           tc_fence_after();
           const uint32_t slot = a_base + (uint32_t)sa * a_slot;
+          // Resident weights (conv1): nothing to wait for between the vertical taps, so ONE elected block issues their NDY x 4 (x 2)
+          // MMAs back to back with descriptors advanced by addition.  The general loop below spends ~870 clk of scalar work per
+          // tap (elect, descriptor assembly, commits, warp sync) -- more than the 256 clk its four N = 128 MMAs take.
+          if (a.fast_taps && !wait_b && sb + a.NDY <= SB) {
+            if (elect_one()) {
+              uint64_t da_hi = DESC_HI | (uint64_t)((slot & 0x3FFFFu) >> 4);
+              uint64_t da_lo = DESC_HI | (uint64_t)(((slot + a_plane) & 0x3FFFFu) >> 4);
+              uint64_t db = DESC_HI | (uint64_t)(((b_base + (uint32_t)sb * B_BYTES) & 0x3FFFFu) >> 4);
+              uint64_t dby = DESC_HI | (uint64_t)(((b_base + (uint32_t)sb * B_BYTES + BX_ROWS * 128) & 0x3FFFFu) >> 4);
+              const uint64_t step_a = (uint64_t)(((uint32_t)a.TW * 128u) >> 4), step_b = (uint64_t)(B_BYTES >> 4);
+#pragma unroll 1
+              for (int dy = 0; dy < a.NDY; ++dy) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  if (PAIR) {
+                    umma_bf16_2(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));
+                    if (!a.A1) umma_bf16_2(tmem_acc, da_lo + 2 * k4, dby + 2 * k4, IDESC, 1u);
+                  } else {
+                    umma_bf16(tmem_acc, da_hi + 2 * k4, db + 2 * k4, IDESC2, first | (uint32_t)(k4 > 0));
+                    if (!a.A1) umma_bf16(tmem_acc, da_lo + 2 * k4, db + 2 * k4, IDESC, 1u);
+                  }
+                }
+                first = 1u;
+                da_hi += step_a; da_lo += step_a; db += step_b; dby += step_b;
+              }
+              const bool last = dx + 1 == a.NDX && c + 1 == a.CC;
+              if (PAIR) {
+                umma_commit2(bar_aempty + 8 * sa);
+                if (last) umma_commit2(bar_tfull + 8 * b);
+              } else {
+                umma_commit(bar_aempty + 8 * sa);
+                if (last) umma_commit(bar_tfull + 8 * b);
+              }
+            }
+            __syncwarp();
+            first = 1u;
+            sb += a.NDY;
+            if (sb >= SB) { sb -= SB; pb ^= 1; }
+            if (++sa == SA) { sa = 0; pa ^= 1; }
+            continue;
+          }
 #pragma unroll 1
           for (int dy = 0; dy < a.NDY; ++dy) {
             if (wait_b) {                                  // (resident weights: no wait, and no fence between the taps' MMAs)
@@ -2553,6 +2595,8 @@ static int launch_halo(const HaloArgs& a, const HaloMaps& tm, size_t a_slot, cud
   static const int bres_env = env_int("SAG_UMMA_HALO_BRES", 1);
   static const int halo_dbg = env_int("SAG_HALO_DEBUG", 0);
   args.dbg = halo_dbg;
+  static const int fast_taps = env_int("SAG_HALO_FAST_TAPS", 1);
+  args.fast_taps = fast_taps;
   args.BRES = (bres_env && a.NT == 1 && taps <= HL_MAX_SB &&
                (long)fixed + 2 * (long)a_slot + (long)taps * B_BYTES <= (long)budget[dev & 63]) ? 1 : 0;
   if (args.BRES) {
