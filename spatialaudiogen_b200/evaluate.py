@@ -249,7 +249,51 @@ def write_eval_detailed(path, sample_ids, rows):
             f.write('{} | {}\n'.format(sid, ' '.join([str(float(v)) for v in r])))
 
 
+def parse_eval_detailed_file(fn):
+    """parse_eval_results.py:9-30: an eval-detailed.txt back into per-video arrays -- ({video: (n, 28) values}, {video: (n,) times},
+    column names), each video's windows sorted by time."""
+    lines = open(fn).read().splitlines()
+    metrics = lines[0].split(' | ')[1].split()
+    vals, times = OrderedDict(), OrderedDict()
+    for line in lines[1:]:
+        if not line.strip():
+            continue
+        sid, row = line.split(' | ')
+        vid, t = sid.split()
+        times.setdefault(vid, []).append(float(t))
+        vals.setdefault(vid, []).append([float(v) for v in row.split()])
+    for vid in sorted(vals):
+        order = np.argsort(np.asarray(times[vid]), kind='stable')
+        times[vid] = np.asarray(times[vid])[order]
+        vals[vid] = np.asarray(vals[vid])[order]
+    return OrderedDict((v, vals[v]) for v in sorted(vals)), OrderedDict((v, times[v]) for v in sorted(vals)), metrics
+
+
+def parse_eval_results(fn, samples_per_sec=4800):
+    """parse_eval_results.py:32-51, the table the paper reports: per video the mean over its windows of sqrt(mse * 4800),
+    stft, sqrt(env_mse^2 * 4800), sqrt(emd^2 * 4800), then the mean over videos.  Returns OrderedDict MSE / STFT / ENV / EMD;
+    `python -m spatialaudiogen_b200.evaluate <eval-detailed.txt>` prints it like the reference script."""
+    vals, _, keys = parse_eval_detailed_file(fn)
+    out = OrderedDict()
+    for label, mt in (('MSE', 'mse/avg'), ('STFT', 'stft/avg'), ('ENV', 'env_mse/avg'), ('EMD', 'emd/dir')):
+        i = keys.index(mt)
+        if mt in ('emd/dir', 'env_mse/avg'):
+            per_video = [np.sqrt(v[:, i] ** 2 * samples_per_sec).mean() for v in vals.values()]
+        elif mt == 'mse/avg':
+            per_video = [np.sqrt(v[:, i] * samples_per_sec).mean() for v in vals.values()]
+        else:
+            per_video = [v[:, i].mean() for v in vals.values()]
+        out[label] = float(np.mean(per_video))
+    return out
+
+
 def summarize(rows):
     rows = np.asarray(rows.detach().cpu() if isinstance(rows, torch.Tensor) else rows)
     return OrderedDict((k, float(np.nanmean(rows[:, i])) if np.isfinite(rows[:, i]).any() else float('nan'))
                        for k, i in _COL.items())
+
+
+if __name__ == '__main__':                       # python -m spatialaudiogen_b200.evaluate <model_dir>/eval-detailed.txt
+    import sys
+    for _label, _v in parse_eval_results(sys.argv[1]).items():
+        print('{} = {:.3f}'.format(_label.ljust(4), _v))

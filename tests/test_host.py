@@ -270,3 +270,29 @@ def test_prefetch_feeder_thread_keeps_order_and_propagates_errors():
     n = len(seen)
     time.sleep(0.2)
     assert len(seen) == n and n < 20
+
+
+def test_parse_eval_results_matches_the_reference_script(tmp_path):
+    """parse_eval_results.py (the paper's MSE / STFT / ENV / EMD table from eval-detailed.txt): golden = the reference's own script run
+    on the same file (tests/golden/make_parse_eval_golden.py); also run live when /root/reference is present."""
+    import json
+    import subprocess
+    import sys
+    import numpy as np
+    from spatialaudiogen_b200 import evaluate as E
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'parse_eval_results.json')))
+    fn = str(tmp_path / 'eval-detailed.txt')
+    E.write_eval_detailed(fn, g['ids'], np.asarray(g['rows']))
+    vals, times, keys = E.parse_eval_detailed_file(fn)
+    assert keys == E.ALL_METRICS and list(vals) == ['vidA', 'vidB', 'vidC'] and vals['vidA'].shape == (7, 28)
+    assert all(np.all(np.diff(t) > 0) for t in times.values())                       # each video's windows sorted by time
+    table = E.parse_eval_results(fn)
+    mine = ''.join('{} = {:.3f}\n'.format(k.ljust(4), v) for k, v in table.items())
+    assert mine == g['reference_stdout']
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = subprocess.run([sys.executable, '-m', 'spatialaudiogen_b200.evaluate', fn], capture_output=True, text=True, cwd=root)
+    assert cli.returncode == 0 and cli.stdout == g['reference_stdout']
+    ref = '/root/reference/parse_eval_results.py'
+    if os.path.exists(ref):
+        live = subprocess.run([sys.executable, ref, fn], capture_output=True, text=True)
+        assert live.returncode == 0 and live.stdout == mine
