@@ -83,6 +83,32 @@ def img_prep_fcn():
     return lambda x: x / 255. - 0.5
 
 
+def flow_prep_fcn():
+    """reference myutils.py:92-93: `imresize(x, (224, 448), 'nearest')` -- scipy.misc.imresize is PIL's NEAREST resize of the
+    uint8 frame (rows, cols order); frames that already are 224 x 448 pass through unchanged."""
+    def prep(x):
+        from PIL import Image
+        x = np.asarray(x)
+        if x.dtype != np.uint8:
+            raise TypeError('flow_prep_fcn resizes the uint8 frames as decoded (scipy.misc.imresize would rescale other types to bytes)')
+        if x.shape[:2] == (224, 448):
+            return x
+        return np.asarray(Image.fromarray(x).resize((448, 224), Image.NEAREST))
+    return prep
+
+
+def compute_lsd_dist(pred, gt, rate):
+    """reference myutils.py:96-106 (mel log-spectral distance per channel); runs on the GPU (metrics.compute_lsd_dist)."""
+    from . import metrics
+    return metrics.compute_lsd_dist(pred, gt, rate)
+
+
+def compute_envelope_dist(pred, gt):
+    """reference myutils.py:109-116 (Hilbert-envelope distance per channel); runs on the GPU (metrics.compute_envelope_dist)."""
+    from . import metrics
+    return metrics.compute_envelope_dist(pred, gt)
+
+
 # ---- deploy post-processing (reference myutils.gen_360video, myutils.py:224-311): the parts that are arithmetic.
 # Splitting / muxing the streams (ffmpeg) and the spatial-media metadata injection are external tools and stay out.
 def ambix_to_stereo(ambix):

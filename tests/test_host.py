@@ -296,3 +296,20 @@ def test_parse_eval_results_matches_the_reference_script(tmp_path):
     if os.path.exists(ref):
         live = subprocess.run([sys.executable, ref, fn], capture_output=True, text=True)
         assert live.returncode == 0 and live.stdout == mine
+
+
+def test_myutils_prep_functions():
+    """myutils.py:88-93: img_prep_fcn and flow_prep_fcn (nearest-neighbour resize to 224 x 448)."""
+    import numpy as np
+    import pytest
+    from spatialaudiogen_b200 import myutils as M
+    x = np.random.RandomState(0).randint(0, 256, (112, 224, 3)).astype(np.uint8)
+    y = M.flow_prep_fcn()(x)
+    assert y.shape == (224, 448, 3) and y.dtype == np.uint8
+    assert np.array_equal(y[::2, ::2], x) and np.array_equal(y[1::2, 1::2], x)      # every source pixel becomes a 2 x 2 block
+    same = np.zeros((224, 448, 3), np.uint8)
+    assert M.flow_prep_fcn()(same) is same
+    with pytest.raises(TypeError):
+        M.flow_prep_fcn()(x.astype(np.float32))
+    assert np.allclose(M.img_prep_fcn()(np.array([0, 255, 51])), [-0.5, 0.5, -0.3])
+    assert callable(M.compute_lsd_dist) and callable(M.compute_envelope_dist)
