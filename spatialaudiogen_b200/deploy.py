@@ -200,3 +200,45 @@ class W2XYZ(object):
         dt = reader.chunks_t[0] - deploy_start
         reader.chunks_t = [t - dt for t in reader.chunks_t]
         return self.deploy_stream(reader.loop_chunks())
+
+
+def parse_arguments(argv=None):
+    """deploy.py:14-38 -- the same positional and optional arguments (the video / overlay outputs need ffmpeg and the
+    spatial-media injector, which stay external: they are accepted and reported as skipped)."""
+    import argparse
+    import sys
+    parser = argparse.ArgumentParser(description='Generate first-order ambisonics for a clip (reference deploy.py).')
+    parser.add_argument('model_dir', help='Directory containing model snapshot.')
+    parser.add_argument('input_folder', default='', help='Folder with input sample.')
+    parser.add_argument('video', default='', nargs='?', help='High resolution video (only used by the video outputs).')
+    parser.add_argument('--deploy_start', default=0., type=float)
+    parser.add_argument('--deploy_duration', default=10., type=float)
+    parser.add_argument('--output_fn', default='output', help='Basename for output files.')
+    parser.add_argument('--save_ambix', action='store_true', help='Output ambix video file.')
+    parser.add_argument('--save_video', action='store_true', help='Output video file.')
+    parser.add_argument('--overlay_map', action='store_true', help='Overlay spherical map.')
+    parser.add_argument('--VR', action='store_true', help='360 video.')
+    parser.add_argument('--gpu', type=int, default=0, help='GPU id')
+    args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+    if args.deploy_duration <= 0:
+        args.deploy_duration = None                                                # deploy.py:35-36: the whole clip
+    return args
+
+
+def main(args):
+    """deploy.py:155-215 up to the ambisonics: model restored from `model_dir`, windows of `input_folder` generated, the
+    (N, 4) [W, Y, Z, X] track written as `<output_fn>.wav` and its stereo down-mix as `<output_fn>-stereo.wav`."""
+    import sys
+    with torch.cuda.device(args.gpu):
+        model = W2XYZ(args.model_dir)
+        ambi_pred = model.deploy(args.input_folder, args.deploy_start, args.deploy_duration)
+    readers.save_wav(args.output_fn + '.wav', ambi_pred, model.params.audio_rate)
+    readers.save_wav(args.output_fn + '-stereo.wav', myutils.ambix_to_stereo(ambi_pred), model.params.audio_rate)
+    if args.save_ambix or args.save_video or args.overlay_map:
+        sys.stderr.write('video outputs (ffmpeg mux, spatial-media metadata, heat-map overlay) are not produced by this package: '
+                         'see myutils.energy_map_frames for the overlay frames\n')
+    return ambi_pred
+
+
+if __name__ == '__main__':                       # python -m spatialaudiogen_b200.deploy MODEL_DIR INPUT_FOLDER [VIDEO] ...
+    main(parse_arguments())

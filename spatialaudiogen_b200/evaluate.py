@@ -293,7 +293,31 @@ def summarize(rows):
                        for k, i in _COL.items())
 
 
-if __name__ == '__main__':                       # python -m spatialaudiogen_b200.evaluate <model_dir>/eval-detailed.txt
+def parse_arguments(argv=None):
+    """eval.py:14-26 -- the same arguments."""
+    import argparse
     import sys
-    for _label, _v in parse_eval_results(sys.argv[1]).items():
-        print('{} = {:.3f}'.format(_label.ljust(4), _v))
+    parser = argparse.ArgumentParser(description='Evaluate a model snapshot (reference eval.py), or print the table of an eval-detailed.txt.')
+    parser.add_argument('model_dir', help='Directory to store model -- or an eval-detailed.txt to summarise (parse_eval_results.py).')
+    parser.add_argument('--subset_fn', default='')
+    parser.add_argument('--batch_size', default=16, type=int)
+    parser.add_argument('--overwrite', action='store_true')
+    parser.add_argument('--gpu', type=int, default=0, help='GPU id')
+    args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+    if len(args.subset_fn) == 0:
+        args.subset_fn = None
+    return args
+
+
+def main(args):
+    import os
+    if os.path.isfile(args.model_dir):           # parse_eval_results.py
+        for label, v in parse_eval_results(args.model_dir).items():
+            print('{} = {:.3f}'.format(label.ljust(4), v))
+        return
+    with torch.cuda.device(args.gpu):            # eval.py:29-215
+        evaluate_model_dir(args.model_dir, subset_fn=args.subset_fn, overwrite=args.overwrite, batch_size=args.batch_size)
+
+
+if __name__ == '__main__':                       # python -m spatialaudiogen_b200.evaluate MODEL_DIR [--subset_fn ...]  |  <eval-detailed.txt>
+    main(parse_arguments())

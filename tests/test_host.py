@@ -313,3 +313,15 @@ def test_myutils_prep_functions():
         M.flow_prep_fcn()(x.astype(np.float32))
     assert np.allclose(M.img_prep_fcn()(np.array([0, 255, 51])), [-0.5, 0.5, -0.3])
     assert callable(M.compute_lsd_dist) and callable(M.compute_envelope_dist)
+
+
+def test_command_lines_mirror_the_reference_arguments():
+    """deploy.py:14-38 and eval.py:14-26: same arguments, same post-processing of them."""
+    from spatialaudiogen_b200 import deploy as D, evaluate as E
+    a = D.parse_arguments(['snap', 'data/frames/vid', 'vid.mp4', '--deploy_start', '3.5', '--deploy_duration', '0', '--output_fn', 'out/x', '--VR'])
+    assert (a.model_dir, a.input_folder, a.video, a.deploy_start, a.deploy_duration, a.output_fn, a.VR, a.gpu) == \
+        ('snap', 'data/frames/vid', 'vid.mp4', 3.5, None, 'out/x', True, 0)
+    assert D.parse_arguments(['snap', 'folder']).deploy_duration == 10.
+    e = E.parse_arguments(['snap', '--batch_size', '8', '--overwrite'])
+    assert (e.model_dir, e.subset_fn, e.batch_size, e.overwrite, e.gpu) == ('snap', None, 8, True, 0)
+    assert E.parse_arguments(['snap', '--subset_fn', 'meta/subsets/YT-All.test.1.lst']).subset_fn == 'meta/subsets/YT-All.test.1.lst'
