@@ -208,3 +208,30 @@ def test_resnet_known_answer_fixture():
     x = (x - torch.tensor([0.485, 0.456, 0.406])) / torch.tensor([0.229, 0.224, 0.225])
     logits, _ = O.resnet18(O.Weights(pre), '', x[None], bn_train=False, truncate_at=None)
     assert torch.argsort(-logits[0])[:5].tolist() == fx['tiger.jpeg']['top5']
+
+
+def test_mel_lsd_oracle_against_an_independent_librosa_compatible_implementation():
+    """myutils.compute_lsd_dist calls librosa.feature.melspectrogram (librosa 0.6.0, absent here).  The oracle's restatement
+    (Slaney mel filter bank, centred reflect-padded periodic-Hann power spectrogram) is cross-checked against the independent
+    librosa-compatible implementation that ships with `transformers` (audio_utils.mel_filter_bank(norm='slaney',
+    mel_scale='slaney') + audio_utils.spectrogram): filter bank to 1e-12, distances to 1e-6."""
+    au = pytest.importorskip('transformers.audio_utils')
+    sr, n_fft = 48000, 2048
+    mine = O._mel_filter_bank(sr, n_fft, 128, 0.0, 12000.0)
+    theirs = au.mel_filter_bank(1 + n_fft // 2, 128, 0.0, 12000.0, sr, norm='slaney', mel_scale='slaney')
+    assert theirs.shape == (1025, 128) and np.abs(mine - theirs.T).max() < 1e-12 and mine.max() > 1e-3
+    rng = np.random.RandomState(0)
+    y = 0.1 * rng.randn(4800) + 0.3 * np.sin(2 * np.pi * 440 * np.arange(4800) / sr)
+    pred = np.stack([y, 0.9 * y, y + 0.01 * rng.randn(4800)], 1)
+    gt = np.stack([1.1 * y, y, y], 1)
+    win = au.window_function(n_fft, 'hann', periodic=True)
+
+    def mel(v):
+        return au.spectrogram(v.astype(np.float64), win, n_fft, 512, fft_length=n_fft, power=2.0, center=True, pad_mode='reflect',
+                              mel_filters=theirs, mel_floor=0.0, dtype=np.float64)
+
+    def ps(x):
+        return 10 * np.log(np.abs(x) + 1e-2) / np.log(10.)
+
+    ref = np.array([np.sqrt(np.mean((ps(mel(gt[:, i])) - ps(mel(pred[:, i]))) ** 2)) for i in range(3)])
+    assert np.abs(O.compute_lsd_dist(pred, gt, sr) - ref).max() < 1e-6
