@@ -141,6 +141,7 @@ int parse_header(const uint8_t* d, size_t n, Header* h) {
       }
       h->ecs = d + p;
       h->ecs_size = n - p;
+      SAG_REQUIRE(h->ecs_size < ((size_t)1 << 27), SAG_EUNSUPPORTED, "jpeg: scans of 128 MB or more are not supported (32-bit bit positions)");
       break;
     }
   }
@@ -846,8 +847,8 @@ int sag_jpeg_coefficients(const void* host_file, size_t size, int16_t* host_coef
 }
 
 int sag_jpeg_create(sag_jpeg** out, int max_frames, int height, int width) {
-  SAG_REQUIRE(out != nullptr && max_frames > 0 && height > 0 && width > 0 && height < 65536 && width < 65536, SAG_EINVAL,
-              "jpeg: bad decoder geometry");
+  SAG_REQUIRE(out != nullptr && max_frames > 0 && max_frames < 65536 && height > 0 && width > 0 && height < 65536 && width < 65536,
+              SAG_EINVAL, "jpeg: bad decoder geometry (frames, height and width must be in [1, 65535])");
   sag_jpeg* d = new sag_jpeg();
   d->max_frames = max_frames;
   d->height = height;
