@@ -253,14 +253,17 @@ def upsample(plane, h, v, hmax, vmax, width, height):
     p = plane[:dh, :dw].astype(np.int64)
     if h == hmax and v == vmax:
         return p[:height, :width].astype(np.uint8)
+    if hmax == 2 * h and dw <= 2:                                # jinit_upsampler: fancy only if downsampled_width > 2, else replication
+        rep = np.repeat(p, 2, axis=1)
+        if vmax == 2 * v:
+            rep = np.repeat(rep, 2, axis=0)
+        elif v != vmax:
+            raise ValueError('sampling %dx%d of %dx%d is not supported' % (h, v, hmax, vmax))
+        return rep[:height, :width].astype(np.uint8)
     if hmax == 2 * h and v == vmax:                              # h2v1_fancy_upsample
-        if dw < 2:
-            raise ValueError('image too narrow for the fancy upsampler')
         out = _h2_fancy(p, 1, 2, 2, 0)
         return out[:height, :width].astype(np.uint8)
     if hmax == 2 * h and vmax == 2 * v:                          # h2v2_fancy_upsample
-        if dw < 2:
-            raise ValueError('image too narrow for the fancy upsampler')
         above = np.concatenate((p[:1], p[:-1]), 0)               # jdmainct.c replicates the first / last real row
         below = np.concatenate((p[1:], p[-1:]), 0)
         out = np.empty((2 * dh, 2 * dw), np.int64)

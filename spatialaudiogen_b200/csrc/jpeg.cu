@@ -156,7 +156,6 @@ int parse_header(const uint8_t* d, size_t n, Header* h) {
     SAG_REQUIRE(ok && h->comp[i].h <= 2 && h->comp[i].v <= 2, SAG_EUNSUPPORTED,
                 "jpeg: component %d sampled %dx%d of %dx%d (supported: full, 2:1 horizontal, 2:1 both)", i, h->comp[i].h, h->comp[i].v,
                 h->hmax, h->vmax);
-    if (rh == 2) SAG_REQUIRE((h->width * h->comp[i].h + h->hmax - 1) / h->hmax >= 2, SAG_EUNSUPPORTED, "jpeg: image too narrow");
   }
   h->mcux = (h->width + 8 * h->hmax - 1) / (8 * h->hmax);
   h->mcuy = (h->height + 8 * h->vmax - 1) / (8 * h->vmax);
@@ -360,6 +359,8 @@ __device__ __forceinline__ int jpeg_sample(const JpegImage& im, const uint8_t* _
   if (rh == 1) return p[(long long)y * stride + x];
   const int dw = (width * im.h[c] + im.hmax - 1) / im.hmax;     // downsampled_width: the real samples of a row
   const int cx = x >> 1;
+  // components at most two samples wide are replicated, not filtered (jdsample.c jinit_upsampler: fancy only if downsampled_width > 2)
+  if (dw <= 2) return p[(long long)(rv == 1 ? y : (y >> 1)) * stride + cx];
   if (rv == 1) {                                                // h2v1_fancy_upsample
     const uint8_t* r = p + (long long)y * stride;
     const int s = r[cx];
@@ -903,9 +904,13 @@ void sag_jpeg_destroy(sag_jpeg* d) {
 }
 
 int sag_jpeg_set_option(sag_jpeg* d, const char* key, int value) {
-  SAG_REQUIRE(d != nullptr && key != nullptr, SAG_EINVAL, "jpeg: null argument");
-  if (strcmp(key, "device_huffman") == 0) { d->device_huffman = value != 0; return SAG_OK; }
-  if (strcmp(key, "sub_bytes") == 0) {                    // (process wide) shortest subsequence of the device entropy decoder
+  SAG_REQUIRE(key != nullptr, SAG_EINVAL, "jpeg: null argument");
+  if (strcmp(key, "device_huffman") == 0) {
+    SAG_REQUIRE(d != nullptr, SAG_EINVAL, "jpeg: device_huffman is an option of a decoder");
+    d->device_huffman = value != 0;
+    return SAG_OK;
+  }
+  if (strcmp(key, "sub_bytes") == 0) {                    // (process wide; dec may be NULL) shortest subsequence of the device entropy decoder
     SAG_REQUIRE(value >= 32 && value <= 65536, SAG_EINVAL, "jpeg: sub_bytes must be in [32, 65536]");
     g_min_sub_bytes = value;
     return SAG_OK;

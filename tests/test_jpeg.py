@@ -45,7 +45,11 @@ def _cases():
            ('one MCU', _jpeg(_picture(16, 16, 6), quality=30, subsampling=2)),
            ('grey', _jpeg(_picture(40, 56, 7)[:, :, 0], quality=80)),
            ('noise q100', _jpeg(np.random.RandomState(8).randint(0, 256, (48, 64, 3)).astype(np.uint8), quality=100, subsampling=2)),
-           ('optimised tables', _jpeg(_picture(56, 72, 9), quality=70, subsampling=2, optimize=True))]
+           ('optimised tables', _jpeg(_picture(56, 72, 9), quality=70, subsampling=2, optimize=True)),
+           # components at most two samples wide are replicated, not filtered (jdsample.c jinit_upsampler)
+           ('narrow 4:2:0 40x3', _jpeg(_picture(40, 3, 11), quality=80, subsampling=2)),
+           ('narrow 4:2:2 9x4', _jpeg(_picture(9, 4, 12), quality=60, subsampling=1)),
+           ('one column 4:2:0 17x1', _jpeg(_picture(17, 1, 13), quality=90, subsampling=2))]
     try:                                               # restart intervals (Pillow >= 10.2 writes DRI on request)
         d = _jpeg(_picture(64, 96, 10), quality=80, subsampling=2, restart_marker_blocks=3)
         if b'\xff\xdd' in d:
@@ -103,6 +107,44 @@ def test_parallel_entropy_decoder_emulated_on_the_host(name, data):
         L.check(L.lib().sag_jpeg_coefficients_parallel(data, len(data), nthreads, out.ctypes.data, out.size, C.byref(rounds)))
         assert np.array_equal(out[:n], ref[:n]), nthreads
         assert 1 <= rounds.value <= 2050
+
+
+def test_parallel_entropy_decoder_fuzz_with_short_subsequences():
+    """Random files (sizes 1..120 x 1..160, every sampling, qualities 1..100, grey, optimised tables, restart intervals) through the
+    emulated device decoder with the shortest allowed subsequences (32 bytes: many subsequences, many synchronisation rounds,
+    symbols that straddle two of them) and with 64 / 256 bytes, for CTA sizes 1, 5 and 64 -- always the serial decoder's output."""
+    lib = L.lib()
+    rng = np.random.RandomState(3)
+    try:
+        for it in range(60):
+            h, w = int(rng.randint(1, 121)), int(rng.randint(1, 161))
+            if it % 3 == 0:
+                img = rng.randint(0, 256, (h, w, 3))
+            else:
+                img = np.kron(rng.randint(0, 256, ((h + 5) // 6, (w + 5) // 6, 3)), np.ones((6, 6, 1)))[:h, :w] + rng.randn(h, w, 3) * rng.uniform(0, 30)
+            img = np.clip(img, 0, 255).astype(np.uint8)
+            kw = dict(quality=int(rng.choice([1, 10, 50, 75, 90, 100])))
+            grey = it % 7 == 0
+            if not grey:
+                kw['subsampling'] = int(rng.randint(3))
+            if it % 4 == 1:
+                kw['optimize'] = True
+            if it % 5 == 2:
+                kw['restart_marker_blocks'] = int(rng.randint(1, 9))
+            try:
+                data = _jpeg(img[:, :, 0] if grey else img, **kw)
+            except (TypeError, OSError):                 # (restart markers need Pillow >= 10.2; a rare encoder failure on tiny images)
+                continue
+            hdr, ref, bw, bh, _ = _native_coefficients(data)
+            n = sum(bw[c] * bh[c] * 64 for c in range(3))
+            for sub in (32, 64, 256):
+                L.check(lib.sag_jpeg_set_option(None, b'sub_bytes', sub))
+                for nthreads in (1, 5, 64):
+                    out = np.full(ref.size, -7, np.int16)
+                    L.check(lib.sag_jpeg_coefficients_parallel(data, len(data), nthreads, out.ctypes.data, out.size, None))
+                    assert np.array_equal(out[:n], ref[:n]), (it, h, w, kw, sub, nthreads)
+    finally:
+        L.check(lib.sag_jpeg_set_option(None, b'sub_bytes', 256))
 
 
 def test_unsupported_and_broken_files_fail_loudly():

@@ -99,7 +99,8 @@ def _picture(h, w, seed):
     return np.clip(img + rng.randn(h, w, 3) * 12, 0, 255).astype(np.uint8)
 
 
-CASES = [(64, 80, 2, 90), (37, 53, 2, 60), (41, 67, 1, 95), (33, 49, 0, 75), (16, 16, 2, 30), (48, 64, 2, 100), (40, 56, None, 80)]
+CASES = [(64, 80, 2, 90), (37, 53, 2, 60), (41, 67, 1, 95), (33, 49, 0, 75), (16, 16, 2, 30), (48, 64, 2, 100), (40, 56, None, 80),
+         (40, 3, 2, 80), (9, 4, 1, 60), (17, 1, 2, 90), (5, 2, 2, 50)]          # narrow: replicated chroma (jinit_upsampler)
 
 
 @pytest.mark.parametrize('h,w,ss,q', CASES)
