@@ -33,6 +33,7 @@ def parse(data):
     if d[:2] != b'\xff\xd8':
         raise ValueError('not a JPEG file (no SOI)')
     out = {'qt': {}, 'huff': {}, 'restart_interval': 0}
+    jfif, adobe = False, None
     p = 2
     while True:
         while d[p] != 0xFF:
@@ -76,6 +77,10 @@ def parse(data):
                 ns = sum(counts)
                 out['huff'][(cls, tid)] = (counts, list(seg[q + 17:q + 17 + ns]))
                 q += 17 + ns
+        elif m == 0xE0 and seg[:5] == b'JFIF\0':
+            jfif = True
+        elif m == 0xEE and seg[:5] == b'Adobe' and len(seg) >= 12:
+            adobe = seg[11]
         elif m == 0xDD:
             out['restart_interval'] = (seg[0] << 8) | seg[1]
         elif m == 0xDA:
@@ -84,6 +89,9 @@ def parse(data):
             out['scan'] = [(ids.index(seg[1 + 2 * i]), seg[2 + 2 * i] >> 4, seg[2 + 2 * i] & 15) for i in range(ns)]
             if ns != len(out['comps']):
                 raise ValueError('only one interleaved scan with all components is supported')
+            # jdapimin.c default_decompress_parms: without a JFIF marker, Adobe transform 0 or component ids R, G, B mean RGB samples
+            if len(ids) == 3 and not jfif and (adobe == 0 or (adobe is None and ids == [82, 71, 66])):
+                raise ValueError('the file stores RGB samples: only YCbCr and grey files are supported')
             out['ecs'] = d[p:]
             return out
 

@@ -71,7 +71,8 @@ int build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int
 int parse_header(const uint8_t* d, size_t n, Header* h) {
   SAG_REQUIRE(n >= 4 && d[0] == 0xFF && d[1] == 0xD8, SAG_EINVAL, "jpeg: not a JPEG file (no SOI marker)");
   size_t p = 2;
-  bool have_sof = false;
+  bool have_sof = false, saw_jfif = false;
+  int adobe_transform = -1;                  // APP14 "Adobe": 0 = components are RGB / CMYK as they are, 1 = YCbCr, 2 = YCCK
   for (;;) {
     while (p < n && d[p] != 0xFF) ++p;
     while (p < n && d[p] == 0xFF) ++p;
@@ -124,6 +125,10 @@ int parse_header(const uint8_t* d, size_t n, Header* h) {
                     "jpeg: inconsistent Huffman table");
         q += 17 + ns;
       }
+    } else if (m == 0xE0) {
+      if (sl >= 5 && memcmp(s, "JFIF", 5) == 0) saw_jfif = true;
+    } else if (m == 0xEE) {
+      if (sl >= 12 && memcmp(s, "Adobe", 5) == 0) adobe_transform = s[11];
     } else if (m == 0xDD) {
       SAG_REQUIRE(sl >= 2, SAG_EINVAL, "jpeg: bad DRI segment");
       h->restart_interval = (s[0] << 8) | s[1];
@@ -146,6 +151,13 @@ int parse_header(const uint8_t* d, size_t n, Header* h) {
     }
   }
   SAG_REQUIRE(h->width > 0 && h->height > 0, SAG_EINVAL, "jpeg: empty image");
+  // colour space as libjpeg guesses it (jdapimin.c default_decompress_parms): three components are YCbCr unless an Adobe marker
+  // says "no transform" or, without JFIF / Adobe markers, the component ids spell R, G, B -- those files hold RGB samples
+  if (h->ncomp == 3 && !saw_jfif) {
+    const bool rgb_ids = h->comp[0].id == 'R' && h->comp[1].id == 'G' && h->comp[2].id == 'B';
+    SAG_REQUIRE(!(adobe_transform == 0 || (adobe_transform < 0 && rgb_ids)), SAG_EUNSUPPORTED,
+                "jpeg: the file stores RGB samples (Adobe transform 0 / component ids R, G, B): only YCbCr and grey files are supported");
+  }
   if (h->ncomp == 1) h->comp[0].h = h->comp[0].v = 1;          // a one-component scan is never interleaved: MCU = one block
   h->hmax = h->vmax = 1;
   for (int i = 0; i < h->ncomp; ++i) { h->hmax = std::max(h->hmax, h->comp[i].h); h->vmax = std::max(h->vmax, h->comp[i].v); }

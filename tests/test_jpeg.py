@@ -156,6 +156,19 @@ def test_unsupported_and_broken_files_fail_loudly():
     with pytest.raises(ValueError):
         J.decode(prog)
     good = CASES[2][1]
+    # an Adobe APP14 segment with transform 0 in place of the JFIF header: libjpeg takes the three components as RGB
+    assert good[2:4] == b'\xff\xe0' and good[6:11] == b'JFIF\0'
+    n0 = (good[4] << 8) | good[5]
+    adobe = good[:2] + b'\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00\x00' + good[4 + n0:]
+    assert not np.array_equal(_pil(adobe), _pil(good))                                # (PIL indeed skips the colour conversion)
+    with pytest.raises(L.SagError) as e:
+        L.check(lib.sag_jpeg_info(adobe, len(adobe), None, None, None, None, None))
+    assert e.value.code == L.SAG_EUNSUPPORTED and 'RGB' in str(e.value)
+    with pytest.raises(ValueError):
+        J.decode(adobe)
+    ycc = adobe[:17] + b'\x01' + adobe[18:]                                            # transform 1: YCbCr, decodes like the JFIF file
+    L.check(lib.sag_jpeg_info(ycc, len(ycc), None, None, None, None, None))
+    assert np.array_equal(_pil(ycc), _pil(good)) and np.array_equal(J.decode(ycc), _pil(good))
     with pytest.raises(ValueError):
         L.check(lib.sag_jpeg_info(b'not a jpeg', 10, None, None, None, None, None))
     with pytest.raises(ValueError):                                                  # the file ends inside its tables
