@@ -17,8 +17,9 @@ subsamplings / sizes, and of the reference's own photographs (pyutils/tflib/mode
 tests/golden/_ref/ by build()).
 
 Scope: baseline sequential (SOF0), 8 bit, 1 or 3 components in one interleaved scan, sampling 4:4:4 / 4:2:2 / 4:2:0,
-restart intervals.  Progressive files raise ValueError (the reference's frames are written by ffmpeg's mjpeg encoder:
-baseline 4:2:0, scraping/preprocess.py:98-153)."""
+restart intervals.  Progressive files raise ValueError (the reference's frames are written by skimage.io.imsave, i.e. PIL's
+encoder with its defaults -- baseline, 4:2:0, quality 75 -- scraping/preprocess.py:141-143 and :198: the same encoder the tests
+write their files with)."""
 import numpy as np
 
 ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,

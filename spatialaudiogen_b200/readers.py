@@ -74,7 +74,8 @@ class JpegDecoder(object):
     """Batches of jpg files -> uint8 RGB frames on the GPU: what `scipy.misc.imread` does per frame in the reference's feeder
     (feeder.py:120-127), bit-identical to PIL / libjpeg (islow inverse DCT, fancy upsampling).  libsag.so decodes the entropy-coded
     segments with a pool of host threads and runs the rest as CUDA kernels on the current stream (include/sag.h sag_jpeg_*).
-    Baseline sequential files only (what ffmpeg's mjpeg encoder and PIL write by default); others raise."""
+    Baseline sequential YCbCr / grey files only -- what the reference's preprocessing writes (skimage.io.imsave = PIL's encoder with its
+    defaults: baseline, 4:2:0, quality 75; scraping/preprocess.py:141-143, 198); others raise."""
 
     def __init__(self, max_frames, height, width, device=None, threads=0, device_huffman=True):
         """device_huffman: decode the entropy-coded segments on the GPU too (parallel, self-synchronising subsequences: only the
