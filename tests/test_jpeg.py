@@ -36,7 +36,8 @@ def _pil(data):
 
 
 def _cases():
-    out = [('frame 4:2:0 q90', _jpeg(_picture(224, 448), quality=90, subsampling=2)),
+    out = [('dataset frame (PIL defaults, as skimage.io.imsave writes them: scraping/preprocess.py:141-143)', _jpeg(_picture(224, 448, 14))),
+           ('frame 4:2:0 q90', _jpeg(_picture(224, 448), quality=90, subsampling=2)),
            ('frame 4:4:4 q75', _jpeg(_picture(224, 448, 1), quality=75, subsampling=0)),
            ('4:2:2 64x80', _jpeg(_picture(64, 80, 2), quality=50, subsampling=1)),
            ('4:2:0 odd 37x53', _jpeg(_picture(37, 53, 3), quality=85, subsampling=2)),
