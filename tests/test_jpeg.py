@@ -156,7 +156,7 @@ def test_unsupported_and_broken_files_fail_loudly():
     assert e.value.code == L.SAG_EUNSUPPORTED and 'baseline' in str(e.value)
     with pytest.raises(ValueError):
         J.decode(prog)
-    good = CASES[2][1]
+    good = dict(CASES)['4:2:2 64x80']
     # an Adobe APP14 segment with transform 0 in place of the JFIF header: libjpeg takes the three components as RGB
     assert good[2:4] == b'\xff\xe0' and good[6:11] == b'JFIF\0'
     n0 = (good[4] << 8) | good[5]
