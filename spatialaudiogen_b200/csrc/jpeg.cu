@@ -54,6 +54,7 @@ int build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int
   int code = 0, k = 0;
   for (int len = 1; len <= 16; ++len) {
     t.valoffset[len] = k - code;
+    if (code + counts[len - 1] > (1 << len) || k + counts[len - 1] > nsym) return SAG_EINVAL;   // more codes than the length has / symbols than listed
     for (int i = 0; i < counts[len - 1]; ++i, ++code, ++k) {
       if (len <= 9) {
         const int lo = code << (9 - len);
@@ -169,6 +170,9 @@ int parse_header(const uint8_t* d, size_t n, Header* h) {
                 "jpeg: component %d sampled %dx%d of %dx%d (supported: full, 2:1 horizontal, 2:1 both)", i, h->comp[i].h, h->comp[i].v,
                 h->hmax, h->vmax);
   }
+  int blocks_per_mcu = 0;
+  for (int i = 0; i < h->ncomp; ++i) blocks_per_mcu += h->comp[i].h * h->comp[i].v;
+  SAG_REQUIRE(blocks_per_mcu <= 10, SAG_EINVAL, "jpeg: %d blocks per MCU (the standard allows 10)", blocks_per_mcu);
   h->mcux = (h->width + 8 * h->hmax - 1) / (8 * h->hmax);
   h->mcuy = (h->height + 8 * h->vmax - 1) / (8 * h->vmax);
   for (int i = 0; i < h->ncomp; ++i) { h->bw[i] = h->mcux * h->comp[i].h; h->bh[i] = h->mcuy * h->comp[i].v; }
@@ -453,8 +457,8 @@ struct JpegStream {           // the scan of one frame
   long long data_off;         // byte offset of the unstuffed stream in the batch's buffer (padded with 16 zero bytes)
   int sub0, n_subs;           // its rows of the batch's JpegSub table
   int bpm;                    // blocks per MCU
-  unsigned comp_nib;          // component of block i of an MCU in bits 4i..4i+3 (what the decode loop reads)
-  int blk_comp[6], blk_x[6], blk_y[6];
+  unsigned comp_nib;          // component of block i of an MCU in bits 2i, 2i+1 (what the decode loop reads)
+  int blk_comp[10], blk_x[10], blk_y[10];   // (at most 10 blocks per MCU: the standard's limit, checked by parse_header)
   int mcux, n_mcus;
   int restart_mcus;           // MCUs per restart segment (0: one segment)
   int dc_tab[3], ac_tab[3];   // rows of the batch's table array
@@ -531,7 +535,7 @@ __host__ __device__ inline int decode_span(const uint8_t* s, const HuffView& hv,
   if (WRITE && q < q_end) blk = block_ptr(js, *im, coef, q);
   while (p < end_bit) {
     if (WRITE && q >= q_end) break;                     // only padding bits are left in this restart segment
-    const int c = (int)((nib >> (4 * b)) & 15u);
+    const int c = (int)((nib >> (2 * b)) & 3u);
     const uint32_t w = bw.peek32(p);
     // one path for DC and AC symbols (threads of a warp sit at different places of their blocks): a DC symbol is its size
     // (<= 11, so its "run" nibble is 0), an AC symbol (run << 4) | size
@@ -753,7 +757,7 @@ void plan_stream(const Header& h, const std::vector<int>& seg_start, int stream_
     for (int y = 0; y < h.comp[c].v; ++y)
       for (int x = 0; x < h.comp[c].h; ++x) {
         js->blk_comp[js->bpm] = c; js->blk_x[js->bpm] = x; js->blk_y[js->bpm] = y;
-        js->comp_nib |= (unsigned)c << (4 * js->bpm);
+        js->comp_nib |= (unsigned)c << (2 * js->bpm);
         ++js->bpm;
       }
   js->mcux = h.mcux;

@@ -148,6 +148,42 @@ def test_parallel_entropy_decoder_fuzz_with_short_subsequences():
         L.check(lib.sag_jpeg_set_option(None, b'sub_bytes', 256))
 
 
+def test_corrupted_files_are_rejected_or_decoded_without_touching_foreign_memory():
+    """Random byte flips and truncations of valid files (headers, tables, scan data) through the marker parser, the serial decoder and
+    the emulated device decoder: every call returns 0 or an error code, and the canary behind the caller's buffer survives.  (The
+    same loop ran 150 000 files under AddressSanitizer: profiles/r2_jpeg_fuzz.txt -- it found a Huffman table with more codes than
+    its length allows overflowing the lookahead table, and sampling factors giving more than 10 blocks per MCU.)"""
+    lib = L.lib()
+    rng = np.random.RandomState(11)
+    bases = [c[1] for c in CASES if c[0] in ('4:2:2 64x80', '4:2:0 odd 37x53', '4:4:4 odd 33x49', 'restart interval 3', 'grey')]
+    codes = {0, L.SAG_EINVAL, L.SAG_EUNSUPPORTED, L.SAG_ENOMEM}
+    decoded = 0
+    for it in range(3000):
+        d = bytearray(bases[it % len(bases)])
+        for _ in range(int(rng.randint(1, 4))):
+            pos = int(rng.randint(2, min(len(d), 700))) if it % 4 == 0 else int(rng.randint(2, len(d)))
+            if it % 4 == 3 and rng.rand() < 0.5:
+                d = d[:pos]
+                break
+            d[pos] = int(rng.randint(256))
+        d = bytes(d)
+        v = [C.c_int() for _ in range(5)]
+        rc = lib.sag_jpeg_info(d, len(d), *[C.byref(x) for x in v])
+        assert rc in codes
+        if rc != 0 or v[0].value * v[1].value > 1 << 20:
+            continue
+        cap = 3 * ((v[1].value + 15) // 16 * 16) * ((v[0].value + 15) // 16 * 16)
+        for parallel in (False, True):
+            out = np.full(cap + 64, 12345, np.int16)
+            if parallel:
+                rc = lib.sag_jpeg_coefficients_parallel(d, len(d), int(rng.choice([1, 7, 64])), out.ctypes.data, cap, None)
+            else:
+                rc = lib.sag_jpeg_coefficients(d, len(d), out.ctypes.data, cap, None, None, None)
+            assert rc in codes and np.all(out[cap:] == 12345)
+            decoded += rc == 0
+    assert decoded > 1000
+
+
 def test_unsupported_and_broken_files_fail_loudly():
     lib = L.lib()
     prog = _jpeg(_picture(32, 32), quality=80, progressive=True)
